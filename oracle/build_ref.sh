@@ -1,0 +1,52 @@
+#!/bin/bash
+# oracle/build_ref.sh -- TEST INFRASTRUCTURE, not product code.
+#
+# Builds the reference's own C implementation of the hot path from the sources
+# where they lie under /root/reference into shared libraries under oracle/_ref/
+# (git-ignored; they travel to the GPU box with the snapshot).  Nothing from
+# /root/reference is copied into the repository: scratch files live in a
+# mktemp directory that is removed on exit.
+#
+#   _ref/libquisk_filter_ref.so  filter.c, verbatim (all 17 filter.h functions + filters.h tables)
+#   _ref/libquisk_rx_ref.so      filter.c + the static RX functions of quisk.c (see ref_wrap/quisk_rx_wrap.c)
+#   _ref/libwdsp_ref.so          wdsp/*.c (minus the make_*.c table generators) + our FFTW-API shim
+#
+# Flags: -O2 for the Quisk sources (setuptools default), -O3 for WDSP
+# (wdsp/Makefile:9); never -ffast-math.
+set -euo pipefail
+REF=${QUISK_REFERENCE:-/root/reference}
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/_ref"
+if [ ! -d "$REF" ]; then
+    echo "build_ref: $REF not present; keeping prebuilt files in $OUT" >&2
+    exit 0
+fi
+PYINC=$(python3 -c 'import sysconfig; print(sysconfig.get_paths()["include"])')
+if [ ! -f "$PYINC/Python.h" ]; then PYINC=/usr/include/python3.12; fi
+mkdir -p "$OUT"
+TMP=$(mktemp -d)
+trap 'rm -rf "$TMP"' EXIT
+
+# 1. filter.c verbatim
+gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" "$REF/filter.c" -o "$OUT/libquisk_filter_ref.so" -lm
+
+# 2. quisk.c RX functions through the wrapper TU
+{ sed -n '46,53p' "$REF/quisk.c"; sed -n '68,81p' "$REF/quisk.c"; } > "$TMP/quisk_rx_consts.inc"
+{ sed -n '622,665p' "$REF/quisk.c"; sed -n '1182,1256p' "$REF/quisk.c"; sed -n '1633,1671p' "$REF/quisk.c";
+  sed -n '1673,1846p' "$REF/quisk.c"; sed -n '1848,2160p' "$REF/quisk.c"; sed -n '2162,2287p' "$REF/quisk.c"; } > "$TMP/quisk_rx_funcs.inc"
+gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_rx_wrap.c" "$REF/filter.c" \
+    -o "$OUT/libquisk_rx_ref.so" -lm
+
+# 3. WDSP against the FFTW shim
+WSRC=$(ls "$REF"/wdsp/*.c | grep -v '/make_')
+mkdir -p "$TMP/wobj"
+i=0
+for f in $WSRC; do
+    gcc -O3 -fPIC -w -D_GNU_SOURCE -I"$HERE/fftw_shim" -I"$REF/wdsp" -c "$f" -o "$TMP/wobj/$(basename "$f" .c).o" &
+    i=$((i+1)); if [ $((i % 8)) -eq 0 ]; then wait; fi
+done
+wait
+gcc -O3 -fPIC -w -c "$HERE/fftw_shim/fftw_shim.c" -o "$TMP/wobj/_fftw_shim.o"
+gcc -O3 -fPIC -w -c "$HERE/fft64.c" -o "$TMP/wobj/_fft64.o"
+gcc -shared -o "$OUT/libwdsp_ref.so" "$TMP"/wobj/*.o -lm -lpthread
+echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')"

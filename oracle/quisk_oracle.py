@@ -1,0 +1,605 @@
+"""oracle/quisk_oracle.py -- TEST INFRASTRUCTURE (CPU oracle), NOT product code.
+
+A NumPy restatement of the reference's receive-DSP hot path (Quisk 4.2.52,
+`filter.c`, the RX functions of `quisk.c`, the panadapter math).  Only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline leg may import
+this module; the product (`quisk_b200`, `libquisk_cuda.so`) never does.
+
+Formulation.  The reference keeps ring buffers and computes one output at a
+time.  This restatement keeps, for every filter, a *linear history* of the most
+recent inputs and evaluates each block as an explicit convolution over
+`[history | block]`.  That is a deliberately different program from both the
+reference and the CUDA kernels, so agreement between the three is meaningful.
+Floating-point sums are therefore ordered differently from the reference
+(agreement ~1e-15 relative); sample COUNTS and phase carry-over are exact.
+
+Pinned against the compiled reference (`oracle/_ref`, built by
+`oracle/build_ref.sh` from /root/reference) by `tests/test_oracle_vs_ref.py` and
+against the committed fixtures in `tests/golden/` (generated from the compiled
+reference by `tests/golden/make_golden.py`).  The reference itself ships no
+tests or golden vectors, so that is the only pin available.
+
+All citations are file:line under /root/reference.
+"""
+from __future__ import annotations
+
+import math
+import numpy as np
+
+SAMP_BUFFER_SIZE = 66000                  # quisk.h:15
+OUT_CLIP = SAMP_BUFFER_SIZE * 8 // 10     # filter.c:158,194,315 (52 800)
+CLIP32 = 2147483647                       # quisk.h:13
+
+# Half-band 45-tap coefficients: the static table inside quisk_cDecim2HB45
+# (filter.c:381-384).  coef[11] = 0.5 is the centre tap; taps 0 and 44 of the
+# 45-tap prototype are zero.
+HB45_COEF = np.array([
+    0.000018566625444266, -0.000118469698701817, 0.000457318798253456,
+    -0.001347840471412094, 0.003321838571445455, -0.007198422696929033,
+    0.014211106939802483, -0.026424776824073383, 0.048414810444971007,
+    -0.096214669073304823, 0.314881034738348550, 0.500000000000000000])
+
+
+def hb45_dense() -> np.ndarray:
+    """The half-band as a dense 43-tap filter g (zero outer taps dropped):
+    g[2k] = g[42-2k] = coef[k], g[21] = 0.5  (filter.c:401-413)."""
+    g = np.zeros(43)
+    for k in range(11):
+        g[2 * k] = HB45_COEF[k]
+        g[42 - 2 * k] = HB45_COEF[k]
+    g[21] = HB45_COEF[11]
+    return g
+
+
+def _conv_at(X: np.ndarray, h: np.ndarray, pos: np.ndarray) -> np.ndarray:
+    """sum_k h[k] * X[pos-k]; pos-k is guaranteed in range by the callers."""
+    if len(pos) == 0:
+        return np.zeros(0, dtype=np.result_type(X, h))
+    full = np.convolve(X, h)
+    return full[pos]
+
+
+class HB45Decim:
+    """quisk_cDecim2HB45 (filter.c:377-417).  With n the index of an input
+    since the filter was fresh, an output is produced on every odd n and equals
+    sum_{k<=10} (x[n-2k] + x[n-42+2k]) c[k] + 0.5 x[n-21]."""
+
+    H = 42
+
+    def __init__(self, dtype=np.complex128):
+        self.hist = np.zeros(self.H, dtype=dtype)
+        self.toggle = 0
+        self.g = hb45_dense()
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        X = np.concatenate([self.hist, x])
+        # the input at block offset i is an output sample iff (toggle + i) is odd
+        first = 1 - self.toggle
+        i = np.arange(first, len(x), 2)
+        y = _conv_at(X, self.g, i + self.H)
+        self.toggle = (self.toggle + len(x)) & 1
+        self.hist = X[len(X) - self.H:]
+        return y
+
+
+class FirDecim:
+    """quisk_cDecimate / quisk_dDecimate / quisk_cFilter / quisk_dFilter
+    (filter.c:203-229, 259-285, 347-375) and, with complex `coefs`,
+    quisk_cCDecimate (filter.c:231-257).  Output on the input that makes
+    ++decim_index reach `decim`; newest sample times coef[0]."""
+
+    def __init__(self, coefs, decim=1, dtype=np.complex128):
+        self.h = np.asarray(coefs)
+        self.decim = int(decim)
+        self.H = len(self.h) - 1
+        self.hist = np.zeros(self.H, dtype=dtype)
+        self.decim_index = 0
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        X = np.concatenate([self.hist, x])
+        D = self.decim
+        first = D - 1 - self.decim_index
+        i = np.arange(first, len(x), D)
+        y = _conv_at(X, self.h, i + self.H)
+        self.decim_index = (self.decim_index + len(x)) % D
+        self.hist = X[len(X) - self.H:] if self.H else X[:0]
+        return y
+
+
+class FirInterp:
+    """quisk_cInterpolate / quisk_dInterpolate (filter.c:131-201): per input,
+    `interp` outputs interp * sum_{k < nTaps/interp} x[i-k] coef[j + k*interp].
+    NOTE the integer quotient nTaps/interp: trailing taps are never used
+    (SURVEY.md F10).  Output is cut at 52 800 samples (filter.c:158)."""
+
+    def __init__(self, coefs, interp, dtype=np.complex128):
+        self.h = np.asarray(coefs, dtype=np.float64)
+        self.L = int(interp)
+        self.K = len(self.h) // self.L
+        self.H = len(self.h) - 1          # the reference ring holds nTaps samples
+        self.hist = np.zeros(self.H, dtype=dtype)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        X = np.concatenate([self.hist, x])
+        n = len(x)
+        y = np.zeros(n * self.L, dtype=X.dtype)
+        pos = np.arange(n) + self.H
+        for j in range(self.L):
+            hj = self.h[j:j + self.K * self.L:self.L][:self.K]
+            y[j::self.L] = _conv_at(X, hj, pos) * self.L
+        self.hist = X[len(X) - self.H:]
+        return y[:OUT_CLIP]
+
+
+class FirInterpDecim:
+    """quisk_cInterpDecim (filter.c:287-324).  On the up-sampled time line input
+    i covers positions [i*L, (i+1)*L); output m sits at u = decim_index0 + m*M,
+    i.e. comes from input floor(u/L) with phase u mod L.  Same nTaps/interp tap
+    truncation as FirInterp; same 52 800 output cut (filter.c:315)."""
+
+    def __init__(self, coefs, interp, decim, dtype=np.complex128):
+        self.h = np.asarray(coefs, dtype=np.float64)
+        self.L = int(interp)
+        self.M = int(decim)
+        self.K = len(self.h) // self.L
+        self.H = len(self.h) - 1
+        self.hist = np.zeros(self.H, dtype=dtype)
+        self.decim_index = 0
+
+    def n_out(self, count: int) -> int:
+        span = count * self.L - self.decim_index
+        return max(0, -(-span // self.M))
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        X = np.concatenate([self.hist, x])
+        n = len(x)
+        nout = self.n_out(n)
+        u = self.decim_index + np.arange(nout) * self.M
+        src = u // self.L
+        ph = u % self.L
+        y = np.zeros(nout, dtype=X.dtype)
+        for p in range(self.L):
+            sel = np.nonzero(ph == p)[0]
+            if len(sel) == 0:
+                continue
+            hp = self.h[p:p + self.K * self.L:self.L][:self.K]
+            y[sel] = _conv_at(X, hp, src[sel] + self.H) * self.L
+        self.decim_index = self.decim_index + nout * self.M - n * self.L
+        self.hist = X[len(X) - self.H:]
+        return y[:OUT_CLIP]
+
+
+class HB45Interp:
+    """quisk_dInterp2HB45 / quisk_cInterp2HB45 (filter.c:420-488): per input two
+    outputs, 2*c[11]*s[11] and 2*sum_{k<11}(s[k]+s[21-k])*c[k], s[k] = x[i-k].
+    The output clip test is `nOut > 52800` checked before each PAIR
+    (filter.c:444,479), so up to 52 802 samples can be written."""
+
+    H = 21
+
+    def __init__(self, dtype=np.float64):
+        self.hist = np.zeros(self.H, dtype=dtype)
+        side = np.zeros(22)
+        for k in range(11):
+            side[k] = HB45_COEF[k]
+            side[21 - k] = HB45_COEF[k]
+        self.side = side
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        X = np.concatenate([self.hist, x])
+        n = len(x)
+        pos = np.arange(n) + self.H
+        y = np.zeros(2 * n, dtype=X.dtype)
+        y[0::2] = X[pos - 11] * HB45_COEF[11] * 2
+        y[1::2] = _conv_at(X, self.side, pos) * 2
+        self.hist = X[len(X) - self.H:]
+        npairs = min(n, (OUT_CLIP + 2) // 2)     # pairs written while nOut <= 52800
+        return y[:2 * npairs]
+
+
+def rx_filter_impulse(filt: np.ndarray) -> np.ndarray:
+    """Effective impulse response of cRxFilterOut/dRxFilterOut for a tap table
+    `filt` (quisk.c:1203-1215, 1240-1255): the newest sample meets filt[0], then
+    the ring is walked FORWARD from the write index, so the oldest sample meets
+    filt[1] ... the previous sample meets filt[N-1]:  h[0] = filt[0],
+    h[m] = filt[N-m]  (SURVEY.md F2)."""
+    f = np.asarray(filt, dtype=np.float64)
+    h = np.empty_like(f)
+    h[0] = f[0]
+    h[1:] = f[:0:-1]
+    return h
+
+
+class RxFilterC:
+    """cRxFilterOut (quisk.c:1218-1256): I rail filtered by filtI, Q rail by
+    filtQ, result accI + j accQ."""
+
+    def __init__(self, filt_i, filt_q):
+        self.hi = rx_filter_impulse(filt_i)
+        self.hq = rx_filter_impulse(filt_q)
+        self.H = len(self.hi) - 1
+        self.hist = np.zeros(self.H, dtype=np.complex128)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        X = np.concatenate([self.hist, x])
+        pos = np.arange(len(x)) + self.H
+        yi = _conv_at(X.real, self.hi, pos)
+        yq = _conv_at(X.imag, self.hq, pos)
+        self.hist = X[len(X) - self.H:]
+        return yi + 1j * yq
+
+
+class RxFilterD:
+    """dRxFilterOut (quisk.c:1182-1216): one real tap set on complex samples."""
+
+    def __init__(self, filt_i):
+        self.h = rx_filter_impulse(filt_i)
+        self.H = len(self.h) - 1
+        self.hist = np.zeros(self.H, dtype=np.complex128)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        X = np.concatenate([self.hist, x])
+        pos = np.arange(len(x)) + self.H
+        y = _conv_at(X, self.h, pos)
+        self.hist = X[len(X) - self.H:]
+        return y
+
+
+class TuneNCO:
+    """The tuning loop of quisk_process_samples (quisk.c:2477-2488):
+    x[i] *= v; v *= phase, phase = cexp(-j 2 pi tune / rate); v is static and
+    starts at 1.  Restated literally (sequential recurrence, separately rounded
+    products as gcc -O2 without FMA produces), so use it for short vectors."""
+
+    def __init__(self, tune_hz: float, rate: int):
+        ang = -2.0 * math.pi * tune_hz / rate
+        self.phase = complex(math.cos(ang), math.sin(ang))
+        self.v = 1.0 + 0.0j
+        self.tune_hz = tune_hz
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        if self.tune_hz == 0:
+            return x.copy()
+        y = np.empty_like(x)
+        vr, vi = self.v.real, self.v.imag
+        pr, pi = self.phase.real, self.phase.imag
+        xr = x.real.tolist()
+        xi = x.imag.tolist()
+        outr = [0.0] * len(xr)
+        outi = [0.0] * len(xr)
+        for n in range(len(xr)):
+            a, b = xr[n], xi[n]
+            outr[n] = a * vr - b * vi
+            outi[n] = a * vi + b * vr
+            vr, vi = vr * pr - vi * pi, vr * pi + vi * pr
+        y.real = outr
+        y.imag = outi
+        self.v = complex(vr, vi)
+        return y
+
+
+def plan_decimation(sample_rate: int):
+    """PlanDecimation (quisk.c:1633-1671): the (i2<=6, i3<=3, i5<=3) with the
+    smallest resulting rate >= 48000 (first found wins ties because the test is
+    a strict `<`).  Returns (best_rate_after_24/25_fixup, decim2, decim3, decim5)."""
+    best = sample_rate
+    d2 = d3 = d5 = 0
+    for i2 in range(7):
+        for i3 in range(4):
+            for i5 in range(4):
+                t = sample_rate
+                for _ in range(i2):
+                    t //= 2
+                for _ in range(i3):
+                    t //= 3
+                for _ in range(i5):
+                    t //= 5
+                if 48000 <= t < best:
+                    d2, d3, d5, best = i2, i3, i5, t
+    if best >= 50000:
+        best = best * 24 // 25
+    return best, d2, d3, d5
+
+
+class ProcessDecimate:
+    """quisk_process_decimate, default branch (quisk.c:1769-1844): decim2-1 half
+    bands, decim3 x (147 taps /3), decim5 x (245 taps /5), then the 98-tap /2 FIR
+    if decim2 > 0, then the 6/5 + 4/5 rate fix when the result is >= 50 kS/s.
+    `tables` maps the reference's coefficient-table names to arrays.  The SDR-IQ
+    special rates (quisk.c:1731-1767) are handled as in the reference."""
+
+    def __init__(self, sample_rate: int, tables: dict):
+        self.rate = sample_rate
+        self.stages = []
+        key = (sample_rate + 100) // 1000
+        T = tables
+        rate = sample_rate
+        if key == 41:
+            rate = 48000
+        elif key == 53:
+            self.stages.append(FirDecim(T["quiskFilt53D1Coefs"], 1))
+        elif key == 111:
+            self.stages.append(FirDecim(T["quiskFilt111D2Coefs"], 2)); rate //= 2
+        elif key == 133:
+            self.stages.append(FirDecim(T["quiskFilt133D2Coefs"], 2)); rate //= 2
+        elif key == 185:
+            self.stages.append(FirDecim(T["quiskFilt185D3Coefs"], 3)); rate //= 3
+        elif key == 370:
+            self.stages += [HB45Decim(), FirDecim(T["quiskFilt185D3Coefs"], 3)]; rate //= 6
+        elif key == 740:
+            self.stages += [HB45Decim(), HB45Decim(), FirDecim(T["quiskFilt185D3Coefs"], 3)]; rate //= 12
+        elif key == 1333:
+            self.stages += [HB45Decim(), HB45Decim(), HB45Decim(), FirDecim(T["quiskFilt167D3Coefs"], 3)]; rate //= 24
+        else:
+            _, d2, d3, d5 = plan_decimation(sample_rate)
+            i2 = d2
+            n_hb = 0
+            while i2 > 1 and n_hb < 5:
+                self.stages.append(HB45Decim()); rate //= 2; i2 -= 1; n_hb += 1
+            for _ in range(d3):
+                self.stages.append(FirDecim(T["quiskFilt144D3Coefs"], 3)); rate //= 3
+            for _ in range(d5):
+                self.stages.append(FirDecim(T["quiskFilt240D5CoefsSharp"], 5)); rate //= 5
+            if i2 > 0:
+                self.stages.append(FirDecim(T["quiskFilt48dec24Coefs"], 2)); rate //= 2
+            if rate >= 50000:
+                rate = rate * 24 // 25
+                self.stages.append(FirInterpDecim(T["quiskFilt300D5Coefs"], 6, 5))
+                self.stages.append(FirInterpDecim(T["quiskFilt240D5CoefsSharp"], 4, 5))
+        self.decim_srate = rate
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        for s in self.stages:
+            x = s(x)
+        return x
+
+
+FM_FILTER_DEMPH = 300.0      # quisk.c:46
+
+
+class ProcessDemodulate:
+    """quisk_process_demodulate (quisk.c:1848-2160) for the modes on the hot
+    path: CWL/CWU (/8 -> 6 k), LSB/USB (/4 -> 12 k), AM (/2 -> 24 k, |x| + DC
+    block, 36-tap audio FIR), FM (48 k, arg(x conj(x_-1)), x 20e5, one-pole
+    de-emphasis, /4, high-pass FIR, x4).  The optional auto-notch / SSB squelch
+    are off, as they are by default in the reference.  Returns real audio at 48 k."""
+
+    def __init__(self, mode: str, filt_i, filt_q, tables: dict):
+        T = tables
+        self.mode = mode
+        self.pre = []
+        self.post = []
+        if mode in ("CWL", "CWU"):
+            self.pre = [HB45Decim(), HB45Decim(), FirDecim(T["quiskFilt48dec24Coefs"], 2)]
+            self.rx = RxFilterC(filt_i, filt_q)
+            self.post = [FirInterp(T["quiskAudio24p4Coefs"], 2, np.float64), HB45Interp(), HB45Interp()]
+        elif mode in ("LSB", "USB"):
+            self.pre = [HB45Decim(), FirDecim(T["quiskFilt48dec24Coefs"], 2)]
+            self.rx = RxFilterC(filt_i, filt_q)
+            self.post = [FirInterp(T["quiskAudio24p4Coefs"], 2, np.float64), HB45Interp()]
+        elif mode == "AM":
+            self.pre = [FirDecim(T["quiskFilt48dec24Coefs"], 2)]
+            self.rx = RxFilterD(filt_i)
+            self.dc_remove = 0.0
+            self.post = [FirDecim(T["quiskAudio24p6Coefs"], 1, np.float64), HB45Interp()]
+        elif mode == "FM":
+            self.rx = RxFilterD(filt_i)
+            self.fm_1 = 10.0 + 0.0j                             # quisk.c:1893
+            www = math.tan(math.pi * FM_FILTER_DEMPH / 48000)   # quisk.c:1895-1899
+            nnn = 1.0 / (1.0 + www)
+            self.a0 = www * nnn
+            self.a1 = self.a0
+            self.b1 = nnn * (www - 1.0)
+            self.x1 = 0.0
+            self.y1 = 0.0
+            self.post = [FirDecim(T["quiskLpFilt48Coefs"], 4, np.float64),
+                         FirDecim(T["quiskAudioFmHpCoefs"], 1, np.float64),
+                         HB45Interp(), HB45Interp()]
+        else:
+            raise ValueError(mode)
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        for s in self.pre:
+            x = s(x)
+        cx = self.rx(x)
+        if self.mode in ("CWL", "LSB"):
+            d = cx.real + cx.imag                       # quisk.c:1916,1962
+        elif self.mode in ("CWU", "USB"):
+            d = cx.real - cx.imag                       # quisk.c:1939,1986
+        elif self.mode == "AM":
+            mag = np.abs(cx)                            # quisk.c:2007-2011
+            d = np.empty(len(mag))
+            dc = self.dc_remove
+            for i, m in enumerate(mag.tolist()):
+                t = m + dc * 0.99
+                d[i] = t - dc
+                dc = t
+            self.dc_remove = dc
+        else:                                           # FM, quisk.c:2029-2064
+            prev = np.concatenate([[self.fm_1], cx[:-1]]) if len(cx) else cx
+            di = np.angle(cx * np.conj(prev))
+            if len(cx):
+                self.fm_1 = cx[-1]
+            di = di * 20e5
+            d = np.empty(len(di))
+            x1, y1 = self.x1, self.y1
+            for i, v in enumerate(di.tolist()):
+                y1 = v * self.a0 + x1 * self.a1 - y1 * self.b1
+                x1 = v
+                d[i] = y1
+            self.x1, self.y1 = x1, y1
+        for s in self.post:
+            d = s(d)
+        return d
+
+
+def make_filter_coef(rate: int, N, bw: int, center: int, prototypes: dict):
+    """MakeFilterCoef (quisk.py:5405-5456).  `prototypes` is the Filters dict of
+    filters.py (key = bw*24000//rate//2).  Returns (filtI, filtQ)."""
+    center = abs(center)
+    lowpass = bw * 24000 // rate // 2
+    if lowpass in prototypes:
+        filt_d = list(prototypes[lowpass])
+    else:
+        if N is None:
+            shape = 1.5
+            trans = (bw / 2.0 / rate) * (shape - 1.0)
+            N = int(4.0 / trans)
+            if N > 1000:
+                N = 1000
+            N = (N // 2) * 2 + 1
+        K = bw * N // rate
+        filt_d = []
+        for k in range(-N // 2, N // 2 + 1):
+            if k == 0:
+                z = float(K) / N
+            else:
+                z = 1.0 / N * math.sin(math.pi * k * K / N) / math.sin(math.pi * k / N)
+            w = 0.42 + 0.5 * math.cos(2. * math.pi * k / N) + 0.08 * math.cos(4. * math.pi * k / N)
+            filt_d.append(z * w)
+    if center:
+        import cmath
+        tune = -1j * 2.0 * math.pi * center / rate
+        NN = len(filt_d)
+        D = (NN - 1.0) / 2.0
+        fi, fq = [], []
+        for i in range(NN):
+            z = 2.0 * cmath.exp(tune * (i - D)) * filt_d[i]
+            fi.append(z.real)
+            fq.append(z.imag)
+        return np.array(fi), np.array(fq)
+    return np.array(filt_d), np.array(filt_d)
+
+
+# --------------------------------------------------------------------------
+# Panadapter (quisk.c:5142-5331, 4868-4930, 4957-5011, 4932-4955, 6003-6009)
+# --------------------------------------------------------------------------
+
+def hann_window(n: int) -> np.ndarray:
+    """record_app window (quisk.c:6003-6009): 0.5 + 0.5 cos(2 pi j / N), j = -N/2 .. N/2-1."""
+    j = np.arange(n) - n // 2
+    return 0.5 + 0.5 * np.cos(2.0 * math.pi * j / n)
+
+
+def panadapter_accumulate(frames: np.ndarray) -> np.ndarray:
+    """get_graph's per-frame work (quisk.c:5212-5215, 5271-5276): window, complex
+    FFT, then fft_avg[k] += |X[(k + N/2) mod N]| over the given frames.
+    `frames` is [count_fft, N] complex."""
+    n = frames.shape[-1]
+    w = hann_window(n)
+    X = np.fft.fft(frames * w, axis=-1)
+    return np.abs(np.fft.fftshift(X, axes=-1)).sum(axis=0)
+
+
+def panadapter_pixels(fft_avg: np.ndarray, count_fft: int, data_width: int, zoom: float,
+                      deltaf: float, fft_sample_rate: float) -> np.ndarray:
+    """The graph-return half of get_graph (quisk.c:5279-5321): bin fft_avg into
+    data_width pixels IN PLACE (pixel i overwrites fft_avg[i] while later pixels
+    still read fft_avg -- the aliasing is reproduced), then
+    20 log10(sum) - 20 (log10 count + log10 N + 31 log10 2), clamped to [-200, 0]."""
+    avg = np.array(fft_avg, dtype=np.float64)
+    n_fft = len(avg)
+    scale = (math.log10(count_fft) + math.log10(n_fft) + 31.0 * math.log10(2.0)) * 20.0
+    n = int(zoom * float(n_fft) / data_width + 0.5)
+    if n < 1:
+        n = 1
+    for i in range(data_width):
+        k = int(n_fft * (deltaf / fft_sample_rate + zoom * (float(i) / data_width - 0.5) + 0.5) + 0.1)
+        d2 = 0.0
+        for j in range(n):
+            if 0 <= k < n_fft:
+                d2 += avg[k]
+            k += 1
+        avg[i] = d2
+    out = np.empty(data_width)
+    for i in range(data_width):
+        d2 = 20.0 * math.log10(avg[i]) - scale if avg[i] > 0 else -math.inf
+        if d2 < -200:
+            d2 = -200.0
+        elif d2 > 0:
+            d2 = 0.0
+        out[i] = d2
+    return out
+
+
+def multirx_graph(samples: np.ndarray, mult: int = 8) -> np.ndarray:
+    """get_multirx_graph (quisk.c:4868-4930): Hann, FFT, |X| summed in groups of
+    MULTIRX_FFT_MULT bins in fftshift order, 20 log10 - 20 (log10 N + 31 log10 2),
+    floor -200 (no upper clamp)."""
+    n = len(samples)
+    X = np.fft.fft(samples * hann_window(n))
+    mag = np.abs(np.fft.fftshift(X))
+    scale = (math.log10(n) + 31.0 * math.log10(2.0)) * 20.0
+    d1 = mag.reshape(-1, mult).sum(axis=1)
+    with np.errstate(divide="ignore"):
+        d2 = 20.0 * np.log10(d1) - scale
+    return np.maximum(d2, -200.0)
+
+
+def copy2pixels(fft: np.ndarray, n_pixels: int, zoom: float, deltaf: float, rate: float) -> np.ndarray:
+    """copy2pixels (quisk.c:4932-4955): fractional-bin integration of `fft`
+    (which must have one spare element at the end) into n_pixels."""
+    fft_size = len(fft) - 1
+    f1 = deltaf + rate / 2.0 * (1.0 - zoom)
+    out = np.empty(n_pixels)
+    for i in range(n_pixels):
+        d1 = fft_size / rate * (f1 + float(i) / n_pixels * zoom * rate)
+        d2 = fft_size / rate * (f1 + float(i + 1) / n_pixels * zoom * rate)
+        j1 = math.floor(d1)
+        j2 = math.floor(d2)
+        if j1 == j2:
+            s = (d2 - d1) * fft[j1]
+        else:
+            s = (j1 + 1 - d1) * fft[j1]
+            for j in range(j1 + 1, j2):
+                s += fft[j]
+            s += (d2 - j2) * fft[j2]
+        out[i] = s
+    return out
+
+
+def bandscope(blocks: np.ndarray, graph_width: int, clock: int, zoom: float, deltaf: float) -> np.ndarray:
+    """get_bandscope (quisk.c:4957-5011) for fft_count = len(blocks) real blocks
+    of bandscope_size samples: window (Hann, quisk.c bandscopeWindow), r2c FFT,
+    |X| average over L = size/2+1 bins, copy2pixels, scale, 20 log10 (<=1e-10 -> -200)."""
+    fft_count, size = blocks.shape
+    L = size // 2 + 1
+    w = hann_window(size)
+    avg = np.abs(np.fft.rfft(blocks * w, axis=-1)).sum(axis=0)
+    avg = np.concatenate([avg, [0.0]])
+    frac = float(L) / graph_width
+    scale = 1.0 / frac / fft_count / size
+    pix = copy2pixels(avg, graph_width, zoom, deltaf, clock / 2.0)
+    out = np.empty(graph_width)
+    for i in range(graph_width):
+        s = pix[i] * scale
+        out[i] = -200.0 if s <= 1e-10 else 20.0 * math.log10(s)
+    return out
+
+
+# --------------------------------------------------------------------------
+# Synthetic input
+# --------------------------------------------------------------------------
+
+def synth_iq(n: int, channel: int = 0, fs: float = 1.0, start: int = 0) -> np.ndarray:
+    """Eight complex tones at +-0.01/0.07/0.13/0.31 fs with amplitudes 2^24..2^30
+    plus Gaussian noise sigma = 2^20, numpy default_rng(1234 + channel)."""
+    rng = np.random.default_rng(1234 + channel)
+    fr = np.array([0.01, -0.01, 0.07, -0.07, 0.13, -0.13, 0.31, -0.31])
+    amp = 2.0 ** np.linspace(24, 30, 8)
+    ph = rng.uniform(0, 2 * math.pi, 8)
+    t = np.arange(start, start + n, dtype=np.float64)
+    x = np.zeros(n, dtype=np.complex128)
+    for f, a, p in zip(fr, amp, ph):
+        x += a * np.exp(1j * (2 * math.pi * f * t + p))
+    x += (2.0 ** 20) * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return x
+
+
+def rel_rms(a: np.ndarray, b: np.ndarray) -> float:
+    """relative RMS error of a against b."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    den = np.sqrt(np.mean(np.abs(b) ** 2))
+    num = np.sqrt(np.mean(np.abs(a - b) ** 2)) if len(a) else 0.0
+    return float(num / den) if den > 0 else float(num)

@@ -1,0 +1,115 @@
+/* oracle/ref_wrap/quisk_rx_wrap.c -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Translation unit that turns the `static` receive-chain functions of the
+ * reference's quisk.c into a loadable library WITHOUT copying them into this
+ * repository: oracle/build_ref.sh extracts the line ranges listed below from
+ * /root/reference/quisk.c into a scratch file under /tmp at build time, and
+ * this wrapper `#include`s that scratch file.  Everything in THIS file is our
+ * own glue: the handful of file-scope variables those functions expect
+ * (quisk.c:127-134,191-195,202,254-269), no-op stand-ins for the optional
+ * stages that are switched off by default (auto-notch, SSB squelch), and
+ * `ref_*` accessors for ctypes.
+ *
+ * Extracted ranges (quisk.c):  46-53 constants, 68-81 struct AgcState,
+ * 622-665 cFracDecim, 1182-1256 dRxFilterOut/cRxFilterOut,
+ * 1633-1671 PlanDecimation, 1673-1846 quisk_process_decimate,
+ * 1848-2160 quisk_process_demodulate, 2162-2287 process_agc.
+ */
+#include <Python.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <complex.h>
+#include "quisk.h"
+#include "filter.h"
+
+#define DEBUG 0
+#include "quisk_rx_consts.inc"      /* quisk.c:46-53, 68-81 */
+
+struct sound_conf quisk_sound_state;
+
+static double cFilterI[MAX_RX_FILTERS][MAX_FILTER_SIZE];
+static double cFilterQ[MAX_RX_FILTERS][MAX_FILTER_SIZE];
+static int sizeFilter;
+static int filter_bandwidth[MAX_RX_FILTERS];
+static int quisk_decim_srate;
+static int quisk_filter_srate = 48000;
+static double agcReleaseGain = 80;
+static double agc_release_time = 1.0;
+static double squelch_level = -999.0;
+static int ssb_squelch_enabled;
+static int rit_freq;
+static double measured_audio;
+static double measure_audio_sum;
+static int measure_audio_count;
+static int measure_audio_time = 1;
+static struct _MeasureSquelch {
+    int squelch_active;
+    double rf_sum;
+    double squelch;
+    int rf_count;
+    double *in_fft;
+    int index;
+    int sq_open;
+} MeasureSquelch[MAX_RX_CHANNELS];
+
+/* Optional stages, off by default in the reference (quisk_auto_notch == 0,
+ * ssb_squelch_enabled == 0): the calls stay in the extracted code, they do nothing. */
+static void dAutoNotch(double *d, int n, int f, int r) { (void)d; (void)n; (void)f; (void)r; }
+static void ssb_squelch(double *d, int n, int r, struct _MeasureSquelch *m) { (void)d; (void)n; (void)r; (void)m; }
+static void d_delay(double *d, int n, int b, int s) { (void)d; (void)n; (void)b; (void)s; }
+
+#include "quisk_rx_funcs.inc"       /* the function ranges listed above */
+
+/* ---- accessors ---- */
+void ref_set_sample_rate(int rate) { quisk_sound_state.sample_rate = rate; }
+void ref_set_playback_rate(int rate) { quisk_sound_state.playback_rate = rate; }
+int ref_decim_srate(void) { return quisk_decim_srate; }
+int ref_filter_srate(void) { return quisk_filter_srate; }
+void ref_init_chain(void)
+{
+    quisk_process_decimate(NULL, 0, 0, 0);
+    quisk_process_demodulate(NULL, NULL, 0, 0, 0, 0);
+}
+void ref_set_filters(const double *fi, const double *fq, int size, int bw, int nFilter)
+{   /* same effect as set_filters(), quisk.c:4551-4594 */
+    int i;
+    filter_bandwidth[nFilter] = bw;
+    for (i = 0; i < size; i++) { cFilterI[nFilter][i] = fi[i]; cFilterQ[nFilter][i] = fq[i]; }
+    sizeFilter = size;
+}
+int ref_plan_decimation(int *p2, int *p3, int *p5) { return PlanDecimation(p2, p3, p5); }
+int ref_process_decimate(complex double *cs, int n, int bank, int mode)
+{ return quisk_process_decimate(cs, n, bank, (rx_mode_type)mode); }
+int ref_process_demodulate(complex double *cs, double *ds, int n, int bank, int nFilter, int mode)
+{ return quisk_process_demodulate(cs, ds, n, bank, nFilter, (rx_mode_type)mode); }
+void ref_cRxFilterOut(complex double *cs, int n, int bank, int nFilter)
+{ int i; for (i = 0; i < n; i++) cs[i] = cRxFilterOut(cs[i], bank, nFilter); }
+void ref_dRxFilterOut(complex double *cs, int n, int bank, int nFilter)
+{ int i; for (i = 0; i < n; i++) cs[i] = dRxFilterOut(cs[i], bank, nFilter); }
+int ref_cFracDecim(complex double *cs, int n, double fdecim) { return cFracDecim(cs, n, fdecim); }
+
+/* The tune loop is four lines inside quisk_process_samples (quisk.c:2477-2488);
+ * `vec` plays the role of the static rxTuneVector and is carried by the caller. */
+void ref_tune(complex double *cs, int n, double tune_hz, int sample_rate, complex double *vec)
+{
+    complex double phase = cexp((I * -2.0 * M_PI * tune_hz) / sample_rate);
+    complex double v = *vec;
+    int i;
+    for (i = 0; i < n; i++) { cs[i] *= v; v *= phase; }
+    *vec = v;
+}
+
+/* process_agc: opaque state handle for ctypes */
+void *ref_agc_new(double max_out, int sample_rate)
+{
+    struct AgcState *s = (struct AgcState *)calloc(1, sizeof(*s));
+    s->max_out = max_out;
+    s->sample_rate = sample_rate;
+    s->buf_size = 0;
+    process_agc(s, NULL, 0, 0);     /* first call initialises (quisk.c:2174-2190) */
+    return s;
+}
+void ref_agc_set(double release_gain, double release_time) { agcReleaseGain = release_gain; agc_release_time = release_time; }
+void ref_agc_run(void *s, complex double *cs, int n, int is_cpx) { process_agc((struct AgcState *)s, cs, n, is_cpx); }
+double ref_agc_gain(void *s) { return ((struct AgcState *)s)->gain; }
