@@ -1,0 +1,260 @@
+/* include/quisk_cuda.h -- C ABI of libquisk_cuda.so
+ *
+ * A B200 (sm_100a) implementation of Quisk's receive-DSP hot path behind the
+ * reference's own C entry points.  Three groups of exports:
+ *
+ *   1. The seventeen functions of the reference's filter.h (filter.h:39-55),
+ *      same names, same signatures, same caller-owned state structs (layouts
+ *      below are ABI-identical to filter.h:1-37: 56 / 56 / 544 / 280 bytes on
+ *      LP64).  Sample buffers are HOST pointers, processed in place, return
+ *      value = new sample count -- exactly what `_quisk` (quisk.c, sound.c,
+ *      microphone.c) links against today.  All arithmetic runs on the GPU.
+ *
+ *   2. `quisk_cuda_*` batched variants: many independent receiver channels
+ *      laid out [channel][sample] in DEVICE memory with per-channel filter
+ *      state kept resident in HBM.  These are new surface (the reference has
+ *      no batched API); they are where throughput is measured.
+ *
+ *   3. `quisk_cuda_rx_*` / `quisk_cuda_pan_*`: the fused receive chain
+ *      (quisk_process_samples' tune -> quisk_process_decimate ->
+ *      quisk_process_demodulate, quisk.c:2477-2530) and the panadapter
+ *      (get_graph, quisk.c:5142-5331) for a batch of channels.
+ *
+ * No torch types, no C++ types: plain pointers and sizes.  `stream` arguments
+ * are a `cudaStream_t` passed as `void *` (NULL = the legacy default stream).
+ * Every function that can fail returns 0 on success and a negative QC_E* code
+ * on failure, with a message retrievable through quisk_cuda_last_error().
+ * There is no CPU fallback anywhere: without a usable CUDA device the legacy
+ * entry points abort with a diagnostic (they have no error channel in the
+ * reference either) and the quisk_cuda_* entry points return QC_ENODEV.
+ */
+#ifndef QUISK_CUDA_H
+#define QUISK_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+typedef struct { double re, im; } quisk_cd;       /* layout of C99 `complex double` */
+#else
+#include <complex.h>
+typedef complex double quisk_cd;
+#endif
+
+/* ------------------------------------------------------------------------
+ * 1. filter.h drop-in
+ * --------------------------------------------------------------------- */
+
+struct quisk_cFilter {              /* filter.h:1-10 */
+    double *dCoefs;
+    quisk_cd *cpxCoefs;
+    int nBuf;
+    int nTaps;
+    int decim_index;
+    quisk_cd *cSamples;
+    quisk_cd *ptcSamp;
+    quisk_cd *cBuf;
+};
+
+struct quisk_dFilter {              /* filter.h:12-21 */
+    double *dCoefs;
+    quisk_cd *cpxCoefs;
+    int nBuf;
+    int nTaps;
+    int decim_index;
+    double *dSamples;
+    double *ptdSamp;
+    double *dBuf;
+};
+
+struct quisk_cHB45Filter {          /* filter.h:23-29 */
+    quisk_cd *cBuf;
+    int nBuf;
+    int toggle;
+    quisk_cd samples[22];
+    quisk_cd center[11];
+};
+
+struct quisk_dHB45Filter {          /* filter.h:31-37 */
+    double *dBuf;
+    int nBuf;
+    int toggle;
+    double samples[22];
+    double center[11];
+};
+
+void quisk_filt_cInit(struct quisk_cFilter *, double *, int);                   /* filter.h:39, filter.c:9   */
+void quisk_filt_dInit(struct quisk_dFilter *, double *, int);                   /* filter.h:40, filter.c:22  */
+void quisk_filt_differInit(struct quisk_dFilter *, int);                        /* filter.h:41, filter.c:35  */
+void quisk_filt_tune(struct quisk_dFilter *, double, int);                      /* filter.h:42, filter.c:58  */
+quisk_cd quisk_dC_out(double, struct quisk_dFilter *);                          /* filter.h:43, filter.c:83  */
+double quisk_dD_out(double, struct quisk_dFilter *);                            /* filter.h:44, filter.c:326 */
+int quisk_cInterpolate(quisk_cd *, int, struct quisk_cFilter *, int);           /* filter.h:45, filter.c:131 */
+int quisk_dInterpolate(double *, int, struct quisk_dFilter *, int);             /* filter.h:46, filter.c:167 */
+int quisk_cDecimate(quisk_cd *, int, struct quisk_cFilter *, int);              /* filter.h:47, filter.c:203 */
+int quisk_cCDecimate(quisk_cd *, int, struct quisk_cFilter *, int);             /* filter.h:48, filter.c:231 */
+int quisk_dDecimate(double *, int, struct quisk_dFilter *, int);                /* filter.h:49, filter.c:259 */
+int quisk_cInterpDecim(quisk_cd *, int, struct quisk_cFilter *, int, int);      /* filter.h:50, filter.c:287 */
+int quisk_cDecim2HB45(quisk_cd *, int, struct quisk_cHB45Filter *);             /* filter.h:51, filter.c:377 */
+int quisk_dInterp2HB45(double *, int, struct quisk_dHB45Filter *);              /* filter.h:52, filter.c:420 */
+int quisk_cInterp2HB45(quisk_cd *, int, struct quisk_cHB45Filter *);            /* filter.h:53, filter.c:455 */
+int quisk_dFilter(double *, int, struct quisk_dFilter *);                       /* filter.h:54, filter.c:347 */
+int quisk_cFilter(quisk_cd *, int, struct quisk_cFilter *);                     /* filter.h:55, filter.c:372 */
+
+/* ------------------------------------------------------------------------
+ * Library status
+ * --------------------------------------------------------------------- */
+
+#define QC_OK        0
+#define QC_ENODEV   (-1)    /* no usable CUDA device / driver */
+#define QC_ECUDA    (-2)    /* a CUDA runtime call failed     */
+#define QC_EINVAL   (-3)    /* bad argument                   */
+#define QC_ENOMEM   (-4)
+
+const char *quisk_cuda_last_error(void);
+int quisk_cuda_device_count(void);
+int quisk_cuda_set_device(int device);
+/* Kernels launched by this library since load (all threads); the bench reports the delta. */
+unsigned long long quisk_cuda_launch_count(void);
+const char *quisk_cuda_version(void);
+
+/* ------------------------------------------------------------------------
+ * 2. Batched single-stage filters, device resident
+ *
+ * One object = one filter.h filter instantiated for `n_channels` independent
+ * streams that are always fed the same number of samples per call (so the
+ * decimation phase -- toggle / decim_index -- is one host-side integer and
+ * output counts need no device round trip).  Input  [n_channels][in_stride],
+ * output [n_channels][out_stride], element type quisk_cd or double as the
+ * kind says.  Out-of-place (in != out).
+ * --------------------------------------------------------------------- */
+
+typedef struct qcBatchFilter qcBatchFilter;
+
+enum qcFilterKind {
+    QC_C_DECIM2_HB45 = 1,   /* quisk_cDecim2HB45                    complex -> complex */
+    QC_C_DECIMATE    = 2,   /* quisk_cDecimate / quisk_cFilter      complex -> complex, real taps */
+    QC_C_CDECIMATE   = 3,   /* quisk_cCDecimate                     complex -> complex, complex taps */
+    QC_D_DECIMATE    = 4,   /* quisk_dDecimate / quisk_dFilter      real -> real */
+    QC_C_INTERPOLATE = 5,   /* quisk_cInterpolate                   complex -> complex */
+    QC_D_INTERPOLATE = 6,   /* quisk_dInterpolate                   real -> real */
+    QC_C_INTERPDECIM = 7,   /* quisk_cInterpDecim                   complex -> complex */
+    QC_C_INTERP2_HB45 = 8,  /* quisk_cInterp2HB45                   complex -> complex */
+    QC_D_INTERP2_HB45 = 9,  /* quisk_dInterp2HB45                   real -> real */
+    QC_C_RXFILTER    = 10,  /* cRxFilterOut (quisk.c:1218): I taps on I rail, Q taps on Q rail */
+    QC_D_RXFILTER    = 11   /* dRxFilterOut (quisk.c:1182): one real tap set on complex samples */
+};
+
+/* coefs: HOST pointer, n_taps doubles (QC_C_CDECIMATE: n_taps complex = 2*n_taps
+ * doubles; QC_C_RXFILTER: filtI then filtQ, 2*n_taps doubles).  Ignored for the
+ * HB45 kinds.  interp/decim as in the matching filter.h call (unused ones = 1). */
+qcBatchFilter *quisk_cuda_batch_create(int kind, int n_channels, const double *coefs, int n_taps,
+                                       int interp, int decim);
+void quisk_cuda_batch_destroy(qcBatchFilter *f);
+/* Samples each channel will produce for `count` inputs given the current phase. */
+int quisk_cuda_batch_count_out(const qcBatchFilter *f, int count);
+/* The legacy API's silent output cut at 52 800 samples (filter.c:158) applies
+ * only when `legacy_clip` is non-zero. */
+int quisk_cuda_batch_run(qcBatchFilter *f, const void *d_in, long in_stride, int count,
+                         void *d_out, long out_stride, int *n_out, int legacy_clip, void *stream);
+/* Zero the history and phase (a freshly quisk_filt_cInit'ed filter). */
+int quisk_cuda_batch_reset(qcBatchFilter *f, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 3a. Batched receive chain
+ * --------------------------------------------------------------------- */
+
+typedef struct qcRxChain qcRxChain;
+
+enum qcRxMode {     /* values of rx_mode_type, quisk.h:56-70 */
+    QC_MODE_CWL = 0, QC_MODE_CWU = 1, QC_MODE_LSB = 2, QC_MODE_USB = 3, QC_MODE_AM = 4, QC_MODE_FM = 5
+};
+
+/* The reference keeps its decimation / audio coefficient tables in filters.h;
+ * a caller hands the ones a chain needs to the library by name (the drop-in
+ * build links the reference's own filters.h, tests load them from a fixture). */
+struct qcRxTables {
+    const double *filt144D3;      int n_filt144D3;       /* quiskFilt144D3Coefs       (147) */
+    const double *filt240D5Sharp; int n_filt240D5Sharp;  /* quiskFilt240D5CoefsSharp  (245) */
+    const double *filt48dec24;    int n_filt48dec24;     /* quiskFilt48dec24Coefs     (98)  */
+    const double *filt300D5;      int n_filt300D5;       /* quiskFilt300D5Coefs       (125) */
+    const double *audio24p4;      int n_audio24p4;       /* quiskAudio24p4Coefs       (50)  */
+    const double *audio24p6;      int n_audio24p6;       /* quiskAudio24p6Coefs       (36)  */
+    const double *lpFilt48;       int n_lpFilt48;        /* quiskLpFilt48Coefs        (186) */
+    const double *audioFmHp;      int n_audioFmHp;       /* quiskAudioFmHpCoefs       (309) */
+    const double *filt53D1;       int n_filt53D1;        /* SDR-IQ special rates, quisk.c:1731-1767 */
+    const double *filt111D2;      int n_filt111D2;
+    const double *filt133D2;      int n_filt133D2;
+    const double *filt167D3;      int n_filt167D3;
+    const double *filt185D3;      int n_filt185D3;
+};
+
+struct qcRxConfig {
+    int n_channels;
+    int sample_rate;            /* quisk_sound_state.sample_rate */
+    int mode;                   /* enum qcRxMode */
+    const double *filt_i;       /* set_filters() tap tables (quisk.c:4551), HOST, n_filt doubles each */
+    const double *filt_q;
+    int n_filt;
+    const double *tune_hz;      /* per-channel rx_tune_freq in Hz (HOST, n_channels) or NULL = no tuning */
+    struct qcRxTables tables;
+    int fused;                  /* 1 = fused shared-memory cascade kernels, 0 = one kernel per stage */
+};
+
+qcRxChain *quisk_cuda_rx_create(const struct qcRxConfig *cfg);
+void quisk_cuda_rx_destroy(qcRxChain *rx);
+/* PlanDecimation (quisk.c:1633): returns the planned rate, fills the three counts. */
+int quisk_cuda_plan_decimation(int sample_rate, int *decim2, int *decim3, int *decim5);
+int quisk_cuda_rx_decim_srate(const qcRxChain *rx);     /* quisk_decim_srate  */
+int quisk_cuda_rx_filter_srate(const qcRxChain *rx);    /* quisk_filter_srate */
+/* Upper bound on audio samples per channel for `count` inputs (for sizing buffers). */
+int quisk_cuda_rx_max_out(const qcRxChain *rx, int count);
+/* d_iq: [n_channels][iq_stride] quisk_cd (device).  d_audio: [n_channels][audio_stride]
+ * double (device), real audio at ~48 kS/s.  *n_audio = samples written per channel.
+ * Optionally also returns the complex samples after quisk_process_decimate
+ * (d_decim may be NULL): [n_channels][decim_stride] quisk_cd, *n_decim each. */
+int quisk_cuda_rx_process(qcRxChain *rx, const void *d_iq, long iq_stride, int count,
+                          double *d_audio, long audio_stride, int *n_audio,
+                          void *d_decim, long decim_stride, int *n_decim, void *stream);
+/* Same through HOST buffers: H2D copy of the block, the chain, D2H copy of the audio. */
+int quisk_cuda_rx_process_host(qcRxChain *rx, const quisk_cd *h_iq, long iq_stride, int count,
+                               double *h_audio, long audio_stride, int *n_audio);
+int quisk_cuda_rx_reset(qcRxChain *rx);
+
+/* ------------------------------------------------------------------------
+ * 3b. Batched panadapter (get_graph, quisk.c:5142-5331)
+ * --------------------------------------------------------------------- */
+
+typedef struct qcPanadapter qcPanadapter;
+
+qcPanadapter *quisk_cuda_pan_create(int n_streams, int fft_size);
+void quisk_cuda_pan_destroy(qcPanadapter *p);
+/* Window + FFT + fftshift + |X| accumulate of `n_frames` consecutive frames per
+ * stream (quisk.c:5212-5215, 5271-5276).  d_frames: [n_streams][frame_stride]
+ * quisk_cd with the n_frames frames of a stream contiguous (frame f at
+ * offset f*fft_size).  Adds into the per-stream average and bumps count_fft. */
+int quisk_cuda_pan_accumulate(qcPanadapter *p, const void *d_frames, long stream_stride,
+                              int n_frames, void *stream);
+/* The graph-return half (quisk.c:5279-5321): pixel binning, dB scaling, clamp to
+ * [-200, 0]; zeroes the averages and count_fft.  d_graph: [n_streams][data_width]
+ * double (device). */
+int quisk_cuda_pan_graph(qcPanadapter *p, int data_width, double zoom, double deltaf,
+                         double fft_sample_rate, double *d_graph, void *stream);
+/* get_multirx_graph (quisk.c:4868-4930): one frame per stream, |X| summed in
+ * groups of 8 bins, no averaging state.  d_graph: [n_streams][fft_size/8]. */
+int quisk_cuda_pan_multirx(qcPanadapter *p, const void *d_frames, long stream_stride,
+                           double *d_graph, void *stream);
+int quisk_cuda_pan_count(const qcPanadapter *p);
+/* Raw device pointer to the [n_streams][fft_size] running |X| sums (for tests). */
+const double *quisk_cuda_pan_average_ptr(const qcPanadapter *p);
+
+/* Batched complex FFT (unnormalised, sign -1 forward / +1 backward), sizes 2^k,
+ * 8 <= n <= 16384: the in-house Stockham kernel the panadapter and the WDSP
+ * overlap-save stages are built on; exported so tests can pin it against
+ * numpy / cuFFT.  d_in may equal d_out. */
+int quisk_cuda_fft_batch(const void *d_in, void *d_out, int n, int batch, int sign, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUISK_CUDA_H */

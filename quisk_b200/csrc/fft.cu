@@ -1,0 +1,356 @@
+// quisk_b200/csrc/fft.cu -- batched FFT entry point and the panadapter (get_graph,
+// quisk.c:5142-5331; get_multirx_graph, quisk.c:4868-4930; window quisk.c:6003-6009).
+#include "fft_device.cuh"
+#include <cmath>
+#include <map>
+
+namespace qc {
+
+int fft_log2(int n)
+{
+    if (n < 8 || n > 8192 || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < n) l++;
+    return l;
+}
+
+void fft_shape(int n, int *lanes, int *per_cta)
+{
+    const int t = fft_threads(n);
+    *lanes = t;
+    int pc = 128 / t;                 // aim for >= 128 threads per CTA
+    if (pc < 1) pc = 1;
+    *per_cta = pc;
+}
+
+const cd *fft_twiddles(int n)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, cd *> cache;
+    std::lock_guard<std::mutex> g(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto key = std::make_pair(dev, n);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    std::vector<cd> h((size_t)n);
+    for (int k = 0; k < n; k++) {
+        const double a = 2.0 * M_PI * (double)k / (double)n;
+        h[k] = make_double2(cos(a), -sin(a));
+    }
+    cd *d = nullptr;
+    if (cudaMalloc((void **)&d, (size_t)n * sizeof(cd)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), (size_t)n * sizeof(cd), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    cache[key] = d;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------
+// plain batched transform
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) fft_batch_kernel(const cd *in, cd *out, int n, int batch, const cd *tw, int sign)
+{
+    extern __shared__ double smem_raw[];
+    cd *s = reinterpret_cast<cd *>(smem_raw) + (size_t)threadIdx.y * n;
+    const int f = blockIdx.x * blockDim.y + threadIdx.y;
+    const bool live = f < batch;
+    const int lane = threadIdx.x, lanes = blockDim.x;
+    if (live) {
+        const cd *src = in + (size_t)f * n;
+        for (int i = lane; i < n; i += lanes) s[i] = src[i];
+    }
+    __syncthreads();
+    fft_smem(s, n, tw, sign, lane, lanes);
+    if (live) {
+        cd *dst = out + (size_t)f * n;
+        for (int i = lane; i < n; i += lanes) dst[i] = s[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// panadapter accumulate: window -> FFT -> fftshift -> |X| -> running sum
+//
+// grid = (groups, n_streams).  A CTA walks frames g, g+groups, ... of its stream and keeps
+// the per-bin sums of the bins its threads own in registers; with groups == 1 the sum over
+// frames is formed in the reference's order (fft_avg[k] += cabs(...) frame by frame,
+// quisk.c:5271-5276) starting from the value already in `avg`.  With groups > 1 each group
+// writes a partial sum and pan_reduce_kernel folds them in.
+// ---------------------------------------------------------------------------------------
+static constexpr int PAN_MAX_OWN = 8;      // bins per thread: n / fft_threads(n) = 8
+
+__global__ void __launch_bounds__(1024) pan_accumulate_kernel(const cd *frames, long stream_stride, int n_frames, int n,
+                                      const cd *tw, const double *window, double *avg, double *partial, int groups)
+{
+    extern __shared__ double smem_raw[];
+    cd *s = reinterpret_cast<cd *>(smem_raw);
+    const int stream = blockIdx.y, g = blockIdx.x;
+    const int lane = threadIdx.x, lanes = blockDim.x;
+    const int half = n >> 1;
+    double acc[PAN_MAX_OWN];
+    double *dst = groups == 1 ? avg + (size_t)stream * n : partial + ((size_t)stream * groups + g) * n;
+#pragma unroll
+    for (int u = 0; u < PAN_MAX_OWN; u++) {
+        const int k = lane + u * lanes;
+        acc[u] = (groups == 1 && k < n) ? dst[k] : 0.0;
+    }
+    const cd *base = frames + (size_t)stream * stream_stride;
+    for (int f = g; f < n_frames; f += groups) {
+        const cd *src = base + (size_t)f * n;
+        for (int i = lane; i < n; i += lanes) {
+            const cd x = src[i];
+            const double w = window[i];
+            s[i] = make_double2(x.x * w, x.y * w);                  // quisk.c:5212-5213
+        }
+        __syncthreads();
+        fft_smem(s, n, tw, -1, lane, lanes);
+#pragma unroll
+        for (int u = 0; u < PAN_MAX_OWN; u++) {
+            const int k = lane + u * lanes;                         // graph bin k <- FFT bin (k + n/2) mod n
+            if (k < n) {
+                const cd X = s[(k + half) & (n - 1)];
+                acc[u] += hypot(X.x, X.y);                          // cabs, quisk.c:5273,5275
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < PAN_MAX_OWN; u++) {
+        const int k = lane + u * lanes;
+        if (k < n) dst[k] = acc[u];
+    }
+}
+
+__global__ void pan_reduce_kernel(double *avg, const double *partial, int n, int groups)
+{
+    const int stream = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double a = avg[(size_t)stream * n + k];
+    for (int g = 0; g < groups; g++) a += partial[((size_t)stream * groups + g) * n + k];
+    avg[(size_t)stream * n + k] = a;
+}
+
+// graph-return half (quisk.c:5279-5321), hazard-free case: every pixel reads only bins >= its own index
+__global__ void pan_graph_kernel(double *avg, int n, int data_width, int nbin, double zoom, double deltaf,
+                                 double rate, double scale, double *graph)
+{
+    const int stream = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= data_width) return;
+    const double *a = avg + (size_t)stream * n;
+    int k = (int)(n * (deltaf / rate + zoom * ((double)i / data_width - 0.5) + 0.5) + 0.1);
+    double d2 = 0.0;
+    for (int j = 0; j < nbin; j++, k++)
+        if (k >= 0 && k < n) d2 += a[k];
+    d2 = 20.0 * log10(d2) - scale;
+    if (d2 < -200) d2 = -200;
+    else if (d2 > 0) d2 = 0;
+    graph[(size_t)stream * data_width + i] = d2;
+}
+
+// same, literal in-place walk for the zoomed cases where pixel i reads bins already overwritten
+__global__ void pan_graph_serial_kernel(double *avg, int n, int data_width, int nbin, double zoom, double deltaf,
+                                        double rate, double scale, double *graph)
+{
+    double *a = avg + (size_t)blockIdx.y * n;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int i = 0; i < data_width; i++) {
+        int k = (int)(n * (deltaf / rate + zoom * ((double)i / data_width - 0.5) + 0.5) + 0.1);
+        double d2 = 0.0;
+        for (int j = 0; j < nbin; j++, k++)
+            if (k >= 0 && k < n) d2 += a[k];
+        a[i] = d2;
+    }
+    for (int i = 0; i < data_width; i++) {
+        double d2 = 20.0 * log10(a[i]) - scale;
+        if (d2 < -200) d2 = -200;
+        else if (d2 > 0) d2 = 0;
+        graph[(size_t)blockIdx.y * data_width + i] = d2;
+    }
+}
+
+// get_multirx_graph: one frame per stream, |X| summed over groups of 8 bins in fftshift order
+__global__ void __launch_bounds__(1024) pan_multirx_kernel(const cd *frames, long stream_stride, int n, const cd *tw, const double *window,
+                                   double scale, double *graph)
+{
+    extern __shared__ double smem_raw[];
+    cd *s = reinterpret_cast<cd *>(smem_raw);
+    const int stream = blockIdx.x;
+    const int lane = threadIdx.x, lanes = blockDim.x;
+    const int half = n >> 1;
+    const cd *src = frames + (size_t)stream * stream_stride;
+    for (int i = lane; i < n; i += lanes) {
+        const cd x = src[i];
+        const double w = window[i];
+        s[i] = make_double2(x.x * w, x.y * w);
+    }
+    __syncthreads();
+    fft_smem(s, n, tw, -1, lane, lanes);
+    for (int p = lane; p < n / 8; p += lanes) {
+        double d1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const cd X = s[(p * 8 + j + half) & (n - 1)];
+            d1 += hypot(X.x, X.y);
+        }
+        double d2 = 20.0 * log10(d1) - scale;
+        if (d2 < -200) d2 = -200;
+        graph[(size_t)stream * (n / 8) + p] = d2;
+    }
+}
+
+struct Panadapter {
+    int S = 0, n = 0;
+    const cd *tw = nullptr;
+    double *d_window = nullptr, *d_avg = nullptr, *d_partial = nullptr;
+    int partial_groups = 0;
+    int count = 0;
+
+    int init(int streams, int fft_size)
+    {
+        S = streams; n = fft_size;
+        if (S <= 0 || fft_log2(n) < 0 || n / fft_threads(n) > PAN_MAX_OWN) {
+            set_error("pan_create: fft_size must be a power of two in [8, 8192] (got %d)", fft_size); return QC_EINVAL;
+        }
+        tw = fft_twiddles(n);
+        if (!tw) { set_error("pan_create: twiddle table allocation failed"); return QC_ENOMEM; }
+        std::vector<double> w((size_t)n);
+        for (int i = 0, j = -n / 2; i < n; i++, j++) w[i] = 0.5 + 0.5 * cos(2. * M_PI * j / n);      // quisk.c:6003-6009
+        QC_CUDA(cudaMalloc((void **)&d_window, (size_t)n * sizeof(double)));
+        QC_CUDA(cudaMemcpy(d_window, w.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        QC_CUDA(cudaMalloc((void **)&d_avg, (size_t)S * n * sizeof(double)));
+        QC_CUDA(cudaMemset(d_avg, 0, (size_t)S * n * sizeof(double)));
+        return QC_OK;
+    }
+    void release()
+    {
+        if (d_window) cudaFree(d_window); if (d_avg) cudaFree(d_avg); if (d_partial) cudaFree(d_partial);
+        d_window = d_avg = d_partial = nullptr;
+    }
+};
+
+static int fft_smem_optin(const void *kern, size_t bytes)
+{
+    if (bytes > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return QC_OK;
+}
+
+}  // namespace qc
+
+using namespace qc;
+
+struct qcPanadapter { qc::Panadapter p; };
+
+extern "C" {
+
+int quisk_cuda_fft_batch(const void *d_in, void *d_out, int n, int batch, int sign, void *stream)
+{
+    if (ensure_device() != QC_OK) return QC_ENODEV;
+    if (fft_log2(n) < 0) { set_error("fft_batch: n must be a power of two in [8, 8192] (got %d)", n); return QC_EINVAL; }
+    if (batch <= 0) return QC_OK;
+    const cd *tw = fft_twiddles(n);
+    if (!tw) { set_error("fft_batch: twiddle table allocation failed"); return QC_ENOMEM; }
+    int lanes, per;
+    fft_shape(n, &lanes, &per);
+    const size_t sh = (size_t)per * n * sizeof(cd);
+    int rc = fft_smem_optin((const void *)fft_batch_kernel, sh); if (rc != QC_OK) return rc;
+    dim3 block(lanes, per);
+    fft_batch_kernel<<<(batch + per - 1) / per, block, sh, (cudaStream_t)stream>>>((const cd *)d_in, (cd *)d_out, n, batch, tw, sign < 0 ? -1 : 1);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+qcPanadapter *quisk_cuda_pan_create(int n_streams, int fft_size)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    qcPanadapter *p = new qcPanadapter();
+    if (p->p.init(n_streams, fft_size) != QC_OK) { p->p.release(); delete p; return nullptr; }
+    return p;
+}
+
+void quisk_cuda_pan_destroy(qcPanadapter *p) { if (p) { p->p.release(); delete p; } }
+int quisk_cuda_pan_count(const qcPanadapter *p) { return p ? p->p.count : QC_EINVAL; }
+const double *quisk_cuda_pan_average_ptr(const qcPanadapter *p) { return p ? p->p.d_avg : nullptr; }
+
+int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long stream_stride, int n_frames, void *stream)
+{
+    if (!pp) { set_error("pan_accumulate: null handle"); return QC_EINVAL; }
+    Panadapter &p = pp->p;
+    if (n_frames <= 0) return QC_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    // enough CTAs to fill the machine, but keep the reference's summation order when streams alone do
+    int groups = 1;
+    if (p.S < 2 * 148) {
+        groups = (2 * 148 + p.S - 1) / p.S;
+        if (groups > n_frames) groups = n_frames;
+        if (groups < 1) groups = 1;
+    }
+    if (groups > 1 && groups > p.partial_groups) {
+        if (p.d_partial) cudaFree(p.d_partial);
+        p.d_partial = nullptr;
+        QC_CUDA(cudaMalloc((void **)&p.d_partial, (size_t)p.S * groups * p.n * sizeof(double)));
+        p.partial_groups = groups;
+    }
+    const int lanes = fft_threads(p.n);
+    const size_t sh = (size_t)p.n * sizeof(cd);
+    int rc = fft_smem_optin((const void *)pan_accumulate_kernel, sh); if (rc != QC_OK) return rc;
+    pan_accumulate_kernel<<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.tw,
+                                                                 p.d_window, p.d_avg, p.d_partial, groups);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    if (groups > 1) {
+        pan_reduce_kernel<<<dim3((p.n + 255) / 256, p.S), 256, 0, s>>>(p.d_avg, p.d_partial, p.n, groups);
+        count_launch();
+        QC_CUDA_LAUNCH();
+    }
+    p.count += n_frames;
+    return QC_OK;
+}
+
+int quisk_cuda_pan_graph(qcPanadapter *pp, int data_width, double zoom, double deltaf, double fft_sample_rate,
+                         double *d_graph, void *stream)
+{
+    if (!pp) { set_error("pan_graph: null handle"); return QC_EINVAL; }
+    Panadapter &p = pp->p;
+    if (p.count <= 0) { set_error("pan_graph: no frames accumulated"); return QC_EINVAL; }
+    if (data_width <= 0 || data_width > p.n) { set_error("pan_graph: data_width %d out of range", data_width); return QC_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = p.n;
+    double scale = log10((double)p.count) + log10((double)n) + 31.0 * log10(2.0);       // quisk.c:5284-5285
+    scale *= 20.0;
+    int nbin = (int)(zoom * (double)n / data_width + 0.5);
+    if (nbin < 1) nbin = 1;
+    // does any pixel read a bin that an earlier pixel has already overwritten? (in-place walk, quisk.c:5289-5301)
+    bool hazard = false;
+    for (int i = 0; i < data_width && !hazard; i++) {
+        int k = (int)(n * (deltaf / fft_sample_rate + zoom * ((double)i / data_width - 0.5) + 0.5) + 0.1);
+        for (int j = 0; j < nbin; j++, k++)
+            if (k >= 0 && k < n && k < i) { hazard = true; break; }
+    }
+    if (!hazard)
+        pan_graph_kernel<<<dim3((data_width + 127) / 128, p.S), 128, 0, s>>>(p.d_avg, n, data_width, nbin, zoom, deltaf, fft_sample_rate, scale, d_graph);
+    else
+        pan_graph_serial_kernel<<<dim3(1, p.S), 32, 0, s>>>(p.d_avg, n, data_width, nbin, zoom, deltaf, fft_sample_rate, scale, d_graph);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    QC_CUDA(cudaMemsetAsync(p.d_avg, 0, (size_t)p.S * n * sizeof(double), s));            // quisk.c:5322-5324
+    p.count = 0;
+    return QC_OK;
+}
+
+int quisk_cuda_pan_multirx(qcPanadapter *pp, const void *d_frames, long stream_stride, double *d_graph, void *stream)
+{
+    if (!pp) { set_error("pan_multirx: null handle"); return QC_EINVAL; }
+    Panadapter &p = pp->p;
+    const int lanes = fft_threads(p.n);
+    const size_t sh = (size_t)p.n * sizeof(cd);
+    int rc = fft_smem_optin((const void *)pan_multirx_kernel, sh); if (rc != QC_OK) return rc;
+    double scale = (log10((double)p.n) + 31.0 * log10(2.0)) * 20.0;                      // quisk.c:4892-4893
+    pan_multirx_kernel<<<p.S, lanes, sh, (cudaStream_t)stream>>>((const cd *)d_frames, stream_stride, p.n, p.tw, p.d_window, scale, d_graph);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// quisk_b200/csrc/pointwise.cu -- per-sample stages of the receive chain that are not FIR
+// filters: the tuning NCO (quisk.c:2477-2488), the SSB/CW sideband combine
+// (quisk.c:1916,1939,1962,1986), the AM envelope detector with DC blocker
+// (quisk.c:2005-2011) and the FM discriminator with one-pole de-emphasis
+// (quisk.c:2029-2064).  Used by the unfused chain; the fused cascade in
+// rxchain.cu has these inlined.
+#include "qc_common.cuh"
+#include "nco_device.cuh"
+
+namespace qc {
+
+__global__ void tune_kernel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C,
+                            const double *nco, unsigned long long n0)
+{
+    const long total = (long)n * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / n);
+        const int j = (int)(idx - (long)c * n);
+        const double *nc = nco + (long)c * 8;
+        const cd w = nco_pow(nc, n0 + (unsigned long long)j);
+        const cd v = cmul_rn(make_double2(nc[3], nc[4]), w);
+        const cd x = in[(long)c * in_stride + j];
+        out[(long)c * out_stride + j] = cmul_rn(x, v);
+    }
+}
+
+int launch_tune(const cd *in, long in_stride, cd *out, long out_stride, int n, int C,
+                const double *d_nco, unsigned long long n0, cudaStream_t s)
+{
+    if (n <= 0 || C <= 0) return QC_OK;
+    const long total = (long)n * C;
+    int blocks = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
+    tune_kernel<<<blocks, 256, 0, s>>>(in, in_stride, out, out_stride, n, C, d_nco, n0);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+__global__ void demod_ssb_kernel(const cd *in, long in_stride, double *out, long out_stride, int n, int C, int lower)
+{
+    const long total = (long)n * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / n);
+        const int j = (int)(idx - (long)c * n);
+        const cd x = in[(long)c * in_stride + j];
+        out[(long)c * out_stride + j] = lower ? __dadd_rn(x.x, x.y) : __dsub_rn(x.x, x.y);
+    }
+}
+
+int launch_demod_ssb(const cd *in, long in_stride, double *out, long out_stride, int n, int C, int lower, cudaStream_t s)
+{
+    if (n <= 0 || C <= 0) return QC_OK;
+    const long total = (long)n * C;
+    int blocks = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
+    demod_ssb_kernel<<<blocks, 256, 0, s>>>(in, in_stride, out, out_stride, n, C, lower);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+// One thread per channel: the DC blocker is a scalar recurrence (d = |x| + 0.99 dc; out = d - dc; dc = d).
+__global__ void am_detect_kernel(const cd *in, long in_stride, double *out, long out_stride, int n, int C, double *dc_state)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double dc = dc_state[c];
+    const cd *x = in + (long)c * in_stride;
+    double *o = out + (long)c * out_stride;
+    for (int i = 0; i < n; i++) {
+        const double di = hypot(x[i].x, x[i].y);
+        const double d = __dadd_rn(di, __dmul_rn(dc, 0.99));
+        o[i] = __dsub_rn(d, dc);
+        dc = d;
+    }
+    dc_state[c] = dc;
+}
+
+int launch_am_detect(const cd *in, long in_stride, double *out, long out_stride, int n, int C, double *d_dc, cudaStream_t s)
+{
+    if (n <= 0 || C <= 0) return QC_OK;
+    am_detect_kernel<<<(C + 63) / 64, 64, 0, s>>>(in, in_stride, out, out_stride, n, C, d_dc);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+// One thread per channel: di = carg(x conj(x_-1)) * 20e5; y = di a0 + x_1 a1 - y_1 b1.
+__global__ void fm_detect_kernel(const cd *in, long in_stride, double *out, long out_stride, int n, int C,
+                                 double *state, double a0, double a1, double b1)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double *st = state + (long)c * 4;
+    cd prev = make_double2(st[0], st[1]);
+    double x1 = st[2], y1 = st[3];
+    const cd *x = in + (long)c * in_stride;
+    double *o = out + (long)c * out_stride;
+    for (int i = 0; i < n; i++) {
+        const cd cx = x[i];
+        // cx * conj(prev)
+        const double re = __dadd_rn(__dmul_rn(cx.x, prev.x), __dmul_rn(cx.y, prev.y));
+        const double im = __dsub_rn(__dmul_rn(cx.y, prev.x), __dmul_rn(cx.x, prev.y));
+        prev = cx;
+        const double di = __dmul_rn(atan2(im, re), 20e5);
+        y1 = __dsub_rn(__dadd_rn(__dmul_rn(di, a0), __dmul_rn(x1, a1)), __dmul_rn(y1, b1));
+        x1 = di;
+        o[i] = y1;
+    }
+    st[0] = prev.x; st[1] = prev.y; st[2] = x1; st[3] = y1;
+}
+
+int launch_fm_detect(const cd *in, long in_stride, double *out, long out_stride, int n, int C,
+                     double *d_state, double a0, double a1, double b1, cudaStream_t s)
+{
+    if (n <= 0 || C <= 0) return QC_OK;
+    fm_detect_kernel<<<(C + 63) / 64, 64, 0, s>>>(in, in_stride, out, out_stride, n, C, d_state, a0, a1, b1);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+}  // namespace qc

@@ -1,0 +1,358 @@
+// quisk_b200/csrc/rxchain.cu -- quisk_cuda_rx_*: the receive chain of quisk_process_samples
+// for a batch of channels: tune (quisk.c:2477-2488) -> quisk_process_decimate
+// (quisk.c:1673-1846, planned by PlanDecimation quisk.c:1633-1671) ->
+// quisk_process_demodulate (quisk.c:1848-2160).
+//
+// Two executions of the same stage graph:
+//   fused = 0  one exact kernel per stage (polyfir.cu / pointwise.cu), intermediates in HBM;
+//   fused = 1  the shared-memory cascade of rxfused.cu for the full-rate decimator
+//              (one CTA streams one channel through every half band and FIR without
+//              touching HBM in between), exact per-stage kernels for the 48 kS/s tail.
+#include "qc_common.cuh"
+#include "batch.h"
+#include "rxchain.h"
+#include <cmath>
+
+namespace qc {
+
+int plan_decimation(int sample_rate, int *p2, int *p3, int *p5)
+{   // PlanDecimation, quisk.c:1633-1671
+    int best = sample_rate, d2 = 0, d3 = 0, d5 = 0;
+    for (int i2 = 0; i2 <= 6; i2++)
+        for (int i3 = 0; i3 <= 3; i3++)
+            for (int i5 = 0; i5 <= 3; i5++) {
+                int t = sample_rate;
+                for (int i = 0; i < i2; i++) t /= 2;
+                for (int i = 0; i < i3; i++) t /= 3;
+                for (int i = 0; i < i5; i++) t /= 5;
+                if (t >= 48000 && t < best) { d2 = i2; d3 = i3; d5 = i5; best = t; }
+            }
+    if (best >= 50000) best = best * 24 / 25;
+    if (p2) { *p2 = d2; *p3 = d3; *p5 = d5; }
+    return best;
+}
+
+static BatchFilter *mk(int kind, int C, const double *coefs, int n, int interp, int decim)
+{
+    if (kind != QC_C_DECIM2_HB45 && kind != QC_C_INTERP2_HB45 && kind != QC_D_INTERP2_HB45 && (coefs == nullptr || n <= 0)) {
+        set_error("rx_create: a coefficient table this sample rate / mode needs was not supplied");
+        return nullptr;
+    }
+    BatchFilter *f = new BatchFilter();
+    if (f->init(kind, C, coefs, n, interp, decim) != QC_OK) { f->release(); delete f; return nullptr; }
+    return f;
+}
+
+#define ADD(vec, expr) do { BatchFilter *_f = (expr); if (!_f) return QC_EINVAL; (vec).push_back(_f); } while (0)
+
+int RxChain::init(const qcRxConfig &cfg)
+{
+    C = cfg.n_channels; sample_rate = cfg.sample_rate; mode = cfg.mode; fused = cfg.fused;
+    if (C <= 0 || sample_rate <= 0) { set_error("rx_create: bad channel count / sample rate"); return QC_EINVAL; }
+    const qcRxTables &T = cfg.tables;
+    // ---- quisk_process_decimate -------------------------------------------------
+    int rate = sample_rate;
+    switch ((sample_rate + 100) / 1000) {       // quisk.c:1731
+    case 41: rate = 48000; break;
+    case 53: ADD(cst, mk(QC_C_DECIMATE, C, T.filt53D1, T.n_filt53D1, 1, 1)); break;
+    case 111: ADD(cst, mk(QC_C_DECIMATE, C, T.filt111D2, T.n_filt111D2, 1, 2)); rate /= 2; break;
+    case 133: ADD(cst, mk(QC_C_DECIMATE, C, T.filt133D2, T.n_filt133D2, 1, 2)); rate /= 2; break;
+    case 185: ADD(cst, mk(QC_C_DECIMATE, C, T.filt185D3, T.n_filt185D3, 1, 3)); rate /= 3; break;
+    case 370:
+        ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+        ADD(cst, mk(QC_C_DECIMATE, C, T.filt185D3, T.n_filt185D3, 1, 3)); rate /= 6; break;
+    case 740:
+        ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+        ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+        ADD(cst, mk(QC_C_DECIMATE, C, T.filt185D3, T.n_filt185D3, 1, 3)); rate /= 12; break;
+    case 1333:
+        for (int i = 0; i < 3; i++) ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+        ADD(cst, mk(QC_C_DECIMATE, C, T.filt167D3, T.n_filt167D3, 1, 3)); rate /= 24; break;
+    default: {
+        int d2, d3, d5;
+        plan_decimation(sample_rate, &d2, &d3, &d5);
+        int i2 = d2, nhb = 0;
+        while (i2 > 1 && nhb < 5) { ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1)); rate /= 2; i2--; nhb++; }
+        for (int i = 0; i < d3; i++) { ADD(cst, mk(QC_C_DECIMATE, C, T.filt144D3, T.n_filt144D3, 1, 3)); rate /= 3; }
+        for (int i = 0; i < d5; i++) { ADD(cst, mk(QC_C_DECIMATE, C, T.filt240D5Sharp, T.n_filt240D5Sharp, 1, 5)); rate /= 5; }
+        if (i2 > 0) { ADD(cst, mk(QC_C_DECIMATE, C, T.filt48dec24, T.n_filt48dec24, 1, 2)); rate /= 2; }
+        if (rate >= 50000) {                    // quisk.c:1834-1838
+            rate = rate * 24 / 25;
+            ADD(cst, mk(QC_C_INTERPDECIM, C, T.filt300D5, T.n_filt300D5, 6, 5));
+            ADD(cst, mk(QC_C_INTERPDECIM, C, T.filt240D5Sharp, T.n_filt240D5Sharp, 4, 5));
+        }
+    } }
+    decim_srate = rate;
+    n_decim_stages = (int)cst.size();
+    // ---- quisk_process_demodulate ------------------------------------------------
+    if (cfg.n_filt <= 0 || !cfg.filt_i) { set_error("rx_create: receive filter taps missing"); return QC_EINVAL; }
+    std::vector<double> iq((size_t)2 * cfg.n_filt);
+    for (int i = 0; i < cfg.n_filt; i++) { iq[i] = cfg.filt_i[i]; iq[cfg.n_filt + i] = cfg.filt_q ? cfg.filt_q[i] : cfg.filt_i[i]; }
+    switch (mode) {
+    case QC_MODE_CWL: case QC_MODE_CWU:         // quisk.c:1909-1955
+        filter_srate = decim_srate / 8;
+        ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+        ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+        ADD(cst, mk(QC_C_DECIMATE, C, T.filt48dec24, T.n_filt48dec24, 1, 2));
+        rxf = mk(QC_C_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
+        ADD(rst, mk(QC_D_INTERPOLATE, C, T.audio24p4, T.n_audio24p4, 2, 1));
+        ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+        ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+        break;
+    case QC_MODE_LSB: case QC_MODE_USB:         // quisk.c:1956-2001
+        filter_srate = decim_srate / 4;
+        ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+        ADD(cst, mk(QC_C_DECIMATE, C, T.filt48dec24, T.n_filt48dec24, 1, 2));
+        rxf = mk(QC_C_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
+        ADD(rst, mk(QC_D_INTERPOLATE, C, T.audio24p4, T.n_audio24p4, 2, 1));
+        ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+        break;
+    case QC_MODE_AM:                            // quisk.c:2002-2026
+        filter_srate = decim_srate / 2;
+        ADD(cst, mk(QC_C_DECIMATE, C, T.filt48dec24, T.n_filt48dec24, 1, 2));
+        rxf = mk(QC_D_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
+        ADD(rst, mk(QC_D_DECIMATE, C, T.audio24p6, T.n_audio24p6, 1, 1));
+        ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+        QC_CUDA(cudaMalloc((void **)&d_dc, (size_t)C * sizeof(double)));
+        QC_CUDA(cudaMemset(d_dc, 0, (size_t)C * sizeof(double)));
+        break;
+    case QC_MODE_FM: {                          // quisk.c:2027-2090
+        filter_srate = decim_srate;
+        rxf = mk(QC_D_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
+        ADD(rst, mk(QC_D_DECIMATE, C, T.lpFilt48, T.n_lpFilt48, 1, 4));
+        ADD(rst, mk(QC_D_DECIMATE, C, T.audioFmHp, T.n_audioFmHp, 1, 1));
+        ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+        ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+        const double www = tan(M_PI * 300.0 / 48000);       // FM_FILTER_DEMPH, quisk.c:46,1895-1899
+        const double nnn = 1.0 / (1.0 + www);
+        fm_a0 = www * nnn; fm_a1 = fm_a0; fm_b1 = nnn * (www - 1.0);
+        QC_CUDA(cudaMalloc((void **)&d_fm, (size_t)C * 4 * sizeof(double)));
+        { int rcf = reset_fm(); if (rcf != QC_OK) return rcf; }
+        break; }
+    default:
+        set_error("rx_create: mode %d is not on the accelerated path", mode); return QC_EINVAL;
+    }
+    if (!rxf) return QC_EINVAL;
+    // ---- tuning NCO ----------------------------------------------------------------
+    if (cfg.tune_hz) {
+        tune_hz.assign(cfg.tune_hz, cfg.tune_hz + C);
+        bool any = false;
+        for (double t : tune_hz) any = any || t != 0.0;
+        tune = any;
+        if (tune) {
+            QC_CUDA(cudaMalloc((void **)&d_nco, (size_t)C * 8 * sizeof(double)));
+            int rc = upload_nco(); if (rc != QC_OK) return rc;
+        }
+    }
+    return QC_OK;
+}
+
+int RxChain::reset_fm()
+{
+    std::vector<double> st((size_t)C * 4, 0.0);
+    for (int c = 0; c < C; c++) st[(size_t)c * 4] = 10.0;         // fm_1 = 10, quisk.c:1893
+    QC_CUDA(cudaMemcpy(d_fm, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return QC_OK;
+}
+
+int RxChain::upload_nco()
+{
+    std::vector<double> h((size_t)C * 8);
+    for (int c = 0; c < C; c++) nco_make(tune_hz[c], sample_rate, 1.0, 0.0, &h[(size_t)c * 8]);
+    QC_CUDA(cudaMemcpy(d_nco, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    n_base = 0;
+    return QC_OK;
+}
+
+void RxChain::release()
+{
+    for (auto *f : cst) { f->release(); delete f; }
+    for (auto *f : rst) { f->release(); delete f; }
+    if (rxf) { rxf->release(); delete rxf; }
+    cst.clear(); rst.clear(); rxf = nullptr;
+    for (int i = 0; i < 2; i++) { if (bufc[i]) cudaFree(bufc[i]); if (bufr[i]) cudaFree(bufr[i]); bufc[i] = nullptr; bufr[i] = nullptr; }
+    if (d_nco) cudaFree(d_nco); if (d_dc) cudaFree(d_dc); if (d_fm) cudaFree(d_fm);
+    if (h_pin) cudaFreeHost(h_pin); if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out);
+    d_nco = d_dc = d_fm = nullptr; h_pin = nullptr; d_host_in = nullptr; d_host_out = nullptr;
+    release_fused();
+}
+
+int RxChain::reserve(int count)
+{
+    const long need = (long)count + 64;
+    if (need <= cap) return QC_OK;
+    for (int i = 0; i < 2; i++) {
+        if (bufc[i]) cudaFree(bufc[i]); if (bufr[i]) cudaFree(bufr[i]);
+        bufc[i] = nullptr; bufr[i] = nullptr;
+    }
+    cap = need;
+    // complex scratch only has to hold what follows the first decimating stage when the
+    // input itself is never copied (no tuning); keep it simple and size for the block.
+    for (int i = 0; i < 2; i++) {
+        QC_CUDA(cudaMalloc((void **)&bufc[i], (size_t)C * cap * sizeof(cd)));
+        QC_CUDA(cudaMalloc((void **)&bufr[i], (size_t)C * cap * sizeof(double)));
+    }
+    return QC_OK;
+}
+
+int RxChain::max_out(int count) const
+{
+    // every stage at worst keeps ceil() of its ratio; the audio side multiplies by <= 8
+    double n = count;
+    for (auto *f : cst) {
+        switch (f->kind) {
+        case QC_C_DECIM2_HB45: n = n / 2 + 1; break;
+        case QC_C_INTERPDECIM: n = n * f->interp / f->decim + 2; break;
+        default: n = n / f->decim + 1; break;
+        }
+    }
+    for (auto *f : rst) {
+        switch (f->kind) {
+        case QC_D_INTERPOLATE: n = n * f->interp; break;
+        case QC_D_INTERP2_HB45: n = n * 2; break;
+        default: n = n / f->decim + 1; break;
+        }
+    }
+    return (int)n + 8;
+}
+
+int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audio, long audio_stride, int *n_audio,
+                     void *d_decim, long decim_stride, int *n_decim, cudaStream_t s)
+{
+    if (count < 0) { set_error("rx_process: negative count"); return QC_EINVAL; }
+    if (n_audio) *n_audio = 0;
+    if (n_decim) *n_decim = 0;
+    if (count == 0) return QC_OK;
+    int rc = reserve(count); if (rc != QC_OK) return rc;
+
+    const cd *cur = (const cd *)d_iq; long stride = iq_stride; int n = count; int pp = 0;
+    size_t first_stage = 0;
+    if (fused && fused_applicable()) {
+        rc = run_fused_decimator(cur, stride, count, bufc[0], cap, &n, s); if (rc != QC_OK) return rc;
+        cur = bufc[0]; stride = cap; pp = 1; first_stage = n_fused_stages;
+        if (tune) n_base += (unsigned long long)count;
+    } else if (tune) {
+        rc = launch_tune(cur, stride, bufc[0], cap, n, C, d_nco, n_base, s); if (rc != QC_OK) return rc;
+        n_base += (unsigned long long)count;
+        cur = bufc[0]; stride = cap; pp = 1;
+    }
+    for (size_t i = first_stage; i < cst.size(); i++) {
+        if ((int)i == n_decim_stages && d_decim) {
+            QC_CUDA(cudaMemcpy2DAsync(d_decim, (size_t)decim_stride * sizeof(cd), cur, (size_t)stride * sizeof(cd),
+                                      (size_t)n * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
+            if (n_decim) *n_decim = n;
+        }
+        int no = 0;
+        rc = cst[i]->run(cur, stride, n, bufc[pp], cap, &no, 0, s); if (rc != QC_OK) return rc;
+        cur = bufc[pp]; stride = cap; pp ^= 1; n = no;
+    }
+    if ((int)cst.size() == n_decim_stages && d_decim) {
+        QC_CUDA(cudaMemcpy2DAsync(d_decim, (size_t)decim_stride * sizeof(cd), cur, (size_t)stride * sizeof(cd),
+                                  (size_t)n * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
+        if (n_decim) *n_decim = n;
+    }
+    // main receive filter
+    int no = 0;
+    rc = rxf->run(cur, stride, n, bufc[pp], cap, &no, 0, s); if (rc != QC_OK) return rc;
+    cur = bufc[pp]; n = no;
+    // detector -> real audio at the filter rate
+    double *rcur = bufr[0]; int rp = 1;
+    switch (mode) {
+    case QC_MODE_CWL: case QC_MODE_LSB: rc = launch_demod_ssb(cur, cap, rcur, cap, n, C, 1, s); break;
+    case QC_MODE_CWU: case QC_MODE_USB: rc = launch_demod_ssb(cur, cap, rcur, cap, n, C, 0, s); break;
+    case QC_MODE_AM: rc = launch_am_detect(cur, cap, rcur, cap, n, C, d_dc, s); break;
+    case QC_MODE_FM: rc = launch_fm_detect(cur, cap, rcur, cap, n, C, d_fm, fm_a0, fm_a1, fm_b1, s); break;
+    }
+    if (rc != QC_OK) return rc;
+    // audio stages; the last one writes straight into the caller's buffer
+    for (size_t i = 0; i < rst.size(); i++) {
+        const bool last = i + 1 == rst.size();
+        double *dst = last ? d_audio : bufr[rp];
+        const long dstride = last ? audio_stride : cap;
+        if (last && audio_stride < rst[i]->count_out(n, 0)) { set_error("rx_process: audio_stride too small"); return QC_EINVAL; }
+        rc = rst[i]->run(rcur, (rcur == d_audio) ? audio_stride : cap, n, dst, dstride, &no, 0, s); if (rc != QC_OK) return rc;
+        rcur = dst; rp ^= 1; n = no;
+    }
+    if (n_audio) *n_audio = n;
+    return QC_OK;
+}
+
+int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, double *h_audio, long audio_stride, int *n_audio)
+{
+    if (count <= 0) { if (n_audio) *n_audio = 0; return QC_OK; }
+    if (!hs) QC_CUDA(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
+    const int mo = max_out(count);
+    if (count > host_cap) {
+        if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out); if (h_pin) cudaFreeHost(h_pin);
+        d_host_in = nullptr; d_host_out = nullptr; h_pin = nullptr;
+        host_cap = count; host_out_cap = mo;
+        QC_CUDA(cudaMalloc((void **)&d_host_in, (size_t)C * host_cap * sizeof(cd)));
+        QC_CUDA(cudaMalloc((void **)&d_host_out, (size_t)C * host_out_cap * sizeof(double)));
+    }
+    // H2D straight from the caller's memory (pinned by the caller or pageable), row by row layout kept
+    QC_CUDA(cudaMemcpy2DAsync(d_host_in, (size_t)host_cap * sizeof(cd), h_iq, (size_t)iq_stride * sizeof(cd),
+                              (size_t)count * sizeof(cd), C, cudaMemcpyHostToDevice, hs));
+    int na = 0;
+    int rc = process(d_host_in, host_cap, count, d_host_out, host_out_cap, &na, nullptr, 0, nullptr, hs);
+    if (rc != QC_OK) return rc;
+    if (na > audio_stride) { set_error("rx_process_host: audio_stride %ld < %d", audio_stride, na); return QC_EINVAL; }
+    if (na > 0)
+        QC_CUDA(cudaMemcpy2DAsync(h_audio, (size_t)audio_stride * sizeof(double), d_host_out, (size_t)host_out_cap * sizeof(double),
+                                  (size_t)na * sizeof(double), C, cudaMemcpyDeviceToHost, hs));
+    QC_CUDA(cudaStreamSynchronize(hs));
+    if (n_audio) *n_audio = na;
+    return QC_OK;
+}
+
+int RxChain::reset()
+{
+    for (auto *f : cst) { int rc = f->reset(nullptr); if (rc != QC_OK) return rc; }
+    for (auto *f : rst) { int rc = f->reset(nullptr); if (rc != QC_OK) return rc; }
+    int rc = rxf->reset(nullptr); if (rc != QC_OK) return rc;
+    if (d_dc) QC_CUDA(cudaMemset(d_dc, 0, (size_t)C * sizeof(double)));
+    if (d_fm) { rc = reset_fm(); if (rc != QC_OK) return rc; }
+    if (tune) { rc = upload_nco(); if (rc != QC_OK) return rc; }
+    rc = reset_fused(); if (rc != QC_OK) return rc;
+    QC_CUDA(cudaDeviceSynchronize());
+    return QC_OK;
+}
+
+}  // namespace qc
+
+struct qcRxChain { qc::RxChain rx; };
+
+extern "C" {
+
+int quisk_cuda_plan_decimation(int sample_rate, int *d2, int *d3, int *d5) { return qc::plan_decimation(sample_rate, d2, d3, d5); }
+
+qcRxChain *quisk_cuda_rx_create(const struct qcRxConfig *cfg)
+{
+    if (!cfg) { qc::set_error("rx_create: null config"); return nullptr; }
+    if (qc::ensure_device() != QC_OK) return nullptr;
+    qcRxChain *r = new qcRxChain();
+    if (r->rx.init(*cfg) != QC_OK) { r->rx.release(); delete r; return nullptr; }
+    return r;
+}
+
+void quisk_cuda_rx_destroy(qcRxChain *rx) { if (rx) { rx->rx.release(); delete rx; } }
+int quisk_cuda_rx_decim_srate(const qcRxChain *rx) { return rx ? rx->rx.decim_srate : QC_EINVAL; }
+int quisk_cuda_rx_filter_srate(const qcRxChain *rx) { return rx ? rx->rx.filter_srate : QC_EINVAL; }
+int quisk_cuda_rx_max_out(const qcRxChain *rx, int count) { return rx ? rx->rx.max_out(count) : QC_EINVAL; }
+
+int quisk_cuda_rx_process(qcRxChain *rx, const void *d_iq, long iq_stride, int count, double *d_audio, long audio_stride,
+                          int *n_audio, void *d_decim, long decim_stride, int *n_decim, void *stream)
+{
+    if (!rx) { qc::set_error("rx_process: null chain"); return QC_EINVAL; }
+    return rx->rx.process(d_iq, iq_stride, count, d_audio, audio_stride, n_audio, d_decim, decim_stride, n_decim, (cudaStream_t)stream);
+}
+
+int quisk_cuda_rx_process_host(qcRxChain *rx, const quisk_cd *h_iq, long iq_stride, int count, double *h_audio,
+                               long audio_stride, int *n_audio)
+{
+    if (!rx) { qc::set_error("rx_process_host: null chain"); return QC_EINVAL; }
+    return rx->rx.process_host(h_iq, iq_stride, count, h_audio, audio_stride, n_audio);
+}
+
+int quisk_cuda_rx_reset(qcRxChain *rx) { return rx ? rx->rx.reset() : QC_EINVAL; }
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// quisk_b200/csrc/rxchain.h -- internal: batched receive chain object (see rxchain.cu, rxfused.cu)
+#pragma once
+#include "qc_common.cuh"
+#include "batch.h"
+
+namespace qc {
+
+int plan_decimation(int sample_rate, int *p2, int *p3, int *p5);
+
+struct FusedDecimator;      // rxfused.cu
+
+struct RxChain {
+    int C = 0, sample_rate = 0, mode = 0, fused = 0;
+    int decim_srate = 0, filter_srate = 0;
+    std::vector<BatchFilter *> cst;     // complex stages: process_decimate then the demod pre-filters
+    int n_decim_stages = 0;             // how many of cst belong to quisk_process_decimate
+    BatchFilter *rxf = nullptr;         // cRxFilterOut / dRxFilterOut
+    std::vector<BatchFilter *> rst;     // real audio stages after the detector
+    // tuning NCO
+    bool tune = false;
+    std::vector<double> tune_hz;
+    double *d_nco = nullptr;
+    unsigned long long n_base = 0;      // samples since the NCO constants were (re)based
+    // detectors
+    double *d_dc = nullptr, *d_fm = nullptr;
+    double fm_a0 = 0, fm_a1 = 0, fm_b1 = 0;
+    // scratch
+    cd *bufc[2] = {nullptr, nullptr};
+    double *bufr[2] = {nullptr, nullptr};
+    long cap = 0;
+    // host-buffer entry point
+    cudaStream_t hs = nullptr;
+    char *h_pin = nullptr;
+    cd *d_host_in = nullptr; double *d_host_out = nullptr;
+    int host_cap = 0, host_out_cap = 0;
+    // fused full-rate decimator
+    FusedDecimator *fd = nullptr;
+    size_t n_fused_stages = 0;
+
+    int init(const qcRxConfig &cfg);
+    void release();
+    int reserve(int count);
+    int max_out(int count) const;
+    int reset_fm();
+    int upload_nco();
+    int process(const void *d_iq, long iq_stride, int count, double *d_audio, long audio_stride, int *n_audio,
+                void *d_decim, long decim_stride, int *n_decim, cudaStream_t s);
+    int process_host(const quisk_cd *h_iq, long iq_stride, int count, double *h_audio, long audio_stride, int *n_audio);
+    int reset();
+    // rxfused.cu
+    bool fused_applicable();
+    int run_fused_decimator(const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t s);
+    int reset_fused();
+    void release_fused();
+};
+
+}  // namespace qc

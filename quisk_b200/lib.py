@@ -1,0 +1,100 @@
+"""quisk_b200/lib.py -- ctypes loader and prototypes for libquisk_cuda.so (include/quisk_cuda.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libquisk_cuda.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class QuiskCudaError(RuntimeError):
+    pass
+
+
+class RxTables(C.Structure):        # struct qcRxTables
+    _names = ["filt144D3", "filt240D5Sharp", "filt48dec24", "filt300D5", "audio24p4", "audio24p6",
+              "lpFilt48", "audioFmHp", "filt53D1", "filt111D2", "filt133D2", "filt167D3", "filt185D3"]
+    _fields_ = sum(([(n, c_double_p), ("n_" + n, C.c_int)] for n in _names), [])
+
+
+class RxConfig(C.Structure):        # struct qcRxConfig
+    _fields_ = [("n_channels", C.c_int), ("sample_rate", C.c_int), ("mode", C.c_int),
+                ("filt_i", c_double_p), ("filt_q", c_double_p), ("n_filt", C.c_int),
+                ("tune_hz", c_double_p), ("tables", RxTables), ("fused", C.c_int)]
+
+
+# qcRxTables field -> the reference's table name in filters.h
+TABLE_NAMES = {
+    "filt144D3": "quiskFilt144D3Coefs", "filt240D5Sharp": "quiskFilt240D5CoefsSharp",
+    "filt48dec24": "quiskFilt48dec24Coefs", "filt300D5": "quiskFilt300D5Coefs",
+    "audio24p4": "quiskAudio24p4Coefs", "audio24p6": "quiskAudio24p6Coefs",
+    "lpFilt48": "quiskLpFilt48Coefs", "audioFmHp": "quiskAudioFmHpCoefs",
+    "filt53D1": "quiskFilt53D1Coefs", "filt111D2": "quiskFilt111D2Coefs",
+    "filt133D2": "quiskFilt133D2Coefs", "filt167D3": "quiskFilt167D3Coefs",
+    "filt185D3": "quiskFilt185D3Coefs",
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libquisk_cuda.so and declare the quisk_cuda_* prototypes.  Raises
+    QuiskCudaError when the library has not been built -- there is nothing to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QuiskCudaError(f"{LIB_PATH} not found: run `python -m quisk_b200.build` (nvcc, sm_100a)")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.quisk_cuda_last_error.restype = C.c_char_p
+    lib.quisk_cuda_version.restype = C.c_char_p
+    lib.quisk_cuda_launch_count.restype = C.c_ulonglong
+    lib.quisk_cuda_set_device.argtypes = [C.c_int]
+    lib.quisk_cuda_batch_create.argtypes = [C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, C.c_int]
+    lib.quisk_cuda_batch_create.restype = vp
+    lib.quisk_cuda_batch_destroy.argtypes = [vp]
+    lib.quisk_cuda_batch_destroy.restype = None
+    lib.quisk_cuda_batch_count_out.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_batch_run.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p, C.c_int, vp]
+    lib.quisk_cuda_batch_reset.argtypes = [vp, vp]
+    lib.quisk_cuda_plan_decimation.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p]
+    lib.quisk_cuda_rx_create.argtypes = [C.POINTER(RxConfig)]
+    lib.quisk_cuda_rx_create.restype = vp
+    lib.quisk_cuda_rx_destroy.argtypes = [vp]
+    lib.quisk_cuda_rx_destroy.restype = None
+    lib.quisk_cuda_rx_decim_srate.argtypes = [vp]
+    lib.quisk_cuda_rx_filter_srate.argtypes = [vp]
+    lib.quisk_cuda_rx_max_out.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rx_process.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p, vp, C.c_long, c_int_p, vp]
+    lib.quisk_cuda_rx_process_host.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p]
+    lib.quisk_cuda_rx_reset.argtypes = [vp]
+    lib.quisk_cuda_pan_create.argtypes = [C.c_int, C.c_int]
+    lib.quisk_cuda_pan_create.restype = vp
+    lib.quisk_cuda_pan_destroy.argtypes = [vp]
+    lib.quisk_cuda_pan_destroy.restype = None
+    lib.quisk_cuda_pan_accumulate.argtypes = [vp, vp, C.c_long, C.c_int, vp]
+    lib.quisk_cuda_pan_graph.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, vp, vp]
+    lib.quisk_cuda_pan_multirx.argtypes = [vp, vp, C.c_long, vp, vp]
+    lib.quisk_cuda_pan_count.argtypes = [vp]
+    lib.quisk_cuda_pan_average_ptr.argtypes = [vp]
+    lib.quisk_cuda_pan_average_ptr.restype = vp
+    lib.quisk_cuda_fft_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    _lib = lib
+    return lib
+
+
+def check(lib: C.CDLL, rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise QuiskCudaError(f"{what}: rc={rc}: {lib.quisk_cuda_last_error().decode()}")
+
+
+def require_device(lib: C.CDLL | None = None) -> C.CDLL:
+    lib = lib or load()
+    if lib.quisk_cuda_device_count() <= 0:
+        raise QuiskCudaError("no CUDA device visible: libquisk_cuda has no CPU fallback")
+    return lib

@@ -1,0 +1,119 @@
+"""quisk_b200/rx.py -- thin Python handles over the batched C ABI (quisk_cuda_batch_*,
+quisk_cuda_rx_*, quisk_cuda_pan_*).  Device buffers are passed as raw integer pointers
+(e.g. torch.Tensor.data_ptr()), streams as integer cudaStream_t handles."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+
+MODES = {"CWL": 0, "CWU": 1, "LSB": 2, "USB": 3, "AM": 4, "FM": 5}     # quisk.h:56-70
+KINDS = {"cDecim2HB45": 1, "cDecimate": 2, "cCDecimate": 3, "dDecimate": 4, "cInterpolate": 5,
+         "dInterpolate": 6, "cInterpDecim": 7, "cInterp2HB45": 8, "dInterp2HB45": 9,
+         "cRxFilter": 10, "dRxFilter": 11}
+
+
+def _dp(a):
+    return a.ctypes.data_as(L.c_double_p)
+
+
+class BatchFilter:
+    """quisk_cuda_batch_*: one filter.h filter for n_channels streams, state in HBM."""
+
+    def __init__(self, kind: str, n_channels: int, coefs=None, interp: int = 1, decim: int = 1):
+        self.lib = L.require_device()
+        self.kind = kind
+        if coefs is None:
+            c = np.zeros(1); ntaps = 0
+        elif kind == "cCDecimate":
+            cc = np.ascontiguousarray(coefs, dtype=np.complex128); ntaps = len(cc)
+            c = cc.view(np.float64)
+        elif kind == "cRxFilter":
+            fi, fq = coefs
+            c = np.ascontiguousarray(np.concatenate([fi, fq]), dtype=np.float64); ntaps = len(fi)
+        else:
+            c = np.ascontiguousarray(coefs, dtype=np.float64); ntaps = len(c)
+        self.h = self.lib.quisk_cuda_batch_create(KINDS[kind], n_channels, _dp(c), ntaps, interp, decim)
+        if not self.h:
+            raise L.QuiskCudaError("batch_create: " + self.lib.quisk_cuda_last_error().decode())
+
+    def count_out(self, count: int) -> int:
+        return self.lib.quisk_cuda_batch_count_out(self.h, count)
+
+    def run(self, d_in: int, in_stride: int, count: int, d_out: int, out_stride: int, legacy_clip: int = 0, stream: int = 0) -> int:
+        n = C.c_int(0)
+        L.check(self.lib, self.lib.quisk_cuda_batch_run(self.h, d_in, in_stride, count, d_out, out_stride, C.byref(n), legacy_clip, stream), "batch_run")
+        return n.value
+
+    def close(self):
+        if self.h:
+            self.lib.quisk_cuda_batch_destroy(self.h); self.h = None
+
+    __del__ = close
+
+
+class RxChain:
+    """quisk_cuda_rx_*: tune -> quisk_process_decimate -> quisk_process_demodulate for a batch."""
+
+    def __init__(self, n_channels: int, sample_rate: int, mode: str, filt_i, filt_q, tables: dict,
+                 tune_hz=None, fused: bool = True):
+        self.lib = L.require_device()
+        self._keep = []
+        cfg = L.RxConfig()
+        cfg.n_channels = n_channels; cfg.sample_rate = sample_rate; cfg.mode = MODES[mode]; cfg.fused = int(fused)
+        fi = np.ascontiguousarray(filt_i, dtype=np.float64); fq = np.ascontiguousarray(filt_q, dtype=np.float64)
+        self._keep += [fi, fq]
+        cfg.filt_i = _dp(fi); cfg.filt_q = _dp(fq); cfg.n_filt = len(fi)
+        if tune_hz is not None:
+            t = np.ascontiguousarray(np.broadcast_to(np.asarray(tune_hz, dtype=np.float64), (n_channels,)))
+            self._keep.append(t); cfg.tune_hz = _dp(t)
+        for field, ref_name in L.TABLE_NAMES.items():
+            if ref_name in tables:
+                a = np.ascontiguousarray(tables[ref_name], dtype=np.float64)
+                self._keep.append(a)
+                setattr(cfg.tables, field, _dp(a)); setattr(cfg.tables, "n_" + field, len(a))
+        self.n_channels = n_channels
+        self.h = self.lib.quisk_cuda_rx_create(C.byref(cfg))
+        if not self.h:
+            raise L.QuiskCudaError("rx_create: " + self.lib.quisk_cuda_last_error().decode())
+
+    @property
+    def decim_srate(self): return self.lib.quisk_cuda_rx_decim_srate(self.h)
+
+    @property
+    def filter_srate(self): return self.lib.quisk_cuda_rx_filter_srate(self.h)
+
+    def max_out(self, count: int) -> int: return self.lib.quisk_cuda_rx_max_out(self.h, count)
+
+    def process(self, d_iq: int, iq_stride: int, count: int, d_audio: int, audio_stride: int,
+                d_decim: int = 0, decim_stride: int = 0, stream: int = 0):
+        na, nd = C.c_int(0), C.c_int(0)
+        L.check(self.lib, self.lib.quisk_cuda_rx_process(self.h, d_iq, iq_stride, count, d_audio, audio_stride, C.byref(na),
+                                                         d_decim or None, decim_stride, C.byref(nd), stream), "rx_process")
+        return na.value, nd.value
+
+    def process_host(self, h_iq: np.ndarray, count: int, h_audio: np.ndarray) -> int:
+        na = C.c_int(0)
+        L.check(self.lib, self.lib.quisk_cuda_rx_process_host(self.h, h_iq.ctypes.data, h_iq.strides[0] // 16, count,
+                                                              h_audio.ctypes.data, h_audio.strides[0] // 8, C.byref(na)), "rx_process_host")
+        return na.value
+
+    def reset(self): L.check(self.lib, self.lib.quisk_cuda_rx_reset(self.h), "rx_reset")
+
+    def close(self):
+        if self.h:
+            self.lib.quisk_cuda_rx_destroy(self.h); self.h = None
+
+    __del__ = close
+
+
+def load_tables(path: str | None = None) -> dict:
+    """The reference's coefficient tables (filters.h) and prototype filters (filters.py) as
+    extracted from the compiled reference into tests/golden/quisk_tables.npz.  In a drop-in
+    build the caller links the reference's own filters.h instead."""
+    import os
+    path = path or os.path.join(os.path.dirname(L.HERE), "tests", "golden", "quisk_tables.npz")
+    z = np.load(path)
+    return {k: z[k] for k in z.files}

@@ -1,0 +1,186 @@
+"""GPU parity of the batched device-resident filters (quisk_cuda_batch_*) and the batched
+receive chain (quisk_cuda_rx_*), through the C ABI, against the fixtures and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import quisk_oracle as O
+from tests.golden.make_golden import RATES, DEMOD_TAPS, demod_taps
+from tests.util import SPLITS, CHAIN_SPLITS, DEMOD_SPLITS, golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def tabs():
+    return golden("quisk_tables.npz")
+
+
+def _run_batch(torch, bf, x, splits, out_cap, real_out=None):
+    """x: [C, n] numpy; returns [C, n_out] numpy and per-block counts."""
+    C = x.shape[0]
+    d_in = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    cplx = x.dtype == np.complex128
+    outs, counts, pos = [], [], 0
+    for n in splits:
+        blk = d_in[:, pos:pos + n].contiguous(); pos += n
+        out = torch.zeros((C, out_cap), dtype=torch.complex128 if cplx else torch.float64, device="cuda")
+        k = bf.run(blk.data_ptr(), blk.stride(0) if n else 1, n, out.data_ptr(), out_cap)
+        torch.cuda.synchronize()
+        outs.append(out[:, :k].cpu().numpy()); counts.append(k)
+    return np.concatenate(outs, axis=1), counts
+
+
+BATCH_CASES = [
+    ("cDecim2HB45", None, 1, 1, False),
+    ("cDecimate", "quiskFilt48dec24Coefs", 1, 2, False),
+    ("cDecimate", "quiskFilt240D5CoefsSharp", 1, 5, False),
+    ("dDecimate", "quiskLpFilt48Coefs", 1, 4, True),
+    ("cInterpolate", "quiskAudio24p4Coefs", 2, 1, False),
+    ("dInterpolate", "quiskAudio24p3Coefs", 3, 1, True),
+    ("cInterpDecim", "quiskFilt300D5Coefs", 6, 5, False),
+    ("cInterpDecim", "quiskFilt240D5CoefsSharp", 4, 5, False),
+    ("cInterp2HB45", None, 1, 1, False),
+    ("dInterp2HB45", None, 1, 1, True),
+]
+
+
+def _oracle_for(kind, tab, interp, decim, real):
+    dt = np.float64 if real else np.complex128
+    return {"cDecim2HB45": lambda: O.HB45Decim(), "cDecimate": lambda: O.FirDecim(tab, decim),
+            "dDecimate": lambda: O.FirDecim(tab, decim, np.float64), "cInterpolate": lambda: O.FirInterp(tab, interp),
+            "dInterpolate": lambda: O.FirInterp(tab, interp, np.float64),
+            "cInterpDecim": lambda: O.FirInterpDecim(tab, interp, decim),
+            "cInterp2HB45": lambda: O.HB45Interp(np.complex128), "dInterp2HB45": lambda: O.HB45Interp(np.float64)}[kind]()
+
+
+@pytest.mark.parametrize("case", BATCH_CASES, ids=["%s-%s" % (c[0], c[1]) for c in BATCH_CASES])
+def test_batch_filter_vs_oracle(case, torch, tabs):
+    from quisk_b200.rx import BatchFilter
+    kind, tname, interp, decim, real = case
+    tab = tabs[tname] if tname else None
+    C = 5
+    x = np.stack([O.synth_iq(sum(SPLITS), 30 + c, 1.0) for c in range(C)])
+    if real:
+        x = np.ascontiguousarray(x.real)
+    bf = BatchFilter(kind, C, tab, interp, decim)
+    y, counts = _run_batch(torch, bf, x, SPLITS, 2 * 6 * 2300)
+    for c in range(C):
+        st = _oracle_for(kind, tab, interp, decim, real)
+        yo, co, pos = [], [], 0
+        for n in SPLITS:
+            o = st(x[c, pos:pos + n]); pos += n
+            yo.append(o); co.append(len(o))
+        assert co == counts
+        assert O.rel_rms(y[c], np.concatenate(yo)) < 1e-13
+    bf.close()
+
+
+def test_batch_rxfilter_tap_order(torch):
+    from quisk_b200.rx import BatchFilter
+    rng = np.random.default_rng(5)
+    fi = rng.standard_normal(164); fq = rng.standard_normal(164)
+    C = 3
+    x = np.stack([O.synth_iq(3000, 40 + c, 1.0) for c in range(C)])
+    bf = BatchFilter("cRxFilter", C, (fi, fq))
+    y, _ = _run_batch(torch, bf, x, [1000, 1, 1999], 3000)
+    bd = BatchFilter("dRxFilter", C, fi)
+    yd, _ = _run_batch(torch, bd, x, [1000, 1, 1999], 3000)
+    for c in range(C):
+        assert O.rel_rms(y[c], O.RxFilterC(fi, fq)(x[c])) < 1e-13
+        assert O.rel_rms(yd[c], O.RxFilterD(fi)(x[c])) < 1e-13
+
+
+def _run_chain(torch, rx, x, splits, want_decim=False):
+    C = x.shape[0]
+    d_in = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    aud, dec, ca, cdm, pos = [], [], [], [], 0
+    for n in splits:
+        blk = d_in[:, pos:pos + n].contiguous(); pos += n
+        cap = rx.max_out(n)
+        a = torch.zeros((C, cap), dtype=torch.float64, device="cuda")
+        d = torch.zeros((C, n + 8), dtype=torch.complex128, device="cuda")
+        na, nd = rx.process(blk.data_ptr(), max(n, 1), n, a.data_ptr(), cap, d.data_ptr() if want_decim else 0, n + 8)
+        torch.cuda.synchronize()
+        aud.append(a[:, :na].cpu().numpy()); ca.append(na)
+        dec.append(d[:, :nd].cpu().numpy()); cdm.append(nd)
+    return np.concatenate(aud, axis=1), ca, np.concatenate(dec, axis=1), cdm
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("rate", RATES)
+def test_rx_decimate_kat(rate, fused, torch, tabs):
+    """quisk_process_decimate output (tapped through d_decim) against the reference fixture."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = demod_taps("USB")
+    rx = RxChain(2, rate, "USB", fi, fq, tabs, fused=bool(fused))
+    x = np.stack([O.synth_iq(40000, 9, 1.0)] * 2)
+    _, _, dec, cdm = _run_chain(torch, rx, x, CHAIN_SPLITS, want_decim=True)
+    assert cdm == kat["decimate_%d/counts" % rate].tolist()
+    assert rx.decim_srate == int(kat["decimate_%d/srate" % rate][0])
+    for c in range(2):
+        assert O.rel_rms(dec[c], kat["decimate_%d/y" % rate]) < 1e-12
+    rx.close()
+
+
+@pytest.mark.parametrize("mode", list(DEMOD_TAPS))
+def test_rx_demod_kat(mode, torch, tabs):
+    """quisk_process_demodulate at 48 kS/s in (no decimation planned) against the reference fixture."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = demod_taps(mode)
+    rx = RxChain(3, 48000, mode, fi, fq, tabs, fused=False)
+    x = np.stack([O.synth_iq(12000, 10, 1.0)] * 3)
+    aud, ca, _, _ = _run_chain(torch, rx, x, DEMOD_SPLITS)
+    assert ca == kat["demod_%s/counts" % mode].tolist()
+    for c in range(3):
+        assert O.rel_rms(aud[c], kat["demod_%s/y" % mode]) < (1e-10 if mode == "FM" else 1e-12)
+    rx.close()
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("tune", [0, 12345])
+def test_c1_chain_kat(tune, fused, torch, tabs):
+    """BASELINE.json configs[0] through the batched chain, 10 ms blocks, vs the reference fixture."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    C = 4
+    rx = RxChain(C, 1536000, "USB", fi, fq, tabs, tune_hz=[float(tune)] * C, fused=bool(fused))
+    x = np.stack([O.synth_iq(153600, 20, 1.0)] * C)
+    aud, ca, _, _ = _run_chain(torch, rx, x, [15360] * 10)
+    assert ca == kat["c1_tune%d/counts" % tune].tolist()
+    for c in range(C):
+        assert O.rel_rms(aud[c], kat["c1_tune%d/y" % tune]) < 1e-12
+    # block-split invariance: one 153 600-sample call gives the same stream
+    rx.reset()
+    aud1, ca1, _, _ = _run_chain(torch, rx, x, [153600])
+    assert ca1 == [4800]
+    assert O.rel_rms(aud1[0], kat["c1_tune%d/y" % tune]) < 1e-12
+    rx.close()
+
+
+def test_rx_process_host(torch, tabs):
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    C = 3
+    rx = RxChain(C, 1536000, "USB", fi, fq, tabs, fused=True)
+    x = np.stack([O.synth_iq(153600, 20, 1.0)] * C)
+    outs = []
+    for b in range(10):
+        blk = np.ascontiguousarray(x[:, b * 15360:(b + 1) * 15360])
+        a = np.zeros((C, rx.max_out(15360)))
+        na = rx.process_host(blk, 15360, a)
+        outs.append(a[:, :na])
+    aud = np.concatenate(outs, axis=1)
+    for c in range(C):
+        assert O.rel_rms(aud[c], kat["c1_tune0/y"]) < 1e-12
+    rx.close()

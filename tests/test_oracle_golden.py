@@ -1,0 +1,93 @@
+"""The NumPy oracle against the committed fixtures (generated from the compiled reference
+by tests/golden/make_golden.py).  Runs everywhere -- no reference, no GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import quisk_oracle as O
+from tests.golden.make_golden import FILTER_CASES, RATES, DEMOD_TAPS, kat_input, demod_taps
+from tests.util import SPLITS, CHAIN_SPLITS, DEMOD_SPLITS, golden
+
+TOL = 1e-13
+
+
+@pytest.fixture(scope="module")
+def tabs():
+    return golden("quisk_tables.npz")
+
+
+def _oracle_stage(fn, tab, args, tune, real):
+    dt = np.float64 if real else np.complex128
+    if fn == "quisk_cDecim2HB45": return O.HB45Decim()
+    if fn in ("quisk_cInterp2HB45", "quisk_dInterp2HB45"): return O.HB45Interp(dt)
+    if fn in ("quisk_cDecimate", "quisk_dDecimate"): return O.FirDecim(tab, args[0], dt)
+    if fn in ("quisk_cFilter", "quisk_dFilter"): return O.FirDecim(tab, 1, dt)
+    if fn == "quisk_cCDecimate":
+        D = (len(tab) - 1.0) / 2.0
+        hc = np.exp(2j * np.pi * tune[0] * (np.arange(len(tab)) - D)) * tab
+        if not tune[1]: hc = hc.imag + 1j * hc.real          # filter.c:76-79
+        return O.FirDecim(hc, args[0])
+    if fn in ("quisk_cInterpolate", "quisk_dInterpolate"): return O.FirInterp(tab, args[0], dt)
+    if fn == "quisk_cInterpDecim": return O.FirInterpDecim(tab, args[0], args[1])
+    raise KeyError(fn)
+
+
+@pytest.mark.parametrize("case", FILTER_CASES, ids=[c[0] for c in FILTER_CASES])
+def test_filter_kat(case, tabs):
+    name, fn, seed, real, tab, args, tune = case
+    kat = golden("filter_kat.npz")
+    x = kat_input(seed, real)
+    st = _oracle_stage(fn, tabs[tab] if tab else None, args, tune, real)
+    outs, counts, pos = [], [], 0
+    for n in SPLITS:
+        y = st(x[pos:pos + n]); pos += n
+        outs.append(y); counts.append(len(y))
+    assert counts == kat[name + "/counts"].tolist()
+    assert O.rel_rms(np.concatenate(outs), kat[name + "/y"]) < TOL
+
+
+@pytest.mark.parametrize("rate", RATES)
+def test_decimate_kat(rate, tabs):
+    kat = golden("chain_kat.npz")
+    chain = O.ProcessDecimate(rate, tabs)
+    x = O.synth_iq(40000, 9, 1.0)
+    outs, counts, pos = [], [], 0
+    for n in CHAIN_SPLITS:
+        y = chain(x[pos:pos + n]); pos += n
+        outs.append(y); counts.append(len(y))
+    assert counts == kat["decimate_%d/counts" % rate].tolist()
+    assert chain.decim_srate == int(kat["decimate_%d/srate" % rate][0])
+    assert O.rel_rms(np.concatenate(outs), kat["decimate_%d/y" % rate]) < TOL
+
+
+@pytest.mark.parametrize("mode", list(DEMOD_TAPS))
+def test_demod_kat(mode, tabs):
+    kat = golden("chain_kat.npz")
+    fi, fq = demod_taps(mode)
+    chain = O.ProcessDemodulate(mode, fi, fq, tabs)
+    x = O.synth_iq(12000, 10, 1.0)
+    outs, counts, pos = [], [], 0
+    for n in DEMOD_SPLITS:
+        y = chain(x[pos:pos + n]); pos += n
+        outs.append(y); counts.append(len(y))
+    assert counts == kat["demod_%s/counts" % mode].tolist()
+    assert O.rel_rms(np.concatenate(outs), kat["demod_%s/y" % mode]) < (1e-11 if mode == "FM" else TOL)
+
+
+@pytest.mark.parametrize("tune", [0, 12345])
+def test_c1_chain_kat(tune, tabs):
+    """BASELINE.json configs[0]: 1.536 MS/s -> 4 x HB45 -> 98-tap /2 -> 48 k -> USB (164-tap I/Q)."""
+    kat = golden("chain_kat.npz")
+    protos = {int(k[6:]): v for k, v in tabs.items() if k.startswith("proto_")}
+    fi, fq = O.make_filter_coef(12000, None, 2800, 300 + 2800 // 2, protos)
+    assert np.array_equal(fi, kat["c1/filt_i"]) and np.array_equal(fq, kat["c1/filt_q"]) and len(fi) == 164
+    dec = O.ProcessDecimate(1536000, tabs)
+    dem = O.ProcessDemodulate("USB", fi, fq, tabs)
+    nco = O.TuneNCO(float(tune), 1536000)
+    x = O.synth_iq(153600, 20, 1.0)
+    outs, counts = [], []
+    for b in range(10):
+        blk = x[b * 15360:(b + 1) * 15360]
+        y = dem(dec(nco(blk)))
+        outs.append(y); counts.append(len(y))
+    assert counts == kat["c1_tune%d/counts" % tune].tolist() == [480] * 10
+    assert O.rel_rms(np.concatenate(outs), kat["c1_tune%d/y" % tune]) < TOL

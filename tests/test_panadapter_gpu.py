@@ -1,0 +1,125 @@
+"""GPU parity of the in-house batched FFT and the panadapter (get_graph math,
+quisk.c:5142-5331, get_multirx_graph quisk.c:4868-4930) against the NumPy oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import quisk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from quisk_b200 import lib as L
+    return L.require_device()
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 256, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("sign", [-1, 1])
+def test_fft_batch_vs_numpy(n, sign, torch, lib):
+    rng = np.random.default_rng(n)
+    batch = 7
+    x = rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))
+    d = torch.from_numpy(x).cuda()
+    o = torch.empty_like(d)
+    assert lib.quisk_cuda_fft_batch(d.data_ptr(), o.data_ptr(), n, batch, sign, None) == 0
+    torch.cuda.synchronize()
+    ref = np.fft.fft(x, axis=1) if sign < 0 else np.fft.ifft(x, axis=1) * n
+    assert O.rel_rms(o.cpu().numpy(), ref) < 1e-14
+    # in place
+    assert lib.quisk_cuda_fft_batch(d.data_ptr(), d.data_ptr(), n, batch, sign, None) == 0
+    torch.cuda.synchronize()
+    assert O.rel_rms(d.cpu().numpy(), ref) < 1e-14
+
+
+def test_fft_rejects_unsupported_sizes(lib):
+    assert lib.quisk_cuda_fft_batch(None, None, 1000, 1, -1, None) != 0
+    assert b"power of two" in lib.quisk_cuda_last_error()
+
+
+@pytest.mark.parametrize("streams,count_fft", [(16, 1), (16, 8), (300, 3)])
+def test_panadapter_c2(streams, count_fft, torch, lib):
+    """BASELINE.json configs[1]: 16 streams, 8192-pt FFT + Hann + |X| averaging + dB graph."""
+    n = 8192
+    data_width = 1024
+    frames = np.stack([O.synth_iq(n * count_fft, 50 + s, 1.0).reshape(count_fft, n) for s in range(streams)])
+    d = torch.from_numpy(frames.reshape(streams, -1)).cuda()
+    pan = lib.quisk_cuda_pan_create(streams, n)
+    assert pan
+    assert lib.quisk_cuda_pan_accumulate(pan, d.data_ptr(), n * count_fft, count_fft, None) == 0
+    torch.cuda.synchronize()
+    assert lib.quisk_cuda_pan_count(pan) == count_fft
+    avg_ptr = lib.quisk_cuda_pan_average_ptr(pan)
+    avg = torch.empty((streams, n), dtype=torch.float64, device="cuda")
+    C.CDLL("libcudart.so.12").cudaMemcpy(C.c_void_p(avg.data_ptr()), C.c_void_p(avg_ptr), streams * n * 8, 3)
+    avg = avg.cpu().numpy()
+    g = torch.empty((streams, data_width), dtype=torch.float64, device="cuda")
+    assert lib.quisk_cuda_pan_graph(pan, data_width, 1.0, 0.0, 192000.0, g.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    g = g.cpu().numpy()
+    for s in range(0, streams, max(1, streams // 16)):
+        ref_avg = O.panadapter_accumulate(frames[s])
+        assert O.rel_rms(avg[s], ref_avg) < 1e-12
+        ref_g = O.panadapter_pixels(ref_avg, count_fft, data_width, 1.0, 0.0, 192000.0)
+        assert np.max(np.abs(g[s] - ref_g)) < 1e-9          # dB
+    assert lib.quisk_cuda_pan_count(pan) == 0
+    lib.quisk_cuda_pan_destroy(pan)
+
+
+def test_panadapter_incremental_and_zoom(torch, lib):
+    """Frames fed one call at a time give the same averages; zoomed graph with the in-place
+    pixel aliasing of quisk.c:5289-5301 (pixel i overwrites fft_avg[i] while still reading)."""
+    n, streams, data_width = 1024, 300, 1024
+    frames = np.stack([O.synth_iq(n * 4, 70 + s, 1.0).reshape(4, n) for s in range(streams)])
+    pan = lib.quisk_cuda_pan_create(streams, n)
+    for f in range(4):
+        d = torch.from_numpy(np.ascontiguousarray(frames[:, f, :])).cuda()
+        assert lib.quisk_cuda_pan_accumulate(pan, d.data_ptr(), n, 1, None) == 0
+    g = torch.empty((streams, data_width), dtype=torch.float64, device="cuda")
+    assert lib.quisk_cuda_pan_graph(pan, data_width, 0.5, 3000.0, 48000.0, g.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    g = g.cpu().numpy()
+    for s in (0, 17, 299):
+        ref_g = O.panadapter_pixels(O.panadapter_accumulate(frames[s]), 4, data_width, 0.5, 3000.0, 48000.0)
+        assert np.max(np.abs(g[s] - ref_g)) < 1e-9
+    lib.quisk_cuda_pan_destroy(pan)
+
+
+def test_full_scale_tone_reads_minus_6_dB(torch, lib):
+    """A full-scale (2^31-1) bin-centred tone reads ~ -6.02 dB: Hann coherent gain 0.5."""
+    n = 4096
+    t = np.arange(n)
+    x = (2.0 ** 31 - 1) * np.exp(2j * np.pi * 256 * t / n)
+    d = torch.from_numpy(x[None, :].copy()).cuda()
+    pan = lib.quisk_cuda_pan_create(1, n)
+    assert lib.quisk_cuda_pan_accumulate(pan, d.data_ptr(), n, 1, None) == 0
+    g = torch.empty((1, n), dtype=torch.float64, device="cuda")
+    assert lib.quisk_cuda_pan_graph(pan, n, 1.0, 0.0, 48000.0, g.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    g = g.cpu().numpy()[0]
+    assert abs(g.max() - 20 * np.log10(0.5)) < 1e-6
+    assert int(np.argmax(g)) == n // 2 + 256
+    lib.quisk_cuda_pan_destroy(pan)
+
+
+def test_multirx_graph(torch, lib):
+    n, streams = 2048, 5
+    x = np.stack([O.synth_iq(n, 90 + s, 1.0) for s in range(streams)])
+    d = torch.from_numpy(x).cuda()
+    pan = lib.quisk_cuda_pan_create(streams, n)
+    g = torch.empty((streams, n // 8), dtype=torch.float64, device="cuda")
+    assert lib.quisk_cuda_pan_multirx(pan, d.data_ptr(), n, g.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    g = g.cpu().numpy()
+    for s in range(streams):
+        assert np.max(np.abs(g[s] - O.multirx_graph(x[s]))) < 1e-9
+    lib.quisk_cuda_pan_destroy(pan)
