@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Quisk receive-DSP hot path on B200 (libquisk_cuda) next to the
+reference's own CPU implementation.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload rx_chain|panadapter|rx_chain+panadapter] [--channels C] [--block B]
+
+One "step" = one pass of the hot path over one block of synthetic IQ for every channel:
+  rx_chain    C independent receivers at 1.536 MS/s (BASELINE.json configs[0] batched): tune NCO ->
+              4 x quisk_cDecim2HB45 -> quisk_cDecimate(98 taps, /2) -> 48 kS/s -> HB45 -> FIR /2 ->
+              cRxFilterOut (164-tap I/Q, USB bw 2800) -> re-im -> quisk_dInterpolate x2 ->
+              quisk_dInterp2HB45 -> 48 kS/s audio.
+  panadapter  BASELINE.json configs[1] batched: 8192-point Hann/FFT/|X| accumulation of every input
+              frame of every channel, one dB graph per channel per step.
+metric = complex input MS/s, whole job.  `value` is timed with inputs resident in HBM; `e2e` is the
+same work through the host-buffer C-ABI entry point (H2D of the block + D2H of the audio inside the
+timed region).  With N > 1 (torchrun) every rank runs its own C channels -- independent receivers,
+no data-path collective -- and the time is the max over ranks ("weak" scaling).
+
+--impl reference times the reference's own C code (oracle/_ref: filter.c verbatim + the quisk.c RX
+functions, gcc -O2, no -ffast-math) on the host cores, one private copy of the library per thread.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLE_RATE = 1536000
+FFT_SIZE = 8192
+ALG_BYTES_RX = 16.0 + 8.0 * 48000 / SAMPLE_RATE          # 16 B in + 0.25 B out
+ALG_BYTES_PAN = 16.0                                     # C2: 16 B in (+ 8 B/bin per returned graph)
+
+
+def synth_block_torch(torch, C_, n, device, seed):
+    """Multi-tone + noise IQ generated on the device: [C, n] complex128."""
+    g = torch.Generator(device=device); g.manual_seed(1234 + seed)
+    t = torch.arange(n, device=device, dtype=torch.float64)
+    fr = torch.tensor([0.01, -0.01, 0.07, -0.07, 0.13, -0.13, 0.31, -0.31], device=device, dtype=torch.float64)
+    amp = 2.0 ** torch.linspace(24, 30, 8, device=device, dtype=torch.float64)
+    x = torch.zeros((C_, n), dtype=torch.complex128, device=device)
+    CH = 64
+    for c0 in range(0, C_, CH):
+        c1 = min(C_, c0 + CH)
+        ph = torch.rand((c1 - c0, 8), generator=g, device=device, dtype=torch.float64) * 2 * np.pi
+        acc = torch.zeros((c1 - c0, n), dtype=torch.complex128, device=device)
+        for k in range(8):
+            acc += amp[k] * torch.exp(1j * (2 * np.pi * fr[k] * t[None, :] + ph[:, k:k + 1]))
+        acc += (2.0 ** 20) * (torch.randn((c1 - c0, n), generator=g, device=device, dtype=torch.float64)
+                              + 1j * torch.randn((c1 - c0, n), generator=g, device=device, dtype=torch.float64))
+        x[c0:c1] = acc
+    return x
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.stop_flag = False; self.sm = []; self.reasons = set(); self.sm_max = None; self.ok = False
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            self.ok = True
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:      # NVML missing: report that, never fake a value
+            self.err = str(e)
+
+    def result(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["nvml_unavailable: %s" % getattr(self, "err", "no samples")]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# reference CPU arm
+# --------------------------------------------------------------------------------------------
+
+def ref_worker_setup(fi, fq):
+    from oracle import ref_ctypes as R
+    lib = R.load("libquisk_rx_ref.so", private_copy=True)
+    lib.ref_set_sample_rate(SAMPLE_RATE); lib.ref_init_chain()
+    lib.ref_set_filters(fi.ctypes.data_as(C.c_void_p), fq.ctypes.data_as(C.c_void_p), len(fi), 2800, 0)
+    lib.ref_tune.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
+    return lib
+
+
+def ref_run_block(lib, x, scratch, dbuf, vec, tune_hz):
+    """One channel, one block, in <= 61440-sample calls (the reference's buffers hold 66000)."""
+    n = len(x); pos = 0; total = 0
+    while pos < n:
+        m = min(61440, n - pos)
+        scratch[:m] = x[pos:pos + m]
+        if tune_hz:
+            lib.ref_tune(scratch.ctypes.data, m, tune_hz, SAMPLE_RATE, vec.ctypes.data)
+        nd = lib.ref_process_decimate(scratch.ctypes.data_as(C.c_void_p), m, 0, 3)
+        total += lib.ref_process_demodulate(scratch.ctypes.data_as(C.c_void_p), dbuf.ctypes.data_as(C.c_void_p), nd, 0, 0, 3)
+        pos += m
+    return total
+
+
+def ref_pan_block(x, window):
+    """Reference panadapter math on the CPU for one channel block: numpy pocketfft stands in for
+    FFTW (un-vendored dependency of the reference, absent from this image)."""
+    fr = x.reshape(-1, FFT_SIZE) * window
+    return np.abs(np.fft.fftshift(np.fft.fft(fr, axis=-1), axes=-1)).sum(axis=0)
+
+
+def cpu_reference_rate(block, steps, warmup, workload, fi, fq, tune_hz):
+    """Complex MS/s of the reference CPU code on all host cores: every core runs one channel."""
+    from oracle import quisk_oracle as O
+    cores = os.cpu_count() or 1
+    libs = [ref_worker_setup(fi, fq) for _ in range(cores)]
+    xs = [O.synth_iq(block, 1000 + i, 1.0) for i in range(cores)]
+    window = O.hann_window(FFT_SIZE)
+    state = [(np.zeros(66000, dtype=np.complex128), np.zeros(132000), np.array([1.0 + 0j])) for _ in range(cores)]
+
+    def work(i, nsteps):
+        for _ in range(nsteps):
+            if "rx_chain" in workload:
+                ref_run_block(libs[i], xs[i], state[i][0], state[i][1], state[i][2], tune_hz)
+            if "panadapter" in workload:
+                ref_pan_block(xs[i][: (block // FFT_SIZE) * FFT_SIZE], window)
+
+    def run(nsteps):
+        th = [threading.Thread(target=work, args=(i, nsteps)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th: t.start()
+        for t in th: t.join()
+        return time.perf_counter() - t0
+
+    run(warmup)
+    dt = run(steps)
+    return cores * block * steps / dt / 1e6, cores, dt
+
+
+# --------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rx_chain", choices=["rx_chain", "panadapter", "rx_chain+panadapter"])
+    ap.add_argument("--channels", type=int, default=4096)
+    ap.add_argument("--block", type=int, default=32768, help="input samples per channel per step (multiple of 8192)")
+    ap.add_argument("--tune", type=float, default=12345.0, help="rx_tune_freq in Hz (0 = no tuning stage)")
+    ap.add_argument("--unfused", action="store_true", help="run the one-kernel-per-stage exact path instead of the fused cascade")
+    ap.add_argument("--chunk", type=int, default=0, help="fused decimator chunk (input samples), 0 = default")
+    ap.add_argument("--threads", type=int, default=0, help="fused decimator CTA width (128/256), 0 = default")
+    ap.add_argument("--min-r", type=int, default=0, help="fused decimator: min outputs per thread in half-band stages")
+    ap.add_argument("--dense", type=int, default=-1, help="fused decimator: 1 = 128-register cap, 0 = 255")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    block = max(FFT_SIZE, (args.block // FFT_SIZE) * FFT_SIZE)
+
+    from quisk_b200.rx import load_tables
+    tabs = load_tables()
+    kat = np.load(os.path.join(ROOT, "tests", "golden", "chain_kat.npz"))
+    fi = np.ascontiguousarray(kat["c1/filt_i"]); fq = np.ascontiguousarray(kat["c1/filt_q"])
+    wl_name = {"rx_chain": "rx_chain: C x 1.536 MS/s tune->4xHB45->FIR98/2->48k->HB45->FIR98/2->cRxFilterOut(164 I/Q, USB)->audio 48k (BASELINE configs[0], batched)",
+               "panadapter": "panadapter: C streams x 8192-pt Hann+FFT+|X| average+dB graph (BASELINE configs[1], batched)",
+               "rx_chain+panadapter": "rx_chain + panadapter on the same input (configs[0]+configs[1], batched)"}[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ref_block = 61440
+        v, cores, dt = cpu_reference_rate(ref_block, args.steps, args.warmup, args.workload, fi, fq, args.tune)
+        line = {"impl": "reference", "metric": "complex MS/s through RX chain", "value": v, "unit": "MS/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl_name, "channels": cores, "block": ref_block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune},
+                "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
+                                 "sample": "%d channels (one per host core) x %d samples x %d steps; oracle/_ref = filter.c verbatim + quisk.c RX functions, gcc -O2"
+                                           % (cores, ref_block, args.steps)},
+                "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line)); return
+
+    import torch
+    import torch.distributed as dist
+    from quisk_b200 import lib as L
+    from quisk_b200.rx import RxChain
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = L.require_device()
+    L.check(lib, lib.quisk_cuda_set_device(local_rank), "set_device")
+    C_ = args.channels
+
+    x = synth_block_torch(torch, C_, block, dev, rank)
+    rx = pan = None
+    stream = torch.cuda.current_stream().cuda_stream
+    if "rx_chain" in args.workload:
+        rx = RxChain(C_, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=[args.tune] * C_ if args.tune else None, fused=not args.unfused)
+        if args.chunk:
+            rx.set_option(2, args.chunk)
+        if args.threads:
+            rx.set_option(3, args.threads)
+        if args.min_r:
+            rx.set_option(4, args.min_r)
+        if args.dense >= 0:
+            rx.set_option(5, args.dense)
+        acap = rx.max_out(block)
+        audio = torch.zeros((C_, acap), dtype=torch.float64, device=dev)
+    if "panadapter" in args.workload:
+        pan = lib.quisk_cuda_pan_create(C_, FFT_SIZE)
+        if not pan:
+            raise L.QuiskCudaError(lib.quisk_cuda_last_error().decode())
+        graph = torch.zeros((C_, 1024), dtype=torch.float64, device=dev)
+    frames = block // FFT_SIZE
+
+    def step():
+        if pan:
+            L.check(lib, lib.quisk_cuda_pan_accumulate(pan, x.data_ptr(), block, frames, stream), "pan_accumulate")
+            L.check(lib, lib.quisk_cuda_pan_graph(pan, 1024, 1.0, 0.0, float(SAMPLE_RATE), graph.data_ptr(), stream), "pan_graph")
+        if rx:
+            rx.process(x.data_ptr(), block, block, audio.data_ptr(), acap, stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    if rx:
+        rx.set_option(1, 1); rx.kernel_time()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = lib.quisk_cuda_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.quisk_cuda_launch_count() - l0)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    kms, kn = (rx.kernel_time() if rx else (0.0, 0))
+    if rx:
+        rx.set_option(1, 0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * C_ * block * args.steps / (ms_max / 1e3) / 1e6
+
+    # ---- end to end through the host-buffer entry point (H2D + chain + D2H inside the timed region)
+    e2e = None
+    if rx and args.e2e_steps > 0:
+        Ce = min(C_, 1024)
+        hx = torch.empty((Ce, block), dtype=torch.complex128).pin_memory()
+        hx.copy_(x[:Ce].cpu())
+        ha = torch.zeros((Ce, acap), dtype=torch.float64).pin_memory()
+        rx_h = RxChain(Ce, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=[args.tune] * Ce if args.tune else None, fused=not args.unfused)
+        hx_np = hx.numpy(); ha_np = ha.numpy()
+        rx_h.process_host(hx_np, block, ha_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            na = rx_h.process_host(hx_np, block, ha_np)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * Ce * block * args.e2e_steps / float(tt.item()) / 1e6, "unit": "MS/s",
+               "h2d_bytes_per_step": Ce * block * 16, "d2h_bytes_per_step": Ce * na * 8,
+               "channels": Ce, "note": "quisk_cuda_rx_process_host: pinned host IQ -> H2D -> chain -> D2H audio, per step"}
+        rx_h.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    roofline = None
+    if rx and kn > 0:
+        per_launch_ms = kms / kn
+        alg = (16.0 + 16.0 / 32.0) * C_ * block             # fused decimator: 16 B in, 16 B out per 32 inputs
+        ach = alg / (per_launch_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "fused_decim_kernel (tune + 4xHB45 + FIR98/2)", "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kms / ms,
+                    "alg_bytes_per_launch": alg}
+    elif pan:
+        alg = ALG_BYTES_PAN * C_ * block
+        ach = alg * args.steps / (ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "pan_accumulate_kernel (whole step)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            v, cores, dt = cpu_reference_rate(61440, 40, 2, args.workload, fi, fq, args.tune)
+            cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
+                   "sample": "%d channels (one per host core) x 61440 samples x 40 steps, %.1f s wall; oracle/_ref (filter.c verbatim + quisk.c RX functions, gcc -O2)" % (cores, dt)}
+        except Exception as ex:     # the compiled reference did not travel: say so
+            cpu = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
+
+    line = {"metric": "complex MS/s through RX chain", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "channels_per_gpu": C_, "block": block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune,
+                       "fused": not args.unfused, "l2": "input %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (C_ * block * 16 / 1e6)},
+            "clocks": sampler.result(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,7 @@ int BatchFilter::init(int kind_, int C_, const double *coefs, int n_taps, int in
         H = nTaps - 1; up.assign(coefs, coefs + nTaps); break;
     }
     if (C <= 0 || (up.empty() && H != 44 && H != 22)) { set_error("batch_create: bad arguments"); return QC_EINVAL; }
+    h_coef = up;
     if (!up.empty()) {
         QC_CUDA(cudaMalloc((void **)&d_coef, up.size() * sizeof(double)));
         QC_CUDA(cudaMemcpy(d_coef, up.data(), up.size() * sizeof(double), cudaMemcpyHostToDevice));

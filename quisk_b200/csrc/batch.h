@@ -10,6 +10,7 @@ struct BatchFilter {
     int phase = 0;               // toggle (HB45) or decim_index
     int cur = 0;                 // which history buffer is current
     double *d_coef = nullptr;
+    std::vector<double> h_coef;  // host copy of the taps as uploaded
     void *d_hist[2] = {nullptr, nullptr};
 
     int init(int kind, int C, const double *coefs, int n_taps, int interp, int decim);

@@ -355,4 +355,42 @@ int quisk_cuda_rx_process_host(qcRxChain *rx, const quisk_cd *h_iq, long iq_stri
 
 int quisk_cuda_rx_reset(qcRxChain *rx) { return rx ? rx->rx.reset() : QC_EINVAL; }
 
+int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
+{
+    if (!rx) return QC_EINVAL;
+    switch (option) {
+    case QC_RX_OPT_TIMING: rx->rx.timing = value != 0; return QC_OK;
+    case QC_RX_OPT_FUSED_CHUNK:
+        if (value < 128 || value > 2048) { qc::set_error("rx_set_option: chunk %d out of range", value); return QC_EINVAL; }
+        rx->rx.fused_chunk = value; return QC_OK;
+    case QC_RX_OPT_FUSED_THREADS:
+        if (value != 128 && value != 256) { qc::set_error("rx_set_option: threads must be 128 or 256"); return QC_EINVAL; }
+        rx->rx.fused_threads = value; return QC_OK;
+    case QC_RX_OPT_FUSED_DENSE: rx->rx.fused_dense = value; return QC_OK;
+    case QC_RX_OPT_FUSED_MIN_R:
+        if (value != 0 && value != 2 && value != 4 && value != 8) { qc::set_error("rx_set_option: min R must be 0/2/4/8"); return QC_EINVAL; }
+        rx->rx.fused_min_r = value; return QC_OK;
+    }
+    qc::set_error("rx_set_option: unknown option %d", option);
+    return QC_EINVAL;
+}
+
+int quisk_cuda_rx_kernel_time(qcRxChain *rx, double *ms_total, int *launches)
+{
+    if (!rx) return QC_EINVAL;
+    double tot = 0.0;
+    int n = 0;
+    for (auto &pr : rx->rx.timed) {
+        float ms = 0.f;
+        QC_CUDA(cudaEventSynchronize(pr.second));
+        QC_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms; n++;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    rx->rx.timed.clear();
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = n;
+    return QC_OK;
+}
+
 }  // extern "C"

@@ -36,6 +36,13 @@ struct RxChain {
     // fused full-rate decimator
     FusedDecimator *fd = nullptr;
     size_t n_fused_stages = 0;
+    int fused_chunk = 2048;             // target input samples per shared-memory chunk
+    int fused_threads = 128;            // CTA width of the fused kernel (128 or 256)
+    int fused_dense = 1;                // 1: cap registers at 128/thread for more resident CTAs
+    int fused_min_r = 0;                // force at least this many outputs per thread in half-band stages
+    // optional device timing of the dominant (fused) kernel
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
 
     int init(const qcRxConfig &cfg);
     void release();

@@ -1,12 +1,503 @@
-// quisk_b200/csrc/rxfused.cu -- fused shared-memory cascade for the full-rate decimator (placeholder
-// until the cascade kernel lands: the chain then runs stage by stage).
+// quisk_b200/csrc/rxfused.cu -- the fused full-rate decimator: ONE kernel for the tuning NCO
+// (quisk.c:2477-2488) and every quisk_cDecim2HB45 / quisk_cDecimate stage of
+// quisk_process_decimate (+ the demodulator's own pre-decimation, quisk.c:1909-1983).
+//
+// Design (B200-first, see DESIGN.md section "fused decimator"):
+//  * One CTA streams one channel through time.  Per chunk of T0 input samples it loads the
+//    chunk with coalesced 16-byte loads (multiplying by the NCO phasor on the way in), then
+//    runs every stage out of shared memory into the next stage's shared-memory buffer; only
+//    the last stage writes HBM.  Algorithmic traffic is therefore 16 B in + 16/Dtot B out per
+//    input sample, and nothing is re-read: there are no halos because a channel never leaves
+//    its CTA, and the inter-chunk FIR histories stay in shared memory.
+//  * Between calls the per-stage histories live in the same [C][H] arrays the unfused exact
+//    kernels use (batch.cu), so a stream can switch between the two paths at any call.
+//  * Half-band stages are register blocked: a thread produces R consecutive outputs from one
+//    window of 22+R-1 even-phase and R odd-phase samples held in registers (R = 8/4/2), so
+//    shared-memory traffic per output drops from 23 to (21+2R)/R loads.  Buffers are padded
+//    by one element every 2R so that the per-thread stride (2R+1 elements) is odd and the
+//    16-byte loads of a quarter-warp never collide; the buffer origin is shifted so every
+//    thread's window starts on a pad boundary and all offsets are compile-time immediates.
+//  * FIR stages split taps across TS adjacent lanes (13 taps per step, R = 4 outputs per
+//    thread from one register window), then butterfly-reduce the partial sums with shuffles.
+//  * Arithmetic is FP64 FMA in (nearly) the reference's summation order: within ~1e-15 of
+//    the exact path, not bit-identical to it (tests/test_batch_gpu.py states the bound).
 #include "rxchain.h"
+#include "nco_device.cuh"
 
 namespace qc {
 
-bool RxChain::fused_applicable() { return false; }
-int RxChain::run_fused_decimator(const cd *, long, int, cd *, long, int *, cudaStream_t) { set_error("fused decimator not built"); return QC_EINVAL; }
+static constexpr int FNT = 128;         // chunk granularity: CTAs are 128 or 256 threads wide
+static constexpr int MAXST = 10;
+static constexpr int FIR_KB = 13;       // taps per register window (odd: lanes of a tap split never collide)
+static constexpr int FIR_R = 2;
+static constexpr int MAXCOEF = 1536;
+
+struct FStage {
+    int type;           // 0 = half band, 1 = FIR
+    int D, nTaps;
+    int Hs;             // history length of the state arrays (BatchFilter::H)
+    int Ha;             // history kept in shared memory (>= Hs, covers the zero-padded taps)
+    int u0;             // offset of the first output-producing sample among the new samples
+    int R;
+    int pu;             // pad unit (0 = unpadded)
+    unsigned magic;     // ceil(2^32 / pu)
+    int org;            // origin shift: q = logical + org
+    int buf;            // offset of this stage's input buffer in shared memory (cd units)
+    int buf_len;        // physical length (cd units)
+    int coef;           // FIR: offset into FusedParams::coef
+    int Kpad, TS;       // FIR: zero-padded tap count, tap splits
+    int p0;             // half band: physical index of thread 0's window start
+    int n_full;         // new samples this stage sees per full chunk
+    int n_out_full;     // outputs per full chunk
+    const cd *hin;
+    cd *hout;
+};
+
+struct FusedParams {
+    int ns;
+    FStage st[MAXST];
+    const cd *in; long in_stride; int n_in;
+    cd *out; long out_stride;
+    int T0;
+    const double *nco; unsigned long long n_base; int tune;
+    int smem_cd;        // total shared memory in cd units
+    int scratch;        // offset of the history-slide scratch area (cd units)
+    int coef_sm;        // offset of the tap copy in shared memory (cd units)
+    int ncoef;
+    double coef[MAXCOEF];
+};
+
+__constant__ double c_hb[12] = {        // filter.c:381-384
+    0.000018566625444266, -0.000118469698701817, 0.000457318798253456,
+    -0.001347840471412094, 0.003321838571445455, -0.007198422696929033,
+    0.014211106939802483, -0.026424776824073383, 0.048414810444971007,
+    -0.096214669073304823, 0.314881034738348550, 0.500000000000000000 };
+
+__device__ __forceinline__ int phys(const FStage &s, int logical)
+{
+    const unsigned q = (unsigned)(logical + s.org);
+    return (int)(q + __umulhi(q, s.magic));
+}
+
+struct Sink {           // where a stage's outputs go: the next stage's buffer or HBM
+    cd *sm;             // shared memory base (nullptr -> global)
+    int H, org; unsigned magic;
+    cd *g;
+    __device__ __forceinline__ void put(int m, cd v) const
+    {
+        if (sm) {
+            const unsigned q = (unsigned)(H + m + org);
+            sm[q + __umulhi(q, magic)] = v;
+        } else {
+            g[m] = v;
+        }
+    }
+};
+
+__device__ __forceinline__ cd fmaz(cd a, double c, cd acc) { return make_double2(fma(a.x, c, acc.x), fma(a.y, c, acc.y)); }
+
+// Half band, R outputs per thread.  sb = stage buffer, p0 = physical index of thread 0's window start.
+// The window is streamed: every even-phase sample E[j] = X[n0 - 42 + 2j] is loaded once and fed to
+// each of the (up to R) outputs it belongs to, so the thread holds R accumulators and a couple of
+// loads in flight instead of the whole window.  samples[k] of output r is E[r + 21 - k] and meets
+// coef[min(k, 21-k)] (filter.c:401-413 without the pre-addition of the symmetric pair: same number
+// of FP64 operations, a quarter of the registers).
+template <int R>
+__device__ __forceinline__ void hb_stage(const cd *__restrict__ sb, int p0, int n_out, const Sink &sink)
+{
+    const int t = threadIdx.x;
+    const int m0 = t * R;
+    if (m0 >= n_out) return;
+    const cd *w = sb + p0 + (2 * R + 1) * t;
+    cd acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < 22 + R - 1; j++) {
+        const cd e = w[2 * j + (2 * j) / (2 * R)];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = r + 21 - j;                    // samples[] index of E[j] for output r
+            if (k >= 0 && k <= 21) acc[r] = fmaz(e, c_hb[k <= 10 ? k : 21 - k], acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const cd o = w[(21 + 2 * r) + (21 + 2 * r) / (2 * R)];     // center[10] = X[n - 21]
+        acc[r] = fmaz(o, c_hb[11], acc[r]);
+        if (m0 + r < n_out) sink.put(m0 + r, acc[r]);
+    }
+}
+
+// FIR with decimation D: lane = g * TS + ts; thread handles outputs R*g .. R*g+R-1 over its tap blocks.
+template <int D, int NT>
+__device__ __forceinline__ void fir_stage(const cd *__restrict__ sb, const FStage &s, const double *__restrict__ coef,
+                                          int n_out, const Sink &sink)
+{
+    constexpr int R = FIR_R, KB = FIR_KB, W = KB + D * (R - 1);
+    const int TS = s.TS;
+    const int t = threadIdx.x;
+    const int ts = t & (TS - 1);
+    int g = t / TS;
+    const int n_groups = (n_out + R - 1) / R;
+    const int rounds = (n_groups * TS + NT - 1) / NT;           // uniform
+    for (int round = 0; round < rounds; round++, g += NT / TS) {
+        const bool live = g < n_groups;
+        const int gg = live ? g : 0;
+        cd acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = make_double2(0.0, 0.0);
+        // logical index of the sample that meets tap 0 for output r = 0
+        const int nbase = s.Hs + s.u0 + D * R * gg + (s.Ha - s.Hs);
+        for (int k0 = ts * KB; k0 < s.Kpad; k0 += TS * KB) {
+            const cd *w = sb + (nbase - k0 - (KB - 1) + s.org);
+            cd Wn[W];
+#pragma unroll
+            for (int i = 0; i < W; i++) Wn[i] = w[i];
+#pragma unroll
+            for (int kk = 0; kk < KB; kk++) {
+                const double c = coef[k0 + kk];
+#pragma unroll
+                for (int r = 0; r < R; r++) acc[r] = fmaz(Wn[D * r + KB - 1 - kk], c, acc[r]);
+            }
+        }
+        for (int off = TS >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, off);
+                acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, off);
+            }
+        }
+        if (live && ts == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (R * g + r < n_out) sink.put(R * g + r, acc[r]);
+        }
+    }
+}
+
+__device__ __forceinline__ int stage_out_count(const FStage &s, int n_in)
+{
+    return n_in > s.u0 ? (n_in - s.u0 - 1) / s.D + 1 : 0;
+}
+
+// One stage of the cascade for n_out outputs (uniform across the CTA).
+template <int NT>
+__device__ __forceinline__ void run_stage(cd *sm, const FusedParams &P, int s, int n_out, cd *gdst)
+{
+    const FStage &S = P.st[s];
+    Sink sink;
+    if (s + 1 < P.ns) {
+        const FStage &N = P.st[s + 1];
+        sink.sm = sm + N.buf; sink.H = N.Ha; sink.org = N.org; sink.magic = N.magic; sink.g = nullptr;
+    } else {
+        sink.sm = nullptr; sink.H = 0; sink.org = 0; sink.magic = 0; sink.g = gdst;
+    }
+    const cd *sb = sm + S.buf;
+    if (S.type == 0) {
+        if (S.R == 8) { if constexpr (NT == 128) hb_stage<8>(sb, S.p0, n_out, sink); }
+        else if (S.R == 4) hb_stage<4>(sb, S.p0, n_out, sink);
+        else hb_stage<2>(sb, S.p0, n_out, sink);
+    } else {
+        const double *coef = reinterpret_cast<const double *>(sm + P.coef_sm) + S.coef;
+        if (S.D == 2) fir_stage<2, NT>(sb, S, coef, n_out, sink);
+        else if (S.D == 3) fir_stage<3, NT>(sb, S, coef, n_out, sink);
+        else if (S.D == 5) fir_stage<5, NT>(sb, S, coef, n_out, sink);
+        else fir_stage<1, NT>(sb, S, coef, n_out, sink);
+    }
+}
+
+template <int NT, int R0, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_constant__ FusedParams P)
+{
+    extern __shared__ double smem_raw[];
+    cd *sm = reinterpret_cast<cd *>(smem_raw);
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ cd s_pstep;                      // phase^NT
+    constexpr int NLD = 2048 / NT;              // loads per thread per chunk (T0 <= 2048)
+    constexpr int NSL = 512 / NT;               // history elements a thread carries in the slide
+
+    // zero everything once: pads, and the history beyond what the state arrays hold
+    for (int i = tid; i < P.smem_cd; i += NT) sm[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int s = 0; s < P.ns; s++) {
+        const FStage &S = P.st[s];
+        const cd *h = S.hin + (size_t)c * S.Hs;
+        for (int i = tid; i < S.Hs; i += NT) sm[S.buf + phys(S, (S.Ha - S.Hs) + i)] = h[i];
+    }
+    {
+        double *cs = reinterpret_cast<double *>(sm + P.coef_sm);
+        for (int i = tid; i < P.ncoef; i += NT) cs[i] = P.coef[i];
+    }
+    cd u = make_double2(1.0, 0.0), pstep = make_double2(1.0, 0.0);
+    if (P.tune) {
+        const double *nc = P.nco + (size_t)c * 8;
+        if (tid == 0) s_pstep = nco_pow(nc, (unsigned long long)NT);
+        u = cmul_rn(make_double2(nc[3], nc[4]), nco_pow(nc, P.n_base + (unsigned long long)tid));
+    }
+    // slide table for full chunks: which shared-memory element this thread moves where
+    int sl_src[NSL], sl_dst[NSL];
+#pragma unroll
+    for (int e = 0; e < NSL; e++) {
+        int idx = tid + e * NT, src = -1, dst = -1;
+        for (int s = 0; s < P.ns; s++) {
+            const FStage &S = P.st[s];
+            if (idx >= 0 && idx < S.Ha) { src = S.buf + phys(S, S.n_full + idx); dst = S.buf + phys(S, idx); }
+            idx -= S.Ha;
+        }
+        sl_src[e] = src; sl_dst[e] = dst;
+    }
+    __syncthreads();
+    if (P.tune) pstep = s_pstep;
+
+    const cd *gin = P.in + (size_t)c * P.in_stride;
+    cd *gout = P.out + (size_t)c * P.out_stride;
+    const FStage &S0 = P.st[0];
+    // stage 0's new samples: element k*NT + tid lands at pb0 + k*step0 (NT is a multiple of the pad unit)
+    // (stage 0 is padded every 2*R0 elements when it is a half band, unpadded when it is a FIR)
+    cd *pb0 = sm + S0.buf + phys(S0, S0.Ha + tid);
+    constexpr int STEP_PAD = NT + NT / (2 * R0);
+    const bool pad0 = S0.pu != 0;
+    const bool tune = P.tune != 0;
+
+    const int n_full = P.n_in / P.T0;
+    const int rem = P.n_in - n_full * P.T0;
+    const int nld = P.T0 / NT;                  // loads per thread in a full chunk (uniform)
+
+    // The next chunk's samples are fetched into registers while the current chunk is worked on:
+    // up to NLD independent 16-byte loads per thread stay in flight across the whole cascade.
+    cd nx[NLD];
+    if (n_full > 0) {
+#pragma unroll
+        for (int k = 0; k < NLD; k++) if (k < nld) nx[k] = gin[k * NT + tid];
+    }
+    int out_pos = 0;
+    for (int ch = 0; ch < n_full; ch++) {
+        // ---- commit the prefetched chunk behind stage 0's history, applying the NCO on the way
+        if (tune) {
+#pragma unroll
+            for (int k = 0; k < NLD; k++) {
+                if (k < nld) {
+                    // x * v with fused multiply-adds; v advances NT samples per step
+                    nx[k] = make_double2(fma(nx[k].x, u.x, -nx[k].y * u.y), fma(nx[k].x, u.y, nx[k].y * u.x));
+                    u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
+                }
+            }
+        }
+        if (pad0) {
+#pragma unroll
+            for (int k = 0; k < NLD; k++) if (k < nld) pb0[k * STEP_PAD] = nx[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NLD; k++) if (k < nld) pb0[k * NT] = nx[k];
+        }
+        __syncthreads();
+        // ---- start fetching the next full chunk
+        if (ch + 1 < n_full) {
+            const cd *g1 = gin + (size_t)(ch + 1) * P.T0 + tid;
+#pragma unroll
+            for (int k = 0; k < NLD; k++) if (k < nld) nx[k] = g1[k * NT];
+        }
+        // ---- the cascade
+        for (int s = 0; s < P.ns; s++) {
+            run_stage<NT>(sm, P, s, P.st[s].n_out_full, gout + out_pos);
+            __syncthreads();
+        }
+        out_pos += P.st[P.ns - 1].n_out_full;
+        // ---- slide the histories: tail -> registers, barrier, registers -> front.  The writes are
+        //      ordered against the next reads by the barrier that follows the next commit.
+        cd keep[NSL];
+#pragma unroll
+        for (int e = 0; e < NSL; e++) if (sl_src[e] >= 0) keep[e] = sm[sl_src[e]];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < NSL; e++) if (sl_src[e] >= 0) sm[sl_dst[e]] = keep[e];
+    }
+    __syncthreads();
+    // ---- ragged tail (at most one partial chunk), generic indexing
+    int n_s = 0;
+    if (rem > 0) {
+        const cd *g1 = gin + (size_t)n_full * P.T0;
+        for (int i = tid; i < ((rem + NT - 1) / NT) * NT; i += NT) {
+            cd x = make_double2(0.0, 0.0);
+            if (i < rem) x = g1[i];
+            if (P.tune) {
+                x = make_double2(fma(x.x, u.x, -x.y * u.y), fma(x.x, u.y, x.y * u.x));
+                u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
+            }
+            if (i < rem) sm[S0.buf + phys(S0, S0.Ha + i)] = x;
+        }
+        __syncthreads();
+        int n_in = rem;
+        for (int s = 0; s < P.ns; s++) {
+            const int n_out = stage_out_count(P.st[s], n_in);
+            run_stage<NT>(sm, P, s, n_out, gout + out_pos);
+            n_in = n_out;
+            __syncthreads();
+        }
+        n_s = rem;
+    }
+    // ---- hand the histories back: the last Hs inputs of every stage
+    for (int s = 0; s < P.ns; s++) {
+        const FStage &S = P.st[s];
+        cd *h = S.hout + (size_t)c * S.Hs;
+        for (int i = tid; i < S.Hs; i += NT) h[i] = sm[S.buf + phys(S, n_s + (S.Ha - S.Hs) + i)];
+        n_s = stage_out_count(S, n_s);
+    }
+}
+
+struct FusedDecimator {
+    FusedParams P;
+    size_t smem_bytes = 0;
+    bool attr_set = false;
+};
+
+static bool stage_fusable(const BatchFilter *f)
+{
+    if (f->kind == QC_C_DECIM2_HB45) return true;
+    if (f->kind == QC_C_DECIMATE) return f->decim == 1 || f->decim == 2 || f->decim == 3 || f->decim == 5;
+    return false;
+}
+
+bool RxChain::fused_applicable()
+{
+    if (fd) return n_fused_stages > 0;
+    fd = new FusedDecimator();
+    // leading run of half-band / FIR-decimate stages of quisk_process_decimate
+    size_t n = 0;
+    int ncoef = 0;
+    long dtot = 1;
+    while (n < (size_t)n_decim_stages && n < (size_t)MAXST && stage_fusable(cst[n])) {
+        const BatchFilter *f = cst[n];
+        long d = f->kind == QC_C_DECIM2_HB45 ? 2 : f->decim;
+        int kp = 0;
+        if (f->kind == QC_C_DECIMATE) kp = ((f->nTaps + 8 * FIR_KB - 1) / (8 * FIR_KB)) * (8 * FIR_KB);
+        // the chunk must be a multiple of both the total decimation and the CTA width
+        long l = dtot * d;
+        long lcm = l;
+        while (lcm % FNT) lcm += l;
+        if (lcm > 2048 || ncoef + kp > MAXCOEF) break;
+        dtot = l; ncoef += kp; n++;
+    }
+    n_fused_stages = n;
+    return n > 0;
+}
+
+int RxChain::run_fused_decimator(const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t strm)
+{
+    FusedParams &P = fd->P;
+    const int ns = (int)n_fused_stages;
+    // total decimation and chunk size
+    int dtot = 1;
+    for (int s = 0; s < ns; s++) dtot *= (cst[s]->kind == QC_C_DECIM2_HB45 ? 2 : cst[s]->decim);
+    int lcm = dtot;
+    while (lcm % FNT) lcm += dtot;
+    int T0 = (fused_chunk / lcm) * lcm;
+    if (T0 <= 0) T0 = lcm;
+    if (T0 > 2048) T0 = (2048 / lcm) * lcm;
+    const int NT = fused_threads == 256 ? 256 : 128;
+    if (T0 % NT) T0 = ((T0 / NT) * NT > 0 && ((T0 / NT) * NT) % lcm == 0) ? (T0 / NT) * NT : T0;
+    if (T0 % NT) { set_error("fused decimator: chunk %d is not a multiple of the CTA width %d", T0, NT); return QC_EINVAL; }
+    P.ns = ns; P.T0 = T0;
+    P.in = in; P.in_stride = in_stride; P.n_in = count; P.out = out; P.out_stride = out_stride;
+    P.nco = d_nco; P.n_base = n_base; P.tune = tune ? 1 : 0;
+    int off = 0, coff = 0, chunk_in = T0, n = count;
+    for (int s = 0; s < ns; s++) {
+        BatchFilter *f = cst[s];
+        FStage &S = P.st[s];
+        memset(&S, 0, sizeof(S));
+        S.Hs = f->H;
+        S.hin = (const cd *)f->d_hist[f->cur];
+        S.hout = (cd *)f->d_hist[f->cur ^ 1];
+        if (f->kind == QC_C_DECIM2_HB45) {
+            S.type = 0; S.D = 2; S.nTaps = 43; S.Ha = 48;
+            S.u0 = 1 - f->phase;
+            const int nout = chunk_in / 2;
+            S.R = nout > 4 * NT ? 8 : (nout > 2 * NT ? 4 : 2);
+            if (fused_min_r > S.R) S.R = fused_min_r;
+            S.pu = 2 * S.R;
+            S.magic = (unsigned)((0x100000000ULL + S.pu - 1) / S.pu);
+            // window start of thread 0 (logical Ha + u0 - 42) must land on a pad boundary
+            const int ws = S.Ha + S.u0 - 42;
+            S.org = (S.pu - (ws % S.pu)) % S.pu;
+            const int qmax = S.Ha + chunk_in + S.org + 2 * S.R + 64;
+            S.buf_len = qmax + qmax / S.pu + 8;
+            const int q0 = ws + S.org;
+            S.p0 = q0 + q0 / S.pu;
+        } else {
+            S.type = 1; S.D = f->decim; S.nTaps = f->nTaps; S.TS = 8;
+            S.Kpad = ((f->nTaps + S.TS * FIR_KB - 1) / (S.TS * FIR_KB)) * (S.TS * FIR_KB);
+            S.Ha = S.Kpad + 8;
+            S.u0 = f->decim - 1 - f->phase;
+            S.R = FIR_R; S.pu = 0; S.magic = 0; S.org = 0;
+            S.coef = coff;
+            for (int k = 0; k < S.Kpad; k++) P.coef[coff + k] = k < f->nTaps ? f->h_coef[k] : 0.0;
+            coff += S.Kpad;
+            // the last thread group may read R*D samples past the chunk when n_out is not a multiple of R
+            S.buf_len = S.Ha + chunk_in + S.D * FIR_R + 16;
+        }
+        S.buf = off;
+        off += S.buf_len;
+        S.n_full = chunk_in;
+        S.n_out_full = chunk_in / S.D;
+        // host-side phase bookkeeping, same formulas as BatchFilter::run
+        const int no = f->count_out(n, 0);
+        if (f->kind == QC_C_DECIM2_HB45) f->phase = (f->phase + n) & 1;
+        else f->phase = (f->phase + n) % f->decim;
+        f->cur ^= 1;
+        n = no;
+        chunk_in = chunk_in / S.D;
+    }
+    P.scratch = off;
+    {
+        int tot = 0;
+        for (int s = 0; s < ns; s++) tot += P.st[s].Ha;
+        if (tot > 512) { set_error("fused decimator: %d history elements exceed the slide capacity", tot); return QC_EINVAL; }
+    }
+    P.coef_sm = off; P.ncoef = coff;
+    off += (coff + 1) / 2 + 1;
+    P.smem_cd = off;
+    *n_out = n;
+    const size_t sh = (size_t)off * sizeof(cd);
+    if (sh > 226 * 1024) { set_error("fused decimator: %zu bytes of shared memory needed", sh); return QC_EINVAL; }
+    if (!fd->attr_set) {
+#define QC_OPTIN(...) QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))
+        QC_OPTIN(128, 8, 2); QC_OPTIN(128, 4, 2); QC_OPTIN(128, 2, 2);
+        QC_OPTIN(128, 8, 4); QC_OPTIN(128, 4, 4); QC_OPTIN(128, 2, 4);
+        QC_OPTIN(128, 8, 3); QC_OPTIN(128, 4, 3);
+        QC_OPTIN(256, 4, 1); QC_OPTIN(256, 2, 1);
+        QC_OPTIN(256, 4, 2); QC_OPTIN(256, 2, 2);
+#undef QC_OPTIN
+        fd->attr_set = true;
+    }
+    const int R0 = P.st[0].type == 0 ? P.st[0].R : 2;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timing) {
+        QC_CUDA(cudaEventCreate(&e0)); QC_CUDA(cudaEventCreate(&e1));
+        QC_CUDA(cudaEventRecord(e0, strm));
+    }
+    const bool dense = fused_dense != 0;        // more CTAs per SM at a 128-register cap
+    if (NT == 256) {
+        if (R0 == 4) { if (dense) fused_decim_kernel<256, 4, 2><<<C, 256, sh, strm>>>(P); else fused_decim_kernel<256, 4, 1><<<C, 256, sh, strm>>>(P); }
+        else if (R0 == 2) { if (dense) fused_decim_kernel<256, 2, 2><<<C, 256, sh, strm>>>(P); else fused_decim_kernel<256, 2, 1><<<C, 256, sh, strm>>>(P); }
+        else { set_error("fused decimator: unsupported stage-0 blocking %d at 256 threads", R0); return QC_EINVAL; }
+    } else {
+        if (R0 == 8) { if (fused_dense == 2) fused_decim_kernel<128, 8, 3><<<C, 128, sh, strm>>>(P); else if (dense) fused_decim_kernel<128, 8, 4><<<C, 128, sh, strm>>>(P); else fused_decim_kernel<128, 8, 2><<<C, 128, sh, strm>>>(P); }
+        else if (R0 == 4) { if (fused_dense == 2) fused_decim_kernel<128, 4, 3><<<C, 128, sh, strm>>>(P); else if (dense) fused_decim_kernel<128, 4, 4><<<C, 128, sh, strm>>>(P); else fused_decim_kernel<128, 4, 2><<<C, 128, sh, strm>>>(P); }
+        else { if (dense) fused_decim_kernel<128, 2, 4><<<C, 128, sh, strm>>>(P); else fused_decim_kernel<128, 2, 2><<<C, 128, sh, strm>>>(P); }
+    }
+    count_launch();
+    QC_CUDA_LAUNCH();
+    if (timing) { QC_CUDA(cudaEventRecord(e1, strm)); timed.push_back(std::make_pair(e0, e1)); }
+    return QC_OK;
+}
+
 int RxChain::reset_fused() { return QC_OK; }
-void RxChain::release_fused() {}
+
+void RxChain::release_fused()
+{
+    if (fd) { delete fd; fd = nullptr; }
+}
 
 }  // namespace qc

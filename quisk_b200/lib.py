@@ -73,6 +73,8 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rx_process.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p, vp, C.c_long, c_int_p, vp]
     lib.quisk_cuda_rx_process_host.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p]
     lib.quisk_cuda_rx_reset.argtypes = [vp]
+    lib.quisk_cuda_rx_set_option.argtypes = [vp, C.c_int, C.c_int]
+    lib.quisk_cuda_rx_kernel_time.argtypes = [vp, c_double_p, c_int_p]
     lib.quisk_cuda_pan_create.argtypes = [C.c_int, C.c_int]
     lib.quisk_cuda_pan_create.restype = vp
     lib.quisk_cuda_pan_destroy.argtypes = [vp]

@@ -102,6 +102,15 @@ class RxChain:
 
     def reset(self): L.check(self.lib, self.lib.quisk_cuda_rx_reset(self.h), "rx_reset")
 
+    def set_option(self, option: int, value: int):
+        L.check(self.lib, self.lib.quisk_cuda_rx_set_option(self.h, option, value), "rx_set_option")
+
+    def kernel_time(self):
+        """(total ms, launches) of the event-timed dominant kernel since the last call."""
+        ms, n = C.c_double(0), C.c_int(0)
+        L.check(self.lib, self.lib.quisk_cuda_rx_kernel_time(self.h, C.byref(ms), C.byref(n)), "rx_kernel_time")
+        return ms.value, n.value
+
     def close(self):
         if self.h:
             self.lib.quisk_cuda_rx_destroy(self.h); self.h = None
