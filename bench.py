@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="fused decimator CTA width (128/256), 0 = default")
     ap.add_argument("--min-r", type=int, default=0, help="fused decimator: min outputs per thread in half-band stages")
     ap.add_argument("--dense", type=int, default=-1, help="fused decimator: 1 = 128-register cap, 0 = 255")
+    ap.add_argument("--plans", type=int, default=-1, help="fused decimator: 0 = generic kernel only")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -202,14 +203,15 @@ def main():
         if rank != 0:
             return
         ref_block = 61440
-        v, cores, dt = cpu_reference_rate(ref_block, args.steps, args.warmup, args.workload, fi, fq, args.tune)
+        blocks_per_step = 32
+        v, cores, dt = cpu_reference_rate(ref_block, args.steps * blocks_per_step, args.warmup * blocks_per_step, args.workload, fi, fq, args.tune)
         line = {"impl": "reference", "metric": "complex MS/s through RX chain", "value": v, "unit": "MS/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl_name, "channels": cores, "block": ref_block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune},
+                "config": {"workload": wl_name, "channels": cores, "block": ref_block * blocks_per_step, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune},
                 "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
-                                 "sample": "%d channels (one per host core) x %d samples x %d steps; oracle/_ref = filter.c verbatim + quisk.c RX functions, gcc -O2"
-                                           % (cores, ref_block, args.steps)},
+                                 "sample": "%d channels (one per host core) x %d blocks of %d samples per step x %d steps; oracle/_ref = filter.c verbatim + quisk.c RX functions, gcc -O2"
+                                           % (cores, blocks_per_step, ref_block, args.steps)},
                 "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line)); return
 
@@ -239,6 +241,8 @@ def main():
             rx.set_option(4, args.min_r)
         if args.dense >= 0:
             rx.set_option(5, args.dense)
+        if args.plans >= 0:
+            rx.set_option(6, args.plans)
         acap = rx.max_out(block)
         audio = torch.zeros((C_, acap), dtype=torch.float64, device=dev)
     if "panadapter" in args.workload:
@@ -320,10 +324,15 @@ def main():
     roofline = None
     if rx and kn > 0:
         per_launch_ms = kms / kn
-        alg = (16.0 + 16.0 / 32.0) * C_ * block             # fused decimator: 16 B in, 16 B out per 32 inputs
+        # fused kernel = tune + 4xHB45 + FIR/2 + HB45 + FIR/2: 16 B in per input sample, 16 B out per 128 inputs
+        alg = (16.0 + 16.0 / 128.0) * C_ * block
         ach = alg / (per_launch_ms / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "fused_decim_kernel (tune + 4xHB45 + FIR98/2)", "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):      # dram__bytes_read+write of one `ncu --set full` capture, scaled to this launch size
+            traffic = json.load(open(tp))["dram_bytes_per_input_sample"] * C_ * block
+        roofline = {"bound": "hbm", "kernel": "fused_decim_kernel (tune + 4xHB45 + FIR98/2 + HB45 + FIR98/2, 1.536 MS/s -> 12 kS/s)", "achieved": ach, "peak": peak,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kms / ms,
                     "alg_bytes_per_launch": alg}
     elif pan:
@@ -335,9 +344,9 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            v, cores, dt = cpu_reference_rate(61440, 40, 2, args.workload, fi, fq, args.tune)
+            v, cores, dt = cpu_reference_rate(61440, 600, 5, args.workload, fi, fq, args.tune)
             cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
-                   "sample": "%d channels (one per host core) x 61440 samples x 40 steps, %.1f s wall; oracle/_ref (filter.c verbatim + quisk.c RX functions, gcc -O2)" % (cores, dt)}
+                   "sample": "%d channels (one per host core) x 61440 samples x 600 blocks, %.1f s wall (%.0f core-seconds); oracle/_ref (filter.c verbatim + quisk.c RX functions, gcc -O2)" % (cores, dt, dt * cores)}
         except Exception as ex:     # the compiled reference did not travel: say so
             cpu = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
 

@@ -224,12 +224,16 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_TIMING       1   /* value != 0: record CUDA events around the dominant (fused) kernel */
 #define QC_RX_OPT_FUSED_CHUNK  2   /* target input samples per shared-memory chunk of the fused decimator */
 #define QC_RX_OPT_FUSED_THREADS 3  /* CTA width of the fused decimator: 128 or 256 */
+#define QC_RX_OPT_TRACE        7   /* debug: record clock64() stamps per chunk phase in the fused kernel */
+#define QC_RX_OPT_FUSED_PLANS  6   /* 1 (default): use plan-specialised kernels when the stage list matches one */
 #define QC_RX_OPT_FUSED_DENSE  5   /* 1: 128-register cap (more resident CTAs), 0: up to 255 registers */
 #define QC_RX_OPT_FUSED_MIN_R  4   /* minimum outputs per thread in its half-band stages: 0 (auto), 2, 4, 8 */
 int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value);
 /* Sum of the event-timed durations (ms) of the dominant kernel since the last call, and how
  * many launches that covers.  Synchronises on the recorded events. */
 int quisk_cuda_rx_kernel_time(qcRxChain *rx, double *ms_total, int *launches);
+/* Debug: copy the [n_channels][16 chunks][16 stamps] clock64() trace of the last fused launch to the host. */
+int quisk_cuda_rx_read_trace(qcRxChain *rx, long long *host_out, int n_channels);
 
 /* ------------------------------------------------------------------------
  * 3b. Batched panadapter (get_graph, quisk.c:5142-5331)

@@ -227,9 +227,11 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
 
     const cd *cur = (const cd *)d_iq; long stride = iq_stride; int n = count; int pp = 0;
     size_t first_stage = 0;
-    if (fused && fused_applicable()) {
-        rc = run_fused_decimator(cur, stride, count, bufc[0], cap, &n, s); if (rc != QC_OK) return rc;
-        cur = bufc[0]; stride = cap; pp = 1; first_stage = n_fused_stages;
+    // fuse through the demodulator's own pre-decimation unless the caller wants the 48 kS/s tap
+    const size_t nf = fused ? fusable_prefix(d_decim ? (size_t)n_decim_stages : cst.size()) : 0;
+    if (nf > 0) {
+        rc = run_fused_decimator(nf, cur, stride, count, bufc[0], cap, &n, s); if (rc != QC_OK) return rc;
+        cur = bufc[0]; stride = cap; pp = 1; first_stage = nf;
         if (tune) n_base += (unsigned long long)count;
     } else if (tune) {
         rc = launch_tune(cur, stride, bufc[0], cap, n, C, d_nco, n_base, s); if (rc != QC_OK) return rc;
@@ -366,6 +368,11 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
     case QC_RX_OPT_FUSED_THREADS:
         if (value != 128 && value != 256) { qc::set_error("rx_set_option: threads must be 128 or 256"); return QC_EINVAL; }
         rx->rx.fused_threads = value; return QC_OK;
+    case QC_RX_OPT_TRACE:
+        if (value && !rx->rx.d_trace) { QC_CUDA(cudaMalloc((void **)&rx->rx.d_trace, (size_t)rx->rx.C * 256 * sizeof(long long))); QC_CUDA(cudaMemset(rx->rx.d_trace, 0, (size_t)rx->rx.C * 256 * sizeof(long long))); }
+        if (!value && rx->rx.d_trace) { cudaFree(rx->rx.d_trace); rx->rx.d_trace = nullptr; }
+        return QC_OK;
+    case QC_RX_OPT_FUSED_PLANS: rx->rx.fused_plans = value != 0; return QC_OK;
     case QC_RX_OPT_FUSED_DENSE: rx->rx.fused_dense = value; return QC_OK;
     case QC_RX_OPT_FUSED_MIN_R:
         if (value != 0 && value != 2 && value != 4 && value != 8) { qc::set_error("rx_set_option: min R must be 0/2/4/8"); return QC_EINVAL; }
@@ -373,6 +380,15 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
     }
     qc::set_error("rx_set_option: unknown option %d", option);
     return QC_EINVAL;
+}
+
+int quisk_cuda_rx_read_trace(qcRxChain *rx, long long *host_out, int n_channels)
+{
+    if (!rx || !rx->rx.d_trace) { qc::set_error("rx_read_trace: tracing is off"); return QC_EINVAL; }
+    if (n_channels > rx->rx.C) n_channels = rx->rx.C;
+    QC_CUDA(cudaDeviceSynchronize());
+    QC_CUDA(cudaMemcpy(host_out, rx->rx.d_trace, (size_t)n_channels * 256 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return QC_OK;
 }
 
 int quisk_cuda_rx_kernel_time(qcRxChain *rx, double *ms_total, int *launches)

@@ -38,7 +38,9 @@ struct RxChain {
     size_t n_fused_stages = 0;
     int fused_chunk = 2048;             // target input samples per shared-memory chunk
     int fused_threads = 128;            // CTA width of the fused kernel (128 or 256)
-    int fused_dense = 1;                // 1: cap registers at 128/thread for more resident CTAs
+    long long *d_trace = nullptr;       // debug: per-chunk clock64() stamps of the fused kernel
+    int fused_plans = 1;                // use the plan-specialised instantiations when one matches
+    int fused_dense = 0;                // 1: cap registers at 128/thread for more resident CTAs
     int fused_min_r = 0;                // force at least this many outputs per thread in half-band stages
     // optional device timing of the dominant (fused) kernel
     bool timing = false;
@@ -55,8 +57,8 @@ struct RxChain {
     int process_host(const quisk_cd *h_iq, long iq_stride, int count, double *h_audio, long audio_stride, int *n_audio);
     int reset();
     // rxfused.cu
-    bool fused_applicable();
-    int run_fused_decimator(const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t s);
+    size_t fusable_prefix(size_t limit);
+    int run_fused_decimator(size_t n_stages, const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t s);
     int reset_fused();
     void release_fused();
 };

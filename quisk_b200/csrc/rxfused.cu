@@ -46,6 +46,7 @@ struct FStage {
     int buf_len;        // physical length (cd units)
     int coef;           // FIR: offset into FusedParams::coef
     int Kpad, TS;       // FIR: zero-padded tap count, tap splits
+    int Rplan;          // FIR: outputs per thread in the plan-specialised kernels
     int p0;             // half band: physical index of thread 0's window start
     int n_full;         // new samples this stage sees per full chunk
     int n_out_full;     // outputs per full chunk
@@ -64,6 +65,7 @@ struct FusedParams {
     int scratch;        // offset of the history-slide scratch area (cd units)
     int coef_sm;        // offset of the tap copy in shared memory (cd units)
     int ncoef;
+    long long *trace;   // optional [C][16 chunks][16] clock64() stamps (debug)
     double coef[MAXCOEF];
 };
 
@@ -176,9 +178,94 @@ __device__ __forceinline__ void fir_stage(const cd *__restrict__ sb, const FStag
     }
 }
 
+// Plan-specialised FIR: the whole (zero-padded) tap table is TS * KB long, so a lane's KB taps never
+// change -- they are loaded into registers once per kernel (cf) -- and one register window of
+// KB + D (R - 1) samples feeds R outputs.  lane = g * TS + ts.
+template <int D, int NT, int R>
+__device__ __forceinline__ void fir_stage_c(const cd *__restrict__ sb, const FStage &s, const double (&cf)[FIR_KB],
+                                            int n_out, const Sink &sink)
+{
+    constexpr int KB = FIR_KB, W = KB + D * (R - 1), TS = 8;
+    const int t = threadIdx.x;
+    const int ts = t & (TS - 1);
+    int g = t / TS;
+    const int n_groups = (n_out + R - 1) / R;
+    const int rounds = (n_groups * TS + NT - 1) / NT;           // uniform
+    for (int round = 0; round < rounds; round++, g += NT / TS) {
+        const bool live = g < n_groups;
+        const int gg = live ? g : 0;
+        cd acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = make_double2(0.0, 0.0);
+        const cd *w = sb + (s.Ha + s.u0 + D * R * gg - ts * KB - (KB - 1) + s.org);
+        cd Wn[W];
+#pragma unroll
+        for (int i = 0; i < W; i++) Wn[i] = w[i];
+#pragma unroll
+        for (int kk = 0; kk < KB; kk++) {
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = fmaz(Wn[D * r + KB - 1 - kk], cf[kk], acc[r]);
+        }
+#pragma unroll
+        for (int off = TS >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, off);
+                acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, off);
+            }
+        }
+        if (live && ts == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (R * g + r < n_out) sink.put(R * g + r, acc[r]);
+        }
+    }
+}
+
+// register-resident tap sets for the (at most MAXFIR) FIR stages of a plan
+static constexpr int MAXFIR = 2;
+struct FirTaps { double cf[MAXFIR][FIR_KB]; };
+
 __device__ __forceinline__ int stage_out_count(const FStage &s, int n_in)
 {
     return n_in > s.u0 ? (n_in - s.u0 - 1) / s.D + 1 : 0;
+}
+
+// ---- plan-specialised cascade: stage kinds are template constants (CODE = type*100 + R*10 + D), the
+//      stage index is static, so every descriptor field is a constant-bank operand and the chunk
+//      loop is straight-line code.  A partial (ragged) chunk uses the same code with runtime counts.
+template <int NT, int CODE, int IDX, bool LAST, int FIRIDX>
+__device__ __forceinline__ void run_stage_c(cd *sm, const FusedParams &P, int n_out, cd *gdst, const FirTaps &ft)
+{
+    constexpr int TYPE = CODE / 100, R = (CODE / 10) % 10, D = CODE % 10;
+    const FStage &S = P.st[IDX];
+    Sink sink;
+    if constexpr (!LAST) {
+        const FStage &N = P.st[IDX + 1];
+        sink.sm = sm + N.buf; sink.H = N.Ha; sink.org = N.org; sink.magic = N.magic; sink.g = nullptr;
+    } else {
+        sink.sm = nullptr; sink.H = 0; sink.org = 0; sink.magic = 0; sink.g = gdst;
+    }
+    const cd *sb = sm + S.buf;
+    if constexpr (TYPE == 0) {
+        hb_stage<R>(sb, S.p0, n_out, sink);
+    } else {
+        fir_stage_c<D, NT, R>(sb, S, ft.cf[FIRIDX], n_out, sink);
+    }
+}
+
+template <int NT, bool FULL, int IDX, int FIRIDX, int CODE0, int... REST>
+__device__ __forceinline__ int cascade_c(cd *sm, const FusedParams &P, int n_in, cd *gdst, long long *tr, const FirTaps &ft)
+{
+    constexpr int D = CODE0 % 10;
+    constexpr int NEXTFIR = FIRIDX + (CODE0 / 100 == 1 ? 1 : 0);
+    const FStage &S = P.st[IDX];
+    const int n_out = FULL ? S.n_out_full : (n_in > S.u0 ? (n_in - S.u0 - 1) / D + 1 : 0);
+    run_stage_c<NT, CODE0, IDX, sizeof...(REST) == 0, FIRIDX>(sm, P, n_out, gdst, ft);
+    __syncthreads();
+    if (FULL && tr) tr[3 + IDX] = clock64();
+    if constexpr (sizeof...(REST) > 0) return cascade_c<NT, FULL, IDX + 1, NEXTFIR, REST...>(sm, P, n_out, gdst, tr, ft);
+    else return n_out;
 }
 
 // One stage of the cascade for n_out outputs (uniform across the CTA).
@@ -207,7 +294,7 @@ __device__ __forceinline__ void run_stage(cd *sm, const FusedParams &P, int s, i
     }
 }
 
-template <int NT, int R0, int MINB>
+template <int NT, int R0, int MINB, int... PLAN>
 __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_constant__ FusedParams P)
 {
     extern __shared__ double smem_raw[];
@@ -230,10 +317,14 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
         double *cs = reinterpret_cast<double *>(sm + P.coef_sm);
         for (int i = tid; i < P.ncoef; i += NT) cs[i] = P.coef[i];
     }
+    // NCO: sample k*NT + tid of a chunk is multiplied by u * s_q[k], u = v(chunk start + tid),
+    // s_q[k] = phase^(k NT); u advances by pstep = phase^T0 per chunk.  No per-sample recurrence.
+    __shared__ cd s_q[2048 / NT];
     cd u = make_double2(1.0, 0.0), pstep = make_double2(1.0, 0.0);
     if (P.tune) {
         const double *nc = P.nco + (size_t)c * 8;
-        if (tid == 0) s_pstep = nco_pow(nc, (unsigned long long)NT);
+        if (tid == 0) s_pstep = nco_pow(nc, (unsigned long long)P.T0);
+        if (tid < 2048 / NT) s_q[tid] = nco_pow(nc, (unsigned long long)tid * NT);
         u = cmul_rn(make_double2(nc[3], nc[4]), nco_pow(nc, P.n_base + (unsigned long long)tid));
     }
     // slide table for full chunks: which shared-memory element this thread moves where
@@ -250,6 +341,22 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
     }
     __syncthreads();
     if (P.tune) pstep = s_pstep;
+    // register-resident taps of the plan's FIR stages (lane's tap split is ts = tid & 7)
+    FirTaps ft;
+    if constexpr (sizeof...(PLAN) > 0) {
+        const double *cs = reinterpret_cast<const double *>(sm + P.coef_sm);
+        int fi = 0;
+        for (int s = 0; s < P.ns && fi < MAXFIR; s++) {
+            if (P.st[s].type == 1) {
+#pragma unroll
+                for (int kk = 0; kk < FIR_KB; kk++) {
+                    const double v = cs[P.st[s].coef + (tid & 7) * FIR_KB + kk];
+                    if (fi == 0) ft.cf[0][kk] = v; else ft.cf[1][kk] = v;
+                }
+                fi++;
+            }
+        }
+    }
 
     const cd *gin = P.in + (size_t)c * P.in_stride;
     cd *gout = P.out + (size_t)c * P.out_stride;
@@ -263,48 +370,58 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
 
     const int n_full = P.n_in / P.T0;
     const int rem = P.n_in - n_full * P.T0;
-    const int nld = P.T0 / NT;                  // loads per thread in a full chunk (uniform)
+    constexpr bool FIXED = sizeof...(PLAN) > 0; // plan kernels always run T0 == 2048: no per-load guards
+    const int nld = FIXED ? NLD : P.T0 / NT;    // loads per thread in a full chunk (uniform)
 
     // The next chunk's samples are fetched into registers while the current chunk is worked on:
     // up to NLD independent 16-byte loads per thread stay in flight across the whole cascade.
     cd nx[NLD];
     if (n_full > 0) {
 #pragma unroll
-        for (int k = 0; k < NLD; k++) if (k < nld) nx[k] = gin[k * NT + tid];
+        for (int k = 0; k < NLD; k++) if (FIXED || k < nld) nx[k] = gin[k * NT + tid];
     }
     int out_pos = 0;
     for (int ch = 0; ch < n_full; ch++) {
+        long long *tr = (P.trace && tid == 0 && ch < 16) ? P.trace + ((size_t)c * 16 + ch) * 16 : nullptr;
+        if (tr) tr[0] = clock64();
         // ---- commit the prefetched chunk behind stage 0's history, applying the NCO on the way
         if (tune) {
 #pragma unroll
             for (int k = 0; k < NLD; k++) {
-                if (k < nld) {
-                    // x * v with fused multiply-adds; v advances NT samples per step
-                    nx[k] = make_double2(fma(nx[k].x, u.x, -nx[k].y * u.y), fma(nx[k].x, u.y, nx[k].y * u.x));
-                    u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
+                if (FIXED || k < nld) {
+                    const cd q = s_q[k];
+                    const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                    nx[k] = make_double2(fma(nx[k].x, v.x, -nx[k].y * v.y), fma(nx[k].x, v.y, nx[k].y * v.x));
                 }
             }
+            u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
         }
         if (pad0) {
 #pragma unroll
-            for (int k = 0; k < NLD; k++) if (k < nld) pb0[k * STEP_PAD] = nx[k];
+            for (int k = 0; k < NLD; k++) if (FIXED || k < nld) pb0[k * STEP_PAD] = nx[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < NLD; k++) if (k < nld) pb0[k * NT] = nx[k];
+            for (int k = 0; k < NLD; k++) if (FIXED || k < nld) pb0[k * NT] = nx[k];
         }
         __syncthreads();
+        if (tr) tr[1] = clock64();
         // ---- start fetching the next full chunk
         if (ch + 1 < n_full) {
             const cd *g1 = gin + (size_t)(ch + 1) * P.T0 + tid;
 #pragma unroll
-            for (int k = 0; k < NLD; k++) if (k < nld) nx[k] = g1[k * NT];
+            for (int k = 0; k < NLD; k++) if (FIXED || k < nld) nx[k] = g1[k * NT];
         }
+        if (tr) tr[2] = clock64();
         // ---- the cascade
-        for (int s = 0; s < P.ns; s++) {
-            run_stage<NT>(sm, P, s, P.st[s].n_out_full, gout + out_pos);
-            __syncthreads();
+        if constexpr (sizeof...(PLAN) > 0) {
+            out_pos += cascade_c<NT, true, 0, 0, PLAN...>(sm, P, P.T0, gout + out_pos, tr, ft);
+        } else {
+            for (int s = 0; s < P.ns; s++) {
+                run_stage<NT>(sm, P, s, P.st[s].n_out_full, gout + out_pos);
+                __syncthreads();
+            }
+            out_pos += P.st[P.ns - 1].n_out_full;
         }
-        out_pos += P.st[P.ns - 1].n_out_full;
         // ---- slide the histories: tail -> registers, barrier, registers -> front.  The writes are
         //      ordered against the next reads by the barrier that follows the next commit.
         cd keep[NSL];
@@ -313,28 +430,33 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < NSL; e++) if (sl_src[e] >= 0) sm[sl_dst[e]] = keep[e];
+        if (tr) tr[15] = clock64();
     }
     __syncthreads();
     // ---- ragged tail (at most one partial chunk), generic indexing
     int n_s = 0;
     if (rem > 0) {
         const cd *g1 = gin + (size_t)n_full * P.T0;
-        for (int i = tid; i < ((rem + NT - 1) / NT) * NT; i += NT) {
-            cd x = make_double2(0.0, 0.0);
-            if (i < rem) x = g1[i];
+        for (int i = tid, k = 0; i < rem; i += NT, k++) {
+            cd x = g1[i];
             if (P.tune) {
-                x = make_double2(fma(x.x, u.x, -x.y * u.y), fma(x.x, u.y, x.y * u.x));
-                u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
+                const cd q = s_q[k];
+                const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                x = make_double2(fma(x.x, v.x, -x.y * v.y), fma(x.x, v.y, x.y * v.x));
             }
-            if (i < rem) sm[S0.buf + phys(S0, S0.Ha + i)] = x;
+            sm[S0.buf + phys(S0, S0.Ha + i)] = x;
         }
         __syncthreads();
-        int n_in = rem;
-        for (int s = 0; s < P.ns; s++) {
-            const int n_out = stage_out_count(P.st[s], n_in);
-            run_stage<NT>(sm, P, s, n_out, gout + out_pos);
-            n_in = n_out;
-            __syncthreads();
+        if constexpr (sizeof...(PLAN) > 0) {
+            cascade_c<NT, false, 0, 0, PLAN...>(sm, P, rem, gout + out_pos, nullptr, ft);
+        } else {
+            int n_in = rem;
+            for (int s = 0; s < P.ns; s++) {
+                const int n_out = stage_out_count(P.st[s], n_in);
+                run_stage<NT>(sm, P, s, n_out, gout + out_pos);
+                n_in = n_out;
+                __syncthreads();
+            }
         }
         n_s = rem;
     }
@@ -360,34 +482,32 @@ static bool stage_fusable(const BatchFilter *f)
     return false;
 }
 
-bool RxChain::fused_applicable()
+size_t RxChain::fusable_prefix(size_t limit)
 {
-    if (fd) return n_fused_stages > 0;
-    fd = new FusedDecimator();
-    // leading run of half-band / FIR-decimate stages of quisk_process_decimate
+    if (!fd) fd = new FusedDecimator();
+    // leading run of half-band / FIR-decimate stages (quisk_process_decimate, then the demodulator's own)
     size_t n = 0;
-    int ncoef = 0;
+    int ncoef = 0, hist = 0;
     long dtot = 1;
-    while (n < (size_t)n_decim_stages && n < (size_t)MAXST && stage_fusable(cst[n])) {
+    while (n < limit && n < cst.size() && n < (size_t)MAXST && stage_fusable(cst[n])) {
         const BatchFilter *f = cst[n];
         long d = f->kind == QC_C_DECIM2_HB45 ? 2 : f->decim;
-        int kp = 0;
-        if (f->kind == QC_C_DECIMATE) kp = ((f->nTaps + 8 * FIR_KB - 1) / (8 * FIR_KB)) * (8 * FIR_KB);
+        int kp = 0, ha = 48;
+        if (f->kind == QC_C_DECIMATE) { kp = ((f->nTaps + 8 * FIR_KB - 1) / (8 * FIR_KB)) * (8 * FIR_KB); ha = kp + 8; }
         // the chunk must be a multiple of both the total decimation and the CTA width
         long l = dtot * d;
         long lcm = l;
         while (lcm % FNT) lcm += l;
-        if (lcm > 2048 || ncoef + kp > MAXCOEF) break;
-        dtot = l; ncoef += kp; n++;
+        if (lcm > 2048 || ncoef + kp > MAXCOEF || hist + ha > 512) break;
+        dtot = l; ncoef += kp; hist += ha; n++;
     }
-    n_fused_stages = n;
-    return n > 0;
+    return n;
 }
 
-int RxChain::run_fused_decimator(const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t strm)
+int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t strm)
 {
     FusedParams &P = fd->P;
-    const int ns = (int)n_fused_stages;
+    const int ns = (int)n_stages;
     // total decimation and chunk size
     int dtot = 1;
     for (int s = 0; s < ns; s++) dtot *= (cst[s]->kind == QC_C_DECIM2_HB45 ? 2 : cst[s]->decim);
@@ -402,6 +522,7 @@ int RxChain::run_fused_decimator(const cd *in, long in_stride, int count, cd *ou
     P.ns = ns; P.T0 = T0;
     P.in = in; P.in_stride = in_stride; P.n_in = count; P.out = out; P.out_stride = out_stride;
     P.nco = d_nco; P.n_base = n_base; P.tune = tune ? 1 : 0;
+    P.trace = d_trace;
     int off = 0, coff = 0, chunk_in = T0, n = count;
     for (int s = 0; s < ns; s++) {
         BatchFilter *f = cst[s];
@@ -431,6 +552,11 @@ int RxChain::run_fused_decimator(const cd *in, long in_stride, int count, cd *ou
             S.Ha = S.Kpad + 8;
             S.u0 = f->decim - 1 - f->phase;
             S.R = FIR_R; S.pu = 0; S.magic = 0; S.org = 0;
+            {   // plan kernels: outputs per thread so that one round of NT threads covers the chunk
+                const int no = chunk_in / S.D;
+                int r = (no * 8 + NT - 1) / NT;
+                S.Rplan = r >= 4 ? 4 : (r >= 2 ? 2 : 1);
+            }
             S.coef = coff;
             for (int k = 0; k < S.Kpad; k++) P.coef[coff + k] = k < f->nTaps ? f->h_coef[k] : 0.0;
             coff += S.Kpad;
@@ -461,32 +587,40 @@ int RxChain::run_fused_decimator(const cd *in, long in_stride, int count, cd *ou
     *n_out = n;
     const size_t sh = (size_t)off * sizeof(cd);
     if (sh > 226 * 1024) { set_error("fused decimator: %zu bytes of shared memory needed", sh); return QC_EINVAL; }
-    if (!fd->attr_set) {
-#define QC_OPTIN(...) QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024))
-        QC_OPTIN(128, 8, 2); QC_OPTIN(128, 4, 2); QC_OPTIN(128, 2, 2);
-        QC_OPTIN(128, 8, 4); QC_OPTIN(128, 4, 4); QC_OPTIN(128, 2, 4);
-        QC_OPTIN(128, 8, 3); QC_OPTIN(128, 4, 3);
-        QC_OPTIN(256, 4, 1); QC_OPTIN(256, 2, 1);
-        QC_OPTIN(256, 4, 2); QC_OPTIN(256, 2, 2);
-#undef QC_OPTIN
-        fd->attr_set = true;
-    }
     const int R0 = P.st[0].type == 0 ? P.st[0].R : 2;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timing) {
         QC_CUDA(cudaEventCreate(&e0)); QC_CUDA(cudaEventCreate(&e1));
         QC_CUDA(cudaEventRecord(e0, strm));
     }
-    const bool dense = fused_dense != 0;        // more CTAs per SM at a 128-register cap
-    if (NT == 256) {
-        if (R0 == 4) { if (dense) fused_decim_kernel<256, 4, 2><<<C, 256, sh, strm>>>(P); else fused_decim_kernel<256, 4, 1><<<C, 256, sh, strm>>>(P); }
-        else if (R0 == 2) { if (dense) fused_decim_kernel<256, 2, 2><<<C, 256, sh, strm>>>(P); else fused_decim_kernel<256, 2, 1><<<C, 256, sh, strm>>>(P); }
+    // plan code per stage: type*100 + R*10 + D
+    int codes[MAXST]; bool plan_ok = NT == 128 && fused_plans && T0 == 2048;
+    for (int s = 0; s < ns; s++) codes[s] = P.st[s].type * 100 + (P.st[s].type ? P.st[s].Rplan : P.st[s].R) * 10 + P.st[s].D;
+    for (int s = 0; s < ns; s++) if (P.st[s].type == 1 && P.st[s].Kpad != 8 * FIR_KB) plan_ok = false;
+    auto is_plan = [&](std::initializer_list<int> pl) {
+        if (!plan_ok || (int)pl.size() != ns) return false;
+        int i = 0;
+        for (int c : pl) if (codes[i++] != c) return false;
+        return true;
+    };
+#define QC_LAUNCH(...) do { \
+        static bool optin = false; \
+        if (!optin) { QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin = true; } \
+        fused_decim_kernel<__VA_ARGS__><<<C, NT, sh, strm>>>(P); } while (0)
+    if (is_plan({82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142);                       // 1.536 MS/s -> 48 k
+    else if (is_plan({82, 42, 22, 22, 142, 22, 112})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142, 22, 112);  // ... -> 12 k (SSB)
+    else if (is_plan({82, 42, 22, 22, 142, 22, 22, 112})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142, 22, 22, 112);  // ... -> 6 k (CW)
+    else if (is_plan({82, 42, 22, 22, 142, 122})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142, 122);          // ... -> 24 k (AM)
+    else if (NT == 256) {
+        if (R0 == 4) { if (fused_dense) QC_LAUNCH(256, 4, 2); else QC_LAUNCH(256, 4, 1); }
+        else if (R0 == 2) { if (fused_dense) QC_LAUNCH(256, 2, 2); else QC_LAUNCH(256, 2, 1); }
         else { set_error("fused decimator: unsupported stage-0 blocking %d at 256 threads", R0); return QC_EINVAL; }
     } else {
-        if (R0 == 8) { if (fused_dense == 2) fused_decim_kernel<128, 8, 3><<<C, 128, sh, strm>>>(P); else if (dense) fused_decim_kernel<128, 8, 4><<<C, 128, sh, strm>>>(P); else fused_decim_kernel<128, 8, 2><<<C, 128, sh, strm>>>(P); }
-        else if (R0 == 4) { if (fused_dense == 2) fused_decim_kernel<128, 4, 3><<<C, 128, sh, strm>>>(P); else if (dense) fused_decim_kernel<128, 4, 4><<<C, 128, sh, strm>>>(P); else fused_decim_kernel<128, 4, 2><<<C, 128, sh, strm>>>(P); }
-        else { if (dense) fused_decim_kernel<128, 2, 4><<<C, 128, sh, strm>>>(P); else fused_decim_kernel<128, 2, 2><<<C, 128, sh, strm>>>(P); }
+        if (R0 == 8) { if (fused_dense) QC_LAUNCH(128, 8, 4); else QC_LAUNCH(128, 8, 2); }
+        else if (R0 == 4) { if (fused_dense) QC_LAUNCH(128, 4, 4); else QC_LAUNCH(128, 4, 2); }
+        else { if (fused_dense) QC_LAUNCH(128, 2, 4); else QC_LAUNCH(128, 2, 2); }
     }
+#undef QC_LAUNCH
     count_launch();
     QC_CUDA_LAUNCH();
     if (timing) { QC_CUDA(cudaEventRecord(e1, strm)); timed.push_back(std::make_pair(e0, e1)); }

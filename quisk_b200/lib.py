@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rx_reset.argtypes = [vp]
     lib.quisk_cuda_rx_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.quisk_cuda_rx_kernel_time.argtypes = [vp, c_double_p, c_int_p]
+    lib.quisk_cuda_rx_read_trace.argtypes = [vp, vp, C.c_int]
     lib.quisk_cuda_pan_create.argtypes = [C.c_int, C.c_int]
     lib.quisk_cuda_pan_create.restype = vp
     lib.quisk_cuda_pan_destroy.argtypes = [vp]
