@@ -1,0 +1,108 @@
+/* include/quisk_cuda_wdsp.h -- C ABI of libquisk_cuda.so, WDSP RXA part (WDSP 1.25 as vendored by
+ * Quisk 4.2.52 under wdsp/).
+ *
+ * Batched, device-resident versions of the RXA stages the receive hot path uses: the
+ * partitioned overlap-save FIR `fircore` (wdsp/firmin.c:290-430) that nbp / bandpass / fmd run on,
+ * the rational resampler (wdsp/resample.c), the frequency shifter (wdsp/shift.c), wcpAGC
+ * (wdsp/wcpAGC.c), the FM and AM demodulators (wdsp/fmd.c, wdsp/amd.c), the patch panel and meters,
+ * and `quisk_cuda_rxa_*`: the stage order of xrxa (wdsp/RXA.c:561-598) with create_rxa's defaults
+ * (wdsp/RXA.c:31-490) for n_channels independent channels at once.
+ *
+ * All sample buffers are interleaved complex double (re, im) == the `double *` buffers of WDSP,
+ * laid out [channel][sample] in DEVICE memory.  Host-side design helpers return plain arrays.
+ * Same status codes / error string as quisk_cuda.h.
+ */
+#ifndef QUISK_CUDA_WDSP_H
+#define QUISK_CUDA_WDSP_H
+
+#include "quisk_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- host-side design (taps are computed on the CPU with libm, bit-identical to the reference) ---- */
+/* fir_bandpass, wdsp/fir.c:187-254.  rtype 0: N doubles, rtype 1: N complex. wintype 0 = BH4, 1 = BH7. */
+int quisk_cuda_fir_bandpass(int N, double f_low, double f_high, double samplerate, int wintype, int rtype,
+                            double scale, double *out);
+/* fc_impulse, wdsp/fcurve.c:29-143 (FM pre/de-emphasis), nc complex out. */
+int quisk_cuda_fc_impulse(int nc, double f0, double f1, double g0, double g1, int curve, double samplerate,
+                          double scale, int ctfmode, int wintype, double *out);
+/* calc_resample, wdsp/resample.c:35-78: L, M, ncoef and (if h != NULL) the ncoef prototype taps. */
+int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_in, double gain,
+                               int *L, int *M, int *ncoef, double *h, int h_cap);
+
+/* ---- fircore: uniformly partitioned overlap-save complex FIR (wdsp/firmin.c:290-430) ---- */
+typedef struct qcFircore qcFircore;
+/* impulse: HOST, nc complex, the same for every channel (callers bake 1/(2*size) into it exactly as
+ * nbp.c:233-237 / bandpass.c:302 do).  mp (minimum phase, fir.c mp_imp) must be 0 in this version. */
+qcFircore *quisk_cuda_fircore_create(int n_channels, int size, int nc, int mp, const double *impulse);
+void quisk_cuda_fircore_destroy(qcFircore *f);
+/* xfircore for every channel: d_in/d_out [n_channels][stride] complex, `size` samples each. in may equal out. */
+int quisk_cuda_fircore_run(qcFircore *f, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream);
+/* setImpulse_fircore (firmin.c:448-452): new masks are computed into the idle set and take effect
+ * with the next block when update != 0, or at quisk_cuda_fircore_update() (setUpdate_fircore). */
+int quisk_cuda_fircore_set_impulse(qcFircore *f, const double *impulse, int update);
+int quisk_cuda_fircore_update(qcFircore *f);
+int quisk_cuda_fircore_flush(qcFircore *f);
+
+/* ---- rational resampler (wdsp/resample.c:121-157) ---- */
+typedef struct qcResample qcResample;
+qcResample *quisk_cuda_resample_create(int n_channels, int in_rate, int out_rate, double fc, int ncoef, double gain);
+void quisk_cuda_resample_destroy(qcResample *r);
+int quisk_cuda_resample_count_out(const qcResample *r, int count);
+int quisk_cuda_resample_run(qcResample *r, const void *d_in, long in_stride, int count,
+                            void *d_out, long out_stride, int *n_out, void *stream);
+
+/* ---- per-sample recurrent stages: one GPU thread walks one channel's block ---- */
+typedef struct qcSeqStage qcSeqStage;
+/* xshift (wdsp/shift.c:60-86); shift_hz: HOST, one value per channel. */
+qcSeqStage *quisk_cuda_shift_create(int n_channels, int rate, const double *shift_hz);
+/* xwcpagc (wdsp/wcpAGC.c:161-348) with create_rxa's parameters (RXA.c:337-360) and the preset of
+ * SetRXAAGCMode(mode) (wcpAGC.c:370-411); mode 0 = fixed gain. */
+qcSeqStage *quisk_cuda_wcpagc_create(int n_channels, int rate, int mode);
+int quisk_cuda_wcpagc_set_fixed_gain_db(qcSeqStage *s, double gain_db);     /* SetRXAAGCFixed */
+int quisk_cuda_wcpagc_set_top_db(qcSeqStage *s, double max_gain_db);        /* SetRXAAGCTop */
+/* xamd (wdsp/amd.c:115-239): mode 0 AM envelope, 1 synchronous AM; sbmode 0/1/2; create_rxa's constants. */
+qcSeqStage *quisk_cuda_amd_create(int n_channels, int rate, int mode, int levelfade, int sbmode);
+/* the PLL + DC removal of xfmd (wdsp/fmd.c:144-170) and, separately, xsnotch (wdsp/iir.c:76-95) */
+qcSeqStage *quisk_cuda_fmpll_create(int n_channels, int rate, double deviation, double fmin, double fmax,
+                                    double zeta, double omegaN, double tau);
+qcSeqStage *quisk_cuda_snotch_create(int n_channels, int rate, double f, double bw);
+void quisk_cuda_seq_destroy(qcSeqStage *s);
+/* n samples per channel, in may equal out */
+int quisk_cuda_seq_run(qcSeqStage *s, const void *d_in, long in_stride, void *d_out, long out_stride, int n, void *stream);
+int quisk_cuda_seq_flush(qcSeqStage *s);
+
+/* ---- the RXA chain (wdsp/RXA.c) for a batch of channels ---- */
+typedef struct qcRxa qcRxa;
+enum qcRxaMode {    /* wdsp/RXA.h: enum rxaMode */
+    QC_RXA_LSB = 0, QC_RXA_USB = 1, QC_RXA_DSB = 2, QC_RXA_CWL = 3, QC_RXA_CWU = 4, QC_RXA_FM = 5,
+    QC_RXA_AM = 6, QC_RXA_DIGU = 7, QC_RXA_SPEC = 8, QC_RXA_DIGL = 9, QC_RXA_SAM = 10, QC_RXA_DRM = 11
+};
+/* OpenChannel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, type = 0 (RX), ...) + create_rxa. */
+qcRxa *quisk_cuda_rxa_create(int n_channels, int in_size, int dsp_size, int in_rate, int dsp_rate, int out_rate);
+void quisk_cuda_rxa_destroy(qcRxa *r);
+int quisk_cuda_rxa_set_mode(qcRxa *r, int mode);                            /* SetRXAMode,        RXA.c:749-787  */
+int quisk_cuda_rxa_set_passband(qcRxa *r, double f_low, double f_high);     /* RXASetPassband,    RXA.c:927-932  */
+int quisk_cuda_rxa_set_nc(qcRxa *r, int nc);                                /* RXASetNC,          RXA.c:935-946  */
+int quisk_cuda_rxa_set_agc_mode(qcRxa *r, int mode);                        /* SetRXAAGCMode,     wcpAGC.c:370   */
+int quisk_cuda_rxa_set_agc_fixed(qcRxa *r, double gain_db);                 /* SetRXAAGCFixed                    */
+int quisk_cuda_rxa_set_shift(qcRxa *r, int run, const double *shift_hz);    /* SetRXAShiftRun / SetRXAShiftFreq  */
+int quisk_cuda_rxa_set_nbp_run(qcRxa *r, int run);                          /* RXANBPSetRun                      */
+int quisk_cuda_rxa_set_panel_gain(qcRxa *r, double gain1);                  /* SetRXAPanelGain1                  */
+int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per channel consumed per xrxa  */
+int quisk_cuda_rxa_out_size(const qcRxa *r);     /* dsp_outsize: samples per channel produced per xrxa */
+/* xrxa (RXA.c:561-598) for one DSP block of every channel. d_in [n_channels][in_stride], d_out likewise. */
+int quisk_cuda_rxa_xrxa(qcRxa *r, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream);
+/* fexchange0-shaped entry (wdsp/iobuffs.c:464-516) with HOST buffers for all channels: copies a block in,
+ * runs xrxa, returns the block that the reference would return at this call, i.e. delayed by the two
+ * DSP buffers of its output ring (zeros first); *error = 0.  Slew ramps are not applied. */
+int quisk_cuda_rxa_fexchange0(qcRxa *r, const double *h_in, double *h_out, int *error);
+/* meters (wdsp/meter.c:75-107): which = 0 ADC, 1 S, 2 AGC; av/pk/gain in dB, HOST arrays of n_channels (any may be NULL) */
+int quisk_cuda_rxa_get_meter(qcRxa *r, int which, double *av, double *pk, double *gain);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUISK_CUDA_WDSP_H */

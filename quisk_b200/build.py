@@ -51,7 +51,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if force or _newer(obj, [src] + headers):
             log = open(obj + ".log", "w")
-            procs.append((f, log, subprocess.Popen([NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj], stdout=log, stderr=subprocess.STDOUT)))
+            flags = list(NVCC_FLAGS)
+            if f.endswith("_nofma.cu"):      # recurrent WDSP stages: a*b+c must round twice, as gcc's x86-64 code does
+                flags[flags.index("--fmad=true")] = "--fmad=false"
+            procs.append((f, log, subprocess.Popen([NVCC] + flags + ["-c", src, "-o", obj], stdout=log, stderr=subprocess.STDOUT)))
     for f in cpp:
         src = os.path.join(CSRC, f)
         obj = os.path.join(OBJ, f[:-4] + ".o")

@@ -119,7 +119,7 @@ int BatchFilter::run(const void *d_in, long in_stride, int count, void *d_out, l
     case QC_C_INTERPOLATE: case QC_D_INTERPOLATE:
         p.K = nTaps / interp; p.L = interp; p.gain = (double)interp; break;
     case QC_C_INTERPDECIM:
-        p.K = nTaps / interp; p.L = interp; p.M = decim; p.u0 = phase; p.gain = (double)interp;
+        p.K = nTaps / interp; p.L = interp; p.M = decim; p.u0 = phase; p.gain = unit_gain ? 1.0 : (double)interp;
         phase = (int)(phase + full * decim - (long)count * interp); break;
     case QC_C_INTERP2_HB45: case QC_D_INTERP2_HB45:
         p.hb_mode = HB_INTERP; break;

@@ -9,6 +9,7 @@ struct BatchFilter {
     int H = 0, esize = 16;
     int phase = 0;               // toggle (HB45) or decim_index
     int cur = 0;                 // which history buffer is current
+    bool unit_gain = false;      // interpolating kinds: do not multiply by `interp` (WDSP resampler taps carry the gain)
     double *d_coef = nullptr;
     std::vector<double> h_coef;  // host copy of the taps as uploaded
     void *d_hist[2] = {nullptr, nullptr};

@@ -1,0 +1,321 @@
+// quisk_b200/csrc/wdsp_rxa.cu -- quisk_cuda_rxa_*: WDSP's receive chain for a batch of channels.
+//
+// Mirrors create_rxa's stage list and defaults (wdsp/RXA.c:31-490) and xrxa's order
+// (wdsp/RXA.c:561-598) for the stages that run in a default / Quisk-configured channel:
+//   shift -> resample(in) -> ADC meter -> nbp0 -> S meter -> amd -> fmd -> bp1 -> wcpagc -> AGC meter
+//   -> panel -> resample(out)
+// The stages that create_rxa builds with run = 0 (gen, bpsnba, sender, amsq, fmsq, snba, eq, anf, anr,
+// emnr, cbl, speak, mpeak, ssql, siphon) are outside this round's scope and are not instantiated.
+// Quirks kept: bp1 is created running and stays so until a mode change calls RXAbp1Set;
+// xpanel ignores its run flag (F9); the panel gain is gain1 * gain2 = 4.0.
+#include "wdsp_internal.h"
+#include <cmath>
+
+namespace qc {
+
+struct Rxa {
+    int C = 0, in_size = 0, dsp_size = 0, in_rate = 0, dsp_rate = 0, out_rate = 0;
+    int dsp_insize = 0, dsp_outsize = 0, out_size = 0;
+    int mode = QC_RXA_LSB;
+    // shift
+    int shift_run = 1; bool shift_nonzero = false; SeqStage *shift = nullptr;
+    Resampler *rsmpin = nullptr, *rsmpout = nullptr;
+    SeqStage *adcmeter = nullptr, *smeter = nullptr, *agcmeter = nullptr;
+    // nbp0
+    int nbp_run = 1, nbp_nc = 0; double nbp_flow = -4150.0, nbp_fhigh = -150.0; FirCore *nbp0 = nullptr;
+    // amd / fmd
+    int amd_run = 0, amd_mode = 0; SeqStage *amd = nullptr;
+    int fmd_run = 0, fm_nc_de = 0, fm_nc_aud = 0; SeqStage *fmpll = nullptr, *sntch = nullptr; FirCore *pde = nullptr, *paud = nullptr;
+    // bp1
+    int bp1_run = 1, bp1_nc = 0; double bp1_flow = -4150.0, bp1_fhigh = -150.0, bp1_gain = 1.0; FirCore *bp1 = nullptr;
+    // agc, panel
+    int agc_run = 1; SeqStage *agc = nullptr;
+    double panel_gain1 = 4.0, panel_gain2I = 1.0, panel_gain2Q = 1.0;
+    // buffers
+    cd *mid = nullptr, *mid2 = nullptr, *audio = nullptr;
+    // fexchange0 emulation
+    cd *d_in = nullptr, *d_out = nullptr; double *h_ring = nullptr; int ring_blocks = 0, ring_pos = 0; cudaStream_t hs = nullptr;
+
+    int init(int C, int in_size, int dsp_size, int in_rate, int dsp_rate, int out_rate);
+    void release();
+    int make_nbp0();
+    int make_bp1();
+    int make_fmd();
+    int xrxa(const void *din, long is, void *dout, long os, cudaStream_t s);
+};
+
+static FirCore *new_fircore(int C, int size, int nc, const std::vector<double> &imp)
+{
+    FirCore *f = new FirCore();
+    if (f->init(C, size, nc, 0, imp.data()) != QC_OK) { f->release(); delete f; return nullptr; }
+    return f;
+}
+
+int Rxa::make_nbp0()
+{   // create_nbp + calc_nbp_impulse without notches (nbp.c:214-239, 241-270): gain / (2 size) baked in
+    std::vector<double> imp((size_t)2 * nbp_nc);
+    quisk_cuda_fir_bandpass(nbp_nc, nbp_flow, nbp_fhigh, (double)dsp_rate, 0, 1, 1.0 / (double)(2 * dsp_size), imp.data());
+    if (nbp0) { nbp0->release(); delete nbp0; }
+    nbp0 = new_fircore(C, dsp_size, nbp_nc, imp);
+    return nbp0 ? QC_OK : QC_EINVAL;
+}
+
+int Rxa::make_bp1()
+{   // create_bandpass (bandpass.c:284-306), wintype 1
+    std::vector<double> imp((size_t)2 * bp1_nc);
+    quisk_cuda_fir_bandpass(bp1_nc, bp1_flow, bp1_fhigh, (double)dsp_rate, 1, 1, bp1_gain / (double)(2 * dsp_size), imp.data());
+    if (bp1) { bp1->release(); delete bp1; }
+    bp1 = new_fircore(C, dsp_size, bp1_nc, imp);
+    return bp1 ? QC_OK : QC_EINVAL;
+}
+
+int Rxa::make_fmd()
+{   // create_fmd (fmd.c:81-120) with create_rxa's arguments (RXA.c:192-212)
+    const double f_low = 300.0, f_high = 3000.0, afgain = 0.5, rate = (double)dsp_rate;
+    std::vector<double> imp((size_t)2 * fm_nc_de);
+    quisk_cuda_fc_impulse(fm_nc_de, f_low, f_high, +20.0 * log10(f_high / f_low), 0.0, 1, rate, 1.0 / (2.0 * dsp_size), 0, 0, imp.data());
+    if (pde) { pde->release(); delete pde; }
+    pde = new_fircore(C, dsp_size, fm_nc_de, imp);
+    imp.assign((size_t)2 * fm_nc_aud, 0.0);
+    quisk_cuda_fir_bandpass(fm_nc_aud, 0.8 * f_low, 1.1 * f_high, rate, 0, 1, afgain / (2.0 * dsp_size), imp.data());
+    if (paud) { paud->release(); delete paud; }
+    paud = new_fircore(C, dsp_size, fm_nc_aud, imp);
+    return pde && paud ? QC_OK : QC_EINVAL;
+}
+
+int Rxa::init(int C_, int in_size_, int dsp_size_, int in_rate_, int dsp_rate_, int out_rate_)
+{
+    C = C_; in_size = in_size_; dsp_size = dsp_size_; in_rate = in_rate_; dsp_rate = dsp_rate_; out_rate = out_rate_;
+    if (C <= 0 || dsp_size <= 0 || in_rate <= 0 || dsp_rate <= 0 || out_rate <= 0) { set_error("rxa_create: bad arguments"); return QC_EINVAL; }
+    // pre_main_build, channel.c:36-58
+    dsp_insize = in_rate >= dsp_rate ? dsp_size * (in_rate / dsp_rate) : dsp_size / (dsp_rate / in_rate);
+    dsp_outsize = out_rate >= dsp_rate ? dsp_size * (out_rate / dsp_rate) : dsp_size / (dsp_rate / out_rate);
+    out_size = in_rate >= out_rate ? in_size / (in_rate / out_rate) : in_size * (out_rate / in_rate);
+    const size_t mlen = (size_t)C * (2 * (dsp_size > dsp_insize ? dsp_size : dsp_insize) + 64);
+    QC_CUDA(cudaMalloc((void **)&mid, mlen * sizeof(cd)));
+    QC_CUDA(cudaMalloc((void **)&mid2, mlen * sizeof(cd)));
+    QC_CUDA(cudaMalloc((void **)&audio, (size_t)C * dsp_size * sizeof(cd)));
+    shift = make_shift(C, in_rate, nullptr);
+    if (in_rate != dsp_rate) {          // RXAResCheck, RXA.c:789-798
+        rsmpin = new Resampler();
+        if (rsmpin->init(C, in_rate, dsp_rate, 0.0, 0, 1.0) != QC_OK) return QC_EINVAL;
+    }
+    if (dsp_rate != out_rate) {
+        rsmpout = new Resampler();
+        if (rsmpout->init(C, dsp_rate, out_rate, 0.0, 0, 1.0) != QC_OK) return QC_EINVAL;
+    }
+    adcmeter = make_meter(C, dsp_rate, 0.100, 0.100);
+    smeter = make_meter(C, dsp_rate, 0.100, 0.100);
+    agcmeter = make_meter(C, dsp_rate, 0.100, 0.100);
+    nbp_nc = bp1_nc = fm_nc_de = fm_nc_aud = dsp_size > 2048 ? dsp_size : 2048;       // max(2048, dsp_size)
+    int rc;
+    if ((rc = make_nbp0()) != QC_OK) return rc;
+    if ((rc = make_bp1()) != QC_OK) return rc;
+    amd = make_amd(C, dsp_rate, 0, 1, 0);
+    fmpll = make_fmpll(C, dsp_rate, 5000.0, -8000.0, +8000.0, 1.0, 20000.0, 0.02);
+    sntch = make_snotch(C, dsp_rate, 254.1, 0.0002);
+    if ((rc = make_fmd()) != QC_OK) return rc;
+    agc = make_wcpagc(C, dsp_rate, 3);
+    if (!shift || !adcmeter || !smeter || !agcmeter || !amd || !fmpll || !sntch || !agc) return QC_EINVAL;
+    return QC_OK;
+}
+
+void Rxa::release()
+{
+    for (SeqStage **p : {&shift, &adcmeter, &smeter, &agcmeter, &amd, &fmpll, &sntch, &agc}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
+    for (FirCore **p : {&nbp0, &bp1, &pde, &paud}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
+    for (Resampler **p : {&rsmpin, &rsmpout}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
+    if (mid) cudaFree(mid); if (mid2) cudaFree(mid2); if (audio) cudaFree(audio);
+    if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out); if (h_ring) free(h_ring);
+    mid = mid2 = audio = d_in = d_out = nullptr; h_ring = nullptr;
+}
+
+int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
+{
+    int rc;
+    const cd *cur = (const cd *)din; long cs = is;
+    const long ms = 2 * (dsp_size > dsp_insize ? dsp_size : dsp_insize) + 64;
+    // xshift on inbuff (in place in the reference; a zero shift is the exact identity: phase stays 0)
+    if (shift_run && shift_nonzero) {
+        rc = shift->run(cur, cs, mid2, ms, dsp_insize, s); if (rc) return rc;
+        cur = mid2; cs = ms;
+    }
+    // xresample(rsmpin): inbuff -> midbuff
+    cd *m = mid;
+    if (rsmpin) {
+        int no = 0;
+        rc = rsmpin->f->run(cur, cs, dsp_insize, m, ms, &no, 0, s); if (rc) return rc;
+        if (no != dsp_size) { set_error("rxa: input resampler produced %d samples, dsp_size is %d", no, dsp_size); return QC_EINVAL; }
+    } else {
+        QC_CUDA(cudaMemcpy2DAsync(m, (size_t)ms * sizeof(cd), cur, (size_t)cs * sizeof(cd), (size_t)dsp_size * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
+    }
+    rc = adcmeter->run(m, ms, nullptr, 0, dsp_size, s); if (rc) return rc;
+    if (nbp_run) { rc = nbp0->run(m, ms, m, ms, s); if (rc) return rc; }
+    rc = smeter->run(m, ms, nullptr, 0, dsp_size, s); if (rc) return rc;
+    if (amd_run) { rc = amd->run(m, ms, m, ms, dsp_size, s); if (rc) return rc; }
+    if (fmd_run) {
+        rc = fmpll->run(m, ms, audio, dsp_size, dsp_size, s); if (rc) return rc;       // pll -> audio
+        rc = pde->run(audio, dsp_size, m, ms, s); if (rc) return rc;                   // de-emphasis: audio -> out
+        rc = paud->run(m, ms, m, ms, s); if (rc) return rc;                            // audio filter, in place
+        rc = sntch->run(m, ms, m, ms, dsp_size, s); if (rc) return rc;                 // CTCSS notch (I rail)
+    }
+    if (bp1_run) { rc = bp1->run(m, ms, m, ms, s); if (rc) return rc; }
+    if (agc_run) { rc = agc->run(m, ms, m, ms, dsp_size, s); if (rc) return rc; }
+    rc = agcmeter->run(m, ms, agc->d_state, 0, dsp_size, s); if (rc) return rc;
+    // xpanel always applies gain1 * gain2 (F9), inselect 3, no copy
+    if (rsmpout) {
+        rc = launch_panel(m, ms, m, ms, dsp_size, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s); if (rc) return rc;
+        int no = 0;
+        rc = rsmpout->f->run(m, ms, dsp_size, dout, os, &no, 0, s); if (rc) return rc;
+        if (no != dsp_outsize) { set_error("rxa: output resampler produced %d samples, expected %d", no, dsp_outsize); return QC_EINVAL; }
+    } else {
+        rc = launch_panel(m, ms, (cd *)dout, os, dsp_size, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s); if (rc) return rc;
+    }
+    return QC_OK;
+}
+
+}  // namespace qc
+
+using namespace qc;
+struct qcRxa { qc::Rxa r; };
+
+extern "C" {
+
+qcRxa *quisk_cuda_rxa_create(int n_channels, int in_size, int dsp_size, int in_rate, int dsp_rate, int out_rate)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    qcRxa *p = new qcRxa();
+    if (p->r.init(n_channels, in_size, dsp_size, in_rate, dsp_rate, out_rate) != QC_OK) { p->r.release(); delete p; return nullptr; }
+    return p;
+}
+
+void quisk_cuda_rxa_destroy(qcRxa *r) { if (r) { r->r.release(); delete r; } }
+int quisk_cuda_rxa_in_size(const qcRxa *r) { return r ? r->r.dsp_insize : QC_EINVAL; }
+int quisk_cuda_rxa_out_size(const qcRxa *r) { return r ? r->r.dsp_outsize : QC_EINVAL; }
+
+int quisk_cuda_rxa_set_mode(qcRxa *p, int mode)
+{   // SetRXAMode, RXA.c:749-787
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    if (r.mode == mode) return QC_OK;
+    const int amd_run = (mode == QC_RXA_AM) || (mode == QC_RXA_SAM);
+    // RXAbp1Check: gain 2 when the AM demodulator (or a noise reducer) feeds bp1; new masks wait for setUpdate
+    const double gain = amd_run ? 2.0 : 1.0;
+    if (r.bp1_gain != gain) {
+        r.bp1_gain = gain;
+        std::vector<double> imp((size_t)2 * r.bp1_nc);
+        quisk_cuda_fir_bandpass(r.bp1_nc, r.bp1_flow, r.bp1_fhigh, (double)r.dsp_rate, 1, 1, r.bp1_gain / (double)(2 * r.dsp_size), imp.data());
+        int rc = r.bp1->set_impulse(imp.data(), 0); if (rc) return rc;
+    }
+    r.mode = mode;
+    r.amd_run = 0; r.fmd_run = 0; r.agc_run = 1;
+    if (mode == QC_RXA_AM) { r.amd_run = 1; r.amd->par[0] = 0; }
+    else if (mode == QC_RXA_SAM) { r.amd_run = 1; r.amd->par[0] = 1; }
+    else if (mode == QC_RXA_FM) { r.fmd_run = 1; r.agc_run = 0; }
+    // RXAbp1Set, RXA.c:815-827
+    const int old = r.bp1_run;
+    r.bp1_run = r.amd_run ? 1 : 0;
+    if (!old && r.bp1_run) { int rc = r.bp1->flush(); if (rc) return rc; }
+    return r.bp1->update();
+}
+
+int quisk_cuda_rxa_set_passband(qcRxa *p, double f_low, double f_high)
+{   // RXASetPassband = SetRXABandpassFreqs (bandpass.c:393-409) + RXANBPSetFreqs (nbp.c:528-540)
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    if (f_low != r.bp1_flow || f_high != r.bp1_fhigh) {
+        std::vector<double> imp((size_t)2 * r.bp1_nc);
+        quisk_cuda_fir_bandpass(r.bp1_nc, f_low, f_high, (double)r.dsp_rate, 1, 1, r.bp1_gain / (double)(2 * r.dsp_size), imp.data());
+        int rc = r.bp1->set_impulse(imp.data(), 0); if (rc) return rc;
+        r.bp1_flow = f_low; r.bp1_fhigh = f_high;
+        r.bp1->update();
+    }
+    if (f_low != r.nbp_flow || f_high != r.nbp_fhigh) {
+        r.nbp_flow = f_low; r.nbp_fhigh = f_high;
+        std::vector<double> imp((size_t)2 * r.nbp_nc);
+        quisk_cuda_fir_bandpass(r.nbp_nc, f_low, f_high, (double)r.dsp_rate, 0, 1, 1.0 / (double)(2 * r.dsp_size), imp.data());
+        int rc = r.nbp0->set_impulse(imp.data(), 1); if (rc) return rc;
+    }
+    return QC_OK;
+}
+
+int quisk_cuda_rxa_set_nc(qcRxa *p, int nc)
+{   // RXASetNC, RXA.c:935-946: every fircore is re-planned (fresh, zeroed state) with nc taps
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    if (nc < r.dsp_size || nc % r.dsp_size) { set_error("rxa_set_nc: nc must be a multiple of dsp_size"); return QC_EINVAL; }
+    int rc;
+    if (r.nbp_nc != nc) { r.nbp_nc = nc; if ((rc = r.make_nbp0()) != QC_OK) return rc; }
+    if (r.bp1_nc != nc) { r.bp1_nc = nc; if ((rc = r.make_bp1()) != QC_OK) return rc; }
+    if (r.fm_nc_de != nc || r.fm_nc_aud != nc) { r.fm_nc_de = r.fm_nc_aud = nc; if ((rc = r.make_fmd()) != QC_OK) return rc; }
+    return QC_OK;
+}
+
+int quisk_cuda_rxa_set_agc_mode(qcRxa *p, int mode) { if (!p) return QC_EINVAL; agc_set_mode(p->r.agc, mode); return QC_OK; }
+int quisk_cuda_rxa_set_agc_fixed(qcRxa *p, double gain_db)
+{ if (!p) return QC_EINVAL; p->r.agc->agc.fixed_gain = pow(10.0, gain_db / 20.0); p->r.agc->load_agc(); return QC_OK; }
+
+int quisk_cuda_rxa_set_shift(qcRxa *p, int run, const double *shift_hz)
+{
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    r.shift_run = run;
+    if (shift_hz) {
+        if (r.shift) { r.shift->release(); delete r.shift; }
+        r.shift = make_shift(r.C, r.in_rate, shift_hz);
+        if (!r.shift) return QC_ENOMEM;
+        r.shift_nonzero = false;
+        for (int c = 0; c < r.C; c++) r.shift_nonzero = r.shift_nonzero || shift_hz[c] != 0.0;
+    }
+    return QC_OK;
+}
+
+int quisk_cuda_rxa_set_nbp_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.nbp_run = run; return QC_OK; }
+int quisk_cuda_rxa_set_panel_gain(qcRxa *p, double g) { if (!p) return QC_EINVAL; p->r.panel_gain1 = g; return QC_OK; }
+
+int quisk_cuda_rxa_xrxa(qcRxa *p, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream)
+{ return p ? p->r.xrxa(d_in, in_stride, d_out, out_stride, (cudaStream_t)stream) : QC_EINVAL; }
+
+int quisk_cuda_rxa_fexchange0(qcRxa *p, const double *h_in, double *h_out, int *error)
+{   // iobuffs.c:464-516 with in_size == dsp_insize: r2 starts with (DSP_MULT - 1) buffers of zeros
+    // (iobuffs.c:409-413) and dexchange pushes the PREVIOUS outbuff before xrxa runs (iobuffs.c:583-604),
+    // so the block returned now is the one computed two calls ago.
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    if (error) *error = 0;
+    if (r.in_size != r.dsp_insize) { set_error("rxa_fexchange0: in_size must equal dsp_insize in this version"); return QC_EINVAL; }
+    const size_t nin = (size_t)r.C * r.dsp_insize, nout = (size_t)r.C * r.dsp_outsize;
+    if (!r.d_in) {
+        QC_CUDA(cudaMalloc((void **)&r.d_in, nin * sizeof(cd)));
+        QC_CUDA(cudaMalloc((void **)&r.d_out, nout * sizeof(cd)));
+        QC_CUDA(cudaStreamCreateWithFlags(&r.hs, cudaStreamNonBlocking));
+        r.ring_blocks = 2;
+        r.h_ring = (double *)calloc(nout * 2 * r.ring_blocks, sizeof(double));
+        r.ring_pos = 0;
+    }
+    QC_CUDA(cudaMemcpyAsync(r.d_in, h_in, nin * sizeof(cd), cudaMemcpyHostToDevice, r.hs));
+    int rc = r.xrxa(r.d_in, r.dsp_insize, r.d_out, r.dsp_outsize, r.hs); if (rc) return rc;
+    double *slot = r.h_ring + (size_t)r.ring_pos * nout * 2;
+    memcpy(h_out, slot, nout * sizeof(cd));                       // the block from two calls ago (zeros at first)
+    QC_CUDA(cudaMemcpyAsync(slot, r.d_out, nout * sizeof(cd), cudaMemcpyDeviceToHost, r.hs));
+    QC_CUDA(cudaStreamSynchronize(r.hs));
+    r.ring_pos = (r.ring_pos + 1) % r.ring_blocks;
+    return QC_OK;
+}
+
+int quisk_cuda_rxa_get_meter(qcRxa *p, int which, double *av, double *pk, double *gain)
+{
+    if (!p) return QC_EINVAL;
+    SeqStage *m = which == 0 ? p->r.adcmeter : (which == 1 ? p->r.smeter : p->r.agcmeter);
+    std::vector<double> h((size_t)p->r.C * 3);
+    QC_CUDA(cudaDeviceSynchronize());
+    QC_CUDA(cudaMemcpy(h.data(), m->d_meter, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < p->r.C; c++) {
+        if (av) av[c] = h[(size_t)c * 3];
+        if (pk) pk[c] = h[(size_t)c * 3 + 1];
+        if (gain) gain[c] = h[(size_t)c * 3 + 2];
+    }
+    return QC_OK;
+}
+
+}  // extern "C"

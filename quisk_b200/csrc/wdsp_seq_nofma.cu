@@ -1,0 +1,510 @@
+// quisk_b200/csrc/wdsp_seq_nofma.cu -- the per-sample recurrent RXA stages: xshift (wdsp/shift.c:60-86),
+// xwcpagc (wdsp/wcpAGC.c:161-348), xamd (wdsp/amd.c:115-239), the PLL of xfmd (wdsp/fmd.c:144-170),
+// xsnotch (wdsp/iir.c:76-95), xmeter (wdsp/meter.c:75-107) and xpanel (wdsp/patchpanel.c:55-105).
+//
+// These are scalar state machines / IIR recurrences: there is no parallelism along time that keeps
+// the reference's arithmetic, so ONE GPU THREAD WALKS ONE CHANNEL'S BLOCK and the batch supplies the
+// parallelism ("do not time-shard exactly; shard by channel").  A lane reads its
+// own row sequentially, so every 128-byte line is fetched once and reused for 8 samples out of L1.
+// This file is compiled with --fmad=false: a*b+c is two roundings, as in the reference built by gcc for
+// baseline x86-64, so the state trajectories (AGC state switches, PLL phase) follow the reference's to
+// the last bit except where device libm (cos, sin, atan2, log10) differs from glibc by an ulp.
+#include "wdsp_internal.h"
+#include <cmath>
+
+namespace qc {
+
+static const double kPI = 3.1415926535897932, kTWOPI = 6.2831853071795864;
+#define TWOPI_D 6.2831853071795864
+
+// ------------------------------------------------------------------------------------------- shift
+__global__ void shift_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, const double *par)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double phase = state[c];
+    const double delta = par[c * 3], cos_delta = par[c * 3 + 1], sin_delta = par[c * 3 + 2];
+    double cos_phase = cos(phase), sin_phase = sin(phase);
+    const cd *x = in + (size_t)c * is;
+    cd *y = out + (size_t)c * os;
+    for (int i = 0; i < n; i++) {
+        const double I1 = x[i].x, Q1 = x[i].y;
+        y[i] = make_double2(I1 * cos_phase - Q1 * sin_phase, I1 * sin_phase + Q1 * cos_phase);
+        const double t1 = cos_phase, t2 = sin_phase;
+        cos_phase = t1 * cos_delta - t2 * sin_delta;
+        sin_phase = t1 * sin_delta + t2 * cos_delta;
+        phase += delta;
+        if (phase >= TWOPI_D) phase -= TWOPI_D;
+        if (phase < 0.0) phase += TWOPI_D;
+    }
+    state[c] = phase;
+}
+
+// ------------------------------------------------------------------------------------------ wcpagc
+// state: 0 out_index 1 in_index 2 ring_max 3 volts 4 save_volts 5 fast_backaverage 6 hang_backaverage
+//        7 hang_counter 8 decay_type 9 state 10 gain
+__global__ void wcpagc_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, double *ring, AgcParams a)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const cd *x = in + (size_t)c * is;
+    cd *y = out + (size_t)c * os;
+    if (a.mode == 0) {
+        for (int i = 0; i < n; i++) y[i] = make_double2(a.fixed_gain * x[i].x, a.fixed_gain * x[i].y);
+        return;
+    }
+    double *st = state + (size_t)c * 16;
+    double *rg = ring + (size_t)c * a.ring_buffsize * 3;
+    int out_index = (int)st[0], in_index = (int)st[1];
+    double ring_max = st[2], volts = st[3], save_volts = st[4], fast_backaverage = st[5], hang_backaverage = st[6];
+    int hang_counter = (int)st[7], decay_type = (int)st[8], state_ = (int)st[9];
+    double gain = st[10];
+    for (int i = 0; i < n; i++) {
+        if (++out_index >= a.ring_buffsize) out_index -= a.ring_buffsize;
+        if (++in_index >= a.ring_buffsize) in_index -= a.ring_buffsize;
+        const double o0 = rg[out_index * 3], o1 = rg[out_index * 3 + 1], abs_out_sample = rg[out_index * 3 + 2];
+        const double r0 = x[i].x, r1 = x[i].y;
+        rg[in_index * 3] = r0; rg[in_index * 3 + 1] = r1;
+        double ab;
+        if (a.pmode == 0) { const double f0 = fabs(r0), f1 = fabs(r1); ab = f0 < f1 ? f1 : f0; }
+        else ab = sqrt(r0 * r0 + r1 * r1);
+        rg[in_index * 3 + 2] = ab;
+        fast_backaverage = a.fast_backmult * abs_out_sample + a.onemfast_backmult * fast_backaverage;
+        hang_backaverage = a.hang_backmult * abs_out_sample + a.onemhang_backmult * hang_backaverage;
+        if (abs_out_sample >= ring_max && abs_out_sample > 0.0) {
+            ring_max = 0.0;
+            int k = out_index;
+            for (int j = 0; j < a.attack_buffsize; j++) {
+                if (++k == a.ring_buffsize) k = 0;
+                const double v = rg[k * 3 + 2];
+                if (v > ring_max) ring_max = v;
+            }
+        }
+        if (ab > ring_max) ring_max = ab;
+        if (hang_counter > 0) --hang_counter;
+        switch (state_) {
+        case 0:
+            if (ring_max >= volts) volts += (ring_max - volts) * a.attack_mult;
+            else if (volts > a.pop_ratio * fast_backaverage) { state_ = 1; volts += (ring_max - volts) * a.fast_decay_mult; }
+            else if (a.hang_enable && hang_backaverage > a.hang_level) { state_ = 2; hang_counter = (int)(a.hangtime * a.sample_rate); decay_type = 1; }
+            else { state_ = 3; volts += (ring_max - volts) * a.decay_mult; decay_type = 0; }
+            break;
+        case 1:
+            if (ring_max >= volts) { state_ = 0; volts += (ring_max - volts) * a.attack_mult; }
+            else if (volts > save_volts) volts += (ring_max - volts) * a.fast_decay_mult;
+            else if (hang_counter > 0) state_ = 2;
+            else if (decay_type == 0) { state_ = 3; volts += (ring_max - volts) * a.decay_mult; }
+            else { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
+            break;
+        case 2:
+            if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
+            else if (hang_counter == 0) { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
+            break;
+        case 3:
+            if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
+            else volts += (ring_max - volts) * a.decay_mult;
+            break;
+        case 4:
+            if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
+            else volts += (ring_max - volts) * a.hang_decay_mult;
+            break;
+        }
+        if (volts < a.min_volts) volts = a.min_volts;
+        gain = volts * a.inv_out_target;
+        const double lg = log10(a.inv_max_input * volts);
+        const double mult = (a.out_target - a.slope_constant * (0.0 < lg ? 0.0 : lg)) / volts;
+        y[i] = make_double2(o0 * mult, o1 * mult);
+    }
+    st[0] = out_index; st[1] = in_index; st[2] = ring_max; st[3] = volts; st[4] = save_volts;
+    st[5] = fast_backaverage; st[6] = hang_backaverage; st[7] = hang_counter; st[8] = decay_type; st[9] = state_; st[10] = gain;
+}
+
+// --------------------------------------------------------------------------------------------- amd
+// state: 0 dc 1 dc_insert 2 phs 3 fil_out 4 omega 5 dsI 6 dsQ 7.. a[24] b[24] c[24] d[24]
+// par:   0 mode 1 levelfade 2 sbmode 3 omega_min 4 omega_max 5 g1 6 g2 7 mtauR 8 onem_mtauR 9 mtauI 10 onem_mtauI
+__constant__ double c_amd_c0[7] = {-0.328201924180698, -0.744171491539427, -0.923022915444215, -0.978490468768238,
+                                   -0.994128272402075, -0.998458978159551, -0.999790306259206};      // amd.c:92-98
+__constant__ double c_amd_c1[7] = {-0.0991227952747244, -0.565619728761389, -0.857467122550052, -0.959123933111275,
+                                   -0.988739372718090, -0.996959189310611, -0.999282492800792};      // amd.c:100-106
+
+struct SeqPar { double v[32]; };
+
+__global__ void amd_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const cd *x = in + (size_t)c * is;
+    cd *y = out + (size_t)c * os;
+    double *st = state + (size_t)c * 104;
+    const int mode = (int)P.v[0], levelfade = (int)P.v[1], sbmode = (int)P.v[2];
+    const double omega_min = P.v[3], omega_max = P.v[4], g1 = P.v[5], g2 = P.v[6];
+    const double mtauR = P.v[7], onem_mtauR = P.v[8], mtauI = P.v[9], onem_mtauI = P.v[10];
+    double dc = st[0], dc_insert = st[1], phs = st[2], fil_out = st[3], omega = st[4], dsI = st[5], dsQ = st[6];
+    if (mode == 0) {
+        for (int i = 0; i < n; i++) {
+            double audio = sqrt(x[i].x * x[i].x + x[i].y * x[i].y);
+            if (levelfade) {
+                dc = mtauR * dc + onem_mtauR * audio;
+                dc_insert = mtauI * dc_insert + onem_mtauI * audio;
+                audio += dc_insert - dc;
+            }
+            y[i] = make_double2(audio, audio);
+        }
+    } else {
+        double *A = st + 7, *B = st + 31, *Cc = st + 55, *D = st + 79;      // a[], b[], c[], d[] (amd.h:64-67)
+        for (int i = 0; i < n; i++) {
+            const double v0 = cos(phs), v1 = sin(phs);
+            const double ai = x[i].x * v0, bi = x[i].x * v1, aq = x[i].y * v0, bq = x[i].y * v1;
+            double ai_ps = 0, bi_ps = 0, aq_ps = 0, bq_ps = 0;
+            if (sbmode != 0) {
+                A[0] = dsI; B[0] = bi; Cc[0] = dsQ; D[0] = aq;
+                dsI = ai; dsQ = bq;
+                for (int j = 0; j < 7; j++) {
+                    const int k = 3 * j;
+                    A[k + 3] = c_amd_c0[j] * (A[k] - A[k + 5]) + A[k + 2];
+                    B[k + 3] = c_amd_c1[j] * (B[k] - B[k + 5]) + B[k + 2];
+                    Cc[k + 3] = c_amd_c0[j] * (Cc[k] - Cc[k + 5]) + Cc[k + 2];
+                    D[k + 3] = c_amd_c1[j] * (D[k] - D[k + 5]) + D[k + 2];
+                }
+                ai_ps = A[21]; bi_ps = B[21]; bq_ps = Cc[21]; aq_ps = D[21];
+                for (int j = 23; j > 0; j--) { A[j] = A[j - 1]; B[j] = B[j - 1]; Cc[j] = Cc[j - 1]; D[j] = D[j - 1]; }
+            }
+            double corr0 = +ai + bq;
+            const double corr1 = -bi + aq;
+            double audio;
+            if (sbmode == 1) audio = (ai_ps - bi_ps) + (aq_ps + bq_ps);
+            else if (sbmode == 2) audio = (ai_ps + bi_ps) - (aq_ps - bq_ps);
+            else audio = corr0;
+            if (levelfade) {
+                dc = mtauR * dc + onem_mtauR * audio;
+                dc_insert = mtauI * dc_insert + onem_mtauI * corr0;
+                audio += dc_insert - dc;
+            }
+            y[i] = make_double2(audio, audio);
+            if (corr0 == 0.0 && corr1 == 0.0) corr0 = 1.0;
+            const double det = atan2(corr1, corr0);
+            const double del_out = fil_out;
+            omega += g2 * det;
+            if (omega < omega_min) omega = omega_min;
+            if (omega > omega_max) omega = omega_max;
+            fil_out = g1 * det + omega;
+            phs += del_out;
+            while (phs >= TWOPI_D) phs -= TWOPI_D;
+            while (phs < 0.0) phs += TWOPI_D;
+        }
+    }
+    st[0] = dc; st[1] = dc_insert; st[2] = phs; st[3] = fil_out; st[4] = omega; st[5] = dsI; st[6] = dsQ;
+}
+
+// ------------------------------------------------------------------------------------------- fm pll
+// state: 0 phs 1 fil_out 2 omega 3 fmdc ; par: 0 omega_min 1 omega_max 2 g1 3 g2 4 mtau 5 onem_mtau 6 again
+__global__ void fmpll_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const cd *x = in + (size_t)c * is;
+    cd *y = out + (size_t)c * os;
+    double *st = state + (size_t)c * 4;
+    double phs = st[0], fil_out = st[1], omega = st[2], fmdc = st[3];
+    const double omega_min = P.v[0], omega_max = P.v[1], g1 = P.v[2], g2 = P.v[3], mtau = P.v[4], onem_mtau = P.v[5], again = P.v[6];
+    for (int i = 0; i < n; i++) {
+        const double v0 = cos(phs), v1 = sin(phs);
+        double corr0 = +x[i].x * v0 + x[i].y * v1;
+        const double corr1 = -x[i].x * v1 + x[i].y * v0;
+        if (corr0 == 0.0 && corr1 == 0.0) corr0 = 1.0;
+        const double det = atan2(corr1, corr0);
+        const double del_out = fil_out;
+        omega += g2 * det;
+        if (omega < omega_min) omega = omega_min;
+        if (omega > omega_max) omega = omega_max;
+        fil_out = g1 * det + omega;
+        phs += del_out;
+        while (phs >= TWOPI_D) phs -= TWOPI_D;
+        while (phs < 0.0) phs += TWOPI_D;
+        fmdc = mtau * fmdc + onem_mtau * fil_out;
+        const double a = again * (fil_out - fmdc);
+        y[i] = make_double2(a, a);
+    }
+    st[0] = phs; st[1] = fil_out; st[2] = omega; st[3] = fmdc;
+}
+
+// ------------------------------------------------------------------------------------------ snotch
+// state: x1 x2 y1 y2 ; par: a0 a1 a2 b1 b2.  Only the I rail is filtered (iir.c:85-86).
+__global__ void snotch_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const cd *x = in + (size_t)c * is;
+    cd *y = out + (size_t)c * os;
+    double *st = state + (size_t)c * 4;
+    double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
+    const double a0 = P.v[0], a1 = P.v[1], a2 = P.v[2], b1 = P.v[3], b2 = P.v[4];
+    for (int i = 0; i < n; i++) {
+        const double x0 = x[i].x;
+        const double o = a0 * x0 + a1 * x1 + a2 * x2 + b1 * y1 + b2 * y2;
+        y[i] = make_double2(o, x[i].y);
+        y2 = y1; y1 = o; x2 = x1; x1 = x0;
+    }
+    st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
+}
+
+// ------------------------------------------------------------------------------------------- meter
+// state: avg peak ; par: mult_average mult_peak ; results: av dB, pk dB (10 log10, meter.c:98-99)
+__global__ void meter_kernel(const cd *in, long is, int n, int C, double *state, SeqPar P, double *result, const double *agc_state)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const cd *x = in + (size_t)c * is;
+    double avg = state[c * 2], peak = state[c * 2 + 1];
+    const double ma = P.v[0], mp = P.v[1];
+    double np = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double smag = x[i].x * x[i].x + x[i].y * x[i].y;
+        avg = avg * ma + (1.0 - ma) * smag;
+        peak *= mp;
+        if (smag > np) np = smag;
+    }
+    if (np > peak) peak = np;
+    state[c * 2] = avg; state[c * 2 + 1] = peak;
+    result[c * 3] = 10.0 * log10(avg + 1.0e-40);
+    result[c * 3 + 1] = 10.0 * log10(peak + 1.0e-40);
+    result[c * 3 + 2] = agc_state ? 20.0 * log10(agc_state[(size_t)c * 16 + 10] + 1.0e-40) : 0.0;
+}
+
+__global__ void panel_kernel(const cd *in, long is, cd *out, long os, int n, int C, double gainI, double gainQ, int inselect, int copy)
+{
+    const long total = (long)n * C;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / n);
+        const int i = (int)(idx - (long)c * n);
+        const cd v = in[(size_t)c * is + i];
+        double I, Q;
+        switch (copy) {
+        case 1: I = v.x * (inselect >> 1); Q = I; break;
+        case 2: Q = v.y * (inselect & 1); I = Q; break;
+        case 3: Q = v.x * (inselect >> 1); I = v.y * (inselect & 1); break;
+        default: I = v.x * (inselect >> 1); Q = v.y * (inselect & 1); break;
+        }
+        out[(size_t)c * os + i] = make_double2(gainI * I, gainQ * Q);
+    }
+}
+
+int launch_panel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C, double gainI, double gainQ,
+                 int inselect, int copy, cudaStream_t s)
+{
+    const long total = (long)n * C;
+    if (total <= 0) return QC_OK;
+    int blocks = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
+    panel_kernel<<<blocks, 256, 0, s>>>(in, in_stride, out, out_stride, n, C, gainI, gainQ, inselect, copy);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+// ------------------------------------------------------------------------------------------- host
+int SeqStage::init_common(int kind_, int C_, int sd)
+{
+    kind = kind_; C = C_; state_doubles = sd;
+    if (C <= 0) { set_error("seq stage: bad channel count"); return QC_EINVAL; }
+    QC_CUDA(cudaMalloc((void **)&d_state, (size_t)C * sd * sizeof(double)));
+    return flush();
+}
+
+void SeqStage::release()
+{
+    if (d_state) cudaFree(d_state); if (d_ring) cudaFree(d_ring); if (d_par) cudaFree(d_par); if (d_meter) cudaFree(d_meter);
+    d_state = d_ring = d_par = d_meter = nullptr;
+}
+
+int SeqStage::flush()
+{
+    QC_CUDA(cudaMemset(d_state, 0, (size_t)C * state_doubles * sizeof(double)));
+    if (kind == SEQ_WCPAGC) {
+        // calc_wcpagc (wcpAGC.c:35-52): out_index = -1, in_index = attack_buffsize + out_index, everything else 0
+        std::vector<double> st((size_t)C * 16, 0.0);
+        for (int c = 0; c < C; c++) { st[(size_t)c * 16] = -1.0; st[(size_t)c * 16 + 1] = agc.attack_buffsize - 1.0; }
+        QC_CUDA(cudaMemcpy(d_state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (d_ring) QC_CUDA(cudaMemset(d_ring, 0, (size_t)C * ring_len * 3 * sizeof(double)));
+    }
+    if (kind == SEQ_METER && d_meter) {
+        std::vector<double> r((size_t)C * 3, -400.0);
+        QC_CUDA(cudaMemcpy(d_meter, r.data(), r.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return QC_OK;
+}
+
+void SeqStage::load_agc()
+{   // loadWcpAGC, wcpAGC.c:115-147
+    AgcParams &a = agc;
+    a.attack_buffsize = (int)ceil(a.sample_rate * a.n_tau * a.tau_attack);
+    a.attack_mult = 1.0 - exp(-1.0 / (a.sample_rate * a.tau_attack));
+    a.decay_mult = 1.0 - exp(-1.0 / (a.sample_rate * a.tau_decay));
+    a.fast_decay_mult = 1.0 - exp(-1.0 / (a.sample_rate * a.tau_fast_decay));
+    a.fast_backmult = 1.0 - exp(-1.0 / (a.sample_rate * a.tau_fast_backaverage));
+    a.onemfast_backmult = 1.0 - a.fast_backmult;
+    a.out_target = a.out_targ * (1.0 - exp(-(double)a.n_tau)) * 0.9999;
+    a.min_volts = a.out_target / (a.var_gain * a.max_gain);
+    a.inv_out_target = 1.0 / a.out_target;
+    double tmp = log10(a.out_target / (a.max_input * a.var_gain * a.max_gain));
+    if (tmp == 0.0) tmp = 1e-16;
+    a.slope_constant = (a.out_target * (1.0 - 1.0 / a.var_gain)) / tmp;
+    a.inv_max_input = 1.0 / a.max_input;
+    tmp = pow(10.0, (a.hang_thresh - 1.0) / 0.125);
+    a.hang_level = (a.max_input * tmp + (a.out_target / (a.var_gain * a.max_gain)) * (1.0 - tmp)) * 0.637;
+    a.hang_backmult = 1.0 - exp(-1.0 / (a.sample_rate * a.tau_hang_backmult));
+    a.onemhang_backmult = 1.0 - a.hang_backmult;
+    a.hang_decay_mult = 1.0 - exp(-1.0 / (a.sample_rate * a.tau_hang_decay));
+}
+
+void agc_set_mode(SeqStage *s, int mode)
+{   // SetRXAAGCMode, wcpAGC.c:370-411
+    AgcParams &a = s->agc;
+    switch (mode) {
+    case 0: a.mode = 0; break;
+    case 1: a.mode = 1; a.hangtime = 2.000; a.tau_decay = 2.000; break;
+    case 2: a.mode = 2; a.hangtime = 1.000; a.tau_decay = 0.500; break;
+    case 3: a.mode = 3; a.hang_thresh = 1.0; a.hangtime = 0.000; a.tau_decay = 0.250; break;
+    case 4: a.mode = 4; a.hang_thresh = 1.0; a.hangtime = 0.000; a.tau_decay = 0.050; break;
+    default: a.mode = 5; return;
+    }
+    s->load_agc();
+}
+
+int SeqStage::run(const void *d_in, long is, void *d_out, long os, int n, cudaStream_t s)
+{
+    if (n <= 0) return QC_OK;
+    const int tb = 32, nb = (C + tb - 1) / tb;
+    SeqPar P;
+    memcpy(P.v, par, sizeof(P.v));
+    const cd *in = (const cd *)d_in; cd *out = (cd *)d_out;
+    switch (kind) {
+    case SEQ_SHIFT: shift_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, d_par); break;
+    case SEQ_WCPAGC: wcpagc_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, d_ring, agc); break;
+    case SEQ_AMD: amd_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, P); break;
+    case SEQ_FMPLL: fmpll_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, P); break;
+    case SEQ_SNOTCH: snotch_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, P); break;
+    case SEQ_METER: meter_kernel<<<nb, tb, 0, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out); break;
+    default: set_error("seq stage: unknown kind %d", kind); return QC_EINVAL;
+    }
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+SeqStage *make_shift(int C, int rate, const double *shift_hz)
+{
+    SeqStage *s = new SeqStage();
+    if (s->init_common(SEQ_SHIFT, C, 1) != QC_OK) { s->release(); delete s; return nullptr; }
+    std::vector<double> p((size_t)C * 3);
+    for (int c = 0; c < C; c++) {       // calc_shift, shift.c:29-34
+        const double delta = kTWOPI * (shift_hz ? shift_hz[c] : 0.0) / (double)rate;
+        p[c * 3] = delta; p[c * 3 + 1] = cos(delta); p[c * 3 + 2] = sin(delta);
+    }
+    if (cudaMalloc((void **)&s->d_par, p.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(s->d_par, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { s->release(); delete s; return nullptr; }
+    return s;
+}
+
+SeqStage *make_wcpagc(int C, int rate, int mode)
+{
+    SeqStage *s = new SeqStage();
+    AgcParams &a = s->agc;
+    memset(&a, 0, sizeof(a));
+    // create_rxa's arguments to create_wcpagc (RXA.c:337-360)
+    a.mode = 3; a.pmode = 1; a.sample_rate = (double)rate; a.tau_attack = 0.001; a.tau_decay = 0.250; a.n_tau = 4;
+    a.max_gain = 10000.0; a.var_gain = 1.5; a.fixed_gain = 1000.0; a.max_input = 1.0; a.out_targ = 1.0;
+    a.tau_fast_backaverage = 0.250; a.tau_fast_decay = 0.005; a.pop_ratio = 5.0; a.hang_enable = 1;
+    a.tau_hang_backmult = 0.500; a.hangtime = 0.250; a.hang_thresh = 0.250; a.tau_hang_decay = 0.100;
+    s->load_agc();
+    agc_set_mode(s, mode);
+    s->kind = SEQ_WCPAGC;
+    s->ring_len = a.attack_buffsize + 1;    // the reference ring is RB_SIZE long; only this window is ever live
+    a.ring_buffsize = s->ring_len;
+    if (cudaMalloc((void **)&s->d_ring, (size_t)C * s->ring_len * 3 * sizeof(double)) != cudaSuccess) { delete s; return nullptr; }
+    if (s->init_common(SEQ_WCPAGC, C, 16) != QC_OK) { s->release(); delete s; return nullptr; }
+    return s;
+}
+
+SeqStage *make_amd(int C, int rate, int mode, int levelfade, int sbmode)
+{
+    SeqStage *s = new SeqStage();
+    if (s->init_common(SEQ_AMD, C, 104) != QC_OK) { s->release(); delete s; return nullptr; }
+    // init_amd (amd.c:72-107) with create_rxa's constants (RXA.c:175-189)
+    const double sr = (double)rate, fmin = -2000.0, fmax = +2000.0, zeta = 1.0, omegaN = 250.0, tauR = 0.02, tauI = 1.4;
+    double *p = s->par;
+    p[0] = mode; p[1] = levelfade; p[2] = sbmode;
+    p[3] = kTWOPI * fmin / sr; p[4] = kTWOPI * fmax / sr;
+    p[5] = 1.0 - exp(-2.0 * omegaN * zeta / sr);
+    p[6] = -p[5] + 2.0 * (1 - exp(-omegaN * zeta / sr) * cos(omegaN / sr * sqrt(1.0 - zeta * zeta)));
+    p[7] = exp(-1.0 / (sr * tauR)); p[8] = 1.0 - p[7];
+    p[9] = exp(-1.0 / (sr * tauI)); p[10] = 1.0 - p[9];
+    return s;
+}
+
+SeqStage *make_fmpll(int C, int rate, double deviation, double fmin, double fmax, double zeta, double omegaN, double tau)
+{
+    SeqStage *s = new SeqStage();
+    if (s->init_common(SEQ_FMPLL, C, 4) != QC_OK) { s->release(); delete s; return nullptr; }
+    const double sr = (double)rate;         // calc_fmd, fmd.c:29-47
+    double *p = s->par;
+    p[0] = kTWOPI * fmin / sr; p[1] = kTWOPI * fmax / sr;
+    p[2] = 1.0 - exp(-2.0 * omegaN * zeta / sr);
+    p[3] = -p[2] + 2.0 * (1 - exp(-omegaN * zeta / sr) * cos(omegaN / sr * sqrt(1.0 - zeta * zeta)));
+    p[4] = exp(-1.0 / (sr * tau)); p[5] = 1.0 - p[4];
+    p[6] = sr / (deviation * kTWOPI);
+    return s;
+}
+
+SeqStage *make_snotch(int C, int rate, double f, double bw)
+{
+    SeqStage *s = new SeqStage();
+    if (s->init_common(SEQ_SNOTCH, C, 4) != QC_OK) { s->release(); delete s; return nullptr; }
+    // calc_snotch, iir.c:29-48
+    const double fn = f / (double)rate;
+    const double csn = cos(kTWOPI * fn);
+    const double qr = 1.0 - 3.0 * bw;
+    const double qk = (1.0 - 2.0 * qr * csn + qr * qr) / (2.0 * (1.0 - csn));
+    double *p = s->par;
+    p[0] = +qk; p[1] = -2.0 * qk * csn; p[2] = +qk; p[3] = +2.0 * qr * csn; p[4] = -qr * qr;
+    return s;
+}
+
+SeqStage *make_meter(int C, int rate, double tau_av, double tau_decay)
+{
+    SeqStage *s = new SeqStage();
+    s->kind = SEQ_METER;
+    if (cudaMalloc((void **)&s->d_meter, (size_t)C * 3 * sizeof(double)) != cudaSuccess) { delete s; return nullptr; }
+    if (s->init_common(SEQ_METER, C, 2) != QC_OK) { s->release(); delete s; return nullptr; }
+    s->par[0] = exp(-1.0 / ((double)rate * tau_av));        // calc_meter, meter.c:30-34
+    s->par[1] = exp(-1.0 / ((double)rate * tau_decay));
+    return s;
+}
+
+}  // namespace qc
+
+struct qcSeqStage { qc::SeqStage *s; };
+
+extern "C" {
+
+static qcSeqStage *wrap(qc::SeqStage *s) { if (!s) return nullptr; qcSeqStage *w = new qcSeqStage(); w->s = s; return w; }
+
+qcSeqStage *quisk_cuda_shift_create(int n_channels, int rate, const double *shift_hz)
+{ return qc::ensure_device() == QC_OK ? wrap(qc::make_shift(n_channels, rate, shift_hz)) : nullptr; }
+qcSeqStage *quisk_cuda_wcpagc_create(int n_channels, int rate, int mode)
+{ return qc::ensure_device() == QC_OK ? wrap(qc::make_wcpagc(n_channels, rate, mode)) : nullptr; }
+int quisk_cuda_wcpagc_set_fixed_gain_db(qcSeqStage *s, double gain_db)
+{ if (!s || s->s->kind != qc::SEQ_WCPAGC) return QC_EINVAL; s->s->agc.fixed_gain = pow(10.0, gain_db / 20.0); s->s->load_agc(); return QC_OK; }
+int quisk_cuda_wcpagc_set_top_db(qcSeqStage *s, double max_gain_db)
+{ if (!s || s->s->kind != qc::SEQ_WCPAGC) return QC_EINVAL; s->s->agc.max_gain = pow(10.0, max_gain_db / 20.0); s->s->load_agc(); return QC_OK; }
+qcSeqStage *quisk_cuda_amd_create(int n_channels, int rate, int mode, int levelfade, int sbmode)
+{ return qc::ensure_device() == QC_OK ? wrap(qc::make_amd(n_channels, rate, mode, levelfade, sbmode)) : nullptr; }
+qcSeqStage *quisk_cuda_fmpll_create(int n_channels, int rate, double deviation, double fmin, double fmax, double zeta, double omegaN, double tau)
+{ return qc::ensure_device() == QC_OK ? wrap(qc::make_fmpll(n_channels, rate, deviation, fmin, fmax, zeta, omegaN, tau)) : nullptr; }
+qcSeqStage *quisk_cuda_snotch_create(int n_channels, int rate, double f, double bw)
+{ return qc::ensure_device() == QC_OK ? wrap(qc::make_snotch(n_channels, rate, f, bw)) : nullptr; }
+void quisk_cuda_seq_destroy(qcSeqStage *s) { if (s) { s->s->release(); delete s->s; delete s; } }
+int quisk_cuda_seq_run(qcSeqStage *s, const void *d_in, long in_stride, void *d_out, long out_stride, int n, void *stream)
+{ return s ? s->s->run(d_in, in_stride, d_out, out_stride, n, (cudaStream_t)stream) : QC_EINVAL; }
+int quisk_cuda_seq_flush(qcSeqStage *s) { return s ? s->s->flush() : QC_EINVAL; }
+
+}  // extern "C"

@@ -87,6 +87,48 @@ def load() -> C.CDLL:
     lib.quisk_cuda_pan_average_ptr.argtypes = [vp]
     lib.quisk_cuda_pan_average_ptr.restype = vp
     lib.quisk_cuda_fft_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    # ---- WDSP RXA part (include/quisk_cuda_wdsp.h) ----
+    D = C.c_double
+    lib.quisk_cuda_fir_bandpass.argtypes = [C.c_int, D, D, D, C.c_int, C.c_int, D, vp]
+    lib.quisk_cuda_fc_impulse.argtypes = [C.c_int, D, D, D, D, C.c_int, D, D, C.c_int, C.c_int, vp]
+    lib.quisk_cuda_resample_design.argtypes = [C.c_int, C.c_int, D, C.c_int, D, c_int_p, c_int_p, c_int_p, vp, C.c_int]
+    lib.quisk_cuda_fircore_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.quisk_cuda_fircore_create.restype = vp
+    lib.quisk_cuda_fircore_destroy.argtypes = [vp]; lib.quisk_cuda_fircore_destroy.restype = None
+    lib.quisk_cuda_fircore_run.argtypes = [vp, vp, C.c_long, vp, C.c_long, vp]
+    lib.quisk_cuda_fircore_set_impulse.argtypes = [vp, vp, C.c_int]
+    lib.quisk_cuda_fircore_update.argtypes = [vp]
+    lib.quisk_cuda_fircore_flush.argtypes = [vp]
+    lib.quisk_cuda_resample_create.argtypes = [C.c_int, C.c_int, C.c_int, D, C.c_int, D]
+    lib.quisk_cuda_resample_create.restype = vp
+    lib.quisk_cuda_resample_destroy.argtypes = [vp]; lib.quisk_cuda_resample_destroy.restype = None
+    lib.quisk_cuda_resample_count_out.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_resample_run.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p, vp]
+    lib.quisk_cuda_shift_create.argtypes = [C.c_int, C.c_int, vp]; lib.quisk_cuda_shift_create.restype = vp
+    lib.quisk_cuda_wcpagc_create.argtypes = [C.c_int, C.c_int, C.c_int]; lib.quisk_cuda_wcpagc_create.restype = vp
+    lib.quisk_cuda_wcpagc_set_fixed_gain_db.argtypes = [vp, D]
+    lib.quisk_cuda_wcpagc_set_top_db.argtypes = [vp, D]
+    lib.quisk_cuda_amd_create.argtypes = [C.c_int] * 5; lib.quisk_cuda_amd_create.restype = vp
+    lib.quisk_cuda_fmpll_create.argtypes = [C.c_int, C.c_int, D, D, D, D, D, D]; lib.quisk_cuda_fmpll_create.restype = vp
+    lib.quisk_cuda_snotch_create.argtypes = [C.c_int, C.c_int, D, D]; lib.quisk_cuda_snotch_create.restype = vp
+    lib.quisk_cuda_seq_destroy.argtypes = [vp]; lib.quisk_cuda_seq_destroy.restype = None
+    lib.quisk_cuda_seq_run.argtypes = [vp, vp, C.c_long, vp, C.c_long, C.c_int, vp]
+    lib.quisk_cuda_seq_flush.argtypes = [vp]
+    lib.quisk_cuda_rxa_create.argtypes = [C.c_int] * 6; lib.quisk_cuda_rxa_create.restype = vp
+    lib.quisk_cuda_rxa_destroy.argtypes = [vp]; lib.quisk_cuda_rxa_destroy.restype = None
+    lib.quisk_cuda_rxa_set_mode.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_set_passband.argtypes = [vp, D, D]
+    lib.quisk_cuda_rxa_set_nc.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_set_agc_mode.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_set_agc_fixed.argtypes = [vp, D]
+    lib.quisk_cuda_rxa_set_shift.argtypes = [vp, C.c_int, vp]
+    lib.quisk_cuda_rxa_set_nbp_run.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_set_panel_gain.argtypes = [vp, D]
+    lib.quisk_cuda_rxa_in_size.argtypes = [vp]
+    lib.quisk_cuda_rxa_out_size.argtypes = [vp]
+    lib.quisk_cuda_rxa_xrxa.argtypes = [vp, vp, C.c_long, vp, C.c_long, vp]
+    lib.quisk_cuda_rxa_fexchange0.argtypes = [vp, vp, vp, c_int_p]
+    lib.quisk_cuda_rxa_get_meter.argtypes = [vp, C.c_int, vp, vp, vp]
     _lib = lib
     return lib
 

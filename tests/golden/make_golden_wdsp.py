@@ -1,0 +1,225 @@
+"""tests/golden/make_golden_wdsp.py -- known-answer fixtures for the WDSP RXA stages, generated from the
+COMPILED REFERENCE (oracle/_ref/libwdsp_ref.so = wdsp/*.c + our FFTW-API shim, built by
+oracle/build_ref.sh).  WDSP ships no tests; these are outputs of its own code on seeded inputs.
+Writes tests/golden/wdsp_kat.npz.   Run:  python tests/golden/make_golden_wdsp.py
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import ref_ctypes as R            # noqa: E402
+
+D = C.c_double
+VP = C.c_void_p
+
+
+def wdsp():
+    lib = R.load("libwdsp_ref.so")
+    lib.fir_bandpass.restype = C.POINTER(D)
+    lib.fir_bandpass.argtypes = [C.c_int, D, D, D, C.c_int, C.c_int, D]
+    lib.create_fircore.restype = VP
+    lib.create_fircore.argtypes = [C.c_int, VP, VP, C.c_int, C.c_int, VP]
+    lib.xfircore.argtypes = [VP]
+    lib.setImpulse_fircore.argtypes = [VP, VP, C.c_int]
+    lib.create_resample.restype = VP
+    lib.create_resample.argtypes = [C.c_int, C.c_int, VP, VP, C.c_int, C.c_int, D, C.c_int, D]
+    lib.xresample.argtypes = [VP]
+    lib.xresample.restype = C.c_int
+    lib.create_shift.restype = VP
+    lib.create_shift.argtypes = [C.c_int, C.c_int, VP, VP, C.c_int, D]
+    lib.xshift.argtypes = [VP]
+    lib.create_wcpagc.restype = VP
+    lib.create_wcpagc.argtypes = [C.c_int, C.c_int, C.c_int, VP, VP, C.c_int, C.c_int, D, D, C.c_int] + [D] * 8 + [C.c_int] + [D] * 4
+    lib.xwcpagc.argtypes = [VP]
+    lib.create_amd.restype = VP
+    lib.create_amd.argtypes = [C.c_int, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, D, D, D, D, D, D]
+    lib.xamd.argtypes = [VP]
+    lib.create_fmd.restype = VP
+    lib.create_fmd.argtypes = [C.c_int, C.c_int, VP, VP, C.c_int] + [D] * 9 + [C.c_int, D, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.xfmd.argtypes = [VP]
+    lib.OpenChannel.argtypes = [C.c_int] * 8 + [D] * 4 + [C.c_int]
+    lib.fexchange0.argtypes = [C.c_int, VP, VP, VP]
+    lib.SetRXAMode.argtypes = [C.c_int, C.c_int]
+    lib.RXASetPassband.argtypes = [C.c_int, D, D]
+    lib.RXASetNC.argtypes = [C.c_int, C.c_int]
+    lib.SetRXAAGCMode.argtypes = [C.c_int, C.c_int]
+    lib.SetRXAShiftRun.argtypes = [C.c_int, C.c_int]
+    return lib
+
+
+def sig(n, seed, fs, tones=((1000.0, 0.3), (-1500.0, 0.2), (4000.0, 0.1)), noise=0.01):
+    """Complex test signal in WDSP's +-1.0 range."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    x = np.zeros(n, dtype=np.complex128)
+    for f, a in tones:
+        x += a * np.exp(2j * np.pi * f * t + 1j * rng.uniform(0, 2 * np.pi))
+    return x + noise * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+
+
+def fm_sig(n, seed, fs, dev=5000.0, fmod=1000.0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    ph = dev / fmod * np.sin(2 * np.pi * fmod * t)
+    return 0.5 * np.exp(1j * ph) + 0.001 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+
+
+def am_sig(n, seed, fs, fc=300.0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    env = 0.4 * (1 + 0.5 * np.sin(2 * np.pi * 700.0 * t) + 0.3 * np.sin(2 * np.pi * 1900.0 * t))
+    return env * np.exp(2j * np.pi * fc * t) + 0.002 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+
+
+def bandpass(lib, N, fl, fh, rate, wintype, rtype, scale):
+    p = lib.fir_bandpass(N, fl, fh, rate, wintype, rtype, scale)
+    return np.ctypeslib.as_array(p, (N * (2 if rtype else 1),)).copy()
+
+
+FM_BLOCKS = 176
+FIRCORE_CASES = [(64, 256, 48000.0), (256, 1024, 48000.0), (1024, 4096, 192000.0), (256, 256, 48000.0)]
+RESAMPLE_CASES = [(384000, 48000, [2048, 2048, 1000, 24]), (192000, 48000, [1024, 7, 1017]), (48000, 192000, [256, 255]),
+                  (44100, 48000, [4096, 441])]
+
+
+def main():
+    lib = wdsp()
+    out = {}
+    # ---- fircore ----
+    for size, nc, rate in FIRCORE_CASES:
+        imp = bandpass(lib, nc, 150.0, 2850.0, rate, 0, 1, 1.0 / (2 * size))
+        imp2 = bandpass(lib, nc, -2850.0, -150.0, rate, 0, 1, 1.0 / (2 * size))
+        inb = np.zeros(size, dtype=np.complex128); outb = np.zeros(2 * size, dtype=np.complex128)
+        f = lib.create_fircore(size, inb.ctypes.data, outb.ctypes.data, nc, 0, imp.ctypes.data)
+        x = sig(size * 8, 100 + size, rate)
+        ys = []
+        for b in range(8):
+            if b == 5:
+                lib.setImpulse_fircore(f, imp2.ctypes.data, 1)      # retune mid-stream
+            inb[:] = x[b * size:(b + 1) * size]
+            lib.xfircore(f)
+            ys.append(outb[:size].copy())
+        out["fircore_%d_%d/y" % (size, nc)] = np.concatenate(ys)
+    # ---- resample ----
+    for in_rate, out_rate, splits in RESAMPLE_CASES:
+        x = sig(sum(splits), 200, in_rate)
+        ys, counts, pos = [], [], 0
+        r = None
+        cap = max(splits) * max(1, out_rate // in_rate + 1) + 16
+        for n in splits:
+            inb = np.ascontiguousarray(x[pos:pos + n]); pos += n
+            outb = np.zeros(cap * 2, dtype=np.complex128)
+            # the reference object is tied to one block size: re-point its buffers per block
+            if r is None:
+                r = lib.create_resample(1, n, inb.ctypes.data, outb.ctypes.data, in_rate, out_rate, 0.0, 0, 1.0)
+            lib.setBuffers_resample.argtypes = [VP, VP, VP]; lib.setBuffers_resample(r, inb.ctypes.data, outb.ctypes.data)
+            lib.setSize_resample_keep = None
+            # `size` is the first int after `run` in struct _resample (resample.h): run, size
+            C.cast(r, C.POINTER(C.c_int))[1] = n
+            k = lib.xresample(r)
+            ys.append(outb[:k].copy()); counts.append(k)
+        out["resample_%d_%d/y" % (in_rate, out_rate)] = np.concatenate(ys)
+        out["resample_%d_%d/counts" % (in_rate, out_rate)] = np.array(counts)
+    # ---- shift ----
+    n = 1024
+    x = sig(3 * n, 300, 48000.0)
+    inb = np.zeros(n, dtype=np.complex128)
+    s = lib.create_shift(1, n, inb.ctypes.data, inb.ctypes.data, 48000, 1234.5)
+    ys = []
+    for b in range(3):
+        inb[:] = x[b * n:(b + 1) * n]; lib.xshift(s); ys.append(inb.copy())
+    out["shift/y"] = np.concatenate(ys)
+    # ---- wcpagc: create_rxa's parameters with the SetRXAAGCMode presets ----
+    for mode, hang_thresh, hangtime, tau_decay in [(3, 1.0, 0.0, 0.250), (1, 0.250, 2.0, 2.0), (4, 1.0, 0.0, 0.050)]:
+        n = 1024; rate = 192000 if mode == 3 else 48000
+        x = sig(8 * n, 400 + mode, float(rate))
+        x[2 * n:3 * n] *= 3.0; x[4 * n:6 * n] *= 0.05; x[6 * n:] *= 2.0      # level steps drive the state machine
+        inb = np.zeros(n, dtype=np.complex128)
+        a = lib.create_wcpagc(1, mode, 1, inb.ctypes.data, inb.ctypes.data, n, rate, 0.001, tau_decay, 4, 10000.0, 1.5, 1000.0,
+                              1.0, 1.0, 0.250, 0.005, 5.0, 1, 0.500, hangtime, hang_thresh, 0.100)
+        ys = []
+        for b in range(8):
+            inb[:] = x[b * n:(b + 1) * n]; lib.xwcpagc(a); ys.append(inb.copy())
+        out["wcpagc_mode%d/y" % mode] = np.concatenate(ys)
+    # ---- amd ----
+    for mode, sb in [(0, 0), (1, 0), (1, 1), (1, 2)]:
+        n = 512
+        x = am_sig(4 * n, 500, 48000.0)
+        inb = np.zeros(n, dtype=np.complex128)
+        a = lib.create_amd(1, n, inb.ctypes.data, inb.ctypes.data, mode, 1, sb, 48000, -2000.0, 2000.0, 1.0, 250.0, 0.02, 1.4)
+        ys = []
+        for b in range(4):
+            inb[:] = x[b * n:(b + 1) * n]; lib.xamd(a); ys.append(inb.copy())
+        out["amd_%d_%d/y" % (mode, sb)] = np.concatenate(ys)
+    # ---- fmd (create_rxa's arguments) ----
+    n = 256
+    x = fm_sig(12 * n, 600, 48000.0)
+    inb = np.zeros(2 * n, dtype=np.complex128)      # fircore writes 2*size samples into its out buffer (firmin.c:318)
+    f = lib.create_fmd(1, n, inb.ctypes.data, inb.ctypes.data, 48000, 5000.0, 300.0, 3000.0, -8000.0, 8000.0, 1.0, 20000.0, 0.02, 0.5,
+                       1, 254.1, 2048, 0, 2048, 0)
+    ys = []
+    for b in range(12):
+        inb[:n] = x[b * n:(b + 1) * n]; lib.xfmd(f); ys.append(inb[:n].copy())
+    out["fmd/y"] = np.concatenate(ys)
+    # ---- the whole channel through OpenChannel + fexchange0 (blocking output, zero slew times) ----
+    def run_channel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, setup, x, nblocks):
+        lib.OpenChannel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, 0, 1, 0.0, 0.0, 0.0, 0.0, 1)
+        setup(ch)
+        out_size = in_size * out_rate // in_rate if out_rate <= in_rate else in_size * (out_rate // in_rate)
+        err = C.c_int(0)
+        ys = []
+        for b in range(nblocks):
+            inb = np.ascontiguousarray(x[b * in_size:(b + 1) * in_size])
+            outb = np.zeros(out_size, dtype=np.complex128)
+            lib.fexchange0(ch, inb.ctypes.data, outb.ctypes.data, C.byref(err))
+            assert err.value == 0
+            ys.append(outb)
+            # Pace the caller like a sound card would.  Called back to back, the reference's exchange
+            # (one block of slack from Sem_OutReady's initial credit, iobuffs.c:409-416) lets the caller
+            # run ahead of the DSP thread and its output becomes timing dependent -- two identical runs
+            # differ.  With pacing it is deterministic and equals the composition of its own stages.
+            time.sleep(0.004)
+        return np.concatenate(ys)
+
+    def setup_usb(ch):          # the C3 concretisation of SURVEY.md 8(d), scaled down
+        lib.SetRXAShiftRun(ch, 0)
+        lib.RXASetNC(ch, 2048)
+        lib.SetRXAMode(ch, 1)
+        lib.RXASetPassband(ch, 150.0, 2850.0)
+        lib.SetRXAAGCMode(ch, 3)
+    x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    out["rxa_usb/y"] = run_channel(0, 256, 256, 48000, 48000, 48000, setup_usb, x, 24)
+
+    def setup_default(ch):      # no mode set: bp1 still runs
+        lib.SetRXAShiftRun(ch, 0)
+    x = sig(256 * 16, 701, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    out["rxa_default/y"] = run_channel(1, 256, 256, 48000, 48000, 48000, setup_default, x, 16)
+
+    def setup_fm(ch):           # the C4 concretisation: 384 k in, 48 k dsp/out, FM
+        lib.SetRXAShiftRun(ch, 0)
+        lib.SetRXAMode(ch, 5)
+        lib.RXASetPassband(ch, -8000.0, 8000.0)
+    # The PLL starts on FFT rounding noise (nbp0 delays the signal by 1024 samples), so the first
+    # ~10^4 output samples depend on the FFT library's last bits -- in the reference too.  Parity is
+    # therefore taken on the tail of a long run, after the loop has locked and the DC estimate settled.
+    x = fm_sig(2048 * FM_BLOCKS, 702, 384000.0)
+    out["rxa_fm/y_tail"] = run_channel(2, 2048, 256, 384000, 48000, 48000, setup_fm, x, FM_BLOCKS)[-16 * 256:]
+
+    def setup_am(ch):
+        lib.SetRXAShiftRun(ch, 0)
+        lib.SetRXAMode(ch, 6)
+        lib.RXASetPassband(ch, -4000.0, 4000.0)
+    x = am_sig(256 * 16, 703, 48000.0)
+    out["rxa_am/y"] = run_channel(3, 256, 256, 48000, 48000, 48000, setup_am, x, 16)
+    np.savez_compressed(os.path.join(HERE, "wdsp_kat.npz"), **out)
+    print("wrote wdsp_kat.npz:", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
