@@ -166,6 +166,176 @@ def cpu_reference_rate(block, steps, warmup, workload, fi, fq, tune_hz):
 
 
 # --------------------------------------------------------------------------------------------
+# WDSP RXA workloads (BASELINE.json configs[2] and configs[3])
+# --------------------------------------------------------------------------------------------
+
+RXA_CFG = {
+    # 64 ch x 192 kS/s, dsp_size 1024, nbp0 nc 4096 (nfor 4, FFT 2048), wcpAGC mode 3, panel
+    "rxa_usb": dict(channels=64, in_size=1024, dsp_size=1024, in_rate=192000, dsp_rate=192000, out_rate=192000, mode=1,
+                    passband=(150.0, 2850.0), nc=4096, agc=3, alg_bytes=32.0,
+                    name="rxa_usb: C ch x 192 kS/s WDSP RXA nbp0 overlap-save bandpass (4096 taps) + wcpAGC + panel (BASELINE configs[2])"),
+    # C4: 256 ch x 384 kS/s -> resample (1121 taps, /8) -> 48 k -> nbp0 -> fmd (PLL + 2 fircores + notch) -> panel
+    "rxa_fm": dict(channels=256, in_size=2048, dsp_size=256, in_rate=384000, dsp_rate=48000, out_rate=48000, mode=5,
+                   passband=(-8000.0, 8000.0), nc=2048, agc=None, alg_bytes=18.0,
+                   name="rxa_fm: C ch x 384 kS/s WDSP RXA resample + nbp0 + fmd FM demod (BASELINE configs[3])"),
+}
+
+
+def rxa_reference_rate(cfg, blocks, steps, warmup):
+    """The reference's own stage functions (libwdsp_ref.so: wdsp/*.c + our FFTW-API shim -- FFTW3 itself is absent
+    from this image) composed in xrxa's order, one channel per host core."""
+    from tests.golden.make_golden_wdsp import wdsp, bandpass, sig, fm_sig
+    lib = wdsp()
+    cores = os.cpu_count() or 1
+    n, m = cfg["dsp_size"], cfg["in_size"]
+    objs = []
+    for i in range(cores):
+        inb = np.zeros(m, dtype=np.complex128); buf = np.zeros(2 * n, dtype=np.complex128)
+        o = {"inb": inb, "buf": buf}
+        if cfg["in_rate"] != cfg["dsp_rate"]:
+            o["rs"] = lib.create_resample(1, m, inb.ctypes.data, buf.ctypes.data, cfg["in_rate"], cfg["dsp_rate"], 0.0, 0, 1.0)
+        imp = bandpass(lib, cfg["nc"], cfg["passband"][0], cfg["passband"][1], float(cfg["dsp_rate"]), 0, 1, 1.0 / (2 * n))
+        o["nbp"] = lib.create_fircore(n, buf.ctypes.data, buf.ctypes.data, cfg["nc"], 0, imp.ctypes.data)
+        if cfg["mode"] == 5:
+            o["fmd"] = lib.create_fmd(1, n, buf.ctypes.data, buf.ctypes.data, cfg["dsp_rate"], 5000.0, 300.0, 3000.0, -8000.0, 8000.0,
+                                      1.0, 20000.0, 0.02, 0.5, 1, 254.1, cfg["nc"], 0, cfg["nc"], 0)
+        else:
+            o["agc"] = lib.create_wcpagc(1, 3, 1, buf.ctypes.data, buf.ctypes.data, n, cfg["dsp_rate"], 0.001, 0.250, 4, 10000.0, 1.5,
+                                         1000.0, 1.0, 1.0, 0.250, 0.005, 5.0, 1, 0.500, 0.0, 1.0, 0.100)
+        o["x"] = (fm_sig if cfg["mode"] == 5 else sig)(m * 4, 900 + i, float(cfg["in_rate"]))
+        objs.append(o)
+
+    def work(i, nblk):
+        o = objs[i]
+        for b in range(nblk):
+            if "rs" in o:
+                o["inb"][:] = o["x"][(b % 4) * m:(b % 4 + 1) * m]; lib.xresample(o["rs"])
+            else:
+                o["buf"][:n] = o["x"][(b % 4) * m:(b % 4 + 1) * m]
+            lib.xfircore(o["nbp"])
+            if "fmd" in o: lib.xfmd(o["fmd"])
+            else: lib.xwcpagc(o["agc"])
+            o["buf"][:n] *= 4.0
+
+    def run(nblk):
+        th = [threading.Thread(target=work, args=(i, nblk)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th: t.start()
+        for t in th: t.join()
+        return time.perf_counter() - t0
+    run(warmup * blocks)
+    dt = run(steps * blocks)
+    return cores * m * blocks * steps / dt / 1e6, cores, dt
+
+
+def rxa_main(args, rank, world, local_rank):
+    cfg = dict(RXA_CFG[args.workload])
+    C_ = args.channels if args.channels != 4096 else cfg["channels"]
+    blocks = 32
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, cores, dt = rxa_reference_rate(cfg, blocks, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "complex MS/s through RX chain", "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": cfg["name"], "channels": cores, "blocks_per_step": blocks},
+                "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
+                                 "sample": "%d channels x %d blocks x %d steps; libwdsp_ref.so stage functions (FFT = our shim, not FFTW3)" % (cores, blocks, args.steps)},
+                "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line)); return
+    import torch
+    import torch.distributed as dist
+    from quisk_b200 import lib as L
+    from tests.golden.make_golden_wdsp import sig, fm_sig
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = L.require_device()
+    L.check(lib, lib.quisk_cuda_set_device(local_rank), "set_device")
+    rxa = lib.quisk_cuda_rxa_create(C_, cfg["in_size"], cfg["dsp_size"], cfg["in_rate"], cfg["dsp_rate"], cfg["out_rate"])
+    if not rxa:
+        raise L.QuiskCudaError(lib.quisk_cuda_last_error().decode())
+    lib.quisk_cuda_rxa_set_shift(rxa, 0, None)
+    L.check(lib, lib.quisk_cuda_rxa_set_nc(rxa, cfg["nc"]), "set_nc")
+    L.check(lib, lib.quisk_cuda_rxa_set_mode(rxa, cfg["mode"]), "set_mode")
+    L.check(lib, lib.quisk_cuda_rxa_set_passband(rxa, *cfg["passband"]), "set_passband")
+    if cfg["agc"] is not None:
+        lib.quisk_cuda_rxa_set_agc_mode(rxa, cfg["agc"])
+    m = cfg["in_size"]; osz = lib.quisk_cuda_rxa_out_size(rxa)
+    base = np.stack([(fm_sig if cfg["mode"] == 5 else sig)(m * blocks, 900 + (c % 16), float(cfg["in_rate"])) for c in range(min(C_, 16))])
+    x = torch.from_numpy(base).to(dev).repeat((C_ + 15) // 16, 1)[:C_].contiguous()
+    y = torch.zeros((C_, osz * blocks), dtype=torch.complex128, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        for b in range(blocks):
+            L.check(lib, lib.quisk_cuda_rxa_xrxa(rxa, x.data_ptr() + b * m * 16, x.stride(0), y.data_ptr() + b * osz * 16, y.stride(0), stream), "xrxa")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = lib.quisk_cuda_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.quisk_cuda_launch_count() - l0)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * C_ * m * blocks * args.steps / (ms_max / 1e3) / 1e6
+    # e2e: the fexchange0-shaped host entry, block by block (H2D + xrxa + D2H per call)
+    e2e = None
+    if cfg["in_size"] == lib.quisk_cuda_rxa_in_size(rxa) and args.e2e_steps > 0:
+        hx = np.ascontiguousarray(x[:, :m].cpu().numpy()); hy = np.zeros((C_, osz), dtype=np.complex128)
+        err = C.c_int(0)
+        lib.quisk_cuda_rxa_fexchange0(rxa, hx.ctypes.data, hy.ctypes.data, C.byref(err))
+        t0 = time.perf_counter()
+        nb = blocks * args.e2e_steps
+        for _ in range(nb):
+            lib.quisk_cuda_rxa_fexchange0(rxa, hx.ctypes.data, hy.ctypes.data, C.byref(err))
+        dt = time.perf_counter() - t0
+        e2e = {"value": world * C_ * m * nb / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": C_ * m * 16 * blocks,
+               "d2h_bytes_per_step": C_ * osz * 16 * blocks, "note": "quisk_cuda_rxa_fexchange0, pageable host buffers, one call per DSP block"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    alg = cfg["alg_bytes"] * C_ * m * blocks
+    ach = alg * args.steps / (ms / 1e3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            v, cores, dt = rxa_reference_rate(cfg, blocks, 8, 1)
+            cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
+                   "sample": "%d channels x %d blocks x 8 steps, %.1f s wall; libwdsp_ref.so stage functions, FFT = our shim (FFTW3 absent)" % (cores, blocks, dt)}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
+    line = {"metric": "complex MS/s through RX chain", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "channels_per_gpu": C_, "blocks_per_step": blocks, "in_size": m, "dsp_size": cfg["dsp_size"],
+                       "l2": "working set %.0f MB per GPU; L2-resident by design for this config (FDL + masks), not flushed" % ((x.numel() + y.numel()) * 16 / 1e6)},
+            "clocks": sampler.result(), "gpu_launches": launches, "e2e": e2e,
+            "roofline": {"bound": "hbm", "kernel": "whole step (fircore + recurrent stages)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src}, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -173,7 +343,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rx_chain", choices=["rx_chain", "panadapter", "rx_chain+panadapter"])
+    ap.add_argument("--workload", default="rx_chain", choices=["rx_chain", "panadapter", "rx_chain+panadapter", "rxa_usb", "rxa_fm"])
     ap.add_argument("--channels", type=int, default=4096)
     ap.add_argument("--block", type=int, default=32768, help="input samples per channel per step (multiple of 8192)")
     ap.add_argument("--tune", type=float, default=12345.0, help="rx_tune_freq in Hz (0 = no tuning stage)")
@@ -190,6 +360,8 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     block = max(FFT_SIZE, (args.block // FFT_SIZE) * FFT_SIZE)
+    if args.workload.startswith("rxa_"):
+        return rxa_main(args, rank, world, local_rank)
 
     from quisk_b200.rx import load_tables
     tabs = load_tables()

@@ -3,9 +3,8 @@
 // xsnotch (wdsp/iir.c:76-95), xmeter (wdsp/meter.c:75-107) and xpanel (wdsp/patchpanel.c:55-105).
 //
 // These are scalar state machines / IIR recurrences: there is no parallelism along time that keeps
-// the reference's arithmetic, so ONE GPU THREAD WALKS ONE CHANNEL'S BLOCK and the batch supplies the
-// parallelism ("do not time-shard exactly; shard by channel").  A lane reads its
-// own row sequentially, so every 128-byte line is fetched once and reused for 8 samples out of L1.
+// the reference's arithmetic, so ONE LANE WALKS ONE CHANNEL'S BLOCK (out of shared memory) and the batch
+// supplies the parallelism ("do not time-shard exactly; shard by channel").
 // This file is compiled with --fmad=false: a*b+c is two roundings, as in the reference built by gcc for
 // baseline x86-64, so the state trajectories (AGC state switches, PLL phase) follow the reference's to
 // the last bit except where device libm (cos, sin, atan2, log10) differs from glibc by an ulp.
@@ -17,16 +16,37 @@ namespace qc {
 static const double kPI = 3.1415926535897932, kTWOPI = 6.2831853071795864;
 #define TWOPI_D 6.2831853071795864
 
+// Execution shape shared by these kernels: ONE CTA PER CHANNEL.  The block is staged in shared memory with
+// coalesced 16-byte loads, lane 0 walks the recurrence over shared memory (a dependent FP64 chain of a few
+// tens of cycles per sample instead of an L2 round trip per sample), then the CTA stores the block
+// coalesced.  SEQ_T threads only do the staging; the batch of channels supplies the parallelism.
+static constexpr int SEQ_T = 64;
+#define SEQ_STAGE_IN()                                                              \
+    extern __shared__ double seq_smem[];                                            \
+    cd *sx = reinterpret_cast<cd *>(seq_smem);                                      \
+    const int c = blockIdx.x;                                                       \
+    {                                                                               \
+        const cd *gx = in + (size_t)c * is;                                         \
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = gx[i];            \
+    }                                                                               \
+    __syncthreads();
+#define SEQ_STAGE_OUT()                                                             \
+    __syncthreads();                                                                \
+    {                                                                               \
+        cd *gy = out + (size_t)c * os;                                              \
+        for (int i = threadIdx.x; i < n; i += blockDim.x) gy[i] = sx[i];            \
+    }
+
 // ------------------------------------------------------------------------------------------- shift
 __global__ void shift_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, const double *par)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    SEQ_STAGE_IN();
+    if (threadIdx.x == 0) {
     double phase = state[c];
     const double delta = par[c * 3], cos_delta = par[c * 3 + 1], sin_delta = par[c * 3 + 2];
     double cos_phase = cos(phase), sin_phase = sin(phase);
-    const cd *x = in + (size_t)c * is;
-    cd *y = out + (size_t)c * os;
+    const cd *x = sx;
+    cd *y = sx;
     for (int i = 0; i < n; i++) {
         const double I1 = x[i].x, Q1 = x[i].y;
         y[i] = make_double2(I1 * cos_phase - Q1 * sin_phase, I1 * sin_phase + Q1 * cos_phase);
@@ -38,85 +58,129 @@ __global__ void shift_kernel(const cd *in, long is, cd *out, long os, int n, int
         if (phase < 0.0) phase += TWOPI_D;
     }
     state[c] = phase;
+    }
+    SEQ_STAGE_OUT();
 }
 
 // ------------------------------------------------------------------------------------------ wcpagc
-// state: 0 out_index 1 in_index 2 ring_max 3 volts 4 save_volts 5 fast_backaverage 6 hang_backaverage
+// state: 0 (unused) 1 (unused) 2 ring_max 3 volts 4 save_volts 5 fast_backaverage 6 hang_backaverage
 //        7 hang_counter 8 decay_type 9 state 10 gain
-__global__ void wcpagc_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, double *ring, AgcParams a)
+// hist : [C][ab][3] the last ab = attack_buffsize inputs (re, im, |x|), oldest first -- the live part of the
+//        reference's ring (wcpAGC.c:179-190: out_index trails in_index by attack_buffsize).
+//
+// One CTA per channel, four phases:
+//  1. stage [history | block] and the magnitudes in shared memory (coalesced);
+//  2. ring_max for every sample IN PARALLEL.  The reference maintains it lazily (rescan the window when the
+//     outgoing sample was the maximum, wcpAGC.c:196-210), but its value is exactly the maximum of the last
+//     attack_buffsize magnitudes including the new one -- a pure function of the input, no rounding involved;
+//  3. lane 0 walks the five-state attack/decay/hang machine (wcpAGC.c:215-333) over shared memory: volts[i];
+//  4. the gain law (log10, divide) and the delayed output sample for every i in parallel (wcpAGC.c:335-340).
+__global__ void __launch_bounds__(128) wcpagc_kernel(const cd *in, long is, cd *out, long os, int n, int C,
+                                                     double *state, double *hist, AgcParams a)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    extern __shared__ double seq_smem[];
+    const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const cd *x = in + (size_t)c * is;
     cd *y = out + (size_t)c * os;
-    if (a.mode == 0) {
-        for (int i = 0; i < n; i++) y[i] = make_double2(a.fixed_gain * x[i].x, a.fixed_gain * x[i].y);
+    if (a.mode == 0) {          // fixed gain, wcpAGC.c:168-176
+        for (int i = tid; i < n; i += nt) y[i] = make_double2(a.fixed_gain * x[i].x, a.fixed_gain * x[i].y);
         return;
     }
+    const int ab = a.attack_buffsize, tot = ab + n;
+    cd *X = reinterpret_cast<cd *>(seq_smem);               // [tot]
+    double *A = reinterpret_cast<double *>(X + tot);        // [tot] magnitudes
+    double *RM = A + tot;                                   // [n]  ring_max, then reused for mult
+    double *V = RM + n;                                     // [n]  volts
+    double *BM = V + n;                                     // [(tot + 31) / 32] block maxima
+    double *hs = hist + (size_t)c * ab * 3;
+    for (int i = tid; i < ab; i += nt) { X[i] = make_double2(hs[i * 3], hs[i * 3 + 1]); A[i] = hs[i * 3 + 2]; }
+    for (int i = tid; i < n; i += nt) {
+        const cd v = x[i];
+        X[ab + i] = v;
+        double m;
+        if (a.pmode == 0) { const double f0 = fabs(v.x), f1 = fabs(v.y); m = f0 < f1 ? f1 : f0; }
+        else m = sqrt(v.x * v.x + v.y * v.y);
+        A[ab + i] = m;
+    }
+    __syncthreads();
+    const int nblk = (tot + 31) >> 5;
+    for (int j = tid; j < nblk; j += nt) {
+        double m = 0.0;
+        const int e = min(tot, (j + 1) << 5);
+        for (int k = j << 5; k < e; k++) m = A[k] > m ? A[k] : m;
+        BM[j] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        // window = combined indices [i + 1, i + ab]
+        const int lo = i + 1, hi = i + ab;
+        double m = 0.0;
+        const int b0 = (lo + 31) >> 5, b1 = (hi + 1) >> 5;  // whole 32-blocks [b0, b1)
+        if (b0 >= b1) {
+            for (int k = lo; k <= hi; k++) m = A[k] > m ? A[k] : m;
+        } else {
+            for (int k = lo; k < (b0 << 5); k++) m = A[k] > m ? A[k] : m;
+            for (int j = b0; j < b1; j++) m = BM[j] > m ? BM[j] : m;
+            for (int k = b1 << 5; k <= hi; k++) m = A[k] > m ? A[k] : m;
+        }
+        RM[i] = m;
+    }
+    __syncthreads();
     double *st = state + (size_t)c * 16;
-    double *rg = ring + (size_t)c * a.ring_buffsize * 3;
-    int out_index = (int)st[0], in_index = (int)st[1];
-    double ring_max = st[2], volts = st[3], save_volts = st[4], fast_backaverage = st[5], hang_backaverage = st[6];
-    int hang_counter = (int)st[7], decay_type = (int)st[8], state_ = (int)st[9];
-    double gain = st[10];
-    for (int i = 0; i < n; i++) {
-        if (++out_index >= a.ring_buffsize) out_index -= a.ring_buffsize;
-        if (++in_index >= a.ring_buffsize) in_index -= a.ring_buffsize;
-        const double o0 = rg[out_index * 3], o1 = rg[out_index * 3 + 1], abs_out_sample = rg[out_index * 3 + 2];
-        const double r0 = x[i].x, r1 = x[i].y;
-        rg[in_index * 3] = r0; rg[in_index * 3 + 1] = r1;
-        double ab;
-        if (a.pmode == 0) { const double f0 = fabs(r0), f1 = fabs(r1); ab = f0 < f1 ? f1 : f0; }
-        else ab = sqrt(r0 * r0 + r1 * r1);
-        rg[in_index * 3 + 2] = ab;
-        fast_backaverage = a.fast_backmult * abs_out_sample + a.onemfast_backmult * fast_backaverage;
-        hang_backaverage = a.hang_backmult * abs_out_sample + a.onemhang_backmult * hang_backaverage;
-        if (abs_out_sample >= ring_max && abs_out_sample > 0.0) {
-            ring_max = 0.0;
-            int k = out_index;
-            for (int j = 0; j < a.attack_buffsize; j++) {
-                if (++k == a.ring_buffsize) k = 0;
-                const double v = rg[k * 3 + 2];
-                if (v > ring_max) ring_max = v;
+    if (tid == 0) {
+        double volts = st[3], save_volts = st[4], fast_backaverage = st[5], hang_backaverage = st[6];
+        int hang_counter = (int)st[7], decay_type = (int)st[8], state_ = (int)st[9];
+        for (int i = 0; i < n; i++) {
+            const double abs_out_sample = A[i];
+            const double ring_max = RM[i];
+            fast_backaverage = a.fast_backmult * abs_out_sample + a.onemfast_backmult * fast_backaverage;
+            hang_backaverage = a.hang_backmult * abs_out_sample + a.onemhang_backmult * hang_backaverage;
+            if (hang_counter > 0) --hang_counter;
+            switch (state_) {
+            case 0:
+                if (ring_max >= volts) volts += (ring_max - volts) * a.attack_mult;
+                else if (volts > a.pop_ratio * fast_backaverage) { state_ = 1; volts += (ring_max - volts) * a.fast_decay_mult; }
+                else if (a.hang_enable && hang_backaverage > a.hang_level) { state_ = 2; hang_counter = (int)(a.hangtime * a.sample_rate); decay_type = 1; }
+                else { state_ = 3; volts += (ring_max - volts) * a.decay_mult; decay_type = 0; }
+                break;
+            case 1:
+                if (ring_max >= volts) { state_ = 0; volts += (ring_max - volts) * a.attack_mult; }
+                else if (volts > save_volts) volts += (ring_max - volts) * a.fast_decay_mult;
+                else if (hang_counter > 0) state_ = 2;
+                else if (decay_type == 0) { state_ = 3; volts += (ring_max - volts) * a.decay_mult; }
+                else { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
+                break;
+            case 2:
+                if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
+                else if (hang_counter == 0) { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
+                break;
+            case 3:
+                if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
+                else volts += (ring_max - volts) * a.decay_mult;
+                break;
+            case 4:
+                if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
+                else volts += (ring_max - volts) * a.hang_decay_mult;
+                break;
             }
+            if (volts < a.min_volts) volts = a.min_volts;
+            V[i] = volts;
         }
-        if (ab > ring_max) ring_max = ab;
-        if (hang_counter > 0) --hang_counter;
-        switch (state_) {
-        case 0:
-            if (ring_max >= volts) volts += (ring_max - volts) * a.attack_mult;
-            else if (volts > a.pop_ratio * fast_backaverage) { state_ = 1; volts += (ring_max - volts) * a.fast_decay_mult; }
-            else if (a.hang_enable && hang_backaverage > a.hang_level) { state_ = 2; hang_counter = (int)(a.hangtime * a.sample_rate); decay_type = 1; }
-            else { state_ = 3; volts += (ring_max - volts) * a.decay_mult; decay_type = 0; }
-            break;
-        case 1:
-            if (ring_max >= volts) { state_ = 0; volts += (ring_max - volts) * a.attack_mult; }
-            else if (volts > save_volts) volts += (ring_max - volts) * a.fast_decay_mult;
-            else if (hang_counter > 0) state_ = 2;
-            else if (decay_type == 0) { state_ = 3; volts += (ring_max - volts) * a.decay_mult; }
-            else { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
-            break;
-        case 2:
-            if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
-            else if (hang_counter == 0) { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
-            break;
-        case 3:
-            if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
-            else volts += (ring_max - volts) * a.decay_mult;
-            break;
-        case 4:
-            if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
-            else volts += (ring_max - volts) * a.hang_decay_mult;
-            break;
-        }
-        if (volts < a.min_volts) volts = a.min_volts;
-        gain = volts * a.inv_out_target;
+        st[2] = RM[n - 1]; st[3] = volts; st[4] = save_volts; st[5] = fast_backaverage; st[6] = hang_backaverage;
+        st[7] = hang_counter; st[8] = decay_type; st[9] = state_; st[10] = volts * a.inv_out_target;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+        const double volts = V[i];
         const double lg = log10(a.inv_max_input * volts);
         const double mult = (a.out_target - a.slope_constant * (0.0 < lg ? 0.0 : lg)) / volts;
-        y[i] = make_double2(o0 * mult, o1 * mult);
+        const cd o = X[i];                                  // the sample written attack_buffsize inputs ago
+        y[i] = make_double2(o.x * mult, o.y * mult);
     }
-    st[0] = out_index; st[1] = in_index; st[2] = ring_max; st[3] = volts; st[4] = save_volts;
-    st[5] = fast_backaverage; st[6] = hang_backaverage; st[7] = hang_counter; st[8] = decay_type; st[9] = state_; st[10] = gain;
+    for (int i = tid; i < ab; i += nt) {
+        const cd v = X[n + i];
+        hs[i * 3] = v.x; hs[i * 3 + 1] = v.y; hs[i * 3 + 2] = A[n + i];
+    }
 }
 
 // --------------------------------------------------------------------------------------------- amd
@@ -131,10 +195,10 @@ struct SeqPar { double v[32]; };
 
 __global__ void amd_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const cd *x = in + (size_t)c * is;
-    cd *y = out + (size_t)c * os;
+    SEQ_STAGE_IN();
+    if (threadIdx.x == 0) {
+    const cd *x = sx;
+    cd *y = sx;
     double *st = state + (size_t)c * 104;
     const int mode = (int)P.v[0], levelfade = (int)P.v[1], sbmode = (int)P.v[2];
     const double omega_min = P.v[3], omega_max = P.v[4], g1 = P.v[5], g2 = P.v[6];
@@ -194,16 +258,18 @@ __global__ void amd_kernel(const cd *in, long is, cd *out, long os, int n, int C
         }
     }
     st[0] = dc; st[1] = dc_insert; st[2] = phs; st[3] = fil_out; st[4] = omega; st[5] = dsI; st[6] = dsQ;
+    }
+    SEQ_STAGE_OUT();
 }
 
 // ------------------------------------------------------------------------------------------- fm pll
 // state: 0 phs 1 fil_out 2 omega 3 fmdc ; par: 0 omega_min 1 omega_max 2 g1 3 g2 4 mtau 5 onem_mtau 6 again
 __global__ void fmpll_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const cd *x = in + (size_t)c * is;
-    cd *y = out + (size_t)c * os;
+    SEQ_STAGE_IN();
+    if (threadIdx.x == 0) {
+    const cd *x = sx;
+    cd *y = sx;
     double *st = state + (size_t)c * 4;
     double phs = st[0], fil_out = st[1], omega = st[2], fmdc = st[3];
     const double omega_min = P.v[0], omega_max = P.v[1], g1 = P.v[2], g2 = P.v[3], mtau = P.v[4], onem_mtau = P.v[5], again = P.v[6];
@@ -226,16 +292,18 @@ __global__ void fmpll_kernel(const cd *in, long is, cd *out, long os, int n, int
         y[i] = make_double2(a, a);
     }
     st[0] = phs; st[1] = fil_out; st[2] = omega; st[3] = fmdc;
+    }
+    SEQ_STAGE_OUT();
 }
 
 // ------------------------------------------------------------------------------------------ snotch
 // state: x1 x2 y1 y2 ; par: a0 a1 a2 b1 b2.  Only the I rail is filtered (iir.c:85-86).
 __global__ void snotch_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const cd *x = in + (size_t)c * is;
-    cd *y = out + (size_t)c * os;
+    SEQ_STAGE_IN();
+    if (threadIdx.x == 0) {
+    const cd *x = sx;
+    cd *y = sx;
     double *st = state + (size_t)c * 4;
     double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
     const double a0 = P.v[0], a1 = P.v[1], a2 = P.v[2], b1 = P.v[3], b2 = P.v[4];
@@ -246,15 +314,17 @@ __global__ void snotch_kernel(const cd *in, long is, cd *out, long os, int n, in
         y2 = y1; y1 = o; x2 = x1; x1 = x0;
     }
     st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
+    }
+    SEQ_STAGE_OUT();
 }
 
 // ------------------------------------------------------------------------------------------- meter
 // state: avg peak ; par: mult_average mult_peak ; results: av dB, pk dB (10 log10, meter.c:98-99)
 __global__ void meter_kernel(const cd *in, long is, int n, int C, double *state, SeqPar P, double *result, const double *agc_state)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const cd *x = in + (size_t)c * is;
+    SEQ_STAGE_IN();
+    if (threadIdx.x != 0) return;
+    const cd *x = sx;
     double avg = state[c * 2], peak = state[c * 2 + 1];
     const double ma = P.v[0], mp = P.v[1];
     double np = 0.0;
@@ -322,7 +392,7 @@ int SeqStage::flush()
     if (kind == SEQ_WCPAGC) {
         // calc_wcpagc (wcpAGC.c:35-52): out_index = -1, in_index = attack_buffsize + out_index, everything else 0
         std::vector<double> st((size_t)C * 16, 0.0);
-        for (int c = 0; c < C; c++) { st[(size_t)c * 16] = -1.0; st[(size_t)c * 16 + 1] = agc.attack_buffsize - 1.0; }
+        for (int c = 0; c < C; c++) { st[(size_t)c * 16] = -1.0; st[(size_t)c * 16 + 1] = agc.attack_buffsize - 1.0; }     // informational
         QC_CUDA(cudaMemcpy(d_state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
         if (d_ring) QC_CUDA(cudaMemset(d_ring, 0, (size_t)C * ring_len * 3 * sizeof(double)));
     }
@@ -373,17 +443,25 @@ void agc_set_mode(SeqStage *s, int mode)
 int SeqStage::run(const void *d_in, long is, void *d_out, long os, int n, cudaStream_t s)
 {
     if (n <= 0) return QC_OK;
-    const int tb = 32, nb = (C + tb - 1) / tb;
     SeqPar P;
     memcpy(P.v, par, sizeof(P.v));
     const cd *in = (const cd *)d_in; cd *out = (cd *)d_out;
+    const size_t sh = (size_t)n * sizeof(cd);           // the staged block
+    if (sh > 200 * 1024) { set_error("seq stage: block of %d samples does not fit in shared memory", n); return QC_EINVAL; }
+#define QC_SEQ_OPTIN(k, bytes) do { if ((bytes) > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); } while (0)
     switch (kind) {
-    case SEQ_SHIFT: shift_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, d_par); break;
-    case SEQ_WCPAGC: wcpagc_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, d_ring, agc); break;
-    case SEQ_AMD: amd_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, P); break;
-    case SEQ_FMPLL: fmpll_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, P); break;
-    case SEQ_SNOTCH: snotch_kernel<<<nb, tb, 0, s>>>(in, is, out, os, n, C, d_state, P); break;
-    case SEQ_METER: meter_kernel<<<nb, tb, 0, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out); break;
+    case SEQ_SHIFT: QC_SEQ_OPTIN(shift_kernel, sh); shift_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, d_par); break;
+    case SEQ_WCPAGC: {
+        const int tot = agc.attack_buffsize + n;
+        const size_t sa = (size_t)tot * 24 + (size_t)n * 16 + (size_t)((tot + 31) / 32 + 1) * 8;
+        if (sa > 220 * 1024) { set_error("wcpagc: attack buffer + block (%d samples) exceed shared memory", tot); return QC_EINVAL; }
+        QC_SEQ_OPTIN(wcpagc_kernel, sa);
+        wcpagc_kernel<<<C, 128, sa, s>>>(in, is, out, os, n, C, d_state, d_ring, agc);
+        break; }
+    case SEQ_AMD: QC_SEQ_OPTIN(amd_kernel, sh); amd_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
+    case SEQ_FMPLL: QC_SEQ_OPTIN(fmpll_kernel, sh); fmpll_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
+    case SEQ_SNOTCH: QC_SEQ_OPTIN(snotch_kernel, sh); snotch_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
+    case SEQ_METER: QC_SEQ_OPTIN(meter_kernel, sh); meter_kernel<<<C, SEQ_T, sh, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out); break;
     default: set_error("seq stage: unknown kind %d", kind); return QC_EINVAL;
     }
     count_launch();
@@ -418,7 +496,7 @@ SeqStage *make_wcpagc(int C, int rate, int mode)
     s->load_agc();
     agc_set_mode(s, mode);
     s->kind = SEQ_WCPAGC;
-    s->ring_len = a.attack_buffsize + 1;    // the reference ring is RB_SIZE long; only this window is ever live
+    s->ring_len = a.attack_buffsize;        // the reference ring is RB_SIZE long; only the last attack_buffsize inputs are live
     a.ring_buffsize = s->ring_len;
     if (cudaMalloc((void **)&s->d_ring, (size_t)C * s->ring_len * 3 * sizeof(double)) != cudaSuccess) { delete s; return nullptr; }
     if (s->init_common(SEQ_WCPAGC, C, 16) != QC_OK) { s->release(); delete s; return nullptr; }
