@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--min-r", type=int, default=0, help="fused decimator: min outputs per thread in half-band stages")
     ap.add_argument("--dense", type=int, default=-1, help="fused decimator: 1 = 128-register cap, 0 = 255")
     ap.add_argument("--plans", type=int, default=-1, help="fused decimator: 0 = generic kernel only")
+    ap.add_argument("--deepk", type=int, default=0, help="fused decimator: low-rate stages every k chunks (1 or 4)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -415,6 +416,8 @@ def main():
             rx.set_option(5, args.dense)
         if args.plans >= 0:
             rx.set_option(6, args.plans)
+        if args.deepk:
+            rx.set_option(8, args.deepk)
         acap = rx.max_out(block)
         audio = torch.zeros((C_, acap), dtype=torch.float64, device=dev)
     if "panadapter" in args.workload:

@@ -224,6 +224,7 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_TIMING       1   /* value != 0: record CUDA events around the dominant (fused) kernel */
 #define QC_RX_OPT_FUSED_CHUNK  2   /* target input samples per shared-memory chunk of the fused decimator */
 #define QC_RX_OPT_FUSED_THREADS 3  /* CTA width of the fused decimator: 128 or 256 */
+#define QC_RX_OPT_FUSED_DEEPK  8   /* plan kernels: low-rate stages run once per this many chunks (1 or 4, default 1: measured slower at 4 with two CTAs per SM) */
 #define QC_RX_OPT_TRACE        7   /* debug: record clock64() stamps per chunk phase in the fused kernel */
 #define QC_RX_OPT_FUSED_PLANS  6   /* 1 (default): use plan-specialised kernels when the stage list matches one */
 #define QC_RX_OPT_FUSED_DENSE  5   /* 1: 128-register cap (more resident CTAs), 0: up to 255 registers */
@@ -261,6 +262,30 @@ int quisk_cuda_pan_multirx(qcPanadapter *p, const void *d_frames, long stream_st
 int quisk_cuda_pan_count(const qcPanadapter *p);
 /* Raw device pointer to the [n_streams][fft_size] running |X| sums (for tests). */
 const double *quisk_cuda_pan_average_ptr(const qcPanadapter *p);
+
+/* get_bandscope (quisk.c:4957-5011): real blocks of `size` samples (power of two <= 8192), Hann window,
+ * FFT, |X| average over L = size/2+1 bins; then copy2pixels (quisk.c:4932-4955), scale, 20 log10 (<= 1e-10 -> -200). */
+typedef struct qcBandscope qcBandscope;
+qcBandscope *quisk_cuda_bandscope_create(int n_streams, int size);
+void quisk_cuda_bandscope_destroy(qcBandscope *b);
+int quisk_cuda_bandscope_accumulate(qcBandscope *b, const double *d_blocks, long stream_stride, int n_blocks, void *stream);
+int quisk_cuda_bandscope_graph(qcBandscope *b, int graph_width, int clock, double zoom, double deltaf, double *d_graph, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 3c. process_agc (quisk.c:2162-2287) and cFracDecim (quisk.c:622-665), batched
+ * --------------------------------------------------------------------- */
+typedef struct qcAgc qcAgc;
+/* struct AgcState {max_out, sample_rate} + agcReleaseGain + agc_release_time (quisk.c:68-81,191-192) */
+qcAgc *quisk_cuda_agc_create(int n_channels, int sample_rate, double max_out, double release_gain, double release_time);
+void quisk_cuda_agc_destroy(qcAgc *a);
+/* in place on d_samples [n_channels][stride] quisk_cd; is_cpx as in the reference call */
+int quisk_cuda_agc_run(qcAgc *a, void *d_samples, long stride, int count, int is_cpx, void *stream);
+
+typedef struct qcFracDecim qcFracDecim;
+qcFracDecim *quisk_cuda_fracdecim_create(int n_channels);
+void quisk_cuda_fracdecim_destroy(qcFracDecim *f);
+int quisk_cuda_fracdecim_run(qcFracDecim *f, const void *d_in, long in_stride, int count, double fdecim,
+                             void *d_out, long out_stride, int *n_out, void *stream);
 
 /* Batched complex FFT (unnormalised, sign -1 forward / +1 backward), sizes 2^k,
  * 8 <= n <= 16384: the in-house Stockham kernel the panadapter and the WDSP

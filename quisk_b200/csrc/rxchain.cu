@@ -372,6 +372,9 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
         if (value && !rx->rx.d_trace) { QC_CUDA(cudaMalloc((void **)&rx->rx.d_trace, (size_t)rx->rx.C * 256 * sizeof(long long))); QC_CUDA(cudaMemset(rx->rx.d_trace, 0, (size_t)rx->rx.C * 256 * sizeof(long long))); }
         if (!value && rx->rx.d_trace) { cudaFree(rx->rx.d_trace); rx->rx.d_trace = nullptr; }
         return QC_OK;
+    case QC_RX_OPT_FUSED_DEEPK:
+        if (value != 1 && value != 4) { qc::set_error("rx_set_option: deepk must be 1 or 4"); return QC_EINVAL; }
+        rx->rx.fused_deepk = value; return QC_OK;
     case QC_RX_OPT_FUSED_PLANS: rx->rx.fused_plans = value != 0; return QC_OK;
     case QC_RX_OPT_FUSED_DENSE: rx->rx.fused_dense = value; return QC_OK;
     case QC_RX_OPT_FUSED_MIN_R:

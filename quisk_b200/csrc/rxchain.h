@@ -39,6 +39,7 @@ struct RxChain {
     int fused_chunk = 2048;             // target input samples per shared-memory chunk
     int fused_threads = 128;            // CTA width of the fused kernel (128 or 256)
     long long *d_trace = nullptr;       // debug: per-chunk clock64() stamps of the fused kernel
+    int fused_deepk = 1;                // plan kernels: run the <=128-sample stages once per this many chunks (1 = every chunk)
     int fused_plans = 1;                // use the plan-specialised instantiations when one matches
     int fused_dense = 0;                // 1: cap registers at 128/thread for more resident CTAs
     int fused_min_r = 0;                // force at least this many outputs per thread in half-band stages

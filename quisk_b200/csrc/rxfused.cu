@@ -65,6 +65,7 @@ struct FusedParams {
     int scratch;        // offset of the history-slide scratch area (cd units)
     int coef_sm;        // offset of the tap copy in shared memory (cd units)
     int ncoef;
+    int deepk;          // multi-rate plans: the deep stages run once per this many chunks
     long long *trace;   // optional [C][16 chunks][16] clock64() stamps (debug)
     double coef[MAXCOEF];
 };
@@ -235,14 +236,14 @@ __device__ __forceinline__ int stage_out_count(const FStage &s, int n_in)
 //      stage index is static, so every descriptor field is a constant-bank operand and the chunk
 //      loop is straight-line code.  A partial (ragged) chunk uses the same code with runtime counts.
 template <int NT, int CODE, int IDX, bool LAST, int FIRIDX>
-__device__ __forceinline__ void run_stage_c(cd *sm, const FusedParams &P, int n_out, cd *gdst, const FirTaps &ft)
+__device__ __forceinline__ void run_stage_c(cd *sm, const FusedParams &P, int n_out, cd *gdst, const FirTaps &ft, int sink_off)
 {
     constexpr int TYPE = CODE / 100, R = (CODE / 10) % 10, D = CODE % 10;
     const FStage &S = P.st[IDX];
     Sink sink;
     if constexpr (!LAST) {
         const FStage &N = P.st[IDX + 1];
-        sink.sm = sm + N.buf; sink.H = N.Ha; sink.org = N.org; sink.magic = N.magic; sink.g = nullptr;
+        sink.sm = sm + N.buf; sink.H = N.Ha + sink_off; sink.org = N.org; sink.magic = N.magic; sink.g = nullptr;
     } else {
         sink.sm = nullptr; sink.H = 0; sink.org = 0; sink.magic = 0; sink.g = gdst;
     }
@@ -254,18 +255,37 @@ __device__ __forceinline__ void run_stage_c(cd *sm, const FusedParams &P, int n_
     }
 }
 
-template <int NT, bool FULL, int IDX, int FIRIDX, int CODE0, int... REST>
-__device__ __forceinline__ int cascade_c(cd *sm, const FusedParams &P, int n_in, cd *gdst, long long *tr, const FirTaps &ft)
+// Runs stages [START, STOP) of the plan.  n_in is the input count of stage START; sink_off is where, behind
+// the history of stage STOP (if there is one), the outputs of stage STOP-1 go (the deep stages of a multi-rate
+// plan accumulate several chunks before they run).
+template <int NT, bool FULL, int START, int STOP, int IDX, int FIRIDX, int CODE0, int... REST>
+__device__ __forceinline__ int cascade_c(cd *sm, const FusedParams &P, int n_in, cd *gdst, long long *tr, const FirTaps &ft, int sink_off)
 {
     constexpr int D = CODE0 % 10;
     constexpr int NEXTFIR = FIRIDX + (CODE0 / 100 == 1 ? 1 : 0);
-    const FStage &S = P.st[IDX];
-    const int n_out = FULL ? S.n_out_full : (n_in > S.u0 ? (n_in - S.u0 - 1) / D + 1 : 0);
-    run_stage_c<NT, CODE0, IDX, sizeof...(REST) == 0, FIRIDX>(sm, P, n_out, gdst, ft);
-    __syncthreads();
-    if (FULL && tr) tr[3 + IDX] = clock64();
-    if constexpr (sizeof...(REST) > 0) return cascade_c<NT, FULL, IDX + 1, NEXTFIR, REST...>(sm, P, n_out, gdst, tr, ft);
-    else return n_out;
+    int n_out = n_in;
+    if constexpr (IDX >= START && IDX < STOP) {
+        const FStage &S = P.st[IDX];
+        n_out = FULL ? S.n_out_full : (n_in > S.u0 ? (n_in - S.u0 - 1) / D + 1 : 0);
+        run_stage_c<NT, CODE0, IDX, sizeof...(REST) == 0, FIRIDX>(sm, P, n_out, gdst, ft, IDX == STOP - 1 ? sink_off : 0);
+        __syncthreads();
+        if (FULL && tr) tr[3 + IDX] = clock64();
+    }
+    if constexpr (sizeof...(REST) > 0 && IDX + 1 < STOP)
+        return cascade_c<NT, FULL, START, STOP, IDX + 1, NEXTFIR, REST...>(sm, P, n_out, gdst, tr, ft, sink_off);
+    else
+        return n_out;
+}
+
+// history slide table: element idx (counted over stages [s0, s1)) -> (source, destination) in shared memory
+__device__ __forceinline__ void slide_entry(const FusedParams &P, int s0, int s1, int idx, int &src, int &dst)
+{
+    src = -1; dst = -1;
+    for (int s = s0; s < s1; s++) {
+        const FStage &S = P.st[s];
+        if (idx >= 0 && idx < S.Ha) { src = S.buf + phys(S, S.n_full + idx); dst = S.buf + phys(S, idx); }
+        idx -= S.Ha;
+    }
 }
 
 // One stage of the cascade for n_out outputs (uniform across the CTA).
@@ -294,7 +314,10 @@ __device__ __forceinline__ void run_stage(cd *sm, const FusedParams &P, int s, i
     }
 }
 
-template <int NT, int R0, int MINB, int... PLAN>
+// SPLIT: plan kernels only -- stages [SPLIT, ns) are "deep": they run once every P.deepk chunks on the
+// accumulated output of stage SPLIT-1, which amortises their fixed per-phase latency (they carry <10 % of
+// the flops but cost ~30 % of a chunk's time when run every chunk).  SPLIT == number of stages: no deep part.
+template <int NT, int R0, int MINB, int SPLIT, int... PLAN>
 __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_constant__ FusedParams P)
 {
     extern __shared__ double smem_raw[];
@@ -328,17 +351,14 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
         u = cmul_rn(make_double2(nc[3], nc[4]), nco_pow(nc, P.n_base + (unsigned long long)tid));
     }
     // slide table for full chunks: which shared-memory element this thread moves where
-    int sl_src[NSL], sl_dst[NSL];
+    constexpr int NS = (int)sizeof...(PLAN);
+    constexpr bool MULTI = NS > 0 && SPLIT < NS;
+    constexpr int NSL_D = MULTI ? 3 : 1;        // deep-stage slide slots (sum of their Ha <= 3 * NT)
+    int sl_src[NSL], sl_dst[NSL], sd_src[NSL_D], sd_dst[NSL_D];
 #pragma unroll
-    for (int e = 0; e < NSL; e++) {
-        int idx = tid + e * NT, src = -1, dst = -1;
-        for (int s = 0; s < P.ns; s++) {
-            const FStage &S = P.st[s];
-            if (idx >= 0 && idx < S.Ha) { src = S.buf + phys(S, S.n_full + idx); dst = S.buf + phys(S, idx); }
-            idx -= S.Ha;
-        }
-        sl_src[e] = src; sl_dst[e] = dst;
-    }
+    for (int e = 0; e < NSL; e++) slide_entry(P, 0, MULTI ? SPLIT : P.ns, tid + e * NT, sl_src[e], sl_dst[e]);
+#pragma unroll
+    for (int e = 0; e < NSL_D; e++) { sd_src[e] = -1; sd_dst[e] = -1; if (MULTI) slide_entry(P, SPLIT, P.ns, tid + e * NT, sd_src[e], sd_dst[e]); }
     __syncthreads();
     if (P.tune) pstep = s_pstep;
     // register-resident taps of the plan's FIR stages (lane's tap split is ts = tid & 7)
@@ -381,6 +401,7 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
         for (int k = 0; k < NLD; k++) if (FIXED || k < nld) nx[k] = gin[k * NT + tid];
     }
     int out_pos = 0;
+    int deep_acc = 0;           // multi-rate plans: samples waiting in front of the first deep stage
     for (int ch = 0; ch < n_full; ch++) {
         long long *tr = (P.trace && tid == 0 && ch < 16) ? P.trace + ((size_t)c * 16 + ch) * 16 : nullptr;
         if (tr) tr[0] = clock64();
@@ -413,8 +434,22 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
         }
         if (tr) tr[2] = clock64();
         // ---- the cascade
-        if constexpr (sizeof...(PLAN) > 0) {
-            out_pos += cascade_c<NT, true, 0, 0, PLAN...>(sm, P, P.T0, gout + out_pos, tr, ft);
+        if constexpr (MULTI) {
+            const int per = P.st[SPLIT - 1].n_out_full;
+            cascade_c<NT, true, 0, SPLIT, 0, 0, PLAN...>(sm, P, P.T0, nullptr, tr, ft, deep_acc);
+            deep_acc += per;
+            if (deep_acc == per * P.deepk) {
+                out_pos += cascade_c<NT, true, SPLIT, NS, 0, 0, PLAN...>(sm, P, deep_acc, gout + out_pos, tr, ft, 0);
+                cd kd[NSL_D];
+#pragma unroll
+                for (int e = 0; e < NSL_D; e++) if (sd_src[e] >= 0) kd[e] = sm[sd_src[e]];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < NSL_D; e++) if (sd_src[e] >= 0) sm[sd_dst[e]] = kd[e];
+                deep_acc = 0;
+            }
+        } else if constexpr (NS > 0) {
+            out_pos += cascade_c<NT, true, 0, NS, 0, 0, PLAN...>(sm, P, P.T0, gout + out_pos, tr, ft, 0);
         } else {
             for (int s = 0; s < P.ns; s++) {
                 run_stage<NT>(sm, P, s, P.st[s].n_out_full, gout + out_pos);
@@ -447,8 +482,10 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
             sm[S0.buf + phys(S0, S0.Ha + i)] = x;
         }
         __syncthreads();
-        if constexpr (sizeof...(PLAN) > 0) {
-            cascade_c<NT, false, 0, 0, PLAN...>(sm, P, rem, gout + out_pos, nullptr, ft);
+        if constexpr (MULTI) {
+            deep_acc += cascade_c<NT, false, 0, SPLIT, 0, 0, PLAN...>(sm, P, rem, nullptr, nullptr, ft, deep_acc);
+        } else if constexpr (NS > 0) {
+            cascade_c<NT, false, 0, NS, 0, 0, PLAN...>(sm, P, rem, gout + out_pos, nullptr, ft, 0);
         } else {
             int n_in = rem;
             for (int s = 0; s < P.ns; s++) {
@@ -460,9 +497,14 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
         }
         n_s = rem;
     }
+    // multi-rate plans: whatever is still waiting in front of the deep stages goes through them now
+    if constexpr (MULTI) {
+        if (deep_acc > 0) cascade_c<NT, false, SPLIT, NS, 0, 0, PLAN...>(sm, P, deep_acc, gout + out_pos, nullptr, ft, 0);
+    }
     // ---- hand the histories back: the last Hs inputs of every stage
     for (int s = 0; s < P.ns; s++) {
         const FStage &S = P.st[s];
+        if (MULTI && s == SPLIT) n_s = deep_acc;
         cd *h = S.hout + (size_t)c * S.Hs;
         for (int i = tid; i < S.Hs; i += NT) h[i] = sm[S.buf + phys(S, n_s + (S.Ha - S.Hs) + i)];
         n_s = stage_out_count(S, n_s);
@@ -523,11 +565,27 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     P.in = in; P.in_stride = in_stride; P.n_in = count; P.out = out; P.out_stride = out_stride;
     P.nco = d_nco; P.n_base = n_base; P.tune = tune ? 1 : 0;
     P.trace = d_trace;
-    int off = 0, coff = 0, chunk_in = T0, n = count;
+    // multi-rate split: the first stage that sees <= 128 samples per chunk, and everything after it, runs
+    // once every `deepk` chunks (plan kernels only)
+    int split = ns, deepk = 1;
+    if (fused_plans && fused_deepk > 1 && NT == 128 && T0 == 2048) {
+        int ci = T0;
+        for (int s = 0; s < ns; s++) {
+            if (ci <= 128 && s > 0) { split = s; deepk = fused_deepk; break; }
+            ci /= (cst[s]->kind == QC_C_DECIM2_HB45 ? 2 : cst[s]->decim);
+        }
+    }
+    int codes[MAXST];
+    size_t sh = 0;
+    // stage descriptors for a given multi-rate split (no filter state is touched here)
+    auto build = [&](int split, int deepk) -> int {
+    P.deepk = deepk;
+    int off = 0, coff = 0, chunk_in = T0;
     for (int s = 0; s < ns; s++) {
         BatchFilter *f = cst[s];
         FStage &S = P.st[s];
         memset(&S, 0, sizeof(S));
+        if (s == split) chunk_in *= deepk;          // deep stages see deepk chunks' worth per run
         S.Hs = f->H;
         S.hin = (const cd *)f->d_hist[f->cur];
         S.hout = (cd *)f->d_hist[f->cur ^ 1];
@@ -567,26 +625,52 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         off += S.buf_len;
         S.n_full = chunk_in;
         S.n_out_full = chunk_in / S.D;
-        // host-side phase bookkeeping, same formulas as BatchFilter::run
+        chunk_in = chunk_in / S.D;
+        codes[s] = S.type * 100 + (S.type ? S.Rplan : S.R) * 10 + S.D;
+    }
+    P.scratch = off;
+    {
+        int tot = 0, deep = 0;
+        for (int s = 0; s < ns; s++) { if (s < split) tot += P.st[s].Ha; else deep += P.st[s].Ha; }
+        if (tot > 512 || deep > 384) { set_error("fused decimator: %d/%d history elements exceed the slide capacity", tot, deep); return QC_EINVAL; }
+    }
+    P.coef_sm = off; P.ncoef = coff;
+    off += (coff + 1) / 2 + 1;
+    P.smem_cd = off;
+    sh = (size_t)off * sizeof(cd);
+    if (sh > 226 * 1024) { set_error("fused decimator: %zu bytes of shared memory needed", sh); return QC_EINVAL; }
+    return QC_OK;
+    };
+    // the multi-rate plans that have a compiled instantiation
+    auto multi_plan_exists = [&]() {
+        static const int plans[4][MAXST] = {{82, 42, 22, 22, 142}, {82, 42, 22, 22, 142, 22, 142},
+                                            {82, 42, 22, 22, 142, 22, 22, 122}, {82, 42, 22, 22, 142, 142}};
+        static const int lens[4] = {5, 7, 8, 6};
+        for (int p = 0; p < 4; p++) {
+            if (lens[p] != ns) continue;
+            bool ok = true;
+            for (int i = 0; i < ns; i++) ok = ok && codes[i] == plans[p][i];
+            if (ok) return true;
+        }
+        return false;
+    };
+    int rcb;
+    if (split != ns) {
+        rcb = build(split, deepk);
+        if (rcb != QC_OK || split != 4 || !multi_plan_exists()) { split = ns; deepk = 1; }
+    }
+    if (split == ns) { rcb = build(ns, 1); if (rcb != QC_OK) return rcb; }
+    // host-side phase bookkeeping, same formulas as BatchFilter::run
+    int n = count;
+    for (int s = 0; s < ns; s++) {
+        BatchFilter *f = cst[s];
         const int no = f->count_out(n, 0);
         if (f->kind == QC_C_DECIM2_HB45) f->phase = (f->phase + n) & 1;
         else f->phase = (f->phase + n) % f->decim;
         f->cur ^= 1;
         n = no;
-        chunk_in = chunk_in / S.D;
     }
-    P.scratch = off;
-    {
-        int tot = 0;
-        for (int s = 0; s < ns; s++) tot += P.st[s].Ha;
-        if (tot > 512) { set_error("fused decimator: %d history elements exceed the slide capacity", tot); return QC_EINVAL; }
-    }
-    P.coef_sm = off; P.ncoef = coff;
-    off += (coff + 1) / 2 + 1;
-    P.smem_cd = off;
     *n_out = n;
-    const size_t sh = (size_t)off * sizeof(cd);
-    if (sh > 226 * 1024) { set_error("fused decimator: %zu bytes of shared memory needed", sh); return QC_EINVAL; }
     const int R0 = P.st[0].type == 0 ? P.st[0].R : 2;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timing) {
@@ -594,11 +678,10 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         QC_CUDA(cudaEventRecord(e0, strm));
     }
     // plan code per stage: type*100 + R*10 + D
-    int codes[MAXST]; bool plan_ok = NT == 128 && fused_plans && T0 == 2048;
-    for (int s = 0; s < ns; s++) codes[s] = P.st[s].type * 100 + (P.st[s].type ? P.st[s].Rplan : P.st[s].R) * 10 + P.st[s].D;
+    bool plan_ok = fused_plans && T0 == 2048;
     for (int s = 0; s < ns; s++) if (P.st[s].type == 1 && P.st[s].Kpad != 8 * FIR_KB) plan_ok = false;
-    auto is_plan = [&](std::initializer_list<int> pl) {
-        if (!plan_ok || (int)pl.size() != ns) return false;
+    auto is_plan = [&](int sp, std::initializer_list<int> pl, int nt = 128) {
+        if (!plan_ok || (int)pl.size() != ns || sp != split || nt != NT) return false;
         int i = 0;
         for (int c : pl) if (codes[i++] != c) return false;
         return true;
@@ -607,18 +690,27 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         static bool optin = false; \
         if (!optin) { QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin = true; } \
         fused_decim_kernel<__VA_ARGS__><<<C, NT, sh, strm>>>(P); } while (0)
-    if (is_plan({82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142);                       // 1.536 MS/s -> 48 k
-    else if (is_plan({82, 42, 22, 22, 142, 22, 112})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142, 22, 112);  // ... -> 12 k (SSB)
-    else if (is_plan({82, 42, 22, 22, 142, 22, 22, 112})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142, 22, 22, 112);  // ... -> 6 k (CW)
-    else if (is_plan({82, 42, 22, 22, 142, 122})) QC_LAUNCH(128, 8, 2, 82, 42, 22, 22, 142, 122);          // ... -> 24 k (AM)
+    // single-rate plans (every stage every chunk)
+    if (is_plan(5, {82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 5, 82, 42, 22, 22, 142);                        // 1.536 MS/s -> 48 k
+    else if (is_plan(7, {82, 42, 22, 22, 142, 22, 112})) QC_LAUNCH(128, 8, 2, 7, 82, 42, 22, 22, 142, 22, 112);   // ... -> 12 k (SSB)
+    else if (is_plan(8, {82, 42, 22, 22, 142, 22, 22, 112})) QC_LAUNCH(128, 8, 2, 8, 82, 42, 22, 22, 142, 22, 22, 112);   // ... -> 6 k (CW)
+    else if (is_plan(6, {82, 42, 22, 22, 142, 122})) QC_LAUNCH(128, 8, 2, 6, 82, 42, 22, 22, 142, 122);           // ... -> 24 k (AM)
+    // 256-thread CTAs, two per SM under a 128-register cap (16 warps per SM)
+    else if (is_plan(7, {42, 22, 22, 22, 122, 22, 112}, 256)) QC_LAUNCH(256, 4, 2, 7, 42, 22, 22, 22, 122, 22, 112);
+    else if (is_plan(5, {42, 22, 22, 22, 122}, 256)) QC_LAUNCH(256, 4, 2, 5, 42, 22, 22, 22, 122);
+    // multi-rate plans: stages from index 4 on run once per 4 chunks
+    else if (is_plan(4, {82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 4, 82, 42, 22, 22, 142);
+    else if (is_plan(4, {82, 42, 22, 22, 142, 22, 142})) QC_LAUNCH(128, 8, 2, 4, 82, 42, 22, 22, 142, 22, 142);
+    else if (is_plan(4, {82, 42, 22, 22, 142, 22, 22, 122})) QC_LAUNCH(128, 8, 2, 4, 82, 42, 22, 22, 142, 22, 22, 122);
+    else if (is_plan(4, {82, 42, 22, 22, 142, 142})) QC_LAUNCH(128, 8, 2, 4, 82, 42, 22, 22, 142, 142);
     else if (NT == 256) {
-        if (R0 == 4) { if (fused_dense) QC_LAUNCH(256, 4, 2); else QC_LAUNCH(256, 4, 1); }
-        else if (R0 == 2) { if (fused_dense) QC_LAUNCH(256, 2, 2); else QC_LAUNCH(256, 2, 1); }
+        if (R0 == 4) { if (fused_dense) QC_LAUNCH(256, 4, 2, 0); else QC_LAUNCH(256, 4, 1, 0); }
+        else if (R0 == 2) { if (fused_dense) QC_LAUNCH(256, 2, 2, 0); else QC_LAUNCH(256, 2, 1, 0); }
         else { set_error("fused decimator: unsupported stage-0 blocking %d at 256 threads", R0); return QC_EINVAL; }
     } else {
-        if (R0 == 8) { if (fused_dense) QC_LAUNCH(128, 8, 4); else QC_LAUNCH(128, 8, 2); }
-        else if (R0 == 4) { if (fused_dense) QC_LAUNCH(128, 4, 4); else QC_LAUNCH(128, 4, 2); }
-        else { if (fused_dense) QC_LAUNCH(128, 2, 4); else QC_LAUNCH(128, 2, 2); }
+        if (R0 == 8) { if (fused_dense) QC_LAUNCH(128, 8, 4, 0); else QC_LAUNCH(128, 8, 2, 0); }
+        else if (R0 == 4) { if (fused_dense) QC_LAUNCH(128, 4, 4, 0); else QC_LAUNCH(128, 4, 2, 0); }
+        else { if (fused_dense) QC_LAUNCH(128, 2, 4, 0); else QC_LAUNCH(128, 2, 2, 0); }
     }
 #undef QC_LAUNCH
     count_launch();

@@ -1,0 +1,314 @@
+// quisk_b200/csrc/rxmisc_nofma.cu -- the remaining small pieces of the Quisk receive path:
+//   process_agc  (quisk.c:2162-2287)  Quisk's own look-ahead AGC at playback rate (15 ms FIFO)
+//   cFracDecim   (quisk.c:622-665)    fractional decimation by 4-point Lagrange interpolation
+//   get_bandscope (quisk.c:4957-5011) + copy2pixels (quisk.c:4932-4955): real-input spectrum display
+// process_agc and cFracDecim are scalar recurrences: one CTA per channel, block staged in shared
+// memory, lane 0 walks it (compiled with --fmad=false so the state follows the reference bit for bit).
+#include "fft_device.cuh"
+#include <cmath>
+
+namespace qc {
+
+static const double kCLIP32 = 2147483647.0;
+
+// state: 0 index_read 1 index_start 2 is_clipping 3 themax 4 gain 5 delta 6 target_gain
+struct AgcPar { int buf_size, is_cpx; double max_out, time_release, release_gain; };
+
+__global__ void agc_kernel(cd *samples, long stride, int n, int C, double *state, cd *fifo, AgcPar p)
+{
+    extern __shared__ double sm_raw[];
+    cd *sx = reinterpret_cast<cd *>(sm_raw);            // [n] block
+    cd *sf = sx + n;                                    // [buf_size] FIFO
+    const int c = blockIdx.x;
+    cd *g = samples + (size_t)c * stride;
+    cd *gf = fifo + (size_t)c * p.buf_size;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = g[i];
+    for (int i = threadIdx.x; i < p.buf_size; i += blockDim.x) sf[i] = gf[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *st = state + (size_t)c * 8;
+        int index_read = (int)st[0], index_start = (int)st[1], is_clipping = (int)st[2];
+        double themax = st[3], gain = st[4], delta = st[5], target_gain = st[6];
+        for (int i = 0; i < n; i++) {
+            const cd csample = sx[i];
+            cd o = make_double2(sf[index_read].x * gain, sf[index_read].y * gain);      // FIFO output
+            const double out_magn = p.is_cpx ? hypot(o.x, o.y) : fabs(o.x);
+            if (out_magn > kCLIP32) { o.x /= out_magn; o.y /= out_magn; }               // quisk.c:2203-2204
+            sx[i] = o;
+            sf[index_read] = csample;
+            const double buf_magn = p.is_cpx ? hypot(csample.x, csample.y) : fabs(csample.x);
+            if (is_clipping == 0) {
+                if (buf_magn * gain > p.max_out * kCLIP32) {
+                    target_gain = p.max_out * kCLIP32 / buf_magn;
+                    delta = (gain - target_gain) / p.buf_size;
+                    is_clipping = 1;
+                    themax = buf_magn;
+                    gain -= delta;
+                } else if (index_read == index_start) {
+                    const double clip_gain = p.max_out * kCLIP32 / themax;
+                    target_gain = p.release_gain > clip_gain ? clip_gain : p.release_gain;
+                    themax = buf_magn;
+                    gain = gain * (1.0 - p.time_release) + target_gain * p.time_release;
+                } else {
+                    if (themax < buf_magn) themax = buf_magn;
+                    gain = gain * (1.0 - p.time_release) + target_gain * p.time_release;
+                }
+            } else {
+                if (buf_magn > themax) {
+                    themax = buf_magn;
+                    target_gain = p.max_out * kCLIP32 / buf_magn;
+                    const double dtmp = (gain - target_gain) / p.buf_size;
+                    if (dtmp > delta) delta = dtmp;
+                }
+                gain -= delta;
+                if (gain <= target_gain) {
+                    is_clipping = 0;
+                    gain = target_gain;
+                    themax = buf_magn;
+                    index_start = index_read;
+                }
+            }
+            if (++index_read >= p.buf_size) index_read = 0;
+        }
+        st[0] = index_read; st[1] = index_start; st[2] = is_clipping; st[3] = themax; st[4] = gain; st[5] = delta; st[6] = target_gain;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = sx[i];
+    for (int i = threadIdx.x; i < p.buf_size; i += blockDim.x) gf[i] = sf[i];
+}
+
+// cFracDecim: state 0 dindex, 1..6 c0 c1 c2 (complex).  The index walk does not depend on the data, so the host
+// knows every output count; the device just follows the same walk.
+__global__ void fracdecim_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, double fdecim)
+{
+    extern __shared__ double sm_raw[];
+    cd *sx = reinterpret_cast<cd *>(sm_raw);
+    const int c = blockIdx.x;
+    const cd *g = in + (size_t)c * is;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = g[i];
+    __syncthreads();
+    __shared__ int s_nout;
+    if (threadIdx.x == 0) {
+        double *st = state + (size_t)c * 8;
+        double dindex = st[0];
+        cd c0 = make_double2(st[1], st[2]), c1 = make_double2(st[3], st[4]), c2 = make_double2(st[5], st[6]);
+        int nout = 0;
+        for (int i = 0; i < n; i++) {
+            const cd c3 = sx[i];
+            if (dindex < 2) {
+                const double xm0 = dindex - 0, xm1 = dindex - 1, xm2 = dindex - 2, xm3 = dindex - 3;
+                // (xm1*xm2*xm3*c0 / -6 + xm0*xm2*xm3*c1 / 2 + xm0*xm1*xm3*c2 / -2 + xm0*xm1*xm2*c3 / 6), quisk.c:645-647
+                const double w0 = xm1 * xm2 * xm3, w1 = xm0 * xm2 * xm3, w2 = xm0 * xm1 * xm3, w3 = xm0 * xm1 * xm2;
+                cd o;
+                o.x = ((w0 * c0.x / -6.0 + w1 * c1.x / 2.0) + w2 * c2.x / -2.0) + w3 * c3.x / 6.0;
+                o.y = ((w0 * c0.y / -6.0 + w1 * c1.y / 2.0) + w2 * c2.y / -2.0) + w3 * c3.y / 6.0;
+                sx[nout++] = o;                         // nout <= i: in place like the reference
+                dindex += fdecim - 1;
+            } else {
+                dindex -= 1;
+            }
+            c0 = c1; c1 = c2; c2 = c3;
+        }
+        st[0] = dindex; st[1] = c0.x; st[2] = c0.y; st[3] = c1.x; st[4] = c1.y; st[5] = c2.x; st[6] = c2.y;
+        s_nout = nout;
+    }
+    __syncthreads();
+    cd *y = out + (size_t)c * os;
+    for (int i = threadIdx.x; i < s_nout; i += blockDim.x) y[i] = sx[i];
+}
+
+// bandscope: real block * Hann -> FFT (complex transform of the real block) -> |X[0..N/2]| accumulate
+__global__ void __launch_bounds__(1024) bandscope_accumulate_kernel(const double *blocks, long stream_stride, int n_blocks, int n,
+                                                                    const cd *tw, const double *window, double *avg, double *the_max)
+{
+    extern __shared__ double sm_raw[];
+    cd *s = reinterpret_cast<cd *>(sm_raw);
+    const int stream = blockIdx.x, lane = threadIdx.x, lanes = blockDim.x;
+    const int L = n / 2 + 1;
+    double *a = avg + (size_t)stream * (L + 1);
+    double mx = 0.0;
+    for (int b = 0; b < n_blocks; b++) {
+        const double *src = blocks + (size_t)stream * stream_stride + (size_t)b * n;
+        for (int i = lane; i < n; i += lanes) {
+            const double v = src[i];
+            mx = fmax(mx, fabs(v));
+            s[i] = make_double2(v * window[i], 0.0);
+        }
+        __syncthreads();
+        fft_smem(s, n, tw, -1, lane, lanes);
+        for (int i = lane; i < L; i += lanes) a[i] += hypot(s[i].x, s[i].y);        // quisk.c:4981
+        __syncthreads();
+    }
+    // the_max (hermes_adc_level, quisk.c:4972-4974): block-wide maximum of |sample|
+    __shared__ double s_mx[32];
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((lane & 31) == 0) s_mx[lane >> 5] = mx;
+    __syncthreads();
+    if (lane == 0) {
+        double m = the_max[stream];
+        for (int w = 0; w < (lanes + 31) / 32; w++) m = fmax(m, s_mx[w]);
+        the_max[stream] = m;
+    }
+}
+
+// copy2pixels (quisk.c:4932-4955) + scale + 20 log10 (quisk.c:4991-4999); one thread per pixel
+__global__ void bandscope_graph_kernel(const double *avg, int L, int graph_width, double zoom, double deltaf, double rate,
+                                       double scale, double *graph)
+{
+    const int stream = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= graph_width) return;
+    const double *fft = avg + (size_t)stream * (L + 1);
+    const int fft_size = L;
+    const double f1 = deltaf + rate / 2.0 * (1.0 - zoom);
+    const double d1 = fft_size / rate * (f1 + (double)i / graph_width * zoom * rate);
+    const double d2 = fft_size / rate * (f1 + (double)(i + 1) / graph_width * zoom * rate);
+    const int j1 = (int)floor(d1), j2 = (int)floor(d2);
+    double sample;
+    if (j1 == j2) sample = (d2 - d1) * fft[j1];
+    else {
+        sample = (j1 + 1 - d1) * fft[j1];
+        for (int j = j1 + 1; j < j2; j++) sample += fft[j];
+        sample += (d2 - j2) * fft[j2];
+    }
+    sample = sample * scale;
+    graph[(size_t)stream * graph_width + i] = sample <= 1E-10 ? -200.0 : 20.0 * log10(sample);
+}
+
+struct QAgc { int C, rate, buf_size; AgcPar p; double *d_state; cd *d_fifo; };
+struct QFrac { int C; double dindex; double *d_state; };
+struct QBand { int S, n, L, count; const cd *tw; double *d_window, *d_avg, *d_max; };
+
+}  // namespace qc
+
+using namespace qc;
+struct qcAgc { QAgc a; };
+struct qcFracDecim { QFrac f; };
+struct qcBandscope { QBand b; };
+
+extern "C" {
+
+qcAgc *quisk_cuda_agc_create(int n_channels, int sample_rate, double max_out, double release_gain, double release_time)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    qcAgc *h = new qcAgc();
+    QAgc &a = h->a;
+    a.C = n_channels; a.rate = sample_rate;
+    a.buf_size = sample_rate * 15 / 1000;                       // AGC_DELAY, quisk.c:47,2177
+    a.p.buf_size = a.buf_size; a.p.is_cpx = 1; a.p.max_out = max_out; a.p.release_gain = release_gain;
+    a.p.time_release = 1.0 - exp(-1.0 / sample_rate / release_time);    // quisk.c:2186
+    if (n_channels <= 0 || a.buf_size <= 0 ||
+        cudaMalloc((void **)&a.d_state, (size_t)n_channels * 8 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&a.d_fifo, (size_t)n_channels * a.buf_size * sizeof(cd)) != cudaSuccess) {
+        set_error("agc_create: bad arguments or allocation failure"); delete h; return nullptr;
+    }
+    std::vector<double> st((size_t)n_channels * 8, 0.0);
+    for (int c = 0; c < n_channels; c++) { st[c * 8 + 3] = 1.0; st[c * 8 + 4] = 100.0; st[c * 8 + 6] = 100.0; }     // themax, gain, target_gain
+    cudaMemcpy(a.d_state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(a.d_fifo, 0, (size_t)n_channels * a.buf_size * sizeof(cd));
+    return h;
+}
+
+void quisk_cuda_agc_destroy(qcAgc *h) { if (h) { cudaFree(h->a.d_state); cudaFree(h->a.d_fifo); delete h; } }
+
+int quisk_cuda_agc_run(qcAgc *h, void *d_samples, long stride, int count, int is_cpx, void *stream)
+{
+    if (!h) return QC_EINVAL;
+    if (count <= 0) return QC_OK;
+    QAgc &a = h->a;
+    AgcPar p = a.p; p.is_cpx = is_cpx;
+    const size_t sh = (size_t)(count + a.buf_size) * sizeof(cd);
+    if (sh > 200 * 1024) { set_error("agc_run: block too large"); return QC_EINVAL; }
+    if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(agc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    agc_kernel<<<a.C, 64, sh, (cudaStream_t)stream>>>((cd *)d_samples, stride, count, a.C, a.d_state, a.d_fifo, p);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+qcFracDecim *quisk_cuda_fracdecim_create(int n_channels)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    qcFracDecim *h = new qcFracDecim();
+    h->f.C = n_channels; h->f.dindex = 1.0;                     // static double dindex = 1, quisk.c:627
+    if (n_channels <= 0 || cudaMalloc((void **)&h->f.d_state, (size_t)n_channels * 8 * sizeof(double)) != cudaSuccess) { delete h; return nullptr; }
+    std::vector<double> st((size_t)n_channels * 8, 0.0);
+    for (int c = 0; c < n_channels; c++) st[c * 8] = 1.0;
+    cudaMemcpy(h->f.d_state, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice);
+    return h;
+}
+
+void quisk_cuda_fracdecim_destroy(qcFracDecim *h) { if (h) { cudaFree(h->f.d_state); delete h; } }
+
+int quisk_cuda_fracdecim_run(qcFracDecim *h, const void *d_in, long in_stride, int count, double fdecim,
+                             void *d_out, long out_stride, int *n_out, void *stream)
+{
+    if (!h) return QC_EINVAL;
+    // the host walks the same index recurrence (same doubles, same order) to know the count
+    double dindex = h->f.dindex; int nout = 0;
+    for (int i = 0; i < count; i++) { if (dindex < 2) { nout++; dindex += fdecim - 1; } else dindex -= 1; }
+    h->f.dindex = dindex;
+    if (n_out) *n_out = nout;
+    if (count <= 0) return QC_OK;
+    const size_t sh = (size_t)count * sizeof(cd);
+    if (sh > 200 * 1024) { set_error("fracdecim_run: block too large"); return QC_EINVAL; }
+    if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(fracdecim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    fracdecim_kernel<<<h->f.C, 64, sh, (cudaStream_t)stream>>>((const cd *)d_in, in_stride, (cd *)d_out, out_stride, count, h->f.C, h->f.d_state, fdecim);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+qcBandscope *quisk_cuda_bandscope_create(int n_streams, int size)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    if (n_streams <= 0 || fft_log2(size) < 0) { set_error("bandscope_create: size must be a power of two in [8, 8192]"); return nullptr; }
+    qcBandscope *h = new qcBandscope();
+    QBand &b = h->b;
+    b.S = n_streams; b.n = size; b.L = size / 2 + 1; b.count = 0; b.tw = fft_twiddles(size);
+    std::vector<double> w((size_t)size);
+    for (int i = 0, j = -size / 2; i < size; i++, j++) w[i] = 0.5 + 0.5 * cos(2. * M_PI * j / size);       // quisk.c:2887-2888
+    if (!b.tw || cudaMalloc((void **)&b.d_window, (size_t)size * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&b.d_avg, (size_t)n_streams * (b.L + 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&b.d_max, (size_t)n_streams * sizeof(double)) != cudaSuccess) { delete h; return nullptr; }
+    cudaMemcpy(b.d_window, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(b.d_avg, 0, (size_t)n_streams * (b.L + 1) * sizeof(double));
+    cudaMemset(b.d_max, 0, (size_t)n_streams * sizeof(double));
+    return h;
+}
+
+void quisk_cuda_bandscope_destroy(qcBandscope *h) { if (h) { cudaFree(h->b.d_window); cudaFree(h->b.d_avg); cudaFree(h->b.d_max); delete h; } }
+
+int quisk_cuda_bandscope_accumulate(qcBandscope *h, const double *d_blocks, long stream_stride, int n_blocks, void *stream)
+{
+    if (!h) return QC_EINVAL;
+    if (n_blocks <= 0) return QC_OK;
+    QBand &b = h->b;
+    const size_t sh = (size_t)b.n * sizeof(cd);
+    if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(bandscope_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    bandscope_accumulate_kernel<<<b.S, fft_threads(b.n), sh, (cudaStream_t)stream>>>(d_blocks, stream_stride, n_blocks, b.n, b.tw, b.d_window, b.d_avg, b.d_max);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    b.count += n_blocks;
+    return QC_OK;
+}
+
+int quisk_cuda_bandscope_graph(qcBandscope *h, int graph_width, int clock, double zoom, double deltaf, double *d_graph, void *stream)
+{
+    if (!h) return QC_EINVAL;
+    QBand &b = h->b;
+    if (b.count <= 0 || graph_width <= 0) { set_error("bandscope_graph: nothing accumulated"); return QC_EINVAL; }
+    const double frac = (double)b.L / graph_width;
+    const double scale = 1.0 / frac / b.count / b.n;             // quisk.c:4989
+    const double rate = clock / 2.0;
+    cudaStream_t s = (cudaStream_t)stream;
+    bandscope_graph_kernel<<<dim3((graph_width + 127) / 128, b.S), 128, 0, s>>>(b.d_avg, b.L, graph_width, zoom, deltaf, rate, scale, d_graph);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    QC_CUDA(cudaMemsetAsync(b.d_avg, 0, (size_t)b.S * (b.L + 1) * sizeof(double), s));
+    QC_CUDA(cudaMemsetAsync(b.d_max, 0, (size_t)b.S * sizeof(double), s));
+    b.count = 0;
+    return QC_OK;
+}
+
+}  // extern "C"

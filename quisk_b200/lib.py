@@ -87,6 +87,16 @@ def load() -> C.CDLL:
     lib.quisk_cuda_pan_average_ptr.argtypes = [vp]
     lib.quisk_cuda_pan_average_ptr.restype = vp
     lib.quisk_cuda_fft_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    lib.quisk_cuda_bandscope_create.argtypes = [C.c_int, C.c_int]; lib.quisk_cuda_bandscope_create.restype = vp
+    lib.quisk_cuda_bandscope_destroy.argtypes = [vp]; lib.quisk_cuda_bandscope_destroy.restype = None
+    lib.quisk_cuda_bandscope_accumulate.argtypes = [vp, vp, C.c_long, C.c_int, vp]
+    lib.quisk_cuda_bandscope_graph.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp]
+    lib.quisk_cuda_agc_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]; lib.quisk_cuda_agc_create.restype = vp
+    lib.quisk_cuda_agc_destroy.argtypes = [vp]; lib.quisk_cuda_agc_destroy.restype = None
+    lib.quisk_cuda_agc_run.argtypes = [vp, vp, C.c_long, C.c_int, C.c_int, vp]
+    lib.quisk_cuda_fracdecim_create.argtypes = [C.c_int]; lib.quisk_cuda_fracdecim_create.restype = vp
+    lib.quisk_cuda_fracdecim_destroy.argtypes = [vp]; lib.quisk_cuda_fracdecim_destroy.restype = None
+    lib.quisk_cuda_fracdecim_run.argtypes = [vp, vp, C.c_long, C.c_int, C.c_double, vp, C.c_long, c_int_p, vp]
     # ---- WDSP RXA part (include/quisk_cuda_wdsp.h) ----
     D = C.c_double
     lib.quisk_cuda_fir_bandpass.argtypes = [C.c_int, D, D, D, C.c_int, C.c_int, D, vp]

@@ -1,0 +1,61 @@
+"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287) and cFracDecim (quisk.c:622-665)
+from the compiled reference (oracle/_ref/libquisk_rx_ref.so).  Writes tests/golden/misc_kat.npz."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import quisk_oracle as O          # noqa: E402
+from oracle import ref_ctypes as R            # noqa: E402
+
+AGC_SPLITS = [480, 1, 479, 960, 333, 627]
+
+
+def agc_input(n, seed):
+    """Audio-like signal around 2^24 with bursts that force clipping (gain starts at 100, max_out 0.7 * 2^31)."""
+    x = O.synth_iq(n, seed, 1.0) / 64.0
+    x[n // 4:n // 4 + 300] *= 40.0
+    x[n // 2:n // 2 + 50] *= 200.0
+    return x
+
+
+def main():
+    out = {}
+    for is_cpx in (1, 0):
+        lib = R.load("libquisk_rx_ref.so", private_copy=True)
+        lib.ref_agc_new.restype = C.c_void_p
+        lib.ref_agc_new.argtypes = [C.c_double, C.c_int]
+        lib.ref_agc_set.argtypes = [C.c_double, C.c_double]
+        lib.ref_agc_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.ref_agc_set(80.0, 1.0)
+        st = lib.ref_agc_new(0.7, 48000)
+        x = agc_input(sum(AGC_SPLITS), 60)
+        if not is_cpx:
+            x = x.real.astype(np.complex128)
+        ys, pos = [], 0
+        for n in AGC_SPLITS:
+            blk = np.ascontiguousarray(x[pos:pos + n]); pos += n
+            lib.ref_agc_run(st, blk.ctypes.data, n, is_cpx)
+            ys.append(blk)
+        out["agc_cpx%d/y" % is_cpx] = np.concatenate(ys)
+    for fdecim in (1.25, 1.0416666666666667, 1.5):
+        lib = R.load("libquisk_rx_ref.so", private_copy=True)
+        lib.ref_cFracDecim.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        x = O.synth_iq(6000, 61, 1.0)
+        ys, counts, pos = [], [], 0
+        for n in [1000, 1, 2, 997, 4000]:
+            blk = np.ascontiguousarray(x[pos:pos + n]); pos += n
+            k = lib.ref_cFracDecim(blk.ctypes.data, n, fdecim)
+            ys.append(blk[:k].copy()); counts.append(k)
+        out["fracdecim_%g/y" % fdecim] = np.concatenate(ys)
+        out["fracdecim_%g/counts" % fdecim] = np.array(counts)
+    np.savez_compressed(os.path.join(HERE, "misc_kat.npz"), **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
