@@ -48,22 +48,24 @@ const cd *fft_twiddles(int n)
 // ---------------------------------------------------------------------------------------
 // plain batched transform
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) fft_batch_kernel(const cd *in, cd *out, int n, int batch, const cd *tw, int sign)
+__global__ void __launch_bounds__(256) fft_batch_kernel(const cd *in, cd *out, int n, int batch, const cd *tw, int sign)
 {
     extern __shared__ double smem_raw[];
-    cd *s = reinterpret_cast<cd *>(smem_raw) + (size_t)threadIdx.y * n;
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *s = twl + fft_tw_entries(n) + (size_t)threadIdx.y * n;
+    fft_stage_twiddles(twl, tw, n);
     const int f = blockIdx.x * blockDim.y + threadIdx.y;
     const bool live = f < batch;
     const int lane = threadIdx.x, lanes = blockDim.x;
     if (live) {
         const cd *src = in + (size_t)f * n;
-        for (int i = lane; i < n; i += lanes) s[i] = src[i];
+        for (int i = lane; i < n; i += lanes) s[fsw(i)] = src[i];
     }
     __syncthreads();
-    fft_smem(s, n, tw, sign, lane, lanes);
+    fft_smem(s, n, twl, sign, lane, lanes);
     if (live) {
         cd *dst = out + (size_t)f * n;
-        for (int i = lane; i < n; i += lanes) dst[i] = s[i];
+        for (int i = lane; i < n; i += lanes) dst[i] = s[fsw(i)];
     }
 }
 
@@ -76,48 +78,38 @@ __global__ void __launch_bounds__(1024) fft_batch_kernel(const cd *in, cd *out, 
 // quisk.c:5271-5276) starting from the value already in `avg`.  With groups > 1 each group
 // writes a partial sum and pan_reduce_kernel folds them in.
 // ---------------------------------------------------------------------------------------
-static constexpr int PAN_MAX_OWN = 8;      // bins per thread: n / fft_threads(n) = 8
+static constexpr int PAN_MAX_OWN = 16;     // bins per thread: n / fft_threads(n) = 16
 
-__global__ void __launch_bounds__(1024) pan_accumulate_kernel(const cd *frames, long stream_stride, int n_frames, int n,
+__global__ void __launch_bounds__(256) pan_accumulate_kernel(const cd *frames, long stream_stride, int n_frames, int n,
                                       const cd *tw, const double *window, double *avg, double *partial, int groups)
 {
     extern __shared__ double smem_raw[];
-    cd *s = reinterpret_cast<cd *>(smem_raw);
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *s = twl + fft_tw_entries(n);
+    double *sacc = reinterpret_cast<double *>(s + n);        // running per-bin sums of this CTA
+    fft_stage_twiddles(twl, tw, n);
     const int stream = blockIdx.y, g = blockIdx.x;
     const int lane = threadIdx.x, lanes = blockDim.x;
     const int half = n >> 1;
-    double acc[PAN_MAX_OWN];
     double *dst = groups == 1 ? avg + (size_t)stream * n : partial + ((size_t)stream * groups + g) * n;
-#pragma unroll
-    for (int u = 0; u < PAN_MAX_OWN; u++) {
-        const int k = lane + u * lanes;
-        acc[u] = (groups == 1 && k < n) ? dst[k] : 0.0;
-    }
+    for (int k = lane; k < n; k += lanes) sacc[k] = groups == 1 ? dst[k] : 0.0;
     const cd *base = frames + (size_t)stream * stream_stride;
     for (int f = g; f < n_frames; f += groups) {
         const cd *src = base + (size_t)f * n;
         for (int i = lane; i < n; i += lanes) {
             const cd x = src[i];
             const double w = window[i];
-            s[i] = make_double2(x.x * w, x.y * w);                  // quisk.c:5212-5213
+            s[fsw(i)] = make_double2(x.x * w, x.y * w);             // quisk.c:5212-5213
         }
         __syncthreads();
-        fft_smem(s, n, tw, -1, lane, lanes);
-#pragma unroll
-        for (int u = 0; u < PAN_MAX_OWN; u++) {
-            const int k = lane + u * lanes;                         // graph bin k <- FFT bin (k + n/2) mod n
-            if (k < n) {
-                const cd X = s[(k + half) & (n - 1)];
-                acc[u] += hypot(X.x, X.y);                          // cabs, quisk.c:5273,5275
-            }
+        fft_smem(s, n, twl, -1, lane, lanes);
+        for (int k = lane; k < n; k += lanes) {                     // graph bin k <- FFT bin (k + n/2) mod n
+            const cd X = s[fsw((k + half) & (n - 1))];
+            sacc[k] += sqrt(fma(X.x, X.x, X.y * X.y));              // cabs, quisk.c:5273,5275 (no overflow at these scales)
         }
         __syncthreads();
     }
-#pragma unroll
-    for (int u = 0; u < PAN_MAX_OWN; u++) {
-        const int k = lane + u * lanes;
-        if (k < n) dst[k] = acc[u];
-    }
+    for (int k = lane; k < n; k += lanes) dst[k] = sacc[k];
 }
 
 __global__ void pan_reduce_kernel(double *avg, const double *partial, int n, int groups)
@@ -170,11 +162,13 @@ __global__ void pan_graph_serial_kernel(double *avg, int n, int data_width, int 
 }
 
 // get_multirx_graph: one frame per stream, |X| summed over groups of 8 bins in fftshift order
-__global__ void __launch_bounds__(1024) pan_multirx_kernel(const cd *frames, long stream_stride, int n, const cd *tw, const double *window,
+__global__ void __launch_bounds__(256) pan_multirx_kernel(const cd *frames, long stream_stride, int n, const cd *tw, const double *window,
                                    double scale, double *graph)
 {
     extern __shared__ double smem_raw[];
-    cd *s = reinterpret_cast<cd *>(smem_raw);
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *s = twl + fft_tw_entries(n);
+    fft_stage_twiddles(twl, tw, n);
     const int stream = blockIdx.x;
     const int lane = threadIdx.x, lanes = blockDim.x;
     const int half = n >> 1;
@@ -182,16 +176,16 @@ __global__ void __launch_bounds__(1024) pan_multirx_kernel(const cd *frames, lon
     for (int i = lane; i < n; i += lanes) {
         const cd x = src[i];
         const double w = window[i];
-        s[i] = make_double2(x.x * w, x.y * w);
+        s[fsw(i)] = make_double2(x.x * w, x.y * w);
     }
     __syncthreads();
-    fft_smem(s, n, tw, -1, lane, lanes);
+    fft_smem(s, n, twl, -1, lane, lanes);
     for (int p = lane; p < n / 8; p += lanes) {
         double d1 = 0.0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const cd X = s[(p * 8 + j + half) & (n - 1)];
-            d1 += hypot(X.x, X.y);
+            const cd X = s[fsw((p * 8 + j + half) & (n - 1))];
+            d1 += sqrt(fma(X.x, X.x, X.y * X.y));
         }
         double d2 = 20.0 * log10(d1) - scale;
         if (d2 < -200) d2 = -200;
@@ -209,7 +203,7 @@ struct Panadapter {
     int init(int streams, int fft_size)
     {
         S = streams; n = fft_size;
-        if (S <= 0 || fft_log2(n) < 0 || n / fft_threads(n) > PAN_MAX_OWN) {
+        if (S <= 0 || fft_log2(n) < 0) {
             set_error("pan_create: fft_size must be a power of two in [8, 8192] (got %d)", fft_size); return QC_EINVAL;
         }
         tw = fft_twiddles(n);
@@ -252,7 +246,7 @@ int quisk_cuda_fft_batch(const void *d_in, void *d_out, int n, int batch, int si
     if (!tw) { set_error("fft_batch: twiddle table allocation failed"); return QC_ENOMEM; }
     int lanes, per;
     fft_shape(n, &lanes, &per);
-    const size_t sh = (size_t)per * n * sizeof(cd);
+    const size_t sh = ((size_t)per * n + fft_tw_entries(n)) * sizeof(cd);
     int rc = fft_smem_optin((const void *)fft_batch_kernel, sh); if (rc != QC_OK) return rc;
     dim3 block(lanes, per);
     fft_batch_kernel<<<(batch + per - 1) / per, block, sh, (cudaStream_t)stream>>>((const cd *)d_in, (cd *)d_out, n, batch, tw, sign < 0 ? -1 : 1);
@@ -293,7 +287,7 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
         p.partial_groups = groups;
     }
     const int lanes = fft_threads(p.n);
-    const size_t sh = (size_t)p.n * sizeof(cd);
+    const size_t sh = (size_t)p.n * (sizeof(cd) + sizeof(double)) + (size_t)fft_tw_entries(p.n) * sizeof(cd);
     int rc = fft_smem_optin((const void *)pan_accumulate_kernel, sh); if (rc != QC_OK) return rc;
     pan_accumulate_kernel<<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.tw,
                                                                  p.d_window, p.d_avg, p.d_partial, groups);
@@ -344,7 +338,7 @@ int quisk_cuda_pan_multirx(qcPanadapter *pp, const void *d_frames, long stream_s
     if (!pp) { set_error("pan_multirx: null handle"); return QC_EINVAL; }
     Panadapter &p = pp->p;
     const int lanes = fft_threads(p.n);
-    const size_t sh = (size_t)p.n * sizeof(cd);
+    const size_t sh = ((size_t)p.n + fft_tw_entries(p.n)) * sizeof(cd);
     int rc = fft_smem_optin((const void *)pan_multirx_kernel, sh); if (rc != QC_OK) return rc;
     double scale = (log10((double)p.n) + 31.0 * log10(2.0)) * 20.0;                      // quisk.c:4892-4893
     pan_multirx_kernel<<<p.S, lanes, sh, (cudaStream_t)stream>>>((const cd *)d_frames, stream_stride, p.n, p.tw, p.d_window, scale, d_graph);

@@ -118,11 +118,13 @@ __global__ void fracdecim_kernel(const cd *in, long is, cd *out, long os, int n,
 }
 
 // bandscope: real block * Hann -> FFT (complex transform of the real block) -> |X[0..N/2]| accumulate
-__global__ void __launch_bounds__(1024) bandscope_accumulate_kernel(const double *blocks, long stream_stride, int n_blocks, int n,
+__global__ void __launch_bounds__(256) bandscope_accumulate_kernel(const double *blocks, long stream_stride, int n_blocks, int n,
                                                                     const cd *tw, const double *window, double *avg, double *the_max)
 {
     extern __shared__ double sm_raw[];
-    cd *s = reinterpret_cast<cd *>(sm_raw);
+    cd *twl = reinterpret_cast<cd *>(sm_raw);
+    cd *s = twl + fft_tw_entries(n);
+    fft_stage_twiddles(twl, tw, n);
     const int stream = blockIdx.x, lane = threadIdx.x, lanes = blockDim.x;
     const int L = n / 2 + 1;
     double *a = avg + (size_t)stream * (L + 1);
@@ -132,11 +134,11 @@ __global__ void __launch_bounds__(1024) bandscope_accumulate_kernel(const double
         for (int i = lane; i < n; i += lanes) {
             const double v = src[i];
             mx = fmax(mx, fabs(v));
-            s[i] = make_double2(v * window[i], 0.0);
+            s[fsw(i)] = make_double2(v * window[i], 0.0);
         }
         __syncthreads();
-        fft_smem(s, n, tw, -1, lane, lanes);
-        for (int i = lane; i < L; i += lanes) a[i] += hypot(s[i].x, s[i].y);        // quisk.c:4981
+        fft_smem(s, n, twl, -1, lane, lanes);
+        for (int i = lane; i < L; i += lanes) { const cd X = s[fsw(i)]; a[i] += sqrt(X.x * X.x + X.y * X.y); }   // cabs, quisk.c:4981
         __syncthreads();
     }
     // the_max (hermes_adc_level, quisk.c:4972-4974): block-wide maximum of |sample|
@@ -284,7 +286,7 @@ int quisk_cuda_bandscope_accumulate(qcBandscope *h, const double *d_blocks, long
     if (!h) return QC_EINVAL;
     if (n_blocks <= 0) return QC_OK;
     QBand &b = h->b;
-    const size_t sh = (size_t)b.n * sizeof(cd);
+    const size_t sh = ((size_t)b.n + fft_tw_entries(b.n)) * sizeof(cd);
     if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(bandscope_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     bandscope_accumulate_kernel<<<b.S, fft_threads(b.n), sh, (cudaStream_t)stream>>>(d_blocks, stream_stride, n_blocks, b.n, b.tw, b.d_window, b.d_avg, b.d_max);
     count_launch();

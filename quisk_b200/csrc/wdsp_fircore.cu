@@ -7,7 +7,7 @@
 //   accum = sum_j fftout[(buffidx - j) & mask] (.) fmask[cset][j]          (j = 0 .. nfor-1, that order)
 //   backward FFT (unnormalised: callers bake 1/(2 size) into the impulse)  ->  out = first `size` samples
 // GPU mapping: one CTA per channel per block.  The forward FFT, the partition MAC and the inverse FFT
-// run back to back on one shared-memory buffer (fft_device.cuh); each thread owns 8 fixed bins, so the
+// run back to back on one shared-memory buffer (fft_device.cuh); each thread owns 16 fixed bins, so the
 // newest spectrum goes from registers straight into the MAC, and only the nfor-1 older spectra come
 // from the frequency-domain delay line in global memory (128 KiB per channel at size 1024 / nc 4096:
 // L2 resident for hundreds of channels).  The masks are shared by all channels and are built on the
@@ -19,68 +19,52 @@
 
 namespace qc {
 
-static constexpr int FC_OWN = 8;        // bins per thread = n2 / fft_threads(n2)
 
-__global__ void __launch_bounds__(1024) fircore_kernel(const cd *in, long in_stride, cd *out, long out_stride,
+__global__ void __launch_bounds__(256) fircore_kernel(const cd *in, long in_stride, cd *out, long out_stride,
                                                        int size, int nfor, int buffidx,
                                                        cd *prev /*[C][size]*/, cd *fdl /*[C][nfor][2 size]*/,
                                                        const cd *fmask /*[nfor][2 size]*/, const cd *tw)
 {
     extern __shared__ double smem_raw[];
-    cd *s = reinterpret_cast<cd *>(smem_raw);
+    const int n2 = 2 * size;
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *s = twl + fft_tw_entries(n2);
+    fft_stage_twiddles(twl, tw, n2);
     const int c = blockIdx.x;
     const int lane = threadIdx.x, lanes = blockDim.x;
-    const int n2 = 2 * size;
     const cd *x = in + (size_t)c * in_stride;
     cd *pv = prev + (size_t)c * size;
     // fftin = [prev | new]; the new block becomes prev (firmin.c:411, 429)
     for (int i = lane; i < size; i += lanes) {
         const cd v = x[i];
-        s[i] = pv[i];
-        s[size + i] = v;
+        s[fsw(i)] = pv[i];
+        s[fsw(size + i)] = v;
         pv[i] = v;
     }
     __syncthreads();
-    fft_smem(s, n2, tw, -1, lane, lanes);
-    // partition MAC; bins lane + u*lanes are this thread's
+    fft_smem(s, n2, twl, -1, lane, lanes);
+    // partition MAC; bins lane, lane + lanes, ... are this thread's alone, so each accumulator replaces its
+    // bin in shared memory without a barrier
     cd *fd = fdl + (size_t)c * nfor * n2;
     const int mask = nfor - 1;
-    cd acc[FC_OWN];
-#pragma unroll
-    for (int u = 0; u < FC_OWN; u++) {
-        const int i = lane + u * lanes;
-        if (i < n2) {
-            const cd X = s[i];
-            fd[(size_t)buffidx * n2 + i] = X;
-            const cd m = fmask[i];
-            acc[u] = make_double2(X.x * m.x - X.y * m.y, X.x * m.y + X.y * m.x);
+    for (int i = lane; i < n2; i += lanes) {
+        const cd X = s[fsw(i)];
+        fd[(size_t)buffidx * n2 + i] = X;
+        const cd m0 = fmask[i];
+        cd acc = make_double2(X.x * m0.x - X.y * m0.y, X.x * m0.y + X.y * m0.x);
+        int k = buffidx;
+        for (int j = 1; j < nfor; j++) {
+            k = (k + mask) & mask;
+            const cd Y = fd[(size_t)k * n2 + i], m = fmask[(size_t)j * n2 + i];
+            acc.x += Y.x * m.x - Y.y * m.y;
+            acc.y += Y.x * m.y + Y.y * m.x;
         }
-    }
-    int k = buffidx;
-    for (int j = 1; j < nfor; j++) {
-        k = (k + mask) & mask;
-        const cd *sp = fd + (size_t)k * n2;
-        const cd *mk = fmask + (size_t)j * n2;
-#pragma unroll
-        for (int u = 0; u < FC_OWN; u++) {
-            const int i = lane + u * lanes;
-            if (i < n2) {
-                const cd X = sp[i], m = mk[i];
-                acc[u].x += X.x * m.x - X.y * m.y;
-                acc[u].y += X.x * m.y + X.y * m.x;
-            }
-        }
+        s[fsw(i)] = acc;
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < FC_OWN; u++) {
-        const int i = lane + u * lanes;
-        if (i < n2) s[i] = acc[u];
-    }
-    __syncthreads();
-    fft_smem(s, n2, tw, +1, lane, lanes);
+    fft_smem(s, n2, twl, +1, lane, lanes);
     cd *y = out + (size_t)c * out_stride;
-    for (int i = lane; i < size; i += lanes) y[i] = s[i];
+    for (int i = lane; i < size; i += lanes) y[i] = s[fsw(i)];
 }
 
 int FirCore::init(int C_, int size_, int nc_, int mp, const double *impulse)
@@ -144,7 +128,7 @@ int FirCore::update()
 int FirCore::run(const void *d_in, long in_stride, void *d_out, long out_stride, cudaStream_t s)
 {
     const int lanes = fft_threads(n2);
-    const size_t sh = (size_t)n2 * sizeof(cd);
+    const size_t sh = ((size_t)n2 + fft_tw_entries(n2)) * sizeof(cd);
     if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(fircore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     fircore_kernel<<<C, lanes, sh, s>>>((const cd *)d_in, in_stride, (cd *)d_out, out_stride, size, nfor, buffidx,
                                         d_prev, d_fdl, d_mask[cset], tw);
