@@ -336,6 +336,179 @@ def rxa_main(args, rank, world, local_rank):
     if world > 1:
         dist.destroy_process_group()
 
+# --------------------------------------------------------------------------------------------
+# C5: wideband polyphase channelizer (BASELINE.json configs[4])
+# --------------------------------------------------------------------------------------------
+
+PFB = dict(K=1024, D=512, P=16, fs=98.304e6, alg_bytes=48.0,
+           name="channelizer: one 98.304 MS/s stream -> 1024 receivers x 192 kS/s (D=512, 16x1024-tap fir_bandpass prototype), "
+                "time-block sharded with halos (BASELINE configs[4])")
+
+
+def pfb_proto():
+    from quisk_b200 import lib as L
+    lib = L.load()
+    h = np.zeros(PFB["K"] * PFB["P"])
+    fc = 0.4 * PFB["fs"] / PFB["K"]
+    rc = lib.quisk_cuda_fir_bandpass(len(h), -fc, fc, PFB["fs"], 1, 0, 1.0, h.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    return h
+
+
+def pfb_reference_rate(n_samples, steps, warmup):
+    """The reference's way to get receiver k out of the wideband stream: its tune loop (quisk.c:2477-2494, compiled
+    reference) and quisk_cDecimate with the 16384-tap prototype, /512 (filter.c:203-229) -- per receiver.  One
+    receiver per host core over n_samples; the wideband rate is what all 1024 receivers would sustain."""
+    from oracle import quisk_oracle as O
+    from oracle import ref_ctypes as R
+    cores = os.cpu_count() or 1
+    h = pfb_proto()
+    libs, sts, xs = [], [], []
+    for i in range(cores):
+        lib = R.bind_filter_api(R.load("libquisk_rx_ref.so", private_copy=True))
+        lib.ref_tune.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
+        st = R.cFilter()
+        lib.quisk_filt_cInit(C.byref(st), h.ctypes.data_as(R.c_double_p), len(h))
+        libs.append(lib); sts.append(st); xs.append(O.synth_iq(n_samples, 1100 + i, 1.0))
+    scratch = [np.zeros(61440, dtype=np.complex128) for _ in range(cores)]
+    vec = [np.array([1.0 + 0j]) for _ in range(cores)]
+
+    def work(i, nsteps):
+        for _ in range(nsteps):
+            pos = 0
+            while pos < n_samples:
+                m = min(61440, n_samples - pos)
+                scratch[i][:m] = xs[i][pos:pos + m]
+                libs[i].ref_tune(scratch[i].ctypes.data, m, (i + 1) * PFB["fs"] / PFB["K"], int(PFB["fs"]), vec[i].ctypes.data)
+                libs[i].quisk_cDecimate(scratch[i].ctypes.data, m, C.byref(sts[i]), PFB["D"])
+                pos += m
+
+    def run(nsteps):
+        th = [threading.Thread(target=work, args=(i, nsteps)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th: t.start()
+        for t in th: t.join()
+        return time.perf_counter() - t0
+    run(warmup)
+    dt = run(steps)
+    receiver_rate = cores * n_samples * steps / dt / 1e6        # receiver-input MS/s over all cores
+    return receiver_rate / PFB["K"], cores, dt
+
+
+def pfb_main(args, rank, world, local_rank):
+    cfg = PFB
+    n = args.block if args.block != 32768 else (1 << 24)          # input samples per GPU per step (time block)
+    n = (n // cfg["D"]) * cfg["D"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ns = 61440 * 2
+        v, cores, dt = pfb_reference_rate(ns, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "complex MS/s through RX chain", "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": {"workload": cfg["name"], "receivers_timed": cores, "samples_per_step": ns},
+                "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
+                                 "sample": "%d receivers (one per core) x %d samples x %d steps through the reference's tune loop + quisk_cDecimate(16384 taps, /512); "
+                                           "value = wideband rate at which all 1024 receivers would be served" % (cores, ns, args.steps)},
+                "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line)); return
+    import torch
+    import torch.distributed as dist
+    from quisk_b200 import lib as L
+    from quisk_b200.rx import Channelizer
+    from quisk_b200.shard import time_blocks
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = L.require_device()
+    L.check(lib, lib.quisk_cuda_set_device(local_rank), "set_device")
+    K, D, T = cfg["K"], cfg["D"], cfg["K"] * cfg["P"]
+    ch = Channelizer(K, D, pfb_proto())
+    # this rank's time block of the (world * n)-sample stream, with its halo in front (SURVEY.md 8e)
+    tb = time_blocks(world * n, world, D, T - 1)[rank]
+    halo = tb.start - tb.halo_start
+    x = synth_block_torch(torch, 1, halo + (tb.stop - tb.start), dev, 77 + rank)[0].contiguous()
+    nf = (tb.stop - tb.start) // D
+    y = torch.zeros((K, nf), dtype=torch.complex128, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ch.seek(tb.halo_start)
+        if halo:
+            ch.prime(x.data_ptr(), halo, stream)
+        got = ch.process(x.data_ptr() + halo * 16, tb.stop - tb.start, y.data_ptr(), nf, 0, stream)
+        assert got == nf
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = lib.quisk_cuda_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.quisk_cuda_launch_count() - l0)
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * args.steps / (ms_max / 1e3) / 1e6
+    # e2e: pinned host stream in, a frame-power summary out per step; the 32 B/sample receiver streams stay on the
+    # device for the per-receiver chains (quisk_cuda_rx_process), which is where they are consumed
+    e2e = None
+    if args.e2e_steps > 0:
+        hx = torch.empty(x.shape, dtype=torch.complex128).pin_memory(); hx.copy_(x.cpu())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            x.copy_(hx, non_blocking=True)
+            step()
+            summary = y[:, :64].abs().sum(dim=1).cpu()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": world * n * args.e2e_steps / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": int(x.numel() * 16),
+               "d2h_bytes_per_step": int(summary.numel() * 8),
+               "note": "pinned host IQ -> H2D -> channelizer; receiver streams stay in HBM for quisk_cuda_rx_process, a per-receiver level summary is read back"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    alg = cfg["alg_bytes"] * n
+    ach = alg * args.steps / (ms / 1e3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            v, cores, dt = pfb_reference_rate(61440, 2, 1)
+            cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
+                   "sample": "%d receivers (one per core) x 61440 samples x 2 steps, %.1f s wall: reference tune loop + quisk_cDecimate(16384 taps, /512) per receiver; "
+                             "value = wideband rate at which all 1024 receivers would be served" % (cores, dt)}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
+    line = {"metric": "complex MS/s through RX chain", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "samples_per_gpu_per_step": n, "halo": halo, "receivers": K, "decimation": D, "taps": T,
+                       "l2": "input %.0f MB + output %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (n * 16 / 1e6, n * 32 / 1e6)},
+            "clocks": sampler.result(), "gpu_launches": launches, "e2e": e2e,
+            "roofline": {"bound": "hbm", "kernel": "pfb_kernel (branch FIRs + 1024-point FFT per frame)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_sample": cfg["alg_bytes"]},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -343,7 +516,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rx_chain", choices=["rx_chain", "panadapter", "rx_chain+panadapter", "rxa_usb", "rxa_fm"])
+    ap.add_argument("--workload", default="rx_chain", choices=["rx_chain", "panadapter", "rx_chain+panadapter", "rxa_usb", "rxa_fm", "channelizer"])
     ap.add_argument("--channels", type=int, default=4096)
     ap.add_argument("--block", type=int, default=32768, help="input samples per channel per step (multiple of 8192)")
     ap.add_argument("--tune", type=float, default=12345.0, help="rx_tune_freq in Hz (0 = no tuning stage)")
@@ -363,6 +536,8 @@ def main():
     block = max(FFT_SIZE, (args.block // FFT_SIZE) * FFT_SIZE)
     if args.workload.startswith("rxa_"):
         return rxa_main(args, rank, world, local_rank)
+    if args.workload == "channelizer":
+        return pfb_main(args, rank, world, local_rank)
 
     from quisk_b200.rx import load_tables
     tabs = load_tables()

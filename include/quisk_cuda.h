@@ -224,6 +224,7 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_TIMING       1   /* value != 0: record CUDA events around the dominant (fused) kernel */
 #define QC_RX_OPT_FUSED_CHUNK  2   /* target input samples per shared-memory chunk of the fused decimator */
 #define QC_RX_OPT_FUSED_THREADS 3  /* CTA width of the fused decimator: 128 or 256 */
+#define QC_RX_OPT_FUSED_TAIL   9   /* SSB / CW: one kernel for receive filter + demodulation + audio interpolators (default 1) */
 #define QC_RX_OPT_FUSED_DEEPK  8   /* plan kernels: low-rate stages run once per this many chunks (1 or 4, default 1: measured slower at 4 with two CTAs per SM) */
 #define QC_RX_OPT_TRACE        7   /* debug: record clock64() stamps per chunk phase in the fused kernel */
 #define QC_RX_OPT_FUSED_PLANS  6   /* 1 (default): use plan-specialised kernels when the stage list matches one */
@@ -286,6 +287,25 @@ qcFracDecim *quisk_cuda_fracdecim_create(int n_channels);
 void quisk_cuda_fracdecim_destroy(qcFracDecim *f);
 int quisk_cuda_fracdecim_run(qcFracDecim *f, const void *d_in, long in_stride, int count, double fdecim,
                              void *d_out, long out_stride, int *n_out, void *stream);
+
+/* ---- wideband polyphase channelizer (configuration C5) ----
+ * One wideband stream -> n_channels receivers, receiver k centred on k*fs/n_channels, each decimated by `decim`
+ * through the prototype low-pass `proto` (n_taps real taps, a multiple of n_channels).  Output k equals the
+ * reference's per-receiver front end: mix by exp(-2 pi i k n / n_channels) with n the absolute sample index
+ * (quisk.c:2477-2494), then quisk_cDecimate(proto, decim) (filter.c:203-229) -- computed as branch FIRs + one
+ * FFT per output frame.  n_channels in {256, 512, 1024}; n_taps/n_channels in {4, 8, 16, 32}; decim <= n_channels.
+ * layout 0: d_out[k * out_stride + frame] (feeds quisk_cuda_rx_process); layout 1: d_out[frame * out_stride + k].
+ * State carried between calls: the last n_taps input samples and the absolute sample index, so any block
+ * length is allowed.  Time-block sharding: quisk_cuda_pfb_seek(t - halo) zeroes the state at an absolute index,
+ * quisk_cuda_pfb_prime() feeds the halo samples without producing output. */
+typedef struct qcChannelizer qcChannelizer;
+qcChannelizer *quisk_cuda_pfb_create(int n_channels, int decim, const double *proto, int n_taps);
+void quisk_cuda_pfb_destroy(qcChannelizer *p);
+int quisk_cuda_pfb_count_out(const qcChannelizer *p, int count);
+int quisk_cuda_pfb_seek(qcChannelizer *p, long long n_abs);
+int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *stream);
+int quisk_cuda_pfb_process(qcChannelizer *p, const void *d_in, int count, void *d_out, long out_stride, int layout,
+                           int *n_frames, void *stream);
 
 /* Batched complex FFT (unnormalised, sign -1 forward / +1 backward), sizes 2^k,
  * 8 <= n <= 16384: the in-house Stockham kernel the panadapter and the WDSP

@@ -603,3 +603,22 @@ def rel_rms(a: np.ndarray, b: np.ndarray) -> float:
     den = np.sqrt(np.mean(np.abs(b) ** 2))
     num = np.sqrt(np.mean(np.abs(a - b) ** 2)) if len(a) else 0.0
     return float(num / den) if den > 0 else float(num)
+
+
+def channelizer_oracle(x: np.ndarray, channels, proto: np.ndarray, n_channels: int, decim: int, n0: int = 0) -> np.ndarray:
+    """SURVEY.md section 8 C5 oracle definition: for receiver k, direct-phase mix
+    v[n] = x[n] * exp(-2 pi i k n / K) with n the absolute sample index (the reference's tune step,
+    quisk.c:2477-2494, with the phase taken from an exact K-entry table instead of the recurrence), then the
+    reference's quisk_cDecimate(proto, decim) (filter.c:203-229; FirDecim above).  Returns [len(channels)][frames].
+    Cost is len(proto) MACs per output per receiver, so tests run it on a channel subset."""
+    K = int(n_channels)
+    q = np.arange(K)
+    table = np.cos(2.0 * np.pi * q / K) - 1j * np.sin(2.0 * np.pi * q / K)
+    n = n0 + np.arange(len(x), dtype=np.int64)
+    out = []
+    for k in channels:
+        v = x * table[(int(k) * n) % K]
+        f = FirDecim(proto, decim)
+        f.decim_index = n0 % decim
+        out.append(f(v))
+    return np.stack(out)

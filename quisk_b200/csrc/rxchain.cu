@@ -253,8 +253,13 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
                                   (size_t)n * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
         if (n_decim) *n_decim = n;
     }
-    // main receive filter
     int no = 0;
+    if (fused && fused_tail && tail_fusable()) {
+        rc = run_tail(cur, stride, n, d_audio, audio_stride, &no, s);
+        if (rc == QC_OK) { if (n_audio) *n_audio = no; return QC_OK; }
+        if (rc != QC_ENOMEM) return rc;          // too long for shared memory: per-stage kernels below
+    }
+    // main receive filter
     rc = rxf->run(cur, stride, n, bufc[pp], cap, &no, 0, s); if (rc != QC_OK) return rc;
     cur = bufc[pp]; n = no;
     // detector -> real audio at the filter rate
@@ -372,6 +377,7 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
         if (value && !rx->rx.d_trace) { QC_CUDA(cudaMalloc((void **)&rx->rx.d_trace, (size_t)rx->rx.C * 256 * sizeof(long long))); QC_CUDA(cudaMemset(rx->rx.d_trace, 0, (size_t)rx->rx.C * 256 * sizeof(long long))); }
         if (!value && rx->rx.d_trace) { cudaFree(rx->rx.d_trace); rx->rx.d_trace = nullptr; }
         return QC_OK;
+    case QC_RX_OPT_FUSED_TAIL: rx->rx.fused_tail = value ? 1 : 0; return QC_OK;
     case QC_RX_OPT_FUSED_DEEPK:
         if (value != 1 && value != 4) { qc::set_error("rx_set_option: deepk must be 1 or 4"); return QC_EINVAL; }
         rx->rx.fused_deepk = value; return QC_OK;

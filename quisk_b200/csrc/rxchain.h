@@ -43,6 +43,7 @@ struct RxChain {
     int fused_plans = 1;                // use the plan-specialised instantiations when one matches
     int fused_dense = 0;                // 1: cap registers at 128/thread for more resident CTAs
     int fused_min_r = 0;                // force at least this many outputs per thread in half-band stages
+    int fused_tail = 1;                 // SSB / CW: run filter + demod + audio interpolators as one kernel (rxtail.cu)
     // optional device timing of the dominant (fused) kernel
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -62,6 +63,9 @@ struct RxChain {
     int run_fused_decimator(size_t n_stages, const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t s);
     int reset_fused();
     void release_fused();
+    // rxtail.cu
+    bool tail_fusable() const;
+    int run_tail(const cd *in, long in_stride, int n, double *out, long out_stride, int *n_out, cudaStream_t s);
 };
 
 }  // namespace qc

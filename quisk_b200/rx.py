@@ -126,3 +126,34 @@ def load_tables(path: str | None = None) -> dict:
     path = path or os.path.join(os.path.dirname(L.HERE), "tests", "golden", "quisk_tables.npz")
     z = np.load(path)
     return {k: z[k] for k in z.files}
+
+
+class Channelizer:
+    """Wideband polyphase channelizer (quisk_cuda_pfb_*): one stream -> n_channels receivers at k*fs/n_channels,
+    each equal to the reference's tune (quisk.c:2477-2494) + quisk_cDecimate(proto, decim) (filter.c:203-229)."""
+
+    def __init__(self, n_channels: int, decim: int, proto):
+        self.lib = L.require_device()
+        self.proto = np.ascontiguousarray(proto, dtype=np.float64)
+        self.n_channels, self.decim = n_channels, decim
+        self.h = self.lib.quisk_cuda_pfb_create(n_channels, decim, _dp(self.proto), len(self.proto))
+        if not self.h:
+            raise L.QuiskCudaError("pfb_create: " + self.lib.quisk_cuda_last_error().decode())
+
+    def count_out(self, count: int) -> int: return self.lib.quisk_cuda_pfb_count_out(self.h, count)
+
+    def seek(self, n_abs: int): L.check(self.lib, self.lib.quisk_cuda_pfb_seek(self.h, n_abs), "pfb_seek")
+
+    def prime(self, d_in: int, count: int, stream: int = 0):
+        L.check(self.lib, self.lib.quisk_cuda_pfb_prime(self.h, d_in, count, stream), "pfb_prime")
+
+    def process(self, d_in: int, count: int, d_out: int, out_stride: int, layout: int = 0, stream: int = 0) -> int:
+        nf = C.c_int(0)
+        L.check(self.lib, self.lib.quisk_cuda_pfb_process(self.h, d_in, count, d_out, out_stride, layout, C.byref(nf), stream), "pfb_process")
+        return nf.value
+
+    def close(self):
+        if self.h:
+            self.lib.quisk_cuda_pfb_destroy(self.h); self.h = None
+
+    __del__ = close

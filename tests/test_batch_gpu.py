@@ -130,13 +130,14 @@ def test_rx_decimate_kat(rate, fused, torch, tabs):
     rx.close()
 
 
+@pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("mode", list(DEMOD_TAPS))
-def test_rx_demod_kat(mode, torch, tabs):
+def test_rx_demod_kat(mode, fused, torch, tabs):
     """quisk_process_demodulate at 48 kS/s in (no decimation planned) against the reference fixture."""
     from quisk_b200.rx import RxChain
     kat = golden("chain_kat.npz")
     fi, fq = demod_taps(mode)
-    rx = RxChain(3, 48000, mode, fi, fq, tabs, fused=False)
+    rx = RxChain(3, 48000, mode, fi, fq, tabs, fused=bool(fused))      # fused: rxtail.cu for SSB / CW
     x = np.stack([O.synth_iq(12000, 10, 1.0)] * 3)
     aud, ca, _, _ = _run_chain(torch, rx, x, DEMOD_SPLITS)
     assert ca == kat["demod_%s/counts" % mode].tolist()
