@@ -91,6 +91,9 @@ __device__ __forceinline__ cd fft_tw(const cd *twl, int idx, int sign)
 
 // s: this transform's n-element buffer in shared memory; twl: the staged two-level twiddle store (shared);
 // sign: -1 forward, +1 backward; lane / lanes: this thread's index among the transform's threads.
+// BPT = radix-16 butterflies per thread and pass: 2 covers n = 8192 on 256 lanes; kernels that only run
+// n <= 16 * lanes instantiate BPT = 1 and save the second butterfly's 64 registers.
+template <int BPT = 2>
 __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int sign, int lane, int lanes)
 {
     const double sg = (double)sign;
@@ -100,10 +103,10 @@ __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int si
         const int n1 = len >> 4;
         const int tstep = n / len;
         const int nb = n >> 4;
-        cd v[2][16];
-        int ob[2];
+        cd v[BPT][16];
+        int ob[BPT];
 #pragma unroll
-        for (int t = 0; t < 2; t++) {
+        for (int t = 0; t < BPT; t++) {
             const int b = lane + t * lanes;
             ob[t] = -1;
             if (b < nb) {
@@ -130,7 +133,7 @@ __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int si
         }
         __syncthreads();
 #pragma unroll
-        for (int t = 0; t < 2; t++) {
+        for (int t = 0; t < BPT; t++) {
             if (ob[t] >= 0) {
 #pragma unroll
                 for (int k = 0; k < 16; k++) s[fsw(ob[t] + k * stride)] = v[t][k];

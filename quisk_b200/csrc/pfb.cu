@@ -9,7 +9,19 @@
 // for all K receivers instead of K * T MACs.  The identity is exact; only the summation order differs from the
 // reference (<= 1e-15 relative).  D <= K (D = K/2: the 2x oversampled C5 case; D = K: critically sampled).
 //
-// Mapping: a CTA of K/4 threads = 4 transforms x K/16 lanes handles FOUR consecutive frames per round.
+// Two implementations:
+//  (1) D = K or D = K/2 (every case BASELINE.json names): two kernels per slice of frames.
+//      pfb_fir_kernel  : one THREAD per branch r and frame range.  The branch's taps (T/K per tap alignment, two
+//                        alignments when D = K/2) and its T/K-sample window live in registers; per step the thread
+//                        loads ONE new sample (coalesced across the 128 branches of the CTA, prefetched T/K steps
+//                        ahead), and emits the one or two frames that sample completes: u[frame][r].  Input is read
+//                        once (plus a T/K-sample warm-up per frame range), no shared memory at all.
+//      pfb_fft_kernel  : K-point transforms of u, four frames per CTA, written channel-major or frame-major.
+//      u is produced and consumed slice by slice (default 2048 frames = 32 MiB at K = 1024) so that it lives in
+//      the 126 MB L2 rather than making a round trip through HBM.
+//  (2) any other D <= K: the single generic kernel below (taps in shared memory, window re-read per round).
+//
+// Generic kernel mapping: a CTA of K/4 threads = 4 transforms x K/16 lanes handles FOUR consecutive frames per round.
 //   FIR phase : thread owns 4 branches r; per branch it loads the P + SMAX input samples the four frames need
 //               (coalesced 16-byte loads, history or block selected per load), and accumulates the four frames with
 //               taps read from shared memory (the whole prototype, T doubles, is staged once per CTA).
@@ -105,6 +117,215 @@ __global__ void __launch_bounds__(256, 1) pfb_kernel(PfbParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// (1) register-resident branch FIRs + batched transforms, D = K / OVS with OVS = 1 or 2
+// ------------------------------------------------------------------------------------------------------------
+struct PfbFirParams {
+    const cd *in; int count;
+    const cd *hist; int H;
+    long long n0;                   // absolute index of in[0]
+    long long f0; int nf;           // absolute index of the first frame of this launch, frames in it
+    int fs;                         // frames per CTA range (even)
+    int K, D;
+    const double *taps;
+    cd *u;                          // [nf][K]
+};
+
+// sample at index rel relative to in[0]: the block, the history in front of it, or zero outside both
+__device__ __forceinline__ cd pfb_load(const cd *__restrict__ in, const cd *__restrict__ hist_end, int rel, int count, int H)
+{
+    cd v = make_double2(0.0, 0.0);
+    if (rel >= 0) { if (rel < count) v = in[rel]; }
+    else if (rel >= -H) v = hist_end[rel];
+    return v;
+}
+
+// Branch r sees the sub-stream x_r[a] = x[K a + r].  Frame m ends on sample n_m = D m + D - 1 and uses
+// x_r[a_m - a'] h[t0 + K a'], a' < P, with a_m = floor((n_m - r) / K) and t0 = (n_m - r) mod K.
+//   OVS = 1 (D = K):   a_m = m, t0 = K - 1 - r: one frame per new sample, one tap set.
+//   OVS = 2 (D = K/2): sample a completes frames m_lo = 2a + (r >= D) with t0 = (2D - 1 - r) mod D, and m_lo + 1 with
+//                      t0 + D: two frames per new sample on the same window, two tap sets.
+// A branch is shared by TWO lanes of a warp (l and l + 16): lane half h holds the taps and the window for ages
+// [h P/2, (h+1) P/2).  Per step the young half loads the new sample, the sample that ages out of its window moves
+// to the old half by shuffle, both halves run P/2 taps, and one xor-shuffle adds the halves; the young half then
+// stores frame m_lo, the old half frame m_lo + 1.  That halves the registers per thread (taps + window are the
+// whole footprint), which is what sets the number of resident warps here.
+// All loop arithmetic is 32-bit and relative to the launch (count <= 2^30 is checked by the host).
+static constexpr int PFB_BR = 64;       // branches per 128-thread CTA
+static constexpr int PFB_RING = 16;     // cp.async ring depth in steps (power of two)
+
+template <int P, int OVS>
+__global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirParams p)
+{
+    constexpr int PH = P / 2;
+    const int lane = threadIdx.x & 31, half = lane >> 4;
+    const int r = blockIdx.x * PFB_BR + (threadIdx.x >> 5) * 16 + (lane & 15);
+    const int K = p.K, D = p.D;
+    const int ra = blockIdx.y * p.fs;                                          // this CTA's frames [ra, rb) of the launch
+    const int rb = min(ra + p.fs, p.nf);
+    if (ra >= rb) return;
+    const int tau = OVS == 2 ? (2 * D - 1 - r) % D : K - 1 - r;
+    double lo[PH], hi[OVS == 2 ? PH : 1];
+#pragma unroll
+    for (int a = 0; a < PH; a++) {
+        lo[a] = p.taps[tau + K * (half * PH + a)];
+        if (OVS == 2) hi[a] = p.taps[tau + D + K * (half * PH + a)];
+    }
+    // first and last step (absolute branch sample index), and the launch-relative frame the first step completes
+    const long long fa = p.f0 + ra, fb = p.f0 + rb;
+    long long a_lo, a_hi;
+    if (OVS == 2) { a_lo = (fa >> 1) - 1; a_hi = (fb - 1) >> 1; }
+    else { a_lo = fa; a_hi = fb - 1; }
+    const int steps = (int)(a_hi - a_lo + 1);
+    const int mrel0 = OVS == 2 ? (int)(2 * a_lo - p.f0) + (r >= D ? 1 : 0) : (int)(a_lo - p.f0);
+    const int rel = (int)(a_lo * K + r - p.n0);                                // of step 0's sample
+    const cd *in = p.in, *he = p.hist + p.H;
+    cd w[PH];                                                                  // slot i mod PH: this half's sample of step i
+#pragma unroll
+    for (int q = 1; q < PH; q++) w[PH - q] = pfb_load(in, he, rel - (q + half * PH) * K, p.count, p.H);
+    w[0] = pfb_load(in, he, rel - (PH + half * PH) * K, p.count, p.H);          // ages out at step 0: what the old half takes then
+    // New samples arrive through a per-lane cp.async ring RING steps deep: what hides the HBM latency is bytes in
+    // flight (16 warps x 16 lanes x 16 B x RING = 64 KB per SM), and shared memory holds them without registers.
+    // A lane only ever reads what it copied itself, so cp.async.wait_group is the only synchronisation.
+    __shared__ cd ring[PFB_RING][PFB_BR];
+    const int rl = (threadIdx.x >> 5) * 16 + (lane & 15);
+    auto issue = [&](int step) {
+        if (!half) {
+            const int e = rel + step * K;
+            const cd *src = in; unsigned bytes = 0;
+            if (step < steps) {
+                if (e >= 0) { if (e < p.count) { src = in + e; bytes = 16; } }
+                else if (e >= -p.H) { src = he + e; bytes = 16; }
+            }
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[step & (PFB_RING - 1)][rl]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll 1
+    for (int j = 0; j < PFB_RING - 2; j++) issue(j);
+    cd *uo = p.u + r;
+    for (int i = 0; i < steps; i += PH) {
+#pragma unroll
+        for (int j = 0; j < PH; j++) {
+            if (i + j < steps) {                                                // uniform over the CTA
+                const cd old = w[j];                                            // age PH of the young half = age 0 of the old one
+                const double ox = __shfl_sync(0xffffffffu, old.x, lane & 15), oy = __shfl_sync(0xffffffffu, old.y, lane & 15);
+                // the slot this overwrites was read two steps ago and that value has been consumed since
+                issue(i + j + PFB_RING - 2);
+                asm volatile("cp.async.wait_group %0;" ::"n"(PFB_RING - 2) : "memory");
+                w[j] = half ? make_double2(ox, oy) : ring[(i + j) & (PFB_RING - 1)][rl];
+                double xr = 0.0, xi = 0.0, yr = 0.0, yi = 0.0;
+#pragma unroll
+                for (int t = 0; t < PH; t++) {
+                    const cd x = w[(j - t + PH) % PH];
+                    xr = fma(x.x, lo[t], xr); xi = fma(x.y, lo[t], xi);
+                    if (OVS == 2) { yr = fma(x.x, hi[t], yr); yi = fma(x.y, hi[t], yi); }
+                }
+                xr += __shfl_xor_sync(0xffffffffu, xr, 16); xi += __shfl_xor_sync(0xffffffffu, xi, 16);
+                if (OVS == 2) { yr += __shfl_xor_sync(0xffffffffu, yr, 16); yi += __shfl_xor_sync(0xffffffffu, yi, 16); }
+                const int m = mrel0 + OVS * (i + j) + half;
+                if (OVS == 2) { if (m >= ra && m < rb) uo[(size_t)m * K] = half ? make_double2(yr, yi) : make_double2(xr, xi); }
+                else if (!half && m >= ra && m < rb) uo[(size_t)m * K] = make_double2(xr, xi);
+            }
+        }
+    }
+}
+
+// K-point forward transforms of u, K = 256 R3 (R3 = 1, 2, 4), as 16 x 16 x R3 Stockham passes with FOUR frames
+// interleaved: thread (b, f) = (tid / 4, tid % 4) runs butterfly b of frame 4 g + f, and element i of frame f lives at
+// shared-memory slot 4 (i ^ ((i >> 4) & 1)) + f -- the four frames of one element are 64 contiguous bytes, and the XOR
+// puts the elements of neighbouring butterflies into different halves of a 128-byte row in every pass.
+//   pass 1: inputs straight from global memory (128-byte runs per frame), radix 16, twiddle, to shared memory
+//   pass 2: radix 16 in shared memory (for K = 256 the outputs are final and go to global memory)
+//   pass 3: 16 / R3 radix-R3 butterflies per thread, no twiddles, results from registers to global memory:
+//           channel-major, the four frames of a channel are one 64-byte run; frame-major, 128-byte runs per frame.
+// One shared-memory round trip per pass boundary and three barriers per four transforms.
+template <int R3>
+__global__ void __launch_bounds__(256, 2) pfb_fft_kernel(const cd *__restrict__ u, int nf, const cd *__restrict__ tw,
+                                                        cd *__restrict__ out, long out_stride, long frame0, int layout)
+{
+    constexpr int K = 256 * R3, N1 = K / 16;            // N1 = lanes per transform
+    extern __shared__ double smem_raw[];
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *sb = twl + fft_tw_entries(K);                   // [K][4]
+    const int tid = threadIdx.x, f = tid & 3, b = tid >> 2;
+    const int g = blockIdx.x;
+    const bool live = g * PF + f < nf;                  // ragged last group: the thread still takes part in barriers
+    fft_stage_twiddles(twl, tw, K);
+    auto slot = [f](int i) { return 4 * (i ^ ((i >> 4) & 1)) + f; };
+    cd v[16];
+    // ---- pass 1: len K, stride 1, butterfly p = b
+    {
+        const cd *src = u + ((size_t)g * PF + f) * K + b;
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = live ? src[j * N1] : make_double2(0.0, 0.0);
+        dft16(v, -1.0);
+        __syncthreads();                                // twiddle store staged
+        if (b != 0) {
+            const cd w1 = fft_tw(twl, b, -1), w2 = fft_tw(twl, 2 * b, -1), w4 = fft_tw(twl, 4 * b, -1), w8 = fft_tw(twl, 8 * b, -1);
+            v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[4] = cmul(v[4], w4); v[8] = cmul(v[8], w8);
+            const cd w3 = cmul(w1, w2); v[3] = cmul(v[3], w3);
+            const cd w5 = cmul(w1, w4); v[5] = cmul(v[5], w5);
+            const cd w6 = cmul(w2, w4); v[6] = cmul(v[6], w6);
+            const cd w7 = cmul(w3, w4); v[7] = cmul(v[7], w7);
+            v[9] = cmul(v[9], cmul(w1, w8)); v[10] = cmul(v[10], cmul(w2, w8)); v[11] = cmul(v[11], cmul(w3, w8));
+            v[12] = cmul(v[12], cmul(w4, w8)); v[13] = cmul(v[13], cmul(w5, w8)); v[14] = cmul(v[14], cmul(w6, w8));
+            v[15] = cmul(v[15], cmul(w7, w8));
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) sb[slot(16 * b + k)] = v[k];
+    }
+    __syncthreads();
+    // ---- pass 2: len K/16, stride 16, butterfly (p, q) = (b / 16, b % 16)
+    {
+        const int p = b >> 4, q = b & 15;
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = sb[slot(q + 16 * (p + R3 * j))];
+        dft16(v, -1.0);
+        if (R3 > 1 && p != 0) {
+            const int pt = p * 16;                      // index step K / len = 16
+            const cd w1 = fft_tw(twl, pt, -1), w2 = fft_tw(twl, 2 * pt, -1), w4 = fft_tw(twl, 4 * pt, -1), w8 = fft_tw(twl, 8 * pt, -1);
+            v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[4] = cmul(v[4], w4); v[8] = cmul(v[8], w8);
+            const cd w3 = cmul(w1, w2); v[3] = cmul(v[3], w3);
+            const cd w5 = cmul(w1, w4); v[5] = cmul(v[5], w5);
+            const cd w6 = cmul(w2, w4); v[6] = cmul(v[6], w6);
+            const cd w7 = cmul(w3, w4); v[7] = cmul(v[7], w7);
+            v[9] = cmul(v[9], cmul(w1, w8)); v[10] = cmul(v[10], cmul(w2, w8)); v[11] = cmul(v[11], cmul(w3, w8));
+            v[12] = cmul(v[12], cmul(w4, w8)); v[13] = cmul(v[13], cmul(w5, w8)); v[14] = cmul(v[14], cmul(w6, w8));
+            v[15] = cmul(v[15], cmul(w7, w8));
+        }
+        if (R3 > 1) {
+            __syncthreads();                            // every butterfly has read its inputs
+#pragma unroll
+            for (int k = 0; k < 16; k++) sb[slot(q + 256 * p + 16 * k)] = v[k];
+            __syncthreads();
+            // ---- pass 3: len R3, stride 256: butterfly bb = b + N1 t reads bb + 256 j
+#pragma unroll
+            for (int t = 0; t < 16 / R3; t++) {
+                const int bb = b + N1 * t;
+#pragma unroll
+                for (int j = 0; j < R3; j++) v[t * R3 + j] = sb[slot(bb + 256 * j)];
+                if (R3 == 2) {
+                    const cd a0 = v[t * 2], a1 = v[t * 2 + 1];
+                    v[t * 2] = cadd(a0, a1); v[t * 2 + 1] = csub(a0, a1);
+                } else {
+                    bfly4(v[t * 4], v[t * 4 + 1], v[t * 4 + 2], v[t * 4 + 3], -1.0, v[t * 4], v[t * 4 + 1], v[t * 4 + 2], v[t * 4 + 3]);
+                }
+            }
+        }
+    }
+    if (!live) return;
+    // ---- results: v[t R3 + k] = X[b + N1 t + 256 k]  (R3 = 1: v[k] = X[b + 16 k])
+    const long fr = frame0 + (long)g * PF + f;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int ch = R3 == 1 ? b + 16 * e : b + N1 * (e / R3) + 256 * (e % R3);
+        if (layout == 0) out[(size_t)ch * out_stride + fr] = v[e];
+        else out[(size_t)fr * out_stride + ch] = v[e];
+    }
+}
+
 struct Channelizer {
     int K = 0, D = 0, T = 0, P = 0, smax = 0;
     double *d_taps = nullptr;
@@ -113,6 +334,9 @@ struct Channelizer {
     long long n_abs = 0;
     const cd *tw = nullptr;
     int n_sm = 148;
+    int slice_frames = 2048;        // frames of u per kernel pair (L2-resident intermediate)
+    int force_generic = 0;
+    cd *d_u = nullptr; int u_frames = 0;
 
     int init(int K_, int D_, const double *proto, int T_)
     {
@@ -139,6 +363,8 @@ struct Channelizer {
     void release()
     {
         if (d_taps) cudaFree(d_taps);
+        if (d_u) cudaFree(d_u);
+        d_u = nullptr; u_frames = 0;
         for (int i = 0; i < 2; i++) if (d_hist[i]) cudaFree(d_hist[i]);
         d_taps = nullptr; d_hist[0] = d_hist[1] = nullptr;
     }
@@ -170,14 +396,71 @@ struct Channelizer {
         pfb_kernel<PP, SM><<<grid, dim3(K / 16, 4), sh, s>>>(p);
         return QC_OK;
     }
+    template <int PP, int OVS> int launch_fir(const PfbFirParams &q, dim3 grid, cudaStream_t s)
+    {
+        pfb_fir_kernel<PP, OVS><<<grid, 128, 0, s>>>(q);
+        return QC_OK;
+    }
+    // D = K or K/2: slices of (register FIR kernel, transform kernel)
+    int process_fast(const cd *d_in, int count, cd *d_out, long out_stride, int layout, int nf, cudaStream_t s)
+    {
+        const int ovs = K / D;
+        int sf = slice_frames < PF ? PF : (slice_frames / PF) * PF;
+        if (sf > nf) sf = ((nf + PF - 1) / PF) * PF;
+        if (sf > u_frames) {
+            if (d_u) cudaFree(d_u);
+            d_u = nullptr; u_frames = 0;
+            QC_CUDA(cudaMalloc((void **)&d_u, (size_t)sf * K * sizeof(cd)));
+            u_frames = sf;
+        }
+        const size_t sh = ((size_t)fft_tw_entries(K) + (size_t)PF * K) * sizeof(cd);
+        if (sh > 48 * 1024) {
+            if (K == 1024) QC_CUDA(cudaFuncSetAttribute(pfb_fft_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            if (K == 512) QC_CUDA(cudaFuncSetAttribute(pfb_fft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        }
+        const long long m0 = n_abs / D;
+        for (int f0 = 0; f0 < nf; f0 += sf) {
+            const int nfs = nf - f0 < sf ? nf - f0 : sf;
+            PfbFirParams q;
+            q.in = d_in; q.count = count; q.hist = d_hist[cur]; q.H = T; q.n0 = n_abs; q.f0 = m0 + f0; q.nf = nfs;
+            q.K = K; q.D = D; q.taps = d_taps; q.u = d_u;
+            // frame ranges: enough CTAs to fill the machine three deep, at least 2 P frames each
+            const int bx = K / PFB_BR;
+            int S = (n_sm * 4 + bx - 1) / bx;
+            const int min_fs = 2 * P * ovs;
+            if (S > (nfs + min_fs - 1) / min_fs) S = (nfs + min_fs - 1) / min_fs;
+            if (S < 1) S = 1;
+            int fs = (nfs + S - 1) / S;
+            fs += fs & 1;
+            q.fs = fs;
+            S = (nfs + fs - 1) / fs;
+            int rc = QC_EINVAL;
+#define PFB_FIR(PP) case PP: rc = ovs == 2 ? launch_fir<PP, 2>(q, dim3(bx, S), s) : launch_fir<PP, 1>(q, dim3(bx, S), s); break;
+            switch (P) { PFB_FIR(4) PFB_FIR(8) PFB_FIR(16) PFB_FIR(32) }
+#undef PFB_FIR
+            if (rc != QC_OK) return rc;
+            count_launch();
+            QC_CUDA_LAUNCH();
+            const int gf = (nfs + PF - 1) / PF;
+            if (K == 1024) pfb_fft_kernel<4><<<gf, K / 4, sh, s>>>(d_u, nfs, tw, d_out, out_stride, f0, layout);
+            else if (K == 512) pfb_fft_kernel<2><<<gf, K / 4, sh, s>>>(d_u, nfs, tw, d_out, out_stride, f0, layout);
+            else pfb_fft_kernel<1><<<gf, K / 4, sh, s>>>(d_u, nfs, tw, d_out, out_stride, f0, layout);
+            count_launch();
+            QC_CUDA_LAUNCH();
+        }
+        return QC_OK;
+    }
     int process(const cd *d_in, int count, cd *d_out, long out_stride, int layout, int *n_frames, cudaStream_t s)
     {
-        if (count < 0) { set_error("pfb_process: negative count"); return QC_EINVAL; }
+        if (count < 0 || count > (1 << 30)) { set_error("pfb_process: count must be in [0, 2^30]"); return QC_EINVAL; }
         const int nf = frames(count);
         if (n_frames) *n_frames = nf;
         if (count == 0) return QC_OK;
-        if (nf > 0) {
-            if (layout == 0 ? out_stride < nf : out_stride < K) { set_error("pfb_process: out_stride %ld too small", out_stride); return QC_EINVAL; }
+        if (nf > 0 && (layout == 0 ? out_stride < nf : out_stride < K)) { set_error("pfb_process: out_stride %ld too small", out_stride); return QC_EINVAL; }
+        if (nf > 0 && !force_generic && (D == K || 2 * D == K)) {
+            int rc = process_fast(d_in, count, d_out, out_stride, layout, nf, s);
+            if (rc != QC_OK) return rc;
+        } else if (nf > 0) {
             PfbParams p;
             p.in = d_in; p.count = count; p.hist = d_hist[cur]; p.H = T; p.n0 = n_abs; p.m0 = n_abs / D; p.n_frames = nf;
             p.K = K; p.D = D; p.T = T; p.lgK = fft_log2(K); p.taps = d_taps; p.tw = tw; p.out = d_out; p.out_stride = out_stride; p.layout = layout;
@@ -219,6 +502,16 @@ int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *st
     if (!p || count < 0) return QC_EINVAL;
     if (count == 0) return QC_OK;
     return p->c.roll((const cd *)d_in, count, (cudaStream_t)stream);
+}
+int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value)
+{
+    if (!p) return QC_EINVAL;
+    switch (option) {
+    case QC_PFB_OPT_SLICE_FRAMES: if (value < 4) return QC_EINVAL; p->c.slice_frames = value; return QC_OK;
+    case QC_PFB_OPT_GENERIC: p->c.force_generic = value ? 1 : 0; return QC_OK;
+    }
+    qc::set_error("pfb_set_option: unknown option %d", option);
+    return QC_EINVAL;
 }
 int quisk_cuda_pfb_process(qcChannelizer *p, const void *d_in, int count, void *d_out, long out_stride, int layout,
                            int *n_frames, void *stream)

@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_pfb_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]; lib.quisk_cuda_pfb_create.restype = vp
     lib.quisk_cuda_pfb_destroy.argtypes = [vp]; lib.quisk_cuda_pfb_destroy.restype = None
     lib.quisk_cuda_pfb_count_out.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_pfb_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.quisk_cuda_pfb_seek.argtypes = [vp, C.c_longlong]
     lib.quisk_cuda_pfb_prime.argtypes = [vp, vp, C.c_int, vp]
     lib.quisk_cuda_pfb_process.argtypes = [vp, vp, C.c_int, vp, C.c_long, C.c_int, c_int_p, vp]

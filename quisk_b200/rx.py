@@ -142,6 +142,9 @@ class Channelizer:
 
     def count_out(self, count: int) -> int: return self.lib.quisk_cuda_pfb_count_out(self.h, count)
 
+    def set_option(self, option: int, value: int):
+        L.check(self.lib, self.lib.quisk_cuda_pfb_set_option(self.h, option, value), "pfb_set_option")
+
     def seek(self, n_abs: int): L.check(self.lib, self.lib.quisk_cuda_pfb_seek(self.h, n_abs), "pfb_seek")
 
     def prime(self, d_in: int, count: int, stream: int = 0):
