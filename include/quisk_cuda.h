@@ -167,7 +167,8 @@ int quisk_cuda_batch_reset(qcBatchFilter *f, void *stream);
 typedef struct qcRxChain qcRxChain;
 
 enum qcRxMode {     /* values of rx_mode_type, quisk.h:56-70 */
-    QC_MODE_CWL = 0, QC_MODE_CWU = 1, QC_MODE_LSB = 2, QC_MODE_USB = 3, QC_MODE_AM = 4, QC_MODE_FM = 5
+    QC_MODE_CWL = 0, QC_MODE_CWU = 1, QC_MODE_LSB = 2, QC_MODE_USB = 3, QC_MODE_AM = 4, QC_MODE_FM = 5,
+    QC_MODE_DGT_U = 7, QC_MODE_DGT_L = 8, QC_MODE_DGT_IQ = 9, QC_MODE_FDV_U = 11, QC_MODE_FDV_L = 12
 };
 
 /* The reference keeps its decimation / audio coefficient tables in filters.h;
@@ -199,6 +200,10 @@ struct qcRxConfig {
     const double *tune_hz;      /* per-channel rx_tune_freq in Hz (HOST, n_channels) or NULL = no tuning */
     struct qcRxTables tables;
     int fused;                  /* 1 = fused shared-memory cascade kernels, 0 = one kernel per stage */
+    int filter_bandwidth;       /* filter_bandwidth[nFilter] in Hz (set_filters, quisk.c:4551).  Only the digital modes look
+                                 * at it: DGT-U/L and FDV-U/L filter at 6 kS/s below DGT_NARROW_FREQ = 3000 (quisk.c:2089) and at
+                                 * 48 kS/s otherwise; DGT-IQ skips its filter at >= 19000 (quisk.c:2144).  DGT-IQ returns complex
+                                 * samples: d_audio then holds (re, im) pairs, *n_audio counts pairs, audio_stride counts doubles. */
 };
 
 qcRxChain *quisk_cuda_rx_create(const struct qcRxConfig *cfg);
@@ -219,6 +224,11 @@ int quisk_cuda_rx_process(qcRxChain *rx, const void *d_iq, long iq_stride, int c
 /* Same through HOST buffers: H2D copy of the block, the chain, D2H copy of the audio. */
 int quisk_cuda_rx_process_host(qcRxChain *rx, const quisk_cd *h_iq, long iq_stride, int count,
                                double *h_audio, long audio_stride, int *n_audio);
+/* Same with the host block still in its wire format (see section 3e): `bytes` per component, (I, Q) packed,
+ * unpacked on the device exactly as add_rx_samples does on the host (quisk.c:2922-2953).  h_bytes:
+ * [n_channels][byte_stride] bytes.  The H2D copy then carries 2*bytes per sample instead of 16. */
+int quisk_cuda_rx_process_host_packed(qcRxChain *rx, const void *h_bytes, long byte_stride, int count, int bytes, int big_endian,
+                                      double *h_audio, long audio_stride, int *n_audio);
 int quisk_cuda_rx_reset(qcRxChain *rx);
 /* Tuning knobs and instrumentation (not part of the reference's interface). */
 #define QC_RX_OPT_TIMING       1   /* value != 0: record CUDA events around the dominant (fused) kernel */
@@ -288,6 +298,20 @@ void quisk_cuda_fracdecim_destroy(qcFracDecim *f);
 int quisk_cuda_fracdecim_run(qcFracDecim *f, const void *d_in, long in_stride, int count, double fdecim,
                              void *d_out, long out_stride, int *n_out, void *stream);
 
+/* ---- 3e. wire-format ingest: received bytes -> complex double on the device ----
+ * quisk_cuda_unpack_iq: add_rx_samples (quisk.c:2922-2953).  d_bytes [n_channels][byte_stride]: packed (I, Q)
+ * pairs, `bytes` = 1..4 per component, little endian (big_endian = 0) or big endian; each component is
+ * left-justified into an int32 and converted int -> float -> double like the reference's `ii + qq * I`
+ * (4-byte samples therefore keep 24 significant bits, as they do in Quisk).  d_out [n_channels][out_stride] quisk_cd.
+ * quisk_cuda_unpack_hermes: the record loop of read_rx_udp10 (quisk.c:3631,3746-3763).  d_packets = n_packets
+ * consecutive 1032-byte Metis payloads with n_rx = 1 + quisk_multirx_count receivers; receiver r goes to
+ * d_out[r * out_stride + sample]; *n_samples = n_packets * quisk_cuda_hermes_samples_per_packet(n_rx).  Sequence
+ * numbers, sync bytes and the C0..C4 control bytes stay the host's business (quisk.c:3620-3744). */
+int quisk_cuda_unpack_iq(const void *d_bytes, long byte_stride, int n_channels, int count, int bytes, int big_endian,
+                         void *d_out, long out_stride, void *stream);
+int quisk_cuda_hermes_samples_per_packet(int n_rx);
+int quisk_cuda_unpack_hermes(const void *d_packets, int n_packets, int n_rx, void *d_out, long out_stride, int *n_samples, void *stream);
+
 /* ---- wideband polyphase channelizer (configuration C5) ----
  * One wideband stream -> n_channels receivers, receiver k centred on k*fs/n_channels, each decimated by `decim`
  * through the prototype low-pass `proto` (n_taps real taps, a multiple of n_channels).  Output k equals the
@@ -306,6 +330,7 @@ int quisk_cuda_pfb_seek(qcChannelizer *p, long long n_abs);
 int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *stream);
 #define QC_PFB_OPT_SLICE_FRAMES 1   /* frames of the branch-FIR intermediate per kernel pair (default 2048; keeps it in L2) */
 #define QC_PFB_OPT_GENERIC      2   /* 1: force the single generic kernel (the only path when decim is not n_channels or n_channels/2) */
+#define QC_PFB_OPT_PIPELINE     3   /* 1: overlap the branch FIRs of slice i+1 with the transforms of slice i (two internal streams) */
 int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value);
 int quisk_cuda_pfb_process(qcChannelizer *p, const void *d_in, int count, void *d_out, long out_stride, int layout,
                            int *n_frames, void *stream);

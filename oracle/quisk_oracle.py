@@ -361,15 +361,23 @@ class ProcessDemodulate:
     """quisk_process_demodulate (quisk.c:1848-2160) for the modes on the hot
     path: CWL/CWU (/8 -> 6 k), LSB/USB (/4 -> 12 k), AM (/2 -> 24 k, |x| + DC
     block, 36-tap audio FIR), FM (48 k, arg(x conj(x_-1)), x 20e5, one-pole
-    de-emphasis, /4, high-pass FIR, x4).  The optional auto-notch / SSB squelch
+    de-emphasis, /4, high-pass FIR, x4), DGT-U/L and FDV-U/L (CW's structure below
+    3000 Hz bandwidth, else the I/Q filter at 48 k), DGT-IQ (real-tap filter, complex out).  The optional auto-notch / SSB squelch
     are off, as they are by default in the reference.  Returns real audio at 48 k."""
 
-    def __init__(self, mode: str, filt_i, filt_q, tables: dict):
+    def __init__(self, mode: str, filt_i, filt_q, tables: dict, bandwidth: int = 2800):
         T = tables
         self.mode = mode
         self.pre = []
         self.post = []
-        if mode in ("CWL", "CWU"):
+        if mode in ("DGT-U", "DGT-L", "FDV-U", "FDV-L"):        # quisk.c:2087-2140
+            if bandwidth < 3000:                                # DGT_NARROW_FREQ, quisk.c:52
+                self.pre = [HB45Decim(), HB45Decim(), FirDecim(T["quiskFilt48dec24Coefs"], 2)]
+                self.post = [FirInterp(T["quiskAudio24p4Coefs"], 2, np.float64), HB45Interp(), HB45Interp()]
+            self.rx = RxFilterC(filt_i, filt_q)
+        elif mode == "DGT-IQ":                                  # quisk.c:2141-2153
+            self.rx = RxFilterD(filt_i) if bandwidth < 19000 else (lambda x: x)
+        elif mode in ("CWL", "CWU"):
             self.pre = [HB45Decim(), HB45Decim(), FirDecim(T["quiskFilt48dec24Coefs"], 2)]
             self.rx = RxFilterC(filt_i, filt_q)
             self.post = [FirInterp(T["quiskAudio24p4Coefs"], 2, np.float64), HB45Interp(), HB45Interp()]
@@ -402,10 +410,12 @@ class ProcessDemodulate:
         for s in self.pre:
             x = s(x)
         cx = self.rx(x)
-        if self.mode in ("CWL", "LSB"):
-            d = cx.real + cx.imag                       # quisk.c:1916,1962
-        elif self.mode in ("CWU", "USB"):
-            d = cx.real - cx.imag                       # quisk.c:1939,1986
+        if self.mode == "DGT-IQ":
+            return cx                                   # complex out
+        if self.mode in ("CWL", "LSB", "DGT-L", "FDV-L"):
+            d = cx.real + cx.imag                       # quisk.c:1916,1962,2127
+        elif self.mode in ("CWU", "USB", "DGT-U", "FDV-U"):
+            d = cx.real - cx.imag                       # quisk.c:1939,1986,2100
         elif self.mode == "AM":
             mag = np.abs(cx)                            # quisk.c:2007-2011
             d = np.empty(len(mag))
@@ -622,3 +632,43 @@ def channelizer_oracle(x: np.ndarray, channels, proto: np.ndarray, n_channels: i
         f.decim_index = n0 % decim
         out.append(f(v))
     return np.stack(out)
+
+
+def unpack_iq(data, nbytes: int, big_endian: bool) -> np.ndarray:
+    """add_rx_samples' unpack loops (quisk.c:2922-2953): packed (I, Q) pairs, nbytes = 1..4 per component.
+    Either byte order ends up LEFT-justified in a 32-bit int (little endian: memcpy to the top nbytes of the int,
+    :2927-2933; big endian: first byte to the most significant position, :2944-2950).  The store is
+    `ii + qq * I` with int operands (:2935,2950): C's `I` is a FLOAT complex, so both ints are converted to float
+    (round to nearest even) before they widen to the complex double buffer -- exact up to 3-byte samples, 4-byte
+    samples keep 24 significant bits."""
+    b = np.frombuffer(bytes(data), dtype=np.uint8).reshape(-1, 2, nbytes).astype(np.uint32)
+    v = np.zeros(b.shape[:2], dtype=np.uint32)
+    for k in range(nbytes):
+        sh = 8 * (3 - k) if big_endian else 8 * (4 - nbytes + k)
+        v |= b[:, :, k] << np.uint32(sh)
+    v = v.view(np.int32).astype(np.float32).astype(np.float64)
+    return v[:, 0] + 1j * v[:, 1]
+
+
+def unpack_hermes(packet, n_rx: int) -> np.ndarray:
+    """The record loop of read_rx_udp10 (quisk.c:3545, 3631, 3746-3763) on one 1032-byte Metis payload:
+    two 512-byte frames at bytes 11 and 523 (after 8 header + 3 sync bytes), 5 control bytes, then
+    504 // (6 n_rx + 2) records of n_rx x [3 bytes -> imaginary, 3 bytes -> real] (24-bit big endian, << 8)
+    and 2 microphone bytes.  Returns [n_rx][2 * records]."""
+    buf = np.frombuffer(bytes(packet), dtype=np.uint8).astype(np.int64)
+    nrec = 504 // (n_rx * 6 + 2)
+    out = np.zeros((n_rx, 2 * nrec), dtype=np.complex128)
+    n = 0
+    for start in (11, 523):
+        index = start + 5
+        for _ in range(nrec):
+            for r in range(n_rx):
+                xi = (buf[index] << 24 | buf[index + 1] << 16 | buf[index + 2] << 8)
+                xr = (buf[index + 3] << 24 | buf[index + 4] << 16 | buf[index + 5] << 8)
+                xi = xi - (1 << 32) if xi >= (1 << 31) else xi
+                xr = xr - (1 << 32) if xr >= (1 << 31) else xr
+                out[r, n] = float(xr) + 1j * float(xi)
+                index += 6
+            n += 1
+            index += 2
+    return out

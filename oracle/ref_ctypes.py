@@ -55,7 +55,8 @@ TABLES = {   # filter.h:57-86
     "quiskFilt300D6Coefs": 248, "quiskFilt240D4Coefs": 100, "quiskDiff48Coefs": 38,
 }
 
-MODES = {"CWL": 0, "CWU": 1, "LSB": 2, "USB": 3, "AM": 4, "FM": 5}   # quisk.h:56-70
+MODES = {"CWL": 0, "CWU": 1, "LSB": 2, "USB": 3, "AM": 4, "FM": 5,
+         "DGT-U": 7, "DGT-L": 8, "DGT-IQ": 9, "FDV-U": 11, "FDV-L": 12}   # quisk.h:56-70
 
 
 def have_ref(name: str = "libquisk_filter_ref.so") -> bool:

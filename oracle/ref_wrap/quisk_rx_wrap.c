@@ -13,7 +13,9 @@
  * Extracted ranges (quisk.c):  46-53 constants, 68-81 struct AgcState,
  * 622-665 cFracDecim, 1182-1256 dRxFilterOut/cRxFilterOut,
  * 1633-1671 PlanDecimation, 1673-1846 quisk_process_decimate,
- * 1848-2160 quisk_process_demodulate, 2162-2287 process_agc.
+ * 1848-2160 quisk_process_demodulate, 2162-2287 process_agc,
+ * 2922-2953 the two sample-unpack branches of add_rx_samples,
+ * 3746-3763 the 24-bit record loop of read_rx_udp10 (Hermes protocol 1).
  */
 #include <Python.h>
 #include <stdlib.h>
@@ -113,3 +115,42 @@ void *ref_agc_new(double max_out, int sample_rate)
 void ref_agc_set(double release_gain, double release_time) { agcReleaseGain = release_gain; agc_release_time = release_time; }
 void ref_agc_run(void *s, complex double *cs, int n, int is_cpx) { process_agc((struct AgcState *)s, cs, n, is_cpx); }
 double ref_agc_gain(void *s) { return ((struct AgcState *)s)->gain; }
+
+
+/* ---- wire-format ingest: the loops that turn received bytes into complex double ----
+ * add_rx_samples (quisk.c:2894-2956) is a Python method; its two unpack branches (2922-2953) only touch the
+ * variables declared here.  The `if (0) {}` supplies the head of the reference's if / else-if chain. */
+static int py_sample_rx_bytes = 2;
+static int py_sample_rx_endian;
+static complex double PySampleBuf[SAMP_BUFFER_SIZE];
+static int PySampleCount;
+int ref_add_rx_samples(void *data, long len, int bytes, int big_endian, complex double *out)
+{
+    struct { void *buf; long len; } view = { data, len };
+    int ii, qq, i;
+    unsigned char *pt_ii, *pt_qq;
+    py_sample_rx_bytes = bytes; py_sample_rx_endian = big_endian; PySampleCount = 0;
+    if (0) {}
+#include "quisk_unpack_py.inc"
+    memcpy(out, PySampleBuf, PySampleCount * sizeof(complex double));
+    return PySampleCount;
+}
+
+/* read_rx_udp10 (quisk.c:3526-3790): per 1032-byte packet two 512-byte frames starting at byte 11 (after the
+ * 8-byte header and 3 sync bytes); the extracted loop reads num_records records of (1 + multirx) receivers. */
+int quisk_multirx_count;
+static complex double *multirx_cSamples[16];
+static struct { int index; complex double *samples; } multirx_fft_data[16];
+static int multirx_fft_width;       /* 0: the panadapter side copy stays off */
+int ref_hermes_unpack(unsigned char *buf, int multirx, complex double *samp, complex double *sub /* [multirx][126] */)
+{
+    int i, j, xr, xi, index, start, nSamples = 0, num_records;
+    complex double c;
+    quisk_multirx_count = multirx;
+    num_records = 504 / ((quisk_multirx_count + 1) * 6 + 2);       /* quisk.c:3545 */
+    for (j = 0; j < multirx; j++) multirx_cSamples[j] = sub + j * 126;
+    for (start = 11; start < 1000; start += 512) {                  /* quisk.c:3631 */
+#include "quisk_unpack_hermes.inc"
+    }
+    return nSamples;
+}

@@ -336,7 +336,10 @@ struct Channelizer {
     int n_sm = 148;
     int slice_frames = 2048;        // frames of u per kernel pair (L2-resident intermediate)
     int force_generic = 0;
-    cd *d_u = nullptr; int u_frames = 0;
+    cd *d_u = nullptr; int u_frames = 0;    // two slices of u back to back
+    int pipeline = 0;               // 1: branch FIRs of slice i+1 overlap the transforms of slice i on two internal streams
+    cudaStream_t sa = nullptr, sb = nullptr;
+    cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_fft[2] = {nullptr, nullptr}, ev_edge = nullptr;
 
     int init(int K_, int D_, const double *proto, int T_)
     {
@@ -410,8 +413,25 @@ struct Channelizer {
         if (sf > u_frames) {
             if (d_u) cudaFree(d_u);
             d_u = nullptr; u_frames = 0;
-            QC_CUDA(cudaMalloc((void **)&d_u, (size_t)sf * K * sizeof(cd)));
+            QC_CUDA(cudaMalloc((void **)&d_u, (size_t)2 * sf * K * sizeof(cd)));
             u_frames = sf;
+        }
+        const bool pipe = pipeline && nf > sf;
+        cudaStream_t s_fir = s, s_fft = s;
+        if (pipe) {
+            if (!sa) {
+                QC_CUDA(cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking));
+                QC_CUDA(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; i++) {
+                    QC_CUDA(cudaEventCreateWithFlags(&ev_fir[i], cudaEventDisableTiming));
+                    QC_CUDA(cudaEventCreateWithFlags(&ev_fft[i], cudaEventDisableTiming));
+                }
+                QC_CUDA(cudaEventCreateWithFlags(&ev_edge, cudaEventDisableTiming));
+            }
+            QC_CUDA(cudaEventRecord(ev_edge, s));
+            QC_CUDA(cudaStreamWaitEvent(sa, ev_edge, 0));
+            QC_CUDA(cudaStreamWaitEvent(sb, ev_edge, 0));
+            s_fir = sa; s_fft = sb;
         }
         const size_t sh = ((size_t)fft_tw_entries(K) + (size_t)PF * K) * sizeof(cd);
         if (sh > 48 * 1024) {
@@ -419,11 +439,13 @@ struct Channelizer {
             if (K == 512) QC_CUDA(cudaFuncSetAttribute(pfb_fft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         }
         const long long m0 = n_abs / D;
-        for (int f0 = 0; f0 < nf; f0 += sf) {
+        for (int f0 = 0, si = 0; f0 < nf; f0 += sf, si++) {
             const int nfs = nf - f0 < sf ? nf - f0 : sf;
+            cd *ub = d_u + (size_t)(pipe ? (si & 1) : 0) * u_frames * K;
+            if (pipe && si >= 2) QC_CUDA(cudaStreamWaitEvent(sa, ev_fft[si & 1], 0));       // the slice buffer is free again
             PfbFirParams q;
             q.in = d_in; q.count = count; q.hist = d_hist[cur]; q.H = T; q.n0 = n_abs; q.f0 = m0 + f0; q.nf = nfs;
-            q.K = K; q.D = D; q.taps = d_taps; q.u = d_u;
+            q.K = K; q.D = D; q.taps = d_taps; q.u = ub;
             // frame ranges: enough CTAs to fill the machine three deep, at least 2 P frames each
             const int bx = K / PFB_BR;
             int S = (n_sm * 4 + bx - 1) / bx;
@@ -435,18 +457,24 @@ struct Channelizer {
             q.fs = fs;
             S = (nfs + fs - 1) / fs;
             int rc = QC_EINVAL;
-#define PFB_FIR(PP) case PP: rc = ovs == 2 ? launch_fir<PP, 2>(q, dim3(bx, S), s) : launch_fir<PP, 1>(q, dim3(bx, S), s); break;
+#define PFB_FIR(PP) case PP: rc = ovs == 2 ? launch_fir<PP, 2>(q, dim3(bx, S), s_fir) : launch_fir<PP, 1>(q, dim3(bx, S), s_fir); break;
             switch (P) { PFB_FIR(4) PFB_FIR(8) PFB_FIR(16) PFB_FIR(32) }
 #undef PFB_FIR
             if (rc != QC_OK) return rc;
             count_launch();
             QC_CUDA_LAUNCH();
+            if (pipe) { QC_CUDA(cudaEventRecord(ev_fir[si & 1], sa)); QC_CUDA(cudaStreamWaitEvent(sb, ev_fir[si & 1], 0)); }
             const int gf = (nfs + PF - 1) / PF;
-            if (K == 1024) pfb_fft_kernel<4><<<gf, K / 4, sh, s>>>(d_u, nfs, tw, d_out, out_stride, f0, layout);
-            else if (K == 512) pfb_fft_kernel<2><<<gf, K / 4, sh, s>>>(d_u, nfs, tw, d_out, out_stride, f0, layout);
-            else pfb_fft_kernel<1><<<gf, K / 4, sh, s>>>(d_u, nfs, tw, d_out, out_stride, f0, layout);
+            if (K == 1024) pfb_fft_kernel<4><<<gf, K / 4, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout);
+            else if (K == 512) pfb_fft_kernel<2><<<gf, K / 4, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout);
+            else pfb_fft_kernel<1><<<gf, K / 4, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout);
             count_launch();
             QC_CUDA_LAUNCH();
+            if (pipe) QC_CUDA(cudaEventRecord(ev_fft[si & 1], sb));
+        }
+        if (pipe) {
+            QC_CUDA(cudaEventRecord(ev_edge, sa)); QC_CUDA(cudaStreamWaitEvent(s, ev_edge, 0));
+            QC_CUDA(cudaEventRecord(ev_edge, sb)); QC_CUDA(cudaStreamWaitEvent(s, ev_edge, 0));
         }
         return QC_OK;
     }
@@ -509,6 +537,7 @@ int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value)
     switch (option) {
     case QC_PFB_OPT_SLICE_FRAMES: if (value < 4) return QC_EINVAL; p->c.slice_frames = value; return QC_OK;
     case QC_PFB_OPT_GENERIC: p->c.force_generic = value ? 1 : 0; return QC_OK;
+    case QC_PFB_OPT_PIPELINE: p->c.pipeline = value ? 1 : 0; return QC_OK;
     }
     qc::set_error("pfb_set_option: unknown option %d", option);
     return QC_EINVAL;

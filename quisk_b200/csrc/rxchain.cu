@@ -129,10 +129,30 @@ int RxChain::init(const qcRxConfig &cfg)
         QC_CUDA(cudaMalloc((void **)&d_fm, (size_t)C * 4 * sizeof(double)));
         { int rcf = reset_fm(); if (rcf != QC_OK) return rcf; }
         break; }
+    case QC_MODE_DGT_U: case QC_MODE_DGT_L: case QC_MODE_FDV_U: case QC_MODE_FDV_L:        // quisk.c:2087-2140
+        if (cfg.filter_bandwidth < 3000) {      // DGT_NARROW_FREQ, quisk.c:52: filter at 6 kS/s like CW
+            filter_srate = decim_srate / 8;
+            ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+            ADD(cst, mk(QC_C_DECIM2_HB45, C, nullptr, 0, 1, 1));
+            ADD(cst, mk(QC_C_DECIMATE, C, T.filt48dec24, T.n_filt48dec24, 1, 2));
+            rxf = mk(QC_C_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
+            ADD(rst, mk(QC_D_INTERPOLATE, C, T.audio24p4, T.n_audio24p4, 2, 1));
+            ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+            ADD(rst, mk(QC_D_INTERP2_HB45, C, nullptr, 0, 1, 1));
+        } else {                                // filter at 48 kS/s, no audio resampling
+            filter_srate = decim_srate;
+            rxf = mk(QC_C_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
+        }
+        break;
+    case QC_MODE_DGT_IQ:                        // quisk.c:2141-2153: complex out, real-tap filter unless very wide
+        filter_srate = decim_srate;
+        iq_out = true;
+        if (cfg.filter_bandwidth < 19000) rxf = mk(QC_D_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
+        break;
     default:
         set_error("rx_create: mode %d is not on the accelerated path", mode); return QC_EINVAL;
     }
-    if (!rxf) return QC_EINVAL;
+    if (!rxf && !iq_out) return QC_EINVAL;
     // ---- tuning NCO ----------------------------------------------------------------
     if (cfg.tune_hz) {
         tune_hz.assign(cfg.tune_hz, cfg.tune_hz + C);
@@ -213,7 +233,10 @@ int RxChain::max_out(int count) const
         default: n = n / f->decim + 1; break;
         }
     }
-    return (int)n + 8;
+    if (iq_out) n = 2 * n;                      // (re, im) pairs, counted in doubles
+    int r = (int)n + 8;
+    if (iq_out) r += r & 1;
+    return r;
 }
 
 int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audio, long audio_stride, int *n_audio,
@@ -254,6 +277,17 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
         if (n_decim) *n_decim = n;
     }
     int no = 0;
+    if (iq_out) {                               // DGT-IQ: (re, im) pairs straight into the caller's buffer
+        if (audio_stride < 2L * n || (audio_stride & 1)) { set_error("rx_process: DGT-IQ needs an even audio_stride >= 2 * samples"); return QC_EINVAL; }
+        if (rxf) { rc = rxf->run(cur, stride, n, d_audio, audio_stride / 2, &no, 0, s); if (rc != QC_OK) return rc; }
+        else {
+            QC_CUDA(cudaMemcpy2DAsync(d_audio, (size_t)audio_stride * sizeof(double), cur, (size_t)stride * sizeof(cd),
+                                      (size_t)n * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
+            no = n;
+        }
+        if (n_audio) *n_audio = no;
+        return QC_OK;
+    }
     if (fused && fused_tail && tail_fusable()) {
         rc = run_tail(cur, stride, n, d_audio, audio_stride, &no, s);
         if (rc == QC_OK) { if (n_audio) *n_audio = no; return QC_OK; }
@@ -263,10 +297,14 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
     rc = rxf->run(cur, stride, n, bufc[pp], cap, &no, 0, s); if (rc != QC_OK) return rc;
     cur = bufc[pp]; n = no;
     // detector -> real audio at the filter rate
-    double *rcur = bufr[0]; int rp = 1;
+    double *rcur = bufr[0]; int rp = 1; long rstride = cap;
+    if (rst.empty()) {                          // wide DGT: the detector output is the audio
+        if (audio_stride < n) { set_error("rx_process: audio_stride too small"); return QC_EINVAL; }
+        rcur = d_audio; rstride = audio_stride;
+    }
     switch (mode) {
-    case QC_MODE_CWL: case QC_MODE_LSB: rc = launch_demod_ssb(cur, cap, rcur, cap, n, C, 1, s); break;
-    case QC_MODE_CWU: case QC_MODE_USB: rc = launch_demod_ssb(cur, cap, rcur, cap, n, C, 0, s); break;
+    case QC_MODE_CWL: case QC_MODE_LSB: case QC_MODE_DGT_L: case QC_MODE_FDV_L: rc = launch_demod_ssb(cur, cap, rcur, rstride, n, C, 1, s); break;
+    case QC_MODE_CWU: case QC_MODE_USB: case QC_MODE_DGT_U: case QC_MODE_FDV_U: rc = launch_demod_ssb(cur, cap, rcur, rstride, n, C, 0, s); break;
     case QC_MODE_AM: rc = launch_am_detect(cur, cap, rcur, cap, n, C, d_dc, s); break;
     case QC_MODE_FM: rc = launch_fm_detect(cur, cap, rcur, cap, n, C, d_fm, fm_a0, fm_a1, fm_b1, s); break;
     }
@@ -290,7 +328,9 @@ int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, doubl
     if (!hs) QC_CUDA(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
     const int mo = max_out(count);
     if (count > host_cap) {
-        if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out); if (h_pin) cudaFreeHost(h_pin);
+        if (d_packed) cudaFree(d_packed);
+    d_packed = nullptr; packed_cap = 0;
+    if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out); if (h_pin) cudaFreeHost(h_pin);
         d_host_in = nullptr; d_host_out = nullptr; h_pin = nullptr;
         host_cap = count; host_out_cap = mo;
         QC_CUDA(cudaMalloc((void **)&d_host_in, (size_t)C * host_cap * sizeof(cd)));
@@ -302,10 +342,11 @@ int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, doubl
     int na = 0;
     int rc = process(d_host_in, host_cap, count, d_host_out, host_out_cap, &na, nullptr, 0, nullptr, hs);
     if (rc != QC_OK) return rc;
-    if (na > audio_stride) { set_error("rx_process_host: audio_stride %ld < %d", audio_stride, na); return QC_EINVAL; }
-    if (na > 0)
+    const int nd = iq_out ? 2 * na : na;        // doubles per channel
+    if (nd > audio_stride) { set_error("rx_process_host: audio_stride %ld < %d", audio_stride, nd); return QC_EINVAL; }
+    if (nd > 0)
         QC_CUDA(cudaMemcpy2DAsync(h_audio, (size_t)audio_stride * sizeof(double), d_host_out, (size_t)host_out_cap * sizeof(double),
-                                  (size_t)na * sizeof(double), C, cudaMemcpyDeviceToHost, hs));
+                                  (size_t)nd * sizeof(double), C, cudaMemcpyDeviceToHost, hs));
     QC_CUDA(cudaStreamSynchronize(hs));
     if (n_audio) *n_audio = na;
     return QC_OK;
@@ -315,7 +356,7 @@ int RxChain::reset()
 {
     for (auto *f : cst) { int rc = f->reset(nullptr); if (rc != QC_OK) return rc; }
     for (auto *f : rst) { int rc = f->reset(nullptr); if (rc != QC_OK) return rc; }
-    int rc = rxf->reset(nullptr); if (rc != QC_OK) return rc;
+    int rc = rxf ? rxf->reset(nullptr) : QC_OK; if (rc != QC_OK) return rc;
     if (d_dc) QC_CUDA(cudaMemset(d_dc, 0, (size_t)C * sizeof(double)));
     if (d_fm) { rc = reset_fm(); if (rc != QC_OK) return rc; }
     if (tune) { rc = upload_nco(); if (rc != QC_OK) return rc; }
@@ -351,6 +392,13 @@ int quisk_cuda_rx_process(qcRxChain *rx, const void *d_iq, long iq_stride, int c
 {
     if (!rx) { qc::set_error("rx_process: null chain"); return QC_EINVAL; }
     return rx->rx.process(d_iq, iq_stride, count, d_audio, audio_stride, n_audio, d_decim, decim_stride, n_decim, (cudaStream_t)stream);
+}
+
+int quisk_cuda_rx_process_host_packed(qcRxChain *rx, const void *h_bytes, long byte_stride, int count, int bytes, int big_endian,
+                                      double *h_audio, long audio_stride, int *n_audio)
+{
+    if (!rx || !h_bytes || !h_audio) { qc::set_error("rx_process_host_packed: null pointer"); return QC_EINVAL; }
+    return rx->rx.process_host_packed(h_bytes, byte_stride, count, bytes, big_endian, h_audio, audio_stride, n_audio);
 }
 
 int quisk_cuda_rx_process_host(qcRxChain *rx, const quisk_cd *h_iq, long iq_stride, int count, double *h_audio,

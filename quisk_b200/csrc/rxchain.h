@@ -6,6 +6,7 @@
 namespace qc {
 
 int plan_decimation(int sample_rate, int *p2, int *p3, int *p5);
+int launch_unpack_iq(const void *d_bytes, long byte_stride, int C, int count, int nb, int big, cd *out, long out_stride, cudaStream_t s);
 
 struct FusedDecimator;      // rxfused.cu
 
@@ -15,6 +16,7 @@ struct RxChain {
     std::vector<BatchFilter *> cst;     // complex stages: process_decimate then the demod pre-filters
     int n_decim_stages = 0;             // how many of cst belong to quisk_process_decimate
     BatchFilter *rxf = nullptr;         // cRxFilterOut / dRxFilterOut
+    bool iq_out = false;                // DGT-IQ: complex samples out, no detector
     std::vector<BatchFilter *> rst;     // real audio stages after the detector
     // tuning NCO
     bool tune = false;
@@ -33,6 +35,7 @@ struct RxChain {
     char *h_pin = nullptr;
     cd *d_host_in = nullptr; double *d_host_out = nullptr;
     int host_cap = 0, host_out_cap = 0;
+    unsigned char *d_packed = nullptr; size_t packed_cap = 0;      // wire-format staging (ingest.cu)
     // fused full-rate decimator
     FusedDecimator *fd = nullptr;
     size_t n_fused_stages = 0;
@@ -57,6 +60,8 @@ struct RxChain {
     int process(const void *d_iq, long iq_stride, int count, double *d_audio, long audio_stride, int *n_audio,
                 void *d_decim, long decim_stride, int *n_decim, cudaStream_t s);
     int process_host(const quisk_cd *h_iq, long iq_stride, int count, double *h_audio, long audio_stride, int *n_audio);
+    int process_host_packed(const void *h_bytes, long byte_stride, int count, int nb, int big,
+                            double *h_audio, long audio_stride, int *n_audio);
     int reset();
     // rxfused.cu
     size_t fusable_prefix(size_t limit);

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(TT) rx_tail_kernel(TailParams P)
 
 bool RxChain::tail_fusable() const
 {
-    if (!(mode == QC_MODE_LSB || mode == QC_MODE_USB || mode == QC_MODE_CWL || mode == QC_MODE_CWU)) return false;
+    if (!(mode == QC_MODE_LSB || mode == QC_MODE_USB || mode == QC_MODE_CWL || mode == QC_MODE_CWU || mode == QC_MODE_DGT_U ||
+          mode == QC_MODE_DGT_L || mode == QC_MODE_FDV_U || mode == QC_MODE_FDV_L)) return false;
     if (!rxf || rxf->kind != QC_C_RXFILTER) return false;
     if (rst.size() < 2 || rst.size() > 3) return false;
     if (rst[0]->kind != QC_D_INTERPOLATE || rst[0]->interp != 2 || (rst[0]->nTaps & 1) || rst[0]->nTaps > 256) return false;
@@ -142,7 +143,7 @@ int RxChain::run_tail(const cd *in, long in_stride, int n, double *out, long out
     P.in = in; P.in_stride = in_stride; P.n = n; P.out = out; P.out_stride = out_stride;
     P.N = rxf->nTaps; P.rx_coef = rxf->d_coef;
     P.rx_hin = (const cd *)rxf->d_hist[rxf->cur]; P.rx_hout = (cd *)rxf->d_hist[rxf->cur ^ 1];
-    P.lower = (mode == QC_MODE_LSB || mode == QC_MODE_CWL) ? 1 : 0;
+    P.lower = (mode == QC_MODE_LSB || mode == QC_MODE_CWL || mode == QC_MODE_DGT_L || mode == QC_MODE_FDV_L) ? 1 : 0;
     BatchFilter *fi = rst[0];
     P.ntap_i = fi->nTaps; P.i_coef = fi->d_coef; P.i_H = fi->H;
     P.i_hin = (const double *)fi->d_hist[fi->cur]; P.i_hout = (double *)fi->d_hist[fi->cur ^ 1];

@@ -24,7 +24,7 @@ class RxTables(C.Structure):        # struct qcRxTables
 class RxConfig(C.Structure):        # struct qcRxConfig
     _fields_ = [("n_channels", C.c_int), ("sample_rate", C.c_int), ("mode", C.c_int),
                 ("filt_i", c_double_p), ("filt_q", c_double_p), ("n_filt", C.c_int),
-                ("tune_hz", c_double_p), ("tables", RxTables), ("fused", C.c_int)]
+                ("tune_hz", c_double_p), ("tables", RxTables), ("fused", C.c_int), ("filter_bandwidth", C.c_int)]
 
 
 # qcRxTables field -> the reference's table name in filters.h
@@ -97,6 +97,10 @@ def load() -> C.CDLL:
     lib.quisk_cuda_fracdecim_create.argtypes = [C.c_int]; lib.quisk_cuda_fracdecim_create.restype = vp
     lib.quisk_cuda_fracdecim_destroy.argtypes = [vp]; lib.quisk_cuda_fracdecim_destroy.restype = None
     lib.quisk_cuda_fracdecim_run.argtypes = [vp, vp, C.c_long, C.c_int, C.c_double, vp, C.c_long, c_int_p, vp]
+    lib.quisk_cuda_unpack_iq.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp]
+    lib.quisk_cuda_hermes_samples_per_packet.argtypes = [C.c_int]
+    lib.quisk_cuda_unpack_hermes.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, c_int_p, vp]
+    lib.quisk_cuda_rx_process_host_packed.argtypes = [vp, vp, C.c_long, C.c_int, C.c_int, C.c_int, vp, C.c_long, c_int_p]
     lib.quisk_cuda_pfb_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int]; lib.quisk_cuda_pfb_create.restype = vp
     lib.quisk_cuda_pfb_destroy.argtypes = [vp]; lib.quisk_cuda_pfb_destroy.restype = None
     lib.quisk_cuda_pfb_count_out.argtypes = [vp, C.c_int]

@@ -9,7 +9,8 @@ import numpy as np
 
 from . import lib as L
 
-MODES = {"CWL": 0, "CWU": 1, "LSB": 2, "USB": 3, "AM": 4, "FM": 5}     # quisk.h:56-70
+MODES = {"CWL": 0, "CWU": 1, "LSB": 2, "USB": 3, "AM": 4, "FM": 5,
+         "DGT-U": 7, "DGT-L": 8, "DGT-IQ": 9, "FDV-U": 11, "FDV-L": 12}     # quisk.h:56-70
 KINDS = {"cDecim2HB45": 1, "cDecimate": 2, "cCDecimate": 3, "dDecimate": 4, "cInterpolate": 5,
          "dInterpolate": 6, "cInterpDecim": 7, "cInterp2HB45": 8, "dInterp2HB45": 9,
          "cRxFilter": 10, "dRxFilter": 11}
@@ -58,11 +59,12 @@ class RxChain:
     """quisk_cuda_rx_*: tune -> quisk_process_decimate -> quisk_process_demodulate for a batch."""
 
     def __init__(self, n_channels: int, sample_rate: int, mode: str, filt_i, filt_q, tables: dict,
-                 tune_hz=None, fused: bool = True):
+                 tune_hz=None, fused: bool = True, bandwidth: int = 2800):
         self.lib = L.require_device()
         self._keep = []
         cfg = L.RxConfig()
         cfg.n_channels = n_channels; cfg.sample_rate = sample_rate; cfg.mode = MODES[mode]; cfg.fused = int(fused)
+        cfg.filter_bandwidth = int(bandwidth)
         fi = np.ascontiguousarray(filt_i, dtype=np.float64); fq = np.ascontiguousarray(filt_q, dtype=np.float64)
         self._keep += [fi, fq]
         cfg.filt_i = _dp(fi); cfg.filt_q = _dp(fq); cfg.n_filt = len(fi)
@@ -98,6 +100,13 @@ class RxChain:
         na = C.c_int(0)
         L.check(self.lib, self.lib.quisk_cuda_rx_process_host(self.h, h_iq.ctypes.data, h_iq.strides[0] // 16, count,
                                                               h_audio.ctypes.data, h_audio.strides[0] // 8, C.byref(na)), "rx_process_host")
+        return na.value
+
+    def process_host_packed(self, h_bytes: np.ndarray, count: int, nbytes: int, big_endian: bool, h_audio: np.ndarray) -> int:
+        """h_bytes: [n_channels, >= count*2*nbytes] uint8 in the wire format of add_rx_samples (quisk.c:2922-2953)."""
+        na = C.c_int(0)
+        L.check(self.lib, self.lib.quisk_cuda_rx_process_host_packed(self.h, h_bytes.ctypes.data, h_bytes.strides[0], count, nbytes, int(big_endian),
+                                                                     h_audio.ctypes.data, h_audio.strides[0] // 8, C.byref(na)), "rx_process_host_packed")
         return na.value
 
     def reset(self): L.check(self.lib, self.lib.quisk_cuda_rx_reset(self.h), "rx_reset")

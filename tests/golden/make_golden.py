@@ -32,6 +32,9 @@ CHAIN_SPLITS = [1, 2, 3, 7, 255, 256, 257, 1000, 4093, 15360, 18766]
 DEMOD_SPLITS = [1, 2, 3, 7, 255, 256, 257, 1000, 4093, 6126]
 RATES = [1536000, 192000, 96000, 48000, 240000, 250000, 960000, 1200000, 111111, 185185]
 DEMOD_TAPS = {"USB": 164, "LSB": 164, "CWU": 390, "CWL": 390, "AM": 77, "FM": 55}
+# digital modes: (fixture name, mode, taps, filter_bandwidth)
+DGT_CASES = [("DGT-U", "DGT-U", 390, 2800), ("DGT-L", "DGT-L", 390, 2800), ("DGT-U-wide", "DGT-U", 164, 3200),
+             ("FDV-L-wide", "FDV-L", 164, 3000), ("DGT-IQ", "DGT-IQ", 77, 2800)]
 
 # (case name, function, seed, real?, table, trailing args, tune)
 FILTER_CASES = [
@@ -113,6 +116,21 @@ def main():
             outs.append(dbuf[:nr].copy()); counts.append(nr)
         ch["demod_%s/y" % mode] = np.concatenate(outs)
         ch["demod_%s/counts" % mode] = np.array(counts)
+    for name, mode, ntap, bw in DGT_CASES:
+        lib = R.load("libquisk_rx_ref.so", private_copy=True)
+        lib.ref_set_sample_rate(48000); lib.ref_init_chain()
+        rng = np.random.default_rng(3)
+        fi = np.ascontiguousarray(rng.standard_normal(ntap) / ntap); fq = np.ascontiguousarray(rng.standard_normal(ntap) / ntap)
+        lib.ref_set_filters(fi.ctypes.data_as(C.c_void_p), fq.ctypes.data_as(C.c_void_p), len(fi), bw, 0)
+        x = O.synth_iq(12000, 10, 1.0)
+        outs, counts, pos = [], [], 0
+        for n in DEMOD_SPLITS:
+            buf = np.zeros(66000, dtype=np.complex128); buf[:n] = x[pos:pos + n]; pos += n
+            dbuf = np.zeros(132000)
+            nr = lib.ref_process_demodulate(buf.ctypes.data_as(C.c_void_p), dbuf.ctypes.data_as(C.c_void_p), n, 0, 0, R.MODES[mode])
+            outs.append(buf[:nr].copy() if mode == "DGT-IQ" else dbuf[:nr].copy()); counts.append(nr)
+        ch["demod_%s/y" % name] = np.concatenate(outs)
+        ch["demod_%s/counts" % name] = np.array(counts)
     # Full C1 chain: 1.536 MS/s, USB, bw 2800 -> MakeFilterCoef's 164-tap I/Q pair (quisk.py:5405-5468)
     fi, fq = O.make_filter_coef(12000, None, 2800, 300 + 2800 // 2, ref_filters.Filters)
     ch["c1/filt_i"] = fi; ch["c1/filt_q"] = fq

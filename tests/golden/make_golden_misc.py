@@ -1,5 +1,5 @@
-"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287) and cFracDecim (quisk.c:622-665)
-from the compiled reference (oracle/_ref/libquisk_rx_ref.so).  Writes tests/golden/misc_kat.npz."""
+"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287), cFracDecim (quisk.c:622-665) and
+the wire-format unpack loops (quisk.c:2922-2953, 3746-3763) from the compiled reference (oracle/_ref/libquisk_rx_ref.so).  Writes tests/golden/misc_kat.npz."""
 import ctypes as C
 import os
 import sys
@@ -21,6 +21,10 @@ def agc_input(n, seed):
     x[n // 4:n // 4 + 300] *= 40.0
     x[n // 2:n // 2 + 50] *= 200.0
     return x
+
+
+def ingest_bytes(seed, n):
+    return np.random.default_rng(seed).integers(0, 256, size=n, dtype=np.uint8)
 
 
 def main():
@@ -53,6 +57,26 @@ def main():
             ys.append(blk[:k].copy()); counts.append(k)
         out["fracdecim_%g/y" % fdecim] = np.concatenate(ys)
         out["fracdecim_%g/counts" % fdecim] = np.array(counts)
+    # wire-format ingest: the reference's own unpack loops on seeded random bytes
+    lib = R.load("libquisk_rx_ref.so", private_copy=True)
+    lib.ref_add_rx_samples.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]
+    lib.ref_hermes_unpack.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    for nb in (1, 2, 3, 4):
+        for big in (0, 1):
+            data = ingest_bytes(70 + nb, 1000 * 2 * nb)
+            y = np.zeros(1000, dtype=np.complex128)
+            n = lib.ref_add_rx_samples(data.ctypes.data, len(data), nb, big, y.ctypes.data)
+            assert n == 1000
+            out["unpack_iq_%d_%d/y" % (nb, big)] = y
+    for n_rx in (1, 2, 4, 10):
+        pk = ingest_bytes(80 + n_rx, 3 * 1032).reshape(3, 1032)
+        rows = []
+        for p in range(3):
+            samp = np.zeros(126, dtype=np.complex128); sub = np.zeros((max(n_rx - 1, 1), 126), dtype=np.complex128)
+            one = np.ascontiguousarray(pk[p])
+            n = lib.ref_hermes_unpack(one.ctypes.data, n_rx - 1, samp.ctypes.data, sub.ctypes.data)
+            rows.append(np.concatenate([samp[None, :n], sub[:n_rx - 1, :n]], axis=0))
+        out["unpack_hermes_%d/y" % n_rx] = np.concatenate(rows, axis=1)
     np.savez_compressed(os.path.join(HERE, "misc_kat.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import quisk_oracle as O
-from tests.golden.make_golden import RATES, DEMOD_TAPS, demod_taps
+from tests.golden.make_golden import RATES, DEMOD_TAPS, DGT_CASES, demod_taps
 from tests.util import SPLITS, CHAIN_SPLITS, DEMOD_SPLITS, golden
 
 pytestmark = pytest.mark.gpu
@@ -143,6 +143,35 @@ def test_rx_demod_kat(mode, fused, torch, tabs):
     assert ca == kat["demod_%s/counts" % mode].tolist()
     for c in range(3):
         assert O.rel_rms(aud[c], kat["demod_%s/y" % mode]) < (1e-10 if mode == "FM" else 1e-12)
+    rx.close()
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("case", DGT_CASES, ids=[c[0] for c in DGT_CASES])
+def test_rx_demod_digital_modes_kat(case, fused, torch, tabs):
+    """DGT-U/L, FDV (narrow: CW's structure; wide: I/Q filter at 48 k) and DGT-IQ (complex out), quisk.c:2087-2153."""
+    from quisk_b200.rx import RxChain
+    name, mode, ntap, bw = case
+    kat = golden("chain_kat.npz")
+    rng = np.random.default_rng(3)
+    fi, fq = rng.standard_normal(ntap) / ntap, rng.standard_normal(ntap) / ntap
+    C = 3
+    rx = RxChain(C, 48000, mode, fi, fq, tabs, fused=bool(fused), bandwidth=bw)
+    x = np.stack([O.synth_iq(12000, 10, 1.0)] * C)
+    d_in = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    outs, counts, pos = [], [], 0
+    for n in DEMOD_SPLITS:
+        blk = d_in[:, pos:pos + n].contiguous(); pos += n
+        cap = rx.max_out(n)
+        a = torch.zeros((C, cap), dtype=torch.float64, device="cuda")
+        na, _ = rx.process(blk.data_ptr(), n, n, a.data_ptr(), cap)
+        torch.cuda.synchronize()
+        got = a.cpu().numpy()
+        outs.append(got[:, :2 * na].view(np.complex128) if mode == "DGT-IQ" else got[:, :na]); counts.append(na)
+    assert counts == kat["demod_%s/counts" % name].tolist()
+    y = np.concatenate(outs, axis=1)
+    for c in range(C):
+        assert O.rel_rms(y[c], kat["demod_%s/y" % name]) < 1e-12
     rx.close()
 
 

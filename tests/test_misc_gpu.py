@@ -84,3 +84,63 @@ def test_bandscope(torch, lib):
         ref = O.bandscope(blocks[s].reshape(nblk, size), gw, 122880000, 0.7, 1.0e6)
         assert np.max(np.abs(g[s] - ref)) < 1e-9
     lib.quisk_cuda_bandscope_destroy(b)
+
+
+@pytest.mark.parametrize("big", [0, 1])
+@pytest.mark.parametrize("nb", [1, 2, 3, 4])
+def test_unpack_iq(nb, big, torch, lib):
+    """Device unpack of add_rx_samples' wire format, bit-exact vs the compiled reference loops (quisk.c:2922-2953)."""
+    from tests.golden.make_golden_misc import ingest_bytes
+    kat = golden("misc_kat.npz")
+    data = ingest_bytes(70 + nb, 1000 * 2 * nb)
+    for off in (0, 1):                       # aligned and misaligned rows (the int16 / int32 fast paths need alignment)
+        raw = np.zeros((NCH, len(data) + 8), dtype=np.uint8)
+        raw[:, off:off + len(data)] = data
+        d = torch.from_numpy(raw).cuda()
+        out = torch.zeros((NCH, 1003), dtype=torch.complex128, device="cuda")
+        rc = lib.quisk_cuda_unpack_iq(d.data_ptr() + off, raw.shape[1], NCH, 1000, nb, big, out.data_ptr(), 1003, None)
+        assert rc == 0, lib.quisk_cuda_last_error()
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for c in range(NCH):
+            assert np.array_equal(got[c, :1000], kat["unpack_iq_%d_%d/y" % (nb, big)])
+            assert np.all(got[c, 1000:] == 0)
+
+
+@pytest.mark.parametrize("n_rx", [1, 2, 4, 10])
+def test_unpack_hermes(n_rx, torch, lib):
+    """Hermes / Metis protocol-1 de-interleave (quisk.c:3746-3763), bit-exact vs the compiled reference loop."""
+    from tests.golden.make_golden_misc import ingest_bytes
+    kat = golden("misc_kat.npz")
+    pk = ingest_bytes(80 + n_rx, 3 * 1032)
+    d = torch.from_numpy(pk).cuda()
+    per = lib.quisk_cuda_hermes_samples_per_packet(n_rx)
+    assert per == 2 * (504 // (6 * n_rx + 2))
+    out = torch.zeros((n_rx, 3 * per + 5), dtype=torch.complex128, device="cuda")
+    ns = C.c_int(0)
+    rc = lib.quisk_cuda_unpack_hermes(d.data_ptr(), 3, n_rx, out.data_ptr(), 3 * per + 5, C.byref(ns), None)
+    assert rc == 0, lib.quisk_cuda_last_error()
+    torch.cuda.synchronize()
+    assert ns.value == 3 * per
+    assert np.array_equal(out.cpu().numpy()[:, :3 * per], kat["unpack_hermes_%d/y" % n_rx])
+
+
+def test_rx_process_host_packed(torch, lib):
+    """int16 little-endian host block through quisk_cuda_rx_process_host_packed == the same samples widened on the
+    host (add_rx_samples) and fed through quisk_cuda_rx_process_host."""
+    from quisk_b200.rx import RxChain, load_tables
+    tabs = load_tables()
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    Cn, n = 3, 30720
+    rng = np.random.default_rng(5)
+    raw = rng.integers(0, 256, size=(Cn, n * 4), dtype=np.uint8)
+    wide = np.stack([O.unpack_iq(raw[c], 2, False) for c in range(Cn)])
+    rx1 = RxChain(Cn, 1536000, "USB", fi, fq, tabs, fused=True)
+    rx2 = RxChain(Cn, 1536000, "USB", fi, fq, tabs, fused=True)
+    a1 = np.zeros((Cn, rx1.max_out(n))); a2 = np.zeros_like(a1)
+    n1 = rx1.process_host(np.ascontiguousarray(wide), n, a1)
+    n2 = rx2.process_host_packed(raw, n, 2, False, a2)
+    assert n1 == n2 == n // 32
+    assert np.array_equal(a1[:, :n1], a2[:, :n2])
+    rx1.close(); rx2.close()

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import quisk_oracle as O
-from tests.golden.make_golden import FILTER_CASES, RATES, DEMOD_TAPS, kat_input, demod_taps
+from tests.golden.make_golden import FILTER_CASES, RATES, DEMOD_TAPS, DGT_CASES, kat_input, demod_taps
 from tests.util import SPLITS, CHAIN_SPLITS, DEMOD_SPLITS, golden
 
 TOL = 1e-13
@@ -73,6 +73,27 @@ def test_demod_kat(mode, tabs):
     assert O.rel_rms(np.concatenate(outs), kat["demod_%s/y" % mode]) < (1e-11 if mode == "FM" else TOL)
 
 
+def dgt_taps(ntap):
+    rng = np.random.default_rng(3)
+    return rng.standard_normal(ntap) / ntap, rng.standard_normal(ntap) / ntap
+
+
+@pytest.mark.parametrize("case", DGT_CASES, ids=[c[0] for c in DGT_CASES])
+def test_demod_digital_modes_kat(case, tabs):
+    """DGT-U/L, FDV-U/L (narrow and wide) and DGT-IQ (quisk.c:2087-2153) against the compiled reference."""
+    name, mode, ntap, bw = case
+    kat = golden("chain_kat.npz")
+    fi, fq = dgt_taps(ntap)
+    chain = O.ProcessDemodulate(mode, fi, fq, tabs, bandwidth=bw)
+    x = O.synth_iq(12000, 10, 1.0)
+    outs, counts, pos = [], [], 0
+    for n in DEMOD_SPLITS:
+        y = chain(x[pos:pos + n]); pos += n
+        outs.append(y); counts.append(len(y))
+    assert counts == kat["demod_%s/counts" % name].tolist()
+    assert O.rel_rms(np.concatenate(outs), kat["demod_%s/y" % name]) < TOL
+
+
 @pytest.mark.parametrize("tune", [0, 12345])
 def test_c1_chain_kat(tune, tabs):
     """BASELINE.json configs[0]: 1.536 MS/s -> 4 x HB45 -> 98-tap /2 -> 48 k -> USB (164-tap I/Q)."""
@@ -91,3 +112,23 @@ def test_c1_chain_kat(tune, tabs):
         outs.append(y); counts.append(len(y))
     assert counts == kat["c1_tune%d/counts" % tune].tolist() == [480] * 10
     assert O.rel_rms(np.concatenate(outs), kat["c1_tune%d/y" % tune]) < TOL
+
+
+@pytest.mark.parametrize("big", [0, 1])
+@pytest.mark.parametrize("nb", [1, 2, 3, 4])
+def test_unpack_iq_kat(nb, big):
+    """add_rx_samples' unpack loops (quisk.c:2922-2953), incl. the float rounding of 4-byte samples."""
+    from tests.golden.make_golden_misc import ingest_bytes
+    kat = golden("misc_kat.npz")
+    y = O.unpack_iq(ingest_bytes(70 + nb, 1000 * 2 * nb), nb, bool(big))
+    assert np.array_equal(y, kat["unpack_iq_%d_%d/y" % (nb, big)])
+
+
+@pytest.mark.parametrize("n_rx", [1, 2, 4, 10])
+def test_unpack_hermes_kat(n_rx):
+    """read_rx_udp10's 24-bit record loop (quisk.c:3746-3763)."""
+    from tests.golden.make_golden_misc import ingest_bytes
+    kat = golden("misc_kat.npz")
+    pk = ingest_bytes(80 + n_rx, 3 * 1032).reshape(3, 1032)
+    y = np.concatenate([O.unpack_hermes(pk[p], n_rx) for p in range(3)], axis=1)
+    assert np.array_equal(y, kat["unpack_hermes_%d/y" % n_rx])
