@@ -464,22 +464,24 @@ def pfb_main(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * n * args.steps / (ms_max / 1e3) / 1e6
-    # e2e: pinned host stream in, a frame-power summary out per step; the 32 B/sample receiver streams stay on the
+    # e2e: pinned host stream in, one receiver's stream out per step; the 32 B/sample receiver streams stay on the
     # device for the per-receiver chains (quisk_cuda_rx_process), which is where they are consumed
     e2e = None
     if args.e2e_steps > 0:
-        hx = torch.empty(x.shape, dtype=torch.complex128).pin_memory(); hx.copy_(x.cpu())
+        hx = torch.empty((x.numel(), 2), dtype=torch.float64).pin_memory(); hx.copy_(torch.view_as_real(x).cpu())
+        xr = torch.view_as_real(x)
+        xr.copy_(hx, non_blocking=True)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            x.copy_(hx, non_blocking=True)
+            xr.copy_(hx, non_blocking=True)
             step()
-            summary = y[:, :64].abs().sum(dim=1).cpu()
+            summary = torch.view_as_real(y[0]).cpu()      # one receiver's stream; the others stay in HBM
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = {"value": world * n * args.e2e_steps / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": int(x.numel() * 16),
                "d2h_bytes_per_step": int(summary.numel() * 8),
-               "note": "pinned host IQ -> H2D -> channelizer; receiver streams stay in HBM for quisk_cuda_rx_process, a per-receiver level summary is read back"}
+               "note": "pinned host IQ -> H2D -> channelizer -> D2H of one receiver's 192 kS/s stream; the other 1023 streams stay in HBM for quisk_cuda_rx_process"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -643,6 +645,7 @@ def main():
 
     # ---- end to end through the host-buffer entry point (H2D + chain + D2H inside the timed region)
     e2e = None
+    e2e_wire = None
     if rx and args.e2e_steps > 0:
         Ce = min(C_, 1024)
         hx = torch.empty((Ce, block), dtype=torch.complex128).pin_memory()
@@ -663,6 +666,25 @@ def main():
         e2e = {"value": world * Ce * block * args.e2e_steps / float(tt.item()) / 1e6, "unit": "MS/s",
                "h2d_bytes_per_step": Ce * block * 16, "d2h_bytes_per_step": Ce * na * 8,
                "channels": Ce, "note": "quisk_cuda_rx_process_host: pinned host IQ -> H2D -> chain -> D2H audio, per step"}
+        # the same step with the host block still in its wire format (int16 little-endian I/Q pairs, what
+        # add_rx_samples receives, quisk.c:2922): the H2D copy carries 4 B/sample, the widening runs on the device
+        rx_h.reset()
+        hw = torch.empty((Ce, block, 2), dtype=torch.int16).pin_memory()
+        hw.copy_((torch.view_as_real(x[:Ce]) / 65536.0).round().clamp(-32768, 32767).to(torch.int16).cpu())
+        hw_np = hw.numpy().view(np.uint8).reshape(Ce, block * 4)
+        rx_h.process_host_packed(hw_np, block, 2, False, ha_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            na = rx_h.process_host_packed(hw_np, block, 2, False, ha_np)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_wire = {"value": world * Ce * block * args.e2e_steps / float(tt.item()) / 1e6, "unit": "MS/s",
+                    "h2d_bytes_per_step": Ce * block * 4, "d2h_bytes_per_step": Ce * na * 8, "channels": Ce,
+                    "note": "quisk_cuda_rx_process_host_packed: pinned int16 LE I/Q pairs (add_rx_samples wire format) -> H2D -> unpack -> chain -> D2H audio"}
         rx_h.close()
 
     if rank != 0:
@@ -706,6 +728,8 @@ def main():
             "config": {"workload": wl_name, "channels_per_gpu": C_, "block": block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune,
                        "fused": not args.unfused, "l2": "input %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (C_ * block * 16 / 1e6)},
             "clocks": sampler.result(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+    if e2e_wire:
+        line["e2e_wire"] = e2e_wire
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

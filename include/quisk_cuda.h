@@ -328,7 +328,7 @@ void quisk_cuda_pfb_destroy(qcChannelizer *p);
 int quisk_cuda_pfb_count_out(const qcChannelizer *p, int count);
 int quisk_cuda_pfb_seek(qcChannelizer *p, long long n_abs);
 int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *stream);
-#define QC_PFB_OPT_SLICE_FRAMES 1   /* frames of the branch-FIR intermediate per kernel pair (default 2048; keeps it in L2) */
+#define QC_PFB_OPT_SLICE_FRAMES 1   /* frames of the branch-FIR intermediate per kernel pair (default 65536 = 1 GiB at 1024 channels) */
 #define QC_PFB_OPT_GENERIC      2   /* 1: force the single generic kernel (the only path when decim is not n_channels or n_channels/2) */
 #define QC_PFB_OPT_PIPELINE     3   /* 1: overlap the branch FIRs of slice i+1 with the transforms of slice i (two internal streams) */
 int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value);

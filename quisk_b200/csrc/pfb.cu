@@ -17,8 +17,10 @@
 //                        ahead), and emits the one or two frames that sample completes: u[frame][r].  Input is read
 //                        once (plus a T/K-sample warm-up per frame range), no shared memory at all.
 //      pfb_fft_kernel  : K-point transforms of u, four frames per CTA, written channel-major or frame-major.
-//      u is produced and consumed slice by slice (default 2048 frames = 32 MiB at K = 1024) so that it lives in
-//      the 126 MB L2 rather than making a round trip through HBM.
+//      u makes a round trip through HBM (32 B written + 32 B read per input sample on top of the 48 algorithmic
+//      bytes).  Slicing the frames so that u would stay in the 126 MB L2 -- sequentially or with the two kernels
+//      of neighbouring slices overlapped on two streams (QC_PFB_OPT_SLICE_FRAMES / _PIPELINE) -- was measured
+//      SLOWER at every slice size (launch gaps and tails outweigh the saved traffic), so the default is one slice.
 //  (2) any other D <= K: the single generic kernel below (taps in shared memory, window re-read per round).
 //
 // Generic kernel mapping: a CTA of K/4 threads = 4 transforms x K/16 lanes handles FOUR consecutive frames per round.
@@ -334,9 +336,9 @@ struct Channelizer {
     long long n_abs = 0;
     const cd *tw = nullptr;
     int n_sm = 148;
-    int slice_frames = 2048;        // frames of u per kernel pair (L2-resident intermediate)
+    int slice_frames = 1 << 16;     // frames of u per kernel pair; smaller slices were measured slower (launch gaps outweigh L2 reuse)
     int force_generic = 0;
-    cd *d_u = nullptr; int u_frames = 0;    // two slices of u back to back
+    cd *d_u = nullptr; int u_frames = 0, u_bufs = 0;        // one slice of u (two back to back when pipelining)
     int pipeline = 0;               // 1: branch FIRs of slice i+1 overlap the transforms of slice i on two internal streams
     cudaStream_t sa = nullptr, sb = nullptr;
     cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_fft[2] = {nullptr, nullptr}, ev_edge = nullptr;
@@ -410,11 +412,12 @@ struct Channelizer {
         const int ovs = K / D;
         int sf = slice_frames < PF ? PF : (slice_frames / PF) * PF;
         if (sf > nf) sf = ((nf + PF - 1) / PF) * PF;
-        if (sf > u_frames) {
+        const int want_bufs = pipeline ? 2 : 1;
+        if (sf > u_frames || want_bufs > u_bufs) {
             if (d_u) cudaFree(d_u);
-            d_u = nullptr; u_frames = 0;
-            QC_CUDA(cudaMalloc((void **)&d_u, (size_t)2 * sf * K * sizeof(cd)));
-            u_frames = sf;
+            d_u = nullptr; u_frames = 0; u_bufs = 0;
+            QC_CUDA(cudaMalloc((void **)&d_u, (size_t)want_bufs * sf * K * sizeof(cd)));
+            u_frames = sf; u_bufs = want_bufs;
         }
         const bool pipe = pipeline && nf > sf;
         cudaStream_t s_fir = s, s_fft = s;

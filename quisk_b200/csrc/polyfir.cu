@@ -88,8 +88,13 @@ __device__ void write_hist(const PolyFirParams &p, int c)
         ho[i] = load_x<T>(p, c, (long)p.n_in - p.H + i);
 }
 
+// Shared-memory slot of staged sample i.  A decimating stage (L = 1, M = 2^psh) reads sX with a lane stride of M
+// elements: stored densely every lane of a warp lands in the same bank group (M = 8: a 32-way serialised load, the
+// whole cost of the 1121-tap / 8 WDSP resampler).  One pad element per M makes the lane stride M + 1, which is odd.
+__device__ __forceinline__ int xslot(int i, int psh) { return psh > 0 ? i + (i >> psh) : i; }
+
 template <typename T, int TAPMODE>
-__global__ void __launch_bounds__(TM) polyfir_kernel(PolyFirParams p, int tiles, int KC)
+__global__ void __launch_bounds__(TM) polyfir_kernel(PolyFirParams p, int tiles, int KC, int psh)
 {
     extern __shared__ double smem[];
     const int c = blockIdx.x / tiles;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(TM) polyfir_kernel(PolyFirParams p, int tiles,
 
     constexpr int CW = (TAPMODE == TAP_REAL) ? 1 : 2;     // doubles per tap
     T *sX = reinterpret_cast<T *>(smem);
-    const int sx_elems = span + KC;                      // >= span + (k1-k0) - 1
+    const int sx_elems = xslot(span + KC, psh) + 1;      // >= slots of span + (k1-k0) - 1 samples
     double *sC = reinterpret_cast<double *>(sX + sx_elems);
 
     T acc = Zero<T>::v();
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(TM) polyfir_kernel(PolyFirParams p, int tiles,
         const long base = src_lo - (k1 - 1);
         const int nx = span + (k1 - k0) - 1;
         __syncthreads();
-        for (int i = tid; i < nx; i += TM) sX[i] = load_x<T>(p, c, base + i);
+        for (int i = tid; i < nx; i += TM) sX[xslot(i, psh)] = load_x<T>(p, c, base + i);
         const int nc = (k1 - k0) * p.L * CW;
         const double *gC = p.coef + (long)k0 * p.L * CW;
         for (int i = tid; i < nc; i += TM) sC[i] = gC[i];
@@ -146,10 +151,10 @@ __global__ void __launch_bounds__(TM) polyfir_kernel(PolyFirParams p, int tiles,
             const int xo = (int)(src - base);             // index of X[src] in sX
             if (p.order == 0) {
                 for (int k = k0; k < k1; k++)
-                    mac<TAPMODE>(acc, sX[xo - k], sC, ph + (k - k0) * p.L);
+                    mac<TAPMODE>(acc, sX[xslot(xo - k, psh)], sC, ph + (k - k0) * p.L);
             } else {
                 for (int k = k1 - 1; k >= k0; k--)
-                    mac<TAPMODE>(acc, sX[xo - k], sC, ph + (k - k0) * p.L);
+                    mac<TAPMODE>(acc, sX[xslot(xo - k, psh)], sC, ph + (k - k0) * p.L);
             }
         }
     }
@@ -222,9 +227,12 @@ static int launch_t(const PolyFirParams &p, cudaStream_t stream)
     long span = ((long)(TM - 1) * p.M) / p.L + 2;
     int KC = p.K < 512 ? p.K : 512;
     if (KC < 1) KC = 1;
+    int psh = 0;                                        // pad for power-of-two decimation (see xslot)
+    if (p.L == 1 && p.M >= 2 && (p.M & (p.M - 1)) == 0) while ((1 << psh) < p.M) psh++;
     size_t sh;
     for (;;) {
-        sh = (size_t)(span + KC) * sizeof(T) + (size_t)KC * p.L * CW * sizeof(double);
+        const long slots = span + KC + (psh > 0 ? ((span + KC) >> psh) : 0) + 1;
+        sh = (size_t)slots * sizeof(T) + (size_t)KC * p.L * CW * sizeof(double);
         if (sh <= 200 * 1024 || KC <= 16) break;
         KC /= 2;
     }
@@ -235,7 +243,7 @@ static int launch_t(const PolyFirParams &p, cudaStream_t stream)
         std::lock_guard<std::mutex> g(mu);
         QC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    kern<<<(unsigned)grid, TM, sh, stream>>>(p, tiles, KC);
+    kern<<<(unsigned)grid, TM, sh, stream>>>(p, tiles, KC, psh);
     count_launch();
     QC_CUDA_LAUNCH();
     return QC_OK;

@@ -146,11 +146,14 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
         int no = 0;
         rc = rsmpin->f->run(cur, cs, dsp_insize, m, ms, &no, 0, s); if (rc) return rc;
         if (no != dsp_size) { set_error("rxa: input resampler produced %d samples, dsp_size is %d", no, dsp_size); return QC_EINVAL; }
+        rc = adcmeter->run(m, ms, nullptr, 0, dsp_size, s); if (rc) return rc;
+        if (nbp_run) { rc = nbp0->run(m, ms, m, ms, s); if (rc) return rc; }
     } else {
-        QC_CUDA(cudaMemcpy2DAsync(m, (size_t)ms * sizeof(cd), cur, (size_t)cs * sizeof(cd), (size_t)dsp_size * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
+        // no input resampler: the first stage that writes moves the block into midbuff, no separate copy
+        rc = adcmeter->run(cur, cs, nullptr, 0, dsp_size, s); if (rc) return rc;
+        if (nbp_run) { rc = nbp0->run(cur, cs, m, ms, s); if (rc) return rc; }
+        else QC_CUDA(cudaMemcpy2DAsync(m, (size_t)ms * sizeof(cd), cur, (size_t)cs * sizeof(cd), (size_t)dsp_size * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
     }
-    rc = adcmeter->run(m, ms, nullptr, 0, dsp_size, s); if (rc) return rc;
-    if (nbp_run) { rc = nbp0->run(m, ms, m, ms, s); if (rc) return rc; }
     rc = smeter->run(m, ms, nullptr, 0, dsp_size, s); if (rc) return rc;
     if (amd_run) { rc = amd->run(m, ms, m, ms, dsp_size, s); if (rc) return rc; }
     if (fmd_run) {
@@ -160,7 +163,8 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
         rc = sntch->run(m, ms, m, ms, dsp_size, s); if (rc) return rc;                 // CTCSS notch (I rail)
     }
     if (bp1_run) { rc = bp1->run(m, ms, m, ms, s); if (rc) return rc; }
-    if (agc_run) { rc = agc->run(m, ms, m, ms, dsp_size, s); if (rc) return rc; }
+    // out of place into the second scratch buffer (free by now): the AGC kernel then needs no sample staging
+    if (agc_run) { rc = agc->run(m, ms, mid2, ms, dsp_size, s); if (rc) return rc; m = mid2; }
     rc = agcmeter->run(m, ms, agc->d_state, 0, dsp_size, s); if (rc) return rc;
     // xpanel always applies gain1 * gain2 (F9), inselect 3, no copy
     if (rsmpout) {

@@ -87,16 +87,21 @@ __global__ void __launch_bounds__(128) wcpagc_kernel(const cd *in, long is, cd *
         return;
     }
     const int ab = a.attack_buffsize, tot = ab + n;
-    cd *X = reinterpret_cast<cd *>(seq_smem);               // [tot]
-    double *A = reinterpret_cast<double *>(X + tot);        // [tot] magnitudes
-    double *RM = A + tot;                                   // [n]  ring_max, then reused for mult
-    double *V = RM + n;                                     // [n]  volts
-    double *BM = V + n;                                     // [(tot + 31) / 32] block maxima
+    // Shared memory holds the magnitudes of [history | block], ring_max (overwritten by volts, then by the gain) and
+    // the block maxima; the samples themselves are only staged when the stage runs in place (out == in), because
+    // then every input is overwritten before its delayed use.  Out of place that is ~23 KB for a 1024-sample block
+    // and attack_buffsize 768, so a whole batch of 1024 channels is resident at once.
+    const bool inplace = (const cd *)out == in;
+    double *A = seq_smem;                                   // [tot] magnitudes of [history | block]
+    double *RV = A + tot;                                   // [n]   ring_max -> volts -> mult
+    double *BM = RV + n;                                    // [(tot + 31) / 32 + 1] block maxima
+    cd *XS = reinterpret_cast<cd *>(BM + ((tot + 31) / 32 + 1) + 1);      // [n] the block, in-place runs only
+    if ((reinterpret_cast<size_t>(XS) & 15) != 0) XS = reinterpret_cast<cd *>(reinterpret_cast<double *>(XS) + 1);
     double *hs = hist + (size_t)c * ab * 3;
-    for (int i = tid; i < ab; i += nt) { X[i] = make_double2(hs[i * 3], hs[i * 3 + 1]); A[i] = hs[i * 3 + 2]; }
+    for (int i = tid; i < ab; i += nt) A[i] = hs[i * 3 + 2];
     for (int i = tid; i < n; i += nt) {
         const cd v = x[i];
-        X[ab + i] = v;
+        if (inplace) XS[i] = v;
         double m;
         if (a.pmode == 0) { const double f0 = fabs(v.x), f1 = fabs(v.y); m = f0 < f1 ? f1 : f0; }
         else m = sqrt(v.x * v.x + v.y * v.y);
@@ -123,16 +128,18 @@ __global__ void __launch_bounds__(128) wcpagc_kernel(const cd *in, long is, cd *
             for (int j = b0; j < b1; j++) m = BM[j] > m ? BM[j] : m;
             for (int k = b1 << 5; k <= hi; k++) m = A[k] > m ? A[k] : m;
         }
-        RM[i] = m;
+        RV[i] = m;
     }
     __syncthreads();
     double *st = state + (size_t)c * 16;
     if (tid == 0) {
         double volts = st[3], save_volts = st[4], fast_backaverage = st[5], hang_backaverage = st[6];
         int hang_counter = (int)st[7], decay_type = (int)st[8], state_ = (int)st[9];
+        double last_rm = 0.0;
         for (int i = 0; i < n; i++) {
             const double abs_out_sample = A[i];
-            const double ring_max = RM[i];
+            const double ring_max = RV[i];
+            last_rm = ring_max;
             fast_backaverage = a.fast_backmult * abs_out_sample + a.onemfast_backmult * fast_backaverage;
             hang_backaverage = a.hang_backmult * abs_out_sample + a.onemhang_backmult * hang_backaverage;
             if (hang_counter > 0) --hang_counter;
@@ -164,22 +171,39 @@ __global__ void __launch_bounds__(128) wcpagc_kernel(const cd *in, long is, cd *
                 break;
             }
             if (volts < a.min_volts) volts = a.min_volts;
-            V[i] = volts;
+            RV[i] = volts;
         }
-        st[2] = RM[n - 1]; st[3] = volts; st[4] = save_volts; st[5] = fast_backaverage; st[6] = hang_backaverage;
+        st[2] = last_rm; st[3] = volts; st[4] = save_volts; st[5] = fast_backaverage; st[6] = hang_backaverage;
         st[7] = hang_counter; st[8] = decay_type; st[9] = state_; st[10] = volts * a.inv_out_target;
     }
     __syncthreads();
+    // gain law and the delayed sample (the one written attack_buffsize inputs ago): history for i < ab, else this block
     for (int i = tid; i < n; i += nt) {
-        const double volts = V[i];
+        const double volts = RV[i];
         const double lg = log10(a.inv_max_input * volts);
         const double mult = (a.out_target - a.slope_constant * (0.0 < lg ? 0.0 : lg)) / volts;
-        const cd o = X[i];                                  // the sample written attack_buffsize inputs ago
+        cd o;
+        if (i < ab) o = make_double2(hs[i * 3], hs[i * 3 + 1]);
+        else o = inplace ? XS[i - ab] : x[i - ab];
         y[i] = make_double2(o.x * mult, o.y * mult);
     }
-    for (int i = tid; i < ab; i += nt) {
-        const cd v = X[n + i];
-        hs[i * 3] = v.x; hs[i * 3 + 1] = v.y; hs[i * 3 + 2] = A[n + i];
+    __syncthreads();            // every read of the old history is done
+    // new history = combined[n, n + ab): old history shifted down by n (only when n < ab), then the block's tail
+    if (n < ab) {
+        const int keep = ab - n;
+        for (int j0 = 0; j0 < keep; j0 += nt) {             // in-place forward shift, one stripe at a time
+            const int j = j0 + tid;
+            double r0 = 0, r1 = 0;
+            if (j < keep) { r0 = hs[(n + j) * 3]; r1 = hs[(n + j) * 3 + 1]; }
+            __syncthreads();
+            if (j < keep) { hs[j * 3] = r0; hs[j * 3 + 1] = r1; hs[j * 3 + 2] = A[n + j]; }
+            __syncthreads();
+        }
+    }
+    for (int j = tid + max(ab - n, 0); j < ab; j += nt) {
+        const int k = n + j - ab;                            // index into the block
+        const cd v = inplace ? XS[k] : x[k];
+        hs[j * 3] = v.x; hs[j * 3 + 1] = v.y; hs[j * 3 + 2] = A[n + j];
     }
 }
 
@@ -320,19 +344,33 @@ __global__ void snotch_kernel(const cd *in, long is, cd *out, long os, int n, in
 
 // ------------------------------------------------------------------------------------------- meter
 // state: avg peak ; par: mult_average mult_peak ; results: av dB, pk dB (10 log10, meter.c:98-99)
+// The averaging recurrence avg = avg * ma + (1 - ma) * |x|^2 is sequential in the reference's arithmetic, but its
+// inputs are not: every thread forms w[i] = (1 - ma) * |x[i]|^2 and the block maximum in parallel, lane 0 is left with
+// one multiply and one add per sample (the peak decay peak *= mp is a second, independent chain).
 __global__ void meter_kernel(const cd *in, long is, int n, int C, double *state, SeqPar P, double *result, const double *agc_state)
 {
-    SEQ_STAGE_IN();
+    extern __shared__ double seq_smem[];
+    double *w = seq_smem;                       // [n]
+    __shared__ double s_max[2];
+    const int c = blockIdx.x;
+    const double ma = P.v[0], mp = P.v[1], oma = 1.0 - ma;
+    const cd *gx = in + (size_t)c * is;
+    double lm = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const cd v = gx[i];
+        const double smag = v.x * v.x + v.y * v.y;
+        w[i] = oma * smag;
+        lm = smag > lm ? smag : lm;
+    }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, lm, o); lm = t > lm ? t : lm; }
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = lm;
+    __syncthreads();
     if (threadIdx.x != 0) return;
-    const cd *x = sx;
     double avg = state[c * 2], peak = state[c * 2 + 1];
-    const double ma = P.v[0], mp = P.v[1];
-    double np = 0.0;
+    double np = s_max[0] > s_max[1] ? s_max[0] : s_max[1];
     for (int i = 0; i < n; i++) {
-        const double smag = x[i].x * x[i].x + x[i].y * x[i].y;
-        avg = avg * ma + (1.0 - ma) * smag;
+        avg = avg * ma + w[i];
         peak *= mp;
-        if (smag > np) np = smag;
     }
     if (np > peak) peak = np;
     state[c * 2] = avg; state[c * 2 + 1] = peak;
@@ -453,7 +491,7 @@ int SeqStage::run(const void *d_in, long is, void *d_out, long os, int n, cudaSt
     case SEQ_SHIFT: QC_SEQ_OPTIN(shift_kernel, sh); shift_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, d_par); break;
     case SEQ_WCPAGC: {
         const int tot = agc.attack_buffsize + n;
-        const size_t sa = (size_t)tot * 24 + (size_t)n * 16 + (size_t)((tot + 31) / 32 + 1) * 8;
+        const size_t sa = (size_t)tot * 8 + (size_t)n * 8 + (size_t)((tot + 31) / 32 + 4) * 8 + (d_in == d_out ? (size_t)n * 16 : 0);
         if (sa > 220 * 1024) { set_error("wcpagc: attack buffer + block (%d samples) exceed shared memory", tot); return QC_EINVAL; }
         QC_SEQ_OPTIN(wcpagc_kernel, sa);
         wcpagc_kernel<<<C, 128, sa, s>>>(in, is, out, os, n, C, d_state, d_ring, agc);
