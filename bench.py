@@ -67,27 +67,34 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index; self.stop_flag = False; self.sm = []; self.reasons = set(); self.sm_max = None; self.ok = False
+        try:                        # NVML set-up happens here, outside the timed region, so that even a region of a
+            import pynvml as nv     # few milliseconds gets its first sample at once
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                          nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                          nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                          nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                          nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            self.ok = True
+        except Exception as e:      # NVML missing: report that, never fake a value
+            self.err = str(e)
 
     def run(self):
+        if not self.ok:
+            return
+        nv, h = self.nv, self.h
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
-                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-            self.ok = True
             while not self.stop_flag:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
+                for bit, name in self.names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
-        except Exception as e:      # NVML missing: report that, never fake a value
+                time.sleep(0.005)
+        except Exception as e:
             self.err = str(e)
 
     def result(self):
@@ -355,7 +362,7 @@ def pfb_proto():
     return h
 
 
-def pfb_reference_rate(n_samples, steps, warmup):
+def pfb_reference_rate(n_samples, steps, warmup, reps=1):
     """The reference's way to get receiver k out of the wideband stream: its tune loop (quisk.c:2477-2494, compiled
     reference) and quisk_cDecimate with the 16384-tap prototype, /512 (filter.c:203-229) -- per receiver.  One
     receiver per host core over n_samples; the wideband rate is what all 1024 receivers would sustain."""
@@ -374,7 +381,7 @@ def pfb_reference_rate(n_samples, steps, warmup):
     vec = [np.array([1.0 + 0j]) for _ in range(cores)]
 
     def work(i, nsteps):
-        for _ in range(nsteps):
+        for _ in range(nsteps * reps):          # one step = `reps` passes over the receiver's block (state carries on)
             pos = 0
             while pos < n_samples:
                 m = min(61440, n_samples - pos)
@@ -391,7 +398,7 @@ def pfb_reference_rate(n_samples, steps, warmup):
         return time.perf_counter() - t0
     run(warmup)
     dt = run(steps)
-    receiver_rate = cores * n_samples * steps / dt / 1e6        # receiver-input MS/s over all cores
+    receiver_rate = cores * n_samples * reps * steps / dt / 1e6        # receiver-input MS/s over all cores
     return receiver_rate / PFB["K"], cores, dt
 
 
@@ -402,14 +409,14 @@ def pfb_main(args, rank, world, local_rank):
     if args.impl == "reference":
         if rank != 0:
             return
-        ns = 61440 * 2
-        v, cores, dt = pfb_reference_rate(ns, args.steps, args.warmup)
+        ns, reps = 61440, 64
+        v, cores, dt = pfb_reference_rate(ns, args.steps, args.warmup, reps)
         line = {"impl": "reference", "metric": "complex MS/s through RX chain", "value": v, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": {"workload": cfg["name"], "receivers_timed": cores, "samples_per_step": ns},
+                "dtype": "f64", "data": "synthetic", "config": {"workload": cfg["name"], "receivers_timed": cores, "samples_per_step": ns * reps},
                 "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
                                  "sample": "%d receivers (one per core) x %d samples x %d steps through the reference's tune loop + quisk_cDecimate(16384 taps, /512); "
-                                           "value = wideband rate at which all 1024 receivers would be served" % (cores, ns, args.steps)},
+                                           "value = wideband rate at which all 1024 receivers would be served" % (cores, ns * reps, args.steps)},
                 "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line)); return
     import torch
@@ -492,9 +499,9 @@ def pfb_main(args, rank, world, local_rank):
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            v, cores, dt = pfb_reference_rate(61440, 2, 1)
+            v, cores, dt = pfb_reference_rate(61440, 30, 1, 64)
             cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
-                   "sample": "%d receivers (one per core) x 61440 samples x 2 steps, %.1f s wall: reference tune loop + quisk_cDecimate(16384 taps, /512) per receiver; "
+                   "sample": "%d receivers (one per core) x 61440 samples x 64 passes x 30 steps, %.1f s wall: reference tune loop + quisk_cDecimate(16384 taps, /512) per receiver; "
                              "value = wideband rate at which all 1024 receivers would be served" % (cores, dt)}
         except Exception as ex:
             cpu = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
@@ -529,6 +536,7 @@ def main():
     ap.add_argument("--dense", type=int, default=-1, help="fused decimator: 1 = 128-register cap, 0 = 255")
     ap.add_argument("--plans", type=int, default=-1, help="fused decimator: 0 = generic kernel only")
     ap.add_argument("--deepk", type=int, default=0, help="fused decimator: low-rate stages every k chunks (1 or 4)")
+    ap.add_argument("--nco", default="exact", choices=["exact", "closed"], help="tuning phasor at block starts: the reference's recurrence (default) or closed form only")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -595,6 +603,8 @@ def main():
             rx.set_option(6, args.plans)
         if args.deepk:
             rx.set_option(8, args.deepk)
+        if args.nco == "closed":
+            rx.set_option(10, 0)
         acap = rx.max_out(block)
         audio = torch.zeros((C_, acap), dtype=torch.float64, device=dev)
     if "panadapter" in args.workload:
@@ -726,7 +736,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "channels_per_gpu": C_, "block": block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune,
-                       "fused": not args.unfused, "l2": "input %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (C_ * block * 16 / 1e6)},
+                       "fused": not args.unfused, "nco": args.nco if args.tune else "off", "l2": "input %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (C_ * block * 16 / 1e6)},
             "clocks": sampler.result(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
     if e2e_wire:
         line["e2e_wire"] = e2e_wire

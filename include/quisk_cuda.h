@@ -234,6 +234,9 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_TIMING       1   /* value != 0: record CUDA events around the dominant (fused) kernel */
 #define QC_RX_OPT_FUSED_CHUNK  2   /* target input samples per shared-memory chunk of the fused decimator */
 #define QC_RX_OPT_FUSED_THREADS 3  /* CTA width of the fused decimator: 128 or 256 */
+#define QC_RX_OPT_EXACT_NCO   10   /* 1 (default): the tuning phasor at every block start is produced by the reference's own rounded
+                                    * recurrence (quisk.c:2486) on a side stream, so tuned output follows the reference for any stream
+                                    * length; 0: closed form only, ~10 % faster, drifts ~1e-19 per sample from the reference */
 #define QC_RX_OPT_FUSED_TAIL   9   /* SSB / CW: one kernel for receive filter + demodulation + audio interpolators (default 1) */
 #define QC_RX_OPT_FUSED_DEEPK  8   /* plan kernels: low-rate stages run once per this many chunks (1 or 4, default 1: measured slower at 4 with two CTAs per SM) */
 #define QC_RX_OPT_TRACE        7   /* debug: record clock64() stamps per chunk phase in the fused kernel */

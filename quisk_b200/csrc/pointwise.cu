@@ -9,8 +9,56 @@
 
 namespace qc {
 
+// v at the start of the next block by the reference's own rounded recurrence (quisk.c:2483: v *= phase, `count`
+// times): one thread per channel, a dependent chain of count complex multiplies.  It runs on a side stream one
+// block ahead of the kernels that consume it (rxchain.cu), so its latency is hidden; the closed form (nco_pow)
+// then only has to bridge the samples INSIDE one block, and the tuning phasor follows the reference for any
+// stream length.
+__global__ void nco_advance_kernel(const cd *v_in, cd *v_out, const double *nco, int count, int C)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const cd ph = make_double2(nco[(size_t)c * 8 + 5], nco[(size_t)c * 8 + 6]);
+    cd v = v_in[c];
+#pragma unroll 4
+    for (int i = 0; i < count; i++) v = cmul_rn(v, ph);
+    v_out[c] = v;
+}
+
+int launch_nco_advance(const cd *v_in, cd *v_out, const double *d_nco, int count, int C, cudaStream_t s)
+{
+    if (C <= 0) return QC_OK;
+    // 24 KB of (unused) dynamic shared memory per CTA: the block scheduler would otherwise pack these one-warp CTAs
+    // onto the first few SMs with a free slot, where 16+ dependent FP64 chains share one pipe and the recurrence
+    // becomes the slowest thing on the device (measured: 1.6 ms instead of 0.4 ms for 32768 steps).  With the
+    // reservation at most one or two land on an SM, and the two 90 KB CTAs of the fused decimator still fit beside them.
+    static bool optin = false;
+    if (!optin) { QC_CUDA(cudaFuncSetAttribute(nco_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024)); optin = true; }
+    nco_advance_kernel<<<(C + 31) / 32, 32, 24 * 1024, s>>>(v_in, v_out, d_nco, count, C);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+// closed-form counterpart: v_out = v_in * phase^count in one step (QC_RX_OPT_EXACT_NCO = 0)
+__global__ void nco_jump_kernel(const cd *v_in, cd *v_out, const double *nco, int count, int C)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    v_out[c] = cmul_rn(v_in[c], nco_pow(nco + (size_t)c * 8, (unsigned long long)count));
+}
+
+int launch_nco_jump(const cd *v_in, cd *v_out, const double *d_nco, int count, int C, cudaStream_t s)
+{
+    if (C <= 0) return QC_OK;
+    nco_jump_kernel<<<(C + 127) / 128, 128, 0, s>>>(v_in, v_out, d_nco, count, C);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
 __global__ void tune_kernel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C,
-                            const double *nco, unsigned long long n0)
+                            const double *nco, const cd *vstart, unsigned long long n0)
 {
     const long total = (long)n * C;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -18,19 +66,19 @@ __global__ void tune_kernel(const cd *in, long in_stride, cd *out, long out_stri
         const int j = (int)(idx - (long)c * n);
         const double *nc = nco + (long)c * 8;
         const cd w = nco_pow(nc, n0 + (unsigned long long)j);
-        const cd v = cmul_rn(make_double2(nc[3], nc[4]), w);
+        const cd v = cmul_rn(vstart[c], w);
         const cd x = in[(long)c * in_stride + j];
         out[(long)c * out_stride + j] = cmul_rn(x, v);
     }
 }
 
 int launch_tune(const cd *in, long in_stride, cd *out, long out_stride, int n, int C,
-                const double *d_nco, unsigned long long n0, cudaStream_t s)
+                const double *d_nco, const cd *d_vstart, unsigned long long n0, cudaStream_t s)
 {
     if (n <= 0 || C <= 0) return QC_OK;
     const long total = (long)n * C;
     int blocks = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
-    tune_kernel<<<blocks, 256, 0, s>>>(in, in_stride, out, out_stride, n, C, d_nco, n0);
+    tune_kernel<<<blocks, 256, 0, s>>>(in, in_stride, out, out_stride, n, C, d_nco, d_vstart, n0);
     count_launch();
     QC_CUDA_LAUNCH();
     return QC_OK;

@@ -74,7 +74,9 @@ int launch_polyfir(const PolyFirParams &p, cudaStream_t stream);
 // Pointwise helpers (pointwise.cu)
 int launch_demod_ssb(const cd *in, long in_stride, double *out, long out_stride, int n, int C, int lower, cudaStream_t s);
 int launch_tune(const cd *in, long in_stride, cd *out, long out_stride, int n, int C,
-                const double *d_nco /* [C][8] */, unsigned long long n0, cudaStream_t s);
+                const double *d_nco /* [C][8] */, const cd *d_vstart /* [C] v at sample 0 of the block */, unsigned long long n0, cudaStream_t s);
+int launch_nco_advance(const cd *v_in, cd *v_out, const double *d_nco, int count, int C, cudaStream_t s);
+int launch_nco_jump(const cd *v_in, cd *v_out, const double *d_nco, int count, int C, cudaStream_t s);
 int launch_am_detect(const cd *in, long in_stride, double *out, long out_stride, int n, int C, double *d_dc /*[C]*/, cudaStream_t s);
 int launch_fm_detect(const cd *in, long in_stride, double *out, long out_stride, int n, int C,
                      double *d_state /*[C][4]: fm_1.re, fm_1.im, x_1, y_1*/, double a0, double a1, double b1, cudaStream_t s);

@@ -175,12 +175,57 @@ int RxChain::reset_fm()
     return QC_OK;
 }
 
+// The tuning phasor at the first sample of each block comes from the reference's own recurrence
+// (nco_advance_kernel).  Block b reads d_v[vcur]; while its kernels run, the side stream advances that value by
+// `count` steps into the next ring slot for block b + 1.  Events keep the two streams honest: a consumer waits for
+// the recurrence that fills its slot, and the recurrence that recycles a slot waits for the consumer that read it.
+int RxChain::nco_before(int count, cudaStream_t s)
+{
+    // the recurrence for the NEXT block goes first: it only needs this block's start value and length
+    const int b = vcur, nb = (vcur + 1) % NV;
+    if (f_set[nb]) QC_CUDA(cudaStreamWaitEvent(s_nco, ev_f[nb], 0));
+    // exact_nco = 0: the next block start comes from the closed form too (one step instead of `count`); the phasor
+    // then drifts from the reference's by ~1e-19 per sample (1e-12 after ~8 s at 1.536 MS/s)
+    int rc = exact_nco ? launch_nco_advance(d_v[b], d_v[nb], d_nco, count, C, s_nco)
+                       : launch_nco_jump(d_v[b], d_v[nb], d_nco, count, C, s_nco);
+    if (rc != QC_OK) return rc;
+    QC_CUDA(cudaEventRecord(ev_r[nb], s_nco)); r_set[nb] = true;
+    if (r_set[b]) QC_CUDA(cudaStreamWaitEvent(s, ev_r[b], 0));
+    return QC_OK;
+}
+
+int RxChain::nco_after(int count, cudaStream_t s)
+{
+    (void)count;
+    QC_CUDA(cudaEventRecord(ev_f[vcur], s)); f_set[vcur] = true;
+    vcur = (vcur + 1) % NV;
+    return QC_OK;
+}
+
 int RxChain::upload_nco()
 {
     std::vector<double> h((size_t)C * 8);
     for (int c = 0; c < C; c++) nco_make(tune_hz[c], sample_rate, 1.0, 0.0, &h[(size_t)c * 8]);
     QC_CUDA(cudaMemcpy(d_nco, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     n_base = 0;
+    // rxTuneVector starts at 1 (quisk.c:2308); (re)start the ring of block-start phasors
+    if (!s_nco) {
+        // highest priority: the few tiny CTAs of the recurrence must be dispatched at once, not queued behind the
+        // thousands of CTAs of the block kernels (measured: without it the two serialise, -25 % throughput)
+        int pr_lo = 0, pr_hi = 0;
+        QC_CUDA(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+        QC_CUDA(cudaStreamCreateWithPriority(&s_nco, cudaStreamNonBlocking, pr_hi));
+        for (int i = 0; i < NV; i++) {
+            QC_CUDA(cudaMalloc((void **)&d_v[i], (size_t)C * sizeof(cd)));
+            QC_CUDA(cudaEventCreateWithFlags(&ev_r[i], cudaEventDisableTiming));
+            QC_CUDA(cudaEventCreateWithFlags(&ev_f[i], cudaEventDisableTiming));
+        }
+    }
+    QC_CUDA(cudaDeviceSynchronize());
+    std::vector<cd> one((size_t)C, make_double2(1.0, 0.0));
+    QC_CUDA(cudaMemcpy(d_v[0], one.data(), one.size() * sizeof(cd), cudaMemcpyHostToDevice));
+    vcur = 0;
+    for (int i = 0; i < NV; i++) { r_set[i] = false; f_set[i] = false; }
     return QC_OK;
 }
 
@@ -191,6 +236,12 @@ void RxChain::release()
     if (rxf) { rxf->release(); delete rxf; }
     cst.clear(); rst.clear(); rxf = nullptr;
     for (int i = 0; i < 2; i++) { if (bufc[i]) cudaFree(bufc[i]); if (bufr[i]) cudaFree(bufr[i]); bufc[i] = nullptr; bufr[i] = nullptr; }
+    if (s_nco) { cudaStreamSynchronize(s_nco); cudaStreamDestroy(s_nco); s_nco = nullptr; }
+    for (int i = 0; i < NV; i++) {
+        if (d_v[i]) cudaFree(d_v[i]); d_v[i] = nullptr;
+        if (ev_r[i]) cudaEventDestroy(ev_r[i]); if (ev_f[i]) cudaEventDestroy(ev_f[i]);
+        ev_r[i] = ev_f[i] = nullptr;
+    }
     if (d_nco) cudaFree(d_nco); if (d_dc) cudaFree(d_dc); if (d_fm) cudaFree(d_fm);
     if (h_pin) cudaFreeHost(h_pin); if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out);
     d_nco = d_dc = d_fm = nullptr; h_pin = nullptr; d_host_in = nullptr; d_host_out = nullptr;
@@ -252,15 +303,15 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
     size_t first_stage = 0;
     // fuse through the demodulator's own pre-decimation unless the caller wants the 48 kS/s tap
     const size_t nf = fused ? fusable_prefix(d_decim ? (size_t)n_decim_stages : cst.size()) : 0;
+    if (tune) { rc = nco_before(count, s); if (rc != QC_OK) return rc; }
     if (nf > 0) {
         rc = run_fused_decimator(nf, cur, stride, count, bufc[0], cap, &n, s); if (rc != QC_OK) return rc;
         cur = bufc[0]; stride = cap; pp = 1; first_stage = nf;
-        if (tune) n_base += (unsigned long long)count;
     } else if (tune) {
-        rc = launch_tune(cur, stride, bufc[0], cap, n, C, d_nco, n_base, s); if (rc != QC_OK) return rc;
-        n_base += (unsigned long long)count;
+        rc = launch_tune(cur, stride, bufc[0], cap, n, C, d_nco, d_v[vcur], 0, s); if (rc != QC_OK) return rc;
         cur = bufc[0]; stride = cap; pp = 1;
     }
+    if (tune) { rc = nco_after(count, s); if (rc != QC_OK) return rc; n_base += (unsigned long long)count; }
     for (size_t i = first_stage; i < cst.size(); i++) {
         if ((int)i == n_decim_stages && d_decim) {
             QC_CUDA(cudaMemcpy2DAsync(d_decim, (size_t)decim_stride * sizeof(cd), cur, (size_t)stride * sizeof(cd),
@@ -426,6 +477,7 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
         if (!value && rx->rx.d_trace) { cudaFree(rx->rx.d_trace); rx->rx.d_trace = nullptr; }
         return QC_OK;
     case QC_RX_OPT_FUSED_TAIL: rx->rx.fused_tail = value ? 1 : 0; return QC_OK;
+    case QC_RX_OPT_EXACT_NCO: rx->rx.exact_nco = value ? 1 : 0; return QC_OK;
     case QC_RX_OPT_FUSED_DEEPK:
         if (value != 1 && value != 4) { qc::set_error("rx_set_option: deepk must be 1 or 4"); return QC_EINVAL; }
         rx->rx.fused_deepk = value; return QC_OK;

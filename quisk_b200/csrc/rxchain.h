@@ -22,7 +22,17 @@ struct RxChain {
     bool tune = false;
     std::vector<double> tune_hz;
     double *d_nco = nullptr;
-    unsigned long long n_base = 0;      // samples since the NCO constants were (re)based
+    unsigned long long n_base = 0;      // samples since the NCO constants were (re)based (statistics only)
+    // exact phasor at block starts: ring of [C] buffers filled one block ahead on a side stream (pointwise.cu)
+    static constexpr int NV = 4;
+    cd *d_v[NV] = {nullptr, nullptr, nullptr, nullptr};
+    int vcur = 0;
+    int exact_nco = 1;                  // 1: block-start phasors from the reference's recurrence; 0: closed form only
+    cudaStream_t s_nco = nullptr;
+    cudaEvent_t ev_r[NV] = {}, ev_f[NV] = {};
+    bool r_set[NV] = {}, f_set[NV] = {};
+    int nco_before(int count, cudaStream_t s);      // starts the recurrence for the next block; the consumer on s may then read d_v[vcur]
+    int nco_after(int count, cudaStream_t s);       // consumer enqueued: mark the slot as read, move on
     // detectors
     double *d_dc = nullptr, *d_fm = nullptr;
     double fm_a0 = 0, fm_a1 = 0, fm_b1 = 0;

@@ -60,7 +60,7 @@ struct FusedParams {
     const cd *in; long in_stride; int n_in;
     cd *out; long out_stride;
     int T0;
-    const double *nco; unsigned long long n_base; int tune;
+    const double *nco; const cd *vstart; unsigned long long n_base; int tune;
     int smem_cd;        // total shared memory in cd units
     int scratch;        // offset of the history-slide scratch area (cd units)
     int coef_sm;        // offset of the tap copy in shared memory (cd units)
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
         const double *nc = P.nco + (size_t)c * 8;
         if (tid == 0) s_pstep = nco_pow(nc, (unsigned long long)P.T0);
         if (tid < 2048 / NT) s_q[tid] = nco_pow(nc, (unsigned long long)tid * NT);
-        u = cmul_rn(make_double2(nc[3], nc[4]), nco_pow(nc, P.n_base + (unsigned long long)tid));
+        u = cmul_rn(P.vstart[c], nco_pow(nc, P.n_base + (unsigned long long)tid));
     }
     // slide table for full chunks: which shared-memory element this thread moves where
     constexpr int NS = (int)sizeof...(PLAN);
@@ -563,7 +563,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     if (T0 % NT) { set_error("fused decimator: chunk %d is not a multiple of the CTA width %d", T0, NT); return QC_EINVAL; }
     P.ns = ns; P.T0 = T0;
     P.in = in; P.in_stride = in_stride; P.n_in = count; P.out = out; P.out_stride = out_stride;
-    P.nco = d_nco; P.n_base = n_base; P.tune = tune ? 1 : 0;
+    P.nco = d_nco; P.vstart = d_v[vcur]; P.n_base = 0; P.tune = tune ? 1 : 0;
     P.trace = d_trace;
     // multi-rate split: the first stage that sees <= 128 samples per chunk, and everything after it, runs
     // once every `deepk` chunks (plan kernels only)

@@ -197,6 +197,23 @@ def test_c1_chain_kat(tune, fused, torch, tabs):
     rx.close()
 
 
+def test_c1_chain_closed_form_nco(torch, tabs):
+    """QC_RX_OPT_EXACT_NCO = 0: block-start phasors from the closed form instead of the reference's recurrence;
+    over the 0.1 s fixture both are far inside the tolerance (tests/test_c1_fullsize_gpu.py shows where they part)."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    C = 2
+    rx = RxChain(C, 1536000, "USB", fi, fq, tabs, tune_hz=[12345.0] * C, fused=True)
+    rx.set_option(10, 0)
+    x = np.stack([O.synth_iq(153600, 20, 1.0)] * C)
+    aud, ca, _, _ = _run_chain(torch, rx, x, [15360] * 10)
+    assert ca == kat["c1_tune12345/counts"].tolist()
+    for c in range(C):
+        assert O.rel_rms(aud[c], kat["c1_tune12345/y"]) < 1e-12
+    rx.close()
+
+
 def test_rx_process_host(torch, tabs):
     from quisk_b200.rx import RxChain
     kat = golden("chain_kat.npz")
