@@ -90,6 +90,12 @@ int quisk_cuda_rxa_set_agc_mode(qcRxa *r, int mode);                        /* S
 int quisk_cuda_rxa_set_agc_fixed(qcRxa *r, double gain_db);                 /* SetRXAAGCFixed                    */
 int quisk_cuda_rxa_set_shift(qcRxa *r, int run, const double *shift_hz);    /* SetRXAShiftRun / SetRXAShiftFreq  */
 int quisk_cuda_rxa_set_nbp_run(qcRxa *r, int run);                          /* RXANBPSetRun                      */
+/* OpenChannel's tdelayup / tslewup (channel.c:76-104; Quisk passes 0.010 and 0.025, quisk_wdsp.py:79-80) and the
+ * upflag it raises: quisk_cuda_rxa_fexchange0 then runs upslew0's state machine (iobuffs.c:98-160) per channel on the
+ * device -- zeros up to and including the first non-zero sample, tdelayup of zeros, a raised-cosine ramp over
+ * tslewup.  A new handle starts armed with both times 0 (the first non-zero sample is still swallowed).  The
+ * down-slew / flush of SetChannelState(ch, 0) is not reproduced. */
+int quisk_cuda_rxa_set_slew(qcRxa *rxa, double tdelayup, double tslewup);
 int quisk_cuda_rxa_set_panel_gain(qcRxa *r, double gain1);                  /* SetRXAPanelGain1                  */
 int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per channel consumed per xrxa  */
 int quisk_cuda_rxa_out_size(const qcRxa *r);     /* dsp_outsize: samples per channel produced per xrxa */

@@ -33,7 +33,9 @@ struct Rxa {
     double panel_gain1 = 4.0, panel_gain2I = 1.0, panel_gain2Q = 1.0;
     // buffers
     cd *mid = nullptr, *mid2 = nullptr, *audio = nullptr;
-    // fexchange0 emulation
+    // fexchange0 emulation: up-slew state per channel (iobuffs.c:47-160): [C][3] = ustate, ucount, upflag
+    int ndelup = 0, ntup = 0; int *d_uslew = nullptr; double *d_cup = nullptr;
+    int arm_upslew(double tdelayup, double tslewup);
     cd *d_in = nullptr, *d_out = nullptr; double *h_ring = nullptr; int ring_blocks = 0, ring_pos = 0; cudaStream_t hs = nullptr;
 
     int init(int C, int in_size, int dsp_size, int in_rate, int dsp_rate, int out_rate);
@@ -43,6 +45,66 @@ struct Rxa {
     int make_fmd();
     int xrxa(const void *din, long is, void *dout, long os, cudaStream_t s);
 };
+
+// upslew0 (iobuffs.c:98-160), one thread per channel, in place on the block about to enter the DSP chain: zeros until
+// the first non-zero sample (which is swallowed too), ndelup more zeros, a raised-cosine ramp of ntup + 1 samples,
+// then pass-through; the channel's flag drops at the end of the first block that finishes in the ON state.
+enum { U_BEGIN = 0, U_DELAYUP = 1, U_UPSLEW = 2, U_ON = 3 };
+__global__ void upslew_kernel(cd *x, long stride, int n, int C, int *st, const double *cup, int ndelup, int ntup)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C || !st[c * 3 + 2]) return;
+    int ustate = st[c * 3], ucount = st[c * 3 + 1], flag = 1;
+    cd *p = x + (size_t)c * stride;
+    for (int i = 0; i < n; i++) {
+        const cd v = p[i];
+        switch (ustate) {
+        case U_BEGIN:
+            p[i] = make_double2(0.0, 0.0);
+            if (v.x != 0.0 || v.y != 0.0) {
+                if (ndelup > 0) { ustate = U_DELAYUP; ucount = ndelup; }
+                else if (ntup > 0) { ustate = U_UPSLEW; ucount = ntup; }
+                else ustate = U_ON;
+            }
+            break;
+        case U_DELAYUP:
+            p[i] = make_double2(0.0, 0.0);
+            if (ucount-- == 0) {
+                if (ntup > 0) { ustate = U_UPSLEW; ucount = ntup; }
+                else ustate = U_ON;
+            }
+            break;
+        case U_UPSLEW: {
+            const double g = cup[ntup - ucount];
+            p[i] = make_double2(v.x * g, v.y * g);
+            if (ucount-- == 0) ustate = U_ON;
+            break; }
+        case U_ON:
+            if (i == n - 1) { ustate = U_BEGIN; flag = 0; }
+            break;
+        }
+    }
+    st[c * 3] = ustate; st[c * 3 + 1] = ucount; st[c * 3 + 2] = flag;
+}
+
+int Rxa::arm_upslew(double tdelayup, double tslewup)
+{   // create_slews / flush_slews + the upflag OpenChannel and SetChannelState(1) raise (iobuffs.c:47-96, channel.c:95,291)
+    ndelup = (int)(tdelayup * in_rate);
+    ntup = (int)(tslewup * in_rate);
+    std::vector<double> cup((size_t)ntup + 1);
+    const double delta = 3.1415926535897932 / (double)ntup;      // PI / 0 = inf when ntup == 0: cup[0] = 0 and is never used
+    double theta = 0.0;
+    for (int i = 0; i <= ntup; i++) { cup[i] = 0.5 * (1.0 - cos(theta)); theta += delta; }
+    if (d_cup) cudaFree(d_cup);
+    d_cup = nullptr;
+    QC_CUDA(cudaMalloc((void **)&d_cup, cup.size() * sizeof(double)));
+    QC_CUDA(cudaMemcpy(d_cup, cup.data(), cup.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (!d_uslew) QC_CUDA(cudaMalloc((void **)&d_uslew, (size_t)C * 3 * sizeof(int)));
+    std::vector<int> st((size_t)C * 3, 0);
+    for (int c = 0; c < C; c++) st[(size_t)c * 3 + 2] = 1;
+    QC_CUDA(cudaMemcpy(d_uslew, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return QC_OK;
+}
 
 static FirCore *new_fircore(int C, int size, int nc, const std::vector<double> &imp)
 {
@@ -117,7 +179,7 @@ int Rxa::init(int C_, int in_size_, int dsp_size_, int in_rate_, int dsp_rate_, 
     if ((rc = make_fmd()) != QC_OK) return rc;
     agc = make_wcpagc(C, dsp_rate, 3);
     if (!shift || !adcmeter || !smeter || !agcmeter || !amd || !fmpll || !sntch || !agc) return QC_EINVAL;
-    return QC_OK;
+    return arm_upslew(0.0, 0.0);
 }
 
 void Rxa::release()
@@ -127,6 +189,8 @@ void Rxa::release()
     for (Resampler **p : {&rsmpin, &rsmpout}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     if (mid) cudaFree(mid); if (mid2) cudaFree(mid2); if (audio) cudaFree(audio);
     if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out); if (h_ring) free(h_ring);
+    if (d_uslew) cudaFree(d_uslew); if (d_cup) cudaFree(d_cup);
+    d_uslew = nullptr; d_cup = nullptr;
     mid = mid2 = audio = d_in = d_out = nullptr; h_ring = nullptr;
 }
 
@@ -275,6 +339,9 @@ int quisk_cuda_rxa_set_shift(qcRxa *p, int run, const double *shift_hz)
 }
 
 int quisk_cuda_rxa_set_nbp_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.nbp_run = run; return QC_OK; }
+int quisk_cuda_rxa_set_slew(qcRxa *p, double tdelayup, double tslewup)
+{ if (!p || tdelayup < 0 || tslewup < 0) return QC_EINVAL; return p->r.arm_upslew(tdelayup, tslewup); }
+
 int quisk_cuda_rxa_set_panel_gain(qcRxa *p, double g) { if (!p) return QC_EINVAL; p->r.panel_gain1 = g; return QC_OK; }
 
 int quisk_cuda_rxa_xrxa(qcRxa *p, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream)
@@ -298,6 +365,10 @@ int quisk_cuda_rxa_fexchange0(qcRxa *p, const double *h_in, double *h_out, int *
         r.ring_pos = 0;
     }
     QC_CUDA(cudaMemcpyAsync(r.d_in, h_in, nin * sizeof(cd), cudaMemcpyHostToDevice, r.hs));
+    // up-slew on the block as it enters r1 (iobuffs.c:475-476); channels whose flag has dropped return at once
+    upslew_kernel<<<(r.C + 63) / 64, 64, 0, r.hs>>>(r.d_in, r.dsp_insize, r.dsp_insize, r.C, r.d_uslew, r.d_cup, r.ndelup, r.ntup);
+    count_launch();
+    QC_CUDA_LAUNCH();
     int rc = r.xrxa(r.d_in, r.dsp_insize, r.d_out, r.dsp_outsize, r.hs); if (rc) return rc;
     double *slot = r.h_ring + (size_t)r.ring_pos * nout * 2;
     memcpy(h_out, slot, nout * sizeof(cd));                       // the block from two calls ago (zeros at first)

@@ -168,8 +168,8 @@ def main():
         inb[:n] = x[b * n:(b + 1) * n]; lib.xfmd(f); ys.append(inb[:n].copy())
     out["fmd/y"] = np.concatenate(ys)
     # ---- the whole channel through OpenChannel + fexchange0 (blocking output, zero slew times) ----
-    def run_channel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, setup, x, nblocks):
-        lib.OpenChannel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, 0, 1, 0.0, 0.0, 0.0, 0.0, 1)
+    def run_channel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, setup, x, nblocks, slew=(0.0, 0.0, 0.0, 0.0)):
+        lib.OpenChannel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, 0, 1, slew[0], slew[1], slew[2], slew[3], 1)
         setup(ch)
         out_size = in_size * out_rate // in_rate if out_rate <= in_rate else in_size * (out_rate // in_rate)
         err = C.c_int(0)
@@ -195,6 +195,10 @@ def main():
         lib.SetRXAAGCMode(ch, 3)
     x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
     out["rxa_usb/y"] = run_channel(0, 256, 256, 48000, 48000, 48000, setup_usb, x, 24)
+    # the same channel opened the way Quisk opens it (quisk_wdsp.py:79-80): 10 ms of zeros after the first non-zero
+    # sample, then a 25 ms raised-cosine ramp (upslew0, iobuffs.c:98-160); the stream starts with 100 zero samples
+    xs = x.copy(); xs[:100] = 0.0
+    out["rxa_usb_slew/y"] = run_channel(5, 256, 256, 48000, 48000, 48000, setup_usb, xs, 24, slew=(0.010, 0.025, 0.0, 0.010))
 
     def setup_default(ch):      # no mode set: bp1 still runs
         lib.SetRXAShiftRun(ch, 0)

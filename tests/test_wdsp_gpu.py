@@ -156,14 +156,15 @@ def _run_rxa(torch, lib, rxa, x, in_size, nblocks, use_fexchange=False):
 
 
 def _first_sample_swallowed(x):
-    """fexchange0's up-slew state machine zeroes the first non-zero input sample (iobuffs.c:110-128)."""
+    """fexchange0's up-slew state machine zeroes the first non-zero input sample (iobuffs.c:110-128).  Only for the
+    tests that drive xrxa directly: quisk_cuda_rxa_fexchange0 runs that state machine itself."""
     x = x.copy(); x[0] = 0.0
     return x
 
 
 def test_rxa_usb_channel(torch, lib, kat):
     """SURVEY 8(d) C3 scaled down: nbp0 (nc 2048) + wcpAGC mode 3 + panel, through the fexchange0-shaped entry."""
-    x = _first_sample_swallowed(sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2))))
+    x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
     rxa = lib.quisk_cuda_rxa_create(NCH, 256, 256, 48000, 48000, 48000)
     assert rxa, lib.quisk_cuda_last_error()
     assert lib.quisk_cuda_rxa_set_shift(rxa, 0, None) == 0
@@ -181,6 +182,29 @@ def test_rxa_usb_channel(torch, lib, kat):
     assert np.all(av < 0) and np.all(av > -60) and np.all(pk >= av - 1e-9)
     assert lib.quisk_cuda_rxa_get_meter(rxa, 2, av.ctypes.data, pk.ctypes.data, g.ctypes.data) == 0
     assert np.all(np.isfinite(g))
+    lib.quisk_cuda_rxa_destroy(rxa)
+
+
+def test_rxa_usb_channel_upslew(torch, lib, kat):
+    """The channel opened the way Quisk opens it (quisk_wdsp.py:79-80: tdelayup 10 ms, tslewup 25 ms): upslew0's
+    state machine (iobuffs.c:98-160) on a stream that starts with 100 zero samples -- zeros up to and including the
+    first non-zero sample, 480 + 1 more zeros, a 1200 + 1 sample raised-cosine ramp, then pass-through."""
+    x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    x[:100] = 0.0
+    rxa = lib.quisk_cuda_rxa_create(NCH, 256, 256, 48000, 48000, 48000)
+    assert rxa, lib.quisk_cuda_last_error()
+    assert lib.quisk_cuda_rxa_set_slew(rxa, 0.010, 0.025) == 0
+    assert lib.quisk_cuda_rxa_set_shift(rxa, 0, None) == 0
+    assert lib.quisk_cuda_rxa_set_nc(rxa, 2048) == 0
+    assert lib.quisk_cuda_rxa_set_mode(rxa, 1) == 0
+    assert lib.quisk_cuda_rxa_set_passband(rxa, 150.0, 2850.0) == 0
+    assert lib.quisk_cuda_rxa_set_agc_mode(rxa, 3) == 0
+    y = _run_rxa(torch, lib, rxa, x, 256, 24, use_fexchange=True)
+    ref = kat["rxa_usb_slew/y"]
+    assert np.array_equal(np.nonzero(ref)[0][:1], np.nonzero(y[0])[0][:1])       # same first non-zero output sample
+    for c in range(NCH):
+        assert O.rel_rms(y[c], ref) < 1e-11
+    assert O.rel_rms(y[0], kat["rxa_usb/y"]) > 1e-3                               # and the ramp is really there
     lib.quisk_cuda_rxa_destroy(rxa)
 
 
