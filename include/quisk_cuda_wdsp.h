@@ -96,6 +96,11 @@ int quisk_cuda_rxa_set_nbp_run(qcRxa *r, int run);                          /* R
  * tslewup.  A new handle starts armed with both times 0 (the first non-zero sample is still swallowed).  The
  * down-slew / flush of SetChannelState(ch, 0) is not reproduced. */
 int quisk_cuda_rxa_set_slew(qcRxa *rxa, double tdelayup, double tslewup);
+/* sip1 of create_rxa (RXA.c:392-401; xsiphon mode 0, siphon.c:96-129): the last 4096 samples of midbuff per channel,
+ * kept by default like the reference (run = 1).  quisk_cuda_rxa_get_siphon = RXAGetaSipF (complex_out 0: real parts)
+ * / RXAGetaSipF1 (complex_out 1: I/Q pairs) for all channels: h_out[channel][size] floats, newest sample last. */
+int quisk_cuda_rxa_set_siphon_run(qcRxa *rxa, int run);
+int quisk_cuda_rxa_get_siphon(qcRxa *rxa, float *h_out, int size, int complex_out);
 int quisk_cuda_rxa_set_panel_gain(qcRxa *r, double gain1);                  /* SetRXAPanelGain1                  */
 int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per channel consumed per xrxa  */
 int quisk_cuda_rxa_out_size(const qcRxa *r);     /* dsp_outsize: samples per channel produced per xrxa */

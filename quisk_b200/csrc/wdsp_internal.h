@@ -67,6 +67,6 @@ SeqStage *make_meter(int C, int rate, double tau_av, double tau_decay);
 void agc_set_mode(SeqStage *s, int mode);
 
 int launch_panel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C, double gainI, double gainQ,
-                 int inselect, int copy, cudaStream_t s);
+                 int inselect, int copy, cudaStream_t s, cd *sip = nullptr, int sipsize = 0, int sip_idx = 0);
 
 }  // namespace qc

@@ -35,6 +35,8 @@ struct Rxa {
     cd *mid = nullptr, *mid2 = nullptr, *audio = nullptr;
     // fexchange0 emulation: up-slew state per channel (iobuffs.c:47-160): [C][3] = ustate, ucount, upflag
     int ndelup = 0, ntup = 0; int *d_uslew = nullptr; double *d_cup = nullptr;
+    // sip1 (create_rxa, RXA.c:392-401: run 1, position 0, mode 0, 4096 samples): ring per channel, filled by the panel kernel
+    int sip_run = 1, sipsize = 4096, sip_idx = 0; cd *d_sip = nullptr; float *d_sipout = nullptr; int sipout_cap = 0;
     int arm_upslew(double tdelayup, double tslewup);
     cd *d_in = nullptr, *d_out = nullptr; double *h_ring = nullptr; int ring_blocks = 0, ring_pos = 0; cudaStream_t hs = nullptr;
 
@@ -179,6 +181,8 @@ int Rxa::init(int C_, int in_size_, int dsp_size_, int in_rate_, int dsp_rate_, 
     if ((rc = make_fmd()) != QC_OK) return rc;
     agc = make_wcpagc(C, dsp_rate, 3);
     if (!shift || !adcmeter || !smeter || !agcmeter || !amd || !fmpll || !sntch || !agc) return QC_EINVAL;
+    QC_CUDA(cudaMalloc((void **)&d_sip, (size_t)C * sipsize * sizeof(cd)));
+    QC_CUDA(cudaMemset(d_sip, 0, (size_t)C * sipsize * sizeof(cd)));
     return arm_upslew(0.0, 0.0);
 }
 
@@ -191,6 +195,8 @@ void Rxa::release()
     if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out); if (h_ring) free(h_ring);
     if (d_uslew) cudaFree(d_uslew); if (d_cup) cudaFree(d_cup);
     d_uslew = nullptr; d_cup = nullptr;
+    if (d_sip) cudaFree(d_sip); if (d_sipout) cudaFree(d_sipout);
+    d_sip = nullptr; d_sipout = nullptr; sipout_cap = 0;
     mid = mid2 = audio = d_in = d_out = nullptr; h_ring = nullptr;
 }
 
@@ -231,13 +237,16 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
     if (agc_run) { rc = agc->run(m, ms, mid2, ms, dsp_size, s); if (rc) return rc; m = mid2; }
     rc = agcmeter->run(m, ms, agc->d_state, 0, dsp_size, s); if (rc) return rc;
     // xpanel always applies gain1 * gain2 (F9), inselect 3, no copy
+    cd *sp = sip_run ? d_sip : nullptr;
+    const int sidx = sip_idx;
+    if (sip_run && dsp_size < sipsize) sip_idx = (sip_idx + dsp_size) & (sipsize - 1);       // siphon.c:124
     if (rsmpout) {
-        rc = launch_panel(m, ms, m, ms, dsp_size, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s); if (rc) return rc;
+        rc = launch_panel(m, ms, m, ms, dsp_size, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s, sp, sipsize, sidx); if (rc) return rc;
         int no = 0;
         rc = rsmpout->f->run(m, ms, dsp_size, dout, os, &no, 0, s); if (rc) return rc;
         if (no != dsp_outsize) { set_error("rxa: output resampler produced %d samples, expected %d", no, dsp_outsize); return QC_EINVAL; }
     } else {
-        rc = launch_panel(m, ms, (cd *)dout, os, dsp_size, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s); if (rc) return rc;
+        rc = launch_panel(m, ms, (cd *)dout, os, dsp_size, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s, sp, sipsize, sidx); if (rc) return rc;
     }
     return QC_OK;
 }
@@ -339,6 +348,40 @@ int quisk_cuda_rxa_set_shift(qcRxa *p, int run, const double *shift_hz)
 }
 
 int quisk_cuda_rxa_set_nbp_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.nbp_run = run; return QC_OK; }
+// suck + the float conversion of RXAGetaSipF / RXAGetaSipF1 (siphon.c:148-163, 183-211)
+__global__ void siphon_get_kernel(const cd *sip, int sipsize, int idx, int size, int C, int cpx, float *out)
+{
+    const long total = (long)size * C;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(t / size), i = (int)(t - (long)c * size);
+        const cd v = sip[(size_t)c * sipsize + ((idx - size + i) & (sipsize - 1))];
+        if (cpx) { out[2 * t] = (float)v.x; out[2 * t + 1] = (float)v.y; }
+        else out[t] = (float)v.x;
+    }
+}
+
+int quisk_cuda_rxa_set_siphon_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.sip_run = run ? 1 : 0; return QC_OK; }
+
+int quisk_cuda_rxa_get_siphon(qcRxa *p, float *h_out, int size, int complex_out)
+{
+    if (!p || !h_out) return QC_EINVAL;
+    Rxa &r = p->r;
+    if (size <= 0 || size > r.sipsize) { set_error("rxa_get_siphon: size must be in [1, %d]", r.sipsize); return QC_EINVAL; }
+    const size_t nfl = (size_t)r.C * size * (complex_out ? 2 : 1);
+    if ((int)nfl > r.sipout_cap) {
+        if (r.d_sipout) cudaFree(r.d_sipout);
+        r.d_sipout = nullptr; r.sipout_cap = 0;
+        QC_CUDA(cudaMalloc((void **)&r.d_sipout, nfl * sizeof(float)));
+        r.sipout_cap = (int)nfl;
+    }
+    QC_CUDA(cudaDeviceSynchronize());
+    siphon_get_kernel<<<(int)((nfl + 255) / 256 < 1184 ? (nfl + 255) / 256 : 1184), 256>>>(r.d_sip, r.sipsize, r.sip_idx, size, r.C, complex_out ? 1 : 0, r.d_sipout);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    QC_CUDA(cudaMemcpy(h_out, r.d_sipout, nfl * sizeof(float), cudaMemcpyDeviceToHost));
+    return QC_OK;
+}
+
 int quisk_cuda_rxa_set_slew(qcRxa *p, double tdelayup, double tslewup)
 { if (!p || tdelayup < 0 || tslewup < 0) return QC_EINVAL; return p->r.arm_upslew(tdelayup, tslewup); }
 

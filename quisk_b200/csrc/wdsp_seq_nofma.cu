@@ -379,13 +379,22 @@ __global__ void meter_kernel(const cd *in, long is, int n, int C, double *state,
     result[c * 3 + 2] = agc_state ? 20.0 * log10(agc_state[(size_t)c * 16 + 10] + 1.0e-40) : 0.0;
 }
 
-__global__ void panel_kernel(const cd *in, long is, cd *out, long os, int n, int C, double gainI, double gainQ, int inselect, int copy)
+// sip != nullptr: also xsiphon mode 0 (siphon.c:96-129) on the INPUT block -- between xsiphon and xpanel the chain only
+// has stages that are off by default (RXA.c:590-596), so the panel's input is what the siphon would see; the ring
+// write rides on this kernel instead of costing a launch: sample i goes to slot (sip_idx + i) mod sipsize, or the
+// last sipsize samples fill the ring when the block is at least that long.
+__global__ void panel_kernel(const cd *in, long is, cd *out, long os, int n, int C, double gainI, double gainQ, int inselect, int copy,
+                             cd *sip, int sipsize, int sip_idx)
 {
     const long total = (long)n * C;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int c = (int)(idx / n);
         const int i = (int)(idx - (long)c * n);
         const cd v = in[(size_t)c * is + i];
+        if (sip) {
+            if (n >= sipsize) { if (i >= n - sipsize) sip[(size_t)c * sipsize + (i - (n - sipsize))] = v; }
+            else sip[(size_t)c * sipsize + ((sip_idx + i) & (sipsize - 1))] = v;
+        }
         double I, Q;
         switch (copy) {
         case 1: I = v.x * (inselect >> 1); Q = I; break;
@@ -398,12 +407,12 @@ __global__ void panel_kernel(const cd *in, long is, cd *out, long os, int n, int
 }
 
 int launch_panel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C, double gainI, double gainQ,
-                 int inselect, int copy, cudaStream_t s)
+                 int inselect, int copy, cudaStream_t s, cd *sip, int sipsize, int sip_idx)
 {
     const long total = (long)n * C;
     if (total <= 0) return QC_OK;
     int blocks = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
-    panel_kernel<<<blocks, 256, 0, s>>>(in, in_stride, out, out_stride, n, C, gainI, gainQ, inselect, copy);
+    panel_kernel<<<blocks, 256, 0, s>>>(in, in_stride, out, out_stride, n, C, gainI, gainQ, inselect, copy, sip, sipsize, sip_idx);
     count_launch();
     QC_CUDA_LAUNCH();
     return QC_OK;

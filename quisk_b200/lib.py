@@ -145,6 +145,8 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_set_shift.argtypes = [vp, C.c_int, vp]
     lib.quisk_cuda_rxa_set_nbp_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_set_slew.argtypes = [vp, C.c_double, C.c_double]
+    lib.quisk_cuda_rxa_set_siphon_run.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_get_siphon.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.quisk_cuda_rxa_set_panel_gain.argtypes = [vp, D]
     lib.quisk_cuda_rxa_in_size.argtypes = [vp]
     lib.quisk_cuda_rxa_out_size.argtypes = [vp]

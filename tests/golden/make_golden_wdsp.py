@@ -50,6 +50,7 @@ def wdsp():
     lib.RXASetNC.argtypes = [C.c_int, C.c_int]
     lib.SetRXAAGCMode.argtypes = [C.c_int, C.c_int]
     lib.SetRXAShiftRun.argtypes = [C.c_int, C.c_int]
+    lib.RXAGetaSipF1.argtypes = [C.c_int, VP, C.c_int]
     return lib
 
 
@@ -168,6 +169,8 @@ def main():
         inb[:n] = x[b * n:(b + 1) * n]; lib.xfmd(f); ys.append(inb[:n].copy())
     out["fmd/y"] = np.concatenate(ys)
     # ---- the whole channel through OpenChannel + fexchange0 (blocking output, zero slew times) ----
+    siphons = {}
+
     def run_channel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, setup, x, nblocks, slew=(0.0, 0.0, 0.0, 0.0)):
         lib.OpenChannel(ch, in_size, dsp_size, in_rate, dsp_rate, out_rate, 0, 1, slew[0], slew[1], slew[2], slew[3], 1)
         setup(ch)
@@ -185,6 +188,9 @@ def main():
             # run ahead of the DSP thread and its output becomes timing dependent -- two identical runs
             # differ.  With pacing it is deterministic and equals the composition of its own stages.
             time.sleep(0.004)
+        sip = np.zeros(2 * 1024, dtype=np.float32)      # RXAGetaSipF1: the newest 1024 samples of midbuff as floats
+        lib.RXAGetaSipF1(ch, sip.ctypes.data, 1024)
+        siphons[ch] = sip
         return np.concatenate(ys)
 
     def setup_usb(ch):          # the C3 concretisation of SURVEY.md 8(d), scaled down
@@ -195,6 +201,7 @@ def main():
         lib.SetRXAAGCMode(ch, 3)
     x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
     out["rxa_usb/y"] = run_channel(0, 256, 256, 48000, 48000, 48000, setup_usb, x, 24)
+    out["rxa_usb/sip"] = siphons[0]
     # the same channel opened the way Quisk opens it (quisk_wdsp.py:79-80): 10 ms of zeros after the first non-zero
     # sample, then a 25 ms raised-cosine ramp (upslew0, iobuffs.c:98-160); the stream starts with 100 zero samples
     xs = x.copy(); xs[:100] = 0.0

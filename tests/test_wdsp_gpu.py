@@ -182,6 +182,15 @@ def test_rxa_usb_channel(torch, lib, kat):
     assert np.all(av < 0) and np.all(av > -60) and np.all(pk >= av - 1e-9)
     assert lib.quisk_cuda_rxa_get_meter(rxa, 2, av.ctypes.data, pk.ctypes.data, g.ctypes.data) == 0
     assert np.all(np.isfinite(g))
+    # sip1: the newest 1024 samples of midbuff after the last block, as RXAGetaSipF1 returns them (floats)
+    sip = np.zeros((NCH, 2 * 1024), dtype=np.float32)
+    assert lib.quisk_cuda_rxa_get_siphon(rxa, sip.ctypes.data, 1024, 1) == 0, lib.quisk_cuda_last_error()
+    rs = kat["rxa_usb/sip"].astype(np.float64)
+    for c in range(NCH):
+        assert np.sqrt(np.mean((sip[c] - rs) ** 2)) / np.sqrt(np.mean(rs ** 2)) < 1e-6       # float32 output
+    re = np.zeros((NCH, 1024), dtype=np.float32)
+    assert lib.quisk_cuda_rxa_get_siphon(rxa, re.ctypes.data, 1024, 0) == 0
+    assert np.array_equal(re[0], sip[0][0::2])
     lib.quisk_cuda_rxa_destroy(rxa)
 
 
