@@ -48,6 +48,7 @@ const cd *fft_twiddles(int n)
 // ---------------------------------------------------------------------------------------
 // plain batched transform
 // ---------------------------------------------------------------------------------------
+template <int BPT>
 __global__ void __launch_bounds__(256) fft_batch_kernel(const cd *in, cd *out, int n, int batch, const cd *tw, int sign)
 {
     extern __shared__ double smem_raw[];
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(256) fft_batch_kernel(const cd *in, cd *out, i
         for (int i = lane; i < n; i += lanes) s[fsw(i)] = src[i];
     }
     __syncthreads();
-    fft_smem(s, n, twl, sign, lane, lanes);
+    fft_smem<BPT>(s, n, twl, sign, lane, lanes);
     if (live) {
         cd *dst = out + (size_t)f * n;
         for (int i = lane; i < n; i += lanes) dst[i] = s[fsw(i)];
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) fft_batch_kernel(const cd *in, cd *out, i
 // ---------------------------------------------------------------------------------------
 static constexpr int PAN_MAX_OWN = 16;     // bins per thread: n / fft_threads(n) = 16
 
+template <int BPT>
 __global__ void __launch_bounds__(256) pan_accumulate_kernel(const cd *frames, long stream_stride, int n_frames, int n,
                                       const cd *tw, const double *window, double *avg, double *partial, int groups)
 {
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) pan_accumulate_kernel(const cd *frames, l
             s[fsw(i)] = make_double2(x.x * w, x.y * w);             // quisk.c:5212-5213
         }
         __syncthreads();
-        fft_smem(s, n, twl, -1, lane, lanes);
+        fft_smem<BPT>(s, n, twl, -1, lane, lanes);
         for (int k = lane; k < n; k += lanes) {                     // graph bin k <- FFT bin (k + n/2) mod n
             const cd X = s[fsw((k + half) & (n - 1))];
             sacc[k] += sqrt(fma(X.x, X.x, X.y * X.y));              // cabs, quisk.c:5273,5275 (no overflow at these scales)
@@ -110,6 +112,52 @@ __global__ void __launch_bounds__(256) pan_accumulate_kernel(const cd *frames, l
         __syncthreads();
     }
     for (int k = lane; k < n; k += lanes) dst[k] = sacc[k];
+}
+
+// n = 8192 split over TWO CTAs per frame.  One 8192-point transform needs 128 KiB of shared memory, i.e. one CTA of
+// 8 warps per SM with every load, barrier and pass exposed.  A decimation-in-frequency first step done on the way in
+// from global memory halves that:  X[2k] = FFT4096(x[j] + x[j+4096]),  X[2k+1] = FFT4096((x[j] - x[j+4096]) w^j),
+// so CTA parity p owns the bins of parity p, works on 64 KiB, runs one butterfly per thread (128 registers) and two
+// such CTAs share an SM.  Each frame is read by both CTAs of its pair (the second read is an L2 hit when the pair is
+// co-scheduled, which adjacent blockIdx.x makes the common case).  Bin sums keep the reference's frame order.
+__global__ void __launch_bounds__(256, 2) pan_accumulate_split_kernel(const cd *frames, long stream_stride, int n_frames,
+                                      const cd *tw8, const cd *tw4, const double *window, double *avg, double *partial, int groups)
+{
+    constexpr int N = 8192, H = 4096;
+    extern __shared__ double smem_raw[];
+    cd *twl4 = reinterpret_cast<cd *>(smem_raw);
+    cd *twl8 = twl4 + fft_tw_entries(H);
+    cd *s = twl8 + fft_tw_entries(N);
+    double *sacc = reinterpret_cast<double *>(s + H);        // [H] running sums of this CTA's bins
+    fft_stage_twiddles(twl4, tw4, H);
+    fft_stage_twiddles(twl8, tw8, N);
+    const int stream = blockIdx.y, g = blockIdx.x >> 1, par = blockIdx.x & 1;
+    const int lane = threadIdx.x, lanes = blockDim.x;
+    double *dst = groups == 1 ? avg + (size_t)stream * N : partial + ((size_t)stream * groups + g) * N;
+    // FFT bin b = 2 k + par shows at graph bin (b + H) mod N (fftshift, quisk.c:5271-5276)
+    for (int k = lane; k < H; k += lanes) sacc[k] = groups == 1 ? dst[(2 * k + par + H) & (N - 1)] : 0.0;
+    const cd *base = frames + (size_t)stream * stream_stride;
+    __syncthreads();
+    for (int f = g; f < n_frames; f += groups) {
+        const cd *src = base + (size_t)f * N;
+        for (int j = lane; j < H; j += lanes) {
+            const cd x0 = src[j], x1 = src[j + H];
+            const double w0 = window[j], w1 = window[j + H];
+            const cd a = make_double2(x0.x * w0, x0.y * w0), b = make_double2(x1.x * w1, x1.y * w1);      // quisk.c:5212-5213
+            cd v;
+            if (par == 0) v = cadd(a, b);
+            else v = cmul(csub(a, b), fft_tw(twl8, j, -1));
+            s[fsw(j)] = v;
+        }
+        __syncthreads();
+        fft_smem<1>(s, H, twl4, -1, lane, lanes);
+        for (int k = lane; k < H; k += lanes) {
+            const cd X = s[fsw(k)];
+            sacc[k] += sqrt(fma(X.x, X.x, X.y * X.y));
+        }
+        __syncthreads();
+    }
+    for (int k = lane; k < H; k += lanes) dst[(2 * k + par + H) & (N - 1)] = sacc[k];
 }
 
 __global__ void pan_reduce_kernel(double *avg, const double *partial, int n, int groups)
@@ -199,6 +247,7 @@ struct Panadapter {
     double *d_window = nullptr, *d_avg = nullptr, *d_partial = nullptr;
     int partial_groups = 0;
     int count = 0;
+    int split8192 = 1;          // 8192-point frames: two 4096-point CTAs per frame (pan_accumulate_split_kernel)
 
     int init(int streams, int fft_size)
     {
@@ -247,9 +296,15 @@ int quisk_cuda_fft_batch(const void *d_in, void *d_out, int n, int batch, int si
     int lanes, per;
     fft_shape(n, &lanes, &per);
     const size_t sh = ((size_t)per * n + fft_tw_entries(n)) * sizeof(cd);
-    int rc = fft_smem_optin((const void *)fft_batch_kernel, sh); if (rc != QC_OK) return rc;
     dim3 block(lanes, per);
-    fft_batch_kernel<<<(batch + per - 1) / per, block, sh, (cudaStream_t)stream>>>((const cd *)d_in, (cd *)d_out, n, batch, tw, sign < 0 ? -1 : 1);
+    int rc;
+    if (n > 4096) {
+        rc = fft_smem_optin((const void *)fft_batch_kernel<2>, sh); if (rc != QC_OK) return rc;
+        fft_batch_kernel<2><<<(batch + per - 1) / per, block, sh, (cudaStream_t)stream>>>((const cd *)d_in, (cd *)d_out, n, batch, tw, sign < 0 ? -1 : 1);
+    } else {
+        rc = fft_smem_optin((const void *)fft_batch_kernel<1>, sh); if (rc != QC_OK) return rc;
+        fft_batch_kernel<1><<<(batch + per - 1) / per, block, sh, (cudaStream_t)stream>>>((const cd *)d_in, (cd *)d_out, n, batch, tw, sign < 0 ? -1 : 1);
+    }
     count_launch();
     QC_CUDA_LAUNCH();
     return QC_OK;
@@ -287,10 +342,26 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
         p.partial_groups = groups;
     }
     const int lanes = fft_threads(p.n);
-    const size_t sh = (size_t)p.n * (sizeof(cd) + sizeof(double)) + (size_t)fft_tw_entries(p.n) * sizeof(cd);
-    int rc = fft_smem_optin((const void *)pan_accumulate_kernel, sh); if (rc != QC_OK) return rc;
-    pan_accumulate_kernel<<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.tw,
-                                                                 p.d_window, p.d_avg, p.d_partial, groups);
+    int rc;
+    if (p.n == 8192 && p.split8192) {
+        const cd *tw4 = fft_twiddles(4096);
+        if (!tw4) { set_error("pan_accumulate: twiddle table allocation failed"); return QC_ENOMEM; }
+        const size_t sh = (size_t)4096 * (sizeof(cd) + sizeof(double)) + (size_t)(fft_tw_entries(4096) + fft_tw_entries(8192)) * sizeof(cd);
+        rc = fft_smem_optin((const void *)pan_accumulate_split_kernel, sh); if (rc != QC_OK) return rc;
+        pan_accumulate_split_kernel<<<dim3(2 * groups, p.S), 256, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.tw, tw4,
+                                                                           p.d_window, p.d_avg, p.d_partial, groups);
+    } else {
+        const size_t sh = (size_t)p.n * (sizeof(cd) + sizeof(double)) + (size_t)fft_tw_entries(p.n) * sizeof(cd);
+        if (p.n > 4096) {
+            rc = fft_smem_optin((const void *)pan_accumulate_kernel<2>, sh); if (rc != QC_OK) return rc;
+            pan_accumulate_kernel<2><<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.tw,
+                                                                            p.d_window, p.d_avg, p.d_partial, groups);
+        } else {
+            rc = fft_smem_optin((const void *)pan_accumulate_kernel<1>, sh); if (rc != QC_OK) return rc;
+            pan_accumulate_kernel<1><<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.tw,
+                                                                            p.d_window, p.d_avg, p.d_partial, groups);
+        }
+    }
     count_launch();
     QC_CUDA_LAUNCH();
     if (groups > 1) {

@@ -20,6 +20,9 @@
 namespace qc {
 
 
+// BPT = radix-16 butterflies per thread in the transforms: 1 whenever 2 size <= 4096 (every RXA configuration here),
+// which halves the registers and doubles the resident CTAs; 2 only for the 8192-point case.
+template <int BPT>
 __global__ void __launch_bounds__(256) fircore_kernel(const cd *in, long in_stride, cd *out, long out_stride,
                                                        int size, int nfor, int buffidx,
                                                        cd *prev /*[C][size]*/, cd *fdl /*[C][nfor][2 size]*/,
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(256) fircore_kernel(const cd *in, long in_stri
         pv[i] = v;
     }
     __syncthreads();
-    fft_smem(s, n2, twl, -1, lane, lanes);
+    fft_smem<BPT>(s, n2, twl, -1, lane, lanes);
     // partition MAC; bins lane, lane + lanes, ... are this thread's alone, so each accumulator replaces its
     // bin in shared memory without a barrier
     cd *fd = fdl + (size_t)c * nfor * n2;
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(256) fircore_kernel(const cd *in, long in_stri
         s[fsw(i)] = acc;
     }
     __syncthreads();
-    fft_smem(s, n2, twl, +1, lane, lanes);
+    fft_smem<BPT>(s, n2, twl, +1, lane, lanes);
     cd *y = out + (size_t)c * out_stride;
     for (int i = lane; i < size; i += lanes) y[i] = s[fsw(i)];
 }
@@ -129,9 +132,15 @@ int FirCore::run(const void *d_in, long in_stride, void *d_out, long out_stride,
 {
     const int lanes = fft_threads(n2);
     const size_t sh = ((size_t)n2 + fft_tw_entries(n2)) * sizeof(cd);
-    if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(fircore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    fircore_kernel<<<C, lanes, sh, s>>>((const cd *)d_in, in_stride, (cd *)d_out, out_stride, size, nfor, buffidx,
-                                        d_prev, d_fdl, d_mask[cset], tw);
+    if (n2 > 4096) {
+        QC_CUDA(cudaFuncSetAttribute(fircore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        fircore_kernel<2><<<C, lanes, sh, s>>>((const cd *)d_in, in_stride, (cd *)d_out, out_stride, size, nfor, buffidx,
+                                               d_prev, d_fdl, d_mask[cset], tw);
+    } else {
+        if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(fircore_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        fircore_kernel<1><<<C, lanes, sh, s>>>((const cd *)d_in, in_stride, (cd *)d_out, out_stride, size, nfor, buffidx,
+                                               d_prev, d_fdl, d_mask[cset], tw);
+    }
     count_launch();
     QC_CUDA_LAUNCH();
     buffidx = (buffidx + 1) & (nfor - 1);
