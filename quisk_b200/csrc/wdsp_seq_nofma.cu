@@ -136,9 +136,13 @@ __global__ void __launch_bounds__(128) wcpagc_kernel(const cd *in, long is, cd *
         double volts = st[3], save_volts = st[4], fast_backaverage = st[5], hang_backaverage = st[6];
         int hang_counter = (int)st[7], decay_type = (int)st[8], state_ = (int)st[9];
         double last_rm = 0.0;
+        // the next sample's inputs are fetched one step ahead: the shared-memory latency would otherwise sit in
+        // front of every step of this dependent chain
+        double na = A[0], nr = RV[0];
         for (int i = 0; i < n; i++) {
-            const double abs_out_sample = A[i];
-            const double ring_max = RV[i];
+            const double abs_out_sample = na;
+            const double ring_max = nr;
+            if (i + 1 < n) { na = A[i + 1]; nr = RV[i + 1]; }
             last_rm = ring_max;
             fast_backaverage = a.fast_backmult * abs_out_sample + a.onemfast_backmult * fast_backaverage;
             hang_backaverage = a.hang_backmult * abs_out_sample + a.onemhang_backmult * hang_backaverage;
