@@ -66,10 +66,20 @@ def _worker(rank, world, port, n_channels, q):
     y = y[len(y) - blk.out_count:] if blk.out_count else y[:0]
     parts = [None] * world
     dist.all_gather_object(parts, (blk.out_start, y))
+    # --- the C5 channelizer sharded the same way: a rank starts at halo_start with the ABSOLUTE sample index (receiver
+    #     phases and frame alignment follow from it, quisk_cuda_pfb_seek) and drops the frames inside its halo
+    K, D, P = 64, 32, 4
+    proto = np.hanning(K * P) / (K * P)
+    xw = O.synth_iq(64 * D, 998, 1.0)
+    tb = shard.time_blocks(len(xw), world, D, K * P - 1)[rank]
+    yc = O.channelizer_oracle(xw[tb.halo_start:tb.stop], [0, 5, K - 1], proto, K, D, n0=tb.halo_start)
+    yc = yc[:, yc.shape[1] - tb.out_count:]
+    cparts = [None] * world
+    dist.all_gather_object(cparts, (tb.out_start, yc))
     # max-over-ranks reduction of a per-rank time, as bench.py does
     t = torch.tensor([float(rank + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        q.put((np.concatenate(gathered), sizes, parts, float(t.item())))
+        q.put((np.concatenate(gathered), sizes, parts, float(t.item()), cparts))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -85,7 +95,7 @@ def test_world2_gloo_sharding_matches_single_process():
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_channels, q)) for r in range(world)]
     for p in procs: p.start()
-    got, sizes, parts, tmax = q.get(timeout=60)
+    got, sizes, parts, tmax, cparts = q.get(timeout=60)
     for p in procs: p.join(timeout=30)
     assert all(p.exitcode == 0 for p in procs)
     assert sizes == [(0, 3), (3, 5)] and tmax == 2.0
@@ -97,3 +107,11 @@ def test_world2_gloo_sharding_matches_single_process():
     stitched = np.concatenate([y for _, y in sorted(parts, key=lambda t: t[0])])
     assert len(stitched) == len(seq) == 8192
     assert O.rel_rms(stitched, seq) < 1e-14
+    # channelizer: the stitched shards are the sequential frames exactly (same arithmetic on the same samples)
+    K, D, P = 64, 32, 4
+    proto = np.hanning(K * P) / (K * P)
+    xw = O.synth_iq(64 * D, 998, 1.0)
+    cseq = O.channelizer_oracle(xw, [0, 5, K - 1], proto, K, D)
+    cst = np.concatenate([y for _, y in sorted(cparts, key=lambda t: t[0])], axis=1)
+    assert cst.shape == cseq.shape == (3, 64)
+    assert np.array_equal(cst, cseq)
