@@ -156,7 +156,7 @@ __device__ __forceinline__ cd pfb_load(const cd *__restrict__ in, const cd *__re
 static constexpr int PFB_BR = 64;       // branches per 128-thread CTA
 static constexpr int PFB_RING = 16;     // cp.async ring depth in steps (power of two)
 
-template <int P, int OVS>
+template <int P, int OVS, int RING>
 __global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirParams p)
 {
     constexpr int PH = P / 2;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirP
     // New samples arrive through a per-lane cp.async ring RING steps deep: what hides the HBM latency is bytes in
     // flight (16 warps x 16 lanes x 16 B x RING = 64 KB per SM), and shared memory holds them without registers.
     // A lane only ever reads what it copied itself, so cp.async.wait_group is the only synchronisation.
-    __shared__ cd ring[PFB_RING][PFB_BR];
+    __shared__ cd ring[RING][PFB_BR];
     const int rl = (threadIdx.x >> 5) * 16 + (lane & 15);
     auto issue = [&](int step) {
         if (!half) {
@@ -199,13 +199,13 @@ __global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirP
                 if (e >= 0) { if (e < p.count) { src = in + e; bytes = 16; } }
                 else if (e >= -p.H) { src = he + e; bytes = 16; }
             }
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[step & (PFB_RING - 1)][rl]);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[step & (RING - 1)][rl]);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll 1
-    for (int j = 0; j < PFB_RING - 2; j++) issue(j);
+    for (int j = 0; j < RING - 2; j++) issue(j);
     cd *uo = p.u + r;
     for (int i = 0; i < steps; i += PH) {
 #pragma unroll
@@ -214,9 +214,9 @@ __global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirP
                 const cd old = w[j];                                            // age PH of the young half = age 0 of the old one
                 const double ox = __shfl_sync(0xffffffffu, old.x, lane & 15), oy = __shfl_sync(0xffffffffu, old.y, lane & 15);
                 // the slot this overwrites was read two steps ago and that value has been consumed since
-                issue(i + j + PFB_RING - 2);
-                asm volatile("cp.async.wait_group %0;" ::"n"(PFB_RING - 2) : "memory");
-                w[j] = half ? make_double2(ox, oy) : ring[(i + j) & (PFB_RING - 1)][rl];
+                issue(i + j + RING - 2);
+                asm volatile("cp.async.wait_group %0;" ::"n"(RING - 2) : "memory");
+                w[j] = half ? make_double2(ox, oy) : ring[(i + j) & (RING - 1)][rl];
                 double xr = 0.0, xi = 0.0, yr = 0.0, yi = 0.0;
 #pragma unroll
                 for (int t = 0; t < PH; t++) {
@@ -243,23 +243,23 @@ __global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirP
 //   pass 3: 16 / R3 radix-R3 butterflies per thread, no twiddles, results from registers to global memory:
 //           channel-major, the four frames of a channel are one 64-byte run; frame-major, 128-byte runs per frame.
 // One shared-memory round trip per pass boundary and three barriers per four transforms.
-template <int R3>
-__global__ void __launch_bounds__(256, 2) pfb_fft_kernel(const cd *__restrict__ u, int nf, const cd *__restrict__ tw,
-                                                        cd *__restrict__ out, long out_stride, long frame0, int layout)
+template <int R3, int PFI>
+__global__ void __launch_bounds__(64 * PFI, 8 / PFI) pfb_fft_kernel(const cd *__restrict__ u, int nf, const cd *__restrict__ tw,
+                                                                 cd *__restrict__ out, long out_stride, long frame0, int layout)
 {
-    constexpr int K = 256 * R3, N1 = K / 16;            // N1 = lanes per transform
+    constexpr int K = 256 * R3, N1 = K / 16;            // N1 = lanes per transform; PFI = frames interleaved per CTA (2 or 4)
     extern __shared__ double smem_raw[];
     cd *twl = reinterpret_cast<cd *>(smem_raw);
-    cd *sb = twl + fft_tw_entries(K);                   // [K][4]
-    const int tid = threadIdx.x, f = tid & 3, b = tid >> 2;
+    cd *sb = twl + fft_tw_entries(K);                   // [K][PFI]
+    const int tid = threadIdx.x, f = tid % PFI, b = tid / PFI;
     const int g = blockIdx.x;
-    const bool live = g * PF + f < nf;                  // ragged last group: the thread still takes part in barriers
+    const bool live = g * PFI + f < nf;                  // ragged last group: the thread still takes part in barriers
     fft_stage_twiddles(twl, tw, K);
-    auto slot = [f](int i) { return 4 * (i ^ ((i >> 4) & 1)) + f; };
+    auto slot = [f](int i) { return PFI * (i ^ ((i >> 4) & (8 / PFI - 1))) + f; };
     cd v[16];
     // ---- pass 1: len K, stride 1, butterfly p = b
     {
-        const cd *src = u + ((size_t)g * PF + f) * K + b;
+        const cd *src = u + ((size_t)g * PFI + f) * K + b;
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = live ? src[j * N1] : make_double2(0.0, 0.0);
         dft16(v, -1.0);
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256, 2) pfb_fft_kernel(const cd *__restrict__ 
     }
     if (!live) return;
     // ---- results: v[t R3 + k] = X[b + N1 t + 256 k]  (R3 = 1: v[k] = X[b + 16 k])
-    const long fr = frame0 + (long)g * PF + f;
+    const long fr = frame0 + (long)g * PFI + f;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         const int ch = R3 == 1 ? b + 16 * e : b + N1 * (e / R3) + 256 * (e % R3);
@@ -338,6 +338,8 @@ struct Channelizer {
     int n_sm = 148;
     int slice_frames = 1 << 16;     // frames of u per kernel pair; smaller slices were measured slower (launch gaps outweigh L2 reuse)
     int force_generic = 0;
+    int ring = 16;                  // cp.async ring depth of the branch kernel in steps (16 or 32)
+    int fft_frames = 2;             // frames interleaved per transform CTA (2: four CTAs per SM, measured 5 % faster; 4: 64-byte output runs)
     cd *d_u = nullptr; int u_frames = 0, u_bufs = 0;        // one slice of u (two back to back when pipelining)
     int pipeline = 0;               // 1: branch FIRs of slice i+1 overlap the transforms of slice i on two internal streams
     cudaStream_t sa = nullptr, sb = nullptr;
@@ -403,7 +405,8 @@ struct Channelizer {
     }
     template <int PP, int OVS> int launch_fir(const PfbFirParams &q, dim3 grid, cudaStream_t s)
     {
-        pfb_fir_kernel<PP, OVS><<<grid, 128, 0, s>>>(q);
+        if (ring == 32) pfb_fir_kernel<PP, OVS, 32><<<grid, 128, 0, s>>>(q);
+        else pfb_fir_kernel<PP, OVS, 16><<<grid, 128, 0, s>>>(q);
         return QC_OK;
     }
     // D = K or K/2: slices of (register FIR kernel, transform kernel)
@@ -436,10 +439,11 @@ struct Channelizer {
             QC_CUDA(cudaStreamWaitEvent(sb, ev_edge, 0));
             s_fir = sa; s_fft = sb;
         }
-        const size_t sh = ((size_t)fft_tw_entries(K) + (size_t)PF * K) * sizeof(cd);
+        const int pfi = fft_frames == 2 ? 2 : 4;
+        const size_t sh = ((size_t)fft_tw_entries(K) + (size_t)pfi * K) * sizeof(cd);
         if (sh > 48 * 1024) {
-            if (K == 1024) QC_CUDA(cudaFuncSetAttribute(pfb_fft_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-            if (K == 512) QC_CUDA(cudaFuncSetAttribute(pfb_fft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            if (K == 1024 && pfi == 4) QC_CUDA(cudaFuncSetAttribute(pfb_fft_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            if (K == 512 && pfi == 4) QC_CUDA(cudaFuncSetAttribute(pfb_fft_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         }
         const long long m0 = n_abs / D;
         for (int f0 = 0, si = 0; f0 < nf; f0 += sf, si++) {
@@ -467,10 +471,11 @@ struct Channelizer {
             count_launch();
             QC_CUDA_LAUNCH();
             if (pipe) { QC_CUDA(cudaEventRecord(ev_fir[si & 1], sa)); QC_CUDA(cudaStreamWaitEvent(sb, ev_fir[si & 1], 0)); }
-            const int gf = (nfs + PF - 1) / PF;
-            if (K == 1024) pfb_fft_kernel<4><<<gf, K / 4, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout);
-            else if (K == 512) pfb_fft_kernel<2><<<gf, K / 4, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout);
-            else pfb_fft_kernel<1><<<gf, K / 4, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout);
+            const int gf = (nfs + pfi - 1) / pfi, nth = pfi * K / 16;
+#define PFB_FFT(R3) do { if (pfi == 4) pfb_fft_kernel<R3, 4><<<gf, nth, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout); \
+                         else pfb_fft_kernel<R3, 2><<<gf, nth, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout); } while (0)
+            if (K == 1024) PFB_FFT(4); else if (K == 512) PFB_FFT(2); else PFB_FFT(1);
+#undef PFB_FFT
             count_launch();
             QC_CUDA_LAUNCH();
             if (pipe) QC_CUDA(cudaEventRecord(ev_fft[si & 1], sb));
@@ -541,6 +546,8 @@ int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value)
     case QC_PFB_OPT_SLICE_FRAMES: if (value < 4) return QC_EINVAL; p->c.slice_frames = value; return QC_OK;
     case QC_PFB_OPT_GENERIC: p->c.force_generic = value ? 1 : 0; return QC_OK;
     case QC_PFB_OPT_PIPELINE: p->c.pipeline = value ? 1 : 0; return QC_OK;
+    case QC_PFB_OPT_RING: if (value != 16 && value != 32) return QC_EINVAL; p->c.ring = value; return QC_OK;
+    case QC_PFB_OPT_FFT_FRAMES: if (value != 2 && value != 4) return QC_EINVAL; p->c.fft_frames = value; return QC_OK;
     }
     qc::set_error("pfb_set_option: unknown option %d", option);
     return QC_EINVAL;

@@ -147,33 +147,26 @@ __global__ void __launch_bounds__(128) wcpagc_kernel(const cd *in, long is, cd *
             fast_backaverage = a.fast_backmult * abs_out_sample + a.onemfast_backmult * fast_backaverage;
             hang_backaverage = a.hang_backmult * abs_out_sample + a.onemhang_backmult * hang_backaverage;
             if (hang_counter > 0) --hang_counter;
-            switch (state_) {
-            case 0:
-                if (ring_max >= volts) volts += (ring_max - volts) * a.attack_mult;
-                else if (volts > a.pop_ratio * fast_backaverage) { state_ = 1; volts += (ring_max - volts) * a.fast_decay_mult; }
+            // The five cases of wcpAGC.c:215-333 all end in "volts += (ring_max - volts) * mult" or leave volts alone:
+            // pick the next state and the multiplier with compares, then update in ONE place -- same arithmetic and
+            // the same order of tests as the reference, but one short dependent chain instead of five code paths.
+            double m = 0.0;                 // 0: volts stays (the hang entries)
+            if (ring_max >= volts) {
+                if (state_ >= 2) save_volts = volts;
+                state_ = 0; m = a.attack_mult;
+            } else if (state_ == 0) {
+                if (volts > a.pop_ratio * fast_backaverage) { state_ = 1; m = a.fast_decay_mult; }
                 else if (a.hang_enable && hang_backaverage > a.hang_level) { state_ = 2; hang_counter = (int)(a.hangtime * a.sample_rate); decay_type = 1; }
-                else { state_ = 3; volts += (ring_max - volts) * a.decay_mult; decay_type = 0; }
-                break;
-            case 1:
-                if (ring_max >= volts) { state_ = 0; volts += (ring_max - volts) * a.attack_mult; }
-                else if (volts > save_volts) volts += (ring_max - volts) * a.fast_decay_mult;
+                else { state_ = 3; m = a.decay_mult; decay_type = 0; }
+            } else if (state_ == 1) {
+                if (volts > save_volts) m = a.fast_decay_mult;
                 else if (hang_counter > 0) state_ = 2;
-                else if (decay_type == 0) { state_ = 3; volts += (ring_max - volts) * a.decay_mult; }
-                else { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
-                break;
-            case 2:
-                if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
-                else if (hang_counter == 0) { state_ = 4; volts += (ring_max - volts) * a.hang_decay_mult; }
-                break;
-            case 3:
-                if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
-                else volts += (ring_max - volts) * a.decay_mult;
-                break;
-            case 4:
-                if (ring_max >= volts) { state_ = 0; save_volts = volts; volts += (ring_max - volts) * a.attack_mult; }
-                else volts += (ring_max - volts) * a.hang_decay_mult;
-                break;
-            }
+                else if (decay_type == 0) { state_ = 3; m = a.decay_mult; }
+                else { state_ = 4; m = a.hang_decay_mult; }
+            } else if (state_ == 2) {
+                if (hang_counter == 0) { state_ = 4; m = a.hang_decay_mult; }
+            } else m = state_ == 3 ? a.decay_mult : a.hang_decay_mult;
+            if (m != 0.0) volts += (ring_max - volts) * m;
             if (volts < a.min_volts) volts = a.min_volts;
             RV[i] = volts;
         }

@@ -9,7 +9,7 @@ python bench.py --workload channelizer > gpurun_out/bench_r1_channelizer.json 2>
 python bench.py --workload panadapter --channels 16 --block 1048576 --no-cpu-baseline > gpurun_out/bench_r1_pan16.json 2>/dev/null; tail -c 300 gpurun_out/bench_r1_pan16.json
 python bench.py --workload rxa_usb --no-cpu-baseline > gpurun_out/bench_r1_rxa_usb.json 2>/dev/null
 python bench.py --workload rxa_fm --no-cpu-baseline > gpurun_out/bench_r1_rxa_fm.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"qc::|fused_decim|rx_tail" -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fused_decim|rx_tail|nco_|polyfir|hb45|unpack|demod|tune_" -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:pfb -c 8 --csv --log-file gpurun_out/launches_r1_channelizer.csv python bench.py --workload channelizer --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 tail -3 gpurun_out/launches_r1_channelizer.csv | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pan -c 12 --csv --log-file gpurun_out/launches_r1_panadapter.csv python bench.py --workload panadapter --channels 16 --block 1048576 --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
