@@ -3,7 +3,8 @@
 reference's own CPU implementation.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload rx_chain|panadapter|rx_chain+panadapter] [--channels C] [--block B]
+                    [--workload rx_chain|panadapter|rx_chain+panadapter|rxa_usb|rxa_fm|channelizer]
+                    [--channels C] [--block B] [--nco exact|closed]
 
 One "step" = one pass of the hot path over one block of synthetic IQ for every channel:
   rx_chain    C independent receivers at 1.536 MS/s (BASELINE.json configs[0] batched): tune NCO ->
@@ -12,9 +13,14 @@ One "step" = one pass of the hot path over one block of synthetic IQ for every c
               quisk_dInterp2HB45 -> 48 kS/s audio.
   panadapter  BASELINE.json configs[1] batched: 8192-point Hann/FFT/|X| accumulation of every input
               frame of every channel, one dB graph per channel per step.
+  rxa_usb     BASELINE.json configs[2]: C WDSP RXA channels at 192 kS/s, nbp0 overlap-save band-pass (4096 taps) +
+              wcpAGC + panel, 32 DSP blocks of 1024 samples per step.
+  rxa_fm      configs[3]: C channels at 384 kS/s, resample /8 + nbp0 + fmd FM demodulator.
+  channelizer configs[4]: one 98.304 MS/s stream -> 1024 receivers x 192 kS/s through the polyphase channelizer; with
+              N > 1 every rank takes its own time block of the stream (halo in front, no inter-GPU traffic).
 metric = complex input MS/s, whole job.  `value` is timed with inputs resident in HBM; `e2e` is the
 same work through the host-buffer C-ABI entry point (H2D of the block + D2H of the audio inside the
-timed region).  With N > 1 (torchrun) every rank runs its own C channels -- independent receivers,
+timed region); `e2e_wire` (rx_chain only, extra key) is that step from int16 wire-format host blocks.  With N > 1 (torchrun) every rank runs its own C channels -- independent receivers,
 no data-path collective -- and the time is the max over ranks ("weak" scaling).
 
 --impl reference times the reference's own C code (oracle/_ref: filter.c verbatim + the quisk.c RX

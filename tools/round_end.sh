@@ -14,6 +14,6 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 tail -3 gpurun_out/launches_r1_channelizer.csv | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pan -c 12 --csv --log-file gpurun_out/launches_r1_panadapter.csv python bench.py --workload panadapter --channels 16 --block 1048576 --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 python bench.py --nco closed --no-cpu-baseline > gpurun_out/bench_r1_n1_nco_closed.json 2>/dev/null
-ncu --section SpeedOfLight --section WarpStateStats --section MemoryWorkloadAnalysis --section Occupancy --section SchedulerStats --section LaunchStats --clock-control none -k regex:pfb_f -c 2 -f -o gpurun_out/prof_pfb_r1 python tools_pfb2.py 65536 0 > /dev/null 2>&1
+ncu --section SpeedOfLight --section WarpStateStats --section MemoryWorkloadAnalysis --section Occupancy --section SchedulerStats --section LaunchStats --clock-control none -k regex:pfb_f -c 2 -f -o gpurun_out/prof_pfb_r1 python tools/pfb_once.py 65536 0 > /dev/null 2>&1
 ncu --section SpeedOfLight --section WarpStateStats --section MemoryWorkloadAnalysis --section Occupancy --section SchedulerStats --section LaunchStats --clock-control none -k regex:pan_accumulate -c 1 -f -o gpurun_out/prof_pan_r1 python bench.py --workload panadapter --channels 16 --block 1048576 --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools_sweep.sh "<bench args>" ...   -- prints one summary line per configuration
+# usage: tools/sweep.sh "<bench args>" ...   -- prints one summary line per configuration
 for cfg in "$@"; do
   python bench.py --steps 5 --no-cpu-baseline --e2e-steps 0 $cfg 2>&1 | tail -1 | python -c "
 import sys,json

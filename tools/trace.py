@@ -1,7 +1,7 @@
 """Debug helper: per-phase clock64() timeline of the fused decimator (not part of the product)."""
 import sys, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from quisk_b200.rx import RxChain, load_tables
 from quisk_b200 import lib as L
 C_, n = int(sys.argv[1]) if len(sys.argv) > 1 else 1184, 32768
