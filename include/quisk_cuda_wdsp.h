@@ -32,6 +32,14 @@ int quisk_cuda_fc_impulse(int nc, double f0, double f1, double g0, double g1, in
 int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_in, double gain,
                                int *L, int *M, int *ncoef, double *h, int h_cap);
 
+/* calc_nbp_impulse with the notches running (wdsp/nbp.c:64-179, 214-239): the pass band [flow, fhigh] minus the active
+ * notches of the database (centres / widths in RF coordinates, offset = tunefreq + shift), designed piecewise with
+ * fir_bandpass and summed.  impulse: nc complex.  Bit-identical to the reference's taps. */
+int quisk_cuda_nbp_impulse(int nc, double flow, double fhigh, double rate, int wintype, double scale,
+                           int n_notches, const double *fcenter, const double *fwidth, const int *active,
+                           double tunefreq, double shift, int autoincr, int maxpb,
+                           double *impulse, int *numpb, int *havnotch);
+
 /* ---- fircore: uniformly partitioned overlap-save complex FIR (wdsp/firmin.c:290-430) ---- */
 typedef struct qcFircore qcFircore;
 /* impulse: HOST, nc complex, the same for every channel (callers bake 1/(2*size) into it exactly as
@@ -101,6 +109,13 @@ int quisk_cuda_rxa_set_slew(qcRxa *rxa, double tdelayup, double tslewup);
  * / RXAGetaSipF1 (complex_out 1: I/Q pairs) for all channels: h_out[channel][size] floats, newest sample last. */
 int quisk_cuda_rxa_set_siphon_run(qcRxa *rxa, int run);
 int quisk_cuda_rxa_get_siphon(qcRxa *rxa, float *h_out, int size, int complex_out);
+/* Notch database of nbp0 (RXANBPAddNotch / DeleteNotch / SetNotchesRun / SetTuneFrequency / SetShiftFrequency,
+ * nbp.c:359-513): one database per handle, applied to every channel of the batch. */
+int quisk_cuda_rxa_nbp_add_notch(qcRxa *rxa, int notch, double fcenter, double fwidth, int active);
+int quisk_cuda_rxa_nbp_delete_notch(qcRxa *rxa, int notch);
+int quisk_cuda_rxa_nbp_set_notches_run(qcRxa *rxa, int run);
+int quisk_cuda_rxa_nbp_set_tune_frequency(qcRxa *rxa, double tunefreq);
+int quisk_cuda_rxa_nbp_set_shift_frequency(qcRxa *rxa, double shift);
 int quisk_cuda_rxa_set_panel_gain(qcRxa *r, double gain1);                  /* SetRXAPanelGain1                  */
 int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per channel consumed per xrxa  */
 int quisk_cuda_rxa_out_size(const qcRxa *r);     /* dsp_outsize: samples per channel produced per xrxa */

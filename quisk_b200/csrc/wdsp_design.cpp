@@ -7,6 +7,7 @@
 //   fir_fsamp(_odd)     wdsp/fir.c:84-180    frequency-sampling design
 //   fc_impulse          wdsp/fcurve.c:29-143 FM (de-)emphasis curve
 //   calc_resample       wdsp/resample.c:35-78 L/M, tap count and prototype of the rational resampler
+//   make_nbp, fir_mbandpass, min_notch_width  wdsp/nbp.c:64-179   notched band-pass (notch database -> pass bands -> taps)
 // with the same expression order, so the doubles that come out are the reference's.
 #include <cmath>
 #include <cstdlib>
@@ -180,4 +181,68 @@ int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_i
     return QC_OK;
 }
 
+
+/* calc_nbp_impulse with fnfrun = 1 (nbp.c:214-239): the pass band [flow, fhigh] is cut up by the active notches
+ * (make_nbp, nbp.c:97-179, working in RF coordinates: offset = tunefreq + shift), the pieces are designed with
+ * fir_bandpass and summed (fir_mbandpass, nbp.c:64-80).  Same statement order as the reference, so the taps are
+ * the reference's doubles. */
+int quisk_cuda_nbp_impulse(int nc, double flow, double fhigh, double rate, int wintype, double scale,
+                           int n_notches, const double *fcenter, const double *fwidth, const int *active,
+                           double tunefreq, double shift, int autoincr, int maxpb,
+                           double *impulse, int *numpb_out, int *havnotch_out)
+{
+    if (nc < 2 || !impulse || maxpb < 1 || n_notches < 0 || (n_notches > 0 && (!fcenter || !fwidth || !active))) return QC_EINVAL;
+    if (wintype != 0 && wintype != 1) return QC_EINVAL;
+    // min_notch_width, nbp.c:82-95 (nc / 256 is an integer division there)
+    const double minwidth = (wintype == 0 ? 1600.0 : 2200.0) / (nc / 256) * (rate / 48000);
+    const double offset = tunefreq + shift;
+    const double fl = flow + offset, fh = fhigh + offset;
+    std::vector<double> bplow((size_t)maxpb + 1, 0.0), bphigh((size_t)maxpb + 1, 0.0);
+    std::vector<int> del(1024 + (size_t)maxpb, 0);
+    int nbp = 0, havnotch = 0;
+    if (fh > fl) {
+        bplow[0] = fl; bphigh[0] = fh; nbp = 1;
+        for (int k = 0; k < n_notches; k++) {
+            double nl, nh;
+            if (autoincr && fwidth[k] < minwidth) { nl = fcenter[k] - 0.5 * minwidth; nh = fcenter[k] + 0.5 * minwidth; }
+            else { nl = fcenter[k] - 0.5 * fwidth[k]; nh = fcenter[k] + 0.5 * fwidth[k]; }     // nlow / nhigh of RXANBPAddNotch, nbp.c:378-379
+            if (active[k] && (nh > fl && nl < fh)) {
+                havnotch = 1;
+                int adds = 0;
+                for (int i = 0; i < nbp; i++) {
+                    if (nh > bplow[i] && nl < bphigh[i]) {
+                        if (nl <= bplow[i] && nh >= bphigh[i]) del[i] = 1;
+                        else if (nl > bplow[i] && nh < bphigh[i]) {
+                            if (nbp + adds >= maxpb) return QC_EINVAL;
+                            bplow[nbp + adds] = nh; bphigh[nbp + adds] = bphigh[i]; bphigh[i] = nl; adds++;
+                        }
+                        else if (nl <= bplow[i] && nh > bplow[i]) bplow[i] = nh;
+                        else if (nl < bphigh[i] && nh >= bphigh[i]) bphigh[i] = nl;
+                    }
+                }
+                nbp += adds;
+                int nnbp = nbp;
+                for (int i = 0; i < nbp; i++) {
+                    if (del[i] == 1) {
+                        nnbp--;
+                        for (int j = i; j < nnbp; j++) { bplow[j] = bplow[j + 1]; bphigh[j] = bphigh[j + 1]; }
+                        del[i] = 0;
+                    }
+                }
+                nbp = nnbp;
+            }
+        }
+    }
+    for (int i = 0; i < nbp; i++) { bplow[i] -= offset; bphigh[i] -= offset; }
+    memset(impulse, 0, sizeof(double) * 2 * (size_t)nc);
+    std::vector<double> imp((size_t)2 * nc);
+    for (int k = 0; k < nbp; k++) {
+        int rc = quisk_cuda_fir_bandpass(nc, bplow[k], bphigh[k], rate, wintype, 1, scale, imp.data());
+        if (rc != QC_OK) return rc;
+        for (int i = 0; i < nc; i++) { impulse[2 * i] += imp[2 * i]; impulse[2 * i + 1] += imp[2 * i + 1]; }
+    }
+    if (numpb_out) *numpb_out = nbp;
+    if (havnotch_out) *havnotch_out = havnotch;
+    return QC_OK;
+}
 }  // extern "C"

@@ -23,6 +23,10 @@ struct Rxa {
     SeqStage *adcmeter = nullptr, *smeter = nullptr, *agcmeter = nullptr;
     // nbp0
     int nbp_run = 1, nbp_nc = 0; double nbp_flow = -4150.0, nbp_fhigh = -150.0; FirCore *nbp0 = nullptr;
+    // notch database (create_notchdb, RXA.c:85-87; nbp.c:34-47): shared by the batch like every other setting
+    int ndb_run = 0; double ndb_tune = 0.0, ndb_shift = 0.0; int nbp_hadnotch = 0;
+    std::vector<double> ndb_fcenter, ndb_fwidth; std::vector<int> ndb_active;
+    int nbp0_impulse(std::vector<double> &imp, int *havnotch);
     // amd / fmd
     int amd_run = 0, amd_mode = 0; SeqStage *amd = nullptr;
     int fmd_run = 0, fm_nc_de = 0, fm_nc_aud = 0; SeqStage *fmpll = nullptr, *sntch = nullptr; FirCore *pde = nullptr, *paud = nullptr;
@@ -115,10 +119,22 @@ static FirCore *new_fircore(int C, int size, int nc, const std::vector<double> &
     return f;
 }
 
+// calc_nbp_impulse (nbp.c:214-239): gain / (2 size) baked in; with the notches running the pass band is cut up first
+int Rxa::nbp0_impulse(std::vector<double> &imp, int *havnotch)
+{
+    imp.assign((size_t)2 * nbp_nc, 0.0);
+    if (havnotch) *havnotch = 0;
+    const double scale = 1.0 / (double)(2 * dsp_size);
+    if (!ndb_run) return quisk_cuda_fir_bandpass(nbp_nc, nbp_flow, nbp_fhigh, (double)dsp_rate, 0, 1, scale, imp.data());
+    return quisk_cuda_nbp_impulse(nbp_nc, nbp_flow, nbp_fhigh, (double)dsp_rate, 0, scale, (int)ndb_fcenter.size(),
+                                  ndb_fcenter.data(), ndb_fwidth.data(), ndb_active.data(), ndb_tune, ndb_shift,
+                                  1 /* autoincr, RXA.c:104 */, 1025 /* maxpb, RXA.c:105 */, imp.data(), nullptr, havnotch);
+}
+
 int Rxa::make_nbp0()
-{   // create_nbp + calc_nbp_impulse without notches (nbp.c:214-239, 241-270): gain / (2 size) baked in
-    std::vector<double> imp((size_t)2 * nbp_nc);
-    quisk_cuda_fir_bandpass(nbp_nc, nbp_flow, nbp_fhigh, (double)dsp_rate, 0, 1, 1.0 / (double)(2 * dsp_size), imp.data());
+{   // create_nbp (nbp.c:241-270)
+    std::vector<double> imp;
+    int rc = nbp0_impulse(imp, &nbp_hadnotch); if (rc != QC_OK) return rc;
     if (nbp0) { nbp0->release(); delete nbp0; }
     nbp0 = new_fircore(C, dsp_size, nbp_nc, imp);
     return nbp0 ? QC_OK : QC_EINVAL;
@@ -309,9 +325,9 @@ int quisk_cuda_rxa_set_passband(qcRxa *p, double f_low, double f_high)
     }
     if (f_low != r.nbp_flow || f_high != r.nbp_fhigh) {
         r.nbp_flow = f_low; r.nbp_fhigh = f_high;
-        std::vector<double> imp((size_t)2 * r.nbp_nc);
-        quisk_cuda_fir_bandpass(r.nbp_nc, f_low, f_high, (double)r.dsp_rate, 0, 1, 1.0 / (double)(2 * r.dsp_size), imp.data());
-        int rc = r.nbp0->set_impulse(imp.data(), 1); if (rc) return rc;
+        std::vector<double> imp;
+        int rc = r.nbp0_impulse(imp, &r.nbp_hadnotch); if (rc) return rc;
+        rc = r.nbp0->set_impulse(imp.data(), 1); if (rc) return rc;
     }
     return QC_OK;
 }
@@ -345,6 +361,70 @@ int quisk_cuda_rxa_set_shift(qcRxa *p, int run, const double *shift_hz)
         for (int c = 0; c < r.C; c++) r.shift_nonzero = r.shift_nonzero || shift_hz[c] != 0.0;
     }
     return QC_OK;
+}
+
+// ---- notch database (nbp.c:336-513) ----
+static int nbp_update(Rxa &r, bool lightweight)
+{   // UpdateNBPFilters (always recompute when the notches run) / UpdateNBPFiltersLightWeight (tune or shift moved:
+    // recompute only if there were or are notches inside the pass band, nbp.c:181-212)
+    if (!r.ndb_run) { if (lightweight) r.nbp_hadnotch = 1; return QC_OK; }
+    std::vector<double> imp;
+    int hav = 0;
+    int rc = r.nbp0_impulse(imp, &hav); if (rc != QC_OK) return rc;
+    if (!lightweight || r.nbp_hadnotch || hav) { rc = r.nbp0->set_impulse(imp.data(), 1); if (rc != QC_OK) return rc; }
+    r.nbp_hadnotch = hav;
+    return QC_OK;
+}
+
+int quisk_cuda_rxa_nbp_add_notch(qcRxa *p, int notch, double fcenter, double fwidth, int active)
+{   // RXANBPAddNotch, nbp.c:359-387
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    const int nn = (int)r.ndb_fcenter.size();
+    if (notch < 0 || notch > nn || nn >= 1024) return -1;
+    r.ndb_fcenter.insert(r.ndb_fcenter.begin() + notch, fcenter);
+    r.ndb_fwidth.insert(r.ndb_fwidth.begin() + notch, fwidth);
+    r.ndb_active.insert(r.ndb_active.begin() + notch, active);
+    return nbp_update(r, false);
+}
+
+int quisk_cuda_rxa_nbp_delete_notch(qcRxa *p, int notch)
+{   // RXANBPDeleteNotch, nbp.c:414-437
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    if (notch < 0 || notch >= (int)r.ndb_fcenter.size()) return -1;
+    r.ndb_fcenter.erase(r.ndb_fcenter.begin() + notch);
+    r.ndb_fwidth.erase(r.ndb_fwidth.begin() + notch);
+    r.ndb_active.erase(r.ndb_active.begin() + notch);
+    return nbp_update(r, false);
+}
+
+int quisk_cuda_rxa_nbp_set_notches_run(qcRxa *p, int run)
+{   // RXANBPSetNotchesRun, nbp.c:496-513
+    if (!p) return QC_EINVAL;
+    Rxa &r = p->r;
+    run = run ? 1 : 0;
+    if (run == r.ndb_run) return QC_OK;
+    r.ndb_run = run;
+    std::vector<double> imp;
+    int rc = r.nbp0_impulse(imp, &r.nbp_hadnotch); if (rc != QC_OK) return rc;
+    return r.nbp0->set_impulse(imp.data(), 1);
+}
+
+int quisk_cuda_rxa_nbp_set_tune_frequency(qcRxa *p, double tunefreq)
+{   // RXANBPSetTuneFrequency, nbp.c:472-481
+    if (!p) return QC_EINVAL;
+    if (tunefreq == p->r.ndb_tune) return QC_OK;
+    p->r.ndb_tune = tunefreq;
+    return nbp_update(p->r, true);
+}
+
+int quisk_cuda_rxa_nbp_set_shift_frequency(qcRxa *p, double shift)
+{   // RXANBPSetShiftFrequency, nbp.c:484-493
+    if (!p) return QC_EINVAL;
+    if (shift == p->r.ndb_shift) return QC_OK;
+    p->r.ndb_shift = shift;
+    return nbp_update(p->r, true);
 }
 
 int quisk_cuda_rxa_set_nbp_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.nbp_run = run; return QC_OK; }

@@ -147,6 +147,12 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_set_slew.argtypes = [vp, C.c_double, C.c_double]
     lib.quisk_cuda_rxa_set_siphon_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_get_siphon.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.quisk_cuda_nbp_impulse.argtypes = [C.c_int, D, D, D, C.c_int, D, C.c_int, vp, vp, vp, D, D, C.c_int, C.c_int, vp, c_int_p, c_int_p]
+    lib.quisk_cuda_rxa_nbp_add_notch.argtypes = [vp, C.c_int, D, D, C.c_int]
+    lib.quisk_cuda_rxa_nbp_delete_notch.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_nbp_set_notches_run.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_nbp_set_tune_frequency.argtypes = [vp, D]
+    lib.quisk_cuda_rxa_nbp_set_shift_frequency.argtypes = [vp, D]
     lib.quisk_cuda_rxa_set_panel_gain.argtypes = [vp, D]
     lib.quisk_cuda_rxa_in_size.argtypes = [vp]
     lib.quisk_cuda_rxa_out_size.argtypes = [vp]

@@ -51,6 +51,9 @@ def wdsp():
     lib.SetRXAAGCMode.argtypes = [C.c_int, C.c_int]
     lib.SetRXAShiftRun.argtypes = [C.c_int, C.c_int]
     lib.RXAGetaSipF1.argtypes = [C.c_int, VP, C.c_int]
+    lib.RXANBPSetNotchesRun.argtypes = [C.c_int, C.c_int]
+    lib.RXANBPSetTuneFrequency.argtypes = [C.c_int, D]
+    lib.RXANBPAddNotch.argtypes = [C.c_int, C.c_int, D, D, C.c_int]
     return lib
 
 
@@ -202,6 +205,15 @@ def main():
     x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
     out["rxa_usb/y"] = run_channel(0, 256, 256, 48000, 48000, 48000, setup_usb, x, 24)
     out["rxa_usb/sip"] = siphons[0]
+
+    def setup_usb_notch(ch):    # the notch database in action: two notches inside the pass band, one of them on a tone
+        setup_usb(ch)
+        lib.RXANBPSetTuneFrequency(ch, 7000000.0)
+        lib.RXANBPSetNotchesRun(ch, 1)
+        assert lib.RXANBPAddNotch(ch, 0, 7001500.0, 400.0, 1) == 0
+        assert lib.RXANBPAddNotch(ch, 1, 7002400.0, 100.0, 1) == 0        # narrower than the minimum: auto-widened
+    xn = sig(256 * 24, 700, 48000.0, tones=((1000.0, 0.3), (1500.0, 0.2), (2200.0, 0.1)))
+    out["rxa_usb_notch/y"] = run_channel(6, 256, 256, 48000, 48000, 48000, setup_usb_notch, xn, 24)
     # the same channel opened the way Quisk opens it (quisk_wdsp.py:79-80): 10 ms of zeros after the first non-zero
     # sample, then a 25 ms raised-cosine ramp (upslew0, iobuffs.c:98-160); the stream starts with 100 zero samples
     xs = x.copy(); xs[:100] = 0.0

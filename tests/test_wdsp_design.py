@@ -55,3 +55,50 @@ def test_resample_plan(libs, rates, exp):
     L, M, n = C.c_int(), C.c_int(), C.c_int()
     assert lib.quisk_cuda_resample_design(rates[0], rates[1], 0.0, 0, 1.0, C.byref(L), C.byref(M), C.byref(n), None, 0) == 0
     assert (L.value, M.value, n.value) == exp
+
+
+NOTCH_CASES = [
+    # (notches [(centre, width, active)], tunefreq, shift, flow, fhigh): RF coordinates, pass band = tune + [flow, fhigh]
+    ([(7001000.0, 200.0, 1)], 7000000.0, 0.0, 150.0, 2850.0),                                  # widened to the minimum width
+    ([(7001000.0, 900.0, 1), (7002500.0, 700.0, 1), (7000100.0, 300.0, 1)], 7000000.0, 0.0, 150.0, 2850.0),   # inner, upper edge, lower edge
+    ([(7001000.0, 900.0, 0), (7001500.0, 5000.0, 1)], 7000000.0, 0.0, 150.0, 2850.0),          # inactive one + one that swallows the band
+    ([(13998700.0, 600.0, 1), (13998900.0, 600.0, 1)], 14000000.0, 250.0, -2850.0, -150.0),     # overlapping notches, shift, LSB band
+    ([], 7000000.0, 0.0, 150.0, 2850.0),
+]
+
+
+@pytest.mark.parametrize("case", NOTCH_CASES, ids=[str(i) for i in range(len(NOTCH_CASES))])
+def test_nbp_notched_impulse_bit_identical(libs, case):
+    """quisk_cuda_nbp_impulse against the reference's own make_nbp + fir_mbandpass (nbp.c:64-179), called the way
+    calc_nbp_impulse calls them (nbp.c:214-239)."""
+    lib, ref = libs
+    notches, tune, shift, flow, fhigh = case
+    nc, rate, wintype, size = 2048, 48000.0, 0, 256
+    scale = 1.0 / (2 * size)
+    nn = len(notches)
+    fc = np.array([n[0] for n in notches] + [0.0]); fw = np.array([n[1] for n in notches] + [0.0])
+    act = np.array([n[2] for n in notches] + [0], dtype=np.int32)
+    nlow = fc - 0.5 * fw; nhigh = fc + 0.5 * fw
+    DP, IP = C.POINTER(D), C.POINTER(C.c_int)
+    ref.make_nbp.argtypes = [C.c_int, IP, DP, DP, DP, DP, D, C.c_int, D, D, DP, DP, IP]
+    ref.fir_mbandpass.restype = DP
+    ref.fir_mbandpass.argtypes = [C.c_int, C.c_int, DP, DP, D, D, C.c_int]
+    bplow = np.zeros(1025); bphigh = np.zeros(1025); hav = C.c_int(0)
+    minwidth = 1600.0 / (nc // 256) * (rate / 48000)
+    offset = tune + shift
+    p = lambda a, t: a.ctypes.data_as(t)
+    nbp = ref.make_nbp(nn, p(act, IP), p(fc, DP), p(fw, DP), p(nlow, DP), p(nhigh, DP), minwidth, 1, flow + offset, fhigh + offset,
+                       p(bplow, DP), p(bphigh, DP), C.byref(hav))
+    bplow[:nbp] -= offset; bphigh[:nbp] -= offset
+    r = np.ctypeslib.as_array(ref.fir_mbandpass(nc, nbp, p(bplow, DP), p(bphigh, DP), rate, scale, wintype), (2 * nc,)).copy()
+    out = np.zeros(2 * nc); numpb = C.c_int(-1); hav2 = C.c_int(-1)
+    lib.quisk_cuda_nbp_impulse.argtypes = [C.c_int, D, D, D, C.c_int, D, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, D, D, C.c_int, C.c_int,
+                                           C.c_void_p, IP, IP]
+    assert lib.quisk_cuda_nbp_impulse(nc, flow, fhigh, rate, wintype, scale, nn, fc.ctypes.data, fw.ctypes.data, act.ctypes.data,
+                                      tune, shift, 1, 1025, out.ctypes.data, C.byref(numpb), C.byref(hav2)) == 0
+    assert numpb.value == nbp and hav2.value == hav.value
+    assert np.array_equal(out, r)
+    if nn and any(n[2] for n in notches):
+        plain = np.zeros(2 * nc)
+        lib.quisk_cuda_fir_bandpass(nc, flow, fhigh, rate, wintype, 1, scale, plain.ctypes.data)
+        assert not np.array_equal(out, plain)                      # the notches really cut something out

@@ -217,6 +217,29 @@ def test_rxa_usb_channel_upslew(torch, lib, kat):
     lib.quisk_cuda_rxa_destroy(rxa)
 
 
+def test_rxa_usb_channel_notches(torch, lib, kat):
+    """nbp0 with the notch database running (RXANBPSetNotchesRun / AddNotch / SetTuneFrequency, nbp.c:359-513): two
+    notches inside the pass band, one narrower than the minimum width and therefore auto-widened."""
+    x = sig(256 * 24, 700, 48000.0, tones=((1000.0, 0.3), (1500.0, 0.2), (2200.0, 0.1)))
+    rxa = lib.quisk_cuda_rxa_create(NCH, 256, 256, 48000, 48000, 48000)
+    assert rxa, lib.quisk_cuda_last_error()
+    assert lib.quisk_cuda_rxa_set_shift(rxa, 0, None) == 0
+    assert lib.quisk_cuda_rxa_set_nc(rxa, 2048) == 0
+    assert lib.quisk_cuda_rxa_set_mode(rxa, 1) == 0
+    assert lib.quisk_cuda_rxa_set_passband(rxa, 150.0, 2850.0) == 0
+    assert lib.quisk_cuda_rxa_set_agc_mode(rxa, 3) == 0
+    assert lib.quisk_cuda_rxa_nbp_set_tune_frequency(rxa, 7000000.0) == 0
+    assert lib.quisk_cuda_rxa_nbp_set_notches_run(rxa, 1) == 0
+    assert lib.quisk_cuda_rxa_nbp_add_notch(rxa, 0, 7001500.0, 400.0, 1) == 0
+    assert lib.quisk_cuda_rxa_nbp_add_notch(rxa, 1, 7002400.0, 100.0, 1) == 0
+    assert lib.quisk_cuda_rxa_nbp_add_notch(rxa, 5, 7002000.0, 100.0, 1) == -1        # beyond the end of the list
+    y = _run_rxa(torch, lib, rxa, x, 256, 24, use_fexchange=True)
+    ref = kat["rxa_usb_notch/y"]
+    for c in range(NCH):
+        assert O.rel_rms(y[c], ref) < 1e-11
+    lib.quisk_cuda_rxa_destroy(rxa)
+
+
 def test_rxa_default_channel_keeps_bp1(torch, lib, kat):
     """No SetRXAMode: bp1 is still running -- the quirk is part of the reference's behaviour."""
     x = _first_sample_swallowed(sig(256 * 16, 701, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2))))
