@@ -9,6 +9,7 @@
 #
 #   _ref/libquisk_filter_ref.so  filter.c, verbatim (all 17 filter.h functions + filters.h tables)
 #   _ref/libquisk_rx_ref.so      filter.c + the static RX functions of quisk.c (see ref_wrap/quisk_rx_wrap.c)
+#   _ref/libquisk_rx_dropin.so   the same RX functions of quisk.c linked against quisk_b200/libquisk_cuda.so instead of filter.c
 #   _ref/libwdsp_ref.so          wdsp/*.c (minus the make_*.c table generators) + our FFTW-API shim
 #
 # Flags: -O2 for the Quisk sources (setuptools default), -O3 for WDSP
@@ -38,6 +39,17 @@ sed -n '2922,2953p' "$REF/quisk.c" > "$TMP/quisk_unpack_py.inc"          # add_r
 sed -n '3746,3763p' "$REF/quisk.c" > "$TMP/quisk_unpack_hermes.inc"      # read_rx_udp10: 24-bit record loop of one 512-byte frame
 gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_rx_wrap.c" "$REF/filter.c" \
     -o "$OUT/libquisk_rx_ref.so" -lm
+
+# 2b. The same wrapper TU linked against libquisk_cuda.so INSTEAD of filter.c: the reference's own orchestrator code
+#     (quisk_process_decimate / quisk_process_demodulate, unmodified) calling the GPU filter.h drop-in.  This is the
+#     swap-in of INTEGRATION.md section 1 in miniature; filters.h (the coefficient tables filter.c used to emit) is
+#     compiled from the reference's header through a two-line scratch TU.  tests/test_dropin_gpu.py runs it.
+CUDALIB="$HERE/../quisk_b200/libquisk_cuda.so"
+if [ -f "$CUDALIB" ]; then
+    printf '#include <complex.h>\n#include "filters.h"\n' > "$TMP/filters_data.c"
+    gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_rx_wrap.c" "$TMP/filters_data.c" \
+        -o "$OUT/libquisk_rx_dropin.so" -L"$HERE/../quisk_b200" -lquisk_cuda -Wl,-rpath,'$ORIGIN/../../quisk_b200' -lm
+fi
 
 # 3. WDSP against the FFTW shim
 WSRC=$(ls "$REF"/wdsp/*.c | grep -v '/make_')
