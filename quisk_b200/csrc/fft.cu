@@ -329,9 +329,23 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
     if (n_frames <= 0) return QC_OK;
     cudaStream_t s = (cudaStream_t)stream;
     // enough CTAs to fill the machine, but keep the reference's summation order when streams alone do
+    // Frames of a stream are split over `groups` CTAs only when the streams alone cannot fill the machine, and then
+    // so that ALL CTAs are resident at once (one wave): a grid a little larger than the number of slots costs a
+    // whole extra wave (16 streams: 608 CTAs on 296 slots ran 3 waves of 7 frames; 288 CTAs run 1 wave of 15).
+    const bool split = p.n == 8192 && p.split8192;
+    const int cpf = split ? 2 : 1;                                   // CTAs per frame
+    const size_t cta_smem = split ? (size_t)4096 * 24 + 8192 : (size_t)p.n * 24 + 4096;
+    int per_sm = (int)((size_t)220 * 1024 / cta_smem);
+    const int reg_cap = p.n >= 4096 ? 2 : 4;                         // 256 threads x ~128 registers (255 at 8192 unsplit)
+    if (per_sm > reg_cap) per_sm = reg_cap;
+    if (p.n == 8192 && !split) per_sm = 1;
+    if (per_sm < 1) per_sm = 1;
+    int n_sm = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const int slots = per_sm * n_sm;
     int groups = 1;
-    if (p.S < 2 * 148) {
-        groups = (2 * 148 + p.S - 1) / p.S;
+    if (p.S * cpf < slots) {
+        groups = slots / (p.S * cpf);
         if (groups > n_frames) groups = n_frames;
         if (groups < 1) groups = 1;
     }
