@@ -334,6 +334,7 @@ int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *st
 #define QC_PFB_OPT_SLICE_FRAMES 1   /* frames of the branch-FIR intermediate per kernel pair (default 65536 = 1 GiB at 1024 channels) */
 #define QC_PFB_OPT_GENERIC      2   /* 1: force the single generic kernel (the only path when decim is not n_channels or n_channels/2) */
 #define QC_PFB_OPT_PIPELINE     3   /* 1: overlap the branch FIRs of slice i+1 with the transforms of slice i (two internal streams) */
+#define QC_PFB_OPT_FFT_PREFETCH 6   /* 1 (default): transform CTAs prefetch a later CTA's inputs into L2 */
 #define QC_PFB_OPT_RING         5   /* cp.async ring depth of the branch-FIR kernel in steps: 16 (default) or 32 */
 #define QC_PFB_OPT_FFT_FRAMES   4   /* frames interleaved per transform CTA: 2 (default) or 4 */
 int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value);

@@ -150,6 +150,13 @@ __global__ void __launch_bounds__(256, 2) pan_accumulate_split_kernel(const cd *
             s[fsw(j)] = v;
         }
         __syncthreads();
+        // pull this CTA's next frame towards L2 while the transform runs (its pair partner fetches the other half):
+        // the load phase above is otherwise the only time this CTA has memory requests in flight
+        if (f + groups < n_frames) {
+            const char *nxt = reinterpret_cast<const char *>(base + (size_t)(f + groups) * N) + (size_t)par * (N * sizeof(cd) / 2);
+            for (int l = lane; l < (int)(N * sizeof(cd) / 2 / 128); l += lanes)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)l * 128));
+        }
         fft_smem<1>(s, H, twl4, -1, lane, lanes);
         for (int k = lane; k < H; k += lanes) {
             const cd X = s[fsw(k)];

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirP
 // One shared-memory round trip per pass boundary and three barriers per four transforms.
 template <int R3, int PFI>
 __global__ void __launch_bounds__(64 * PFI, 8 / PFI) pfb_fft_kernel(const cd *__restrict__ u, int nf, const cd *__restrict__ tw,
-                                                                 cd *__restrict__ out, long out_stride, long frame0, int layout)
+                                                                 cd *__restrict__ out, long out_stride, long frame0, int layout, int pf_ahead)
 {
     constexpr int K = 256 * R3, N1 = K / 16;            // N1 = lanes per transform; PFI = frames interleaved per CTA (2 or 4)
     extern __shared__ double smem_raw[];
@@ -262,6 +262,16 @@ __global__ void __launch_bounds__(64 * PFI, 8 / PFI) pfb_fft_kernel(const cd *__
         const cd *src = u + ((size_t)g * PFI + f) * K + b;
 #pragma unroll
         for (int j = 0; j < 16; j++) v[j] = live ? src[j * N1] : make_double2(0.0, 0.0);
+        // pull the group a later CTA will work on towards L2 (this kernel is not persistent: by the time the CTA that
+        // takes over this slot starts, its 16 loads per thread find the lines in L2 instead of HBM)
+        {
+            const long gn = (long)g + pf_ahead;
+            if (pf_ahead > 0 && (gn + 1) * PFI <= nf) {
+                const char *nxt = reinterpret_cast<const char *>(u + (size_t)gn * PFI * K);
+                for (int l = tid; l < (int)(PFI * K * sizeof(cd) / 128); l += blockDim.x)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)l * 128));
+            }
+        }
         dft16(v, -1.0);
         __syncthreads();                                // twiddle store staged
         if (b != 0) {
@@ -338,6 +348,7 @@ struct Channelizer {
     int n_sm = 148;
     int slice_frames = 1 << 16;     // frames of u per kernel pair; smaller slices were measured slower (launch gaps outweigh L2 reuse)
     int force_generic = 0;
+    int fft_prefetch = 1;           // transform CTAs prefetch the inputs of the CTA one wave later into L2
     int ring = 16;                  // cp.async ring depth of the branch kernel in steps (16 or 32)
     int fft_frames = 2;             // frames interleaved per transform CTA (2: four CTAs per SM, measured 5 % faster; 4: 64-byte output runs)
     cd *d_u = nullptr; int u_frames = 0, u_bufs = 0;        // one slice of u (two back to back when pipelining)
@@ -472,8 +483,9 @@ struct Channelizer {
             QC_CUDA_LAUNCH();
             if (pipe) { QC_CUDA(cudaEventRecord(ev_fir[si & 1], sa)); QC_CUDA(cudaStreamWaitEvent(sb, ev_fir[si & 1], 0)); }
             const int gf = (nfs + pfi - 1) / pfi, nth = pfi * K / 16;
-#define PFB_FFT(R3) do { if (pfi == 4) pfb_fft_kernel<R3, 4><<<gf, nth, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout); \
-                         else pfb_fft_kernel<R3, 2><<<gf, nth, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout); } while (0)
+            const int ahead = fft_prefetch ? n_sm * (8 / pfi) : 0;           // one full wave of resident CTAs ahead
+#define PFB_FFT(R3) do { if (pfi == 4) pfb_fft_kernel<R3, 4><<<gf, nth, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout, ahead); \
+                         else pfb_fft_kernel<R3, 2><<<gf, nth, sh, s_fft>>>(ub, nfs, tw, d_out, out_stride, f0, layout, ahead); } while (0)
             if (K == 1024) PFB_FFT(4); else if (K == 512) PFB_FFT(2); else PFB_FFT(1);
 #undef PFB_FFT
             count_launch();
@@ -546,6 +558,7 @@ int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value)
     case QC_PFB_OPT_SLICE_FRAMES: if (value < 4) return QC_EINVAL; p->c.slice_frames = value; return QC_OK;
     case QC_PFB_OPT_GENERIC: p->c.force_generic = value ? 1 : 0; return QC_OK;
     case QC_PFB_OPT_PIPELINE: p->c.pipeline = value ? 1 : 0; return QC_OK;
+    case QC_PFB_OPT_FFT_PREFETCH: p->c.fft_prefetch = value ? 1 : 0; return QC_OK;
     case QC_PFB_OPT_RING: if (value != 16 && value != 32) return QC_EINVAL; p->c.ring = value; return QC_OK;
     case QC_PFB_OPT_FFT_FRAMES: if (value != 2 && value != 4) return QC_EINVAL; p->c.fft_frames = value; return QC_OK;
     }
