@@ -40,10 +40,14 @@ int quisk_cuda_nbp_impulse(int nc, double flow, double fhigh, double rate, int w
                            double tunefreq, double shift, int autoincr, int maxpb,
                            double *impulse, int *numpb, int *havnotch);
 
+/* mp_imp, wdsp/fir.c:317-368: the minimum-phase impulse with the magnitude response of `fir` (N complex in, N out;
+ * pfactor 16 and polarity 0 are what calc_fircore passes, firmin.c:328).  N * pfactor must be a power of two. */
+int quisk_cuda_mp_imp(int N, const double *fir, double *mpfir, int pfactor, int polarity);
+
 /* ---- fircore: uniformly partitioned overlap-save complex FIR (wdsp/firmin.c:290-430) ---- */
 typedef struct qcFircore qcFircore;
 /* impulse: HOST, nc complex, the same for every channel (callers bake 1/(2*size) into it exactly as
- * nbp.c:233-237 / bandpass.c:302 do).  mp (minimum phase, fir.c mp_imp) must be 0 in this version. */
+ * nbp.c:233-237 / bandpass.c:302 do).  mp = 1: the masks are built from quisk_cuda_mp_imp(impulse) (firmin.c:327-328). */
 qcFircore *quisk_cuda_fircore_create(int n_channels, int size, int nc, int mp, const double *impulse);
 void quisk_cuda_fircore_destroy(qcFircore *f);
 /* xfircore for every channel: d_in/d_out [n_channels][stride] complex, `size` samples each. in may equal out. */

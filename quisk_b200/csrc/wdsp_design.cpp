@@ -8,8 +8,13 @@
 //   fc_impulse          wdsp/fcurve.c:29-143 FM (de-)emphasis curve
 //   calc_resample       wdsp/resample.c:35-78 L/M, tap count and prototype of the rational resampler
 //   make_nbp, fir_mbandpass, min_notch_width  wdsp/nbp.c:64-179   notched band-pass (notch database -> pass bands -> taps)
+//   analytic, mp_imp    wdsp/fir.c:292-368   minimum-phase version of an impulse response (cepstral method); the
+//                       reference runs its three transforms through FFTW, here a plain radix-2 FFT does -- the
+//                       method takes log|H| of stop-band bins at the rounding floor, so two correct FFTs give
+//                       taps that agree to ~1e-6, not to 1e-13: that is the algorithm's conditioning
 // with the same expression order, so the doubles that come out are the reference's.
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -19,6 +24,29 @@ namespace {
 
 const double kPI = 3.1415926535897932;       // wdsp/comm.h:146-147
 const double kTWOPI = 6.2831853071795864;
+
+// unnormalised radix-2 FFT (sign -1 forward, +1 backward), design-time only
+void host_fft(std::vector<std::complex<double>> &a, int sign)
+{
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t half = len >> 1;
+        for (size_t k = 0; k < half; k++) {
+            const double ang = sign * kTWOPI * (double)k / (double)len;
+            const std::complex<double> w(std::cos(ang), std::sin(ang));
+            for (size_t i = k; i < n; i += len) {
+                const std::complex<double> u = a[i], v = a[i + half] * w;
+                a[i] = u + v; a[i + half] = u - v;
+            }
+        }
+    }
+}
 
 double bh_window(int wintype, double cosphi)
 {
@@ -243,6 +271,44 @@ int quisk_cuda_nbp_impulse(int nc, double flow, double fhigh, double rate, int w
     }
     if (numpb_out) *numpb_out = nbp;
     if (havnotch_out) *havnotch_out = havnotch;
+    return QC_OK;
+}
+
+/* mp_imp (fir.c:317-368) with `analytic` (fir.c:292-315): minimum-phase impulse of the same magnitude response.
+ * N complex taps in, N out; pfactor = zero-padding factor (the reference uses 16, firmin.c:328); N * pfactor must be
+ * a power of two. */
+int quisk_cuda_mp_imp(int N, const double *fir, double *mpfir, int pfactor, int polarity)
+{
+    if (N < 1 || pfactor < 1 || !fir || !mpfir) return QC_EINVAL;
+    const long size = (long)N * pfactor;
+    if (size & (size - 1)) return QC_EINVAL;
+    std::vector<std::complex<double>> firfreq((size_t)size), ana((size_t)size), newfreq((size_t)size);
+    std::vector<double> mag((size_t)size);
+    const double inv_PN = 1.0 / (double)size;
+    for (long i = 0; i < size; i++) firfreq[i] = i < N ? std::complex<double>(fir[2 * i], fir[2 * i + 1]) : std::complex<double>(0.0, 0.0);
+    host_fft(firfreq, -1);
+    for (long i = 0; i < size; i++) {
+        mag[i] = std::sqrt(firfreq[i].real() * firfreq[i].real() + firfreq[i].imag() * firfreq[i].imag()) * inv_PN;
+        ana[i] = std::complex<double>(mag[i] > 0.0 ? std::log(mag[i]) : std::log(1.0e-300), 0.0);
+    }
+    // analytic(size, ana, ana): one-sided spectrum of log|H| -> its imaginary part is minus the minimum phase
+    {
+        const double inv_N = 1.0 / (double)size, two_inv_N = 2.0 * inv_N;
+        host_fft(ana, -1);
+        ana[0] *= inv_N;
+        for (long i = 1; i < size / 2; i++) ana[i] *= two_inv_N;
+        ana[size / 2] *= inv_N;
+        for (long i = size / 2 + 1; i < size; i++) ana[i] = 0.0;
+        host_fft(ana, +1);
+    }
+    for (long i = 0; i < size; i++) {
+        const double re = +mag[i] * std::cos(ana[i].imag());
+        const double im = mag[i] * std::sin(ana[i].imag());
+        newfreq[i] = std::complex<double>(re, polarity ? +im : -im);
+    }
+    host_fft(newfreq, +1);
+    const long off = polarity ? (long)(pfactor - 1) * N : 0;
+    for (long i = 0; i < N; i++) { mpfir[2 * i] = newfreq[off + i].real(); mpfir[2 * i + 1] = newfreq[off + i].imag(); }
     return QC_OK;
 }
 }  // extern "C"

@@ -70,10 +70,10 @@ __global__ void __launch_bounds__(256) fircore_kernel(const cd *in, long in_stri
     for (int i = lane; i < size; i += lanes) y[i] = s[fsw(i)];
 }
 
-int FirCore::init(int C_, int size_, int nc_, int mp, const double *impulse)
+int FirCore::init(int C_, int size_, int nc_, int mp_, const double *impulse)
 {
     C = C_; size = size_; nc = nc_;
-    if (mp) { set_error("fircore: minimum-phase impulses (mp_imp) are not implemented"); return QC_EINVAL; }
+    mp = mp_ ? 1 : 0;
     if (C <= 0 || size < 4 || (size & (size - 1)) || fft_log2(2 * size) < 0 || nc < size || nc % size) {
         set_error("fircore: size must be a power of two in [4, 4096] and nc a multiple of it (size %d, nc %d)", size, nc);
         return QC_EINVAL;
@@ -109,6 +109,12 @@ int FirCore::flush()
 
 int FirCore::set_impulse(const double *impulse, int update)
 {   // calc_fircore: masks into the set that is NOT in use
+    std::vector<double> mpi;
+    if (mp) {                               // calc_fircore, firmin.c:327-328
+        mpi.resize((size_t)2 * nc);
+        if (quisk_cuda_mp_imp(nc, impulse, mpi.data(), 16, 0) != QC_OK) { set_error("fircore: mp_imp needs nc * 16 to be a power of two (nc %d)", nc); return QC_EINVAL; }
+        impulse = mpi.data();
+    }
     std::vector<cd> gen((size_t)nfor * n2, make_double2(0.0, 0.0));
     for (int j = 0; j < nfor; j++)
         for (int i = 0; i < size; i++)

@@ -8,7 +8,7 @@ namespace qc {
 
 struct FirCore {
     int C = 0, size = 0, nc = 0, nfor = 0, n2 = 0;
-    int buffidx = 0, cset = 0, masks_ready = 0;
+    int buffidx = 0, cset = 0, masks_ready = 0, mp = 0;
     const cd *tw = nullptr;
     cd *d_prev = nullptr, *d_fdl = nullptr, *d_gen = nullptr;
     cd *d_mask[2] = {nullptr, nullptr};

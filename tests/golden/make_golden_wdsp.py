@@ -110,6 +110,18 @@ def main():
             lib.xfircore(f)
             ys.append(outb[:size].copy())
         out["fircore_%d_%d/y" % (size, nc)] = np.concatenate(ys)
+    # ---- fircore with minimum-phase masks (mp = 1: calc_fircore runs the impulse through mp_imp, firmin.c:327-328) ----
+    size, nc, rate = 256, 1024, 48000.0
+    imp = bandpass(lib, nc, 150.0, 2850.0, rate, 0, 1, 1.0 / (2 * size))
+    inb = np.zeros(size, dtype=np.complex128); outb = np.zeros(2 * size, dtype=np.complex128)
+    f = lib.create_fircore(size, inb.ctypes.data, outb.ctypes.data, nc, 1, imp.ctypes.data)
+    x = sig(size * 8, 150, rate)
+    ys = []
+    for b in range(8):
+        inb[:] = x[b * size:(b + 1) * size]
+        lib.xfircore(f)
+        ys.append(outb[:size].copy())
+    out["fircore_mp_256_1024/y"] = np.concatenate(ys)
     # ---- resample ----
     for in_rate, out_rate, splits in RESAMPLE_CASES:
         x = sig(sum(splits), 200, in_rate)

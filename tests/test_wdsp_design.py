@@ -102,3 +102,31 @@ def test_nbp_notched_impulse_bit_identical(libs, case):
         plain = np.zeros(2 * nc)
         lib.quisk_cuda_fir_bandpass(nc, flow, fhigh, rate, wintype, 1, scale, plain.ctypes.data)
         assert not np.array_equal(out, plain)                      # the notches really cut something out
+
+
+@pytest.mark.parametrize("args", [(2048, 150., 2850., 48000., 0), (256, -4150., -150., 48000., 1), (1024, -8000., 8000., 192000., 0)])
+@pytest.mark.parametrize("polarity", [0, 1])
+def test_mp_imp_matches_reference(libs, args, polarity):
+    """Minimum-phase impulse (fir.c:317-368).  The reference's three transforms go through FFTW (here: the oracle's
+    FFT shim), ours through a radix-2 host FFT.  The method takes log|H| of stop-band bins that sit at the rounding
+    floor of the first transform, so it amplifies FFT rounding: two correct FFTs give taps that agree to ~1e-6 of
+    the rms tap, not to 1e-13 -- that is the conditioning of the reference's algorithm, the tolerance says so."""
+    lib, ref = libs
+    nc, flow, fhigh, rate, wintype = args
+    imp = np.zeros(2 * nc)
+    assert lib.quisk_cuda_fir_bandpass(nc, flow, fhigh, rate, wintype, 1, 1.0 / 512, imp.ctypes.data) == 0
+    ref.mp_imp.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    ref.mp_imp.restype = None
+    r = np.zeros(2 * nc)
+    ref.mp_imp(nc, imp.ctypes.data, r.ctypes.data, 16, polarity)
+    out = np.zeros(2 * nc)
+    lib.quisk_cuda_mp_imp.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    assert lib.quisk_cuda_mp_imp(nc, imp.ctypes.data, out.ctypes.data, 16, polarity) == 0
+    assert np.sqrt(np.mean((out - r) ** 2)) / np.sqrt(np.mean(r ** 2)) < 1e-5
+    # it is minimum phase: same magnitude response, energy packed at the front (polarity 0) / back (polarity 1)
+    H0 = np.abs(np.fft.fft(imp.view(np.complex128))); H1 = np.abs(np.fft.fft(out.view(np.complex128)))
+    assert np.max(np.abs(H0 - H1)) / H0.max() < 1e-3
+    e = np.abs(out.view(np.complex128)) ** 2
+    centroid = (np.arange(nc) * e).sum() / e.sum() / nc         # the linear-phase input sits at 0.5
+    assert (centroid < 0.3) if polarity == 0 else (centroid > 0.7)
+    assert lib.quisk_cuda_mp_imp(1000, imp.ctypes.data, out.ctypes.data, 16, 0) != 0         # 16000 is not a power of two

@@ -70,6 +70,37 @@ def test_fircore(size, nc, rate, torch, lib, kat):
     lib.quisk_cuda_fircore_destroy(f)
 
 
+def test_fircore_minimum_phase(torch, lib, kat):
+    """mp = 1: the masks come from mp_imp of the impulse (firmin.c:327-328).  mp_imp amplifies FFT rounding (see
+    tests/test_wdsp_design.py), so two correct implementations agree to ~1e-6 here, and the filter now responds
+    at once instead of after nc/2 samples."""
+    size, nc, rate = 256, 1024, 48000.0
+    imp = _bandpass(lib, nc, 150.0, 2850.0, rate, 0, 1, 1.0 / (2 * size))
+    f = lib.quisk_cuda_fircore_create(NCH, size, nc, 1, imp.ctypes.data)
+    assert f, lib.quisk_cuda_last_error()
+    x = sig(size * 8, 150, rate)
+    d = _dev(torch, x)
+    o = torch.zeros_like(d)
+    for b in range(8):
+        blk = d[:, b * size:(b + 1) * size]
+        ob = o[:, b * size:(b + 1) * size]
+        assert lib.quisk_cuda_fircore_run(f, blk.data_ptr(), d.stride(0), ob.data_ptr(), o.stride(0), None) == 0
+    torch.cuda.synchronize()
+    y = o.cpu().numpy()
+    ref = kat["fircore_mp_256_1024/y"]
+    for c in range(NCH):
+        assert O.rel_rms(y[c], ref) < 1e-5
+    lin = lib.quisk_cuda_fircore_create(NCH, size, nc, 0, imp.ctypes.data)
+    o2 = torch.zeros_like(d)
+    for b in range(8):
+        assert lib.quisk_cuda_fircore_run(lin, d[:, b * size:(b + 1) * size].data_ptr(), d.stride(0), o2[:, b * size:(b + 1) * size].data_ptr(), o2.stride(0), None) == 0
+    torch.cuda.synchronize()
+    y2 = o2.cpu().numpy()
+    e_mp = np.sum(np.abs(y[0][:size]) ** 2); e_lin = np.sum(np.abs(y2[0][:size]) ** 2)
+    assert e_mp > 10 * e_lin                         # minimum phase: output energy arrives in the first block
+    lib.quisk_cuda_fircore_destroy(f); lib.quisk_cuda_fircore_destroy(lin)
+
+
 @pytest.mark.parametrize("in_rate,out_rate,splits", RESAMPLE_CASES)
 def test_resample(in_rate, out_rate, splits, torch, lib, kat):
     r = lib.quisk_cuda_resample_create(NCH, in_rate, out_rate, 0.0, 0, 1.0)
