@@ -56,6 +56,7 @@ int quisk_cuda_fircore_run(qcFircore *f, const void *d_in, long in_stride, void 
  * with the next block when update != 0, or at quisk_cuda_fircore_update() (setUpdate_fircore). */
 int quisk_cuda_fircore_set_impulse(qcFircore *f, const double *impulse, int update);
 int quisk_cuda_fircore_update(qcFircore *f);
+int quisk_cuda_fircore_set_mp(qcFircore *f, int mp);                       /* setMp_fircore, firmin.c:469-473 */
 int quisk_cuda_fircore_flush(qcFircore *f);
 
 /* ---- rational resampler (wdsp/resample.c:121-157) ---- */
@@ -120,6 +121,7 @@ int quisk_cuda_rxa_nbp_delete_notch(qcRxa *rxa, int notch);
 int quisk_cuda_rxa_nbp_set_notches_run(qcRxa *rxa, int run);
 int quisk_cuda_rxa_nbp_set_tune_frequency(qcRxa *rxa, double tunefreq);
 int quisk_cuda_rxa_nbp_set_shift_frequency(qcRxa *rxa, double shift);
+int quisk_cuda_rxa_set_mp(qcRxa *rxa, int mp);                               /* RXASetMP, RXA.c:949-958           */
 int quisk_cuda_rxa_set_panel_gain(qcRxa *r, double gain1);                  /* SetRXAPanelGain1                  */
 int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per channel consumed per xrxa  */
 int quisk_cuda_rxa_out_size(const qcRxa *r);     /* dsp_outsize: samples per channel produced per xrxa */

@@ -109,6 +109,8 @@ int FirCore::flush()
 
 int FirCore::set_impulse(const double *impulse, int update)
 {   // calc_fircore: masks into the set that is NOT in use
+    if (impulse != h_impulse.data()) h_impulse.assign(impulse, impulse + (size_t)2 * nc);
+    impulse = h_impulse.data();
     std::vector<double> mpi;
     if (mp) {                               // calc_fircore, firmin.c:327-328
         mpi.resize((size_t)2 * nc);
@@ -126,6 +128,12 @@ int FirCore::set_impulse(const double *impulse, int update)
     masks_ready = 1;
     if (update) return this->update();
     return QC_OK;
+}
+
+int FirCore::set_mp(int mp_)
+{
+    mp = mp_ ? 1 : 0;
+    return set_impulse(h_impulse.data(), 1);
 }
 
 int FirCore::update()
@@ -192,6 +200,7 @@ void quisk_cuda_fircore_destroy(qcFircore *f) { if (f) { f->f.release(); delete 
 int quisk_cuda_fircore_run(qcFircore *f, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream)
 { return f ? f->f.run(d_in, in_stride, d_out, out_stride, (cudaStream_t)stream) : QC_EINVAL; }
 int quisk_cuda_fircore_set_impulse(qcFircore *f, const double *impulse, int update) { return f && impulse ? f->f.set_impulse(impulse, update) : QC_EINVAL; }
+int quisk_cuda_fircore_set_mp(qcFircore *f, int mp) { return f ? f->f.set_mp(mp) : QC_EINVAL; }
 int quisk_cuda_fircore_update(qcFircore *f) { return f ? f->f.update() : QC_EINVAL; }
 int quisk_cuda_fircore_flush(qcFircore *f) { return f ? f->f.flush() : QC_EINVAL; }
 

@@ -16,6 +16,8 @@ struct FirCore {
     void release();
     int flush();
     int set_impulse(const double *impulse, int update);
+    int set_mp(int mp);                     // setMp_fircore, firmin.c:469-473
+    std::vector<double> h_impulse;          // the impulse as handed in (a->impulse), for set_mp
     int update();
     int run(const void *d_in, long in_stride, void *d_out, long out_stride, cudaStream_t s);
 };

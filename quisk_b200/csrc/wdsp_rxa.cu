@@ -462,6 +462,13 @@ int quisk_cuda_rxa_get_siphon(qcRxa *p, float *h_out, int size, int complex_out)
     return QC_OK;
 }
 
+int quisk_cuda_rxa_set_mp(qcRxa *p, int mp)
+{   // RXASetMP, RXA.c:949-958, for the fircores this chain has: nbp0, bp1, the FM de-emphasis and audio filters
+    if (!p) return QC_EINVAL;
+    for (FirCore *f : {p->r.nbp0, p->r.bp1, p->r.pde, p->r.paud}) if (f) { int rc = f->set_mp(mp); if (rc != QC_OK) return rc; }
+    return QC_OK;
+}
+
 int quisk_cuda_rxa_set_slew(qcRxa *p, double tdelayup, double tslewup)
 { if (!p || tdelayup < 0 || tslewup < 0) return QC_EINVAL; return p->r.arm_upslew(tdelayup, tslewup); }
 

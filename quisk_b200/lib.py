@@ -153,6 +153,8 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_nbp_set_notches_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_nbp_set_tune_frequency.argtypes = [vp, D]
     lib.quisk_cuda_rxa_nbp_set_shift_frequency.argtypes = [vp, D]
+    lib.quisk_cuda_rxa_set_mp.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_fircore_set_mp.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_set_panel_gain.argtypes = [vp, D]
     lib.quisk_cuda_rxa_in_size.argtypes = [vp]
     lib.quisk_cuda_rxa_out_size.argtypes = [vp]

@@ -98,7 +98,15 @@ def test_fircore_minimum_phase(torch, lib, kat):
     y2 = o2.cpu().numpy()
     e_mp = np.sum(np.abs(y[0][:size]) ** 2); e_lin = np.sum(np.abs(y2[0][:size]) ** 2)
     assert e_mp > 10 * e_lin                         # minimum phase: output energy arrives in the first block
-    lib.quisk_cuda_fircore_destroy(f); lib.quisk_cuda_fircore_destroy(lin)
+    # setMp_fircore on a fresh linear-phase object gives the object created with mp = 1
+    sw = lib.quisk_cuda_fircore_create(NCH, size, nc, 0, imp.ctypes.data)
+    assert lib.quisk_cuda_fircore_set_mp(sw, 1) == 0
+    o3 = torch.zeros_like(d)
+    for b in range(8):
+        assert lib.quisk_cuda_fircore_run(sw, d[:, b * size:(b + 1) * size].data_ptr(), d.stride(0), o3[:, b * size:(b + 1) * size].data_ptr(), o3.stride(0), None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(o3.cpu().numpy(), y)
+    lib.quisk_cuda_fircore_destroy(f); lib.quisk_cuda_fircore_destroy(lin); lib.quisk_cuda_fircore_destroy(sw)
 
 
 @pytest.mark.parametrize("in_rate,out_rate,splits", RESAMPLE_CASES)
