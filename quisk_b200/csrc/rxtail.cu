@@ -55,40 +55,54 @@ __global__ void __launch_bounds__(TT) rx_tail_kernel(TailParams P)
     extern __shared__ double sm_raw[];
     const int c = blockIdx.x, tid = threadIdx.x;
     const int N = P.N, Hx = N - 1, n = P.n;
-    cd *X = reinterpret_cast<cd *>(sm_raw);                         // [xp(Hx + n + TR) + 1], indexed through xp()
-    double2 *hc = reinterpret_cast<double2 *>(X + xp(Hx + n + TR) + 1); // [N]
-    double *D = reinterpret_cast<double *>(hc + N);                 // [i_H + n]
+    constexpr int XO = 8;                                           // zero slots below sample 0 (a tap block may look there)
+    const int N4 = (N + 3) & ~3;                                    // taps padded with zeros to whole blocks of four
+    cd *X = reinterpret_cast<cd *>(sm_raw);                         // logical sample e in [-XO, Hx + n + TR) lives at xp(e + XO)
+    double2 *hc = reinterpret_cast<double2 *>(X + xp(XO + Hx + n + TR) + 1);    // [N4]
+    double *D = reinterpret_cast<double *>(hc + N4);                // [i_H + n]
     double *ic = D + P.i_H + n;                                     // [ntap_i]
     double *E = ic + P.ntap_i;                                      // [22 + 2n]
     double *F = E + 22 + 2 * n;                                     // [22 + 4n] (CW only)
     // ---- stage
     const cd *gh = P.rx_hin + (size_t)c * Hx;
-    for (int i = tid; i < Hx; i += TT) X[xp(i)] = gh[i];
+    for (int i = tid; i < XO; i += TT) X[xp(i)] = make_double2(0.0, 0.0);
+    for (int i = tid; i < Hx; i += TT) X[xp(XO + i)] = gh[i];
     const cd *gx = P.in + (size_t)c * P.in_stride;
-    for (int i = tid; i < n; i += TT) X[xp(Hx + i)] = gx[i];
-    for (int i = tid; i < TR; i += TT) X[xp(Hx + n + i)] = make_double2(0.0, 0.0);
-    for (int i = tid; i < N; i += TT) hc[i] = make_double2(P.rx_coef[2 * i], P.rx_coef[2 * i + 1]);
+    for (int i = tid; i < n; i += TT) X[xp(XO + Hx + i)] = gx[i];
+    for (int i = tid; i < TR; i += TT) X[xp(XO + Hx + n + i)] = make_double2(0.0, 0.0);
+    for (int i = tid; i < N4; i += TT) hc[i] = i < N ? make_double2(P.rx_coef[2 * i], P.rx_coef[2 * i + 1]) : make_double2(0.0, 0.0);
     for (int i = tid; i < P.i_H; i += TT) D[i] = P.i_hin[(size_t)c * P.i_H + i];
     for (int i = tid; i < P.ntap_i; i += TT) ic[i] = P.i_coef[i];
     for (int i = tid; i < 22; i += TT) E[i] = P.hb_hin[0][(size_t)c * 22 + i];
     if (P.n_hb == 2) for (int i = tid; i < 22; i += TT) F[i] = P.hb_hin[1][(size_t)c * 22 + i];
     __syncthreads();
-    // ---- receive filter + sideband combine: thread -> TR consecutive outputs, one new sample per tap step
+    // ---- receive filter + sideband combine.  A thread owns TR = 4 consecutive outputs and walks the taps in blocks of
+    //      four: output r meets tap k0 + kk at sample m0 + r - k0 - kk, so one block touches the seven samples
+    //      m0 - k0 - 3 .. m0 - k0 + 3, three of which carry over to the next block.  Per block: four sample loads, four
+    //      tap loads (broadcast), 32 FMAs -- the FP64 pipe, not the issue slots, sets the pace.
     for (int m0 = tid * TR; m0 < n; m0 += TT * TR) {
         double aI[TR], aQ[TR];
-        cd w[TR];
+        cd w[7];                                                    // w[d + 3] = X[m0 - k0 + d], d = -3 .. 3
 #pragma unroll
-        for (int r = 0; r < TR; r++) { aI[r] = 0.0; aQ[r] = 0.0; w[r] = X[xp(Hx + m0 + r)]; }      // age 0 of output r
-#pragma unroll 4
-        for (int k = 0; k < N; k++) {
-            const double2 h = hc[k];
+        for (int r = 0; r < TR; r++) { aI[r] = 0.0; aQ[r] = 0.0; }
 #pragma unroll
-            for (int r = 0; r < TR; r++) { aI[r] = fma(w[r].x, h.x, aI[r]); aQ[r] = fma(w[r].y, h.y, aQ[r]); }
-            // age k+1: output r needs X[m0 + r - k - 1] = what output r-1 used at age k
+        for (int i = 0; i < 7; i++) w[i] = X[xp(XO + Hx + m0 - 3 + i)];
+        for (int k0 = 0; k0 < N4; k0 += 4) {
+            double2 h[4];
 #pragma unroll
-            for (int r = TR - 1; r > 0; r--) w[r] = w[r - 1];
-            const int j = Hx + m0 - k - 1;
-            w[0] = j >= 0 ? X[xp(j)] : make_double2(0.0, 0.0);
+            for (int kk = 0; kk < 4; kk++) h[kk] = hc[k0 + kk];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+#pragma unroll
+                for (int r = 0; r < TR; r++) {
+                    aI[r] = fma(w[r - kk + 3].x, h[kk].x, aI[r]);
+                    aQ[r] = fma(w[r - kk + 3].y, h[kk].y, aQ[r]);
+                }
+            }
+            w[6] = w[2]; w[5] = w[1]; w[4] = w[0];
+            const int e = XO + Hx + m0 - k0 - 7;                    // >= XO + N - 1 - N4 - 3 - 3 >= 0
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[i] = X[xp(e + i)];
         }
 #pragma unroll
         for (int r = 0; r < TR; r++)
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(TT) rx_tail_kernel(TailParams P)
     }
     // ---- histories: last N-1 filter inputs, last i_H interpolator inputs, last 22 half-band inputs
     cd *oh = P.rx_hout + (size_t)c * Hx;
-    for (int i = tid; i < Hx; i += TT) oh[i] = X[xp(n + i)];
+    for (int i = tid; i < Hx; i += TT) oh[i] = X[xp(XO + n + i)];
     for (int i = tid; i < P.i_H; i += TT) P.i_hout[(size_t)c * P.i_H + i] = D[n + i];
     for (int i = tid; i < 22; i += TT) P.hb_hout[0][(size_t)c * 22 + i] = E[2 * n + i];
     if (P.n_hb == 2) {
@@ -154,7 +168,7 @@ int RxChain::run_tail(const cd *in, long in_stride, int n, double *out, long out
     }
     const int nout = n * 2 * (P.n_hb == 2 ? 4 : 2);
     if (out_stride < nout) { set_error("rx_process: audio_stride %ld < %d", out_stride, nout); return QC_EINVAL; }
-    const size_t sh = (size_t)(xp(P.N - 1 + n + TR) + 1) * sizeof(cd) + (size_t)P.N * sizeof(double2) +
+    const size_t sh = (size_t)(xp(8 + P.N - 1 + n + TR) + 1) * sizeof(cd) + (size_t)((P.N + 3) & ~3) * sizeof(double2) +
                       (size_t)(P.i_H + n + P.ntap_i + 22 + 2 * n + 22 + 4 * n + 8) * sizeof(double);
     if (sh > 200 * 1024) return QC_ENOMEM;           // caller falls back to the per-stage kernels
     if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rx_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
