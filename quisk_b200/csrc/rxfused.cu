@@ -325,7 +325,9 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
     const int c = blockIdx.x;
     const int tid = threadIdx.x;
     __shared__ cd s_pstep;                      // phase^NT
-    constexpr int NLD = 2048 / NT;              // loads per thread per chunk (T0 <= 2048)
+    // loads per thread per chunk: a plan kernel's chunk is what its first stage consumes in one round, 2 R0 NT samples
+    // (2048 for <128, 8> and <256, 4>, 1024 for <128, 4>); the generic kernel takes any T0 <= 2048
+    constexpr int NLD = sizeof...(PLAN) > 0 ? 2 * R0 : 2048 / NT;
     constexpr int NSL = 512 / NT;               // history elements a thread carries in the slide
 
     // zero everything once: pads, and the history beyond what the state arrays hold
@@ -678,7 +680,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         QC_CUDA(cudaEventRecord(e0, strm));
     }
     // plan code per stage: type*100 + R*10 + D
-    bool plan_ok = fused_plans && T0 == 2048;
+    bool plan_ok = fused_plans && T0 == 2 * R0 * NT;
     for (int s = 0; s < ns; s++) if (P.st[s].type == 1 && P.st[s].Kpad != 8 * FIR_KB) plan_ok = false;
     auto is_plan = [&](int sp, std::initializer_list<int> pl, int nt = 128) {
         if (!plan_ok || (int)pl.size() != ns || sp != split || nt != NT) return false;
@@ -695,6 +697,9 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     else if (is_plan(7, {82, 42, 22, 22, 142, 22, 112})) QC_LAUNCH(128, 8, 2, 7, 82, 42, 22, 22, 142, 22, 112);   // ... -> 12 k (SSB)
     else if (is_plan(8, {82, 42, 22, 22, 142, 22, 22, 112})) QC_LAUNCH(128, 8, 2, 8, 82, 42, 22, 22, 142, 22, 22, 112);   // ... -> 6 k (CW)
     else if (is_plan(6, {82, 42, 22, 22, 142, 122})) QC_LAUNCH(128, 8, 2, 6, 82, 42, 22, 22, 142, 122);           // ... -> 24 k (AM)
+    // half-size chunks (1024 samples): 8 loads in flight per thread instead of 16, half the shared memory, three CTAs per SM
+    else if (is_plan(7, {42, 22, 22, 22, 122, 22, 112}, 128)) QC_LAUNCH(128, 4, 3, 7, 42, 22, 22, 22, 122, 22, 112);
+    else if (is_plan(5, {42, 22, 22, 22, 122}, 128)) QC_LAUNCH(128, 4, 3, 5, 42, 22, 22, 22, 122);
     // 256-thread CTAs, two per SM under a 128-register cap (16 warps per SM)
     else if (is_plan(7, {42, 22, 22, 22, 122, 22, 112}, 256)) QC_LAUNCH(256, 4, 2, 7, 42, 22, 22, 22, 122, 22, 112);
     else if (is_plan(5, {42, 22, 22, 22, 122}, 256)) QC_LAUNCH(256, 4, 2, 5, 42, 22, 22, 22, 122);
