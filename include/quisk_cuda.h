@@ -18,7 +18,12 @@
  *   3. `quisk_cuda_rx_*` / `quisk_cuda_pan_*`: the fused receive chain
  *      (quisk_process_samples' tune -> quisk_process_decimate ->
  *      quisk_process_demodulate, quisk.c:2477-2530) and the panadapter
- *      (get_graph, quisk.c:5142-5331) for a batch of channels.
+ *      (get_graph, quisk.c:5142-5331) for a batch of channels; the stages
+ *      around them (process_agc, cFracDecim, get_bandscope), the wire-format
+ *      unpack loops in front of the chain, and the wideband polyphase
+ *      channelizer (one stream -> many receivers).
+ *
+ *   The WDSP side (fircore, resampler, RXA channel) is in quisk_cuda_wdsp.h.
  *
  * No torch types, no C++ types: plain pointers and sizes.  `stream` arguments
  * are a `cudaStream_t` passed as `void *` (NULL = the legacy default stream).
@@ -342,7 +347,7 @@ int quisk_cuda_pfb_process(qcChannelizer *p, const void *d_in, int count, void *
                            int *n_frames, void *stream);
 
 /* Batched complex FFT (unnormalised, sign -1 forward / +1 backward), sizes 2^k,
- * 8 <= n <= 16384: the in-house Stockham kernel the panadapter and the WDSP
+ * 8 <= n <= 8192: the in-house Stockham kernel the panadapter and the WDSP
  * overlap-save stages are built on; exported so tests can pin it against
  * numpy / cuFFT.  d_in may equal d_out. */
 int quisk_cuda_fft_batch(const void *d_in, void *d_out, int n, int batch, int sign, void *stream);
