@@ -169,3 +169,45 @@ class Channelizer:
             self.lib.quisk_cuda_pfb_destroy(self.h); self.h = None
 
     __del__ = close
+
+
+class Panadapter:
+    """Host-side mirror of the reference's panadapter interface for a batch of streams: `record_app(..., data_width,
+    ..., fft_size, ..., rate, ...)` sets the sizes (quisk.c:5946-6009), the sample thread fills FFT buffers
+    (quisk.c:2454-2475) and `get_graph(job, zoom, deltaf)` returns `data_width` dB values or None when nothing has
+    been averaged yet (quisk.c:5142-5331).  Frames live in device memory; graphs come back as a NumPy array
+    [n_streams, data_width]."""
+
+    def __init__(self, n_streams: int, fft_size: int, data_width: int, sample_rate: float):
+        self.lib = L.require_device()
+        self.n_streams, self.fft_size, self.data_width, self.sample_rate = n_streams, fft_size, data_width, float(sample_rate)
+        self.h = self.lib.quisk_cuda_pan_create(n_streams, fft_size)
+        if not self.h:
+            raise L.QuiskCudaError("pan_create: " + self.lib.quisk_cuda_last_error().decode())
+        self._graph = None
+
+    def add_frames(self, d_frames: int, stream_stride: int, n_frames: int, stream: int = 0):
+        """d_frames: device pointer to [n_streams][stream_stride] complex128, n_frames consecutive frames per stream."""
+        L.check(self.lib, self.lib.quisk_cuda_pan_accumulate(self.h, d_frames, stream_stride, n_frames, stream), "pan_accumulate")
+
+    @property
+    def count_fft(self) -> int: return self.lib.quisk_cuda_pan_count(self.h)
+
+    def get_graph(self, zoom: float = 1.0, deltaf: float = 0.0):
+        """None if no frame has been accumulated since the last graph (the reference returns None too), else the
+        graph of every stream; the running averages restart, as in the reference."""
+        if self.count_fft <= 0:
+            return None
+        import torch
+        if self._graph is None:
+            self._graph = torch.zeros((self.n_streams, self.data_width), dtype=torch.float64, device="cuda")
+        L.check(self.lib, self.lib.quisk_cuda_pan_graph(self.h, self.data_width, zoom, deltaf, self.sample_rate,
+                                                        self._graph.data_ptr(), None), "pan_graph")
+        torch.cuda.synchronize()
+        return self._graph.cpu().numpy()
+
+    def close(self):
+        if self.h:
+            self.lib.quisk_cuda_pan_destroy(self.h); self.h = None
+
+    __del__ = close

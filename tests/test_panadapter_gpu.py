@@ -123,3 +123,23 @@ def test_multirx_graph(torch, lib):
     for s in range(streams):
         assert np.max(np.abs(g[s] - O.multirx_graph(x[s]))) < 1e-9
     lib.quisk_cuda_pan_destroy(pan)
+
+
+def test_panadapter_host_mirror(torch, lib):
+    """quisk_b200.rx.Panadapter mirrors record_app / get_graph (quisk.c:5142-5331, 5946-6009): None until a frame has
+    been averaged, then data_width dB values per stream, and the averages restart."""
+    from quisk_b200.rx import Panadapter
+    n, data_width, streams = 2048, 512, 3
+    pan = Panadapter(streams, n, data_width, 48000.0)
+    assert pan.get_graph() is None
+    frames = np.stack([O.synth_iq(n * 2, 90 + s, 1.0).reshape(2, n) for s in range(streams)])
+    d = torch.from_numpy(frames.reshape(streams, -1)).cuda()
+    pan.add_frames(d.data_ptr(), 2 * n, 2)
+    assert pan.count_fft == 2
+    g = pan.get_graph(1.0, 0.0)
+    assert g.shape == (streams, data_width)
+    for s in range(streams):
+        ref = O.panadapter_pixels(O.panadapter_accumulate(frames[s]), 2, data_width, 1.0, 0.0, 48000.0)
+        assert np.max(np.abs(g[s] - ref)) < 1e-9
+    assert pan.get_graph() is None
+    pan.close()
