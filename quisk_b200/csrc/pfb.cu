@@ -224,11 +224,13 @@ __global__ void __launch_bounds__(128, (P >= 32 ? 3 : 4)) pfb_fir_kernel(PfbFirP
                     xr = fma(x.x, lo[t], xr); xi = fma(x.y, lo[t], xi);
                     if (OVS == 2) { yr = fma(x.x, hi[t], yr); yi = fma(x.y, hi[t], yi); }
                 }
-                xr += __shfl_xor_sync(0xffffffffu, xr, 16); xi += __shfl_xor_sync(0xffffffffu, xi, 16);
-                if (OVS == 2) { yr += __shfl_xor_sync(0xffffffffu, yr, 16); yi += __shfl_xor_sync(0xffffffffu, yi, 16); }
+                // each half finishes ONE frame (young half: m_lo, old half: m_lo + 1), so it only needs the partner's
+                // partial sum of that frame: one exchange of a complex value instead of two
+                const double sr = OVS == 2 ? (half ? xr : yr) : xr, si = OVS == 2 ? (half ? xi : yi) : xi;
+                const double pr = __shfl_xor_sync(0xffffffffu, sr, 16), pi = __shfl_xor_sync(0xffffffffu, si, 16);
                 const int m = mrel0 + OVS * (i + j) + half;
-                if (OVS == 2) { if (m >= ra && m < rb) uo[(size_t)m * K] = half ? make_double2(yr, yi) : make_double2(xr, xi); }
-                else if (!half && m >= ra && m < rb) uo[(size_t)m * K] = make_double2(xr, xi);
+                if (OVS == 2) { if (m >= ra && m < rb) uo[(size_t)m * K] = half ? make_double2(yr + pr, yi + pi) : make_double2(xr + pr, xi + pi); }
+                else if (!half && m >= ra && m < rb) uo[(size_t)m * K] = make_double2(xr + pr, xi + pi);
             }
         }
     }
