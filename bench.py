@@ -723,6 +723,14 @@ def main():
                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kms / ms,
                     "alg_bytes_per_launch": alg}
+        # C1 sits near the FP64 ridge -- quote the FP64 pipe next to HBM.  FMA instructions per input
+        # sample of the cascade: half bands 46 per output at rates 1/2, 1/4, 1/8, 1/16 and 1/64 (43.8), the two 98-tap
+        # FIRs at 1/32 and 1/128 (7.7), the tuning phasor (8): 59.5; the pipe's peak is measured on this device.
+        pk = C.c_double(0.0)
+        if lib.quisk_cuda_fp64_peak(C.byref(pk)) == 0 and pk.value > 0:
+            fma = 59.5 * C_ * block / (per_launch_ms / 1e3)
+            roofline["fp64"] = {"achieved": fma / 1e12, "peak": pk.value / 1e12, "unit": "TFMA/s", "frac": fma / pk.value,
+                                "fma_per_input_sample": 59.5, "peak_source": "measured (quisk_cuda_fp64_peak: 8 independent DFMA chains per thread)"}
     elif pan:
         alg = ALG_BYTES_PAN * C_ * block
         ach = alg * args.steps / (ms / 1e3) / 1e9

@@ -122,6 +122,9 @@ int quisk_cuda_set_device(int device);
 /* Kernels launched by this library since load (all threads); the bench reports the delta. */
 unsigned long long quisk_cuda_launch_count(void);
 const char *quisk_cuda_version(void);
+/* Measured FP64 pipe peak of the current device in DFMA per second (a saturating micro-benchmark, ~10 ms):
+ * the second roofline bench.py quotes for the kernels that sit near the FP64 ridge. */
+int quisk_cuda_fp64_peak(double *dfma_per_second);
 
 /* ------------------------------------------------------------------------
  * 2. Batched single-stage filters, device resident

@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rx_kernel_time.argtypes = [vp, c_double_p, c_int_p]
     lib.quisk_cuda_rx_read_trace.argtypes = [vp, vp, C.c_int]
     lib.quisk_cuda_pan_create.argtypes = [C.c_int, C.c_int]
+    lib.quisk_cuda_fp64_peak.argtypes = [C.POINTER(C.c_double)]
     lib.quisk_cuda_pan_create.restype = vp
     lib.quisk_cuda_pan_destroy.argtypes = [vp]
     lib.quisk_cuda_pan_destroy.restype = None
