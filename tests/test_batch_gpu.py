@@ -197,6 +197,26 @@ def test_c1_chain_kat(tune, fused, torch, tabs):
     rx.close()
 
 
+@pytest.mark.parametrize("fused", [0, 1])
+def test_c1_chain_ragged_blocks_tuned(fused, torch, tabs):
+    """Ragged block lengths (1, 2, 3, 7, ... samples, shorter than any stage's history, shorter than a fused chunk)
+    with tuning on: every phase, history and the block-start tuning phasor carry over, and the concatenated audio is
+    the fixture's stream."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    C = 2
+    rx = RxChain(C, 1536000, "USB", fi, fq, tabs, tune_hz=[12345.0] * C, fused=bool(fused))
+    x = np.stack([O.synth_iq(153600, 20, 1.0)] * C)
+    splits = [1, 2, 3, 7, 255, 256, 257, 1000, 4093, 15360, 18766, 2049, 31, 0, 33]
+    splits.append(153600 - sum(splits))
+    aud, ca, _, _ = _run_chain(torch, rx, x, splits)
+    assert sum(ca) == 4800
+    for c in range(C):
+        assert O.rel_rms(aud[c], kat["c1_tune12345/y"]) < 1e-12
+    rx.close()
+
+
 def test_c1_chain_closed_form_nco(torch, tabs):
     """QC_RX_OPT_EXACT_NCO = 0: block-start phasors from the closed form instead of the reference's recurrence;
     over the 0.1 s fixture both are far inside the tolerance (tests/test_c1_fullsize_gpu.py shows where they part)."""
