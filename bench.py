@@ -596,7 +596,7 @@ def main():
     rx = pan = None
     stream = torch.cuda.current_stream().cuda_stream
     if "rx_chain" in args.workload:
-        rx = RxChain(C_, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=[args.tune] * C_ if args.tune else None, fused=not args.unfused)
+        rx = RxChain(C_, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=[args.tune + 3.0 * (c % 101) for c in range(C_)] if args.tune else None, fused=not args.unfused)
         if args.chunk:
             rx.set_option(2, args.chunk)
         if args.threads:
@@ -667,7 +667,7 @@ def main():
         hx = torch.empty((Ce, block), dtype=torch.complex128).pin_memory()
         hx.copy_(x[:Ce].cpu())
         ha = torch.zeros((Ce, acap), dtype=torch.float64).pin_memory()
-        rx_h = RxChain(Ce, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=[args.tune] * Ce if args.tune else None, fused=not args.unfused)
+        rx_h = RxChain(Ce, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=[args.tune + 3.0 * (c % 101) for c in range(Ce)] if args.tune else None, fused=not args.unfused)
         hx_np = hx.numpy(); ha_np = ha.numpy()
         rx_h.process_host(hx_np, block, ha_np)
         barrier()
@@ -749,7 +749,7 @@ def main():
     line = {"metric": "complex MS/s through RX chain", "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "channels_per_gpu": C_, "block": block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune,
+            "config": {"workload": wl_name, "channels_per_gpu": C_, "block": block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune, "tune_spread": "receiver c is tuned to tune_hz + 3 (c mod 101) Hz",
                        "fused": not args.unfused, "nco": args.nco if args.tune else "off", "l2": "input %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (C_ * block * 16 / 1e6)},
             "clocks": sampler.result(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
     if e2e_wire:
