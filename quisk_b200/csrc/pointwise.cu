@@ -32,8 +32,9 @@ int launch_nco_advance(const cd *v_in, cd *v_out, const double *d_nco, int count
     // onto the first few SMs with a free slot, where 16+ dependent FP64 chains share one pipe and the recurrence
     // becomes the slowest thing on the device (measured: 1.6 ms instead of 0.4 ms for 32768 steps).  With the
     // reservation at most one or two land on an SM, and the two 90 KB CTAs of the fused decimator still fit beside them.
-    static bool optin = false;
-    if (!optin) { QC_CUDA(cudaFuncSetAttribute(nco_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024)); optin = true; }
+    static bool optin[64] = {};         // per device: function attributes belong to the device's context
+    int dev = 0; cudaGetDevice(&dev); dev &= 63;
+    if (!optin[dev]) { QC_CUDA(cudaFuncSetAttribute(nco_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024)); optin[dev] = true; }
     nco_advance_kernel<<<(C + 31) / 32, 32, 24 * 1024, s>>>(v_in, v_out, d_nco, count, C);
     count_launch();
     QC_CUDA_LAUNCH();

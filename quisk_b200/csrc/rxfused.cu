@@ -689,8 +689,9 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         return true;
     };
 #define QC_LAUNCH(...) do { \
-        static bool optin = false; \
-        if (!optin) { QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin = true; } \
+        static bool optin[64] = {}; \
+        int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63; \
+        if (!optin[dev_]) { QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin[dev_] = true; } \
         fused_decim_kernel<__VA_ARGS__><<<C, NT, sh, strm>>>(P); } while (0)
     // single-rate plans (every stage every chunk)
     if (is_plan(5, {82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 5, 82, 42, 22, 22, 142);                        // 1.536 MS/s -> 48 k
