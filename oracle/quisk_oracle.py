@@ -498,7 +498,8 @@ def panadapter_accumulate(frames: np.ndarray) -> np.ndarray:
     n = frames.shape[-1]
     w = hann_window(n)
     X = np.fft.fft(frames * w, axis=-1)
-    return np.abs(np.fft.fftshift(X, axes=-1)).sum(axis=0)
+    # graph bin k <- FFT bin (k + N/2) mod N with N/2 the C integer quotient (quisk.c:5272-5275): fftshift for even N
+    return np.abs(np.roll(X, -(n // 2), axis=-1)).sum(axis=0)
 
 
 def panadapter_pixels(fft_avg: np.ndarray, count_fft: int, data_width: int, zoom: float,

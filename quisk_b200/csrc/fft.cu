@@ -167,6 +167,47 @@ __global__ void __launch_bounds__(256, 2) pan_accumulate_split_kernel(const cd *
     for (int k = lane; k < H; k += lanes) dst[(2 * k + par + H) & (N - 1)] = sacc[k];
 }
 
+// Frames whose length is NOT a power of two (Quisk's fft_size = data_width x fft_mult, quisk.py:187-194, 4179, has
+// factors 3 ... 15): Bluestein's identity turns the n-point DFT into a circular convolution of length M >= 2n - 1,
+// M a power of two, so the same shared-memory transform serves:
+//     X[k] = w[k] * sum_j (x[j] w[j]) conj(w)[k - j],   w[j] = exp(-i pi j^2 / n)
+// a[j] = x[j] window[j] w[j] (zero padded to M) -> FFT_M -> times B = FFT_M(conj(w) wrapped) -> inverse FFT_M -> times
+// w[k] / M.  The chirp is built on the host with j^2 reduced mod 2n in integers, so its angle error does not grow
+// with j.  Costs two M-point transforms per frame (M up to 8192 for n <= 4096): a correctness path, not a fast one.
+template <int BPT>
+__global__ void __launch_bounds__(256) pan_accumulate_bluestein_kernel(const cd *frames, long stream_stride, int n_frames, int n, int M,
+                                      const cd *tw, const cd *chirpwin, const cd *chirp, const cd *B, double *avg, double *partial, int groups)
+{
+    extern __shared__ double smem_raw[];
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *s = twl + fft_tw_entries(M);
+    double *sacc = reinterpret_cast<double *>(s + M);        // [n]
+    fft_stage_twiddles(twl, tw, M);
+    const int stream = blockIdx.y, g = blockIdx.x;
+    const int lane = threadIdx.x, lanes = blockDim.x;
+    const int half = n / 2;                                  // graph bin k <- FFT bin (k + n/2) mod n, quisk.c:5271-5276
+    const double inv_M = 1.0 / (double)M;
+    double *dst = groups == 1 ? avg + (size_t)stream * n : partial + ((size_t)stream * groups + g) * n;
+    for (int k = lane; k < n; k += lanes) sacc[k] = groups == 1 ? dst[k] : 0.0;
+    const cd *base = frames + (size_t)stream * stream_stride;
+    for (int f = g; f < n_frames; f += groups) {
+        const cd *src = base + (size_t)f * n;
+        for (int j = lane; j < M; j += lanes) s[fsw(j)] = j < n ? cmul(src[j], chirpwin[j]) : make_double2(0.0, 0.0);
+        __syncthreads();
+        fft_smem<BPT>(s, M, twl, -1, lane, lanes);
+        for (int m = lane; m < M; m += lanes) s[fsw(m)] = cmul(s[fsw(m)], B[m]);
+        __syncthreads();
+        fft_smem<BPT>(s, M, twl, +1, lane, lanes);
+        for (int k = lane; k < n; k += lanes) {
+            int b = k + half; if (b >= n) b -= n;
+            const cd X = cmul(s[fsw(b)], chirp[b]);
+            sacc[k] += sqrt(fma(X.x, X.x, X.y * X.y)) * inv_M;
+        }
+        __syncthreads();
+    }
+    for (int k = lane; k < n; k += lanes) dst[k] = sacc[k];
+}
+
 __global__ void pan_reduce_kernel(double *avg, const double *partial, int n, int groups)
 {
     const int stream = blockIdx.y;
@@ -178,6 +219,15 @@ __global__ void pan_reduce_kernel(double *avg, const double *partial, int n, int
 }
 
 // graph-return half (quisk.c:5279-5321), hazard-free case: every pixel reads only bins >= its own index
+// First FFT bin of pixel i (quisk.c:5290), with every product and sum rounded separately as the reference's x86-64
+// code does: contracted into FMAs the value can land on the other side of an integer when fft_size is not a power of
+// two (n * x is exact only for powers of two), and the pixel would sum a different set of bins.
+__device__ __forceinline__ int pan_first_bin(int n, int i, int data_width, double zoom, double deltaf, double rate)
+{
+    const double t = __dadd_rn(__dadd_rn(__ddiv_rn(deltaf, rate), __dmul_rn(zoom, __dsub_rn(__ddiv_rn((double)i, (double)data_width), 0.5))), 0.5);
+    return (int)__dadd_rn(__dmul_rn((double)n, t), 0.1);
+}
+
 __global__ void pan_graph_kernel(double *avg, int n, int data_width, int nbin, double zoom, double deltaf,
                                  double rate, double scale, double *graph)
 {
@@ -185,7 +235,7 @@ __global__ void pan_graph_kernel(double *avg, int n, int data_width, int nbin, d
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= data_width) return;
     const double *a = avg + (size_t)stream * n;
-    int k = (int)(n * (deltaf / rate + zoom * ((double)i / data_width - 0.5) + 0.5) + 0.1);
+    int k = pan_first_bin(n, i, data_width, zoom, deltaf, rate);
     double d2 = 0.0;
     for (int j = 0; j < nbin; j++, k++)
         if (k >= 0 && k < n) d2 += a[k];
@@ -202,7 +252,7 @@ __global__ void pan_graph_serial_kernel(double *avg, int n, int data_width, int 
     double *a = avg + (size_t)blockIdx.y * n;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int i = 0; i < data_width; i++) {
-        int k = (int)(n * (deltaf / rate + zoom * ((double)i / data_width - 0.5) + 0.5) + 0.1);
+        int k = pan_first_bin(n, i, data_width, zoom, deltaf, rate);
         double d2 = 0.0;
         for (int j = 0; j < nbin; j++, k++)
             if (k >= 0 && k < n) d2 += a[k];
@@ -255,14 +305,18 @@ struct Panadapter {
     int partial_groups = 0;
     int count = 0;
     int split8192 = 1;          // 8192-point frames: two 4096-point CTAs per frame (pan_accumulate_split_kernel)
+    int M = 0;                  // > 0: Bluestein convolution length for a frame size that is not a power of two
+    cd *d_chirpwin = nullptr, *d_chirp = nullptr, *d_B = nullptr;
 
     int init(int streams, int fft_size)
     {
         S = streams; n = fft_size;
-        if (S <= 0 || fft_log2(n) < 0) {
-            set_error("pan_create: fft_size must be a power of two in [8, 8192] (got %d)", fft_size); return QC_EINVAL;
+        const bool pow2 = fft_log2(n) >= 0;
+        if (S <= 0 || (!pow2 && (n < 8 || n > 4096))) {
+            set_error("pan_create: fft_size must be a power of two in [8, 8192] or any size in [8, 4096] (got %d)", fft_size); return QC_EINVAL;
         }
-        tw = fft_twiddles(n);
+        if (!pow2) { M = 16; while (M < 2 * n - 1) M <<= 1; }
+        tw = fft_twiddles(pow2 ? n : M);
         if (!tw) { set_error("pan_create: twiddle table allocation failed"); return QC_ENOMEM; }
         std::vector<double> w((size_t)n);
         for (int i = 0, j = -n / 2; i < n; i++, j++) w[i] = 0.5 + 0.5 * cos(2. * M_PI * j / n);      // quisk.c:6003-6009
@@ -270,12 +324,33 @@ struct Panadapter {
         QC_CUDA(cudaMemcpy(d_window, w.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
         QC_CUDA(cudaMalloc((void **)&d_avg, (size_t)S * n * sizeof(double)));
         QC_CUDA(cudaMemset(d_avg, 0, (size_t)S * n * sizeof(double)));
+        if (M) {
+            // chirp w[j] = exp(-i pi j^2 / n), j^2 reduced mod 2n exactly; b = conj(w) wrapped around M; B = FFT_M(b)
+            std::vector<cd> ch((size_t)n), cw((size_t)n), b((size_t)M, make_double2(0.0, 0.0));
+            for (int j = 0; j < n; j++) {
+                const long long t = ((long long)j * j) % (2LL * n);
+                const double a = M_PI * (double)t / (double)n;
+                ch[j] = make_double2(cos(a), -sin(a));
+                cw[j] = make_double2(ch[j].x * w[j], ch[j].y * w[j]);
+                b[j] = make_double2(ch[j].x, -ch[j].y);
+                if (j) b[M - j] = b[j];
+            }
+            QC_CUDA(cudaMalloc((void **)&d_chirp, (size_t)n * sizeof(cd)));
+            QC_CUDA(cudaMalloc((void **)&d_chirpwin, (size_t)n * sizeof(cd)));
+            QC_CUDA(cudaMalloc((void **)&d_B, (size_t)M * sizeof(cd)));
+            QC_CUDA(cudaMemcpy(d_chirp, ch.data(), (size_t)n * sizeof(cd), cudaMemcpyHostToDevice));
+            QC_CUDA(cudaMemcpy(d_chirpwin, cw.data(), (size_t)n * sizeof(cd), cudaMemcpyHostToDevice));
+            QC_CUDA(cudaMemcpy(d_B, b.data(), (size_t)M * sizeof(cd), cudaMemcpyHostToDevice));
+            int rc = quisk_cuda_fft_batch(d_B, d_B, M, 1, -1, nullptr); if (rc != QC_OK) return rc;
+            QC_CUDA(cudaDeviceSynchronize());
+        }
         return QC_OK;
     }
     void release()
     {
         if (d_window) cudaFree(d_window); if (d_avg) cudaFree(d_avg); if (d_partial) cudaFree(d_partial);
-        d_window = d_avg = d_partial = nullptr;
+        if (d_chirp) cudaFree(d_chirp); if (d_chirpwin) cudaFree(d_chirpwin); if (d_B) cudaFree(d_B);
+        d_window = d_avg = d_partial = nullptr; d_chirp = d_chirpwin = d_B = nullptr;
     }
 };
 
@@ -341,11 +416,11 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
     // whole extra wave (16 streams: 608 CTAs on 296 slots ran 3 waves of 7 frames; 288 CTAs run 1 wave of 15).
     const bool split = p.n == 8192 && p.split8192;
     const int cpf = split ? 2 : 1;                                   // CTAs per frame
-    const size_t cta_smem = split ? (size_t)4096 * 24 + 8192 : (size_t)p.n * 24 + 4096;
+    const size_t cta_smem = split ? (size_t)4096 * 24 + 8192 : (p.M ? (size_t)p.M * 16 + (size_t)p.n * 8 + 4096 : (size_t)p.n * 24 + 4096);
     int per_sm = (int)((size_t)220 * 1024 / cta_smem);
-    const int reg_cap = p.n >= 4096 ? 2 : 4;                         // 256 threads x ~128 registers (255 at 8192 unsplit)
+    const int reg_cap = (p.M ? p.M : p.n) >= 4096 ? 2 : 4;                         // 256 threads x ~128 registers (255 at 8192 unsplit)
     if (per_sm > reg_cap) per_sm = reg_cap;
-    if (p.n == 8192 && !split) per_sm = 1;
+    if ((p.n == 8192 && !split) || p.M == 8192) per_sm = 1;
     if (per_sm < 1) per_sm = 1;
     int n_sm = 148;
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
@@ -362,9 +437,20 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
         QC_CUDA(cudaMalloc((void **)&p.d_partial, (size_t)p.S * groups * p.n * sizeof(double)));
         p.partial_groups = groups;
     }
-    const int lanes = fft_threads(p.n);
+    const int lanes = fft_threads(p.M ? p.M : p.n);
     int rc;
-    if (p.n == 8192 && p.split8192) {
+    if (p.M) {
+        const size_t sh = (size_t)p.M * sizeof(cd) + (size_t)p.n * sizeof(double) + (size_t)fft_tw_entries(p.M) * sizeof(cd);
+        if (p.M > 4096) {
+            rc = fft_smem_optin((const void *)pan_accumulate_bluestein_kernel<2>, sh); if (rc != QC_OK) return rc;
+            pan_accumulate_bluestein_kernel<2><<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.M, p.tw,
+                                                                                     p.d_chirpwin, p.d_chirp, p.d_B, p.d_avg, p.d_partial, groups);
+        } else {
+            rc = fft_smem_optin((const void *)pan_accumulate_bluestein_kernel<1>, sh); if (rc != QC_OK) return rc;
+            pan_accumulate_bluestein_kernel<1><<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.M, p.tw,
+                                                                                     p.d_chirpwin, p.d_chirp, p.d_B, p.d_avg, p.d_partial, groups);
+        }
+    } else if (p.n == 8192 && p.split8192) {
         const cd *tw4 = fft_twiddles(4096);
         if (!tw4) { set_error("pan_accumulate: twiddle table allocation failed"); return QC_ENOMEM; }
         const size_t sh = (size_t)4096 * (sizeof(cd) + sizeof(double)) + (size_t)(fft_tw_entries(4096) + fft_tw_entries(8192)) * sizeof(cd);
@@ -428,6 +514,7 @@ int quisk_cuda_pan_graph(qcPanadapter *pp, int data_width, double zoom, double d
 int quisk_cuda_pan_multirx(qcPanadapter *pp, const void *d_frames, long stream_stride, double *d_graph, void *stream)
 {
     if (!pp) { set_error("pan_multirx: null handle"); return QC_EINVAL; }
+    if (pp->p.M) { set_error("pan_multirx: needs a power-of-two fft_size (got %d)", pp->p.n); return QC_EINVAL; }
     Panadapter &p = pp->p;
     const int lanes = fft_threads(p.n);
     const size_t sh = ((size_t)p.n + fft_tw_entries(p.n)) * sizeof(cd);
