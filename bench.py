@@ -197,7 +197,8 @@ RXA_CFG = {
 def rxa_reference_rate(cfg, blocks, steps, warmup):
     """The reference's own stage functions (libwdsp_ref.so: wdsp/*.c + our FFTW-API shim -- FFTW3 itself is absent
     from this image) composed in xrxa's order, one channel per host core."""
-    from tests.golden.make_golden_wdsp import wdsp, bandpass, sig, fm_sig
+    from tests.golden.make_golden_wdsp import wdsp, bandpass
+    from quisk_b200.synth import sig, fm_sig
     lib = wdsp()
     cores = os.cpu_count() or 1
     n, m = cfg["dsp_size"], cfg["in_size"]
@@ -259,7 +260,7 @@ def rxa_main(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from quisk_b200 import lib as L
-    from tests.golden.make_golden_wdsp import sig, fm_sig
+    from quisk_b200.synth import sig, fm_sig           # plain NumPy generators: the product arm imports nothing from oracle/
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
