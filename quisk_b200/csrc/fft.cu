@@ -120,41 +120,52 @@ __global__ void __launch_bounds__(256) pan_accumulate_kernel(const cd *frames, l
 // so CTA parity p owns the bins of parity p, works on 64 KiB, runs one butterfly per thread (128 registers) and two
 // such CTAs share an SM.  Each frame is read by both CTAs of its pair (the second read is an L2 hit when the pair is
 // co-scheduled, which adjacent blockIdx.x makes the common case).  Bin sums keep the reference's frame order.
+// SP = 2, 4, 8: frames of N = SP x 4096 points (8192, 16384, 32768).  The first decimation-in-frequency step, radix SP,
+// is done on the way in:  X[SP k + q] = FFT4096( w^{j q} sum_m x[j + 4096 m] W_SP^{m q} ),  w = exp(-2 pi i / N).
+template <int SP>
 __global__ void __launch_bounds__(256, 2) pan_accumulate_split_kernel(const cd *frames, long stream_stride, int n_frames,
-                                      const cd *tw8, const cd *tw4, const double *window, double *avg, double *partial, int groups)
+                                      const cd *twN, const cd *tw4, const double *window, double *avg, double *partial, int groups)
 {
-    constexpr int N = 8192, H = 4096;
+    constexpr int H = 4096, N = SP * H;
     extern __shared__ double smem_raw[];
     cd *twl4 = reinterpret_cast<cd *>(smem_raw);
-    cd *twl8 = twl4 + fft_tw_entries(H);
-    cd *s = twl8 + fft_tw_entries(N);
+    cd *twlN = twl4 + fft_tw_entries(H);
+    cd *s = twlN + fft_tw_entries(N);
     double *sacc = reinterpret_cast<double *>(s + H);        // [H] running sums of this CTA's bins
     fft_stage_twiddles(twl4, tw4, H);
-    fft_stage_twiddles(twl8, tw8, N);
-    const int stream = blockIdx.y, g = blockIdx.x >> 1, par = blockIdx.x & 1;
+    fft_stage_twiddles(twlN, twN, N);
+    const int stream = blockIdx.y, g = blockIdx.x / SP, par = blockIdx.x % SP;
     const int lane = threadIdx.x, lanes = blockDim.x;
     double *dst = groups == 1 ? avg + (size_t)stream * N : partial + ((size_t)stream * groups + g) * N;
-    // FFT bin b = 2 k + par shows at graph bin (b + H) mod N (fftshift, quisk.c:5271-5276)
-    for (int k = lane; k < H; k += lanes) sacc[k] = groups == 1 ? dst[(2 * k + par + H) & (N - 1)] : 0.0;
+    // FFT bin b = SP k + par shows at graph bin (b + N/2) mod N (fftshift, quisk.c:5271-5276)
+    for (int k = lane; k < H; k += lanes) sacc[k] = groups == 1 ? dst[(SP * k + par + N / 2) & (N - 1)] : 0.0;
     const cd *base = frames + (size_t)stream * stream_stride;
+    // W_SP^{m par}, m < SP: exp(-2 pi i m par / SP) = entry (m par mod SP) N / SP of the N-point table
+    cd wq[SP];
     __syncthreads();
+#pragma unroll
+    for (int m = 0; m < SP; m++) wq[m] = fft_tw(twlN, ((m * par) % SP) * (N / SP), -1);
     for (int f = g; f < n_frames; f += groups) {
         const cd *src = base + (size_t)f * N;
         for (int j = lane; j < H; j += lanes) {
-            const cd x0 = src[j], x1 = src[j + H];
-            const double w0 = window[j], w1 = window[j + H];
-            const cd a = make_double2(x0.x * w0, x0.y * w0), b = make_double2(x1.x * w1, x1.y * w1);      // quisk.c:5212-5213
-            cd v;
-            if (par == 0) v = cadd(a, b);
-            else v = cmul(csub(a, b), fft_tw(twl8, j, -1));
+            cd v = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int m = 0; m < SP; m++) {
+                const cd x = src[j + m * H];
+                const double w = window[j + m * H];
+                const cd a = make_double2(x.x * w, x.y * w);                        // quisk.c:5212-5213
+                if (m == 0 || par == 0) v = cadd(v, a);
+                else v = cadd(v, cmul(a, wq[m]));
+            }
+            if (par != 0) v = cmul(v, fft_tw(twlN, j * par, -1));
             s[fsw(j)] = v;
         }
         __syncthreads();
-        // pull this CTA's next frame towards L2 while the transform runs (its pair partner fetches the other half):
+        // pull this CTA's next frame towards L2 while the transform runs (each CTA of the group fetches its share):
         // the load phase above is otherwise the only time this CTA has memory requests in flight
         if (f + groups < n_frames) {
-            const char *nxt = reinterpret_cast<const char *>(base + (size_t)(f + groups) * N) + (size_t)par * (N * sizeof(cd) / 2);
-            for (int l = lane; l < (int)(N * sizeof(cd) / 2 / 128); l += lanes)
+            const char *nxt = reinterpret_cast<const char *>(base + (size_t)(f + groups) * N) + (size_t)par * (N * sizeof(cd) / SP);
+            for (int l = lane; l < (int)(N * sizeof(cd) / SP / 128); l += lanes)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (size_t)l * 128));
         }
         fft_smem<1>(s, H, twl4, -1, lane, lanes);
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(256, 2) pan_accumulate_split_kernel(const cd *
         }
         __syncthreads();
     }
-    for (int k = lane; k < H; k += lanes) dst[(2 * k + par + H) & (N - 1)] = sacc[k];
+    for (int k = lane; k < H; k += lanes) dst[(SP * k + par + N / 2) & (N - 1)] = sacc[k];
 }
 
 // Frames whose length is NOT a power of two (Quisk's fft_size = data_width x fft_mult, quisk.py:187-194, 4179, has
@@ -311,9 +322,9 @@ struct Panadapter {
     int init(int streams, int fft_size)
     {
         S = streams; n = fft_size;
-        const bool pow2 = fft_log2(n) >= 0;
+        const bool pow2 = fft_log2(n) >= 0 || n == 16384 || n == 32768;       // the two largest run split over 4 / 8 CTAs
         if (S <= 0 || (!pow2 && (n < 8 || n > 4096))) {
-            set_error("pan_create: fft_size must be a power of two in [8, 8192] or any size in [8, 4096] (got %d)", fft_size); return QC_EINVAL;
+            set_error("pan_create: fft_size must be a power of two in [8, 32768] or any size in [8, 4096] (got %d)", fft_size); return QC_EINVAL;
         }
         if (!pow2) { M = 16; while (M < 2 * n - 1) M <<= 1; }
         tw = fft_twiddles(pow2 ? n : M);
@@ -414,10 +425,10 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
     // Frames of a stream are split over `groups` CTAs only when the streams alone cannot fill the machine, and then
     // so that ALL CTAs are resident at once (one wave): a grid a little larger than the number of slots costs a
     // whole extra wave (16 streams: 608 CTAs on 296 slots ran 3 waves of 7 frames; 288 CTAs run 1 wave of 15).
-    const bool split = p.n == 8192 && p.split8192;
-    const int cpf = split ? 2 : 1;                                   // CTAs per frame
-    const size_t cta_smem = split ? (size_t)4096 * 24 + 8192 : (p.M ? (size_t)p.M * 16 + (size_t)p.n * 8 + 4096 : (size_t)p.n * 24 + 4096);
-    int per_sm = (int)((size_t)220 * 1024 / cta_smem);
+    const bool split = (p.n == 8192 && p.split8192) || p.n > 8192;
+    const int cpf = split ? p.n / 4096 : 1;                          // CTAs per frame
+    const size_t cta_smem = split ? (size_t)4096 * 24 + (size_t)(fft_tw_entries(4096) + fft_tw_entries(p.n)) * sizeof(cd) + 1024 : (p.M ? (size_t)p.M * 16 + (size_t)p.n * 8 + 4096 : (size_t)p.n * 24 + 4096);
+    int per_sm = (int)((size_t)226 * 1024 / cta_smem);
     const int reg_cap = (p.M ? p.M : p.n) >= 4096 ? 2 : 4;                         // 256 threads x ~128 registers (255 at 8192 unsplit)
     if (per_sm > reg_cap) per_sm = reg_cap;
     if ((p.n == 8192 && !split) || p.M == 8192) per_sm = 1;
@@ -450,13 +461,15 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
             pan_accumulate_bluestein_kernel<1><<<dim3(groups, p.S), lanes, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.n, p.M, p.tw,
                                                                                      p.d_chirpwin, p.d_chirp, p.d_B, p.d_avg, p.d_partial, groups);
         }
-    } else if (p.n == 8192 && p.split8192) {
+    } else if (split) {
         const cd *tw4 = fft_twiddles(4096);
         if (!tw4) { set_error("pan_accumulate: twiddle table allocation failed"); return QC_ENOMEM; }
-        const size_t sh = (size_t)4096 * (sizeof(cd) + sizeof(double)) + (size_t)(fft_tw_entries(4096) + fft_tw_entries(8192)) * sizeof(cd);
-        rc = fft_smem_optin((const void *)pan_accumulate_split_kernel, sh); if (rc != QC_OK) return rc;
-        pan_accumulate_split_kernel<<<dim3(2 * groups, p.S), 256, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.tw, tw4,
-                                                                           p.d_window, p.d_avg, p.d_partial, groups);
+        const size_t sh = (size_t)4096 * (sizeof(cd) + sizeof(double)) + (size_t)(fft_tw_entries(4096) + fft_tw_entries(p.n)) * sizeof(cd);
+#define PAN_SPLIT(SP) do { rc = fft_smem_optin((const void *)pan_accumulate_split_kernel<SP>, sh); if (rc != QC_OK) return rc; \
+        pan_accumulate_split_kernel<SP><<<dim3(SP * groups, p.S), 256, sh, s>>>((const cd *)d_frames, stream_stride, n_frames, p.tw, tw4, \
+                                                                                p.d_window, p.d_avg, p.d_partial, groups); } while (0)
+        if (p.n == 8192) PAN_SPLIT(2); else if (p.n == 16384) PAN_SPLIT(4); else PAN_SPLIT(8);
+#undef PAN_SPLIT
     } else {
         const size_t sh = (size_t)p.n * (sizeof(cd) + sizeof(double)) + (size_t)fft_tw_entries(p.n) * sizeof(cd);
         if (p.n > 4096) {
@@ -514,7 +527,7 @@ int quisk_cuda_pan_graph(qcPanadapter *pp, int data_width, double zoom, double d
 int quisk_cuda_pan_multirx(qcPanadapter *pp, const void *d_frames, long stream_stride, double *d_graph, void *stream)
 {
     if (!pp) { set_error("pan_multirx: null handle"); return QC_EINVAL; }
-    if (pp->p.M) { set_error("pan_multirx: needs a power-of-two fft_size (got %d)", pp->p.n); return QC_EINVAL; }
+    if (pp->p.M || pp->p.n > 8192) { set_error("pan_multirx: needs a power-of-two fft_size <= 8192 (got %d)", pp->p.n); return QC_EINVAL; }
     Panadapter &p = pp->p;
     const int lanes = fft_threads(p.n);
     const size_t sh = ((size_t)p.n + fft_tw_entries(p.n)) * sizeof(cd);

@@ -172,3 +172,30 @@ def test_panadapter_sizes_that_are_not_powers_of_two(n, torch, lib):
         assert np.max(np.abs(g[s] - ref_g)) < 1e-8
     lib.quisk_cuda_pan_destroy(pan)
     assert not lib.quisk_cuda_pan_create(2, 5000)            # beyond the Bluestein range and not a power of two
+
+
+@pytest.mark.parametrize("n,streams,count_fft", [(16384, 3, 3), (32768, 2, 2), (16384, 40, 1)])
+def test_panadapter_large_frames(n, streams, count_fft, torch, lib):
+    """16384- and 32768-point frames: a radix-4 / radix-8 decimation-in-frequency step on the way in, four / eight
+    4096-point CTAs per frame."""
+    data_width = 1024
+    frames = np.stack([O.synth_iq(n * count_fft, 140 + s, 1.0).reshape(count_fft, n) for s in range(streams)])
+    d = torch.from_numpy(frames.reshape(streams, -1)).cuda()
+    pan = lib.quisk_cuda_pan_create(streams, n)
+    assert pan, lib.quisk_cuda_last_error()
+    assert lib.quisk_cuda_pan_accumulate(pan, d.data_ptr(), n * count_fft, count_fft, None) == 0, lib.quisk_cuda_last_error()
+    torch.cuda.synchronize()
+    avg_ptr = lib.quisk_cuda_pan_average_ptr(pan)
+    avg = torch.empty((streams, n), dtype=torch.float64, device="cuda")
+    C.CDLL("libcudart.so.12").cudaMemcpy(C.c_void_p(avg.data_ptr()), C.c_void_p(avg_ptr), streams * n * 8, 3)
+    avg = avg.cpu().numpy()
+    g = torch.empty((streams, data_width), dtype=torch.float64, device="cuda")
+    assert lib.quisk_cuda_pan_graph(pan, data_width, 1.0, 0.0, 1536000.0, g.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    g = g.cpu().numpy()
+    for s in range(0, streams, max(1, streams // 4)):
+        ref_avg = O.panadapter_accumulate(frames[s])
+        assert O.rel_rms(avg[s], ref_avg) < 1e-12
+        ref_g = O.panadapter_pixels(ref_avg, count_fft, data_width, 1.0, 0.0, 1536000.0)
+        assert np.max(np.abs(g[s] - ref_g)) < 1e-9
+    lib.quisk_cuda_pan_destroy(pan)
