@@ -542,6 +542,8 @@ def main():
     ap.add_argument("--min-r", type=int, default=0, help="fused decimator: min outputs per thread in half-band stages")
     ap.add_argument("--dense", type=int, default=-1, help="fused decimator: 1 = 128-register cap, 0 = 255")
     ap.add_argument("--plans", type=int, default=-1, help="fused decimator: 0 = generic kernel only")
+    ap.add_argument("--split", type=int, default=-1, help="fused decimator: 1 = one lane per component in the half bands (default), 0 = complex lanes")
+    ap.add_argument("--tailwarp", type=int, default=-1, help="fused decimator: 1 = low-rate stages on a fifth warp (default), 0 = all stages on the four main warps")
     ap.add_argument("--deepk", type=int, default=0, help="fused decimator: low-rate stages every k chunks (1 or 4)")
     ap.add_argument("--nco", default="exact", choices=["exact", "closed"], help="tuning phasor at block starts: the reference's recurrence (default) or closed form only")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -610,6 +612,10 @@ def main():
             rx.set_option(6, args.plans)
         if args.deepk:
             rx.set_option(8, args.deepk)
+        if args.split >= 0:
+            rx.set_option(11, args.split)
+        if args.tailwarp >= 0:
+            rx.set_option(12, args.tailwarp)
         if args.nco == "closed":
             rx.set_option(10, 0)
         acap = rx.max_out(block)

@@ -55,6 +55,8 @@ struct RxChain {
     int fused_deepk = 1;                // plan kernels: run the <=128-sample stages once per this many chunks (1 = every chunk)
     int fused_plans = 1;                // use the plan-specialised instantiations when one matches
     int fused_dense = 0;                // 1: cap registers at 128/thread for more resident CTAs
+    int fused_tailwarp = 1;             // plan kernels: the low-rate stages run on a fifth warp, one chunk behind (fused_decim_tw_kernel)
+    int fused_split = 0;                // plan kernels: half bands with one lane per component (hb_stage_split)
     int fused_min_r = 0;                // force at least this many outputs per thread in half-band stages
     int fused_tail = 1;                 // SSB / CW: run filter + demod + audio interpolators as one kernel (rxtail.cu)
     // optional device timing of the dominant (fused) kernel

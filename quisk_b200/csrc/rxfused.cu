@@ -39,6 +39,7 @@ struct FStage {
     int Ha;             // history kept in shared memory (>= Hs, covers the zero-padded taps)
     int u0;             // offset of the first output-producing sample among the new samples
     int R;
+    int split;          // half band: 1 = a lane PAIR shares R outputs, one lane per component (hb_stage_split)
     int pu;             // pad unit (0 = unpadded)
     unsigned magic;     // ceil(2^32 / pu)
     int org;            // origin shift: q = logical + org
@@ -65,6 +66,7 @@ struct FusedParams {
     int scratch;        // offset of the history-slide scratch area (cd units)
     int coef_sm;        // offset of the tap copy in shared memory (cd units)
     int ncoef;
+    int tw_stride;      // tail-warp kernel: distance (cd units) between the two halves of the first tail stage's input buffer
     int deepk;          // multi-rate plans: the deep stages run once per this many chunks
     long long *trace;   // optional [C][16 chunks][16] clock64() stamps (debug)
     double coef[MAXCOEF];
@@ -95,6 +97,17 @@ struct Sink {           // where a stage's outputs go: the next stage's buffer o
             g[m] = v;
         }
     }
+    template <bool TOGLOBAL>
+    __device__ __forceinline__ void put_c(int m, int comp, double v) const      // one component of output m
+    {
+        if constexpr (!TOGLOBAL) {
+            const unsigned q = (unsigned)(H + m + org);
+            double *d = reinterpret_cast<double *>(sm);
+            d[2 * (q + __umulhi(q, magic)) + comp] = v;
+        } else {
+            reinterpret_cast<double *>(g)[2 * m + comp] = v;
+        }
+    }
 };
 
 __device__ __forceinline__ cd fmaz(cd a, double c, cd acc) { return make_double2(fma(a.x, c, acc.x), fma(a.y, c, acc.y)); }
@@ -106,9 +119,8 @@ __device__ __forceinline__ cd fmaz(cd a, double c, cd acc) { return make_double2
 // coef[min(k, 21-k)] (filter.c:401-413 without the pre-addition of the symmetric pair: same number
 // of FP64 operations, a quarter of the registers).
 template <int R>
-__device__ __forceinline__ void hb_stage(const cd *__restrict__ sb, int p0, int n_out, const Sink &sink)
+__device__ __forceinline__ void hb_stage(const cd *__restrict__ sb, int p0, int n_out, const Sink &sink, const int t)
 {
-    const int t = threadIdx.x;
     const int m0 = t * R;
     if (m0 >= n_out) return;
     const cd *w = sb + p0 + (2 * R + 1) * t;
@@ -129,6 +141,40 @@ __device__ __forceinline__ void hb_stage(const cd *__restrict__ sb, int p0, int 
         const cd o = w[(21 + 2 * r) + (21 + 2 * r) / (2 * R)];     // center[10] = X[n - 21]
         acc[r] = fmaz(o, c_hb[11], acc[r]);
         if (m0 + r < n_out) sink.put(m0 + r, acc[r]);
+    }
+}
+
+// Half band with the two components of a sample on two adjacent lanes: lane 2p handles the real parts and lane 2p+1
+// the imaginary parts of outputs R p .. R p + R - 1.  For the same number of accumulator registers a lane covers
+// twice as many consecutive outputs as hb_stage, so the 21-sample halo of its window is amortised over twice the
+// work: (21 + 2R) 8-byte loads per R component outputs, i.e. 53 x 8 B per 16 at R = 16 against 37 x 16 B per 8
+// complex outputs at R = 8 -- 28 % fewer shared-memory wavefronts in stage 0, 36-42 % in the deeper stages.  The
+// pair's window starts every 2R+1 elements = 8R+4 words, so a half-warp's 8-byte loads cover all 32 banks once.
+// Same FMA order per component as hb_stage: the two variants are bit-identical.
+template <int R, bool TOGLOBAL>
+__device__ __forceinline__ void hb_stage_split(const cd *__restrict__ sb, int p0, int n_out, const Sink &sink, const int t)
+{
+    const int pr = t >> 1, comp = t & 1;
+    const int m0 = pr * R;
+    if (m0 >= n_out) return;
+    const double *w = reinterpret_cast<const double *>(sb + p0 + (2 * R + 1) * pr) + comp;
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 22 + R - 1; j++) {
+        const double e = w[2 * (2 * j + (2 * j) / (2 * R))];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int k = r + 21 - j;
+            if (k >= 0 && k <= 21) acc[r] = fma(e, c_hb[k <= 10 ? k : 21 - k], acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const double o = w[2 * ((21 + 2 * r) + (21 + 2 * r) / (2 * R))];
+        acc[r] = fma(o, c_hb[11], acc[r]);
+        if (m0 + r < n_out) sink.template put_c<TOGLOBAL>(m0 + r, comp, acc[r]);
     }
 }
 
@@ -182,12 +228,11 @@ __device__ __forceinline__ void fir_stage(const cd *__restrict__ sb, const FStag
 // Plan-specialised FIR: the whole (zero-padded) tap table is TS * KB long, so a lane's KB taps never
 // change -- they are loaded into registers once per kernel (cf) -- and one register window of
 // KB + D (R - 1) samples feeds R outputs.  lane = g * TS + ts.
-template <int D, int NT, int R>
+template <int D, int NT, int R, bool TOGLOBAL>
 __device__ __forceinline__ void fir_stage_c(const cd *__restrict__ sb, const FStage &s, const double (&cf)[FIR_KB],
-                                            int n_out, const Sink &sink)
+                                            int n_out, const Sink &sink, const int t)
 {
-    constexpr int KB = FIR_KB, W = KB + D * (R - 1), TS = 8;
-    const int t = threadIdx.x;
+    constexpr int KB = FIR_KB, W = KB + D * (R - 1), TS = 8, V = 2 * R;
     const int ts = t & (TS - 1);
     int g = t / TS;
     const int n_groups = (n_out + R - 1) / R;
@@ -207,19 +252,37 @@ __device__ __forceinline__ void fir_stage_c(const cd *__restrict__ sb, const FSt
 #pragma unroll
             for (int r = 0; r < R; r++) acc[r] = fmaz(Wn[D * r + KB - 1 - kk], cf[kk], acc[r]);
         }
+        // Sum over the 8 tap lanes as a reduce-scatter: in the round with lane distance `off` a lane keeps one half of
+        // its value list and hands the other half to its partner, so 2R values cost 2R - 1 exchanges (7 for R = 4)
+        // instead of the 3 x 2R of an all-reduce butterfly, and lane ts ends up with value ts (output ts / 2,
+        // component ts & 1), which it stores itself.  Same pairs, same tree: bit-identical sums.
+        double v[V];
+#pragma unroll
+        for (int r = 0; r < R; r++) { v[2 * r] = acc[r].x; v[2 * r + 1] = acc[r].y; }
+        int idx = 0;
+        int n = V;
 #pragma unroll
         for (int off = TS >> 1; off > 0; off >>= 1) {
+            const bool up = (ts & off) != 0;
+            if (n >= 2) {
+                const int half = n / 2;
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, off);
-                acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, off);
+                for (int i = 0; i < V / 2; i++) {
+                    if (i < half) {
+                        const double send = up ? v[i] : v[i + half];
+                        const double keep = up ? v[i + half] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                idx += up ? half : 0;
+                n = half;
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
             }
         }
-        if (live && ts == 0) {
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                if (R * g + r < n_out) sink.put(R * g + r, acc[r]);
-        }
+        // lanes that share a value after the plain butterfly rounds: the lowest one stores
+        constexpr int DUP = V >= TS ? 1 : TS / V;
+        if (live && (ts & (DUP - 1)) == 0 && R * g + (idx >> 1) < n_out) sink.template put_c<TOGLOBAL>(R * g + (idx >> 1), idx & 1, v[0]);
     }
 }
 
@@ -249,10 +312,51 @@ __device__ __forceinline__ void run_stage_c(cd *sm, const FusedParams &P, int n_
     }
     const cd *sb = sm + S.buf;
     if constexpr (TYPE == 0) {
-        hb_stage<R>(sb, S.p0, n_out, sink);
+        hb_stage<R>(sb, S.p0, n_out, sink, threadIdx.x);
+    } else if constexpr (TYPE == 2) {           // CODE's R digit is the complex-equivalent blocking: a lane runs 2 R outputs
+        hb_stage_split<2 * R, LAST>(sb, S.p0, n_out, sink, threadIdx.x);
     } else {
-        fir_stage_c<D, NT, R>(sb, S, ft.cf[FIRIDX], n_out, sink);
+        fir_stage_c<D, NT, R, LAST>(sb, S, ft.cf[FIRIDX], n_out, sink, threadIdx.x);
     }
+}
+
+// ---- the same cascade for the tail-warp kernel: NT threads numbered t = 0 .. NT-1 run stages [START, STOP) and meet at
+//      a barrier of their own kind (SYNC 1: named barrier 1 of the 128 main threads; SYNC 2: the tail warp alone).
+//      src_off shifts the input buffer of stage START, sink_off the output position of stage STOP-1 (the two halves of
+//      the double buffer between the main warps and the tail warp).
+template <int SYNC> __device__ __forceinline__ void group_sync()
+{
+    if constexpr (SYNC == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else if constexpr (SYNC == 2) asm volatile("bar.sync 6, 64;" ::: "memory");
+    else __syncthreads();
+}
+
+template <int NT, int SYNC, bool FULL, int START, int STOP, int IDX, int FIRIDX, int CODE0, int... REST>
+__device__ __forceinline__ int cascade_x(cd *sm, const FusedParams &P, int n_in, cd *gdst, const FirTaps &ft, const int t, int src_off, int sink_off)
+{
+    constexpr int TYPE = CODE0 / 100, R = (CODE0 / 10) % 10, D = CODE0 % 10;
+    constexpr int NEXTFIR = FIRIDX + (TYPE == 1 ? 1 : 0);
+    constexpr bool LAST = sizeof...(REST) == 0;
+    int n_out = n_in;
+    if constexpr (IDX >= START && IDX < STOP) {
+        const FStage &S = P.st[IDX];
+        n_out = FULL ? S.n_out_full : (n_in > S.u0 ? (n_in - S.u0 - 1) / D + 1 : 0);
+        Sink sink;
+        if constexpr (!LAST) {
+            const FStage &N = P.st[IDX + 1];
+            sink.sm = sm + N.buf; sink.H = N.Ha + (IDX == STOP - 1 ? sink_off : 0); sink.org = N.org; sink.magic = N.magic; sink.g = nullptr;
+        } else {
+            sink.sm = nullptr; sink.H = 0; sink.org = 0; sink.magic = 0; sink.g = gdst;
+        }
+        const cd *sb = sm + S.buf + (IDX == START ? src_off : 0);
+        if constexpr (TYPE == 0) hb_stage<R>(sb, S.p0, n_out, sink, t);
+        else fir_stage_c<D, NT, R, LAST>(sb, S, ft.cf[FIRIDX], n_out, sink, t);
+        group_sync<SYNC>();
+    }
+    if constexpr (sizeof...(REST) > 0 && IDX + 1 < STOP)
+        return cascade_x<NT, SYNC, FULL, START, STOP, IDX + 1, NEXTFIR, REST...>(sm, P, n_out, gdst, ft, t, src_off, sink_off);
+    else
+        return n_out;
 }
 
 // Runs stages [START, STOP) of the plan.  n_in is the input count of stage START; sink_off is where, behind
@@ -302,9 +406,9 @@ __device__ __forceinline__ void run_stage(cd *sm, const FusedParams &P, int s, i
     }
     const cd *sb = sm + S.buf;
     if (S.type == 0) {
-        if (S.R == 8) { if constexpr (NT == 128) hb_stage<8>(sb, S.p0, n_out, sink); }
-        else if (S.R == 4) hb_stage<4>(sb, S.p0, n_out, sink);
-        else hb_stage<2>(sb, S.p0, n_out, sink);
+        if (S.R == 8) { if constexpr (NT == 128) hb_stage<8>(sb, S.p0, n_out, sink, threadIdx.x); }
+        else if (S.R == 4) hb_stage<4>(sb, S.p0, n_out, sink, threadIdx.x);
+        else hb_stage<2>(sb, S.p0, n_out, sink, threadIdx.x);
     } else {
         const double *coef = reinterpret_cast<const double *>(sm + P.coef_sm) + S.coef;
         if (S.D == 2) fir_stage<2, NT>(sb, S, coef, n_out, sink);
@@ -317,6 +421,9 @@ __device__ __forceinline__ void run_stage(cd *sm, const FusedParams &P, int s, i
 // SPLIT: plan kernels only -- stages [SPLIT, ns) are "deep": they run once every P.deepk chunks on the
 // accumulated output of stage SPLIT-1, which amortises their fixed per-phase latency (they carry <10 % of
 // the flops but cost ~30 % of a chunk's time when run every chunk).  SPLIT == number of stages: no deep part.
+template <int... P> struct PlanFirst { static constexpr int code = 0; };
+template <int C0, int... P> struct PlanFirst<C0, P...> { static constexpr int code = C0; };
+
 template <int NT, int R0, int MINB, int SPLIT, int... PLAN>
 __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_constant__ FusedParams P)
 {
@@ -386,7 +493,8 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
     // stage 0's new samples: element k*NT + tid lands at pb0 + k*step0 (NT is a multiple of the pad unit)
     // (stage 0 is padded every 2*R0 elements when it is a half band, unpadded when it is a FIR)
     cd *pb0 = sm + S0.buf + phys(S0, S0.Ha + tid);
-    constexpr int STEP_PAD = NT + NT / (2 * R0);
+    constexpr int PU0 = PlanFirst<PLAN...>::code / 100 == 2 ? 4 * R0 : 2 * R0;      // stage 0's pad unit
+    constexpr int STEP_PAD = NT + NT / PU0;
     const bool pad0 = S0.pu != 0;
     const bool tune = P.tune != 0;
 
@@ -513,6 +621,175 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
     }
 }
 
+// ---- Tail-warp variant of the plan kernels.  The stages behind the fourth half band see 128 samples or fewer per
+// chunk: run by all 128 threads they are three barrier-separated phases of pure latency (window loads -> a 13-deep FMA
+// chain -> three shuffle rounds), 2000 of a chunk's 6900 cycles for 12 % of its flops.  Here two extra warps (the "tail warps") own them:
+// the four main warps run commit + stages 0 .. TS-1 of chunk n while the tail warp runs stages TS .. of chunk n-1 out
+// of the other half of a double-buffered stage-TS input.  Hand-over by named barriers (PTX producer/consumer pattern):
+// READY[p] = 2 + p (main arrives, tail waits), FREE[p] = 4 + p (tail arrives, main waits before refilling half p);
+// barrier 1 is the main warps' own.  The stage-TS history is carried from the tail of one half to the front of the other.
+// Same arithmetic in the same order as fused_decim_kernel: bit-identical outputs and state.
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int TS, int... PLAN>
+__global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_constant__ FusedParams P)
+{
+    constexpr int NT = 128, NTT = 64, NTA = NT + NTT, R0 = 8, NLD = 2 * R0, T0 = NLD * NT, NS = (int)sizeof...(PLAN);
+    extern __shared__ double smem_raw[];
+    cd *sm = reinterpret_cast<cd *>(smem_raw);
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ cd s_pstep;
+    __shared__ cd s_q[NLD];
+
+    for (int i = tid; i < P.smem_cd; i += NTA) sm[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (int s = 0; s < P.ns; s++) {
+        const FStage &S = P.st[s];
+        const cd *h = S.hin + (size_t)c * S.Hs;
+        for (int i = tid; i < S.Hs; i += NTA) sm[S.buf + phys(S, (S.Ha - S.Hs) + i)] = h[i];
+    }
+    {
+        double *cs = reinterpret_cast<double *>(sm + P.coef_sm);
+        for (int i = tid; i < P.ncoef; i += NTA) cs[i] = P.coef[i];
+    }
+    cd u = make_double2(1.0, 0.0), pstep = make_double2(1.0, 0.0);
+    if (P.tune) {
+        const double *nc = P.nco + (size_t)c * 8;
+        if (tid == 0) s_pstep = nco_pow(nc, (unsigned long long)T0);
+        if (tid < NLD) s_q[tid] = nco_pow(nc, (unsigned long long)tid * NT);
+        if (tid < NT) u = cmul_rn(P.vstart[c], nco_pow(nc, P.n_base + (unsigned long long)tid));
+    }
+    __syncthreads();
+    const int n_full = P.n_in / T0;
+    const int rem = P.n_in - n_full * T0;
+    const FStage &ST = P.st[TS];
+    const int tws = P.tw_stride;
+    cd *gout = P.out + (size_t)c * P.out_stride;
+    FirTaps ft;
+    auto load_taps = [&](int lane) {
+        const double *cs = reinterpret_cast<const double *>(sm + P.coef_sm);
+        int fi = 0;
+        for (int s = 0; s < P.ns && fi < MAXFIR; s++) {
+            if (P.st[s].type == 1) {
+#pragma unroll
+                for (int kk = 0; kk < FIR_KB; kk++) {
+                    const double v = cs[P.st[s].coef + (lane & 7) * FIR_KB + kk];
+                    if (fi == 0) ft.cf[0][kk] = v; else ft.cf[1][kk] = v;
+                }
+                fi++;
+            }
+        }
+    };
+
+    if (tid >= NT) {
+        // ================= tail warp: stages TS .. NS-1, one chunk behind the main warps
+        const int t = tid - NT;
+        load_taps(t);
+        constexpr int NSLT = 256 / NTT;         // in-place history slides of stages TS+1 .. (at most 256 elements)
+        int ts_src[NSLT], ts_dst[NSLT];
+#pragma unroll
+        for (int e = 0; e < NSLT; e++) slide_entry(P, TS + 1, P.ns, t + e * NTT, ts_src[e], ts_dst[e]);
+        int out_pos = 0;
+        for (int ch = 0; ch < n_full; ch++) {
+            const int p = ch & 1;
+            bar_sync(2 + p, NTA);
+            out_pos += cascade_x<NTT, 2, true, TS, NS, 0, 0, PLAN...>(sm, P, 0, gout + out_pos, ft, t, p * tws, 0);
+            const cd *hs = sm + ST.buf + p * tws + ST.n_full;
+            cd *hd = sm + ST.buf + (p ^ 1) * tws;
+            for (int i = t; i < ST.Ha; i += NTT) hd[i] = hs[i];
+            cd kd[NSLT];
+#pragma unroll
+            for (int e = 0; e < NSLT; e++) if (ts_src[e] >= 0) kd[e] = sm[ts_src[e]];
+            group_sync<2>();
+#pragma unroll
+            for (int e = 0; e < NSLT; e++) if (ts_src[e] >= 0) sm[ts_dst[e]] = kd[e];
+            group_sync<2>();
+            if (ch + 2 < n_full) bar_arrive(4 + p, NTA);
+        }
+    } else {
+        // ================= main warps: NCO + commit + stages 0 .. TS-1
+        constexpr int NSL = 2;                  // four half bands: 4 x 48 history elements
+        int sl_src[NSL], sl_dst[NSL];
+#pragma unroll
+        for (int e = 0; e < NSL; e++) slide_entry(P, 0, TS, tid + e * NT, sl_src[e], sl_dst[e]);
+        if (P.tune) pstep = s_pstep;
+        const cd *gin = P.in + (size_t)c * P.in_stride;
+        const FStage &S0 = P.st[0];
+        cd *pb0 = sm + S0.buf + phys(S0, S0.Ha + tid);
+        constexpr int STEP_PAD = NT + NT / (2 * R0);
+        const bool tune = P.tune != 0;
+        cd nx[NLD];
+        if (n_full > 0) {
+#pragma unroll
+            for (int k = 0; k < NLD; k++) nx[k] = gin[k * NT + tid];
+        }
+        for (int ch = 0; ch < n_full; ch++) {
+            const int p = ch & 1;
+            if (tune) {
+#pragma unroll
+                for (int k = 0; k < NLD; k++) {
+                    const cd q = s_q[k];
+                    const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                    nx[k] = make_double2(fma(nx[k].x, v.x, -nx[k].y * v.y), fma(nx[k].x, v.y, nx[k].y * v.x));
+                }
+                u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
+            }
+#pragma unroll
+            for (int k = 0; k < NLD; k++) pb0[k * STEP_PAD] = nx[k];
+            group_sync<1>();
+            if (ch + 1 < n_full) {
+                const cd *g1 = gin + (size_t)(ch + 1) * T0 + tid;
+#pragma unroll
+                for (int k = 0; k < NLD; k++) nx[k] = g1[k * NT];
+            }
+            cascade_x<NT, 1, true, 0, TS - 1, 0, 0, PLAN...>(sm, P, T0, nullptr, ft, tid, 0, 0);
+            if (ch >= 2) bar_sync(4 + p, NTA);                  // the tail warp has finished with half p (chunk ch - 2)
+            cascade_x<NT, 1, true, TS - 1, TS, 0, 0, PLAN...>(sm, P, 0, nullptr, ft, tid, 0, p * tws);
+            bar_arrive(2 + p, NTA);
+            cd keep[NSL];
+#pragma unroll
+            for (int e = 0; e < NSL; e++) if (sl_src[e] >= 0) keep[e] = sm[sl_src[e]];
+            group_sync<1>();
+#pragma unroll
+            for (int e = 0; e < NSL; e++) if (sl_src[e] >= 0) sm[sl_dst[e]] = keep[e];
+        }
+    }
+    __syncthreads();
+    if (tid >= NT) return;
+    // the stage-TS history sits at the front of half (n_full & 1): bring it to half 0, where the code below expects it
+    if (n_full & 1) {
+        for (int i = tid; i < ST.Ha; i += NT) sm[ST.buf + i] = sm[ST.buf + tws + i];
+    }
+    group_sync<1>();
+    // ---- ragged tail (at most one partial chunk): every stage on the main warps, generic indexing
+    int n_s = 0;
+    if (rem > 0) {
+        load_taps(tid);
+        const cd *g1 = P.in + (size_t)c * P.in_stride + (size_t)n_full * T0;
+        const FStage &S0 = P.st[0];
+        for (int i = tid, k = 0; i < rem; i += NT, k++) {
+            cd x = g1[i];
+            if (P.tune) {
+                const cd q = s_q[k];
+                const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                x = make_double2(fma(x.x, v.x, -x.y * v.y), fma(x.x, v.y, x.y * v.x));
+            }
+            sm[S0.buf + phys(S0, S0.Ha + i)] = x;
+        }
+        group_sync<1>();
+        cascade_x<NT, 1, false, 0, NS, 0, 0, PLAN...>(sm, P, rem, gout + n_full * P.st[NS - 1].n_out_full, ft, tid, 0, 0);
+        n_s = rem;
+    }
+    for (int s = 0; s < P.ns; s++) {
+        const FStage &S = P.st[s];
+        cd *h = S.hout + (size_t)c * S.Hs;
+        for (int i = tid; i < S.Hs; i += NT) h[i] = sm[S.buf + phys(S, n_s + (S.Ha - S.Hs) + i)];
+        n_s = stage_out_count(S, n_s);
+    }
+}
+
 struct FusedDecimator {
     FusedParams P;
     size_t smem_bytes = 0;
@@ -579,6 +856,10 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     }
     int codes[MAXST];
     size_t sh = 0;
+    // component-split half bands (hb_stage_split): plan kernels at the full chunk only
+    constexpr int TW_TS = 4;                // tail-warp kernel: stages from this index on belong to the fifth warp
+    bool use_tw = fused_tailwarp && fused_plans && NT == 128 && T0 == 2048 && split == ns && ns > TW_TS && !d_trace;
+    bool use_split = !use_tw && fused_split && fused_plans && NT == 128 && T0 == 2048 && split == ns;
     // stage descriptors for a given multi-rate split (no filter state is touched here)
     auto build = [&](int split, int deepk) -> int {
     P.deepk = deepk;
@@ -597,6 +878,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
             const int nout = chunk_in / 2;
             S.R = nout > 4 * NT ? 8 : (nout > 2 * NT ? 4 : 2);
             if (fused_min_r > S.R) S.R = fused_min_r;
+            if (use_split) { S.split = 1; S.R *= 2; }
             S.pu = 2 * S.R;
             S.magic = (unsigned)((0x100000000ULL + S.pu - 1) / S.pu);
             // window start of thread 0 (logical Ha + u0 - 42) must land on a pad boundary
@@ -625,10 +907,11 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         }
         S.buf = off;
         off += S.buf_len;
+        if (use_tw && s == TW_TS) { P.tw_stride = S.buf_len; off += S.buf_len; }
         S.n_full = chunk_in;
         S.n_out_full = chunk_in / S.D;
         chunk_in = chunk_in / S.D;
-        codes[s] = S.type * 100 + (S.type ? S.Rplan : S.R) * 10 + S.D;
+        codes[s] = S.type ? 100 + S.Rplan * 10 + S.D : (S.split ? 200 + (S.R / 2) * 10 + 2 : S.R * 10 + 2);
     }
     P.scratch = off;
     {
@@ -657,11 +940,41 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         return false;
     };
     int rcb;
-    if (split != ns) {
+    if (use_split) {
+        static const int plans[4][MAXST] = {{282, 242, 222, 222, 142}, {282, 242, 222, 222, 142, 222, 112},
+                                            {282, 242, 222, 222, 142, 222, 222, 112}, {282, 242, 222, 222, 142, 122}};
+        static const int lens[4] = {5, 7, 8, 6};
+        rcb = build(ns, 1);
+        bool found = false;
+        for (int p = 0; p < 4 && rcb == QC_OK; p++) {
+            if (lens[p] != ns) continue;
+            bool ok = true;
+            for (int i = 0; i < ns; i++) ok = ok && codes[i] == plans[p][i];
+            found = found || ok;
+        }
+        if (!found) use_split = false;
+    }
+    if (use_tw) {
+        static const int plans[4][MAXST] = {{82, 42, 22, 22, 142}, {82, 42, 22, 22, 142, 22, 112},
+                                            {82, 42, 22, 22, 142, 22, 22, 112}, {82, 42, 22, 22, 142, 122}};
+        static const int lens[4] = {5, 7, 8, 6};
+        rcb = build(ns, 1);
+        bool found = false;
+        for (int p = 0; p < 4 && rcb == QC_OK; p++) {
+            if (lens[p] != ns) continue;
+            bool ok = true;
+            for (int i = 0; i < ns; i++) ok = ok && codes[i] == plans[p][i];
+            found = found || ok;
+        }
+        for (int s = 0; s < ns; s++) if (P.st[s].type == 1 && P.st[s].Kpad != 8 * FIR_KB) found = false;
+        if (!found) { use_tw = false; P.tw_stride = 0; }
+    }
+    if (use_tw || use_split) {
+    } else if (split != ns) {
         rcb = build(split, deepk);
         if (rcb != QC_OK || split != 4 || !multi_plan_exists()) { split = ns; deepk = 1; }
     }
-    if (split == ns) { rcb = build(ns, 1); if (rcb != QC_OK) return rcb; }
+    if (split == ns && !use_split && !use_tw) { rcb = build(ns, 1); if (rcb != QC_OK) return rcb; }
     // host-side phase bookkeeping, same formulas as BatchFilter::run
     int n = count;
     for (int s = 0; s < ns; s++) {
@@ -673,7 +986,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         n = no;
     }
     *n_out = n;
-    const int R0 = P.st[0].type == 0 ? P.st[0].R : 2;
+    const int R0 = P.st[0].type == 0 ? (P.st[0].split ? P.st[0].R / 2 : P.st[0].R) : 2;       // complex outputs per thread (pair)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timing) {
         QC_CUDA(cudaEventCreate(&e0)); QC_CUDA(cudaEventCreate(&e1));
@@ -693,11 +1006,26 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63; \
         if (!optin[dev_]) { QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin[dev_] = true; } \
         fused_decim_kernel<__VA_ARGS__><<<C, NT, sh, strm>>>(P); } while (0)
+#define QC_LAUNCH_TW(...) do { \
+        static bool optin[64] = {}; \
+        int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63; \
+        if (!optin[dev_]) { QC_CUDA(cudaFuncSetAttribute(fused_decim_tw_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin[dev_] = true; } \
+        fused_decim_tw_kernel<__VA_ARGS__><<<C, 192, sh, strm>>>(P); } while (0)
+    // tail-warp kernels (default): the stages behind the fourth half band run on a fifth warp, one chunk behind
+    if (use_tw && ns == 5) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142);
+    else if (use_tw && ns == 7) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142, 22, 112);
+    else if (use_tw && ns == 8) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142, 22, 22, 112);
+    else if (use_tw && ns == 6) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142, 122);
     // single-rate plans (every stage every chunk)
-    if (is_plan(5, {82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 5, 82, 42, 22, 22, 142);                        // 1.536 MS/s -> 48 k
+    else if (is_plan(5, {82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 5, 82, 42, 22, 22, 142);                        // 1.536 MS/s -> 48 k
     else if (is_plan(7, {82, 42, 22, 22, 142, 22, 112})) QC_LAUNCH(128, 8, 2, 7, 82, 42, 22, 22, 142, 22, 112);   // ... -> 12 k (SSB)
     else if (is_plan(8, {82, 42, 22, 22, 142, 22, 22, 112})) QC_LAUNCH(128, 8, 2, 8, 82, 42, 22, 22, 142, 22, 22, 112);   // ... -> 6 k (CW)
     else if (is_plan(6, {82, 42, 22, 22, 142, 122})) QC_LAUNCH(128, 8, 2, 6, 82, 42, 22, 22, 142, 122);           // ... -> 24 k (AM)
+    // the same four with component-split half bands (default)
+    else if (is_plan(5, {282, 242, 222, 222, 142})) QC_LAUNCH(128, 8, 2, 5, 282, 242, 222, 222, 142);
+    else if (is_plan(7, {282, 242, 222, 222, 142, 222, 112})) QC_LAUNCH(128, 8, 2, 7, 282, 242, 222, 222, 142, 222, 112);
+    else if (is_plan(8, {282, 242, 222, 222, 142, 222, 222, 112})) QC_LAUNCH(128, 8, 2, 8, 282, 242, 222, 222, 142, 222, 222, 112);
+    else if (is_plan(6, {282, 242, 222, 222, 142, 122})) QC_LAUNCH(128, 8, 2, 6, 282, 242, 222, 222, 142, 122);
     // half-size chunks (1024 samples): 8 loads in flight per thread instead of 16, half the shared memory, three CTAs per SM
     else if (is_plan(7, {42, 22, 22, 22, 122, 22, 112}, 128)) QC_LAUNCH(128, 4, 3, 7, 42, 22, 22, 22, 122, 22, 112);
     else if (is_plan(5, {42, 22, 22, 22, 122}, 128)) QC_LAUNCH(128, 4, 3, 5, 42, 22, 22, 22, 122);
@@ -719,6 +1047,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         else { if (fused_dense) QC_LAUNCH(128, 2, 4, 0); else QC_LAUNCH(128, 2, 2, 0); }
     }
 #undef QC_LAUNCH
+#undef QC_LAUNCH_TW
     count_launch();
     QC_CUDA_LAUNCH();
     if (timing) { QC_CUDA(cudaEventRecord(e1, strm)); timed.push_back(std::make_pair(e0, e1)); }
