@@ -250,7 +250,7 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_TRACE        7   /* debug: record clock64() stamps per chunk phase in the fused kernel */
 #define QC_RX_OPT_FUSED_PLANS  6   /* 1 (default): use plan-specialised kernels when the stage list matches one */
 #define QC_RX_OPT_FUSED_DENSE  5   /* 1: 128-register cap (more resident CTAs), 0: up to 255 registers */
-#define QC_RX_OPT_FUSED_TAILWARP 12 /* 1 (default): plan kernels run the stages behind the fourth half band on a fifth warp, one chunk behind the main warps */
+#define QC_RX_OPT_FUSED_TAILWARP 12 /* plan kernels run the low-rate stages on two tail warps, one chunk behind the four main warps: 1 (default: from stage 3), 2..4 = first tail stage, 0 = off */
 #define QC_RX_OPT_FUSED_SPLIT 11   /* 1: half-band stages of the plan kernels run one lane per component, twice the outputs per lane */
 #define QC_RX_OPT_FUSED_MIN_R  4   /* minimum outputs per thread in its half-band stages: 0 (auto), 2, 4, 8 */
 int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value);

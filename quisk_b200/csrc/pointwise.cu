@@ -35,7 +35,11 @@ int launch_nco_advance(const cd *v_in, cd *v_out, const double *d_nco, int count
     static bool optin[64] = {};         // per device: function attributes belong to the device's context
     int dev = 0; cudaGetDevice(&dev); dev &= 63;
     if (!optin[dev]) { QC_CUDA(cudaFuncSetAttribute(nco_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024)); optin[dev] = true; }
-    nco_advance_kernel<<<(C + 31) / 32, 32, 24 * 1024, s>>>(v_in, v_out, d_nco, count, C);
+    // 128 threads: the four warps of a CTA sit on the four sub-partitions of ONE SM, so every sub-partition of that SM
+    // gives up the same share of its FP64 pipe.  One-warp CTAs put the whole load on a single sub-partition of 128
+    // different SMs, and the barriers of the decimator CTAs living there make their other three warps wait for it
+    // (measured: the recurrence cost 12 % of the step that way, its FP64 work is 3.6 % of it).
+    nco_advance_kernel<<<(C + 127) / 128, 128, 24 * 1024, s>>>(v_in, v_out, d_nco, count, C);
     count_launch();
     QC_CUDA_LAUNCH();
     return QC_OK;

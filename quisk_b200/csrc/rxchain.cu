@@ -483,7 +483,8 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
         rx->rx.fused_deepk = value; return QC_OK;
     case QC_RX_OPT_FUSED_PLANS: rx->rx.fused_plans = value != 0; return QC_OK;
     case QC_RX_OPT_FUSED_DENSE: rx->rx.fused_dense = value; return QC_OK;
-    case QC_RX_OPT_FUSED_TAILWARP: rx->rx.fused_tailwarp = value != 0; return QC_OK;
+    case QC_RX_OPT_FUSED_TAILWARP: if (value < 0 || value > 4) { qc::set_error("rx_set_option: tail-warp split must be 0 (off), 1 (default) or the first tail stage 2..4"); return QC_EINVAL; }
+        rx->rx.fused_tailwarp = value; return QC_OK;
     case QC_RX_OPT_FUSED_SPLIT: rx->rx.fused_split = value != 0; return QC_OK;
     case QC_RX_OPT_FUSED_MIN_R:
         if (value != 0 && value != 2 && value != 4 && value != 8) { qc::set_error("rx_set_option: min R must be 0/2/4/8"); return QC_EINVAL; }

@@ -344,7 +344,7 @@ __device__ __forceinline__ int cascade_x(cd *sm, const FusedParams &P, int n_in,
         Sink sink;
         if constexpr (!LAST) {
             const FStage &N = P.st[IDX + 1];
-            sink.sm = sm + N.buf; sink.H = N.Ha + (IDX == STOP - 1 ? sink_off : 0); sink.org = N.org; sink.magic = N.magic; sink.g = nullptr;
+            sink.sm = sm + N.buf + (IDX == STOP - 1 ? sink_off : 0); sink.H = N.Ha; sink.org = N.org; sink.magic = N.magic; sink.g = nullptr;
         } else {
             sink.sm = nullptr; sink.H = 0; sink.org = 0; sink.magic = 0; sink.g = gdst;
         }
@@ -629,11 +629,17 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
 // READY[p] = 2 + p (main arrives, tail waits), FREE[p] = 4 + p (tail arrives, main waits before refilling half p);
 // barrier 1 is the main warps' own.  The stage-TS history is carried from the tail of one half to the front of the other.
 // Same arithmetic in the same order as fused_decim_kernel: bit-identical outputs and state.
+// 160 registers: two CTAs of six warps put three warps on every SM sub-partition (16384 registers each); at 168 they
+// fill it to the last 256 registers and the one-warp-per-sub-partition CTAs of nco_advance_kernel (768 registers per
+// warp) can only run by displacing a whole decimator CTA for the 0.36 ms they live.
+#ifndef TW_MAXREG
+#define TW_MAXREG 160
+#endif
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int TS, int... PLAN>
-__global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_constant__ FusedParams P)
+__global__ void __maxnreg__(TW_MAXREG) fused_decim_tw_kernel(const __grid_constant__ FusedParams P)
 {
     constexpr int NT = 128, NTT = 64, NTA = NT + NTT, R0 = 8, NLD = 2 * R0, T0 = NLD * NT, NS = (int)sizeof...(PLAN);
     extern __shared__ double smem_raw[];
@@ -643,13 +649,32 @@ __global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_con
     __shared__ cd s_pstep;
     __shared__ cd s_q[NLD];
 
+    // the first chunk and the stage histories are requested before anything else: their latency (one HBM round trip
+    // each; the histories were seven dependent round trips when loaded stage by stage) hides under the zero fill
+    const int n_full = P.n_in / T0;
+    const int rem = P.n_in - n_full * T0;
+    const cd *gin = P.in + (size_t)c * P.in_stride;
+    cd nx[NLD];
+    if (tid < NT && n_full > 0) {
+#pragma unroll
+        for (int k = 0; k < NLD; k++) nx[k] = gin[k * NT + tid];
+    }
+    constexpr int NHL = 3;                      // history elements per thread (at most 3 x 192 = 576 >= the 512 the planner admits)
+    cd hv[NHL]; int hdst[NHL];
+#pragma unroll
+    for (int e = 0; e < NHL; e++) {
+        int idx = tid + e * NTA;
+        hdst[e] = -1;
+        for (int s = 0; s < P.ns; s++) {
+            const FStage &S = P.st[s];
+            if (idx >= 0 && idx < S.Hs) { hdst[e] = S.buf + phys(S, (S.Ha - S.Hs) + idx); hv[e] = S.hin[(size_t)c * S.Hs + idx]; }
+            idx -= S.Hs;
+        }
+    }
     for (int i = tid; i < P.smem_cd; i += NTA) sm[i] = make_double2(0.0, 0.0);
     __syncthreads();
-    for (int s = 0; s < P.ns; s++) {
-        const FStage &S = P.st[s];
-        const cd *h = S.hin + (size_t)c * S.Hs;
-        for (int i = tid; i < S.Hs; i += NTA) sm[S.buf + phys(S, (S.Ha - S.Hs) + i)] = h[i];
-    }
+#pragma unroll
+    for (int e = 0; e < NHL; e++) if (hdst[e] >= 0) sm[hdst[e]] = hv[e];
     {
         double *cs = reinterpret_cast<double *>(sm + P.coef_sm);
         for (int i = tid; i < P.ncoef; i += NTA) cs[i] = P.coef[i];
@@ -662,8 +687,6 @@ __global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_con
         if (tid < NT) u = cmul_rn(P.vstart[c], nco_pow(nc, P.n_base + (unsigned long long)tid));
     }
     __syncthreads();
-    const int n_full = P.n_in / T0;
-    const int rem = P.n_in - n_full * T0;
     const FStage &ST = P.st[TS];
     const int tws = P.tw_stride;
     cd *gout = P.out + (size_t)c * P.out_stride;
@@ -687,7 +710,7 @@ __global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_con
         // ================= tail warp: stages TS .. NS-1, one chunk behind the main warps
         const int t = tid - NT;
         load_taps(t);
-        constexpr int NSLT = 256 / NTT;         // in-place history slides of stages TS+1 .. (at most 256 elements)
+        constexpr int NSLT = 384 / NTT;         // in-place history slides of stages TS+1 .. (at most 384 elements)
         int ts_src[NSLT], ts_dst[NSLT];
 #pragma unroll
         for (int e = 0; e < NSLT; e++) slide_entry(P, TS + 1, P.ns, t + e * NTT, ts_src[e], ts_dst[e]);
@@ -696,9 +719,9 @@ __global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_con
             const int p = ch & 1;
             bar_sync(2 + p, NTA);
             out_pos += cascade_x<NTT, 2, true, TS, NS, 0, 0, PLAN...>(sm, P, 0, gout + out_pos, ft, t, p * tws, 0);
-            const cd *hs = sm + ST.buf + p * tws + ST.n_full;
+            const cd *hs = sm + ST.buf + p * tws;
             cd *hd = sm + ST.buf + (p ^ 1) * tws;
-            for (int i = t; i < ST.Ha; i += NTT) hd[i] = hs[i];
+            for (int i = t; i < ST.Ha; i += NTT) hd[phys(ST, i)] = hs[phys(ST, ST.n_full + i)];
             cd kd[NSLT];
 #pragma unroll
             for (int e = 0; e < NSLT; e++) if (ts_src[e] >= 0) kd[e] = sm[ts_src[e]];
@@ -715,16 +738,10 @@ __global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_con
 #pragma unroll
         for (int e = 0; e < NSL; e++) slide_entry(P, 0, TS, tid + e * NT, sl_src[e], sl_dst[e]);
         if (P.tune) pstep = s_pstep;
-        const cd *gin = P.in + (size_t)c * P.in_stride;
         const FStage &S0 = P.st[0];
         cd *pb0 = sm + S0.buf + phys(S0, S0.Ha + tid);
         constexpr int STEP_PAD = NT + NT / (2 * R0);
         const bool tune = P.tune != 0;
-        cd nx[NLD];
-        if (n_full > 0) {
-#pragma unroll
-            for (int k = 0; k < NLD; k++) nx[k] = gin[k * NT + tid];
-        }
         for (int ch = 0; ch < n_full; ch++) {
             const int p = ch & 1;
             if (tune) {
@@ -760,7 +777,7 @@ __global__ void __launch_bounds__(192, 2) fused_decim_tw_kernel(const __grid_con
     if (tid >= NT) return;
     // the stage-TS history sits at the front of half (n_full & 1): bring it to half 0, where the code below expects it
     if (n_full & 1) {
-        for (int i = tid; i < ST.Ha; i += NT) sm[ST.buf + i] = sm[ST.buf + tws + i];
+        for (int i = tid; i < ST.Ha; i += NT) sm[ST.buf + phys(ST, i)] = sm[ST.buf + tws + phys(ST, i)];
     }
     group_sync<1>();
     // ---- ragged tail (at most one partial chunk): every stage on the main warps, generic indexing
@@ -857,8 +874,9 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     int codes[MAXST];
     size_t sh = 0;
     // component-split half bands (hb_stage_split): plan kernels at the full chunk only
-    constexpr int TW_TS = 4;                // tail-warp kernel: stages from this index on belong to the fifth warp
-    bool use_tw = fused_tailwarp && fused_plans && NT == 128 && T0 == 2048 && split == ns && ns > TW_TS && !d_trace;
+    // tail-warp kernel: stages from index tw_ts on belong to the two tail warps (option value 2, 3 or 4; 1 = default)
+    const int tw_ts = fused_tailwarp >= 2 && fused_tailwarp <= 4 ? fused_tailwarp : 3;
+    bool use_tw = fused_tailwarp && fused_plans && NT == 128 && T0 == 2048 && split == ns && ns > 4 && !d_trace;
     bool use_split = !use_tw && fused_split && fused_plans && NT == 128 && T0 == 2048 && split == ns;
     // stage descriptors for a given multi-rate split (no filter state is touched here)
     auto build = [&](int split, int deepk) -> int {
@@ -876,7 +894,8 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
             S.type = 0; S.D = 2; S.nTaps = 43; S.Ha = 48;
             S.u0 = 1 - f->phase;
             const int nout = chunk_in / 2;
-            S.R = nout > 4 * NT ? 8 : (nout > 2 * NT ? 4 : 2);
+            const int nts = (use_tw && s >= tw_ts) ? 64 : NT;          // the tail warps are 64 threads
+            S.R = nout > 4 * nts ? 8 : (nout > 2 * nts ? 4 : 2);
             if (fused_min_r > S.R) S.R = fused_min_r;
             if (use_split) { S.split = 1; S.R *= 2; }
             S.pu = 2 * S.R;
@@ -896,7 +915,8 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
             S.R = FIR_R; S.pu = 0; S.magic = 0; S.org = 0;
             {   // plan kernels: outputs per thread so that one round of NT threads covers the chunk
                 const int no = chunk_in / S.D;
-                int r = (no * 8 + NT - 1) / NT;
+                const int nts = (use_tw && s >= tw_ts) ? 64 : NT;
+                int r = (no * 8 + nts - 1) / nts;
                 S.Rplan = r >= 4 ? 4 : (r >= 2 ? 2 : 1);
             }
             S.coef = coff;
@@ -907,7 +927,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         }
         S.buf = off;
         off += S.buf_len;
-        if (use_tw && s == TW_TS) { P.tw_stride = S.buf_len; off += S.buf_len; }
+        if (use_tw && s == tw_ts) { P.tw_stride = S.buf_len; off += S.buf_len; }
         S.n_full = chunk_in;
         S.n_out_full = chunk_in / S.D;
         chunk_in = chunk_in / S.D;
@@ -955,15 +975,16 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         if (!found) use_split = false;
     }
     if (use_tw) {
-        static const int plans[4][MAXST] = {{82, 42, 22, 22, 142}, {82, 42, 22, 22, 142, 22, 112},
-                                            {82, 42, 22, 22, 142, 22, 22, 112}, {82, 42, 22, 22, 142, 122}};
+        // the half bands in front, sized for 128 main or 64 tail threads
+        const int head[3][4] = {{82, 42, 42, 22}, {82, 42, 22, 22}, {82, 42, 22, 22}};        // tw_ts = 2, 3, 4
+        static const int tails[4][MAXST] = {{142}, {142, 22, 122}, {142, 22, 22, 112}, {142, 142}};
         static const int lens[4] = {5, 7, 8, 6};
         rcb = build(ns, 1);
         bool found = false;
         for (int p = 0; p < 4 && rcb == QC_OK; p++) {
             if (lens[p] != ns) continue;
             bool ok = true;
-            for (int i = 0; i < ns; i++) ok = ok && codes[i] == plans[p][i];
+            for (int i = 0; i < ns; i++) ok = ok && codes[i] == (i < 4 ? head[tw_ts - 2][i] : tails[p][i - 4]);
             found = found || ok;
         }
         for (int s = 0; s < ns; s++) if (P.st[s].type == 1 && P.st[s].Kpad != 8 * FIR_KB) found = false;
@@ -1012,10 +1033,15 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         if (!optin[dev_]) { QC_CUDA(cudaFuncSetAttribute(fused_decim_tw_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin[dev_] = true; } \
         fused_decim_tw_kernel<__VA_ARGS__><<<C, 192, sh, strm>>>(P); } while (0)
     // tail-warp kernels (default): the stages behind the fourth half band run on a fifth warp, one chunk behind
-    if (use_tw && ns == 5) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142);
-    else if (use_tw && ns == 7) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142, 22, 112);
-    else if (use_tw && ns == 8) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142, 22, 22, 112);
-    else if (use_tw && ns == 6) QC_LAUNCH_TW(4, 82, 42, 22, 22, 142, 122);
+    if (use_tw) {
+#define QC_TW_PLANS(TS, H2) \
+        if (ns == 5) QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142); \
+        else if (ns == 7) QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142, 22, 122); \
+        else if (ns == 8) QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142, 22, 22, 112); \
+        else QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142, 142)
+        if (tw_ts == 2) { QC_TW_PLANS(2, 42); } else if (tw_ts == 3) { QC_TW_PLANS(3, 22); } else { QC_TW_PLANS(4, 22); }
+#undef QC_TW_PLANS
+    }
     // single-rate plans (every stage every chunk)
     else if (is_plan(5, {82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 5, 82, 42, 22, 22, 142);                        // 1.536 MS/s -> 48 k
     else if (is_plan(7, {82, 42, 22, 22, 142, 22, 112})) QC_LAUNCH(128, 8, 2, 7, 82, 42, 22, 22, 142, 22, 112);   // ... -> 12 k (SSB)
