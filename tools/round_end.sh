@@ -17,3 +17,5 @@ python bench.py --nco closed --no-cpu-baseline > gpurun_out/bench_r1_n1_nco_clos
 ncu --section SpeedOfLight --section WarpStateStats --section MemoryWorkloadAnalysis --section Occupancy --section SchedulerStats --section LaunchStats --clock-control none -k regex:pfb_f -c 2 -f -o gpurun_out/prof_pfb_r1 python tools/pfb_once.py 65536 0 > /dev/null 2>&1
 ncu --section SpeedOfLight --section WarpStateStats --section MemoryWorkloadAnalysis --section Occupancy --section SchedulerStats --section LaunchStats --clock-control none -k regex:pan_accumulate -c 1 -f -o gpurun_out/prof_pan_r1 python bench.py --workload panadapter --channels 16 --block 1048576 --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
+ncu --set full --import-source on --clock-control none -k regex:fused_decim -s 2 -c 1 -f -o gpurun_out/prof_fused_r1 python bench.py --channels 1184 --steps 1 --warmup 1 --no-cpu-baseline --e2e-steps 0 > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep
