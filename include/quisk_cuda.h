@@ -314,6 +314,16 @@ void quisk_cuda_fracdecim_destroy(qcFracDecim *f);
 int quisk_cuda_fracdecim_run(qcFracDecim *f, const void *d_in, long in_stride, int count, double fdecim,
                              void *d_out, long out_stride, int *n_out, void *stream);
 
+/* ---- 3d. NoiseBlanker (quisk.c:679-784), batched: the optional impulse blanker Quisk runs on the raw samples in front
+ * of the tuning stage (quisk.c:2448-2449).  In place on d_samples [n_channels][stride] quisk_cd;
+ * `level` = quisk_noise_blanker (1, 2, 3 -> threshold 6, 4, 2.5 times the mean magnitude of the last 1.5 ms; <= 0: off,
+ * the call does nothing, as in the reference).  Output is the input delayed by 3 * (int)(sample_rate * 500e-6 + 0.5)
+ * samples with the blanking applied; state carries over between calls of any length. ---- */
+typedef struct qcNoiseBlanker qcNoiseBlanker;
+qcNoiseBlanker *quisk_cuda_nb_create(int n_channels, int sample_rate);
+void quisk_cuda_nb_destroy(qcNoiseBlanker *b);
+int quisk_cuda_nb_run(qcNoiseBlanker *b, void *d_samples, long stride, int count, int level, void *stream);
+
 /* ---- 3e. wire-format ingest: received bytes -> complex double on the device ----
  * quisk_cuda_unpack_iq: add_rx_samples (quisk.c:2922-2953).  d_bytes [n_channels][byte_stride]: packed (I, Q)
  * pairs, `bytes` = 1..4 per component, little endian (big_endian = 0) or big endian; each component is

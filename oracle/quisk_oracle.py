@@ -589,6 +589,59 @@ def bandscope(blocks: np.ndarray, graph_width: int, clock: int, zoom: float, del
 
 
 # --------------------------------------------------------------------------
+# NoiseBlanker (quisk.c:679-784): optional stage on the raw samples in front of the tuning stage
+# --------------------------------------------------------------------------
+
+class NoiseBlanker:
+    """The pulse decision `|x| > mean(|x| over the last 3 windows) * limit` depends only on the magnitudes, so it is
+    restated here as a pre-pass (magnitudes vectorised, the running sum walked in the reference's order because each
+    `-=` / `+=` is separately rounded, quisk.c:732-735); the blanking state machine (quisk.c:740-765) then edits a
+    delay line of `3 * hwindow` samples: ramp down the `hwindow` samples in front of a pulse, zero while pulses last,
+    ramp up over the next `hwindow`.  Output = the delay line's oldest sample."""
+
+    def __init__(self, sample_rate: int, level: int):
+        self.hw = int(sample_rate * 500.0e-6 + 0.5)             # QUISK_NB_HWINDOW_SECS, quisk.c:679,704
+        self.size = 3 * self.hw
+        self.limit = {2: 4.0, 3: 2.5}.get(level, 6.0)           # quisk.c:716-728
+        self.line = np.zeros(self.size, dtype=np.complex128)
+        self.mags = np.zeros(self.size)
+        self.total = 0.0
+        self.pos = 0
+        self.blanking = False
+        self.ramp = 0
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, dtype=np.complex128)
+        mag = np.hypot(x.real, x.imag)
+        pulse = np.zeros(len(x), dtype=bool)
+        p = self.pos
+        for i, m in enumerate(mag):
+            self.total -= self.mags[p]
+            self.mags[p] = m
+            self.total += m
+            pulse[i] = not (m <= self.total / self.size * self.limit)
+            p = (p + 1) % self.size
+        y = np.empty_like(x)
+        for i in range(len(x)):
+            p = self.pos
+            y[i] = self.line[p]
+            self.line[p] = x[i]
+            if self.blanking:
+                self.line[p] = 0.0
+                if not pulse[i]:
+                    self.blanking, self.ramp = False, 1
+            elif pulse[i]:
+                self.blanking = True
+                back = (p - np.arange(self.hw)) % self.size
+                self.line[back] *= np.arange(self.hw) / float(self.hw)
+            elif self.ramp:
+                self.line[p] *= float(self.ramp) / self.hw
+                self.ramp = self.ramp + 1 if self.ramp + 1 < self.hw else 0
+            self.pos = (p + 1) % self.size
+        return y
+
+
+# --------------------------------------------------------------------------
 # Synthetic input (SURVEY.md section 8d)
 # --------------------------------------------------------------------------
 

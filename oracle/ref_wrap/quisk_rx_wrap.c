@@ -14,6 +14,7 @@
  * 622-665 cFracDecim, 1182-1256 dRxFilterOut/cRxFilterOut,
  * 1633-1671 PlanDecimation, 1673-1846 quisk_process_decimate,
  * 1848-2160 quisk_process_demodulate, 2162-2287 process_agc,
+ * 679-784 NoiseBlanker,
  * 2922-2953 the two sample-unpack branches of add_rx_samples,
  * 3746-3763 the 24-bit record loop of read_rx_udp10 (Hermes protocol 1).
  */
@@ -115,6 +116,13 @@ void *ref_agc_new(double max_out, int sample_rate)
 void ref_agc_set(double release_gain, double release_time) { agcReleaseGain = release_gain; agc_release_time = release_time; }
 void ref_agc_run(void *s, complex double *cs, int n, int is_cpx) { process_agc((struct AgcState *)s, cs, n, is_cpx); }
 double ref_agc_gain(void *s) { return ((struct AgcState *)s)->gain; }
+
+
+/* NoiseBlanker (quisk.c:679-784): called on the raw samples in front of the tuning stage (quisk.c:2448-2449) when
+ * quisk_noise_blanker > 0.  Its state is function-static: one private copy of this library per stream. */
+int quisk_noise_blanker;
+#include "quisk_nb.inc"
+void ref_noise_blanker(complex double *cs, int n, int level) { quisk_noise_blanker = level; NoiseBlanker(cs, n); }
 
 
 /* ---- wire-format ingest: the loops that turn received bytes into complex double ----

@@ -2,6 +2,7 @@
 //   process_agc  (quisk.c:2162-2287)  Quisk's own look-ahead AGC at playback rate (15 ms FIFO)
 //   cFracDecim   (quisk.c:622-665)    fractional decimation by 4-point Lagrange interpolation
 //   get_bandscope (quisk.c:4957-5011) + copy2pixels (quisk.c:4932-4955): real-input spectrum display
+//   NoiseBlanker (quisk.c:679-784)    impulse blanker on the raw samples in front of the tuning stage (optional)
 // process_agc and cFracDecim are scalar recurrences: one CTA per channel, block staged in shared
 // memory, lane 0 walks it (compiled with --fmad=false so the state follows the reference bit for bit).
 #include "fft_device.cuh"
@@ -177,9 +178,111 @@ __global__ void bandscope_graph_kernel(const double *avg, int L, int graph_width
     graph[(size_t)stream * graph_width + i] = sample <= 1E-10 ? -200.0 : 20.0 * log10(sample);
 }
 
+// ---- NoiseBlanker (quisk.c:679-784).  Per channel: a delay line of save_size = 3 * hwindow samples whose entries are
+// edited while they wait (ramp down in front of a pulse, zero while pulses last, ramp up afterwards), and a running sum
+// of the last save_size magnitudes that decides what a pulse is.  The decision depends on the magnitudes only, never on
+// the blanking state, so a chunk is processed in three phases: (1) all lanes: |x| ; lane 0: the running sum in the
+// reference's order (two dependent, separately rounded additions per sample, quisk.c:733-735); (2) all lanes: the
+// threshold test with the reference's division (quisk.c:736); (3) if the chunk holds no pulse and no blanking or ramp is
+// in progress the delay line is a plain ring and all lanes move it, otherwise lane 0 walks the state machine
+// (quisk.c:740-765) sample by sample.  Chunks are at most save_size long, so that a ring slot is touched once per chunk.
+// state per channel: 0 index 1 win_index 2 state 3 save_sum
+struct NbPar { int save_size, hwindow, chunk; double limit; };
+
+__global__ void __launch_bounds__(128) nb_kernel(cd *samples, long stride, int n, double *state, cd *csaved, double *dsaved, NbPar p)
+{
+    extern __shared__ double sm_raw[];
+    cd *sc = reinterpret_cast<cd *>(sm_raw);            // [save_size] delay line
+    cd *sx = sc + p.save_size;                          // [chunk] samples in, delayed samples out
+    double *sd = reinterpret_cast<double *>(sx + p.chunk);      // [save_size] magnitudes
+    double *smag = sd + p.save_size;                    // [chunk] |x|, then the running sum after the sample
+    __shared__ int s_index, s_win, s_state;
+    const int c = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    cd *g = samples + (size_t)c * stride;
+    cd *gc = csaved + (size_t)c * p.save_size;
+    double *gd = dsaved + (size_t)c * p.save_size;
+    double *st = state + (size_t)c * 4;
+    for (int i = tid; i < p.save_size; i += NT) { sc[i] = gc[i]; sd[i] = gd[i]; }
+    double save_sum = st[3];                            // lane 0's copy is the live one
+    if (tid == 0) { s_index = (int)st[0]; s_win = (int)st[1]; s_state = (int)st[2]; }
+    __syncthreads();
+    const double dsize = (double)p.save_size;
+    for (int base = 0; base < n; base += p.chunk) {
+        const int m = min(p.chunk, n - base);
+        for (int i = tid; i < m; i += NT) { const cd x = g[base + i]; sx[i] = x; smag[i] = hypot(x.x, x.y); }
+        __syncthreads();
+        const int index0 = s_index;
+        if (tid == 0) {
+            int k = index0;
+            for (int i = 0; i < m; i++) {
+                const double mag = smag[i];
+                save_sum -= sd[k];
+                sd[k] = mag;
+                save_sum += mag;
+                smag[i] = save_sum;
+                if (++k >= p.save_size) k = 0;
+            }
+        }
+        __syncthreads();
+        int any = 0;
+        unsigned char *flag = reinterpret_cast<unsigned char *>(smag + p.chunk);
+        for (int i = tid; i < m; i += NT) {
+            int k = index0 + i; if (k >= p.save_size) k -= p.save_size;
+            const int is_pulse = sd[k] <= smag[i] / dsize * p.limit ? 0 : 1;
+            flag[i] = (unsigned char)is_pulse;
+            any |= is_pulse;
+        }
+        any = __syncthreads_or(any | s_state | s_win);
+        if (!any) {
+            for (int i = tid; i < m; i += NT) {
+                int k = index0 + i; if (k >= p.save_size) k -= p.save_size;
+                const cd x = sx[i];
+                sx[i] = sc[k];
+                sc[k] = x;
+            }
+            if (tid == 0) { int k = index0 + m; if (k >= p.save_size) k -= p.save_size; s_index = k; }
+        } else if (tid == 0) {
+            int index = index0, win_index = s_win, state_ = s_state;
+            const double hw = (double)p.hwindow;
+            for (int i = 0; i < m; i++) {
+                const cd samp = sx[i];
+                sx[i] = sc[index];
+                sc[index] = samp;
+                const int is_pulse = flag[i];
+                if (state_ == 0) {
+                    if (is_pulse) {
+                        state_ = 1;
+                        int k = index;
+                        for (int j = 0; j < p.hwindow; j++) {
+                            const double w = (double)j / hw;
+                            sc[k].x *= w; sc[k].y *= w;
+                            if (--k < 0) k = p.save_size - 1;
+                        }
+                    } else if (win_index) {
+                        const double w = (double)win_index / hw;
+                        sc[index].x *= w; sc[index].y *= w;
+                        if (++win_index >= p.hwindow) win_index = 0;
+                    }
+                } else {
+                    sc[index] = make_double2(0.0, 0.0);
+                    if (!is_pulse) { state_ = 0; win_index = 1; }
+                }
+                if (++index >= p.save_size) index = 0;
+            }
+            s_index = index; s_win = win_index; s_state = state_;
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += NT) g[base + i] = sx[i];
+        __syncthreads();
+    }
+    for (int i = tid; i < p.save_size; i += NT) { gc[i] = sc[i]; gd[i] = sd[i]; }
+    if (tid == 0) { st[0] = s_index; st[1] = s_win; st[2] = s_state; st[3] = save_sum; }
+}
+
 struct QAgc { int C, rate, buf_size; AgcPar p; double *d_state; cd *d_fifo; };
 struct QFrac { int C; double dindex; double *d_state; };
 struct QBand { int S, n, L, count; const cd *tw; double *d_window, *d_avg, *d_max; };
+struct QNb { int C, rate; NbPar p; size_t smem; double *d_state, *d_mag; cd *d_line; };
 
 }  // namespace qc
 
@@ -187,6 +290,7 @@ using namespace qc;
 struct qcAgc { QAgc a; };
 struct qcFracDecim { QFrac f; };
 struct qcBandscope { QBand b; };
+struct qcNoiseBlanker { QNb b; };
 
 extern "C" {
 
@@ -256,6 +360,51 @@ int quisk_cuda_fracdecim_run(qcFracDecim *h, const void *d_in, long in_stride, i
     if (sh > 200 * 1024) { set_error("fracdecim_run: block too large"); return QC_EINVAL; }
     if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(fracdecim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     fracdecim_kernel<<<h->f.C, 64, sh, (cudaStream_t)stream>>>((const cd *)d_in, in_stride, (cd *)d_out, out_stride, count, h->f.C, h->f.d_state, fdecim);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+qcNoiseBlanker *quisk_cuda_nb_create(int n_channels, int sample_rate)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    qcNoiseBlanker *h = new qcNoiseBlanker();
+    QNb &b = h->b;
+    b.C = n_channels; b.rate = sample_rate;
+    b.p.hwindow = (int)(sample_rate * 500.E-6 + 0.5);           // QUISK_NB_HWINDOW_SECS, quisk.c:679,704
+    b.p.save_size = b.p.hwindow * 3;                            // quisk.c:705
+    b.p.chunk = b.p.save_size < 1024 ? b.p.save_size : 1024;
+    b.p.limit = 6.0;
+    // delay line + magnitudes + one chunk of samples, sums and pulse flags
+    b.smem = (size_t)b.p.save_size * (sizeof(cd) + sizeof(double)) + (size_t)b.p.chunk * (sizeof(cd) + sizeof(double) + 1) + 16;
+    if (n_channels <= 0 || b.p.hwindow <= 0 || b.smem > 220 * 1024) {
+        set_error("nb_create: need n_channels > 0 and a sample rate between 1 kS/s and 6 MS/s (the delay line of 1.5 ms lives in shared memory)");
+        delete h; return nullptr;
+    }
+    if (cudaMalloc((void **)&b.d_state, (size_t)n_channels * 4 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&b.d_mag, (size_t)n_channels * b.p.save_size * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&b.d_line, (size_t)n_channels * b.p.save_size * sizeof(cd)) != cudaSuccess) {
+        set_error("nb_create: allocation failure"); delete h; return nullptr;
+    }
+    cudaMemset(b.d_state, 0, (size_t)n_channels * 4 * sizeof(double));          // state = index = win_index = 0, save_sum = 0.0 (quisk.c:700-703)
+    cudaMemset(b.d_mag, 0, (size_t)n_channels * b.p.save_size * sizeof(double));
+    cudaMemset(b.d_line, 0, (size_t)n_channels * b.p.save_size * sizeof(cd));
+    return h;
+}
+
+void quisk_cuda_nb_destroy(qcNoiseBlanker *h) { if (h) { cudaFree(h->b.d_state); cudaFree(h->b.d_mag); cudaFree(h->b.d_line); delete h; } }
+
+int quisk_cuda_nb_run(qcNoiseBlanker *h, void *d_samples, long stride, int count, int level, void *stream)
+{
+    if (!h) return QC_EINVAL;
+    if (level <= 0 || count <= 0) return QC_OK;                 // quisk.c:695: off, nothing moves through the delay line
+    QNb &b = h->b;
+    NbPar p = b.p;
+    p.limit = level == 2 ? 4.0 : (level == 3 ? 2.5 : 6.0);      // quisk.c:716-728
+    static bool optin[64] = {};
+    int dev = 0; cudaGetDevice(&dev); dev &= 63;
+    if (!optin[dev]) { QC_CUDA(cudaFuncSetAttribute(nb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); optin[dev] = true; }
+    nb_kernel<<<b.C, 128, b.smem, (cudaStream_t)stream>>>((cd *)d_samples, stride, count, b.d_state, b.d_line, b.d_mag, p);
     count_launch();
     QC_CUDA_LAUNCH();
     return QC_OK;

@@ -98,6 +98,9 @@ def load() -> C.CDLL:
     lib.quisk_cuda_fracdecim_create.argtypes = [C.c_int]; lib.quisk_cuda_fracdecim_create.restype = vp
     lib.quisk_cuda_fracdecim_destroy.argtypes = [vp]; lib.quisk_cuda_fracdecim_destroy.restype = None
     lib.quisk_cuda_fracdecim_run.argtypes = [vp, vp, C.c_long, C.c_int, C.c_double, vp, C.c_long, c_int_p, vp]
+    lib.quisk_cuda_nb_create.argtypes = [C.c_int, C.c_int]; lib.quisk_cuda_nb_create.restype = vp
+    lib.quisk_cuda_nb_destroy.argtypes = [vp]; lib.quisk_cuda_nb_destroy.restype = None
+    lib.quisk_cuda_nb_run.argtypes = [vp, vp, C.c_long, C.c_int, C.c_int, vp]
     lib.quisk_cuda_unpack_iq.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp]
     lib.quisk_cuda_hermes_samples_per_packet.argtypes = [C.c_int]
     lib.quisk_cuda_unpack_hermes.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, c_int_p, vp]

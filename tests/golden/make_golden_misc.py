@@ -1,4 +1,4 @@
-"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287), cFracDecim (quisk.c:622-665) and
+"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287), cFracDecim (quisk.c:622-665), NoiseBlanker (quisk.c:679-784) and
 the wire-format unpack loops (quisk.c:2922-2953, 3746-3763) from the compiled reference (oracle/_ref/libquisk_rx_ref.so).  Writes tests/golden/misc_kat.npz."""
 import ctypes as C
 import os
@@ -20,6 +20,22 @@ def agc_input(n, seed):
     x = O.synth_iq(n, seed, 1.0) / 64.0
     x[n // 4:n // 4 + 300] *= 40.0
     x[n // 2:n // 2 + 50] *= 200.0
+    return x
+
+
+NB_SPLITS = [1000, 1, 2, 7, 255, 4093, 2642]
+NB_CASES = [(48000, 1), (48000, 3), (192000, 2), (1536000, 1)]      # (sample rate, quisk_noise_blanker level)
+
+
+def nb_input(n, seed):
+    """IQ with impulse noise: single-sample spikes, a 12-sample burst, two pulses closer together than the blanking
+    window, one pulse across a block boundary of NB_SPLITS, and a stretch of raised level (no pulse, the mean follows)."""
+    x = O.synth_iq(n, seed, 1.0)
+    rng = np.random.default_rng(seed + 1000)
+    for p in (300, 999, 1000, 1003, 1600, 1640, 2900, 5357, 5358, 7000):
+        x[p] *= 60.0
+    x[2200:2212] *= 45.0 * (1.0 + rng.random(12))
+    x[4000:4400] *= 3.0
     return x
 
 
@@ -57,6 +73,18 @@ def main():
             ys.append(blk[:k].copy()); counts.append(k)
         out["fracdecim_%g/y" % fdecim] = np.concatenate(ys)
         out["fracdecim_%g/counts" % fdecim] = np.array(counts)
+    for rate, level in NB_CASES:
+        lib = R.load("libquisk_rx_ref.so", private_copy=True)
+        lib.ref_set_sample_rate.argtypes = [C.c_int]
+        lib.ref_noise_blanker.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.ref_set_sample_rate(rate)
+        x = nb_input(sum(NB_SPLITS), 90)
+        ys, pos = [], 0
+        for n in NB_SPLITS:
+            blk = np.ascontiguousarray(x[pos:pos + n]); pos += n
+            lib.ref_noise_blanker(blk.ctypes.data, n, level)
+            ys.append(blk)
+        out["nb_%d_%d/y" % (rate, level)] = np.concatenate(ys)
     # wire-format ingest: the reference's own unpack loops on seeded random bytes
     lib = R.load("libquisk_rx_ref.so", private_copy=True)
     lib.ref_add_rx_samples.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]

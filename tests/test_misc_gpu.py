@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import quisk_oracle as O
-from tests.golden.make_golden_misc import AGC_SPLITS, agc_input
+from tests.golden.make_golden_misc import AGC_SPLITS, NB_CASES, NB_SPLITS, agc_input, nb_input
 from tests.util import golden
 
 pytestmark = pytest.mark.gpu
@@ -65,6 +65,51 @@ def test_cfracdecim(fdecim, torch, lib):
     for c in range(NCH):
         assert O.rel_rms(y[c], kat["fracdecim_%g/y" % fdecim]) < 1e-14
     lib.quisk_cuda_fracdecim_destroy(f)
+
+
+@pytest.mark.parametrize("rate,level", NB_CASES)
+def test_noise_blanker(rate, level, torch, lib):
+    """NoiseBlanker (quisk.c:679-784) against the compiled reference's fixture: bit-exact, ragged blocks, the state
+    (delay line, running magnitude sum, blanking / ramp phase) carried from call to call; level 0 leaves everything alone."""
+    kat = golden("misc_kat.npz")
+    x = nb_input(sum(NB_SPLITS), 90)
+    d = torch.from_numpy(np.stack([x, x * 0.5, x])).cuda()
+    h = lib.quisk_cuda_nb_create(NCH, rate)
+    assert h
+    before = d.clone()
+    assert lib.quisk_cuda_nb_run(h, d.data_ptr(), d.stride(0), 100, 0, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(d, before)
+    pos = 0
+    for n in NB_SPLITS:
+        blk = d[:, pos:pos + n]
+        assert lib.quisk_cuda_nb_run(h, blk.data_ptr(), d.stride(0), n, level, None) == 0
+        pos += n
+    torch.cuda.synchronize()
+    y = d.cpu().numpy()
+    ref = kat["nb_%d_%d/y" % (rate, level)]
+    assert np.array_equal(y[0], ref) and np.array_equal(y[2], ref)
+    assert np.array_equal(y[1], ref * 0.5)          # scaling by a power of two changes no decision
+    lib.quisk_cuda_nb_destroy(h)
+
+
+def test_noise_blanker_long_blocks(torch, lib):
+    """One call of 70 000 samples equals the oracle fed the same stream in blocks (chunking inside the kernel, quiet
+    fast path and state-machine path both taken); channels are independent."""
+    n = 70000
+    xs = []
+    for c in range(NCH):
+        x = O.synth_iq(n, 95 + c, 1.0)
+        x[5000 + 777 * c] *= 80.0; x[30000:30005] *= 50.0; x[69990] *= 90.0
+        xs.append(x)
+    d = torch.from_numpy(np.stack(xs)).cuda()
+    h = lib.quisk_cuda_nb_create(NCH, 192000)
+    assert lib.quisk_cuda_nb_run(h, d.data_ptr(), d.stride(0), n, 1, None) == 0
+    torch.cuda.synchronize()
+    y = d.cpu().numpy()
+    for c in range(NCH):
+        assert np.array_equal(y[c], O.NoiseBlanker(192000, 1)(xs[c]))
+    lib.quisk_cuda_nb_destroy(h)
 
 
 def test_bandscope(torch, lib):
