@@ -7,11 +7,11 @@ import numpy as np
 import torch
 
 from quisk_b200 import lib as L
-from quisk_b200.synth import synth_iq
 
 lib = L.require_device()
 C_, n, rate = int(sys.argv[1]) if len(sys.argv) > 1 else 1024, 32768, 1536000
-x = synth_iq(n, 7, 1.0)
+rng = np.random.default_rng(7)
+x = (2.0 ** 20) * (rng.standard_normal(n) + 1j * rng.standard_normal(n)) + (2.0 ** 24) * np.exp(2j * np.pi * 0.07 * np.arange(n))
 for name, pulses in (("quiet", 0), ("one pulse per 4096 samples", 8)):
     xx = x.copy()
     for k in range(pulses):
