@@ -324,6 +324,21 @@ qcNoiseBlanker *quisk_cuda_nb_create(int n_channels, int sample_rate);
 void quisk_cuda_nb_destroy(qcNoiseBlanker *b);
 int quisk_cuda_nb_run(qcNoiseBlanker *b, void *d_samples, long stride, int count, int level, void *stream);
 
+/* ---- 3d'. ssb_squelch + d_delay (quisk.c:1056-1180), batched: the optional spectral-flatness squelch of the SSB branch of
+ * quisk_process_demodulate (quisk.c:1925-1928, 1948-1951, 1970-1973).  samp_rate = quisk_filter_srate,
+ * filter_bandwidth = filter_bandwidth[0], level = ssb_squelch_level.  In place on d_audio [n_channels][stride] double at
+ * the filter rate: the audio comes back delayed by 512 samples; per channel sq_open (the one-second timer, in samples)
+ * and squelch_active (what quisk_process_samples mutes on, quisk.c:2552-2623) are kept on the device --
+ * quisk_cuda_ssb_squelch_state copies them out, quisk_cuda_ssb_squelch_state_ptr returns the device array
+ * [n_channels][2] = {sq_open, squelch_active}.  As in the reference the first call only sets up (its samples do not
+ * enter the analysis frame) and the timer is decremented once per call, so `count` is limited to 8192. ---- */
+typedef struct qcSsbSquelch qcSsbSquelch;
+qcSsbSquelch *quisk_cuda_ssb_squelch_create(int n_channels, int samp_rate, int filter_bandwidth);
+void quisk_cuda_ssb_squelch_destroy(qcSsbSquelch *s);
+int quisk_cuda_ssb_squelch_run(qcSsbSquelch *s, double *d_audio, long stride, int count, int level, void *stream);
+int quisk_cuda_ssb_squelch_state(qcSsbSquelch *s, int *sq_open, int *squelch_active, void *stream);
+const int *quisk_cuda_ssb_squelch_state_ptr(qcSsbSquelch *s);
+
 /* ---- 3e. wire-format ingest: received bytes -> complex double on the device ----
  * quisk_cuda_unpack_iq: add_rx_samples (quisk.c:2922-2953).  d_bytes [n_channels][byte_stride]: packed (I, Q)
  * pairs, `bytes` = 1..4 per component, little endian (big_endian = 0) or big endian; each component is

@@ -35,11 +35,12 @@ gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" "$REF/filter.c" -o "$OUT/libquisk_f
 { sed -n '46,53p' "$REF/quisk.c"; sed -n '68,81p' "$REF/quisk.c"; } > "$TMP/quisk_rx_consts.inc"
 { sed -n '622,665p' "$REF/quisk.c"; sed -n '1182,1256p' "$REF/quisk.c"; sed -n '1633,1671p' "$REF/quisk.c";
   sed -n '1673,1846p' "$REF/quisk.c"; sed -n '1848,2160p' "$REF/quisk.c"; sed -n '2162,2287p' "$REF/quisk.c"; } > "$TMP/quisk_rx_funcs.inc"
+{ sed -n '1056,1084p' "$REF/quisk.c"; sed -n '1086,1180p' "$REF/quisk.c"; } > "$TMP/quisk_squelch.inc"     # d_delay, ssb_squelch
 sed -n '679,784p' "$REF/quisk.c" > "$TMP/quisk_nb.inc"                    # NoiseBlanker (optional stage in front of the path)
 sed -n '2922,2953p' "$REF/quisk.c" > "$TMP/quisk_unpack_py.inc"          # add_rx_samples: the two unpack branches
 sed -n '3746,3763p' "$REF/quisk.c" > "$TMP/quisk_unpack_hermes.inc"      # read_rx_udp10: 24-bit record loop of one 512-byte frame
-gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_rx_wrap.c" "$REF/filter.c" \
-    -o "$OUT/libquisk_rx_ref.so" -lm
+gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" -I"$HERE/fftw_shim" "$HERE/ref_wrap/quisk_rx_wrap.c" "$REF/filter.c" \
+    "$HERE/fftw_shim/fftw_shim.c" "$HERE/fft64.c" -o "$OUT/libquisk_rx_ref.so" -lm
 
 # 2b. The same wrapper TU linked against libquisk_cuda.so INSTEAD of filter.c: the reference's own orchestrator code
 #     (quisk_process_decimate / quisk_process_demodulate, unmodified) calling the GPU filter.h drop-in.  This is the
@@ -48,8 +49,8 @@ gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_rx_w
 CUDALIB="$HERE/../quisk_b200/libquisk_cuda.so"
 if [ -f "$CUDALIB" ]; then
     printf '#include <complex.h>\n#include "filters.h"\n' > "$TMP/filters_data.c"
-    gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_rx_wrap.c" "$TMP/filters_data.c" \
-        -o "$OUT/libquisk_rx_dropin.so" -L"$HERE/../quisk_b200" -lquisk_cuda -Wl,-rpath,'$ORIGIN/../../quisk_b200' -lm
+    gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" -I"$HERE/fftw_shim" "$HERE/ref_wrap/quisk_rx_wrap.c" "$TMP/filters_data.c" \
+        "$HERE/fftw_shim/fftw_shim.c" "$HERE/fft64.c" -o "$OUT/libquisk_rx_dropin.so" -L"$HERE/../quisk_b200" -lquisk_cuda -Wl,-rpath,'$ORIGIN/../../quisk_b200' -lm
 fi
 
 # 3. WDSP against the FFTW shim

@@ -32,6 +32,7 @@ fftw_plan fftw_plan_dft_r2c_1d(int n, double *in, fftw_complex *out, unsigned fl
 fftw_plan fftw_plan_dft_c2r_1d(int n, fftw_complex *in, double *out, unsigned flags);
 void fftw_execute(const fftw_plan p);
 void fftw_execute_dft(const fftw_plan p, fftw_complex *in, fftw_complex *out);
+void fftw_execute_dft_r2c(const fftw_plan p, double *in, fftw_complex *out);
 void fftw_destroy_plan(fftw_plan p);
 void *fftw_malloc(size_t n);
 void fftw_free(void *p);

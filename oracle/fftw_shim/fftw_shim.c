@@ -77,6 +77,13 @@ void fftw_execute(const fftw_plan p)
     }
 }
 
+void fftw_execute_dft_r2c(const fftw_plan p, double *in, fftw_complex *out)
+{   /* new-array execute of an r2c plan (quisk.c:1119) */
+    struct fftw_shim_plan_s q = *p;
+    q.in = in; q.out = out;
+    fftw_execute(&q);
+}
+
 void fftw_destroy_plan(fftw_plan p)
 {
     if (!p) return;

@@ -642,6 +642,55 @@ class NoiseBlanker:
 
 
 # --------------------------------------------------------------------------
+# ssb_squelch + d_delay (quisk.c:1056-1180): optional stage on the SSB audio at the filter rate
+# --------------------------------------------------------------------------
+
+class SsbSquelch:
+    """Frames of 512 audio samples -> Hann -> real FFT -> spectral flatness of the bins in [300 Hz, 300 Hz + bw):
+    log(mean |X|^2) - mean(log |X|^2) over the bins above 1e-4 (both means divide by the bin count of the band,
+    quisk.c:1143-1147).  Above level * 0.005 the one-second timer `sq_open` is re-armed; it is decremented once per
+    call by the call's length; squelch_active = timer run out.  The first call only plans the FFT (quisk.c:1104-1112).
+    The audio is delayed by one frame."""
+    N = 512
+
+    def __init__(self, samp_rate: int, bandwidth: int, level: int):
+        self.rate, self.level = samp_rate, level
+        bw = min(bandwidth, 3000)
+        self.b1 = 300 * self.N // samp_rate
+        self.b2 = (bw + 300) * self.N // samp_rate
+        self.window = 0.50 - 0.50 * np.cos(2.0 * np.pi * np.arange(self.N) / self.N)
+        self.pending = np.zeros(0)
+        self.fifo = np.zeros(self.N)
+        self.sq_open = 0
+        self.active = 0
+        self.planned = False
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, dtype=np.float64)
+        if self.planned:
+            buf = np.concatenate([self.pending, x])
+            nfr = len(buf) // self.N
+            for f in range(nfr):
+                X = np.fft.rfft(buf[f * self.N:(f + 1) * self.N] * self.window)[self.b1:self.b2] / 32767.0
+                d = X.real * X.real + X.imag * X.imag
+                d = d[d > 1e-4]
+                arith = float(np.sum(d))
+                ratio = 1.0
+                if arith > 1e-4:
+                    nb = self.b2 - self.b1
+                    ratio = math.log(arith / nb) - float(np.sum(np.log(d))) / nb
+                if ratio > self.level * 0.005:
+                    self.sq_open = self.rate
+            self.pending = buf[nfr * self.N:]
+            self.sq_open = max(self.sq_open - len(x), 0)
+            self.active = int(self.sq_open == 0)
+        self.planned = True
+        line = np.concatenate([self.fifo, x])
+        self.fifo = line[len(x):]
+        return line[:len(x)]
+
+
+# --------------------------------------------------------------------------
 # Synthetic input (SURVEY.md section 8d)
 # --------------------------------------------------------------------------
 

@@ -14,7 +14,7 @@
  * 622-665 cFracDecim, 1182-1256 dRxFilterOut/cRxFilterOut,
  * 1633-1671 PlanDecimation, 1673-1846 quisk_process_decimate,
  * 1848-2160 quisk_process_demodulate, 2162-2287 process_agc,
- * 679-784 NoiseBlanker,
+ * 679-784 NoiseBlanker, 1056-1084 d_delay, 1086-1180 ssb_squelch,
  * 2922-2953 the two sample-unpack branches of add_rx_samples,
  * 3746-3763 the 24-bit record loop of read_rx_udp10 (Hermes protocol 1).
  */
@@ -25,6 +25,7 @@
 #include <complex.h>
 #include "quisk.h"
 #include "filter.h"
+#include <fftw3.h>                  /* oracle/fftw_shim */
 
 #define DEBUG 0
 #include "quisk_rx_consts.inc"      /* quisk.c:46-53, 68-81 */
@@ -56,11 +57,11 @@ static struct _MeasureSquelch {
     int sq_open;
 } MeasureSquelch[MAX_RX_CHANNELS];
 
-/* Optional stages, off by default in the reference (quisk_auto_notch == 0,
- * ssb_squelch_enabled == 0): the calls stay in the extracted code, they do nothing. */
+/* Optional stage, off by default in the reference (quisk_auto_notch == 0): the call stays in the extracted code, it
+ * does nothing.  ssb_squelch and d_delay are the reference's own (quisk.c:1056-1084, 1086-1180; FFTW through the shim). */
 static void dAutoNotch(double *d, int n, int f, int r) { (void)d; (void)n; (void)f; (void)r; }
-static void ssb_squelch(double *d, int n, int r, struct _MeasureSquelch *m) { (void)d; (void)n; (void)r; (void)m; }
-static void d_delay(double *d, int n, int b, int s) { (void)d; (void)n; (void)b; (void)s; }
+static int ssb_squelch_level;
+#include "quisk_squelch.inc"        /* quisk.c:1056-1084 d_delay, 1086-1180 ssb_squelch */
 
 #include "quisk_rx_funcs.inc"       /* the function ranges listed above */
 
@@ -117,6 +118,17 @@ void ref_agc_set(double release_gain, double release_time) { agcReleaseGain = re
 void ref_agc_run(void *s, complex double *cs, int n, int is_cpx) { process_agc((struct AgcState *)s, cs, n, is_cpx); }
 double ref_agc_gain(void *s) { return ((struct AgcState *)s)->gain; }
 
+
+/* ssb_squelch + d_delay as the SSB branch of quisk_process_demodulate calls them (quisk.c:1925-1928): the very first
+ * call only creates the FFT plan and returns (quisk.c:1104-1112).  Returns MS->squelch_active; *sq_open = the timer. */
+int ref_ssb_squelch(double *ds, int n, int samp_rate, int bw, int level, int bank, int *sq_open)
+{
+    filter_bandwidth[0] = bw; ssb_squelch_level = level;
+    ssb_squelch(ds, n, samp_rate, MeasureSquelch + bank);
+    d_delay(ds, n, bank, SQUELCH_FFT_SIZE);
+    if (sq_open) *sq_open = MeasureSquelch[bank].sq_open;
+    return MeasureSquelch[bank].squelch_active;
+}
 
 /* NoiseBlanker (quisk.c:679-784): called on the raw samples in front of the tuning stage (quisk.c:2448-2449) when
  * quisk_noise_blanker > 0.  Its state is function-static: one private copy of this library per stream. */

@@ -3,6 +3,7 @@
 //   cFracDecim   (quisk.c:622-665)    fractional decimation by 4-point Lagrange interpolation
 //   get_bandscope (quisk.c:4957-5011) + copy2pixels (quisk.c:4932-4955): real-input spectrum display
 //   NoiseBlanker (quisk.c:679-784)    impulse blanker on the raw samples in front of the tuning stage (optional)
+//   ssb_squelch + d_delay (quisk.c:1056-1180)  spectral-flatness squelch on the SSB audio at the filter rate (optional)
 // process_agc and cFracDecim are scalar recurrences: one CTA per channel, block staged in shared
 // memory, lane 0 walks it (compiled with --fmad=false so the state follows the reference bit for bit).
 #include "fft_device.cuh"
@@ -213,8 +214,20 @@ __global__ void __launch_bounds__(128) nb_kernel(cd *samples, long stride, int n
         __syncthreads();
         const int index0 = s_index;
         if (tid == 0) {
-            int k = index0;
-            for (int i = 0; i < m; i++) {
+            int k = index0, i = 0;
+            // eight samples at a time: all sixteen loads first (the slots are distinct: a chunk is at most one lap of the
+            // ring), then the dependent chain of sixteen additions in registers, then the stores
+            for (; i + 8 <= m; i += 8) {
+                double mg[8], od[8]; int kk[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { kk[j] = k + j >= p.save_size ? k + j - p.save_size : k + j; mg[j] = smag[i + j]; od[j] = sd[kk[j]]; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) { save_sum -= od[j]; save_sum += mg[j]; od[j] = save_sum; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) { sd[kk[j]] = mg[j]; smag[i + j] = od[j]; }
+                k = k + 8 >= p.save_size ? k + 8 - p.save_size : k + 8;
+            }
+            for (; i < m; i++) {
                 const double mag = smag[i];
                 save_sum -= sd[k];
                 sd[k] = mag;
@@ -279,6 +292,84 @@ __global__ void __launch_bounds__(128) nb_kernel(cd *samples, long stride, int n
     if (tid == 0) { st[0] = s_index; st[1] = s_win; st[2] = s_state; st[3] = save_sum; }
 }
 
+// ---- ssb_squelch (quisk.c:1086-1180) + d_delay (quisk.c:1056-1084).  Per channel the audio samples fill a 512-point
+// frame; a full frame is windowed (Hann), transformed, and the bins between 300 Hz and 300 Hz + bandwidth give
+// ratio = log(arithmetic mean of |X|^2) - mean(log |X|^2) (0.57 for band noise, more for speech); ratio above
+// level * 0.005 re-arms a one-second timer `sq_open`, the squelch is active when the timer has run out.  The frame
+// fill index is the same for every channel (host side), the timers are per channel.  The audio is then delayed by
+// one frame (512 samples) so that the decision is in time for the samples it was made from.
+// state per channel: 0 sq_open 1 squelch_active
+#define QC_SQ_N 512
+struct SqPar { int samp_rate, bw1, bw2; double thresh; };
+
+__global__ void __launch_bounds__(32) ssb_squelch_kernel(double *audio, long stride, int n, int index0, int do_squelch, int didx0, SqPar p,
+                                                         const cd *tw, const double *window, double *infft, double *delay, int *state)
+{
+    extern __shared__ double sm_raw[];
+    cd *twl = reinterpret_cast<cd *>(sm_raw);
+    cd *s = twl + fft_tw_entries(QC_SQ_N);
+    double *fbuf = reinterpret_cast<double *>(s + QC_SQ_N);     // [512] frame being filled
+    double *blk = fbuf + QC_SQ_N;                               // [n] this call's samples
+    const int c = blockIdx.x, lane = threadIdx.x, lanes = blockDim.x;
+    double *g = audio + (size_t)c * stride;
+    double *gf = infft + (size_t)c * QC_SQ_N;
+    double *gd = delay + (size_t)c * QC_SQ_N;
+    for (int i = lane; i < n; i += lanes) blk[i] = g[i];
+    if (do_squelch) {
+        fft_stage_twiddles(twl, tw, QC_SQ_N);
+        for (int i = lane; i < index0; i += lanes) fbuf[i] = gf[i];
+        int sq_open = state[c * 2];
+        __syncthreads();
+        int idx = index0, pos = 0;
+        while (pos < n) {
+            const int take = min(QC_SQ_N - idx, n - pos);
+            for (int j = lane; j < take; j += lanes) fbuf[idx + j] = blk[pos + j];
+            idx += take; pos += take;
+            __syncthreads();
+            if (idx == QC_SQ_N) {
+                for (int i = lane; i < QC_SQ_N; i += lanes) s[fsw(i)] = make_double2(fbuf[i] * window[i], 0.0);
+                __syncthreads();
+                fft_smem(s, QC_SQ_N, twl, -1, lane, lanes);
+                if (lane == 0) {                                // the reference's bin order, quisk.c:1127-1134
+                    double arith_avg = 0.0, geom_avg = 0.0, ratio;
+                    for (int i = p.bw1; i < p.bw2; i++) {
+                        const cd X = s[fsw(i)];
+                        const double re = X.x / 32767.0, im = X.y / 32767.0;        // CLIP16, quisk.h:14
+                        const double d = re * re + im * im;
+                        if (d > 1E-4) { arith_avg += d; geom_avg += log(d); }
+                    }
+                    if (arith_avg > 1E-4) {
+                        const int bw = p.bw2 - p.bw1;
+                        arith_avg = log(arith_avg / bw);
+                        geom_avg /= bw;
+                        ratio = arith_avg - geom_avg;
+                    } else {
+                        ratio = 1.0;
+                    }
+                    if (ratio > p.thresh) sq_open = p.samp_rate;
+                }
+                idx = 0;
+                __syncthreads();
+            }
+        }
+        for (int i = lane; i < idx; i += lanes) gf[i] = fbuf[i];
+        if (lane == 0) {
+            sq_open -= n;
+            if (sq_open < 0) sq_open = 0;
+            state[c * 2] = sq_open;
+            state[c * 2 + 1] = sq_open == 0;
+        }
+    }
+    __syncthreads();
+    // d_delay: a 512-sample FIFO.  Output i is the ring's old entry for i < 512 and this call's sample i - 512 after that.
+    for (int i = lane; i < n; i += lanes) {
+        const int k = (didx0 + i) & (QC_SQ_N - 1);
+        g[i] = i < QC_SQ_N ? gd[k] : blk[i - QC_SQ_N];
+    }
+    __syncthreads();
+    for (int i = max(0, n - QC_SQ_N) + lane; i < n; i += lanes) gd[(didx0 + i) & (QC_SQ_N - 1)] = blk[i];
+}
+
 struct QAgc { int C, rate, buf_size; AgcPar p; double *d_state; cd *d_fifo; };
 struct QFrac { int C; double dindex; double *d_state; };
 struct QBand { int S, n, L, count; const cd *tw; double *d_window, *d_avg, *d_max; };
@@ -291,6 +382,7 @@ struct qcAgc { QAgc a; };
 struct qcFracDecim { QFrac f; };
 struct qcBandscope { QBand b; };
 struct qcNoiseBlanker { QNb b; };
+struct qcSsbSquelch { int C, rate, bw, index, didx, planned; const cd *tw; double *d_window, *d_infft, *d_delay; int *d_state; };
 
 extern "C" {
 
@@ -409,6 +501,75 @@ int quisk_cuda_nb_run(qcNoiseBlanker *h, void *d_samples, long stride, int count
     QC_CUDA_LAUNCH();
     return QC_OK;
 }
+
+qcSsbSquelch *quisk_cuda_ssb_squelch_create(int n_channels, int samp_rate, int filter_bandwidth)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    if (n_channels <= 0 || samp_rate <= 0) { set_error("ssb_squelch_create: bad arguments"); return nullptr; }
+    qcSsbSquelch *h = new qcSsbSquelch();
+    h->C = n_channels; h->rate = samp_rate; h->bw = filter_bandwidth; h->index = 0; h->didx = 0; h->planned = 0;
+    h->tw = fft_twiddles(QC_SQ_N);
+    std::vector<double> w(QC_SQ_N);
+    for (int i = 0; i < QC_SQ_N; i++) w[i] = 0.50 - 0.50 * cos(2. * M_PI * i / QC_SQ_N);        // quisk.c:1110
+    const size_t nb = (size_t)n_channels * QC_SQ_N * sizeof(double);
+    if (!h->tw || cudaMalloc((void **)&h->d_window, QC_SQ_N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_infft, nb) != cudaSuccess || cudaMalloc((void **)&h->d_delay, nb) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_state, (size_t)n_channels * 2 * sizeof(int)) != cudaSuccess) {
+        set_error("ssb_squelch_create: allocation failure"); delete h; return nullptr;
+    }
+    cudaMemcpy(h->d_window, w.data(), QC_SQ_N * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(h->d_infft, 0, nb);
+    cudaMemset(h->d_delay, 0, nb);
+    cudaMemset(h->d_state, 0, (size_t)n_channels * 2 * sizeof(int));        // sq_open = 0 (quisk.c:1102), squelch_active = 0 (quisk.c:1908)
+    return h;
+}
+
+void quisk_cuda_ssb_squelch_destroy(qcSsbSquelch *h)
+{
+    if (h) { cudaFree(h->d_window); cudaFree(h->d_infft); cudaFree(h->d_delay); cudaFree(h->d_state); delete h; }
+}
+
+int quisk_cuda_ssb_squelch_run(qcSsbSquelch *h, double *d_audio, long stride, int count, int level, void *stream)
+{
+    if (!h || count < 0) return QC_EINVAL;
+    if (count > 8192) { set_error("ssb_squelch_run: at most 8192 samples per call (the timer is decremented once per call, so a call cannot be split)"); return QC_EINVAL; }
+    // The reference's first call only creates its FFT plan and returns (quisk.c:1104-1112): those samples never reach
+    // the frame and the timer is not touched; the delay line runs all the same (quisk.c:1926-1927).
+    const int do_squelch = h->planned;
+    h->planned = 1;
+    if (count == 0 && !do_squelch) return QC_OK;
+    SqPar p;
+    p.samp_rate = h->rate;
+    int bw = h->bw > 3000 ? 3000 : h->bw;                       // quisk.c:1120-1124
+    p.bw1 = 300 * QC_SQ_N / h->rate;
+    p.bw2 = (bw + 300) * QC_SQ_N / h->rate;
+    if (p.bw2 > QC_SQ_N / 2 + 1) p.bw2 = QC_SQ_N / 2 + 1;       // out_fft holds N/2 + 1 bins
+    if (p.bw1 > p.bw2) p.bw1 = p.bw2;
+    p.thresh = level * 0.005;                                   // quisk.c:1160
+    const size_t sh = (fft_tw_entries(QC_SQ_N) + QC_SQ_N) * sizeof(cd) + (size_t)(QC_SQ_N + count) * sizeof(double);
+    static bool optin[64] = {};
+    int dev = 0; cudaGetDevice(&dev); dev &= 63;
+    if (!optin[dev]) { QC_CUDA(cudaFuncSetAttribute(ssb_squelch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); optin[dev] = true; }
+    ssb_squelch_kernel<<<h->C, fft_threads(QC_SQ_N), sh, (cudaStream_t)stream>>>(d_audio, stride, count, h->index, do_squelch, h->didx, p,
+                                                                                  h->tw, h->d_window, h->d_infft, h->d_delay, h->d_state);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    if (do_squelch) h->index = (h->index + count) % QC_SQ_N;
+    h->didx = (h->didx + count) % QC_SQ_N;
+    return QC_OK;
+}
+
+int quisk_cuda_ssb_squelch_state(qcSsbSquelch *h, int *sq_open, int *squelch_active, void *stream)
+{
+    if (!h) return QC_EINVAL;
+    std::vector<int> st((size_t)h->C * 2);
+    QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    QC_CUDA(cudaMemcpy(st.data(), h->d_state, st.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < h->C; c++) { if (sq_open) sq_open[c] = st[c * 2]; if (squelch_active) squelch_active[c] = st[c * 2 + 1]; }
+    return QC_OK;
+}
+
+const int *quisk_cuda_ssb_squelch_state_ptr(qcSsbSquelch *h) { return h ? h->d_state : nullptr; }
 
 qcBandscope *quisk_cuda_bandscope_create(int n_streams, int size)
 {

@@ -1,4 +1,4 @@
-"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287), cFracDecim (quisk.c:622-665), NoiseBlanker (quisk.c:679-784) and
+"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287), cFracDecim (quisk.c:622-665), NoiseBlanker (quisk.c:679-784), ssb_squelch + d_delay (quisk.c:1056-1180) and
 the wire-format unpack loops (quisk.c:2922-2953, 3746-3763) from the compiled reference (oracle/_ref/libquisk_rx_ref.so).  Writes tests/golden/misc_kat.npz."""
 import ctypes as C
 import os
@@ -36,6 +36,22 @@ def nb_input(n, seed):
         x[p] *= 60.0
     x[2200:2212] *= 45.0 * (1.0 + rng.random(12))
     x[4000:4400] *= 3.0
+    return x
+
+
+SQ_RATE, SQ_BW = 12000, 2800
+SQ_SPLITS = [120, 1, 391, 512, 513, 2000, 37] + [120] * 100 + [4093, 1500, 3000, 8000, 700]
+SQ_LEVELS = [150, 60]
+
+
+def sq_input(n, seed):
+    """SSB audio at the 12 kS/s filter rate: band noise throughout, three voice-like tones between 0.8 s and 1.3 s."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / float(SQ_RATE)
+    x = (2.0 ** 20) * rng.standard_normal(n)
+    on = (t >= 0.8) & (t < 1.3)
+    for f, a in ((520.0, 2.0 ** 25), (1130.0, 2.0 ** 24), (2210.0, 2.0 ** 23)):
+        x += on * a * np.sin(2 * np.pi * f * t)
     return x
 
 
@@ -85,6 +101,20 @@ def main():
             lib.ref_noise_blanker(blk.ctypes.data, n, level)
             ys.append(blk)
         out["nb_%d_%d/y" % (rate, level)] = np.concatenate(ys)
+    for level in SQ_LEVELS:
+        lib = R.load("libquisk_rx_ref.so", private_copy=True)
+        lib.ref_ssb_squelch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        x = sq_input(sum(SQ_SPLITS), 91)
+        ys, act, opn, pos = [], [], [], 0
+        for n in SQ_SPLITS:
+            blk = np.ascontiguousarray(x[pos:pos + n]); pos += n
+            so = C.c_int(0)
+            act.append(lib.ref_ssb_squelch(blk.ctypes.data, n, SQ_RATE, SQ_BW, level, 0, C.byref(so)))
+            opn.append(so.value)
+            ys.append(blk)
+        out["sq_%d/y" % level] = np.concatenate(ys)
+        out["sq_%d/active" % level] = np.array(act)
+        out["sq_%d/sq_open" % level] = np.array(opn)
     # wire-format ingest: the reference's own unpack loops on seeded random bytes
     lib = R.load("libquisk_rx_ref.so", private_copy=True)
     lib.ref_add_rx_samples.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 from oracle import quisk_oracle as O
-from tests.golden.make_golden_misc import AGC_SPLITS, NB_CASES, NB_SPLITS, agc_input, nb_input
+from tests.golden.make_golden_misc import (AGC_SPLITS, NB_CASES, NB_SPLITS, SQ_BW, SQ_LEVELS, SQ_RATE, SQ_SPLITS, agc_input,
+                                           nb_input, sq_input)
 from tests.util import golden
 
 pytestmark = pytest.mark.gpu
@@ -110,6 +111,38 @@ def test_noise_blanker_long_blocks(torch, lib):
     for c in range(NCH):
         assert np.array_equal(y[c], O.NoiseBlanker(192000, 1)(xs[c]))
     lib.quisk_cuda_nb_destroy(h)
+
+
+@pytest.mark.parametrize("level", SQ_LEVELS)
+def test_ssb_squelch(level, torch, lib):
+    """ssb_squelch + d_delay (quisk.c:1056-1180) against the compiled reference's fixture: the timer and squelch_active
+    after every call (ragged calls from 1 to 8000 samples, several frames per call, the set-up-only first call) and
+    the delayed audio, bit-exact; a second channel with a different stream stays independent."""
+    kat = golden("misc_kat.npz")
+    x = sq_input(sum(SQ_SPLITS), 91)
+    x2 = (2.0 ** 20) * np.random.default_rng(5).standard_normal(len(x))
+    d = torch.from_numpy(np.stack([x, x2, x])).cuda()
+    h = lib.quisk_cuda_ssb_squelch_create(NCH, SQ_RATE, SQ_BW)
+    assert h
+    act, opn, pos = [], [], 0
+    so = (C.c_int * NCH)(); sa = (C.c_int * NCH)()
+    for n in SQ_SPLITS:
+        blk = d[:, pos:pos + n]
+        assert lib.quisk_cuda_ssb_squelch_run(h, blk.data_ptr(), d.stride(0), n, level, None) == 0
+        assert lib.quisk_cuda_ssb_squelch_state(h, so, sa, None) == 0
+        assert so[0] == so[2] and sa[0] == sa[2]
+        act.append(sa[0]); opn.append(so[0]); pos += n
+    assert opn == kat["sq_%d/sq_open" % level].tolist()
+    assert act == kat["sq_%d/active" % level].tolist()
+    y = d.cpu().numpy()
+    assert np.array_equal(y[0], kat["sq_%d/y" % level]) and np.array_equal(y[2], y[0])
+    ref2 = O.SsbSquelch(SQ_RATE, SQ_BW, level)
+    pos = 0
+    for n in SQ_SPLITS:
+        ref2(x2[pos:pos + n]); pos += n
+    assert (so[1], sa[1]) == (ref2.sq_open, ref2.active)
+    assert lib.quisk_cuda_ssb_squelch_run(h, d.data_ptr(), d.stride(0), 8193, level, None) != 0
+    lib.quisk_cuda_ssb_squelch_destroy(h)
 
 
 def test_bandscope(torch, lib):

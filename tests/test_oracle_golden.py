@@ -148,3 +148,21 @@ def test_noise_blanker_kat(rate, level):
     ref = kat["nb_%d_%d/y" % (rate, level)]
     assert np.array_equal(y, ref)
     assert (ref == 0).sum() > 3 * int(rate * 500.0e-6 + 0.5)        # the fixture does blank something beyond the initial delay
+
+
+@pytest.mark.parametrize("level", [150, 60])
+def test_ssb_squelch_kat(level):
+    """ssb_squelch + d_delay (quisk.c:1056-1180): timer and squelch_active after every call equal the compiled
+    reference's, the delayed audio is bit-exact."""
+    from tests.golden.make_golden_misc import SQ_BW, SQ_RATE, SQ_SPLITS, sq_input
+    kat = golden("misc_kat.npz")
+    x = sq_input(sum(SQ_SPLITS), 91)
+    sq = O.SsbSquelch(SQ_RATE, SQ_BW, level)
+    ys, act, opn, pos = [], [], [], 0
+    for n in SQ_SPLITS:
+        ys.append(sq(x[pos:pos + n])); pos += n
+        act.append(sq.active); opn.append(sq.sq_open)
+    assert act == kat["sq_%d/active" % level].tolist()
+    assert opn == kat["sq_%d/sq_open" % level].tolist()
+    assert np.array_equal(np.concatenate(ys), kat["sq_%d/y" % level])
+    assert 0 < sum(act) < len(act)                  # the fixture sees the squelch both closed and open

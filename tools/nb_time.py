@@ -16,17 +16,18 @@ for name, pulses in (("quiet", 0), ("one pulse per 4096 samples", 8)):
     xx = x.copy()
     for k in range(pulses):
         xx[k * 4096 + 100] *= 80.0
-    d = torch.from_numpy(np.stack([xx] * C_)).cuda()
+    src = torch.from_numpy(np.stack([xx] * C_)).cuda()
     h = lib.quisk_cuda_nb_create(C_, rate)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    for it in range(3):
+    ms = 0.0
+    for it in range(4):             # a fresh copy of the stream every call (the blanker works in place); first call = warm-up
+        d = src.clone()
+        torch.cuda.synchronize()
+        ev[0].record()
         lib.quisk_cuda_nb_run(h, d.data_ptr(), d.stride(0), n, 1, None)
-    torch.cuda.synchronize()
-    ev[0].record()
-    for it in range(5):
-        lib.quisk_cuda_nb_run(h, d.data_ptr(), d.stride(0), n, 1, None)
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1]) / 5
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it:
+            ms += ev[0].elapsed_time(ev[1]) / 3
     print("nb %s: %d ch x %d samples at %d S/s: %.3f ms per block = %.2f GS/s" % (name, C_, n, rate, ms, C_ * n / ms / 1e6))
     lib.quisk_cuda_nb_destroy(h)
