@@ -184,8 +184,8 @@ __global__ void bandscope_graph_kernel(const double *avg, int L, int graph_width
 // of the last save_size magnitudes that decides what a pulse is.  The decision depends on the magnitudes only, never on
 // the blanking state, so a chunk is processed in three phases: (1) all lanes: |x| ; lane 0: the running sum in the
 // reference's order (two dependent, separately rounded additions per sample, quisk.c:733-735); (2) all lanes: the
-// threshold test with the reference's division (quisk.c:736); (3) if the chunk holds no pulse and no blanking or ramp is
-// in progress the delay line is a plain ring and all lanes move it, otherwise lane 0 walks the state machine
+// threshold test with the reference's division (quisk.c:736); (3) if the chunk holds no pulse and no blanking is in
+// progress the delay line is a ring that all lanes move (scaling the entering samples while a ramp lasts), otherwise lane 0 walks the state machine
 // (quisk.c:740-765) sample by sample.  Chunks are at most save_size long, so that a ring slot is touched once per chunk.
 // state per channel: 0 index 1 win_index 2 state 3 save_sum
 struct NbPar { int save_size, hwindow, chunk; double limit; };
@@ -245,15 +245,25 @@ __global__ void __launch_bounds__(128) nb_kernel(cd *samples, long stride, int n
             flag[i] = (unsigned char)is_pulse;
             any |= is_pulse;
         }
-        any = __syncthreads_or(any | s_state | s_win);
+        any = __syncthreads_or(any | s_state);
         if (!any) {
+            // no pulse and not blanking: a plain ring, except that a ramp left over from the last pulse scales the
+            // samples entering it (sample i by (win_index + i) / hwindow while that is below 1, quisk.c:752-756)
+            const int w0 = s_win;
+            const double hw = (double)p.hwindow;
             for (int i = tid; i < m; i += NT) {
                 int k = index0 + i; if (k >= p.save_size) k -= p.save_size;
-                const cd x = sx[i];
+                cd x = sx[i];
+                if (w0 && w0 + i < p.hwindow) { const double w = (double)(w0 + i) / hw; x.x *= w; x.y *= w; }
                 sx[i] = sc[k];
                 sc[k] = x;
             }
-            if (tid == 0) { int k = index0 + m; if (k >= p.save_size) k -= p.save_size; s_index = k; }
+            __syncthreads();
+            if (tid == 0) {
+                int k = index0 + m; if (k >= p.save_size) k -= p.save_size;
+                s_index = k;
+                if (w0) s_win = w0 + m < p.hwindow ? w0 + m : 0;
+            }
         } else if (tid == 0) {
             int index = index0, win_index = s_win, state_ = s_state;
             const double hw = (double)p.hwindow;
@@ -465,7 +475,7 @@ qcNoiseBlanker *quisk_cuda_nb_create(int n_channels, int sample_rate)
     b.C = n_channels; b.rate = sample_rate;
     b.p.hwindow = (int)(sample_rate * 500.E-6 + 0.5);           // QUISK_NB_HWINDOW_SECS, quisk.c:679,704
     b.p.save_size = b.p.hwindow * 3;                            // quisk.c:705
-    b.p.chunk = b.p.save_size < 1024 ? b.p.save_size : 1024;
+    b.p.chunk = b.p.save_size < 512 ? b.p.save_size : 512;
     b.p.limit = 6.0;
     // delay line + magnitudes + one chunk of samples, sums and pulse flags
     b.smem = (size_t)b.p.save_size * (sizeof(cd) + sizeof(double)) + (size_t)b.p.chunk * (sizeof(cd) + sizeof(double) + 1) + 16;
