@@ -726,7 +726,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp):      # dram__bytes_read+write of one `ncu --set full` capture, scaled to this launch size
             traffic = json.load(open(tp))["dram_bytes_per_input_sample"] * C_ * block
-        roofline = {"bound": "hbm", "kernel": "fused_decim_kernel (tune + 4xHB45 + FIR98/2 + HB45 + FIR98/2, 1.536 MS/s -> 12 kS/s)", "achieved": ach, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": ("fused_decim_kernel" if (args.unfused or args.tailwarp == 0 or args.threads == 256 or args.chunk not in (0, 2048) or args.plans == 0 or args.deepk > 1) else "fused_decim_tw_kernel") + " (tune + 4xHB45 + FIR98/2 + HB45 + FIR98/2, 1.536 MS/s -> 12 kS/s)", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kms / ms,
                     "alg_bytes_per_launch": alg}
