@@ -339,6 +339,16 @@ int quisk_cuda_ssb_squelch_run(qcSsbSquelch *s, double *d_audio, long stride, in
 int quisk_cuda_ssb_squelch_state(qcSsbSquelch *s, int *sq_open, int *squelch_active, void *stream);
 const int *quisk_cuda_ssb_squelch_state_ptr(qcSsbSquelch *s);
 
+/* ---- 3d''. dAutoNotch (quisk.c:786-963), batched: the optional automatic notch of the SSB / AM branch of
+ * quisk_process_demodulate (quisk.c:1923-1924, on bank 0 when quisk_auto_notch is set).  rate = quisk_filter_srate,
+ * sidetone = rit_freq (a CW side tone is never notched).  In place on d_audio [n_channels][stride] double; the audio
+ * comes back 1538 samples late (overlap-save frames of 2048 with a 511-tap filter).  The object starts in the state
+ * the reference's initialising call dAutoNotch(NULL, ...) leaves. ---- */
+typedef struct qcAutoNotch qcAutoNotch;
+qcAutoNotch *quisk_cuda_autonotch_create(int n_channels, int rate);
+void quisk_cuda_autonotch_destroy(qcAutoNotch *a);
+int quisk_cuda_autonotch_run(qcAutoNotch *a, double *d_audio, long stride, int count, int sidetone, void *stream);
+
 /* ---- 3e. wire-format ingest: received bytes -> complex double on the device ----
  * quisk_cuda_unpack_iq: add_rx_samples (quisk.c:2922-2953).  d_bytes [n_channels][byte_stride]: packed (I, Q)
  * pairs, `bytes` = 1..4 per component, little endian (big_endian = 0) or big endian; each component is

@@ -36,6 +36,7 @@ gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" "$REF/filter.c" -o "$OUT/libquisk_f
 { sed -n '622,665p' "$REF/quisk.c"; sed -n '1182,1256p' "$REF/quisk.c"; sed -n '1633,1671p' "$REF/quisk.c";
   sed -n '1673,1846p' "$REF/quisk.c"; sed -n '1848,2160p' "$REF/quisk.c"; sed -n '2162,2287p' "$REF/quisk.c"; } > "$TMP/quisk_rx_funcs.inc"
 { sed -n '1056,1084p' "$REF/quisk.c"; sed -n '1086,1180p' "$REF/quisk.c"; } > "$TMP/quisk_squelch.inc"     # d_delay, ssb_squelch
+sed -n '786,963p' "$REF/quisk.c" > "$TMP/quisk_notch.inc"                 # dAutoNotch
 sed -n '679,784p' "$REF/quisk.c" > "$TMP/quisk_nb.inc"                    # NoiseBlanker (optional stage in front of the path)
 sed -n '2922,2953p' "$REF/quisk.c" > "$TMP/quisk_unpack_py.inc"          # add_rx_samples: the two unpack branches
 sed -n '3746,3763p' "$REF/quisk.c" > "$TMP/quisk_unpack_hermes.inc"      # read_rx_udp10: 24-bit record loop of one 512-byte frame

@@ -642,6 +642,91 @@ class NoiseBlanker:
 
 
 # --------------------------------------------------------------------------
+# dAutoNotch (quisk.c:786-963): optional automatic notch on the SSB audio at the filter rate
+# --------------------------------------------------------------------------
+
+class AutoNotch:
+    """Overlap-save with frames of 2048 samples advancing by 1538 and a 511-tap notch filter that follows the one or two
+    strongest steady lines of a per-bin running average of |X|.  Restated frame by frame: the reference's sample loop
+    emits, for input sample m, the filtered sample m - 1538 (zeros for the first frame).  State after the reference's
+    initialising call (quisk.c:826-835)."""
+    N, START, BINS = 2048, 510, 1025
+
+    def __init__(self, rate: int, sidetone: int = 0):
+        B = self.BINS
+        self.delta_sig = (300 * 2 * B + rate // 2) // rate
+        self.delta_i1 = (400 * 2 * B + rate // 2) // rate
+        self.signal = (abs(sidetone) * 2 * B + rate // 2) // rate if sidetone else -999
+        self.half_width = max((100 * 2 * 256 + rate // 2) // rate, 3)
+        self.window = 0.50 - 0.50 * np.cos(2.0 * np.pi * np.arange(511) / 511)
+        self.frame = np.zeros(self.N)
+        self.fill = self.START
+        self.ready = np.zeros(self.N - self.START)      # filtered samples waiting to be emitted
+        self.avg = np.zeros(B)
+        self.H = np.zeros(B, dtype=np.complex128)
+        self.old1 = self.old2 = 0
+        self.count1 = self.count2 = -4
+        self.sig = -1
+
+    def _peak(self, mask):
+        cand = np.where(mask, self.avg, 0.0)
+        i = int(np.argmax(cand))                         # first maximum, like the reference's strict `>` scan
+        return i if cand[i] > 0 else 0
+
+    def _design(self, i1, i2):
+        half = np.ones(257)
+        half[256] = self.H[256].real                     # the reference reuses fltr_fft: its bin 256 is stale (quisk.c:913-936)
+        for on, ctr in ((self.count1 > 0, (i1 + 2) // 4), (self.count1 > 0 and self.count2 > 0, (i2 + 2) // 4)):
+            if on:
+                lo, hi = max(ctr - self.half_width, 0), min(ctr + self.half_width, 255)
+                half[lo:hi + 1] = 0.0
+        h = np.fft.irfft(half, 512) * 512                # unnormalised c2r
+        taps = np.empty(511)
+        taps[255:509] = h[0:254]                         # memmove, quisk.c:938
+        taps[509:511] = h[509:511]
+        taps[0:255] = taps[510:255:-1]                   # mirror, quisk.c:939-940
+        padded = np.zeros(self.N)
+        padded[:511] = taps * self.window / 2048 / 4
+        self.H = np.fft.rfft(padded)
+
+    def _frame(self):
+        X = np.fft.rfft(self.frame)
+        self.avg = 0.5 * self.avg + 0.5 * np.abs(X)
+        k = np.arange(self.BINS)
+        far = np.abs(k - self.signal) > self.delta_sig
+        i1 = self._peak(far)
+        self.count1 = min(self.count1 + 1, 4) if abs(i1 - self.old1) < 3 else max(self.count1 - 1, -1)
+        if self.count1 < 0:
+            self.old1 = i1
+        i2 = self._peak(far & (np.abs(k - i1) > self.delta_i1))
+        self.count2 = min(self.count2 + 1, 4) if abs(i2 - self.old2) < 3 else max(self.count2 - 1, -2)
+        if self.count2 < 0:
+            self.old2 = i2
+        sig = i1 + 10000 * i2 if self.count1 > 0 and self.count2 > 0 else (i1 if self.count1 > 0 else 0)
+        if sig != self.sig:
+            self.sig = sig
+            self._design(i1, i2)
+        y = np.fft.irfft(X * self.H, self.N) * self.N    # unnormalised c2r
+        self.ready = y[self.START:] / 102                # NOTCH_DATA_SIZE / 20 in integers, quisk.c:958
+        self.frame[:self.START] = self.frame[self.N - self.START:]
+        self.fill = self.START
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        pos = 0
+        while pos < len(x):
+            take = min(self.N - self.fill, len(x) - pos)
+            y[pos:pos + take] = self.ready[self.fill - self.START:self.fill - self.START + take]
+            self.frame[self.fill:self.fill + take] = x[pos:pos + take]
+            self.fill += take
+            pos += take
+            if self.fill == self.N:
+                self._frame()
+        return y
+
+
+# --------------------------------------------------------------------------
 # ssb_squelch + d_delay (quisk.c:1056-1180): optional stage on the SSB audio at the filter rate
 # --------------------------------------------------------------------------
 

@@ -14,7 +14,7 @@
  * 622-665 cFracDecim, 1182-1256 dRxFilterOut/cRxFilterOut,
  * 1633-1671 PlanDecimation, 1673-1846 quisk_process_decimate,
  * 1848-2160 quisk_process_demodulate, 2162-2287 process_agc,
- * 679-784 NoiseBlanker, 1056-1084 d_delay, 1086-1180 ssb_squelch,
+ * 679-784 NoiseBlanker, 786-963 dAutoNotch, 1056-1084 d_delay, 1086-1180 ssb_squelch,
  * 2922-2953 the two sample-unpack branches of add_rx_samples,
  * 3746-3763 the 24-bit record loop of read_rx_udp10 (Hermes protocol 1).
  */
@@ -57,9 +57,10 @@ static struct _MeasureSquelch {
     int sq_open;
 } MeasureSquelch[MAX_RX_CHANNELS];
 
-/* Optional stage, off by default in the reference (quisk_auto_notch == 0): the call stays in the extracted code, it
- * does nothing.  ssb_squelch and d_delay are the reference's own (quisk.c:1056-1084, 1086-1180; FFTW through the shim). */
-static void dAutoNotch(double *d, int n, int f, int r) { (void)d; (void)n; (void)f; (void)r; }
+/* Optional stages, off by default in the reference (quisk_auto_notch == 0, ssb_squelch_enabled == 0): dAutoNotch,
+ * ssb_squelch and d_delay are the reference's own (quisk.c:786-963, 1056-1084, 1086-1180; FFTW through the shim). */
+int quisk_auto_notch;
+#include "quisk_notch.inc"          /* quisk.c:786-963 dAutoNotch */
 static int ssb_squelch_level;
 #include "quisk_squelch.inc"        /* quisk.c:1056-1084 d_delay, 1086-1180 ssb_squelch */
 
@@ -128,6 +129,16 @@ int ref_ssb_squelch(double *ds, int n, int samp_rate, int bw, int level, int ban
     d_delay(ds, n, bank, SQUELCH_FFT_SIZE);
     if (sq_open) *sq_open = MeasureSquelch[bank].sq_open;
     return MeasureSquelch[bank].squelch_active;
+}
+
+/* dAutoNotch (quisk.c:786-963) as quisk_process_demodulate calls it on bank 0 (quisk.c:1923-1924): `reset` = the
+ * initialising call with a NULL buffer (quisk.c:826-835). */
+void ref_auto_notch(double *ds, int n, int sidetone, int rate, int reset)
+{
+    if (reset) dAutoNotch(NULL, 0, 0, 0);
+    quisk_auto_notch = 1;
+    dAutoNotch(ds, n, sidetone, rate);
+    quisk_auto_notch = 0;
 }
 
 /* NoiseBlanker (quisk.c:679-784): called on the raw samples in front of the tuning stage (quisk.c:2448-2449) when

@@ -3,6 +3,7 @@
 //   cFracDecim   (quisk.c:622-665)    fractional decimation by 4-point Lagrange interpolation
 //   get_bandscope (quisk.c:4957-5011) + copy2pixels (quisk.c:4932-4955): real-input spectrum display
 //   NoiseBlanker (quisk.c:679-784)    impulse blanker on the raw samples in front of the tuning stage (optional)
+//   dAutoNotch (quisk.c:786-963)     automatic notch of the one or two strongest steady carriers in the SSB audio (optional)
 //   ssb_squelch + d_delay (quisk.c:1056-1180)  spectral-flatness squelch on the SSB audio at the filter rate (optional)
 // process_agc and cFracDecim are scalar recurrences: one CTA per channel, block staged in shared
 // memory, lane 0 walks it (compiled with --fmad=false so the state follows the reference bit for bit).
@@ -380,6 +381,133 @@ __global__ void __launch_bounds__(32) ssb_squelch_kernel(double *audio, long str
     for (int i = max(0, n - QC_SQ_N) + lane; i < n; i += lanes) gd[(didx0 + i) & (QC_SQ_N - 1)] = blk[i];
 }
 
+// ---- dAutoNotch (quisk.c:786-963): overlap-save filtering of the audio with a notch filter that follows the one or two
+// strongest steady spectral lines.  Frames of 2048 samples advance by 1538 (the filter has 511 taps); per frame:
+// forward transform, |X| into a running average per bin (0.5 / 0.5), first and second maximum outside the side-tone
+// band, hysteresis counters deciding whether each maximum is steady, and -- only when the (i1, i2) signature changes --
+// a new filter: ones with zeroed bands on 256 bins, 512-point inverse transform, centred and mirrored into 511 taps,
+// Hann, zero-padded 2048-point forward transform.  Then X *= H, inverse transform, divide by 102 (quisk.c:958).
+// One CTA of 128 lanes per channel, frames in sequence inside the kernel; the two scans and the counters are walked by
+// one lane in the reference's order.  Macro arithmetic as the reference's unparenthesised #defines give it
+// (NOTCH_FILTER_DESIGN_SIZE = 2048 / 4 inside expressions, quisk.c:788).
+#define QC_AN_N 2048
+#define QC_AN_BINS 1025
+#define QC_AN_START 510
+#define QC_AN_OUT 1538
+// ints per channel: 0 old1 1 count1 2 old2 3 count2 4 fltrSig
+struct AnPar { int delta_sig, delta_i1, signal, half_width; };
+
+__global__ void __launch_bounds__(128) autonotch_kernel(double *audio, long stride, int n, int index0, AnPar p, const cd *tw2k, const cd *tw512,
+                                                        const double *window, double *g_in, double *g_out, double *g_avg, cd *g_fltr, int *g_ist)
+{
+    extern __shared__ double sm_raw[];
+    cd *twl2k = reinterpret_cast<cd *>(sm_raw);
+    cd *twl512 = twl2k + fft_tw_entries(QC_AN_N);
+    cd *s = twl512 + fft_tw_entries(512);               // [2048] transform buffer
+    cd *X = s + QC_AN_N;                                // [1025] spectrum of the frame
+    double *fo = reinterpret_cast<double *>(X + QC_AN_BINS + 1);        // [512] filter design scratch
+    __shared__ int s_design, s_i1, s_i2, s_c1, s_c2;
+    const int c = blockIdx.x, tid = threadIdx.x, NT = 128;
+    double *a = audio + (size_t)c * stride;
+    double *din = g_in + (size_t)c * QC_AN_N, *dout = g_out + (size_t)c * QC_AN_N, *avg = g_avg + (size_t)c * QC_AN_BINS;
+    cd *fl = g_fltr + (size_t)c * QC_AN_BINS;
+    int *ist = g_ist + (size_t)c * 8;
+    fft_stage_twiddles(twl2k, tw2k, QC_AN_N);
+    fft_stage_twiddles(twl512, tw512, 512);
+    __syncthreads();
+    int idx = index0, pos = 0;
+    while (pos < n) {
+        const int take = min(QC_AN_N - idx, n - pos);
+        for (int j = tid; j < take; j += NT) { const double x = a[pos + j]; a[pos + j] = dout[idx + j]; din[idx + j] = x; }
+        idx += take; pos += take;
+        __syncthreads();
+        if (idx < QC_AN_N) break;
+        idx = QC_AN_START;
+        // forward transform of the frame (real input as a complex frame)
+        for (int i = tid; i < QC_AN_N; i += NT) s[fsw(i)] = make_double2(din[i], 0.0);
+        __syncthreads();
+        fft_smem<1>(s, QC_AN_N, twl2k, -1, tid, NT);
+        for (int i = tid; i < QC_AN_BINS; i += NT) {
+            const cd v = s[fsw(i)];
+            X[i] = v;
+            avg[i] = 0.5 * avg[i] + 0.5 * hypot(v.x, v.y);      // quisk.c:857-860
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int old1 = ist[0], count1 = ist[1], old2 = ist[2], count2 = ist[3], fltrSig = ist[4];
+            double d1 = 0; int i1 = 0;
+            for (int i = 0; i < QC_AN_BINS; i++)
+                if (abs(i - p.signal) > p.delta_sig && avg[i] > d1) { d1 = avg[i]; i1 = i; }
+            if (abs(i1 - old1) < 3) count1++; else count1--;
+            if (count1 > 4) count1 = 4; else if (count1 < -1) count1 = -1;
+            if (count1 < 0) old1 = i1;
+            double d2 = 0; int i2 = 0;
+            for (int i = 0; i < QC_AN_BINS; i++)
+                if (abs(i - p.signal) > p.delta_sig && abs(i - i1) > p.delta_i1 && avg[i] > d2) { d2 = avg[i]; i2 = i; }
+            if (abs(i2 - old2) < 3) count2++; else count2--;
+            if (count2 > 4) count2 = 4; else if (count2 < -2) count2 = -2;
+            if (count2 < 0) old2 = i2;
+            int k;
+            if (count1 > 0 && count2 > 0) k = i1 + 10000 * i2; else if (count1 > 0) k = i1; else k = 0;
+            s_design = fltrSig != k;
+            if (fltrSig != k) fltrSig = k;
+            s_i1 = i1; s_i2 = i2; s_c1 = count1; s_c2 = count2;
+            ist[0] = old1; ist[1] = count1; ist[2] = old2; ist[3] = count2; ist[4] = fltrSig;
+        }
+        __syncthreads();
+        if (s_design) {
+            // half spectrum of the 512-point design: ones, zero bands around (i1 + 2) / 4 and (i2 + 2) / 4; the Nyquist bin is
+            // whatever the last 2048-point filter spectrum left at index 256 (the reference reuses fltr_fft, quisk.c:913-936)
+            const int k1 = (s_i1 + 2) / 4, k2 = (s_i2 + 2) / 4;
+            const bool n1 = s_c1 > 0, n2 = s_c1 > 0 && s_c2 > 0;
+            const double nyq = fl[256].x;
+            for (int i = tid; i < 512; i += NT) {
+                const int b = i <= 256 ? i : 512 - i;
+                double v = 1.0;
+                if (n1 && b >= k1 - p.half_width && b <= k1 + p.half_width) v = 0.0;
+                if (n2 && b >= k2 - p.half_width && b <= k2 + p.half_width) v = 0.0;
+                if (b == 256) v = nyq;
+                s[fsw(i)] = make_double2(v, 0.0);
+            }
+            __syncthreads();
+            fft_smem<1>(s, 512, twl512, +1, tid, NT);
+            for (int i = tid; i < 512; i += NT) fo[i] = s[fsw(i)].x;
+            __syncthreads();
+            // centre, mirror (quisk.c:938-941), window and scale (quisk.c:942-943), zero-pad, forward transform
+            for (int i = tid; i < QC_AN_N; i += NT) {
+                double v = 0.0;
+                if (i < 511) {
+                    double f;
+                    if (i >= 255) f = i <= 508 ? fo[i - 255] : fo[i];
+                    else f = i >= 2 ? fo[255 - i] : fo[510 - i];
+                    v = f * window[i] / 2048 / 4;
+                }
+                s[fsw(i)] = make_double2(v, 0.0);
+            }
+            __syncthreads();
+            fft_smem<1>(s, QC_AN_N, twl2k, -1, tid, NT);
+            for (int i = tid; i < QC_AN_BINS; i += NT) fl[i] = s[fsw(i)];
+            __syncthreads();
+        }
+        // apply the filter, Hermitian extension, inverse transform
+        for (int i = tid; i < QC_AN_BINS; i += NT) {
+            const cd x = X[i], h = fl[i];
+            cd y = make_double2(x.x * h.x - x.y * h.y, x.x * h.y + x.y * h.x);
+            if (i == 0 || i == QC_AN_N / 2) y.y = 0.0;
+            s[fsw(i)] = y;
+            if (i > 0 && i < QC_AN_N / 2) s[fsw(QC_AN_N - i)] = make_double2(y.x, -y.y);
+        }
+        __syncthreads();
+        fft_smem<1>(s, QC_AN_N, twl2k, +1, tid, NT);
+        for (int i = QC_AN_START + tid; i < QC_AN_N; i += NT) dout[i] = s[fsw(i)].x / 102;       // NOTCH_DATA_SIZE / 20
+        double keep[4];
+        for (int e = 0, i = tid; e < 4; e++, i += NT) keep[e] = i < QC_AN_START ? din[QC_AN_OUT + i] : 0.0;
+        __syncthreads();
+        for (int e = 0, i = tid; e < 4; e++, i += NT) if (i < QC_AN_START) din[i] = keep[e];
+        __syncthreads();
+    }
+}
+
 struct QAgc { int C, rate, buf_size; AgcPar p; double *d_state; cd *d_fifo; };
 struct QFrac { int C; double dindex; double *d_state; };
 struct QBand { int S, n, L, count; const cd *tw; double *d_window, *d_avg, *d_max; };
@@ -392,6 +520,7 @@ struct qcAgc { QAgc a; };
 struct qcFracDecim { QFrac f; };
 struct qcBandscope { QBand b; };
 struct qcNoiseBlanker { QNb b; };
+struct qcAutoNotch { int C, rate, index; const cd *tw2k, *tw512; double *d_window, *d_in, *d_out, *d_avg; cd *d_fltr; int *d_ist; };
 struct qcSsbSquelch { int C, rate, bw, index, didx, planned; const cd *tw; double *d_window, *d_infft, *d_delay; int *d_state; };
 
 extern "C" {
@@ -580,6 +709,66 @@ int quisk_cuda_ssb_squelch_state(qcSsbSquelch *h, int *sq_open, int *squelch_act
 }
 
 const int *quisk_cuda_ssb_squelch_state_ptr(qcSsbSquelch *h) { return h ? h->d_state : nullptr; }
+
+qcAutoNotch *quisk_cuda_autonotch_create(int n_channels, int rate)
+{
+    if (ensure_device() != QC_OK) return nullptr;
+    if (n_channels <= 0 || rate <= 0) { set_error("autonotch_create: bad arguments"); return nullptr; }
+    qcAutoNotch *h = new qcAutoNotch();
+    h->C = n_channels; h->rate = rate; h->index = QC_AN_START;          // the state after the initialising call, quisk.c:826-835
+    h->tw2k = fft_twiddles(QC_AN_N); h->tw512 = fft_twiddles(512);
+    std::vector<double> w(QC_AN_N, 0.0);
+    for (int i = 0; i < 511; i++) w[i] = 0.50 - 0.50 * cos(2. * M_PI * i / 511);        // Hann over NOTCH_FILTER_SIZE, quisk.c:822-823
+    const size_t C_ = (size_t)n_channels;
+    if (!h->tw2k || !h->tw512 || cudaMalloc((void **)&h->d_window, QC_AN_N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_in, C_ * QC_AN_N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_out, C_ * QC_AN_N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_avg, C_ * QC_AN_BINS * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_fltr, C_ * QC_AN_BINS * sizeof(cd)) != cudaSuccess ||
+        cudaMalloc((void **)&h->d_ist, C_ * 8 * sizeof(int)) != cudaSuccess) {
+        set_error("autonotch_create: allocation failure"); delete h; return nullptr;
+    }
+    cudaMemcpy(h->d_window, w.data(), QC_AN_N * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(h->d_in, 0, C_ * QC_AN_N * sizeof(double));
+    cudaMemset(h->d_out, 0, C_ * QC_AN_N * sizeof(double));
+    cudaMemset(h->d_avg, 0, C_ * QC_AN_BINS * sizeof(double));
+    cudaMemset(h->d_fltr, 0, C_ * QC_AN_BINS * sizeof(cd));
+    std::vector<int> ist(C_ * 8, 0);
+    for (size_t c = 0; c < C_; c++) { ist[c * 8 + 1] = -4; ist[c * 8 + 3] = -4; ist[c * 8 + 4] = -1; }      // count1, count2, fltrSig
+    cudaMemcpy(h->d_ist, ist.data(), ist.size() * sizeof(int), cudaMemcpyHostToDevice);
+    return h;
+}
+
+void quisk_cuda_autonotch_destroy(qcAutoNotch *h)
+{
+    if (h) { cudaFree(h->d_window); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_avg); cudaFree(h->d_fltr); cudaFree(h->d_ist); delete h; }
+}
+
+int quisk_cuda_autonotch_run(qcAutoNotch *h, double *d_audio, long stride, int count, int sidetone, void *stream)
+{
+    if (!h || count < 0) return QC_EINVAL;
+    if (count == 0) return QC_OK;
+    const int rate = h->rate, NF = QC_AN_BINS, NFF = 256;       // NOTCH_FFT_SIZE, NOTCH_FILTER_FFT_SIZE
+    AnPar p;
+    p.delta_sig = (300 * 2 * NF + rate / 2) / rate;             // quisk.c:842-848
+    p.delta_i1 = (400 * 2 * NF + rate / 2) / rate;
+    p.signal = sidetone != 0 ? (abs(sidetone) * 2 * NF + rate / 2) / rate : -999;
+    p.half_width = (100 * 2 * NFF + rate / 2) / rate;           // quisk.c:905-907
+    if (p.half_width < 3) p.half_width = 3;
+    const size_t sh = (size_t)(fft_tw_entries(QC_AN_N) + fft_tw_entries(512) + QC_AN_N + QC_AN_BINS + 1) * sizeof(cd) + 512 * sizeof(double);
+    static bool optin[64] = {};
+    int dev = 0; cudaGetDevice(&dev); dev &= 63;
+    if (!optin[dev]) { QC_CUDA(cudaFuncSetAttribute(autonotch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); optin[dev] = true; }
+    autonotch_kernel<<<h->C, 128, sh, (cudaStream_t)stream>>>(d_audio, stride, count, h->index, p, h->tw2k, h->tw512, h->d_window,
+                                                              h->d_in, h->d_out, h->d_avg, h->d_fltr, h->d_ist);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    // the frame index advances the same way for every channel: 510 -> 2048 wraps to 510
+    long idx = h->index + (long)count;
+    while (idx >= QC_AN_N) idx -= QC_AN_OUT;
+    h->index = (int)idx;
+    return QC_OK;
+}
 
 qcBandscope *quisk_cuda_bandscope_create(int n_streams, int size)
 {

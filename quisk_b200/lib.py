@@ -106,6 +106,9 @@ def load() -> C.CDLL:
     lib.quisk_cuda_ssb_squelch_run.argtypes = [vp, vp, C.c_long, C.c_int, C.c_int, vp]
     lib.quisk_cuda_ssb_squelch_state.argtypes = [vp, c_int_p, c_int_p, vp]
     lib.quisk_cuda_ssb_squelch_state_ptr.argtypes = [vp]; lib.quisk_cuda_ssb_squelch_state_ptr.restype = vp
+    lib.quisk_cuda_autonotch_create.argtypes = [C.c_int, C.c_int]; lib.quisk_cuda_autonotch_create.restype = vp
+    lib.quisk_cuda_autonotch_destroy.argtypes = [vp]; lib.quisk_cuda_autonotch_destroy.restype = None
+    lib.quisk_cuda_autonotch_run.argtypes = [vp, vp, C.c_long, C.c_int, C.c_int, vp]
     lib.quisk_cuda_unpack_iq.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp]
     lib.quisk_cuda_hermes_samples_per_packet.argtypes = [C.c_int]
     lib.quisk_cuda_unpack_hermes.argtypes = [vp, C.c_int, C.c_int, vp, C.c_long, c_int_p, vp]

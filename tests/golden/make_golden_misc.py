@@ -1,4 +1,4 @@
-"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287), cFracDecim (quisk.c:622-665), NoiseBlanker (quisk.c:679-784), ssb_squelch + d_delay (quisk.c:1056-1180) and
+"""tests/golden/make_golden_misc.py -- fixtures for process_agc (quisk.c:2162-2287), cFracDecim (quisk.c:622-665), NoiseBlanker (quisk.c:679-784), ssb_squelch + d_delay (quisk.c:1056-1180), dAutoNotch (quisk.c:786-963) and
 the wire-format unpack loops (quisk.c:2922-2953, 3746-3763) from the compiled reference (oracle/_ref/libquisk_rx_ref.so).  Writes tests/golden/misc_kat.npz."""
 import ctypes as C
 import os
@@ -52,6 +52,23 @@ def sq_input(n, seed):
     on = (t >= 0.8) & (t < 1.3)
     for f, a in ((520.0, 2.0 ** 25), (1130.0, 2.0 ** 24), (2210.0, 2.0 ** 23)):
         x += on * a * np.sin(2 * np.pi * f * t)
+    return x
+
+
+AN_RATE = 12000
+AN_SPLITS = [120, 1, 1417, 1538, 1539, 5000, 37] + [120] * 60 + [4093, 3000, 8000, 711]
+AN_SIDETONES = [0, 700]
+
+
+def an_input(n, seed):
+    """SSB audio with a steady carrier at 1 kHz, a weaker one at 2.1 kHz from 0.9 s on, a CW-pitch tone at 700 Hz
+    (kept when it is the side tone) and noise."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / float(AN_RATE)
+    x = (2.0 ** 18) * rng.standard_normal(n)
+    x += (2.0 ** 24) * np.sin(2 * np.pi * 1000.0 * t + 0.3)
+    x += (t >= 0.9) * (2.0 ** 23) * np.sin(2 * np.pi * 2100.0 * t)
+    x += (2.0 ** 22) * np.sin(2 * np.pi * 700.0 * t + 1.1)
     return x
 
 
@@ -115,6 +132,16 @@ def main():
         out["sq_%d/y" % level] = np.concatenate(ys)
         out["sq_%d/active" % level] = np.array(act)
         out["sq_%d/sq_open" % level] = np.array(opn)
+    for sidetone in AN_SIDETONES:
+        lib = R.load("libquisk_rx_ref.so", private_copy=True)
+        lib.ref_auto_notch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        x = an_input(sum(AN_SPLITS), 92)
+        ys, pos = [], 0
+        for k, n in enumerate(AN_SPLITS):
+            blk = np.ascontiguousarray(x[pos:pos + n]); pos += n
+            lib.ref_auto_notch(blk.ctypes.data, n, sidetone, AN_RATE, int(k == 0))
+            ys.append(blk)
+        out["notch_%d/y" % sidetone] = np.concatenate(ys)
     # wire-format ingest: the reference's own unpack loops on seeded random bytes
     lib = R.load("libquisk_rx_ref.so", private_copy=True)
     lib.ref_add_rx_samples.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]

@@ -5,8 +5,8 @@ import numpy as np
 import pytest
 
 from oracle import quisk_oracle as O
-from tests.golden.make_golden_misc import (AGC_SPLITS, NB_CASES, NB_SPLITS, SQ_BW, SQ_LEVELS, SQ_RATE, SQ_SPLITS, agc_input,
-                                           nb_input, sq_input)
+from tests.golden.make_golden_misc import (AGC_SPLITS, AN_RATE, AN_SIDETONES, AN_SPLITS, NB_CASES, NB_SPLITS, SQ_BW, SQ_LEVELS,
+                                           SQ_RATE, SQ_SPLITS, agc_input, an_input, nb_input, sq_input)
 from tests.util import golden
 
 pytestmark = pytest.mark.gpu
@@ -143,6 +143,32 @@ def test_ssb_squelch(level, torch, lib):
     assert (so[1], sa[1]) == (ref2.sq_open, ref2.active)
     assert lib.quisk_cuda_ssb_squelch_run(h, d.data_ptr(), d.stride(0), 8193, level, None) != 0
     lib.quisk_cuda_ssb_squelch_destroy(h)
+
+
+@pytest.mark.parametrize("sidetone", AN_SIDETONES)
+def test_auto_notch(sidetone, torch, lib):
+    """dAutoNotch (quisk.c:786-963) against the compiled reference's fixture (FFTW calls through the oracle's shim):
+    ragged calls from 1 to 8000 samples, several frames per call; the stream contains the phases without a notch, with
+    one and with two notches, so every filter design and the hysteresis counters are exercised.  FP64 tolerance 1e-12
+    relative RMS (two different FFT implementations); a wrong decision anywhere would be an error of order one."""
+    kat = golden("misc_kat.npz")
+    x = an_input(sum(AN_SPLITS), 92)
+    d = torch.from_numpy(np.stack([x, 0.25 * x, x])).cuda()
+    h = lib.quisk_cuda_autonotch_create(NCH, AN_RATE)
+    assert h
+    pos = 0
+    for n in AN_SPLITS:
+        blk = d[:, pos:pos + n]
+        assert lib.quisk_cuda_autonotch_run(h, blk.data_ptr(), d.stride(0), n, sidetone, None) == 0
+        pos += n
+    torch.cuda.synchronize()
+    y = d.cpu().numpy()
+    ref = kat["notch_%d/y" % sidetone]
+    assert O.rel_rms(y[0], ref) < 1e-12 and np.array_equal(y[0], y[2])
+    assert O.rel_rms(y[1], 0.25 * ref) < 1e-12
+    for lo in range(0, len(ref) - 2048, 2048):      # and block by block, so a short wrong stretch cannot hide in the total
+        assert O.rel_rms(y[0][lo:lo + 2048], ref[lo:lo + 2048]) < 1e-11
+    lib.quisk_cuda_autonotch_destroy(h)
 
 
 def test_bandscope(torch, lib):

@@ -166,3 +166,20 @@ def test_ssb_squelch_kat(level):
     assert opn == kat["sq_%d/sq_open" % level].tolist()
     assert np.array_equal(np.concatenate(ys), kat["sq_%d/y" % level])
     assert 0 < sum(act) < len(act)                  # the fixture sees the squelch both closed and open
+
+
+@pytest.mark.parametrize("sidetone", [0, 700])
+def test_auto_notch_kat(sidetone):
+    """dAutoNotch (quisk.c:786-963): the frame-by-frame restatement (numpy's FFT) against the compiled reference
+    (the oracle's FFTW shim) on a stream that goes from no notch to one to two."""
+    from tests.golden.make_golden_misc import AN_RATE, AN_SPLITS, an_input
+    kat = golden("misc_kat.npz")
+    x = an_input(sum(AN_SPLITS), 92)
+    an = O.AutoNotch(AN_RATE, sidetone)
+    ys, pos = [], 0
+    for n in AN_SPLITS:
+        ys.append(an(x[pos:pos + n])); pos += n
+    y, ref = np.concatenate(ys), kat["notch_%d/y" % sidetone]
+    assert O.rel_rms(y, ref) < 1e-12
+    for lo in range(0, len(ref) - 2048, 2048):
+        assert O.rel_rms(y[lo:lo + 2048], ref[lo:lo + 2048]) < 1e-11
