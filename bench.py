@@ -89,7 +89,8 @@ class ClockSampler(threading.Thread):
             self.err = str(e)
 
     def run(self):
-        if not self.ok:
+        if not self.ok or os.environ.get("QUISK_BENCH_NO_SAMPLER"):     # diagnostic switch: the line then says so
+            self.ok = False; self.err = "disabled by QUISK_BENCH_NO_SAMPLER"
             return
         nv, h = self.nv, self.h
         try:
@@ -546,6 +547,7 @@ def main():
     ap.add_argument("--tailwarp", type=int, default=-1, help="fused decimator: 1 = low-rate stages on a fifth warp (default), 0 = all stages on the four main warps")
     ap.add_argument("--deepk", type=int, default=0, help="fused decimator: low-rate stages every k chunks (1 or 4)")
     ap.add_argument("--nco", default="exact", choices=["exact", "closed"], help="tuning phasor at block starts: the reference's recurrence (default) or closed form only")
+    ap.add_argument("--sync-steps", action="store_true", help="diagnostic: synchronise after every step, so that each step starts on an idle GPU (the host never runs ahead)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -633,6 +635,8 @@ def main():
             L.check(lib, lib.quisk_cuda_pan_graph(pan, 1024, 1.0, 0.0, float(SAMPLE_RATE), graph.data_ptr(), stream), "pan_graph")
         if rx:
             rx.process(x.data_ptr(), block, block, audio.data_ptr(), acap, stream=stream)
+        if args.sync_steps:
+            torch.cuda.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -660,6 +664,8 @@ def main():
     kms, kn = (rx.kernel_time() if rx else (0.0, 0))
     if rx:
         rx.set_option(1, 0)
+    if world > 1:       # per-rank diagnostics (stderr): a rank that is slower than the others shows up here
+        print("[rank %d] ms_per_step %.4f kernel_ms %.4f clocks %s" % (rank, ms / args.steps, kms / max(kn, 1), sampler.result()), file=sys.stderr, flush=True)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -14,32 +14,64 @@ namespace qc {
 // block ahead of the kernels that consume it (rxchain.cu), so its latency is hidden; the closed form (nco_pow)
 // then only has to bridge the samples INSIDE one block, and the tuning phasor follows the reference for any
 // stream length.
-__global__ void nco_advance_kernel(const cd *v_in, cd *v_out, const double *nco, int count, int C)
+// Work distribution: the recurrence is one dependent FP64 chain per channel, so its speed is set by how many of its
+// warps share an SM sub-partition's FP64 pipe -- one per sub-partition: 20 cycles per step; nine: 108.  The block
+// scheduler gives no control over that (it packs small CTAs onto whatever SMs have room at that instant: beside two
+// resident decimator CTAs that is one per SM, on SMs that are just draining it is nine), and a packed launch is
+// slower than the decimator it hides under, stalls the next block and leaves the device in a state where the next
+// launch is packed again (seen on 8-GPU runs: one rank at 1.95 ms per step instead of 1.24).  So the CTAs elect ONE
+// worker per SM themselves: the grid has 2 x #SM small CTAs; the first CTA of this launch to arrive on an SM (atomicMax
+// of the launch epoch on that SM's slot) becomes its worker and pulls groups of 128 channels from a ticket counter
+// until none are left, every other CTA exits at once.
+__global__ void nco_advance_kernel(const cd *v_in, cd *v_out, const double *nco, int count, int C, unsigned *sched, unsigned epoch)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const cd ph = make_double2(nco[(size_t)c * 8 + 5], nco[(size_t)c * 8 + 6]);
-    cd v = v_in[c];
+    // sched[0]: ticket counter (zeroed on the stream before the launch); sched[1 + smid]: last epoch with a worker there
+    __shared__ int s_item;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_item = atomicMax(&sched[1 + (smid & 1023u)], epoch) < epoch ? 0 : -1;
+    }
+    __syncthreads();
+    if (s_item < 0) return;
+    const int n_items = (C + (int)blockDim.x - 1) / (int)blockDim.x;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(&sched[0], 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) return;
+        const int c = item * (int)blockDim.x + (int)threadIdx.x;
+        if (c < C) {
+            const cd ph = make_double2(nco[(size_t)c * 8 + 5], nco[(size_t)c * 8 + 6]);
+            cd v = v_in[c];
 #pragma unroll 4
-    for (int i = 0; i < count; i++) v = cmul_rn(v, ph);
-    v_out[c] = v;
+            for (int i = 0; i < count; i++) v = cmul_rn(v, ph);
+            v_out[c] = v;
+        }
+    }
 }
 
-int launch_nco_advance(const cd *v_in, cd *v_out, const double *d_nco, int count, int C, cudaStream_t s)
+int launch_nco_advance(const cd *v_in, cd *v_out, const double *d_nco, int count, int C, unsigned *d_sched, unsigned epoch, cudaStream_t s)
 {
     if (C <= 0) return QC_OK;
-    // 24 KB of (unused) dynamic shared memory per CTA: the block scheduler would otherwise pack these one-warp CTAs
-    // onto the first few SMs with a free slot, where 16+ dependent FP64 chains share one pipe and the recurrence
-    // becomes the slowest thing on the device (measured: 1.6 ms instead of 0.4 ms for 32768 steps).  With the
-    // reservation at most one or two land on an SM, and the two 90 KB CTAs of the fused decimator still fit beside them.
+    // 24 KB of (unused) dynamic shared memory per CTA: beside the two 99 KB CTAs of the fused decimator exactly one of
+    // these fits on an SM.  128 threads: the four warps of a worker sit on the four sub-partitions of ONE SM, so every
+    // sub-partition of that SM gives up the same share of its FP64 pipe (one-warp CTAs put the whole load on a single
+    // sub-partition, and the barriers of the decimator CTAs living there make their other warps wait for it: 12 % of
+    // the step that way, the recurrence's FP64 work is 3.6 % of it).
     static bool optin[64] = {};         // per device: function attributes belong to the device's context
+    static int n_sm[64] = {};
     int dev = 0; cudaGetDevice(&dev); dev &= 63;
-    if (!optin[dev]) { QC_CUDA(cudaFuncSetAttribute(nco_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024)); optin[dev] = true; }
-    // 128 threads: the four warps of a CTA sit on the four sub-partitions of ONE SM, so every sub-partition of that SM
-    // gives up the same share of its FP64 pipe.  One-warp CTAs put the whole load on a single sub-partition of 128
-    // different SMs, and the barriers of the decimator CTAs living there make their other three warps wait for it
-    // (measured: the recurrence cost 12 % of the step that way, its FP64 work is 3.6 % of it).
-    nco_advance_kernel<<<(C + 127) / 128, 128, 24 * 1024, s>>>(v_in, v_out, d_nco, count, C);
+    if (!optin[dev]) {
+        QC_CUDA(cudaFuncSetAttribute(nco_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024));
+        QC_CUDA(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
+        optin[dev] = true;
+    }
+    QC_CUDA(cudaMemsetAsync(d_sched, 0, sizeof(unsigned), s));
+    const int items = (C + 127) / 128;
+    const int grid = items < 2 * n_sm[dev] ? 2 * n_sm[dev] : items;     // enough CTAs that every SM sees one
+    nco_advance_kernel<<<grid, 128, 24 * 1024, s>>>(v_in, v_out, d_nco, count, C, d_sched, epoch);
     count_launch();
     QC_CUDA_LAUNCH();
     return QC_OK;

@@ -186,7 +186,7 @@ int RxChain::nco_before(int count, cudaStream_t s)
     if (f_set[nb]) QC_CUDA(cudaStreamWaitEvent(s_nco, ev_f[nb], 0));
     // exact_nco = 0: the next block start comes from the closed form too (one step instead of `count`); the phasor
     // then drifts from the reference's by ~1e-19 per sample (1e-12 after ~8 s at 1.536 MS/s)
-    int rc = exact_nco ? launch_nco_advance(d_v[b], d_v[nb], d_nco, count, C, s_nco)
+    int rc = exact_nco ? launch_nco_advance(d_v[b], d_v[nb], d_nco, count, C, d_sched, ++nco_epoch, s_nco)
                        : launch_nco_jump(d_v[b], d_v[nb], d_nco, count, C, s_nco);
     if (rc != QC_OK) return rc;
     QC_CUDA(cudaEventRecord(ev_r[nb], s_nco)); r_set[nb] = true;
@@ -215,6 +215,9 @@ int RxChain::upload_nco()
         int pr_lo = 0, pr_hi = 0;
         QC_CUDA(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
         QC_CUDA(cudaStreamCreateWithPriority(&s_nco, cudaStreamNonBlocking, pr_hi));
+        QC_CUDA(cudaMalloc((void **)&d_sched, 1025 * sizeof(unsigned)));
+        QC_CUDA(cudaMemset(d_sched, 0, 1025 * sizeof(unsigned)));
+        nco_epoch = 0;
         for (int i = 0; i < NV; i++) {
             QC_CUDA(cudaMalloc((void **)&d_v[i], (size_t)C * sizeof(cd)));
             QC_CUDA(cudaEventCreateWithFlags(&ev_r[i], cudaEventDisableTiming));
@@ -237,6 +240,7 @@ void RxChain::release()
     cst.clear(); rst.clear(); rxf = nullptr;
     for (int i = 0; i < 2; i++) { if (bufc[i]) cudaFree(bufc[i]); if (bufr[i]) cudaFree(bufr[i]); bufc[i] = nullptr; bufr[i] = nullptr; }
     if (s_nco) { cudaStreamSynchronize(s_nco); cudaStreamDestroy(s_nco); s_nco = nullptr; }
+    if (d_sched) { cudaFree(d_sched); d_sched = nullptr; }
     for (int i = 0; i < NV; i++) {
         if (d_v[i]) cudaFree(d_v[i]); d_v[i] = nullptr;
         if (ev_r[i]) cudaEventDestroy(ev_r[i]); if (ev_f[i]) cudaEventDestroy(ev_f[i]);

@@ -29,6 +29,8 @@ struct RxChain {
     int vcur = 0;
     int exact_nco = 1;                  // 1: block-start phasors from the reference's recurrence; 0: closed form only
     cudaStream_t s_nco = nullptr;
+    unsigned *d_sched = nullptr;        // nco_advance_kernel's ticket counter + one worker slot per SM id
+    unsigned nco_epoch = 0;
     cudaEvent_t ev_r[NV] = {}, ev_f[NV] = {};
     bool r_set[NV] = {}, f_set[NV] = {};
     int nco_before(int count, cudaStream_t s);      // starts the recurrence for the next block; the consumer on s may then read d_v[vcur]
