@@ -252,6 +252,9 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_FUSED_DENSE  5   /* 1: 128-register cap (more resident CTAs), 0: up to 255 registers */
 #define QC_RX_OPT_FUSED_TAILWARP 12 /* plan kernels run the low-rate stages on two tail warps, one chunk behind the four main warps: 1 (default: from stage 3), 2..4 = first tail stage, 0 = off */
 #define QC_RX_OPT_FUSED_SPLIT 11   /* 1: half-band stages of the plan kernels run one lane per component, twice the outputs per lane */
+#define QC_RX_OPT_NOISE_BLANKER 13  /* quisk_noise_blanker (0 = off, 1..3): quisk_cuda_rx_process_host / _host_packed run NoiseBlanker
+                                      (quisk.c:679-784) on the staged block in front of the tuning stage, as quisk_process_samples
+                                      does (quisk.c:2448-2449).  The device entry leaves the caller's buffer alone: run quisk_cuda_nb_run first */
 #define QC_RX_OPT_FUSED_MIN_R  4   /* minimum outputs per thread in its half-band stages: 0 (auto), 2, 4, 8 */
 int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value);
 /* Sum of the event-timed durations (ms) of the dominant kernel since the last call, and how

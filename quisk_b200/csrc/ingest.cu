@@ -99,6 +99,8 @@ int RxChain::process_host_packed(const void *h_bytes, long byte_stride, int coun
     int rc = launch_unpack_iq(d_packed, (long)row, C, count, nb, big, d_host_in, host_cap, hs);
     if (rc != QC_OK) return rc;
     int na = 0;
+    rc = host_noise_blanker(hs, count);
+    if (rc != QC_OK) return rc;
     rc = process(d_host_in, host_cap, count, d_host_out, host_out_cap, &na, nullptr, 0, nullptr, hs);
     if (rc != QC_OK) return rc;
     const int nd = iq_out ? 2 * na : na;

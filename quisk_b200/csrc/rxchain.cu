@@ -241,6 +241,7 @@ void RxChain::release()
     for (int i = 0; i < 2; i++) { if (bufc[i]) cudaFree(bufc[i]); if (bufr[i]) cudaFree(bufr[i]); bufc[i] = nullptr; bufr[i] = nullptr; }
     if (s_nco) { cudaStreamSynchronize(s_nco); cudaStreamDestroy(s_nco); s_nco = nullptr; }
     if (d_sched) { cudaFree(d_sched); d_sched = nullptr; }
+    if (nb) { quisk_cuda_nb_destroy(nb); nb = nullptr; }
     for (int i = 0; i < NV; i++) {
         if (d_v[i]) cudaFree(d_v[i]); d_v[i] = nullptr;
         if (ev_r[i]) cudaEventDestroy(ev_r[i]); if (ev_f[i]) cudaEventDestroy(ev_f[i]);
@@ -377,6 +378,16 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
     return QC_OK;
 }
 
+// quisk_process_samples runs NoiseBlanker on the raw block in front of the tuning stage (quisk.c:2448-2449); the host
+// entries do the same on their staged copy of the block when QC_RX_OPT_NOISE_BLANKER is set.
+int RxChain::host_noise_blanker(cudaStream_t s, int count)
+{
+    if (nb_level <= 0) return QC_OK;
+    if (!nb) nb = quisk_cuda_nb_create(C, sample_rate);
+    if (!nb) return QC_EINVAL;
+    return quisk_cuda_nb_run(nb, d_host_in, host_cap, count, nb_level, s);
+}
+
 int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, double *h_audio, long audio_stride, int *n_audio)
 {
     if (count <= 0) { if (n_audio) *n_audio = 0; return QC_OK; }
@@ -395,7 +406,9 @@ int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, doubl
     QC_CUDA(cudaMemcpy2DAsync(d_host_in, (size_t)host_cap * sizeof(cd), h_iq, (size_t)iq_stride * sizeof(cd),
                               (size_t)count * sizeof(cd), C, cudaMemcpyHostToDevice, hs));
     int na = 0;
-    int rc = process(d_host_in, host_cap, count, d_host_out, host_out_cap, &na, nullptr, 0, nullptr, hs);
+    int rc = host_noise_blanker(hs, count);
+    if (rc != QC_OK) return rc;
+    rc = process(d_host_in, host_cap, count, d_host_out, host_out_cap, &na, nullptr, 0, nullptr, hs);
     if (rc != QC_OK) return rc;
     const int nd = iq_out ? 2 * na : na;        // doubles per channel
     if (nd > audio_stride) { set_error("rx_process_host: audio_stride %ld < %d", audio_stride, nd); return QC_EINVAL; }
@@ -470,6 +483,9 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
     if (!rx) return QC_EINVAL;
     switch (option) {
     case QC_RX_OPT_TIMING: rx->rx.timing = value != 0; return QC_OK;
+    case QC_RX_OPT_NOISE_BLANKER:
+        if (value < 0 || value > 3) { qc::set_error("rx_set_option: noise blanker level must be 0 (off) .. 3"); return QC_EINVAL; }
+        rx->rx.nb_level = value; return QC_OK;
     case QC_RX_OPT_FUSED_CHUNK:
         if (value < 128 || value > 2048) { qc::set_error("rx_set_option: chunk %d out of range", value); return QC_EINVAL; }
         rx->rx.fused_chunk = value; return QC_OK;

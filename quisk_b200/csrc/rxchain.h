@@ -29,6 +29,8 @@ struct RxChain {
     int vcur = 0;
     int exact_nco = 1;                  // 1: block-start phasors from the reference's recurrence; 0: closed form only
     cudaStream_t s_nco = nullptr;
+    qcNoiseBlanker *nb = nullptr; int nb_level = 0;     // QC_RX_OPT_NOISE_BLANKER: NoiseBlanker on the staged block of the host entries
+    int host_noise_blanker(cudaStream_t s, int count);
     unsigned *d_sched = nullptr;        // nco_advance_kernel's ticket counter + one worker slot per SM id
     unsigned nco_epoch = 0;
     cudaEvent_t ev_r[NV] = {}, ev_f[NV] = {};

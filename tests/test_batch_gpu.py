@@ -290,3 +290,39 @@ def test_rx_process_host(torch, tabs):
     for c in range(C):
         assert O.rel_rms(aud[c], kat["c1_tune0/y"]) < 1e-12
     rx.close()
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_rx_process_host_noise_blanker(packed, torch, tabs):
+    """QC_RX_OPT_NOISE_BLANKER (13): the host entries run NoiseBlanker (quisk.c:679-784) on the staged block in front of
+    the tuning stage, as quisk_process_samples does (quisk.c:2448-2449).  The blanker is bit-exact, so a chain with the
+    option fed the raw stream must give exactly the audio of a plain chain fed the oracle-blanked stream, block by block."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    C, n, nblk, rate = 2, 15360, 4, 1536000
+    if packed:      # int16 wire format: integers survive the unpack exactly, so the two feeds stay bit-identical
+        rng = np.random.default_rng(41)
+        xi = rng.integers(-2000, 2000, size=(n * nblk, 2)).astype(np.int16)
+        xi[[5000, 5001, 20000, 33000], :] = [[30000, -30000]]
+        x = O.unpack_iq(xi.reshape(-1).view(np.uint8), 2, False)          # what add_rx_samples makes of these bytes
+    else:
+        x = O.synth_iq(n * nblk, 21, 1.0)
+        x[[5000, 20000, 20003, 33000]] *= 70.0
+    a_nb = RxChain(C, rate, "USB", fi, fq, tabs, tune_hz=[5000.0] * C, fused=True)
+    a_nb.set_option(13, 2)
+    a_ref = RxChain(C, rate, "USB", fi, fq, tabs, tune_hz=[5000.0] * C, fused=True)
+    blanker = O.NoiseBlanker(rate, 2)
+    for b in range(nblk):
+        sl = slice(b * n, (b + 1) * n)
+        y0 = np.zeros((C, a_nb.max_out(n))); y1 = np.zeros_like(y0)
+        clean = np.ascontiguousarray(np.stack([blanker(x[sl])] * C))
+        if packed:
+            raw = np.ascontiguousarray(np.stack([xi[sl].reshape(-1).view(np.uint8)] * C))
+            n0 = a_nb.process_host_packed(raw, n, 2, False, y0)
+        else:
+            n0 = a_nb.process_host(np.ascontiguousarray(np.stack([x[sl]] * C)), n, y0)
+        n1 = a_ref.process_host(clean, n, y1)
+        assert n0 == n1 > 0
+        assert np.array_equal(y0[:, :n0], y1[:, :n1])
+    a_nb.close(); a_ref.close()
