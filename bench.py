@@ -332,7 +332,7 @@ def rxa_main(args, rank, world, local_rank):
     alg = cfg["alg_bytes"] * C_ * m * blocks
     ach = alg * args.steps / (ms / 1e3) / 1e9
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # a reported baseline: rank 0 at N = 1 only
         try:
             v, cores, dt = rxa_reference_rate(cfg, blocks, 8, 1)
             cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
@@ -505,7 +505,7 @@ def pfb_main(args, rank, world, local_rank):
     alg = cfg["alg_bytes"] * n
     ach = alg * args.steps / (ms / 1e3) / 1e9
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # a reported baseline: rank 0 at N = 1 only
         try:
             v, cores, dt = pfb_reference_rate(61440, 30, 1, 64)
             cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
@@ -751,7 +751,7 @@ def main():
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # a reported baseline: rank 0 at N = 1 only
         try:
             v, cores, dt = cpu_reference_rate(61440, 600, 5, args.workload, fi, fq, args.tune)
             cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
