@@ -211,3 +211,63 @@ class Panadapter:
             self.lib.quisk_cuda_pan_destroy(self.h); self.h = None
 
     __del__ = close
+
+
+class RxOptions:
+    """Host-side mirror of the three optional receive stages Quisk switches from Python -- `set_noise_blanker(level)`
+    (quisk.c:4605-4611), `set_auto_notch(on)` (quisk.c:4596-4603) and `set_ssb_squelch(enabled, level)`
+    (quisk.c:4729-4735) -- for a batch of receivers.  The setters record the values like the reference's
+    (`set_auto_notch` also re-initialises the notch state, as its `dAutoNotch(NULL, ...)` call does); the `run_*` methods are what the sample
+    thread does with them: `run_noise_blanker` on the raw block in front of the tuning stage (quisk.c:2448-2449),
+    `run_auto_notch` and `run_ssb_squelch` on the SSB audio at the filter rate (quisk.c:1923-1928).  All in place on
+    device memory ([n_channels][stride], complex128 for the blanker, float64 for the audio stages)."""
+
+    def __init__(self, n_channels: int, sample_rate: int, filter_srate: int, filter_bandwidth: int):
+        self.lib = L.require_device()
+        self.n_channels, self.filter_srate = n_channels, filter_srate
+        self.noise_blanker, self.auto_notch, self.ssb_squelch_enabled, self.ssb_squelch_level = 0, 0, 0, 0
+        lib = self.lib
+        self.nb = lib.quisk_cuda_nb_create(n_channels, sample_rate)
+        self.an = lib.quisk_cuda_autonotch_create(n_channels, filter_srate)
+        self.sq = lib.quisk_cuda_ssb_squelch_create(n_channels, filter_srate, filter_bandwidth)
+        if not (self.nb and self.an and self.sq):
+            raise L.QuiskCudaError("RxOptions: " + lib.quisk_cuda_last_error().decode())
+
+    def set_noise_blanker(self, level: int): self.noise_blanker = int(level)
+
+    def set_auto_notch(self, on: int):
+        self.auto_notch = int(on)
+        self.lib.quisk_cuda_autonotch_destroy(self.an)         # dAutoNotch(NULL, 0, 0, 0), quisk.c:4600
+        self.an = self.lib.quisk_cuda_autonotch_create(self.n_channels, self.filter_srate)
+        if not self.an:
+            raise L.QuiskCudaError("autonotch_create: " + self.lib.quisk_cuda_last_error().decode())
+
+    def set_ssb_squelch(self, enabled: int, level: int): self.ssb_squelch_enabled, self.ssb_squelch_level = int(enabled), int(level)
+
+    def run_noise_blanker(self, d_iq: int, stride: int, count: int, stream: int = 0):
+        """NoiseBlanker(cSamples, nSamples): does nothing while the level is 0, like the reference (quisk.c:695)."""
+        L.check(self.lib, self.lib.quisk_cuda_nb_run(self.nb, d_iq, stride, count, self.noise_blanker, stream or None), "nb_run")
+
+    def run_auto_notch(self, d_audio: int, stride: int, count: int, sidetone: int = 0, stream: int = 0):
+        """dAutoNotch(dsamples, nSamples, rit_freq, quisk_filter_srate): skipped while quisk_auto_notch is 0 (quisk.c:835)."""
+        if self.auto_notch:
+            L.check(self.lib, self.lib.quisk_cuda_autonotch_run(self.an, d_audio, stride, count, sidetone, stream or None), "autonotch_run")
+
+    def run_ssb_squelch(self, d_audio: int, stride: int, count: int, stream: int = 0):
+        """ssb_squelch + d_delay when ssb_squelch_enabled (quisk.c:1925-1928); returns squelch_active per channel or None."""
+        if not self.ssb_squelch_enabled:
+            return None
+        L.check(self.lib, self.lib.quisk_cuda_ssb_squelch_run(self.sq, d_audio, stride, count, self.ssb_squelch_level, stream or None), "ssb_squelch_run")
+        act = (C.c_int * self.n_channels)()
+        L.check(self.lib, self.lib.quisk_cuda_ssb_squelch_state(self.sq, None, act, stream or None), "ssb_squelch_state")
+        return list(act)
+
+    def close(self):
+        if getattr(self, "nb", None):
+            self.lib.quisk_cuda_nb_destroy(self.nb); self.nb = None
+        if getattr(self, "an", None):
+            self.lib.quisk_cuda_autonotch_destroy(self.an); self.an = None
+        if getattr(self, "sq", None):
+            self.lib.quisk_cuda_ssb_squelch_destroy(self.sq); self.sq = None
+
+    __del__ = close

@@ -171,6 +171,43 @@ def test_auto_notch(sidetone, torch, lib):
     lib.quisk_cuda_autonotch_destroy(h)
 
 
+def test_rx_options_host_mirror(torch, lib):
+    """quisk_b200.rx.RxOptions = set_noise_blanker / set_auto_notch / set_ssb_squelch + what the sample thread does with
+    them: off means untouched, on means the oracle's output; set_auto_notch restarts the notch like the reference."""
+    from quisk_b200.rx import RxOptions
+    opt = RxOptions(NCH, 192000, AN_RATE, SQ_BW)
+    xn = O.synth_iq(5000, 9, 1.0); xn[1500] *= 70.0
+    d = torch.from_numpy(np.stack([xn] * NCH)).cuda()
+    opt.run_noise_blanker(d.data_ptr(), d.stride(0), 5000)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy()[0], xn)                       # level 0: nothing happens
+    opt.set_noise_blanker(3)
+    opt.run_noise_blanker(d.data_ptr(), d.stride(0), 5000)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy()[NCH - 1], O.NoiseBlanker(192000, 3)(xn))
+    xa = an_input(6000, 92)
+    a = torch.from_numpy(np.stack([xa] * NCH)).cuda()
+    opt.run_auto_notch(a.data_ptr(), a.stride(0), 6000)
+    assert opt.run_ssb_squelch(a.data_ptr(), a.stride(0), 6000) is None
+    torch.cuda.synchronize()
+    assert np.array_equal(a.cpu().numpy()[0], xa)                       # both off
+    for _ in range(2):                                                  # the second switch-on starts from scratch again
+        opt.set_auto_notch(1)
+        a = torch.from_numpy(np.stack([xa] * NCH)).cuda()
+        opt.run_auto_notch(a.data_ptr(), a.stride(0), 6000)
+        torch.cuda.synchronize()
+        assert O.rel_rms(a.cpu().numpy()[1], O.AutoNotch(AN_RATE, 0)(xa)) < 1e-12
+    opt.set_ssb_squelch(1, 150)
+    sq = O.SsbSquelch(AN_RATE, SQ_BW, 150)
+    xs = sq_input(3000, 91)
+    for k in range(3):
+        blk = torch.from_numpy(np.stack([xs[k * 1000:(k + 1) * 1000]] * NCH)).cuda()
+        act = opt.run_ssb_squelch(blk.data_ptr(), blk.stride(0), 1000)
+        ref = sq(xs[k * 1000:(k + 1) * 1000])
+        assert act == [sq.active] * NCH and np.array_equal(blk.cpu().numpy()[0], ref)
+    opt.close()
+
+
 def test_bandscope(torch, lib):
     size, nblk, gw = 4096, 3, 800
     rng = np.random.default_rng(8)
