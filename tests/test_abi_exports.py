@@ -75,6 +75,12 @@ def test_no_device_is_an_error_not_a_fallback(lib):
     h = lib.quisk_cuda_batch_create(1, 4, None, 0, 1, 1)
     assert not h
     assert b"CUDA" in lib.quisk_cuda_last_error()
+    # the optional stages (noise blanker, auto-notch, SSB squelch) have no host path either
+    for name, args in (("quisk_cuda_nb_create", (2, 192000)), ("quisk_cuda_autonotch_create", (2, 12000)),
+                       ("quisk_cuda_ssb_squelch_create", (2, 12000, 2800))):
+        fn = getattr(lib, name)
+        fn.restype = C.c_void_p
+        assert not fn(*args), name
 
 
 def test_plan_decimation_matches_oracle(lib):
