@@ -732,7 +732,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp):      # dram__bytes_read+write of one `ncu --set full` capture, scaled to this launch size
             traffic = json.load(open(tp))["dram_bytes_per_input_sample"] * C_ * block
-        roofline = {"bound": "hbm", "kernel": ("fused_decim_kernel" if (args.unfused or args.tailwarp == 0 or args.threads == 256 or args.chunk not in (0, 2048) or args.plans == 0 or args.deepk > 1) else "fused_decim_tw_kernel") + " (tune + 4xHB45 + FIR98/2 + HB45 + FIR98/2, 1.536 MS/s -> 12 kS/s)", "achieved": ach, "peak": peak,
+        use_tw = not (args.unfused or args.tailwarp == 0 or args.threads == 256 or args.chunk not in (0, 2048) or args.plans == 0 or args.deepk > 1)
+        roofline = {"bound": "hbm", "kernel": ("fused_decim_tw_kernel" if use_tw else "fused_decim_kernel") + " (tune + 4xHB45 + FIR98/2 + HB45 + FIR98/2, 1.536 MS/s -> 12 kS/s)", "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kms / ms,
                     "alg_bytes_per_launch": alg}
@@ -744,6 +745,21 @@ def main():
             fma = 59.5 * C_ * block / (per_launch_ms / 1e3)
             roofline["fp64"] = {"achieved": fma / 1e12, "peak": pk.value / 1e12, "unit": "TFMA/s", "frac": fma / pk.value,
                                 "fma_per_input_sample": 59.5, "peak_source": "measured (quisk_cuda_fp64_peak: 8 independent DFMA chains per thread)"}
+        # the ceiling the kernel actually runs under: shared-memory bytes per input sample from the same ncu
+        # capture as `traffic`, against 128 B per clock per SM at the SM clock sampled during the timed region
+        try:
+            if use_tw and os.path.exists(tp):
+                sb = json.load(open(tp)).get("smem_bytes_per_input_sample")
+                clk = sampler.result().get("sm_mhz")
+                if sb and clk:
+                    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+                    spk = 128.0 * n_sm * clk * 1e6
+                    sach = sb * C_ * block / (per_launch_ms / 1e3)
+                    roofline["smem"] = {"achieved": sach / 1e9, "peak": spk / 1e9, "unit": "GB/s", "frac": sach / spk,
+                                        "bytes_per_input_sample": sb,
+                                        "peak_source": "128 B/clk/SM x %d SMs x sampled SM clock; bytes from profiles/r1_traffic.json (ncu wavefronts x 128 B)" % n_sm}
+        except Exception:       # an extra, never a reason to lose the line
+            pass
     elif pan:
         alg = ALG_BYTES_PAN * C_ * block
         ach = alg * args.steps / (ms / 1e3) / 1e9

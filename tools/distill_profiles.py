@@ -92,7 +92,10 @@ def fused_summary(channels=1184, block=32768):
     n = channels * block
     json.dump({"kernel": out["Kernel Name"], "source": "ncu --set full, profiles/r1_fused_decim_ncu_full.json (%d channels x %d samples, one launch)" % (channels, block),
                "dram_bytes_read": int(rd), "dram_bytes_write": int(wr), "input_samples": n,
-               "dram_bytes_per_input_sample": round((rd + wr) / n, 3)}, open(P + "/r1_traffic.json", "w"), indent=1)
+               "dram_bytes_per_input_sample": round((rd + wr) / n, 3),
+               "smem_wavefronts": int(float(d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]["value"])),
+               "smem_bytes_per_input_sample": round(128.0 * float(d["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]["value"]) / n, 2)},
+              open(P + "/r1_traffic.json", "w"), indent=1)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     gzip.open(P + "/r1_fused_decim_ncu_source.csv.gz", "wt").write(src)
     rows = list(csv.reader(io.StringIO(src)))
