@@ -21,7 +21,10 @@ One "step" = one pass of the hot path over one block of synthetic IQ for every c
 metric = complex input MS/s, whole job.  `value` is timed with inputs resident in HBM; `e2e` is the
 same work through the host-buffer C-ABI entry point (H2D of the block + D2H of the audio inside the
 timed region); `e2e_wire` (rx_chain only, extra key) is that step from int16 wire-format host blocks.  With N > 1 (torchrun) every rank runs its own C channels -- independent receivers,
-no data-path collective -- and the time is the max over ranks ("weak" scaling).
+no data-path collective -- and the time is the max over ranks ("weak" scaling); every rank also prints its own step
+and kernel time on stderr.  `roofline` is the fused decimator against the measured HBM peak (CUDA events around the
+kernel inside the library); `roofline.fp64` = the same launch against the measured FP64 pipe peak, `roofline.smem` =
+its shared-memory traffic (bytes per sample from the committed ncu capture) against 128 B/clk/SM.
 
 --impl reference times the reference's own C code (oracle/_ref: filter.c verbatim + the quisk.c RX
 functions, gcc -O2, no -ffast-math) on the host cores, one private copy of the library per thread.
