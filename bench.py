@@ -563,10 +563,10 @@ def main():
     if args.workload == "channelizer":
         return pfb_main(args, rank, world, local_rank)
 
-    from quisk_b200.rx import load_tables
+    from quisk_b200.rx import get_filter_center, load_tables, make_filter_coef
     tabs = load_tables()
-    kat = np.load(os.path.join(ROOT, "tests", "golden", "chain_kat.npz"))
-    fi = np.ascontiguousarray(kat["c1/filt_i"]); fq = np.ascontiguousarray(kat["c1/filt_q"])
+    # the C1 receive filter: USB, bandwidth 2800 at the 12 kS/s filter rate -> MakeFilterCoef's 164-tap I/Q pair
+    fi, fq = make_filter_coef(SAMPLE_RATE // 128, None, 2800, get_filter_center("USB", 2800), tabs)
     wl_name = {"rx_chain": "rx_chain: C x 1.536 MS/s tune->4xHB45->FIR98/2->48k->HB45->FIR98/2->cRxFilterOut(164 I/Q, USB)->audio 48k (BASELINE configs[0], batched)",
                "panadapter": "panadapter: C streams x 8192-pt Hann+FFT+|X| average+dB graph (BASELINE configs[1], batched)",
                "rx_chain+panadapter": "rx_chain + panadapter on the same input (configs[0]+configs[1], batched)"}[args.workload]

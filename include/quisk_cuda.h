@@ -214,6 +214,16 @@ struct qcRxConfig {
                                  * samples: d_audio then holds (re, im) pairs, *n_audio counts pairs, audio_stride counts doubles. */
 };
 
+/* MakeFilterCoef (quisk.py:5405-5456), host side: the I/Q tap tables set_filters() hands to cRxFilterOut / dRxFilterOut.
+ * proto / n_proto: the filters.py prototype for key quisk_cuda_filter_key(rate, bw) = bw * 24000 // rate // 2 when
+ * that table exists, else NULL / 0 and a Blackman-windowed Dirichlet kernel of N taps is designed (N <= 0: sized from
+ * the bandwidth like the reference's N = None).  center != 0: tuned by 2 exp(-j 2 pi center / rate (i - D)), filt_i =
+ * real parts, filt_q = imaginary parts; center == 0: both are the low-pass.  *n_taps = taps written (QC_ENOMEM and
+ * the needed count if cap is too small).  Bit-identical to the Python reference. */
+int quisk_cuda_filter_key(int rate, int bw);
+int quisk_cuda_make_filter_coef(int rate, int N, int bw, int center, const double *proto, int n_proto,
+                                double *filt_i, double *filt_q, int cap, int *n_taps);
+
 qcRxChain *quisk_cuda_rx_create(const struct qcRxConfig *cfg);
 void quisk_cuda_rx_destroy(qcRxChain *rx);
 /* PlanDecimation (quisk.c:1633): returns the planned rate, fills the three counts. */
@@ -380,7 +390,8 @@ typedef struct qcChannelizer qcChannelizer;
 qcChannelizer *quisk_cuda_pfb_create(int n_channels, int decim, const double *proto, int n_taps);
 void quisk_cuda_pfb_destroy(qcChannelizer *p);
 int quisk_cuda_pfb_count_out(const qcChannelizer *p, int count);
-int quisk_cuda_pfb_seek(qcChannelizer *p, long long n_abs);
+int quisk_cuda_pfb_seek(qcChannelizer *p, long long n_abs);      /* synchronises the device first */
+int quisk_cuda_pfb_seek_async(qcChannelizer *p, long long n_abs, void *stream);  /* ordered on `stream` like process / prime */
 int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *stream);
 #define QC_PFB_OPT_SLICE_FRAMES 1   /* frames of the branch-FIR intermediate per kernel pair (default 65536 = 1 GiB at 1024 channels) */
 #define QC_PFB_OPT_GENERIC      2   /* 1: force the single generic kernel (the only path when decim is not n_channels or n_channels/2) */

@@ -125,13 +125,19 @@ static PolyFirParams base_params(int K, int L, int M, long u0, double gain, int 
 // ---- decimators / plain filters ------------------------------------------------
 template <typename T, typename F>
 static int decimate_impl(const char *fn, T *samples, int count, F *filter, T *ring, T **wr, int decim,
-                         const void *coefs, int tap_mode)
+                         const void *coefs, int tap_mode, bool use_index = true)
 {
     std::lock_guard<std::mutex> g(g_ctx.mu);
     if (count <= 0) return 0;
     const int nTaps = filter->nTaps;
-    const int d0 = filter->decim_index;
-    const int n_out = (count + d0) / decim;                 // filter.c:213
+    // filter.c:213 tests `++decim_index >= decim`: an index left at or above `decim` by another entry point or ratio
+    // (filtDecim5S is shared by cDecimate(5) and cInterpDecim(4, 5), quisk.c:1825,1837) emits on the first sample and
+    // restarts from 0, i.e. it behaves like decim - 1.  quisk_dFilter / quisk_dD_out (filter.c:326-370) never look at
+    // the index: use_index = false leaves it alone.
+    int d0 = use_index ? filter->decim_index : 0;
+    if (d0 > decim - 1) d0 = decim - 1;
+    if (d0 < 0) d0 = 0;
+    const int n_out = (count + d0) / decim;
     std::vector<T> hist;
     ring_history(ring, *wr, nTaps, hist);
     PolyFirParams p = base_params(nTaps, 1, decim, decim - 1 - d0, 1.0, tap_mode);
@@ -139,7 +145,7 @@ static int decimate_impl(const char *fn, T *samples, int count, F *filter, T *ri
     std::vector<T> in(samples, samples + count);            // outputs overwrite the caller's buffer
     run_pass<T>(fn, p, coefs, cb, hist.data(), nTaps - 1, in.data(), count, samples, n_out);
     *wr = ring_push(ring, *wr, nTaps, in.data(), count);
-    filter->decim_index = (d0 + count) % decim;
+    if (use_index) filter->decim_index = (d0 + count) % decim;
     return n_out;
 }
 
@@ -280,17 +286,14 @@ int quisk_dDecimate(double *dSamples, int count, struct quisk_dFilter *filter, i
 int quisk_dFilter(double *dSamples, int count, struct quisk_dFilter *filter)
 {   // filter.c:347-370
     return decimate_impl<double>("quisk_dFilter", dSamples, count, filter, filter->dSamples,
-                                 &filter->ptdSamp, 1, filter->dCoefs, TAP_REAL);
+                                 &filter->ptdSamp, 1, filter->dCoefs, TAP_REAL, false);
 }
 
 double quisk_dD_out(double samp, struct quisk_dFilter *filter)
 {   // filter.c:326-345: one sample through the same dot product (a launch per sample:
     // callers that care about speed use quisk_dFilter on a block)
-    const int saved = filter->decim_index;
-    filter->decim_index = 0;
     double s = samp;
-    decimate_impl<double>("quisk_dD_out", &s, 1, filter, filter->dSamples, &filter->ptdSamp, 1, filter->dCoefs, TAP_REAL);
-    filter->decim_index = saved;
+    decimate_impl<double>("quisk_dD_out", &s, 1, filter, filter->dSamples, &filter->ptdSamp, 1, filter->dCoefs, TAP_REAL, false);
     return s;
 }
 

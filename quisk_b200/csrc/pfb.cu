@@ -387,10 +387,27 @@ struct Channelizer {
         d_u = nullptr; u_frames = 0;
         for (int i = 0; i < 2; i++) if (d_hist[i]) cudaFree(d_hist[i]);
         d_taps = nullptr; d_hist[0] = d_hist[1] = nullptr;
+        if (sa) { cudaStreamSynchronize(sa); cudaStreamDestroy(sa); sa = nullptr; }
+        if (sb) { cudaStreamSynchronize(sb); cudaStreamDestroy(sb); sb = nullptr; }
+        for (int i = 0; i < 2; i++) {
+            if (ev_fir[i]) cudaEventDestroy(ev_fir[i]);
+            if (ev_fft[i]) cudaEventDestroy(ev_fft[i]);
+            ev_fir[i] = ev_fft[i] = nullptr;
+        }
+        if (ev_edge) { cudaEventDestroy(ev_edge); ev_edge = nullptr; }
     }
-    int seek(long long n)
+    int seek(long long n, cudaStream_t s, bool on_stream)
     {
         if (n < 0) { set_error("pfb_seek: negative sample index"); return QC_EINVAL; }
+        if (on_stream) {
+            // ordered on the caller's stream like the process / prime calls around it (the internal pipeline streams
+            // always rejoin the caller's stream at the end of a process call)
+            for (int i = 0; i < 2; i++) QC_CUDA(cudaMemsetAsync(d_hist[i], 0, (size_t)T * sizeof(cd), s));
+            n_abs = n; cur = 0;
+            return QC_OK;
+        }
+        // no stream argument: order it against everything queued on any stream, non-blocking ones included
+        QC_CUDA(cudaDeviceSynchronize());
         for (int i = 0; i < 2; i++) QC_CUDA(cudaMemset(d_hist[i], 0, (size_t)T * sizeof(cd)));
         n_abs = n; cur = 0;
         return QC_OK;
@@ -546,7 +563,8 @@ qcChannelizer *quisk_cuda_pfb_create(int n_channels, int decim, const double *pr
 }
 void quisk_cuda_pfb_destroy(qcChannelizer *p) { if (p) { p->c.release(); delete p; } }
 int quisk_cuda_pfb_count_out(const qcChannelizer *p, int count) { return p && count >= 0 ? p->c.frames(count) : QC_EINVAL; }
-int quisk_cuda_pfb_seek(qcChannelizer *p, long long n_abs) { return p ? p->c.seek(n_abs) : QC_EINVAL; }
+int quisk_cuda_pfb_seek(qcChannelizer *p, long long n_abs) { return p ? p->c.seek(n_abs, nullptr, false) : QC_EINVAL; }
+int quisk_cuda_pfb_seek_async(qcChannelizer *p, long long n_abs, void *stream) { return p ? p->c.seek(n_abs, (cudaStream_t)stream, true) : QC_EINVAL; }
 int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *stream)
 {
     if (!p || count < 0) return QC_EINVAL;

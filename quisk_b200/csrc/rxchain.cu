@@ -255,7 +255,19 @@ void RxChain::release()
 
 int RxChain::reserve(int count)
 {
-    const long need = (long)count + 64;
+    // The scratch rows hold every intermediate of the stage graph, and a stage may emit MORE samples than it
+    // takes: below 96 kS/s PlanDecimation finds no integer decimation and the list starts with the 6/5 converter
+    // (quisk.c:1834-1838), so walk the complex stages and size for the largest intermediate.
+    double big = count, cur = count;
+    for (auto *f : cst) {
+        switch (f->kind) {
+        case QC_C_DECIM2_HB45: cur = cur / 2 + 1; break;
+        case QC_C_INTERPDECIM: cur = cur * f->interp / f->decim + 2; break;
+        default: cur = cur / f->decim + 1; break;
+        }
+        if (cur > big) big = cur;
+    }
+    const long need = (long)big + 64;
     if (need <= cap) return QC_OK;
     for (int i = 0; i < 2; i++) {
         if (bufc[i]) cudaFree(bufc[i]); if (bufr[i]) cudaFree(bufr[i]);
@@ -302,7 +314,21 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
     if (n_audio) *n_audio = 0;
     if (n_decim) *n_decim = 0;
     if (count == 0) return QC_OK;
+    if (poisoned) { set_error("rx_process: an earlier call failed after stage state had advanced; call quisk_cuda_rx_reset() first"); return QC_EINVAL; }
     int rc = reserve(count); if (rc != QC_OK) return rc;
+    // Validate the caller's buffers against the output counts this call WILL produce before any stage state (NCO ring,
+    // decimation phases, history ping-pong) advances: the phases are host integers, so the counts are known up front.
+    {
+        int np_ = count;
+        for (auto *f : cst) np_ = f->count_out(np_, 0);
+        if (iq_out) {
+            if (audio_stride < 2L * np_ || (audio_stride & 1)) { set_error("rx_process: DGT-IQ needs an even audio_stride >= 2 * samples"); return QC_EINVAL; }
+        } else {
+            for (auto *f : rst) np_ = f->count_out(np_, 0);
+            if (audio_stride < np_) { set_error("rx_process: audio_stride %ld < %d samples this call produces", audio_stride, np_); return QC_EINVAL; }
+        }
+    }
+    struct Latch { bool &p; bool ok = false; ~Latch() { if (!ok) p = true; } } latch{poisoned};     // any error return below leaves the streams out of step
 
     const cd *cur = (const cd *)d_iq; long stride = iq_stride; int n = count; int pp = 0;
     size_t first_stage = 0;
@@ -342,11 +368,12 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
             no = n;
         }
         if (n_audio) *n_audio = no;
+        latch.ok = true;
         return QC_OK;
     }
     if (fused && fused_tail && tail_fusable()) {
         rc = run_tail(cur, stride, n, d_audio, audio_stride, &no, s);
-        if (rc == QC_OK) { if (n_audio) *n_audio = no; return QC_OK; }
+        if (rc == QC_OK) { if (n_audio) *n_audio = no; latch.ok = true; return QC_OK; }
         if (rc != QC_ENOMEM) return rc;          // too long for shared memory: per-stage kernels below
     }
     // main receive filter
@@ -375,6 +402,7 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
         rcur = dst; rp ^= 1; n = no;
     }
     if (n_audio) *n_audio = n;
+    latch.ok = true;
     return QC_OK;
 }
 
@@ -430,6 +458,7 @@ int RxChain::reset()
     if (tune) { rc = upload_nco(); if (rc != QC_OK) return rc; }
     rc = reset_fused(); if (rc != QC_OK) return rc;
     QC_CUDA(cudaDeviceSynchronize());
+    poisoned = false;
     return QC_OK;
 }
 

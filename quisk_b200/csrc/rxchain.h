@@ -64,6 +64,7 @@ struct RxChain {
     int fused_min_r = 0;                // force at least this many outputs per thread in half-band stages
     int fused_tail = 1;                 // SSB / CW: run filter + demod + audio interpolators as one kernel (rxtail.cu)
     // optional device timing of the dominant (fused) kernel
+    bool poisoned = false;              // a process() call failed after stage state had advanced: reset() before the next block
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
 

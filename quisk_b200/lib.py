@@ -118,6 +118,9 @@ def load() -> C.CDLL:
     lib.quisk_cuda_pfb_count_out.argtypes = [vp, C.c_int]
     lib.quisk_cuda_pfb_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.quisk_cuda_pfb_seek.argtypes = [vp, C.c_longlong]
+    lib.quisk_cuda_pfb_seek_async.argtypes = [vp, C.c_longlong, vp]
+    lib.quisk_cuda_filter_key.argtypes = [C.c_int, C.c_int]
+    lib.quisk_cuda_make_filter_coef.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, c_double_p, C.c_int, c_int_p]
     lib.quisk_cuda_pfb_prime.argtypes = [vp, vp, C.c_int, vp]
     lib.quisk_cuda_pfb_process.argtypes = [vp, vp, C.c_int, vp, C.c_long, C.c_int, c_int_p, vp]
     # ---- WDSP RXA part (include/quisk_cuda_wdsp.h) ----

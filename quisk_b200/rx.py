@@ -128,13 +128,40 @@ class RxChain:
 
 
 def load_tables(path: str | None = None) -> dict:
-    """The reference's coefficient tables (filters.h) and prototype filters (filters.py) as
-    extracted from the compiled reference into tests/golden/quisk_tables.npz.  In a drop-in
-    build the caller links the reference's own filters.h instead."""
+    """The coefficient tables the chain needs by name (filters.h: quiskFilt48dec24Coefs ...) and the 24 kS/s
+    prototype low-pass tables of filters.py (keys proto_<n>), shipped as package data in
+    quisk_b200/data/quisk_tables.npz (extracted from the compiled reference by tests/golden/make_golden.py).  In a
+    drop-in build the caller links the reference's own filters.h instead."""
     import os
-    path = path or os.path.join(os.path.dirname(L.HERE), "tests", "golden", "quisk_tables.npz")
+    path = path or os.path.join(L.HERE, "data", "quisk_tables.npz")
     z = np.load(path)
     return {k: z[k] for k in z.files}
+
+
+def get_filter_center(mode: str, bandwidth: int, cw_tone: int = 600) -> int:
+    """GetFilterCenter (quisk.py:5464-5488): centre of the mode's I/Q pass band in Hz, negative on the lower side
+    band (MakeFilterCoef takes its absolute value; the sign picks re + im or re - im in the demodulator)."""
+    table = {"CWU": max(cw_tone, bandwidth // 2), "CWL": max(cw_tone, bandwidth // 2), "AM": 0, "FM": 0,
+             "DGT-U": max(1500, bandwidth // 2), "DGT-L": max(1500, bandwidth // 2), "DGT-IQ": 0, "DGT-FM": 0,
+             "FDV-U": 1500 if bandwidth <= 3000 else bandwidth // 2, "FDV-L": 1500 if bandwidth <= 3000 else bandwidth // 2}
+    center = table.get(mode, 300 + bandwidth // 2)            # LSB / USB / IMD and anything else
+    return -center if mode in ("CWL", "LSB", "DGT-L", "FDV-L") else center
+
+
+def make_filter_coef(rate: int, N, bw: int, center: int, tables: dict | None = None):
+    """MakeFilterCoef (quisk.py:5405-5456) -> (filtI, filtQ): quisk_cuda_make_filter_coef with the filters.py
+    prototype for key bw * 24000 // rate // 2 when there is one."""
+    lib = L.load()
+    tables = tables if tables is not None else load_tables()
+    proto = tables.get("proto_%d" % lib.quisk_cuda_filter_key(int(rate), int(bw)))
+    cap = 10001                                     # MAX_FILTER_SIZE, quisk.h:10
+    fi = np.zeros(cap); fq = np.zeros(cap); n = C.c_int(0)
+    if proto is not None:
+        proto = np.ascontiguousarray(proto, dtype=np.float64)
+    L.check(lib, lib.quisk_cuda_make_filter_coef(int(rate), int(N) if N else 0, int(bw), int(center),
+                                                 _dp(proto) if proto is not None else None, len(proto) if proto is not None else 0,
+                                                 _dp(fi), _dp(fq), cap, C.byref(n)), "make_filter_coef")
+    return fi[:n.value].copy(), fq[:n.value].copy()
 
 
 class Channelizer:

@@ -4,7 +4,8 @@ REFERENCE (oracle/_ref, built by oracle/build_ref.sh from /root/reference).
 The reference ships no tests or golden vectors, so these files are
 the known-answer set for this repository:
 
-  quisk_tables.npz    the 30 coefficient tables of filters.h (read out of the compiled
+  quisk_b200/data/quisk_tables.npz (package data, the product reads it)
+                      the 30 coefficient tables of filters.h (read out of the compiled
                       filter.c) and the 17 prototype low-pass tables of filters.py
   filter_kat.npz      every filter.h block function on seeded synthetic IQ fed in
                       uneven blocks: outputs + per-block counts
@@ -30,7 +31,7 @@ from oracle import ref_ctypes as R            # noqa: E402
 SPLITS = [1, 2, 3, 7, 255, 256, 257, 1000, 1, 2218]
 CHAIN_SPLITS = [1, 2, 3, 7, 255, 256, 257, 1000, 4093, 15360, 18766]
 DEMOD_SPLITS = [1, 2, 3, 7, 255, 256, 257, 1000, 4093, 6126]
-RATES = [1536000, 192000, 96000, 48000, 240000, 250000, 960000, 1200000, 111111, 185185]
+RATES = [1536000, 192000, 96000, 48000, 240000, 250000, 960000, 1200000, 111111, 185185, 50000, 60000, 64000]
 DEMOD_TAPS = {"USB": 164, "LSB": 164, "CWU": 390, "CWL": 390, "AM": 77, "FM": 55}
 # digital modes: (fixture name, mode, taps, filter_bandwidth)
 DGT_CASES = [("DGT-U", "DGT-U", 390, 2800), ("DGT-L", "DGT-L", 390, 2800), ("DGT-U-wide", "DGT-U", 164, 3200),
@@ -78,7 +79,7 @@ def main():
     out = dict(tabs)
     for k, v in ref_filters.Filters.items():
         out["proto_%d" % k] = np.array(v, dtype=np.float64)
-    np.savez_compressed(os.path.join(HERE, "quisk_tables.npz"), **out)
+    np.savez_compressed(os.path.join(ROOT, "quisk_b200", "data", "quisk_tables.npz"), **out)     # package data
 
     kat = {}
     for name, fn, seed, real, tab, args, tune in FILTER_CASES:

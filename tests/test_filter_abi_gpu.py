@@ -151,3 +151,42 @@ def test_per_sample_entry_points(lib, tabs):
     hc = np.exp(2j * np.pi * 0.1 * (np.arange(len(h)) - D)) * h
     exp = O.FirDecim(hc, 1)(x.astype(np.complex128))
     assert O.rel_rms(np.array(got), exp) < 1e-13
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref not built")
+def test_shared_struct_stale_decim_index(lib, tabs):
+    """A struct reused across entry points and ratios, as quisk.c does with filtDecim5S (cDecimate(5) then
+    cInterpDecim(4, 5), quisk.c:1825,1837): an index left at or above the new `decim` emits on the first sample
+    (filter.c:213), quisk_cFilter restarts it, quisk_dFilter / quisk_dD_out never touch it (filter.c:326-370)."""
+    ref = R.bind_filter_api(R.load("libquisk_filter_ref.so"))
+    R.bind_filter_api(lib)
+    h = np.ascontiguousarray(tabs["quiskFilt240D5CoefsSharp"])
+    x = kat_input(21, False, 400)
+    res = []
+    for L_ in (ref, lib):
+        st = R.cFilter()
+        L_.quisk_filt_cInit(C.byref(st), h.ctypes.data_as(R.c_double_p), len(h))
+        outs = []
+        for fn, n, args in [("quisk_cDecimate", 103, (5,)), ("quisk_cDecimate", 50, (2,)), ("quisk_cInterpDecim", 57, (4, 5)),
+                            ("quisk_cDecimate", 33, (3,)), ("quisk_cFilter", 20, ()), ("quisk_cDecimate", 41, (5,))]:
+            if fn == "quisk_cDecimate" and args == (2,):
+                st.decim_index = 4                  # stale: >= the new ratio
+            buf = np.zeros(1024, dtype=np.complex128); buf[:n] = x[:n]
+            k = getattr(L_, fn)(buf.ctypes.data, n, C.byref(st), *args)
+            outs.append((k, st.decim_index, buf[:k].copy()))
+        res.append(outs)
+    for (ka, ia, ya), (kb, ib, yb) in zip(*res):
+        assert ka == kb and ia == ib and np.array_equal(ya, yb)
+    hd = np.ascontiguousarray(tabs["quiskAudio24p6Coefs"])
+    xr = kat_input(22, True, 64)
+    res = []
+    for L_ in (ref, lib):
+        st = R.dFilter()
+        L_.quisk_filt_dInit(C.byref(st), hd.ctypes.data_as(R.c_double_p), len(hd))
+        st.decim_index = 3
+        buf = xr.copy()
+        k = L_.quisk_dFilter(buf.ctypes.data, 64, C.byref(st))
+        v = L_.quisk_dD_out(1.5, C.byref(st))
+        res.append((k, st.decim_index, buf[:k].copy(), v))
+    assert res[0][0] == res[1][0] == 64 and res[0][1] == res[1][1] == 3
+    assert np.array_equal(res[0][2], res[1][2]) and res[0][3] == res[1][3]
