@@ -107,7 +107,7 @@ int quisk_cuda_rxa_set_nbp_run(qcRxa *r, int run);                          /* R
  * upflag it raises: quisk_cuda_rxa_fexchange0 then runs upslew0's state machine (iobuffs.c:98-160) per channel on the
  * device -- zeros up to and including the first non-zero sample, tdelayup of zeros, a raised-cosine ramp over
  * tslewup.  A new handle starts armed with both times 0 (the first non-zero sample is still swallowed).  The
- * down-slew / flush of SetChannelState(ch, 0) is not reproduced. */
+ * down-slew / flush of SetChannelState(ch, 0): quisk_cuda_rxa_set_channel_state below. */
 int quisk_cuda_rxa_set_slew(qcRxa *rxa, double tdelayup, double tslewup);
 /* sip1 of create_rxa (RXA.c:392-401; xsiphon mode 0, siphon.c:96-129): the last 4096 samples of midbuff per channel,
  * kept by default like the reference (run = 1).  quisk_cuda_rxa_get_siphon = RXAGetaSipF (complex_out 0: real parts)
@@ -127,12 +127,76 @@ int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per chan
 int quisk_cuda_rxa_out_size(const qcRxa *r);     /* dsp_outsize: samples per channel produced per xrxa */
 /* xrxa (RXA.c:561-598) for one DSP block of every channel. d_in [n_channels][in_stride], d_out likewise. */
 int quisk_cuda_rxa_xrxa(qcRxa *r, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream);
-/* fexchange0-shaped entry (wdsp/iobuffs.c:464-516) with HOST buffers for all channels: copies a block in,
- * runs xrxa, returns the block that the reference would return at this call, i.e. delayed by the two
- * DSP buffers of its output ring (zeros first); *error = 0.  Slew ramps are not applied. */
+/* fexchange0 (wdsp/iobuffs.c:464-516) with HOST buffers for all channels at once: h_in [n_channels][in_size],
+ * h_out [n_channels][out_size] interleaved complex.  The reference's two pseudo-rings (create_iobuffs, iobuffs.c:385-420)
+ * and its ring arithmetic are reproduced, with the DSP thread's turns (dexchange + xrxa, main.c:40-63) run inside the
+ * call: any in_size / dsp_insize ratio (several DSP turns per call, or several calls per turn), the two-DSP-buffer
+ * latency, the up-slew on the way in and the down-slew on the way out.  *error = 0, or -2 with zeros returned when no
+ * output is available (bfo = 0 before the rings have filled).  When the exchange is off (SetChannelState(0) finished)
+ * the call returns at once and leaves h_out alone, as the reference does. */
 int quisk_cuda_rxa_fexchange0(qcRxa *r, const double *h_in, double *h_out, int *error);
+/* SetChannelState (channel.c:262-300) for the batch; returns the prior state.  state 0: the following exchange calls
+ * run downslew0 (tdelaydown of signal, a raised-cosine ramp over tslewdown, out_size + 1 zeros), then the exchange
+ * switches off and the channel is flushed (flush_iobuffs + flush_rxa: note that flush_wcpagc and flush_amd keep
+ * their loop state, as in the reference).  state 1: upflag up, exchange on. */
+int quisk_cuda_rxa_set_channel_state(qcRxa *r, int state, int dmode);
+int quisk_cuda_rxa_set_slew_down(qcRxa *r, double tdelaydown, double tslewdown);    /* OpenChannel's tdelaydown / tslewdown */
+int quisk_cuda_rxa_set_bfo(qcRxa *r, int bfo);                                      /* OpenChannel's bfo (block for output) */
+int quisk_cuda_rxa_exchange_sizes(const qcRxa *r, int *in_size, int *out_size);
 /* meters (wdsp/meter.c:75-107): which = 0 ADC, 1 S, 2 AGC; av/pk/gain in dB, HOST arrays of n_channels (any may be NULL) */
 int quisk_cuda_rxa_get_meter(qcRxa *r, int which, double *av, double *pk, double *gain);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The reference's own WDSP entry points, by channel number (wdsp_compat.cu): the symbols quisk_wdsp.py resolves in
+ * libwdsp.so (quisk_wdsp.py:28-99, quisk.py:6017-6053) with the exact signatures of wdsp/channel.c:76, iobuffs.c:464,
+ * version.c:4, RXA.c:749-958, shift.c:112-128, nbp.c:359-527, wcpAGC.c:370-548, patchpanel.c:125-156, amd.c:279-293,
+ * meter.c:120, siphon.c:183-211 -- `ctypes.CDLL("libquisk_cuda.so")` in place of "./wdsp/libwdsp.so" (INTEGRATION.md
+ * section 2).  One single-channel chain per open channel number, MAX_CHANNELS = 32.  The stages this library does not
+ * build (squelches, EMNR, SNBA, ANF, ANR) are accepted switched off and refused with a message when switched on.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int GetWDSPVersion(void);
+void OpenChannel(int channel, int in_size, int dsp_size, int input_samplerate, int dsp_rate, int output_samplerate,
+                 int type, int state, double tdelayup, double tslewup, double tdelaydown, double tslewdown, int bfo);
+void CloseChannel(int channel);
+int SetChannelState(int channel, int state, int dmode);
+void fexchange0(int channel, double *in, double *out, int *error);
+void SetRXAMode(int channel, int mode);
+void RXASetPassband(int channel, double f_low, double f_high);
+void RXASetNC(int channel, int nc);
+void RXASetMP(int channel, int mp);
+void SetRXAShiftRun(int channel, int run);
+void SetRXAShiftFreq(int channel, double fshift);
+void RXANBPSetRun(int channel, int run);
+void RXANBPSetFreqs(int channel, double flow, double fhigh);
+int RXANBPAddNotch(int channel, int notch, double fcenter, double fwidth, int active);
+int RXANBPDeleteNotch(int channel, int notch);
+void RXANBPGetNumNotches(int channel, int *nnotches);
+void RXANBPSetNotchesRun(int channel, int run);
+void RXANBPSetTuneFrequency(int channel, double tunefreq);
+void RXANBPSetShiftFrequency(int channel, double shift);
+void SetRXAAGCMode(int channel, int mode);
+void SetRXAAGCFixed(int channel, double fixed_agc);
+void SetRXAAGCTop(int channel, double max_agc);
+void SetRXAPanelRun(int channel, int run);
+void SetRXAPanelGain1(int channel, double gain);
+void SetRXAPanelGain2(int channel, double gainI, double gainQ);
+void SetRXAAMDSBMode(int channel, int sbmode);
+void SetRXAAMDFadeLevel(int channel, int levelfade);
+double GetRXAMeter(int channel, int mt);
+void RXAGetaSipF(int channel, float *out, int size);
+void RXAGetaSipF1(int channel, float *out, int size);
+void SetRXAAMSQRun(int channel, int run);
+void SetRXAFMSQRun(int channel, int run);
+void SetRXAEMNRRun(int channel, int run);
+void SetRXAEMNRgainMethod(int channel, int method);
+void SetRXASNBARun(int channel, int run);
+void SetRXAANFRun(int channel, int run);
+void SetRXAANRRun(int channel, int run);
+/* Quisk's side of the boundary: wdspFexchange0 (quisk_wdsp.c:24-73: arbitrary sample counts, 1 / CLIP32 scaling,
+ * re-blocking to in_size, returns the count now in cSamples) and the C half of quisk_wdsp_set_parameter
+ * (quisk_wdsp.c:75-92; in_size <= 0 / in_use < 0: leave alone). */
+int wdspFexchange0(int channel, quisk_cd *cSamples, int nSamples);
+void quisk_cuda_wdsp_set_parameter(int channel, int in_size, int in_use);
 
 #ifdef __cplusplus
 }

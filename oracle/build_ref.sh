@@ -9,7 +9,9 @@
 #
 #   _ref/libquisk_filter_ref.so  filter.c, verbatim (all 17 filter.h functions + filters.h tables)
 #   _ref/libquisk_rx_ref.so      filter.c + the static RX functions of quisk.c (see ref_wrap/quisk_rx_wrap.c)
+#   _ref/libquisk_rx_ref_O3.so   the same at -O3: what bench.py times as the CPU reference
 #   _ref/libquisk_rx_dropin.so   the same RX functions of quisk.c linked against quisk_b200/libquisk_cuda.so instead of filter.c
+#   _ref/libquisk_wdspglue_ref.so  wdspFexchange0 of quisk_wdsp.c (the re-blocker in front of fexchange0)
 #   _ref/libwdsp_ref.so          wdsp/*.c (minus the make_*.c table generators) + our FFTW-API shim
 #
 # Flags: -O2 for the Quisk sources (setuptools default), -O3 for WDSP
@@ -43,6 +45,11 @@ sed -n '3746,3763p' "$REF/quisk.c" > "$TMP/quisk_unpack_hermes.inc"      # read_
 gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" -I"$HERE/fftw_shim" "$HERE/ref_wrap/quisk_rx_wrap.c" "$REF/filter.c" \
     "$HERE/fftw_shim/fftw_shim.c" "$HERE/fft64.c" -o "$OUT/libquisk_rx_ref.so" -lm
 
+# 2a. The timing arm of bench.py uses an -O3 build of the same sources (the fixtures stay on the
+#     setuptools default -O2 above -- without -ffast-math the two produce the same doubles, tests/test_oracle_vs_ref.py checks it)
+gcc -O3 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" -I"$HERE/fftw_shim" "$HERE/ref_wrap/quisk_rx_wrap.c" "$REF/filter.c" \
+    "$HERE/fftw_shim/fftw_shim.c" "$HERE/fft64.c" -o "$OUT/libquisk_rx_ref_O3.so" -lm
+
 # 2b. The same wrapper TU linked against libquisk_cuda.so INSTEAD of filter.c: the reference's own orchestrator code
 #     (quisk_process_decimate / quisk_process_demodulate, unmodified) calling the GPU filter.h drop-in.  This is the
 #     swap-in of INTEGRATION.md section 1 in miniature; filters.h (the coefficient tables filter.c used to emit) is
@@ -53,6 +60,10 @@ if [ -f "$CUDALIB" ]; then
     gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" -I"$HERE/fftw_shim" "$HERE/ref_wrap/quisk_rx_wrap.c" "$TMP/filters_data.c" \
         "$HERE/fftw_shim/fftw_shim.c" "$HERE/fft64.c" -o "$OUT/libquisk_rx_dropin.so" -L"$HERE/../quisk_b200" -lquisk_cuda -Wl,-rpath,'$ORIGIN/../../quisk_b200' -lm
 fi
+
+# 2c. Quisk's side of the WDSP boundary: wdspFexchange0 (quisk_wdsp.c:7-69) through its own wrapper TU
+sed -n '7,69p' "$REF/quisk_wdsp.c" > "$TMP/quisk_wdsp_glue.inc"
+gcc -O2 -fPIC -shared -w -I"$TMP" "$HERE/ref_wrap/quisk_wdsp_wrap.c" -o "$OUT/libquisk_wdspglue_ref.so" -lm
 
 # 3. WDSP against the FFTW shim
 WSRC=$(ls "$REF"/wdsp/*.c | grep -v '/make_')

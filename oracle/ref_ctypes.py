@@ -18,6 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
 c_double_p = C.POINTER(C.c_double)
+_private_seq = 0
+_private_lock = __import__("threading").Lock()
 
 
 class cFilter(C.Structure):          # struct quisk_cFilter, filter.h:1-10
@@ -70,12 +72,22 @@ def load(name: str, private_copy: bool = False) -> C.CDLL:
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path}: run oracle/build_ref.sh (needs /root/reference)")
     if private_copy:
-        fd, tmp = tempfile.mkstemp(suffix=".so")
-        os.close(fd)
-        shutil.copy(path, tmp)
-        lib = C.CDLL(tmp)
-        os.unlink(tmp)
-        return lib
+        # A distinct path gives a distinct dlopen handle with its own statics.  The copies stay on disk under
+        # oracle/_ref/private/ (git-ignored with the rest of oracle/_ref) instead of being unlinked, so that whoever
+        # audits which native code a process loaded (/proc/<pid>/maps) sees the reference library by name.
+        global _private_seq
+        pdir = os.path.join(REF_DIR, "private")
+        os.makedirs(pdir, exist_ok=True)
+        with _private_lock:
+            k = _private_seq
+            _private_seq += 1
+        dst = os.path.join(pdir, "%s.%d.so" % (name[:-3], k))
+        st = os.stat(path)
+        if not (os.path.exists(dst) and os.path.getsize(dst) == st.st_size and os.path.getmtime(dst) >= st.st_mtime):
+            tmp = "%s.%d.tmp" % (dst, os.getpid())
+            shutil.copy(path, tmp)
+            os.replace(tmp, dst)
+        return C.CDLL(dst)
     return C.CDLL(path)
 
 

@@ -56,6 +56,7 @@ struct SeqStage {
     int init_common(int kind, int C, int state_doubles);
     void release();
     int flush();
+    int flush_ref();                // what the reference's own flush_<stage> resets (less than a fresh object for wcpagc / amd)
     int run(const void *d_in, long in_stride, void *d_out, long out_stride, int n, cudaStream_t s);
     void load_agc();
 };
@@ -68,7 +69,67 @@ SeqStage *make_snotch(int C, int rate, double f, double bw);
 SeqStage *make_meter(int C, int rate, double tau_av, double tau_decay);
 void agc_set_mode(SeqStage *s, int mode);
 
+// The RXA chain for a batch of channels (wdsp_rxa.cu); wdsp_compat.cu maps WDSP's channel numbers onto these.
+struct Rxa {
+    int C = 0, in_size = 0, dsp_size = 0, in_rate = 0, dsp_rate = 0, out_rate = 0;
+    int dsp_insize = 0, dsp_outsize = 0, out_size = 0;
+    int mode = QC_RXA_LSB;
+    // shift
+    int shift_run = 1; bool shift_nonzero = false; SeqStage *shift = nullptr;
+    Resampler *rsmpin = nullptr, *rsmpout = nullptr;
+    SeqStage *adcmeter = nullptr, *smeter = nullptr, *agcmeter = nullptr;
+    // nbp0
+    int nbp_run = 1, nbp_nc = 0; double nbp_flow = -4150.0, nbp_fhigh = -150.0; FirCore *nbp0 = nullptr;
+    // notch database (create_notchdb, RXA.c:85-87; nbp.c:34-47): shared by the batch like every other setting
+    int ndb_run = 0; double ndb_tune = 0.0, ndb_shift = 0.0; int nbp_hadnotch = 0;
+    std::vector<double> ndb_fcenter, ndb_fwidth; std::vector<int> ndb_active;
+    int nbp0_impulse(std::vector<double> &imp, int *havnotch);
+    // amd / fmd
+    int amd_run = 0, amd_mode = 0; SeqStage *amd = nullptr;
+    int fmd_run = 0, fm_nc_de = 0, fm_nc_aud = 0; SeqStage *fmpll = nullptr, *sntch = nullptr; FirCore *pde = nullptr, *paud = nullptr;
+    // bp1
+    int bp1_run = 1, bp1_nc = 0; double bp1_flow = -4150.0, bp1_fhigh = -150.0, bp1_gain = 1.0; FirCore *bp1 = nullptr;
+    // agc, panel
+    int agc_run = 1; SeqStage *agc = nullptr;
+    double panel_gain1 = 4.0, panel_gain2I = 1.0, panel_gain2Q = 1.0;
+    // buffers
+    cd *mid = nullptr, *mid2 = nullptr, *audio = nullptr;
+    // fexchange0 emulation: up-slew state per channel (iobuffs.c:47-160): [C][3] = ustate, ucount, upflag
+    int ndelup = 0, ntup = 0; int *d_uslew = nullptr; double *d_cup = nullptr;
+    // sip1 (create_rxa, RXA.c:392-401: run 1, position 0, mode 0, 4096 samples): ring per channel, filled by the panel kernel
+    int sip_run = 1, sipsize = 4096, sip_idx = 0; cd *d_sip = nullptr; float *d_sipout = nullptr; int sipout_cap = 0;
+    int arm_upslew(double tdelayup, double tslewup);
+    // fexchange0 / dexchange emulation (iobuffs.c:385-604): the two pseudo-rings r1 (caller -> DSP) and r2 (DSP -> caller)
+    // live on the device, [C][DSP_MULT * size]; the ring arithmetic (indices, unqueued counts, the Sem_OutReady credit
+    // count) is the reference's, run on the host -- the DSP "thread" is executed synchronously inside the exchange call,
+    // which is the schedule the reference follows when its caller is paced by a sound card.
+    int bfo = 1, exchange_on = 1, state = 1;
+    double tdelayup = 0.0, tslewup = 0.0, tdelaydown = 0.0, tslewdown = 0.0;
+    int r1_size = 0, r2_size = 0, r1_active = 0, r2_active = 0;
+    int r1_inidx = 0, r1_outidx = 0, r1_unq = 0, r2_inidx = 0, r2_outidx = 0, r2_havesamps = 0, r2_unq = 0, out_credits = 0;
+    cd *d_r1 = nullptr, *d_r2 = nullptr, *d_outbuff = nullptr, *d_xout = nullptr; double *d_gain = nullptr;
+    cudaStream_t hs = nullptr;
+    // down-slew (downslew0, iobuffs.c:226-300): data independent, so the state machine runs on the host and hands the
+    // kernel one gain per output sample
+    int downflag = 0, flushflag = 0, dstate = 0, dcount = 0, ndeldown = 0, ntdown = 0;
+    std::vector<double> cdown;
+    int setup_exchange();
+    int flush_iobuffs();
+    int flush_main();                        // flush_rxa (RXA.c:527-559) with the reference's (partial) per-stage flushes
+    int exchange(const double *h_in, double *h_out, int *error);
+    int set_channel_state(int new_state, int dmode);
+
+    int init(int C, int in_size, int dsp_size, int in_rate, int dsp_rate, int out_rate);
+    void release();
+    int make_nbp0();
+    int make_bp1();
+    int make_fmd();
+    int xrxa(const void *din, long is, void *dout, long os, cudaStream_t s);
+};
+
 int launch_panel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C, double gainI, double gainQ,
                  int inselect, int copy, cudaStream_t s, cd *sip = nullptr, int sipsize = 0, int sip_idx = 0);
 
 }  // namespace qc
+
+struct qcRxa { qc::Rxa r; };       // the opaque handle of include/quisk_cuda_wdsp.h

@@ -13,44 +13,6 @@
 
 namespace qc {
 
-struct Rxa {
-    int C = 0, in_size = 0, dsp_size = 0, in_rate = 0, dsp_rate = 0, out_rate = 0;
-    int dsp_insize = 0, dsp_outsize = 0, out_size = 0;
-    int mode = QC_RXA_LSB;
-    // shift
-    int shift_run = 1; bool shift_nonzero = false; SeqStage *shift = nullptr;
-    Resampler *rsmpin = nullptr, *rsmpout = nullptr;
-    SeqStage *adcmeter = nullptr, *smeter = nullptr, *agcmeter = nullptr;
-    // nbp0
-    int nbp_run = 1, nbp_nc = 0; double nbp_flow = -4150.0, nbp_fhigh = -150.0; FirCore *nbp0 = nullptr;
-    // notch database (create_notchdb, RXA.c:85-87; nbp.c:34-47): shared by the batch like every other setting
-    int ndb_run = 0; double ndb_tune = 0.0, ndb_shift = 0.0; int nbp_hadnotch = 0;
-    std::vector<double> ndb_fcenter, ndb_fwidth; std::vector<int> ndb_active;
-    int nbp0_impulse(std::vector<double> &imp, int *havnotch);
-    // amd / fmd
-    int amd_run = 0, amd_mode = 0; SeqStage *amd = nullptr;
-    int fmd_run = 0, fm_nc_de = 0, fm_nc_aud = 0; SeqStage *fmpll = nullptr, *sntch = nullptr; FirCore *pde = nullptr, *paud = nullptr;
-    // bp1
-    int bp1_run = 1, bp1_nc = 0; double bp1_flow = -4150.0, bp1_fhigh = -150.0, bp1_gain = 1.0; FirCore *bp1 = nullptr;
-    // agc, panel
-    int agc_run = 1; SeqStage *agc = nullptr;
-    double panel_gain1 = 4.0, panel_gain2I = 1.0, panel_gain2Q = 1.0;
-    // buffers
-    cd *mid = nullptr, *mid2 = nullptr, *audio = nullptr;
-    // fexchange0 emulation: up-slew state per channel (iobuffs.c:47-160): [C][3] = ustate, ucount, upflag
-    int ndelup = 0, ntup = 0; int *d_uslew = nullptr; double *d_cup = nullptr;
-    // sip1 (create_rxa, RXA.c:392-401: run 1, position 0, mode 0, 4096 samples): ring per channel, filled by the panel kernel
-    int sip_run = 1, sipsize = 4096, sip_idx = 0; cd *d_sip = nullptr; float *d_sipout = nullptr; int sipout_cap = 0;
-    int arm_upslew(double tdelayup, double tslewup);
-    cd *d_in = nullptr, *d_out = nullptr; double *h_ring = nullptr; int ring_blocks = 0, ring_pos = 0; cudaStream_t hs = nullptr;
-
-    int init(int C, int in_size, int dsp_size, int in_rate, int dsp_rate, int out_rate);
-    void release();
-    int make_nbp0();
-    int make_bp1();
-    int make_fmd();
-    int xrxa(const void *din, long is, void *dout, long os, cudaStream_t s);
-};
 
 // upslew0 (iobuffs.c:98-160), one thread per channel, in place on the block about to enter the DSP chain: zeros until
 // the first non-zero sample (which is swallowed too), ndelup more zeros, a raised-cosine ramp of ntup + 1 samples,
@@ -95,6 +57,7 @@ __global__ void upslew_kernel(cd *x, long stride, int n, int C, int *st, const d
 
 int Rxa::arm_upslew(double tdelayup, double tslewup)
 {   // create_slews / flush_slews + the upflag OpenChannel and SetChannelState(1) raise (iobuffs.c:47-96, channel.c:95,291)
+    this->tdelayup = tdelayup; this->tslewup = tslewup;
     ndelup = (int)(tdelayup * in_rate);
     ntup = (int)(tslewup * in_rate);
     std::vector<double> cup((size_t)ntup + 1);
@@ -199,7 +162,18 @@ int Rxa::init(int C_, int in_size_, int dsp_size_, int in_rate_, int dsp_rate_, 
     if (!shift || !adcmeter || !smeter || !agcmeter || !amd || !fmpll || !sntch || !agc) return QC_EINVAL;
     QC_CUDA(cudaMalloc((void **)&d_sip, (size_t)C * sipsize * sizeof(cd)));
     QC_CUDA(cudaMemset(d_sip, 0, (size_t)C * sipsize * sizeof(cd)));
-    return arm_upslew(0.0, 0.0);
+    int rcu = arm_upslew(0.0, 0.0); if (rcu != QC_OK) return rcu;
+    return setup_exchange();
+}
+
+static int raise_upflag(Rxa &r)
+{   // InterlockedBitTestAndSet(&slew.upflag) of OpenChannel / SetChannelState(1) (channel.c:95, 291)
+    std::vector<int> st((size_t)r.C * 3, 0);
+    if (r.hs) QC_CUDA(cudaStreamSynchronize(r.hs));
+    QC_CUDA(cudaMemcpy(st.data(), r.d_uslew, st.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < r.C; c++) st[(size_t)c * 3 + 2] = 1;
+    QC_CUDA(cudaMemcpy(r.d_uslew, st.data(), st.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return QC_OK;
 }
 
 void Rxa::release()
@@ -208,12 +182,15 @@ void Rxa::release()
     for (FirCore **p : {&nbp0, &bp1, &pde, &paud}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     for (Resampler **p : {&rsmpin, &rsmpout}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     if (mid) cudaFree(mid); if (mid2) cudaFree(mid2); if (audio) cudaFree(audio);
-    if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out); if (h_ring) free(h_ring);
+    if (d_r1) cudaFree(d_r1); if (d_r2) cudaFree(d_r2); if (d_outbuff) cudaFree(d_outbuff); if (d_xout) cudaFree(d_xout);
+    if (d_gain) cudaFree(d_gain);
+    d_r1 = d_r2 = d_outbuff = d_xout = nullptr; d_gain = nullptr;
+    if (hs) { cudaStreamSynchronize(hs); cudaStreamDestroy(hs); hs = nullptr; }
     if (d_uslew) cudaFree(d_uslew); if (d_cup) cudaFree(d_cup);
     d_uslew = nullptr; d_cup = nullptr;
     if (d_sip) cudaFree(d_sip); if (d_sipout) cudaFree(d_sipout);
     d_sip = nullptr; d_sipout = nullptr; sipout_cap = 0;
-    mid = mid2 = audio = d_in = d_out = nullptr; h_ring = nullptr;
+    mid = mid2 = audio = nullptr;
 }
 
 int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
@@ -267,10 +244,192 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
     return QC_OK;
 }
 
+// ---- fexchange0 / dexchange / slews / SetChannelState (iobuffs.c, channel.c:262-300) --------------------------------
+enum { D_BEGIN = 0, D_DELAYDOWN = 4, D_DOWNSLEW = 5, D_ZERO = 6, D_OFF = 7 };
+
+__global__ void downslew_kernel(const cd *r2, long r2_stride, cd *out, long out_stride, int n, int C, const double *gain)
+{
+    const long total = (long)n * C;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(t / n), i = (int)(t - (long)c * n);
+        const cd v = r2[(size_t)c * r2_stride + i];
+        const double g = gain[i];
+        out[(size_t)c * out_stride + i] = g == 0.0 ? make_double2(0.0, 0.0) : make_double2(v.x * g, v.y * g);
+    }
+}
+
+int Rxa::setup_exchange()
+{   // create_iobuffs + create_slews (iobuffs.c:47-80, 385-420)
+    r1_size = dsp_insize > in_size ? dsp_insize : in_size;
+    r2_size = out_size > dsp_outsize ? out_size : dsp_outsize;
+    r1_active = 2 * r1_size; r2_active = 2 * r2_size;          // DSP_MULT = 2 (comm.h:118)
+    if (in_size <= 0 || out_size <= 0 || r1_active % in_size || r1_active % dsp_insize || r2_active % out_size || r2_active % dsp_outsize) {
+        set_error("rxa: in_size %d / dsp_insize %d / out_size %d / dsp_outsize %d do not tile the exchange rings", in_size, dsp_insize, out_size, dsp_outsize);
+        return QC_EINVAL;
+    }
+    if (!hs) QC_CUDA(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
+    for (cd **q : {&d_r1, &d_r2, &d_outbuff, &d_xout}) if (*q) { cudaFree(*q); *q = nullptr; }
+    if (d_gain) { cudaFree(d_gain); d_gain = nullptr; }
+    QC_CUDA(cudaMalloc((void **)&d_r1, (size_t)C * r1_active * sizeof(cd)));
+    QC_CUDA(cudaMalloc((void **)&d_r2, (size_t)C * r2_active * sizeof(cd)));
+    QC_CUDA(cudaMalloc((void **)&d_outbuff, (size_t)C * dsp_outsize * sizeof(cd)));
+    QC_CUDA(cudaMalloc((void **)&d_xout, (size_t)C * out_size * sizeof(cd)));
+    QC_CUDA(cudaMalloc((void **)&d_gain, (size_t)out_size * sizeof(double)));
+    QC_CUDA(cudaMemset(d_outbuff, 0, (size_t)C * dsp_outsize * sizeof(cd)));
+    ndeldown = (int)(tdelaydown * out_rate);
+    ntdown = (int)(tslewdown * out_rate);
+    cdown.assign((size_t)ntdown + 1, 0.0);
+    const double delta = 3.1415926535897932 / (double)ntdown;
+    double theta = 0.0;
+    for (int i = 0; i <= ntdown; i++) { cdown[i] = 0.5 * (1 + cos(theta)); theta += delta; }
+    int rc = flush_iobuffs(); if (rc != QC_OK) return rc;
+    return state ? raise_upflag(*this) : QC_OK;                     // OpenChannel, channel.c:93-99
+}
+
+int Rxa::flush_iobuffs()
+{   // flush_iobuffs (iobuffs.c:442-461) + flush_slews
+    QC_CUDA(cudaMemset(d_r1, 0, (size_t)C * r1_active * sizeof(cd)));
+    QC_CUDA(cudaMemset(d_r2, 0, (size_t)C * r2_active * sizeof(cd)));
+    r1_inidx = r1_outidx = r1_unq = 0;
+    r2_inidx = r2_size; r2_outidx = 0; r2_havesamps = r2_size;      // (DSP_MULT - 1) * r2_size
+    out_credits = r2_havesamps / out_size;
+    r2_unq = r2_havesamps - out_credits * out_size;
+    dstate = D_BEGIN; dcount = 0; downflag = 0;
+    // up-slew: states back to BEGIN, flags down (SetChannelState(1) / OpenChannel raise them)
+    if (d_uslew) QC_CUDA(cudaMemset(d_uslew, 0, (size_t)C * 3 * sizeof(int)));
+    return QC_OK;
+}
+
+int Rxa::flush_main()
+{   // flush_rxa, RXA.c:527-559: inbuff / outbuff / midbuff zeroed, then every stage's own flush
+    QC_CUDA(cudaDeviceSynchronize());
+    QC_CUDA(cudaMemset(d_outbuff, 0, (size_t)C * dsp_outsize * sizeof(cd)));
+    int rc;
+    for (SeqStage *q : {shift, adcmeter, smeter, amd, fmpll, sntch, agc, agcmeter}) if (q) { rc = q->flush_ref(); if (rc) return rc; }
+    for (FirCore *f : {nbp0, pde, paud, bp1}) if (f) { rc = f->flush(); if (rc) return rc; }
+    for (Resampler *q : {rsmpin, rsmpout}) if (q) { rc = q->f->reset(nullptr); if (rc) return rc; }
+    QC_CUDA(cudaMemset(d_sip, 0, (size_t)C * sipsize * sizeof(cd)));
+    sip_idx = 0;
+    QC_CUDA(cudaDeviceSynchronize());
+    return QC_OK;
+}
+
+int Rxa::set_channel_state(int new_state, int dmode)
+{   // SetChannelState, channel.c:262-300.  Returns the prior state.  dmode = 1 waits for the down-slew to finish in the
+    // reference (another thread keeps calling fexchange0) and gives up after 100 ms; a single-threaded caller always
+    // takes that give-up branch there: exchange off, no flush.  Here the exchange calls are synchronous, so with
+    // dmode = 1 the same give-up branch is taken at once.
+    const int prior = state;
+    if (state == new_state) return prior;
+    state = new_state;
+    if (new_state == 0) {
+        downflag = 1; flushflag = 1;
+        if (dmode) { exchange_on = 0; flushflag = 0; downflag = 0; }
+    } else {
+        // upflag up; ustate / ucount stay where flush_slews (or the last finished ramp) left them: BEGIN
+        int rc = raise_upflag(*this); if (rc != QC_OK) return rc;
+        exchange_on = 1;
+    }
+    return prior;
+}
+
+int Rxa::exchange(const double *h_in, double *h_out, int *error)
+{
+    if (error) *error = 0;
+    if (!exchange_on) return QC_OK;                                // iobuffs.c:471: nothing moves, `out` is left alone
+    if (!d_r1) { int rc = setup_exchange(); if (rc) return rc; }
+    // in -> r1 (through upslew0 while a channel's upflag is up; the kernel returns at once for the others)
+    cd *slot = d_r1 + r1_inidx;
+    QC_CUDA(cudaMemcpy2DAsync(slot, (size_t)r1_active * sizeof(cd), h_in, (size_t)in_size * sizeof(cd), (size_t)in_size * sizeof(cd), C,
+                              cudaMemcpyHostToDevice, hs));
+    upslew_kernel<<<(C + 63) / 64, 64, 0, hs>>>(slot, r1_active, in_size, C, d_uslew, d_cup, ndelup, ntup);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    int n_dsp = 0;
+    if ((r1_unq += in_size) >= dsp_insize) { n_dsp = r1_unq / dsp_insize; r1_unq -= n_dsp * dsp_insize; }
+    if ((r1_inidx += in_size) == r1_active) r1_inidx = 0;
+    // the DSP thread's turns (wdspmain, main.c:40-63): dexchange pushes the PREVIOUS outbuff into r2 and pulls the next
+    // dsp_insize samples out of r1, then xrxa runs
+    for (int k = 0; k < n_dsp; k++) {
+        r2_havesamps += dsp_outsize;
+        QC_CUDA(cudaMemcpy2DAsync(d_r2 + r2_inidx, (size_t)r2_active * sizeof(cd), d_outbuff, (size_t)dsp_outsize * sizeof(cd),
+                                  (size_t)dsp_outsize * sizeof(cd), C, cudaMemcpyDeviceToDevice, hs));
+        if ((r2_inidx += dsp_outsize) == r2_active) r2_inidx = 0;
+        if (bfo && (r2_unq += dsp_outsize) >= out_size) { const int n = r2_unq / out_size; out_credits += n; r2_unq -= n * out_size; }
+        int rc = xrxa(d_r1 + r1_outidx, r1_active, d_outbuff, dsp_outsize, hs); if (rc) return rc;
+        if ((r1_outidx += dsp_insize) == r1_active) r1_outidx = 0;
+    }
+    const int doit = r2_havesamps >= out_size;
+    if ((r2_havesamps -= out_size) < 0) r2_havesamps = 0;
+    bool have = doit;
+    if (bfo) {      // WaitForSingleObject(Sem_OutReady): the DSP turns above have already run, so a missing credit can never arrive
+        have = out_credits > 0;
+        if (have) out_credits--;
+    }
+    const size_t nout = (size_t)C * out_size;
+    if (have) {
+        if (downflag) {
+            std::vector<double> g((size_t)out_size);
+            for (int i = 0; i < out_size; i++) {                    // downslew0, iobuffs.c:226-300
+                switch (dstate) {
+                case D_BEGIN:
+                    g[i] = 1.0;
+                    if (ndeldown > 0) { dstate = D_DELAYDOWN; dcount = ndeldown; }
+                    else if (ntdown > 0) { dstate = D_DOWNSLEW; dcount = ntdown; }
+                    else { dstate = D_ZERO; dcount = out_size; }
+                    break;
+                case D_DELAYDOWN:
+                    g[i] = 1.0;
+                    if (dcount-- == 0) {
+                        if (ntdown > 0) { dstate = D_DOWNSLEW; dcount = ntdown; }
+                        else { dstate = D_ZERO; dcount = out_size; }
+                    }
+                    break;
+                case D_DOWNSLEW:
+                    g[i] = cdown[(size_t)(ntdown - dcount)];
+                    if (dcount-- == 0) { dstate = D_ZERO; dcount = out_size; }
+                    break;
+                case D_ZERO:
+                    g[i] = 0.0;
+                    if (dcount-- == 0) dstate = D_OFF;
+                    break;
+                default:
+                    g[i] = 0.0;
+                    if (i == out_size - 1) { dstate = D_BEGIN; downflag = 0; }
+                    break;
+                }
+            }
+            QC_CUDA(cudaMemcpyAsync(d_gain, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, hs));
+            const long total = (long)nout;
+            downslew_kernel<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, hs>>>(d_r2 + r2_outidx, r2_active, d_xout, out_size, out_size, C, d_gain);
+            count_launch();
+            QC_CUDA_LAUNCH();
+            QC_CUDA(cudaMemcpyAsync(h_out, d_xout, nout * sizeof(cd), cudaMemcpyDeviceToHost, hs));
+            QC_CUDA(cudaStreamSynchronize(hs));                     // g goes out of scope
+            if (!downflag) {                                        // ramp finished: exchange off, the flush thread's work (channel.c:134-155)
+                exchange_on = 0;
+                if ((r2_outidx += out_size) == r2_active) r2_outidx = 0;
+                int rc = flush_iobuffs(); if (rc) return rc;
+                rc = flush_main(); if (rc) return rc;
+                flushflag = 0;
+                return QC_OK;
+            }
+        } else {
+            QC_CUDA(cudaMemcpy2DAsync(h_out, (size_t)out_size * sizeof(cd), d_r2 + r2_outidx, (size_t)r2_active * sizeof(cd),
+                                      (size_t)out_size * sizeof(cd), C, cudaMemcpyDeviceToHost, hs));
+        }
+    } else {
+        memset(h_out, 0, nout * sizeof(cd));
+        if (error) *error += -2;
+    }
+    if ((r2_outidx += out_size) == r2_active) r2_outidx = 0;
+    QC_CUDA(cudaStreamSynchronize(hs));
+    return QC_OK;
+}
+
 }  // namespace qc
 
 using namespace qc;
-struct qcRxa { qc::Rxa r; };
 
 extern "C" {
 
@@ -478,35 +637,24 @@ int quisk_cuda_rxa_xrxa(qcRxa *p, const void *d_in, long in_stride, void *d_out,
 { return p ? p->r.xrxa(d_in, in_stride, d_out, out_stride, (cudaStream_t)stream) : QC_EINVAL; }
 
 int quisk_cuda_rxa_fexchange0(qcRxa *p, const double *h_in, double *h_out, int *error)
-{   // iobuffs.c:464-516 with in_size == dsp_insize: r2 starts with (DSP_MULT - 1) buffers of zeros
-    // (iobuffs.c:409-413) and dexchange pushes the PREVIOUS outbuff before xrxa runs (iobuffs.c:583-604),
-    // so the block returned now is the one computed two calls ago.
+{   // fexchange0 (iobuffs.c:464-516) for every channel of the batch: h_in [C][in_size], h_out [C][out_size]
     if (!p) return QC_EINVAL;
-    Rxa &r = p->r;
-    if (error) *error = 0;
-    if (r.in_size != r.dsp_insize) { set_error("rxa_fexchange0: in_size must equal dsp_insize in this version"); return QC_EINVAL; }
-    const size_t nin = (size_t)r.C * r.dsp_insize, nout = (size_t)r.C * r.dsp_outsize;
-    if (!r.d_in) {
-        QC_CUDA(cudaMalloc((void **)&r.d_in, nin * sizeof(cd)));
-        QC_CUDA(cudaMalloc((void **)&r.d_out, nout * sizeof(cd)));
-        QC_CUDA(cudaStreamCreateWithFlags(&r.hs, cudaStreamNonBlocking));
-        r.ring_blocks = 2;
-        r.h_ring = (double *)calloc(nout * 2 * r.ring_blocks, sizeof(double));
-        r.ring_pos = 0;
-    }
-    QC_CUDA(cudaMemcpyAsync(r.d_in, h_in, nin * sizeof(cd), cudaMemcpyHostToDevice, r.hs));
-    // up-slew on the block as it enters r1 (iobuffs.c:475-476); channels whose flag has dropped return at once
-    upslew_kernel<<<(r.C + 63) / 64, 64, 0, r.hs>>>(r.d_in, r.dsp_insize, r.dsp_insize, r.C, r.d_uslew, r.d_cup, r.ndelup, r.ntup);
-    count_launch();
-    QC_CUDA_LAUNCH();
-    int rc = r.xrxa(r.d_in, r.dsp_insize, r.d_out, r.dsp_outsize, r.hs); if (rc) return rc;
-    double *slot = r.h_ring + (size_t)r.ring_pos * nout * 2;
-    memcpy(h_out, slot, nout * sizeof(cd));                       // the block from two calls ago (zeros at first)
-    QC_CUDA(cudaMemcpyAsync(slot, r.d_out, nout * sizeof(cd), cudaMemcpyDeviceToHost, r.hs));
-    QC_CUDA(cudaStreamSynchronize(r.hs));
-    r.ring_pos = (r.ring_pos + 1) % r.ring_blocks;
-    return QC_OK;
+    return p->r.exchange(h_in, h_out, error);
 }
+
+int quisk_cuda_rxa_set_channel_state(qcRxa *p, int state, int dmode)
+{ return p ? p->r.set_channel_state(state, dmode) : QC_EINVAL; }
+
+int quisk_cuda_rxa_set_slew_down(qcRxa *p, double tdelaydown, double tslewdown)
+{
+    if (!p || tdelaydown < 0 || tslewdown < 0) return QC_EINVAL;
+    p->r.tdelaydown = tdelaydown; p->r.tslewdown = tslewdown;
+    return p->r.setup_exchange();
+}
+
+int quisk_cuda_rxa_set_bfo(qcRxa *p, int bfo) { if (!p) return QC_EINVAL; p->r.bfo = bfo ? 1 : 0; return QC_OK; }
+int quisk_cuda_rxa_exchange_sizes(const qcRxa *p, int *in_size, int *out_size)
+{ if (!p) return QC_EINVAL; if (in_size) *in_size = p->r.in_size; if (out_size) *out_size = p->r.out_size; return QC_OK; }
 
 int quisk_cuda_rxa_get_meter(qcRxa *p, int which, double *av, double *pk, double *gain)
 {

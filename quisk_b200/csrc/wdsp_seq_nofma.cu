@@ -360,8 +360,30 @@ __global__ void snotch_kernel(const cd *in, long is, cd *out, long os, int n, in
     SEQ_STAGE_OUT();
 }
 
+// mlog10 (wdsp/meterlog10.c:547-554): WDSP's meters do not call log10 -- they take the exponent and an 11-bit table
+// look-up of log2(1 + m / 2048) on the leading mantissa bits, no interpolation, so a meter reads up to 2.1e-3 dB low.
+// Part of the reference's observable behaviour (GetRXAMeter).  The table is rebuilt here from its definition
+// (log10(x) / log10(2) reproduces 2045 of the reference's 2048 entries exactly, the other three to one ulp).
+__device__ double g_mtable[2048];
+static std::once_flag g_mtable_once;
+static void mtable_init()
+{
+    std::call_once(g_mtable_once, [] {
+        std::vector<double> t(2048);
+        for (int m = 0; m < 2048; m++) t[m] = log10(1.0 + (double)m / 2048.0) / log10(2.0);
+        cudaMemcpyToSymbol(g_mtable, t.data(), t.size() * sizeof(double));
+    });
+}
+__device__ __forceinline__ double mlog10_dev(double val)
+{
+    const unsigned long long N = (unsigned long long)__double_as_longlong(val);
+    const int e = (int)((N >> 52) & 2047ull) - 1023;
+    const int m = (int)((N >> 41) & 2047ull);
+    return 0.301029995663981 * ((double)e + g_mtable[m]);
+}
+
 // ------------------------------------------------------------------------------------------- meter
-// state: avg peak ; par: mult_average mult_peak ; results: av dB, pk dB (10 log10, meter.c:98-99)
+// state: avg peak ; par: mult_average mult_peak ; results: av dB, pk dB (10 mlog10, meter.c:96-99)
 // The averaging recurrence avg = avg * ma + (1 - ma) * |x|^2 is sequential in the reference's arithmetic, but its
 // inputs are not: every thread forms w[i] = (1 - ma) * |x[i]|^2 and the block maximum in parallel, lane 0 is left with
 // one multiply and one add per sample (the peak decay peak *= mp is a second, independent chain).
@@ -392,9 +414,9 @@ __global__ void meter_kernel(const cd *in, long is, int n, int C, double *state,
     }
     if (np > peak) peak = np;
     state[c * 2] = avg; state[c * 2 + 1] = peak;
-    result[c * 3] = 10.0 * log10(avg + 1.0e-40);
-    result[c * 3 + 1] = 10.0 * log10(peak + 1.0e-40);
-    result[c * 3 + 2] = agc_state ? 20.0 * log10(agc_state[(size_t)c * 16 + 10] + 1.0e-40) : 0.0;
+    result[c * 3] = 10.0 * mlog10_dev(avg + 1.0e-40);
+    result[c * 3 + 1] = 10.0 * mlog10_dev(peak + 1.0e-40);
+    result[c * 3 + 2] = agc_state ? 20.0 * mlog10_dev(agc_state[(size_t)c * 16 + 10] + 1.0e-40) : 0.0;
 }
 
 // sip != nullptr: also xsiphon mode 0 (siphon.c:96-129) on the INPUT block -- between xsiphon and xpanel the chain only
@@ -468,6 +490,20 @@ int SeqStage::flush()
     return QC_OK;
 }
 
+int SeqStage::flush_ref()
+{   // The reference's own flush_<stage>, which for two stages resets LESS than a fresh object:
+    //   flush_wcpagc (wcpAGC.c:154-159): ring, abs_ring, ring_max -- volts, the state machine and the back averages live on;
+    //   flush_amd    (amd.c:109-113):    dc, dc_insert             -- the PLL and the phasing network live on.
+    // flush_shift, flush_fmd + flush_snotch, flush_meter reset everything the stage carries.
+    if (kind == SEQ_WCPAGC) {
+        if (d_ring) QC_CUDA(cudaMemset(d_ring, 0, (size_t)C * ring_len * 3 * sizeof(double)));
+        return cudaMemset2D(d_state + 2, 16 * sizeof(double), 0, sizeof(double), C) == cudaSuccess ? QC_OK : QC_ECUDA;     // ring_max
+    }
+    if (kind == SEQ_AMD)
+        return cudaMemset2D(d_state, (size_t)state_doubles * sizeof(double), 0, 2 * sizeof(double), C) == cudaSuccess ? QC_OK : QC_ECUDA;
+    return flush();
+}
+
 void SeqStage::load_agc()
 {   // loadWcpAGC, wcpAGC.c:115-147
     AgcParams &a = agc;
@@ -526,7 +562,7 @@ int SeqStage::run(const void *d_in, long is, void *d_out, long os, int n, cudaSt
     case SEQ_AMD: QC_SEQ_OPTIN(amd_kernel, sh); amd_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
     case SEQ_FMPLL: { const size_t sf = sh + (size_t)n * sizeof(double); QC_SEQ_OPTIN(fmpll_kernel, sf); fmpll_kernel<<<C, SEQ_T, sf, s>>>(in, is, out, os, n, C, d_state, P); break; }
     case SEQ_SNOTCH: QC_SEQ_OPTIN(snotch_kernel, sh); snotch_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
-    case SEQ_METER: QC_SEQ_OPTIN(meter_kernel, sh); meter_kernel<<<C, SEQ_T, sh, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out); break;
+    case SEQ_METER: mtable_init(); QC_SEQ_OPTIN(meter_kernel, sh); meter_kernel<<<C, SEQ_T, sh, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out); break;
     default: set_error("seq stage: unknown kind %d", kind); return QC_EINVAL;
     }
     count_launch();

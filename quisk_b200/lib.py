@@ -176,6 +176,10 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_xrxa.argtypes = [vp, vp, C.c_long, vp, C.c_long, vp]
     lib.quisk_cuda_rxa_fexchange0.argtypes = [vp, vp, vp, c_int_p]
     lib.quisk_cuda_rxa_get_meter.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.quisk_cuda_rxa_set_channel_state.argtypes = [vp, C.c_int, C.c_int]
+    lib.quisk_cuda_rxa_set_slew_down.argtypes = [vp, D, D]
+    lib.quisk_cuda_rxa_set_bfo.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_exchange_sizes.argtypes = [vp, c_int_p, c_int_p]
     _lib = lib
     return lib
 

@@ -181,7 +181,13 @@ class Channelizer:
     def set_option(self, option: int, value: int):
         L.check(self.lib, self.lib.quisk_cuda_pfb_set_option(self.h, option, value), "pfb_set_option")
 
-    def seek(self, n_abs: int): L.check(self.lib, self.lib.quisk_cuda_pfb_seek(self.h, n_abs), "pfb_seek")
+    def seek(self, n_abs: int, stream: int | None = None):
+        """Restart at an absolute sample index with an empty history.  Without a stream the device is synchronised first;
+        with one the reset is ordered on that stream like the prime / process calls around it."""
+        if stream is None:
+            L.check(self.lib, self.lib.quisk_cuda_pfb_seek(self.h, n_abs), "pfb_seek")
+        else:
+            L.check(self.lib, self.lib.quisk_cuda_pfb_seek_async(self.h, n_abs, stream), "pfb_seek_async")
 
     def prime(self, d_in: int, count: int, stream: int = 0):
         L.check(self.lib, self.lib.quisk_cuda_pfb_prime(self.h, d_in, count, stream), "pfb_prime")

@@ -117,6 +117,21 @@ def main():
             outs.append(dbuf[:nr].copy()); counts.append(nr)
         ch["demod_%s/y" % mode] = np.concatenate(outs)
         ch["demod_%s/counts" % mode] = np.array(counts)
+        if mode == "FM":
+            # the reference's own sensitivity: the same demodulator on the same input moved by one ulp per component
+            # (carg(x conj(x_-1)) of a multi-tone input passes close to zero magnitude now and then)
+            from tests.golden.make_golden_wdsp import ulp_perturb, rel_rms
+            lib = R.load("libquisk_rx_ref.so", private_copy=True)
+            lib.ref_set_sample_rate(48000); lib.ref_init_chain()
+            lib.ref_set_filters(fi.ctypes.data_as(C.c_void_p), fq.ctypes.data_as(C.c_void_p), len(fi), 2800, 0)
+            xp = ulp_perturb(x, 8)
+            outs, pos = [], 0
+            for n in DEMOD_SPLITS:
+                buf = np.zeros(66000, dtype=np.complex128); buf[:n] = xp[pos:pos + n]; pos += n
+                dbuf = np.zeros(132000)
+                nr = lib.ref_process_demodulate(buf.ctypes.data_as(C.c_void_p), dbuf.ctypes.data_as(C.c_void_p), n, 0, 0, R.MODES[mode])
+                outs.append(dbuf[:nr].copy())
+            ch["demod_FM/cond"] = np.array([rel_rms(np.concatenate(outs), ch["demod_FM/y"])])
     for name, mode, ntap, bw in DGT_CASES:
         lib = R.load("libquisk_rx_ref.so", private_copy=True)
         lib.ref_set_sample_rate(48000); lib.ref_init_chain()

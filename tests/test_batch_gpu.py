@@ -141,8 +141,9 @@ def test_rx_demod_kat(mode, fused, torch, tabs):
     x = np.stack([O.synth_iq(12000, 10, 1.0)] * 3)
     aud, ca, _, _ = _run_chain(torch, rx, x, DEMOD_SPLITS)
     assert ca == kat["demod_%s/counts" % mode].tolist()
-    for c in range(3):
-        assert O.rel_rms(aud[c], kat["demod_%s/y" % mode]) < (1e-10 if mode == "FM" else 1e-12)
+    errs = [O.rel_rms(aud[c], kat["demod_%s/y" % mode]) for c in range(3)]
+    print("demod", mode, fused, errs)
+    assert max(errs) < 1e-12
     rx.close()
 
 

@@ -88,8 +88,9 @@ def test_fircore_minimum_phase(torch, lib, kat):
     torch.cuda.synchronize()
     y = o.cpu().numpy()
     ref = kat["fircore_mp_256_1024/y"]
-    for c in range(NCH):
-        assert O.rel_rms(y[c], ref) < 1e-5
+    errs = [O.rel_rms(y[c], ref) for c in range(NCH)]
+    print("fircore mp", errs, "reference's own sensitivity to a one-ulp change of the impulse", kat["fircore_mp_256_1024/cond"])
+    assert max(errs) < _cond_bound(kat, "fircore_mp_256_1024", k=100.0)
     lin = lib.quisk_cuda_fircore_create(NCH, size, nc, 0, imp.ctypes.data)
     o2 = torch.zeros_like(d)
     for b in range(8):
@@ -166,8 +167,9 @@ def test_wcpagc(mode, torch, lib, kat):
 def test_amd(mode, sb, torch, lib, kat):
     st = lib.quisk_cuda_amd_create(NCH, 48000, mode, 1, sb)
     y = _run_seq(torch, lib, st, am_sig(4 * 512, 500, 48000.0), 512, 4)
-    for c in range(NCH):
-        assert O.rel_rms(y[c], kat["amd_%d_%d/y" % (mode, sb)]) < 1e-11
+    errs = [O.rel_rms(y[c], kat["amd_%d_%d/y" % (mode, sb)]) for c in range(NCH)]
+    print("amd", mode, sb, errs)
+    assert max(errs) < _cond_bound(kat, "amd_%d_%d" % (mode, sb))
     lib.quisk_cuda_seq_destroy(st)
 
 
@@ -214,8 +216,9 @@ def test_rxa_usb_channel(torch, lib, kat):
     y = _run_rxa(torch, lib, rxa, x, 256, 24, use_fexchange=True)
     ref = kat["rxa_usb/y"]
     assert not y[0][:512].any() and not ref[:512].any()            # two DSP buffers of latency
+    print("rxa_usb", [O.rel_rms(y[c], ref) for c in range(NCH)])
     for c in range(NCH):
-        assert O.rel_rms(y[c], ref) < 1e-11
+        assert O.rel_rms(y[c], ref) < _cond_bound(kat, "rxa_usb")
     av = np.zeros(NCH); pk = np.zeros(NCH); g = np.zeros(NCH)
     assert lib.quisk_cuda_rxa_get_meter(rxa, 1, av.ctypes.data, pk.ctypes.data, None) == 0
     assert np.all(av < 0) and np.all(av > -60) and np.all(pk >= av - 1e-9)
@@ -251,7 +254,7 @@ def test_rxa_usb_channel_upslew(torch, lib, kat):
     ref = kat["rxa_usb_slew/y"]
     assert np.array_equal(np.nonzero(ref)[0][:1], np.nonzero(y[0])[0][:1])       # same first non-zero output sample
     for c in range(NCH):
-        assert O.rel_rms(y[c], ref) < 1e-11
+        assert O.rel_rms(y[c], ref) < _cond_bound(kat, "rxa_usb")
     assert O.rel_rms(y[0], kat["rxa_usb/y"]) > 1e-3                               # and the ramp is really there
     lib.quisk_cuda_rxa_destroy(rxa)
 
@@ -275,7 +278,7 @@ def test_rxa_usb_channel_notches(torch, lib, kat):
     y = _run_rxa(torch, lib, rxa, x, 256, 24, use_fexchange=True)
     ref = kat["rxa_usb_notch/y"]
     for c in range(NCH):
-        assert O.rel_rms(y[c], ref) < 1e-11
+        assert O.rel_rms(y[c], ref) < _cond_bound(kat, "rxa_usb")
     lib.quisk_cuda_rxa_destroy(rxa)
 
 
@@ -287,7 +290,7 @@ def test_rxa_default_channel_keeps_bp1(torch, lib, kat):
     y = _run_rxa(torch, lib, rxa, x, 256, 16)
     ref = kat["rxa_default/y"][512:]
     for c in range(NCH):
-        assert O.rel_rms(y[c][:len(ref)], ref) < 1e-11
+        assert O.rel_rms(y[c][:len(ref)], ref) < _cond_bound(kat, "rxa_usb")
     lib.quisk_cuda_rxa_destroy(rxa)
 
 
@@ -312,8 +315,9 @@ def test_fmd_stage_composition(torch, lib, kat):
         assert lib.quisk_cuda_seq_run(sn, blk.data_ptr(), d.stride(0), blk.data_ptr(), d.stride(0), n, None) == 0
     torch.cuda.synchronize()
     y = d.cpu().numpy()
-    for c in range(NCH):
-        assert O.rel_rms(y[c], kat["fmd/y"]) < 1e-10
+    errs = [O.rel_rms(y[c], kat["fmd/y"]) for c in range(NCH)]
+    print("fmd stage", errs, "reference's own one-ulp sensitivity", kat["fmd/cond"])
+    assert max(errs) < _cond_bound(kat, "fmd")
 
 
 def test_rxa_fm_channel(torch, lib, kat):
@@ -328,8 +332,9 @@ def test_rxa_fm_channel(torch, lib, kat):
     y = _run_rxa(torch, lib, rxa, x, 2048, FM_BLOCKS)
     ref = kat["rxa_fm/y_tail"]                      # fexchange0 output blocks FM_BLOCKS-16 .. FM_BLOCKS-1
     ours = y[:, (FM_BLOCKS - 18) * 256:(FM_BLOCKS - 2) * 256]     # same blocks: the exchange delays by two
-    for c in range(NCH):
-        assert O.rel_rms(ours[c], ref) < 1e-8
+    errs = [O.rel_rms(ours[c], ref) for c in range(NCH)]
+    print("rxa_fm tail", errs, "reference's own one-ulp sensitivity", kat["rxa_fm/cond"])
+    assert max(errs) < _cond_bound(kat, "rxa_fm")
     lib.quisk_cuda_rxa_destroy(rxa)
 
 
@@ -341,6 +346,227 @@ def test_rxa_am_channel(torch, lib, kat):
     assert lib.quisk_cuda_rxa_set_passband(rxa, -4000.0, 4000.0) == 0
     y = _run_rxa(torch, lib, rxa, x, 256, 16)
     ref = kat["rxa_am/y"][512:]
-    for c in range(NCH):
-        assert O.rel_rms(y[c][:len(ref)], ref) < 1e-11
+    errs = [O.rel_rms(y[c][:len(ref)], ref) for c in range(NCH)]
+    print("rxa_am", errs)
+    assert max(errs) < _cond_bound(kat, "rxa_am")
     lib.quisk_cuda_rxa_destroy(rxa)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round 2: the full C3 geometry, meters, the general exchange (re-blocking, down-slew, flush, restart) and the
+# reference's own entry points by channel number (wdsp_compat.cu).
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _cond_bound(kat, key, k=20.0, floor=1e-12):
+    """Tolerance from the reference's OWN sensitivity: `<key>/cond` is the relative RMS change of the compiled reference's
+    output when every input component moves by one ulp (tests/golden/make_golden_wdsp.py).  An implementation with
+    different but equally valid roundings (another FFT, another libm) cannot be expected closer than a small multiple of
+    that; where the reference is better conditioned than 1e-12 / k the north star's 1e-12 stands."""
+    return max(floor, k * float(kat[key + "/cond"][0]))
+
+
+def _setup_usb(lib, rxa, nc=2048):
+    assert lib.quisk_cuda_rxa_set_shift(rxa, 0, None) == 0
+    assert lib.quisk_cuda_rxa_set_nc(rxa, nc) == 0
+    assert lib.quisk_cuda_rxa_set_mode(rxa, 1) == 0
+    assert lib.quisk_cuda_rxa_set_passband(rxa, 150.0, 2850.0) == 0
+    assert lib.quisk_cuda_rxa_set_agc_mode(rxa, 3) == 0
+
+
+def _exchange_blocks(lib, rxa, x, in_size, out_size, nblocks, before=None, collect_meters=False):
+    ys, mts = [], []
+    for b in range(nblocks):
+        if before is not None:
+            before(b)
+        hin = np.ascontiguousarray(np.stack([x[b * in_size:(b + 1) * in_size]] * NCH))
+        hout = np.full((NCH, out_size), -7.0 - 7.0j, dtype=np.complex128)
+        err = C.c_int(9)
+        assert lib.quisk_cuda_rxa_fexchange0(rxa, hin.ctypes.data, hout.ctypes.data, C.byref(err)) == 0, lib.quisk_cuda_last_error()
+        assert err.value == 0
+        ys.append(hout)
+        if collect_meters:
+            row = np.zeros((3, 3, NCH))
+            for w in range(3):
+                assert lib.quisk_cuda_rxa_get_meter(rxa, w, row[w, 0].ctypes.data, row[w, 1].ctypes.data, row[w, 2].ctypes.data) == 0
+            # reference order (RXA.h:47-57): S_PK, S_AV, ADC_PK, ADC_AV, AGC_GAIN, AGC_PK, AGC_AV
+            mts.append(np.stack([row[1, 1], row[1, 0], row[0, 1], row[0, 0], row[2, 2], row[2, 1], row[2, 0]], axis=0))
+    return np.concatenate(ys, axis=1), (np.array(mts) if collect_meters else None)
+
+
+def test_rxa_c3_full_geometry(torch, lib, kat):
+    """SURVEY 8(d) C3 as stated: OpenChannel(1024, 1024, 192 k everywhere), RXASetNC(4096), USB 150-2850, AGC mode 3,
+    through the fexchange0 entry; the three meters after every block against GetRXAMeter."""
+    x = sig(1024 * 16, 710, 192000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2), (-30000.0, 0.25)))
+    rxa = lib.quisk_cuda_rxa_create(NCH, 1024, 1024, 192000, 192000, 192000)
+    assert rxa, lib.quisk_cuda_last_error()
+    _setup_usb(lib, rxa, 4096)
+    y, mt = _exchange_blocks(lib, rxa, x, 1024, 1024, 16, collect_meters=True)
+    ref = kat["rxa_c3/y"]
+    tol = _cond_bound(kat, "rxa_c3")
+    errs = [O.rel_rms(y[c], ref) for c in range(NCH)]
+    print("rxa_c3 rel-rms", errs, "bound", tol)
+    assert max(errs) < tol
+    rm = kat["rxa_c3/meters"]
+    for c in range(NCH):
+        assert np.max(np.abs(mt[:, :, c] - rm)) < 1e-9, np.max(np.abs(mt[:, :, c] - rm), axis=0)
+    lib.quisk_cuda_rxa_destroy(rxa)
+
+
+def test_rxa_meters_parity(torch, lib, kat):
+    """xmeter (meter.c:75-107) for all three meters of the chain, every block: average, peak and AGC gain in dB."""
+    x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    rxa = lib.quisk_cuda_rxa_create(NCH, 256, 256, 48000, 48000, 48000)
+    _setup_usb(lib, rxa)
+    y, mt = _exchange_blocks(lib, rxa, x, 256, 256, 24, collect_meters=True)
+    rm = kat["rxa_usb/meters"]
+    assert rm.shape == (24, 7) and np.all(rm[2:, :4] > -120) and np.all(rm[2:, :4] < 10)      # the fixture is not vacuous
+    for c in range(NCH):
+        d = np.abs(mt[:, :, c] - rm)
+        assert np.max(d) < 1e-9, np.max(d, axis=0)
+    assert max(O.rel_rms(y[c], kat["rxa_usb/y"]) for c in range(NCH)) < _cond_bound(kat, "rxa_usb")
+    lib.quisk_cuda_rxa_destroy(rxa)
+
+
+@pytest.mark.parametrize("in_size,nblocks", [(64, 96), (1024, 6)])
+def test_rxa_exchange_reblocking(in_size, nblocks, torch, lib, kat):
+    """in_size != dsp_insize (create_iobuffs / fexchange0 / dexchange, iobuffs.c:385-420, 464-516, 583-604): four calls
+    per DSP turn, and four DSP turns per call."""
+    x = sig(256 * 24, 720, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    rxa = lib.quisk_cuda_rxa_create(NCH, in_size, 256, 48000, 48000, 48000)
+    assert rxa, lib.quisk_cuda_last_error()
+    _setup_usb(lib, rxa)
+    i_s, o_s = C.c_int(0), C.c_int(0)
+    assert lib.quisk_cuda_rxa_exchange_sizes(rxa, C.byref(i_s), C.byref(o_s)) == 0 and (i_s.value, o_s.value) == (in_size, in_size)
+    y, _ = _exchange_blocks(lib, rxa, x, in_size, in_size, nblocks)
+    ref = kat["rxa_reblock_%d_256/y" % in_size]
+    nz = np.nonzero(ref)[0][0]
+    assert nz == np.nonzero(y[0])[0][0]                     # same latency to the sample
+    for c in range(NCH):
+        assert O.rel_rms(y[c], ref) < _cond_bound(kat, "rxa_usb")
+    lib.quisk_cuda_rxa_destroy(rxa)
+
+
+def test_rxa_stop_start(torch, lib, kat):
+    """SetChannelState(0) mid-stream: downslew0 on the way out (10 ms ramp, out_size + 1 zeros), then the exchange
+    switches off (calls return without touching `out`) and the channel is flushed the way the reference flushes it;
+    SetChannelState(1): up-slew from BEGIN on the flushed channel.  Outputs and meters after every call."""
+    x = sig(256 * 32, 730, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    # in_size 64 / dsp_size 256, stop on a call that starts a DSP block: the one geometry in which the reference itself
+    # is deterministic (see the generator: otherwise its DSP and flush threads race for the last block)
+    rxa = lib.quisk_cuda_rxa_create(NCH, 64, 256, 48000, 48000, 48000)
+    assert lib.quisk_cuda_rxa_set_slew_down(rxa, 0.0, 0.010) == 0
+    assert lib.quisk_cuda_rxa_set_slew(rxa, 0.010, 0.025) == 0
+    _setup_usb(lib, rxa)
+
+    def before(b):
+        if b == 40:
+            assert lib.quisk_cuda_rxa_set_channel_state(rxa, 0, 0) == 1
+        if b == 72:
+            assert lib.quisk_cuda_rxa_set_channel_state(rxa, 1, 0) == 0
+    y, mt = _exchange_blocks(lib, rxa, x, 64, 64, 128, before=before, collect_meters=True)
+    ref = kat["rxa_stop_start/y"]
+    untouched = np.all(ref.reshape(128, 64) == -7.0 - 7.0j, axis=1)
+    assert untouched.sum() >= 16                                             # the fixture really has exchange-off calls
+    assert np.array_equal(np.all(y[0].reshape(128, 64) == -7.0 - 7.0j, axis=1), untouched)
+    live = np.repeat(~untouched, 64)
+    for c in range(NCH):
+        assert O.rel_rms(y[c][live], ref[live]) < _cond_bound(kat, "rxa_usb")
+    rm = kat["rxa_stop_start/meters"]
+    for c in range(NCH):
+        d = np.abs(mt[:, :, c] - rm)
+        # below -300 dB a meter reads the FFT rounding floor of an all-zero input just after the flush (1e-22 samples
+        # on top of the 1e-40 the meter adds before its logarithm): implementation noise in the reference too, not compared
+        assert np.max(d[rm > -300]) < 1e-9, np.max(d, axis=0)
+        assert np.array_equal(rm <= -399.9, mt[:, :, c] <= -399.9)          # and the flushed (-400) readings agree call for call
+    lib.quisk_cuda_rxa_destroy(rxa)
+
+
+def _wdsp_cdll():
+    """What quisk_wdsp.py does with libwdsp.so (quisk_wdsp.py:28), on our library."""
+    from quisk_b200 import lib as L
+    w = C.CDLL(L.LIB_PATH)
+    w.GetRXAMeter.restype = C.c_double
+    return w
+
+
+def test_wdsp_compat_quisk_open_sequence(torch, lib, kat):
+    """quisk_wdsp.py's own sequence, call for call (Cwdsp.__init__ :45-67 and open() :69-99), with ctypes' default
+    argument conversion like the reference module uses, then Quisk's re-blocker wdspFexchange0 (quisk_wdsp.c:22-69) on
+    ragged sample counts scaled to CLIP32 -- against the compiled reference driven the same way."""
+    from tests.golden.make_golden_wdsp import QUISK_SPLITS
+    w = _wdsp_cdll()
+    assert w.GetWDSPVersion() == 125
+    fpt = C.cast(w.fexchange0, C.c_void_p).value
+    assert fpt                                                               # the address quisk_wdsp_set_parameter stores
+    channel, in_size, dsp_size = 1, 256, 256
+    w.quisk_cuda_wdsp_set_parameter(channel, in_size, -1)
+    w.OpenChannel(channel, in_size, dsp_size, 48000, 48000, 48000, 0, 1,
+                  C.c_double(0.010), C.c_double(0.025), C.c_double(0.0), C.c_double(0.010), 1)
+    w.SetRXAShiftRun(channel, 0)
+    w.RXANBPSetRun(channel, 0)
+    w.SetRXAAMSQRun(channel, 0)
+    w.SetRXAMode(channel, 1)
+    w.RXASetPassband(channel, C.c_double(300.0), C.c_double(3000.0))
+    w.RXASetNC(channel, dsp_size)
+    w.RXASetMP(channel, 0)
+    w.SetRXAAGCMode(channel, 0)
+    w.SetRXAAGCFixed(channel, C.c_double(0.0))
+    w.SetRXAPanelRun(channel, 0)
+    w.SetRXAEMNRRun(channel, 0)
+    w.quisk_cuda_wdsp_set_parameter(channel, -1, 1)                          # in_use = wdsp_NR2 + wdsp_SNB (quisk.py:6027)
+    xq = sig(6000, 740, 48000.0) * 2.0 ** 30
+    ys, counts, pos = [], [], 0
+    for n in QUISK_SPLITS:
+        buf = np.zeros(n + 1024, dtype=np.complex128); buf[:n] = xq[pos:pos + n]; pos += n
+        k = w.wdspFexchange0(channel, buf.ctypes.data_as(C.c_void_p), n)
+        ys.append(buf[:k].copy()); counts.append(k)
+    assert counts == kat["quisk_reblock/counts"].tolist()
+    y = np.concatenate(ys); ref = kat["quisk_reblock/y"]
+    assert np.nonzero(y)[0][0] == np.nonzero(ref)[0][0]
+    assert O.rel_rms(y, ref) < 1e-14                                         # gain, scaling and ramps only in this configuration
+    # in_use = 0: samples pass through untouched and the re-blocker's indices restart (quisk_wdsp.c:32-37)
+    w.quisk_cuda_wdsp_set_parameter(channel, -1, 0)
+    buf = xq[:300].copy()
+    assert w.wdspFexchange0(channel, buf.ctypes.data_as(C.c_void_p), 300) == 300 and np.array_equal(buf, xq[:300])
+    w.CloseChannel(channel)
+
+
+def test_wdsp_compat_channel_api(torch, lib, kat):
+    """The reference's signatures by channel number against the same fixtures the batched handle is held to: USB channel
+    opened with Quisk's slew times, the notch database, GetRXAMeter, RXAGetaSipF1, two channels open at once."""
+    w = _wdsp_cdll()
+    D = C.c_double
+    x = sig(256 * 24, 700, 48000.0, tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    xs = x.copy(); xs[:100] = 0.0
+    xn = sig(256 * 24, 700, 48000.0, tones=((1000.0, 0.3), (1500.0, 0.2), (2200.0, 0.1)))
+    for ch, slew in ((5, (0.010, 0.025, 0.0, 0.010)), (6, (0.0, 0.0, 0.0, 0.0))):
+        w.OpenChannel(ch, 256, 256, 48000, 48000, 48000, 0, 1, D(slew[0]), D(slew[1]), D(slew[2]), D(slew[3]), 1)
+        w.SetRXAShiftRun(ch, 0); w.RXASetNC(ch, 2048); w.SetRXAMode(ch, 1)
+        w.RXASetPassband(ch, D(150.0), D(2850.0)); w.SetRXAAGCMode(ch, 3)
+    w.RXANBPSetTuneFrequency(6, D(7000000.0))
+    w.RXANBPSetNotchesRun(6, 1)
+    assert w.RXANBPAddNotch(6, 0, D(7001500.0), D(400.0), 1) == 0
+    assert w.RXANBPAddNotch(6, 1, D(7002400.0), D(100.0), 1) == 0
+    nn = C.c_int(0); w.RXANBPGetNumNotches(6, C.byref(nn)); assert nn.value == 2
+    ys = {5: [], 6: []}
+    err = C.c_int(0)
+    for b in range(24):
+        for ch, src in ((5, xs), (6, xn)):                                   # interleaved: the channels are independent
+            inb = np.ascontiguousarray(src[b * 256:(b + 1) * 256]); outb = np.zeros(256, dtype=np.complex128)
+            w.fexchange0(ch, inb.ctypes.data_as(C.c_void_p), outb.ctypes.data_as(C.c_void_p), C.byref(err))
+            assert err.value == 0
+            ys[ch].append(outb)
+    tol = _cond_bound(kat, "rxa_usb")
+    assert O.rel_rms(np.concatenate(ys[5]), kat["rxa_usb_slew/y"]) < tol
+    assert O.rel_rms(np.concatenate(ys[6]), kat["rxa_usb_notch/y"]) < tol
+    for mt in range(7):
+        v = w.GetRXAMeter(5, mt)
+        assert np.isfinite(v) and -200 < v < 100
+    sip = np.zeros(2 * 1024, dtype=np.float32)
+    w.RXAGetaSipF1(5, sip.ctypes.data_as(C.c_void_p), 1024)
+    assert np.any(sip != 0)
+    assert w.SetChannelState(5, 0, 0) == 1 and w.SetChannelState(5, 0, 0) == 0
+    w.CloseChannel(5); w.CloseChannel(6)
+    outb = np.full(256, 3.0 + 0j)
+    w.fexchange0(5, x[:256].ctypes.data_as(C.c_void_p), outb.ctypes.data_as(C.c_void_p), C.byref(err))      # closed: a message, no crash
+    assert np.all(outb == 3.0)
