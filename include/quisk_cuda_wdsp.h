@@ -127,6 +127,11 @@ int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per chan
 int quisk_cuda_rxa_out_size(const qcRxa *r);     /* dsp_outsize: samples per channel produced per xrxa */
 /* xrxa (RXA.c:561-598) for one DSP block of every channel. d_in [n_channels][in_stride], d_out likewise. */
 int quisk_cuda_rxa_xrxa(qcRxa *r, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream);
+/* The same for n_blocks consecutive DSP blocks per channel (block b of a channel at d_in + b * dsp_insize samples,
+ * d_out + b * dsp_outsize): one launch chain instead of one per block -- the state carried between blocks is the same. */
+int quisk_cuda_rxa_xrxa_multi(qcRxa *r, const void *d_in, long in_stride, void *d_out, long out_stride, int n_blocks, void *stream);
+#define QC_RXA_OPT_FUSED 1     /* 1 (default): configurations the single-kernel chain covers (wdsp_rxa_fused.cu) use it; 0: one kernel per stage */
+int quisk_cuda_rxa_set_option(qcRxa *r, int option, int value);
 /* fexchange0 (wdsp/iobuffs.c:464-516) with HOST buffers for all channels at once: h_in [n_channels][in_size],
  * h_out [n_channels][out_size] interleaved complex.  The reference's two pseudo-rings (create_iobuffs, iobuffs.c:385-420)
  * and its ring arithmetic are reproduced, with the DSP thread's turns (dexchange + xrxa, main.c:40-63) run inside the

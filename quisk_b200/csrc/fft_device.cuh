@@ -93,7 +93,16 @@ __device__ __forceinline__ cd fft_tw(const cd *twl, int idx, int sign)
 // sign: -1 forward, +1 backward; lane / lanes: this thread's index among the transform's threads.
 // BPT = radix-16 butterflies per thread and pass: 2 covers n = 8192 on 256 lanes; kernels that only run
 // n <= 16 * lanes instantiate BPT = 1 and save the second butterfly's 64 registers.
-template <int BPT = 2>
+// NBAR: 0 = the transform's barriers are __syncthreads() (every thread of the CTA calls fft_smem); NBAR > 0 = named barrier 1
+// over NBAR threads, for kernels whose other warps are busy with something else (wdsp_rxa_fused.cu).
+template <int NBAR>
+__device__ __forceinline__ void fft_sync()
+{
+    if (NBAR == 0) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" :: "r"(NBAR) : "memory");
+}
+
+template <int BPT = 2, int NBAR = 0>
 __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int sign, int lane, int lanes)
 {
     const double sg = (double)sign;
@@ -131,7 +140,7 @@ __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int si
                 ob[t] = q + stride * 16 * p;
             }
         }
-        __syncthreads();
+        fft_sync<NBAR>();
 #pragma unroll
         for (int t = 0; t < BPT; t++) {
             if (ob[t] >= 0) {
@@ -139,7 +148,7 @@ __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int si
                 for (int k = 0; k < 16; k++) s[fsw(ob[t] + k * stride)] = v[t][k];
             }
         }
-        __syncthreads();
+        fft_sync<NBAR>();
         len >>= 4;
         stride <<= 4;
     }
@@ -168,14 +177,14 @@ __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int si
                 ob[u] = q + stride * 4 * p;
             }
         }
-        __syncthreads();
+        fft_sync<NBAR>();
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             if (ob[u] >= 0) {
                 s[fsw(ob[u])] = r[u][0]; s[fsw(ob[u] + stride)] = r[u][1]; s[fsw(ob[u] + 2 * stride)] = r[u][2]; s[fsw(ob[u] + 3 * stride)] = r[u][3];
             }
         }
-        __syncthreads();
+        fft_sync<NBAR>();
         len >>= 2;
         stride <<= 2;
     }
@@ -188,7 +197,7 @@ __device__ inline void fft_smem(cd *s, int n, const cd *__restrict__ twl, int si
             s[fsw(q)] = cadd(a, b);
             s[fsw(q + nb)] = csub(a, b);
         }
-        __syncthreads();
+        fft_sync<NBAR>();
     }
 }
 

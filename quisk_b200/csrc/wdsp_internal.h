@@ -61,6 +61,18 @@ struct SeqStage {
     void load_agc();
 };
 
+// mlog10 (wdsp/meterlog10.c:547-554): the table look-up logarithm WDSP's meters use; the table lives in device memory
+const double *mlog10_table();
+#ifdef __CUDACC__
+__device__ __forceinline__ double mlog10_dev(const double *__restrict__ mtable, double val)
+{
+    const unsigned long long N = (unsigned long long)__double_as_longlong(val);
+    const int e = (int)((N >> 52) & 2047ull) - 1023;
+    const int m = (int)((N >> 41) & 2047ull);
+    return 0.301029995663981 * ((double)e + mtable[m]);
+}
+#endif
+
 SeqStage *make_shift(int C, int rate, const double *shift_hz);
 SeqStage *make_wcpagc(int C, int rate, int mode);
 SeqStage *make_amd(int C, int rate, int mode, int levelfade, int sbmode);
@@ -125,6 +137,11 @@ struct Rxa {
     int make_bp1();
     int make_fmd();
     int xrxa(const void *din, long is, void *dout, long os, cudaStream_t s);
+    // wdsp_rxa_fused.cu: the whole chain as one kernel for the configurations it covers, any number of DSP blocks per launch
+    int fused_ok = 1;                       // QC_RXA_OPT_FUSED
+    bool fusable() const;
+    int xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s);
+    int xrxa_multi(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s);
 };
 
 int launch_panel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C, double gainI, double gainQ,

@@ -193,8 +193,20 @@ void Rxa::release()
     mid = mid2 = audio = nullptr;
 }
 
+int Rxa::xrxa_multi(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s)
+{   // nblocks consecutive DSP blocks per channel: block b of a channel at in + b * dsp_insize, out + b * dsp_outsize
+    if (nblocks <= 0) return QC_OK;
+    if (fusable()) return xrxa_fused(din, is, dout, os, nblocks, s);
+    for (int b = 0; b < nblocks; b++) {
+        int rc = xrxa((const cd *)din + (size_t)b * dsp_insize, is, (cd *)dout + (size_t)b * dsp_outsize, os, s);
+        if (rc != QC_OK) return rc;
+    }
+    return QC_OK;
+}
+
 int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
 {
+    if (fusable()) return xrxa_fused(din, is, dout, os, 1, s);
     int rc;
     const cd *cur = (const cd *)din; long cs = is;
     const long ms = 2 * (dsp_size > dsp_insize ? dsp_size : dsp_insize) + 64;
@@ -635,6 +647,15 @@ int quisk_cuda_rxa_set_panel_gain(qcRxa *p, double g) { if (!p) return QC_EINVAL
 
 int quisk_cuda_rxa_xrxa(qcRxa *p, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream)
 { return p ? p->r.xrxa(d_in, in_stride, d_out, out_stride, (cudaStream_t)stream) : QC_EINVAL; }
+int quisk_cuda_rxa_xrxa_multi(qcRxa *p, const void *d_in, long in_stride, void *d_out, long out_stride, int n_blocks, void *stream)
+{ return p ? p->r.xrxa_multi(d_in, in_stride, d_out, out_stride, n_blocks, (cudaStream_t)stream) : QC_EINVAL; }
+int quisk_cuda_rxa_set_option(qcRxa *p, int option, int value)
+{
+    if (!p) return QC_EINVAL;
+    if (option == QC_RXA_OPT_FUSED) { p->r.fused_ok = value ? 1 : 0; return QC_OK; }
+    set_error("rxa_set_option: unknown option %d", option);
+    return QC_EINVAL;
+}
 
 int quisk_cuda_rxa_fexchange0(qcRxa *p, const double *h_in, double *h_out, int *error)
 {   // fexchange0 (iobuffs.c:464-516) for every channel of the batch: h_in [C][in_size], h_out [C][out_size]

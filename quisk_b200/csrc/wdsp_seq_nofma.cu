@@ -364,22 +364,21 @@ __global__ void snotch_kernel(const cd *in, long is, cd *out, long os, int n, in
 // look-up of log2(1 + m / 2048) on the leading mantissa bits, no interpolation, so a meter reads up to 2.1e-3 dB low.
 // Part of the reference's observable behaviour (GetRXAMeter).  The table is rebuilt here from its definition
 // (log10(x) / log10(2) reproduces 2045 of the reference's 2048 entries exactly, the other three to one ulp).
-__device__ double g_mtable[2048];
-static std::once_flag g_mtable_once;
-static void mtable_init()
-{
-    std::call_once(g_mtable_once, [] {
+const double *mlog10_table()
+{   // device copy of the table, per device (the library may be used on several GPUs from one process)
+    static std::mutex mu;
+    static double *tab[64] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!tab[dev]) {
         std::vector<double> t(2048);
         for (int m = 0; m < 2048; m++) t[m] = log10(1.0 + (double)m / 2048.0) / log10(2.0);
-        cudaMemcpyToSymbol(g_mtable, t.data(), t.size() * sizeof(double));
-    });
-}
-__device__ __forceinline__ double mlog10_dev(double val)
-{
-    const unsigned long long N = (unsigned long long)__double_as_longlong(val);
-    const int e = (int)((N >> 52) & 2047ull) - 1023;
-    const int m = (int)((N >> 41) & 2047ull);
-    return 0.301029995663981 * ((double)e + g_mtable[m]);
+        if (cudaMalloc((void **)&tab[dev], t.size() * sizeof(double)) != cudaSuccess) { tab[dev] = nullptr; return nullptr; }
+        cudaMemcpy(tab[dev], t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    return tab[dev];
 }
 
 // ------------------------------------------------------------------------------------------- meter
@@ -387,7 +386,7 @@ __device__ __forceinline__ double mlog10_dev(double val)
 // The averaging recurrence avg = avg * ma + (1 - ma) * |x|^2 is sequential in the reference's arithmetic, but its
 // inputs are not: every thread forms w[i] = (1 - ma) * |x[i]|^2 and the block maximum in parallel, lane 0 is left with
 // one multiply and one add per sample (the peak decay peak *= mp is a second, independent chain).
-__global__ void meter_kernel(const cd *in, long is, int n, int C, double *state, SeqPar P, double *result, const double *agc_state)
+__global__ void meter_kernel(const cd *in, long is, int n, int C, double *state, SeqPar P, double *result, const double *agc_state, const double *mtable)
 {
     extern __shared__ double seq_smem[];
     double *w = seq_smem;                       // [n]
@@ -414,9 +413,9 @@ __global__ void meter_kernel(const cd *in, long is, int n, int C, double *state,
     }
     if (np > peak) peak = np;
     state[c * 2] = avg; state[c * 2 + 1] = peak;
-    result[c * 3] = 10.0 * mlog10_dev(avg + 1.0e-40);
-    result[c * 3 + 1] = 10.0 * mlog10_dev(peak + 1.0e-40);
-    result[c * 3 + 2] = agc_state ? 20.0 * mlog10_dev(agc_state[(size_t)c * 16 + 10] + 1.0e-40) : 0.0;
+    result[c * 3] = 10.0 * mlog10_dev(mtable, avg + 1.0e-40);
+    result[c * 3 + 1] = 10.0 * mlog10_dev(mtable, peak + 1.0e-40);
+    result[c * 3 + 2] = agc_state ? 20.0 * mlog10_dev(mtable, agc_state[(size_t)c * 16 + 10] + 1.0e-40) : 0.0;
 }
 
 // sip != nullptr: also xsiphon mode 0 (siphon.c:96-129) on the INPUT block -- between xsiphon and xpanel the chain only
@@ -562,7 +561,8 @@ int SeqStage::run(const void *d_in, long is, void *d_out, long os, int n, cudaSt
     case SEQ_AMD: QC_SEQ_OPTIN(amd_kernel, sh); amd_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
     case SEQ_FMPLL: { const size_t sf = sh + (size_t)n * sizeof(double); QC_SEQ_OPTIN(fmpll_kernel, sf); fmpll_kernel<<<C, SEQ_T, sf, s>>>(in, is, out, os, n, C, d_state, P); break; }
     case SEQ_SNOTCH: QC_SEQ_OPTIN(snotch_kernel, sh); snotch_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
-    case SEQ_METER: mtable_init(); QC_SEQ_OPTIN(meter_kernel, sh); meter_kernel<<<C, SEQ_T, sh, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out); break;
+    case SEQ_METER: { const double *mt = mlog10_table(); if (!mt) { set_error("meter: table allocation failed"); return QC_ENOMEM; }
+        QC_SEQ_OPTIN(meter_kernel, sh); meter_kernel<<<C, SEQ_T, sh, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out, mt); break; }
     default: set_error("seq stage: unknown kind %d", kind); return QC_EINVAL;
     }
     count_launch();

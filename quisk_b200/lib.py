@@ -175,6 +175,8 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_out_size.argtypes = [vp]
     lib.quisk_cuda_rxa_xrxa.argtypes = [vp, vp, C.c_long, vp, C.c_long, vp]
     lib.quisk_cuda_rxa_fexchange0.argtypes = [vp, vp, vp, c_int_p]
+    lib.quisk_cuda_rxa_xrxa_multi.argtypes = [vp, vp, C.c_long, vp, C.c_long, C.c_int, vp]
+    lib.quisk_cuda_rxa_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.quisk_cuda_rxa_get_meter.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.quisk_cuda_rxa_set_channel_state.argtypes = [vp, C.c_int, C.c_int]
     lib.quisk_cuda_rxa_set_slew_down.argtypes = [vp, D, D]

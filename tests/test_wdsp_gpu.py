@@ -570,3 +570,51 @@ def test_wdsp_compat_channel_api(torch, lib, kat):
     outb = np.full(256, 3.0 + 0j)
     w.fexchange0(5, x[:256].ctypes.data_as(C.c_void_p), outb.ctypes.data_as(C.c_void_p), C.byref(err))      # closed: a message, no crash
     assert np.all(outb == 3.0)
+
+
+@pytest.mark.parametrize("geom", [(256, 2048, 48000, 24), (1024, 4096, 192000, 12)])
+@pytest.mark.parametrize("agc_mode", [3, 1, 0])
+def test_rxa_fused_kernel_equals_per_stage_kernels(geom, agc_mode, torch, lib):
+    """wdsp_rxa_fused.cu (the chain as one kernel, speculative AGC lane, meters on their own lanes) against the per-stage
+    kernels it replaces, for one block per launch, for all blocks in one launch, and with the stream switching between
+    the two paths from block to block (they share every state array).  Multi-block and single-block launches of the fused
+    kernel are the same bits; against the per-stage kernels the transforms are two compilations of one source (the
+    compiler contracts multiply-adds differently in the two contexts), so outputs agree to 1e-13 and meters to 1e-9 dB."""
+    size, nc, rate, nblk = geom
+    x = sig(size * nblk, 760 + agc_mode, float(rate), tones=((-1000.0, 0.3), (-2200.0, 0.1), (1500.0, 0.2)))
+    x[4 * size:6 * size] *= 0.02; x[8 * size:] *= 3.0          # level steps walk the AGC through its states
+    d = _dev(torch, x)
+
+    def run(kind):
+        rxa = lib.quisk_cuda_rxa_create(NCH, size, size, rate, rate, rate)
+        assert lib.quisk_cuda_rxa_set_shift(rxa, 0, None) == 0
+        assert lib.quisk_cuda_rxa_set_nc(rxa, nc) == 0
+        assert lib.quisk_cuda_rxa_set_mode(rxa, 1) == 0
+        assert lib.quisk_cuda_rxa_set_passband(rxa, 150.0, 2850.0) == 0
+        assert lib.quisk_cuda_rxa_set_agc_mode(rxa, agc_mode) == 0
+        o = torch.zeros_like(d)
+        if kind == "multi":
+            assert lib.quisk_cuda_rxa_xrxa_multi(rxa, d.data_ptr(), d.stride(0), o.data_ptr(), o.stride(0), nblk, None) == 0, lib.quisk_cuda_last_error()
+        else:
+            for b in range(nblk):
+                fused = {"fused": 1, "stages": 0, "mixed": b % 3 != 1}[kind]
+                assert lib.quisk_cuda_rxa_set_option(rxa, 1, int(fused)) == 0
+                blk = d[:, b * size:(b + 1) * size]; ob = o[:, b * size:(b + 1) * size]
+                assert lib.quisk_cuda_rxa_xrxa(rxa, blk.data_ptr(), d.stride(0), ob.data_ptr(), o.stride(0), None) == 0, lib.quisk_cuda_last_error()
+        torch.cuda.synchronize()
+        mt = np.zeros((3, 3, NCH))
+        for w in range(3):
+            assert lib.quisk_cuda_rxa_get_meter(rxa, w, mt[w, 0].ctypes.data, mt[w, 1].ctypes.data, mt[w, 2].ctypes.data) == 0
+        sip = np.zeros((NCH, 2 * 1024), dtype=np.float32)
+        assert lib.quisk_cuda_rxa_get_siphon(rxa, sip.ctypes.data, 1024, 1) == 0
+        lib.quisk_cuda_rxa_destroy(rxa)
+        return o.cpu().numpy(), mt, sip
+    ref = run("stages")
+    assert np.abs(ref[0]).max() > 0.1
+    res = {kind: run(kind) for kind in ("fused", "multi", "mixed")}
+    for kind, got in res.items():
+        assert max(O.rel_rms(got[0][c], ref[0][c]) for c in range(NCH)) < 1e-13, kind
+        assert np.max(np.abs(got[1] - ref[1])) < 1e-9, (kind, got[1] - ref[1])
+        assert np.max(np.abs(got[2] - ref[2])) <= 1e-6 * np.max(np.abs(ref[2])), kind
+    for k in range(3):
+        assert np.array_equal(res["multi"][k], res["fused"][k])
