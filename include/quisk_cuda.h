@@ -265,6 +265,9 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_NOISE_BLANKER 13  /* quisk_noise_blanker (0 = off, 1..3): quisk_cuda_rx_process_host / _host_packed run NoiseBlanker
                                       (quisk.c:679-784) on the staged block in front of the tuning stage, as quisk_process_samples
                                       does (quisk.c:2448-2449).  The device entry leaves the caller's buffer alone: run quisk_cuda_nb_run first */
+#define QC_RX_OPT_HOST_CHUNKS  15   /* quisk_cuda_rx_process_host / _host_packed: channel chunks whose H2D copy, kernels and D2H copy are pipelined
+                                      over streams of their own; 0 (default) = 8 from 1024 channels up, else 1; 1 = one copy-compute-copy sequence.
+                                      With more than one chunk the host entries keep stage state of their own, separate from quisk_cuda_rx_process */
 #define QC_RX_OPT_FUSED_MIN_R  4   /* minimum outputs per thread in its half-band stages: 0 (auto), 2, 4, 8 */
 int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value);
 /* Sum of the event-timed durations (ms) of the dominant kernel since the last call, and how

@@ -74,45 +74,6 @@ int launch_unpack_iq(const void *d_bytes, long byte_stride, int C, int count, in
 }
 
 // host bytes -> device -> unpack -> chain -> host audio
-int RxChain::process_host_packed(const void *h_bytes, long byte_stride, int count, int nb, int big,
-                                 double *h_audio, long audio_stride, int *n_audio)
-{
-    if (count <= 0) { if (n_audio) *n_audio = 0; return QC_OK; }
-    if (nb < 1 || nb > 4 || byte_stride < (long)count * 2 * nb) { set_error("rx_process_host_packed: bad sizes"); return QC_EINVAL; }
-    if (!hs) QC_CUDA(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
-    const int mo = max_out(count);
-    if (count > host_cap) {
-        if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out);
-        d_host_in = nullptr; d_host_out = nullptr;
-        host_cap = count; host_out_cap = mo;
-        QC_CUDA(cudaMalloc((void **)&d_host_in, (size_t)C * host_cap * sizeof(cd)));
-        QC_CUDA(cudaMalloc((void **)&d_host_out, (size_t)C * host_out_cap * sizeof(double)));
-    }
-    const size_t row = (size_t)count * 2 * nb;
-    if ((size_t)C * row > packed_cap) {
-        if (d_packed) cudaFree(d_packed);
-        d_packed = nullptr; packed_cap = 0;
-        QC_CUDA(cudaMalloc((void **)&d_packed, (size_t)C * row));
-        packed_cap = (size_t)C * row;
-    }
-    QC_CUDA(cudaMemcpy2DAsync(d_packed, row, h_bytes, (size_t)byte_stride, row, C, cudaMemcpyHostToDevice, hs));
-    int rc = launch_unpack_iq(d_packed, (long)row, C, count, nb, big, d_host_in, host_cap, hs);
-    if (rc != QC_OK) return rc;
-    int na = 0;
-    rc = host_noise_blanker(hs, count);
-    if (rc != QC_OK) return rc;
-    rc = process(d_host_in, host_cap, count, d_host_out, host_out_cap, &na, nullptr, 0, nullptr, hs);
-    if (rc != QC_OK) return rc;
-    const int nd = iq_out ? 2 * na : na;
-    if (nd > audio_stride) { set_error("rx_process_host_packed: audio_stride %ld < %d", audio_stride, nd); return QC_EINVAL; }
-    if (nd > 0)
-        QC_CUDA(cudaMemcpy2DAsync(h_audio, (size_t)audio_stride * sizeof(double), d_host_out, (size_t)host_out_cap * sizeof(double),
-                                  (size_t)nd * sizeof(double), C, cudaMemcpyDeviceToHost, hs));
-    QC_CUDA(cudaStreamSynchronize(hs));
-    if (n_audio) *n_audio = na;
-    return QC_OK;
-}
-
 }  // namespace qc
 
 extern "C" {

@@ -49,6 +49,20 @@ int RxChain::init(const qcRxConfig &cfg)
 {
     C = cfg.n_channels; sample_rate = cfg.sample_rate; mode = cfg.mode; fused = cfg.fused;
     if (C <= 0 || sample_rate <= 0) { set_error("rx_create: bad channel count / sample rate"); return QC_EINVAL; }
+    {   // keep what we were given: the pipelined host entries build channel-subset chains from it on first use
+        saved.cfg = cfg;
+        if (cfg.filt_i && cfg.n_filt > 0) saved.fi.assign(cfg.filt_i, cfg.filt_i + cfg.n_filt);
+        if (cfg.filt_q && cfg.n_filt > 0) saved.fq.assign(cfg.filt_q, cfg.filt_q + cfg.n_filt);
+        if (cfg.tune_hz) saved.tune.assign(cfg.tune_hz, cfg.tune_hz + C);
+        const double *const *tp = &cfg.tables.filt144D3;       // 13 (pointer, count) pairs in declaration order
+        const qcRxTables &T0 = cfg.tables;
+        const double *ptrs[13] = {T0.filt144D3, T0.filt240D5Sharp, T0.filt48dec24, T0.filt300D5, T0.audio24p4, T0.audio24p6, T0.lpFilt48,
+                                  T0.audioFmHp, T0.filt53D1, T0.filt111D2, T0.filt133D2, T0.filt167D3, T0.filt185D3};
+        const int cnts[13] = {T0.n_filt144D3, T0.n_filt240D5Sharp, T0.n_filt48dec24, T0.n_filt300D5, T0.n_audio24p4, T0.n_audio24p6, T0.n_lpFilt48,
+                              T0.n_audioFmHp, T0.n_filt53D1, T0.n_filt111D2, T0.n_filt133D2, T0.n_filt167D3, T0.n_filt185D3};
+        (void)tp;
+        for (int i = 0; i < 13; i++) if (ptrs[i] && cnts[i] > 0) saved.tab[i].assign(ptrs[i], ptrs[i] + cnts[i]);
+    }
     const qcRxTables &T = cfg.tables;
     // ---- quisk_process_decimate -------------------------------------------------
     int rate = sample_rate;
@@ -232,8 +246,47 @@ int RxChain::upload_nco()
     return QC_OK;
 }
 
+int RxChain::n_host_chunks() const
+{
+    int k = host_chunks > 0 ? host_chunks : (C >= 1024 ? 8 : 1);
+    if (k > C) k = C;
+    return k < 1 ? 1 : k;
+}
+
+void RxChain::release_sub_chains()
+{
+    for (RxChain *r : sub) { r->release(); delete r; }
+    sub.clear(); sub_c0.clear();
+}
+
+int RxChain::build_sub_chains(int k)
+{
+    release_sub_chains();
+    qcRxConfig cfg = saved.cfg;
+    cfg.filt_i = saved.fi.empty() ? nullptr : saved.fi.data();
+    cfg.filt_q = saved.fq.empty() ? nullptr : saved.fq.data();
+    const double **ptrs[13] = {&cfg.tables.filt144D3, &cfg.tables.filt240D5Sharp, &cfg.tables.filt48dec24, &cfg.tables.filt300D5, &cfg.tables.audio24p4,
+                               &cfg.tables.audio24p6, &cfg.tables.lpFilt48, &cfg.tables.audioFmHp, &cfg.tables.filt53D1, &cfg.tables.filt111D2,
+                               &cfg.tables.filt133D2, &cfg.tables.filt167D3, &cfg.tables.filt185D3};
+    for (int i = 0; i < 13; i++) *ptrs[i] = saved.tab[i].empty() ? nullptr : saved.tab[i].data();
+    for (int j = 0; j < k; j++) {
+        const int c0 = (int)((long)C * j / k), c1 = (int)((long)C * (j + 1) / k);
+        cfg.n_channels = c1 - c0;
+        cfg.tune_hz = saved.tune.empty() ? nullptr : saved.tune.data() + c0;
+        RxChain *r = new RxChain();
+        if (r->init(cfg) != QC_OK) { r->release(); delete r; release_sub_chains(); return QC_EINVAL; }
+        r->host_chunks = 1;
+        r->exact_nco = exact_nco; r->fused_tail = fused_tail; r->nb_level = nb_level; r->fused_chunk = fused_chunk; r->fused_threads = fused_threads;
+        r->fused_plans = fused_plans; r->fused_tailwarp = fused_tailwarp; r->fused_dense = fused_dense; r->fused_split = fused_split;
+        r->fused_min_r = fused_min_r; r->fused_deepk = fused_deepk;
+        sub.push_back(r); sub_c0.push_back(c0);
+    }
+    return QC_OK;
+}
+
 void RxChain::release()
 {
+    release_sub_chains();
     for (auto *f : cst) { f->release(); delete f; }
     for (auto *f : rst) { f->release(); delete f; }
     if (rxf) { rxf->release(); delete rxf; }
@@ -416,23 +469,36 @@ int RxChain::host_noise_blanker(cudaStream_t s, int count)
     return quisk_cuda_nb_run(nb, d_host_in, host_cap, count, nb_level, s);
 }
 
-int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, double *h_audio, long audio_stride, int *n_audio)
+// One chain's share of a host call, enqueued on its own stream `hs` and NOT waited for: H2D of the block (complex double,
+// or wire bytes + the widening kernel), the optional noise blanker, the chain, D2H of the audio.
+int RxChain::host_enqueue(const quisk_cd *h_iq, long iq_stride, const void *h_bytes, long byte_stride, int nb_, int big, int count,
+                          double *h_audio, long audio_stride, int *n_audio)
 {
-    if (count <= 0) { if (n_audio) *n_audio = 0; return QC_OK; }
     if (!hs) QC_CUDA(cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking));
     const int mo = max_out(count);
     if (count > host_cap) {
-        if (d_packed) cudaFree(d_packed);
-    d_packed = nullptr; packed_cap = 0;
-    if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out); if (h_pin) cudaFreeHost(h_pin);
+        if (d_host_in) cudaFree(d_host_in); if (d_host_out) cudaFree(d_host_out); if (h_pin) cudaFreeHost(h_pin);
         d_host_in = nullptr; d_host_out = nullptr; h_pin = nullptr;
         host_cap = count; host_out_cap = mo;
         QC_CUDA(cudaMalloc((void **)&d_host_in, (size_t)C * host_cap * sizeof(cd)));
         QC_CUDA(cudaMalloc((void **)&d_host_out, (size_t)C * host_out_cap * sizeof(double)));
     }
-    // H2D straight from the caller's memory (pinned by the caller or pageable), row by row layout kept
-    QC_CUDA(cudaMemcpy2DAsync(d_host_in, (size_t)host_cap * sizeof(cd), h_iq, (size_t)iq_stride * sizeof(cd),
-                              (size_t)count * sizeof(cd), C, cudaMemcpyHostToDevice, hs));
+    if (h_bytes) {
+        const size_t row = (size_t)count * 2 * nb_;
+        if ((size_t)C * row > packed_cap) {
+            if (d_packed) cudaFree(d_packed);
+            d_packed = nullptr; packed_cap = 0;
+            QC_CUDA(cudaMalloc((void **)&d_packed, (size_t)C * row));
+            packed_cap = (size_t)C * row;
+        }
+        QC_CUDA(cudaMemcpy2DAsync(d_packed, row, h_bytes, (size_t)byte_stride, row, C, cudaMemcpyHostToDevice, hs));
+        int rcu = launch_unpack_iq(d_packed, (long)row, C, count, nb_, big, d_host_in, host_cap, hs);
+        if (rcu != QC_OK) return rcu;
+    } else {
+        // H2D straight from the caller's memory (pinned by the caller or pageable), row by row layout kept
+        QC_CUDA(cudaMemcpy2DAsync(d_host_in, (size_t)host_cap * sizeof(cd), h_iq, (size_t)iq_stride * sizeof(cd),
+                                  (size_t)count * sizeof(cd), C, cudaMemcpyHostToDevice, hs));
+    }
     int na = 0;
     int rc = host_noise_blanker(hs, count);
     if (rc != QC_OK) return rc;
@@ -443,9 +509,44 @@ int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, doubl
     if (nd > 0)
         QC_CUDA(cudaMemcpy2DAsync(h_audio, (size_t)audio_stride * sizeof(double), d_host_out, (size_t)host_out_cap * sizeof(double),
                                   (size_t)nd * sizeof(double), C, cudaMemcpyDeviceToHost, hs));
-    QC_CUDA(cudaStreamSynchronize(hs));
     if (n_audio) *n_audio = na;
     return QC_OK;
+}
+
+static int host_call(RxChain &rx, const quisk_cd *h_iq, long iq_stride, const void *h_bytes, long byte_stride, int nb, int big, int count,
+                     double *h_audio, long audio_stride, int *n_audio)
+{
+    if (count <= 0) { if (n_audio) *n_audio = 0; return QC_OK; }
+    const int k = rx.n_host_chunks();
+    if (k <= 1) {
+        int rc = rx.host_enqueue(h_iq, iq_stride, h_bytes, byte_stride, nb, big, count, h_audio, audio_stride, n_audio);
+        if (rc != QC_OK) return rc;
+        QC_CUDA(cudaStreamSynchronize(rx.hs));
+        return QC_OK;
+    }
+    if ((int)rx.sub.size() != k) { int rc = rx.build_sub_chains(k); if (rc != QC_OK) return rc; }
+    int na = 0;
+    for (int j = 0; j < k; j++) {
+        const int c0 = rx.sub_c0[j];
+        int naj = 0;
+        int rc = rx.sub[j]->host_enqueue(h_iq ? h_iq + (size_t)c0 * iq_stride : nullptr, iq_stride,
+                                         h_bytes ? (const unsigned char *)h_bytes + (size_t)c0 * byte_stride : nullptr, byte_stride, nb, big, count,
+                                         h_audio + (size_t)c0 * audio_stride, audio_stride, &naj);
+        if (rc != QC_OK) return rc;
+        na = naj;
+    }
+    for (int j = 0; j < k; j++) QC_CUDA(cudaStreamSynchronize(rx.sub[j]->hs));
+    if (n_audio) *n_audio = na;
+    return QC_OK;
+}
+
+int RxChain::process_host(const quisk_cd *h_iq, long iq_stride, int count, double *h_audio, long audio_stride, int *n_audio)
+{ return host_call(*this, h_iq, iq_stride, nullptr, 0, 0, 0, count, h_audio, audio_stride, n_audio); }
+
+int RxChain::process_host_packed(const void *h_bytes, long byte_stride, int count, int nb_, int big, double *h_audio, long audio_stride, int *n_audio)
+{
+    if (count > 0 && (nb_ < 1 || nb_ > 4 || byte_stride < (long)count * 2 * nb_)) { set_error("rx_process_host_packed: bad sizes"); return QC_EINVAL; }
+    return host_call(*this, nullptr, 0, h_bytes, byte_stride, nb_, big, count, h_audio, audio_stride, n_audio);
 }
 
 int RxChain::reset()
@@ -457,6 +558,7 @@ int RxChain::reset()
     if (d_fm) { rc = reset_fm(); if (rc != QC_OK) return rc; }
     if (tune) { rc = upload_nco(); if (rc != QC_OK) return rc; }
     rc = reset_fused(); if (rc != QC_OK) return rc;
+    for (RxChain *r : sub) { rc = r->reset(); if (rc != QC_OK) return rc; }
     QC_CUDA(cudaDeviceSynchronize());
     poisoned = false;
     return QC_OK;
@@ -514,7 +616,12 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
     case QC_RX_OPT_TIMING: rx->rx.timing = value != 0; return QC_OK;
     case QC_RX_OPT_NOISE_BLANKER:
         if (value < 0 || value > 3) { qc::set_error("rx_set_option: noise blanker level must be 0 (off) .. 3"); return QC_EINVAL; }
-        rx->rx.nb_level = value; return QC_OK;
+        rx->rx.nb_level = value;
+        for (qc::RxChain *r : rx->rx.sub) r->nb_level = value;
+        return QC_OK;
+    case QC_RX_OPT_HOST_CHUNKS:
+        if (value < 0 || value > 64) { qc::set_error("rx_set_option: host chunks must be 0 (auto) .. 64"); return QC_EINVAL; }
+        rx->rx.host_chunks = value; return QC_OK;
     case QC_RX_OPT_FUSED_CHUNK:
         if (value < 128 || value > 2048) { qc::set_error("rx_set_option: chunk %d out of range", value); return QC_EINVAL; }
         rx->rx.fused_chunk = value; return QC_OK;

@@ -44,7 +44,21 @@ struct RxChain {
     cd *bufc[2] = {nullptr, nullptr};
     double *bufr[2] = {nullptr, nullptr};
     long cap = 0;
-    // host-buffer entry point
+    // host-buffer entry points.  With more than one chunk the channels are split over `sub` chains of their own (own
+    // streams, own stage state): chunk k's H2D copy, kernels and D2H copy overlap those of its neighbours, so a call costs
+    // max(copy in, compute, copy out) instead of their sum.  The host entries then carry their own stream state, separate
+    // from quisk_cuda_rx_process on the parent (a caller feeds a chain through one entry or the other, not both).
+    int host_chunks = 0;                // QC_RX_OPT_HOST_CHUNKS: 0 = auto (8 from 1024 channels up, else 1), 1 = off
+    std::vector<RxChain *> sub;
+    std::vector<int> sub_c0;
+    struct Saved {                      // what init() was given, kept so that the sub-chains can be built later
+        qcRxConfig cfg; std::vector<double> fi, fq, tune; std::vector<double> tab[13];
+    } saved;
+    int n_host_chunks() const;
+    int build_sub_chains(int k);
+    void release_sub_chains();
+    int host_enqueue(const quisk_cd *h_iq, long iq_stride, const void *h_bytes, long byte_stride, int nb, int big, int count,
+                     double *h_audio, long audio_stride, int *n_audio);
     cudaStream_t hs = nullptr;
     char *h_pin = nullptr;
     cd *d_host_in = nullptr; double *d_host_out = nullptr;

@@ -188,6 +188,8 @@ void Rxa::release()
     if (hs) { cudaStreamSynchronize(hs); cudaStreamDestroy(hs); hs = nullptr; }
     if (d_uslew) cudaFree(d_uslew); if (d_cup) cudaFree(d_cup);
     d_uslew = nullptr; d_cup = nullptr;
+    if (d_wide_spec) cudaFree(d_wide_spec); if (d_wide_y) cudaFree(d_wide_y);
+    d_wide_spec = d_wide_y = nullptr; wide_spec_cap = wide_y_cap = 0;
     if (d_sip) cudaFree(d_sip); if (d_sipout) cudaFree(d_sipout);
     d_sip = nullptr; d_sipout = nullptr; sipout_cap = 0;
     mid = mid2 = audio = nullptr;

@@ -28,6 +28,7 @@ static constexpr int RF_THREADS = 192;      // + AGC warp + LIN warp
 
 struct RxaFusedParams {
     const cd *in; long in_stride; cd *out; long out_stride;
+    const cd *in_adc; long adc_stride;      // what the ADC meter looks at when `in` is already filtered (the wide path); nullptr: `in`
     int n, nblocks, C;
     int n_fir; cd *prev[2]; cd *fdl[2]; const cd *mask[2]; int nfor[2]; int buffidx[2];
     const cd *tw;
@@ -48,7 +49,8 @@ __device__ __forceinline__ double rf_smag(cd v) { return __dadd_rn(__dmul_rn(v.x
 // Shared-memory map of one CTA (doubles after the transform buffer)
 struct RfSmem {
     cd *twl, *S;
-    double *SMS, *SMADC, *A, *RV, *BM, *SMAGC, *SC;
+    double *SMS, *SMADC, *A, *RV, *BM, *SMAGC, *SC, *FBA, *HBA;
+    volatile int *linpos;
 };
 __device__ __forceinline__ RfSmem rf_map(double *raw, int n, int tot)
 {
@@ -62,15 +64,19 @@ __device__ __forceinline__ RfSmem rf_map(double *raw, int n, int tot)
     m.RV = m.A + tot;                                       // [n] ring_max -> volts
     m.BM = m.RV + n;                                        // [(tot + 31) / 32 + 1] maxima of 32-sample blocks of A
     m.SMAGC = m.BM + ((tot + 31) / 32 + 1);                 // [n] |AGC output|^2 of the block just finished (the LIN warp reads it one block late)
-    m.SC = m.SMAGC + n;                                     // [16] 0..3 warp maxima, 4 np_adc, 5 np_s, 6 np_agc
+    m.SC = m.SMAGC + n;                                     // [16] 0..3 warp maxima, 4 np_adc, 5 np_s, 6 np_agc, 8.. LIN lanes' dummy store targets
+    m.FBA = m.SC + 48;                                      // [n] fast_backaverage after each sample (LIN lane 6), read by the AGC lane's general path
+    m.HBA = m.FBA + n;                                      // [n] hang_backaverage (LIN lane 7)
+    m.linpos = reinterpret_cast<volatile int *>(m.HBA + n); // how far the LIN warp has got in the current block
     return m;
 }
 
-// One sample through the reference's general machine (wcpAGC.c:195-333), same tests in the same order; expects
-// abs_out_sample and ring_max, advances i.
+// One sample through the reference's general machine (wcpAGC.c:195-333), same tests in the same order; expects ring_max,
+// advances i.  The two back averages (wcpAGC.c:192-193) only look at the input: the LIN warp computes them for the whole
+// block (lanes 6 and 7) and this path -- the only one that reads them -- waits until that warp has passed sample i.
 #define RF_AGC_GENERAL_STEP                                                                                             \
-    fb = __dadd_rn(__dmul_rn(k_fbm, abs_out_sample), __dmul_rn(k_ofbm, fb));                                            \
-    hb = __dadd_rn(__dmul_rn(k_hbm, abs_out_sample), __dmul_rn(k_ohbm, hb));                                            \
+    while (*linpos <= i) { }                                                                                            \
+    const double fb = FBA[i], hb = HBA[i];                                                                              \
     if (hang_counter > 0) --hang_counter;                                                                               \
     {                                                                                                                   \
         const double d = __dsub_rn(ring_max, volts);                                                                    \
@@ -94,80 +100,94 @@ __device__ __forceinline__ RfSmem rf_map(double *raw, int n, int tot)
         }                                                                                                               \
     }                                                                                                                   \
     if (volts < k_minv) volts = k_minv;                                                                                 \
-    if (store) RV[i] = volts;                                                                                           \
+    RV[i] = volts;                                                                                                      \
     i++;
 
 // ---- role 1: the AGC warp.  All 32 lanes run the same instructions on the same data (no divergence inside the warp, so the
-// CTA-wide barriers are reached by whole warps); lane 0 alone stores.
+// CTA-wide barriers are reached by whole warps) and store the same values to the same shared-memory words; lane 0 alone
+// writes the state back to global memory.  (A store predicated on the lane inside the dependent chain made the compiler
+// re-derive the chain from the chunk start for every store: 74 cycles per sample instead of 24.)
 // One block of the volts machine: A[i] = |sample leaving the delay line|, RV[i] = ring_max on the way in, volts on the way out.
-__device__ __forceinline__ void rf_agc_block(const double *A, double *RV, int n, const AgcParams &a, bool store,
-                                             double &volts, double &save_volts, double &fb, double &hb, int &hang_counter, int &decay_type, int &state_)
+__device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, const double *HBA, volatile int *linpos, int n, const AgcParams &a,
+                                             double &volts, double &save_volts, int &hang_counter, int &decay_type, int &state_, long long *dbg)
 {
-    const double k_fbm = a.fast_backmult, k_ofbm = a.onemfast_backmult, k_hbm = a.hang_backmult, k_ohbm = a.onemhang_backmult,
-                 k_attack = a.attack_mult, k_decay = a.decay_mult, k_hdecay = a.hang_decay_mult, k_fdecay = a.fast_decay_mult,
+    int n_single = 0;
+    const long long t_in = clock64();
+    const double k_attack = a.attack_mult, k_decay = a.decay_mult, k_hdecay = a.hang_decay_mult, k_fdecay = a.fast_decay_mult,
                  k_pop = a.pop_ratio, k_hlevel = a.hang_level, k_minv = a.min_volts;
     int i = 0;
-    // the next chunk's inputs are fetched while the current chain runs: their shared-memory latency never sits in front of it
-    double rmn[8], abn[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { rmn[j] = j < n ? RV[j] : 0.0; abn[j] = j < n ? A[j] : 0.0; }
+    // shared-memory accesses of the run loop go through 32-bit shared-window addresses kept in registers: left to itself the
+    // compiler re-derives the window base (an S2R of the cluster CTA id) at the top of every chunk, ~100 cycles in front of
+    // the chain each time
+    const unsigned rv_s = (unsigned)__cvta_generic_to_shared(RV);
+    constexpr int CH = 16;
     while (i < n) {
-        if (n - i >= 8 && (state_ == 0 || state_ >= 3)) {
-            // a run of eight samples on the assumption that the state does not change
+        if (n - i >= CH && (state_ == 0 || state_ >= 3) && !(volts < k_minv)) {      // (a fresh channel starts with volts = 0: the general path clamps it first)
+            // runs of sixteen samples on the assumption that the state does not change
             const double M = state_ == 0 ? k_attack : (state_ == 3 ? k_decay : k_hdecay);
             const bool want = state_ == 0;
-            double rm[8], ab[8];
+            double rm[CH], rn[CH];
+            unsigned a0 = rv_s + 8u * (unsigned)i;
 #pragma unroll
-            for (int j = 0; j < 8; j++) { rm[j] = rmn[j]; ab[j] = abn[j]; }
-            const int nx = i + 8;
-#pragma unroll
-            for (int j = 0; j < 8; j++) { rmn[j] = nx + j < n ? RV[nx + j] : 0.0; abn[j] = nx + j < n ? A[nx + j] : 0.0; }
-            double v = volts, f = fb, h = hb;
+            for (int j = 0; j < CH; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rm[j]) : "r"(a0 + 8u * j));
             bool ok = true;
+            while (ok && n - i >= CH) {
+                // the following run's ring_max is asked for now (RV beyond this run is still input): its latency hides under the chain
+                const bool more = n - i >= 2 * CH;
+                if (more) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool p = rm[j] >= v;
-                const double d = __dsub_rn(rm[j], v);
-                v = __dadd_rn(v, __dmul_rn(d, M));
-                f = __dadd_rn(__dmul_rn(k_fbm, ab[j]), __dmul_rn(k_ofbm, f));
-                h = __dadd_rn(__dmul_rn(k_hbm, ab[j]), __dmul_rn(k_ohbm, h));
-                ok = ok && p == want && !(v < k_minv);
-                if (store) RV[i + j] = v;                   // speculative: put back below if the run did not hold
-            }
-            if (ok) {
-                volts = v; fb = f; hb = h;
-                hang_counter = hang_counter > 8 ? hang_counter - 8 : 0;
-                i += 8;
-                continue;
-            }
-            // the run did not hold (a handful of times per block): ring_max goes back into RV and these eight samples go through
-            // the general machine one by one
-            if (store) {
+                    for (int j = 0; j < CH; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rn[j]) : "r"(a0 + 8u * (CH + j)));
+                }
+                double v = volts;
+                // The run holds if every d = ring_max - volts has the sign the state expects (d >= 0: attack, d < 0: decay; d is the
+                // chain's own first operation), read from the SIGN BITS with integer logic, off the chain.  The min_volts clamp needs
+                // no per-sample test: volts moves monotonically within a run (up in attack, down in decay), it entered the run at
+                // or above min_volts, so only a decay run's last value can fall below.
+                int s_and = -1, s_or = 0;
+                double vv[CH];
 #pragma unroll
-                for (int j = 0; j < 8; j++) RV[i + j] = rm[j];
+                for (int j = 0; j < CH; j++) {
+                    const double d = __dsub_rn(rm[j], v);
+                    v = __dadd_rn(v, __dmul_rn(d, M));
+                    const int hd = __double2hiint(d);
+                    s_and &= hd; s_or |= hd;
+                    vv[j] = v;
+                }
+                ok = want ? s_or >= 0 : (s_and < 0 && !(v < k_minv));
+                if (ok) {
+                    // commit (all lanes store the same values)
+#pragma unroll
+                    for (int j = 0; j < CH; j++) asm volatile("st.shared.f64 [%0], %1;" :: "r"(a0 + 8u * j), "d"(vv[j]) : "memory");
+                    volts = v;
+                    hang_counter = hang_counter > CH ? hang_counter - CH : 0;
+                    i += CH;
+                    a0 += 8u * CH;
+#pragma unroll
+                    for (int j = 0; j < CH; j++) rm[j] = rn[j];
+                }
             }
-            for (int g = 0; g < 8; g++) {
-                const double abs_out_sample = A[i], ring_max = g == 0 ? rm[0] : RV[i];
+            if (ok) continue;                               // fewer than a run's worth of samples left
+            // the run did not hold (a handful of times per block): these samples go through the general machine one by one
+            for (int g = 0; g < CH; g++) {
+                const double ring_max = RV[i];
                 RF_AGC_GENERAL_STEP
             }
-#pragma unroll
-            for (int j = 0; j < 8; j++) { rmn[j] = i + j < n ? RV[i + j] : 0.0; abn[j] = i + j < n ? A[i + j] : 0.0; }
             continue;
         }
         // one sample through the general machine (states 1 and 2, and the last few samples of a block)
         {
-            const double abs_out_sample = A[i], ring_max = RV[i];
+            const double ring_max = RV[i];
+            n_single++;
             RF_AGC_GENERAL_STEP
-#pragma unroll
-            for (int j = 0; j < 8; j++) { rmn[j] = i + j < n ? RV[i + j] : 0.0; abn[j] = i + j < n ? A[i + j] : 0.0; }
         }
     }
+    if (dbg) { dbg[24] = 0; dbg[25] = 0; dbg[26] = n_single; dbg[27] = clock64() - t_in; }
 }
 #undef RF_AGC_GENERAL_STEP
 
 __device__ __forceinline__ void rf_agc_role(const RxaFusedParams &P, const RfSmem &m, int n, bool agc_on, double *ast, bool lane0)
 {
-    double volts = ast[3], save_volts = ast[4], fb = ast[5], hb = ast[6];
+    double volts = ast[3], save_volts = ast[4];
     int hang_counter = (int)ast[7], decay_type = (int)ast[8], state_ = (int)ast[9];
     rf_bar_all();                                           // set-up done
     for (int b = 0; b < P.nblocks; b++) {
@@ -175,10 +195,10 @@ __device__ __forceinline__ void rf_agc_role(const RxaFusedParams &P, const RfSme
         long long t0 = 0;
         const bool stamp = P.dbg && blockIdx.x == 0 && b == P.nblocks - 1 && lane0;
         if (stamp) t0 = clock64();
-        if (agc_on) rf_agc_block(m.A, m.RV, n, P.a, lane0, volts, save_volts, fb, hb, hang_counter, decay_type, state_);
+        if (agc_on) rf_agc_block(m.RV, m.FBA, m.HBA, m.linpos, n, P.a, volts, save_volts, hang_counter, decay_type, state_, stamp ? P.dbg : nullptr);
         if (stamp) { P.dbg[3] = t0; P.dbg[4] = clock64(); }
         if (lane0 && agc_on && b == P.nblocks - 1) {
-            ast[3] = volts; ast[4] = save_volts; ast[5] = fb; ast[6] = hb;
+            ast[3] = volts; ast[4] = save_volts;             // ast[5], ast[6] (the back averages) belong to the LIN warp
             ast[7] = hang_counter; ast[8] = decay_type; ast[9] = state_; ast[10] = __dmul_rn(volts, P.a.inv_out_target);
         }
         rf_bar_all();                                       // volts ready for the gain law
@@ -189,8 +209,10 @@ __device__ __forceinline__ void rf_agc_role(const RxaFusedParams &P, const RfSme
 // ---- role 2: the LIN warp.  Lane l < 6: adc avg, adc peak, s avg, s peak, agc avg, agc peak; s = c1 * x[i] + c2 * s
 // (averages: c1 = 1 - mult, c2 = mult; peak decays: c1 = 0), one instruction stream for all lanes, inputs fetched one
 // group ahead of the dependent multiply-add chain.
-__device__ __forceinline__ double rf_lin_block(const double *x, int n, double c1, double c2, double s)
+__device__ __forceinline__ double rf_lin_block(const double *x, int n, double c1, double c2, double s, double *dst, int dstep, volatile int *pos)
 {
+    // dst / dstep: where the running value goes after every sample -- an [n] array for the two back-average lanes (dstep 1),
+    // a private dummy word for the others (dstep 0): one instruction stream, no lane-predicated store in the chain
     double xa[4], xb[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) xa[j] = j < n ? x[j] : 0.0;
@@ -199,47 +221,57 @@ __device__ __forceinline__ double rf_lin_block(const double *x, int n, double c1
 #pragma unroll
         for (int j = 0; j < 4; j++) xb[j] = i + 4 + j < n ? x[i + 4 + j] : 0.0;
         const double t0 = __dmul_rn(c1, xa[0]), t1 = __dmul_rn(c1, xa[1]), t2 = __dmul_rn(c1, xa[2]), t3 = __dmul_rn(c1, xa[3]);
-        s = __dadd_rn(__dmul_rn(c2, s), t0);
-        s = __dadd_rn(__dmul_rn(c2, s), t1);
-        s = __dadd_rn(__dmul_rn(c2, s), t2);
-        s = __dadd_rn(__dmul_rn(c2, s), t3);
+        s = __dadd_rn(__dmul_rn(c2, s), t0); dst[(i + 0) * dstep] = s;
+        s = __dadd_rn(__dmul_rn(c2, s), t1); dst[(i + 1) * dstep] = s;
+        s = __dadd_rn(__dmul_rn(c2, s), t2); dst[(i + 2) * dstep] = s;
+        s = __dadd_rn(__dmul_rn(c2, s), t3); dst[(i + 3) * dstep] = s;
+        if (pos && (i & 12) == 12) { __threadfence_block(); *pos = i + 4; }    // progress for the AGC lane's general path, every 16 samples
 #pragma unroll
         for (int j = 0; j < 4; j++) xa[j] = xb[j];
     }
-    for (; i < n; i++) s = __dadd_rn(__dmul_rn(c2, s), __dmul_rn(c1, x[i]));
+    for (; i < n; i++) { s = __dadd_rn(__dmul_rn(c2, s), __dmul_rn(c1, x[i])); dst[i * dstep] = s; if (pos) { __threadfence_block(); *pos = i + 1; } }
     return s;
 }
 
-__device__ __forceinline__ void rf_lin_role(const RxaFusedParams &P, const RfSmem &m, int n, int c, int lane, double *ast)
+__device__ __forceinline__ void rf_lin_role(const RxaFusedParams &P, const RfSmem &m, int n, int c, int lane, bool agc_on, double *ast)
 {
-    const int mt = lane < 6 ? lane >> 1 : 0, pk = lane & 1;
-    const bool live = lane < 6;
-    double s = live ? P.mst[mt][(size_t)c * 2 + pk] : 0.0;
-    const double c1 = !live || pk ? 0.0 : 1.0 - P.m_ma;     // (1.0 - mult_average), meter.c:90
-    const double c2 = !live ? 0.0 : (pk ? P.m_mp : P.m_ma);
-    const double *src = mt == 0 ? m.SMADC : (mt == 1 ? m.SMS : m.SMAGC);
+    // lanes 0..5: adc avg, adc peak, s avg, s peak, agc avg, agc peak; lanes 6, 7: the AGC's fast and hang back averages
+    const int mt = lane < 6 ? lane >> 1 : 3, pk = lane & 1;
+    const bool meter = lane < 6, back = agc_on && (lane == 6 || lane == 7), live = meter || back;
+    double s = meter ? P.mst[mt][(size_t)c * 2 + pk] : (back ? ast[lane - 1] : 0.0);        // ast[5] fast_backaverage, ast[6] hang_backaverage
+    double c1 = 0.0, c2 = 0.0;
+    if (meter) { c1 = pk ? 0.0 : 1.0 - P.m_ma; c2 = pk ? P.m_mp : P.m_ma; }                 // (1.0 - mult_average), meter.c:90
+    else if (lane == 6) { c1 = P.a.fast_backmult; c2 = P.a.onemfast_backmult; }             // wcpAGC.c:192
+    else if (lane == 7) { c1 = P.a.hang_backmult; c2 = P.a.onemhang_backmult; }             // wcpAGC.c:193
+    const double *src = mt == 0 ? m.SMADC : (mt == 1 ? m.SMS : (mt == 2 ? m.SMAGC : m.A));
+    double *dst = lane == 6 ? m.FBA : (lane == 7 ? m.HBA : m.SC + 8 + lane);
+    const int dstep = lane == 6 || lane == 7 ? 1 : 0;
+    if (lane == 0) *m.linpos = 0;
     rf_bar_all();
     for (int b = 0; b < P.nblocks; b++) {
         rf_bar_all();
-        if (mt < 2 || b > 0) {                              // the AGC meter runs one block late
-            const double r = rf_lin_block(src, n, c1, c2, s);
-            if (live) { s = r; if (pk) { const double np = m.SC[4 + mt]; if (np > s) s = np; } }     // meter.c:95
-        }
+        // the AGC meter runs one block late (its input is the gain law's output); its lanes idle through the first block
+        const bool run = mt != 2 || b > 0;
+        // (an idle lane still runs the instruction stream, with c1 = 0: its input must be finite -- SMAGC is not written yet)
+        const double r = rf_lin_block(run ? src : m.SMS, n, run ? c1 : 0.0, run ? c2 : 1.0, s, dst, dstep, m.linpos);
+        if (live) { s = r; if (meter && pk && run) { const double np = m.SC[4 + mt]; if (np > s) s = np; } }     // meter.c:95
         if (P.dbg && blockIdx.x == 0 && b == P.nblocks - 1 && lane == 0) P.dbg[5] = clock64();
         rf_bar_all();
-        if (P.dbg && blockIdx.x == 0 && b == P.nblocks - 1 && lane == 0) P.dbg[13] = clock64();
+        if (lane == 0) *m.linpos = 0;
         rf_bar_all();
     }
     // the AGC meter's last block, then the meters' states and readings
-    if (mt == 2 && P.nblocks > 0) {
-        const double r = rf_lin_block(m.SMAGC, n, c1, c2, s);
-        if (live) { s = r; if (pk) { const double np = m.SC[6]; if (np > s) s = np; } }
+    if (P.nblocks > 0) {
+        const double r = rf_lin_block(m.SMAGC, n, mt == 2 ? c1 : 0.0, mt == 2 ? c2 : 1.0, s, m.SC + 8 + lane, 0, nullptr);
+        if (mt == 2) { s = r; if (pk) { const double np = m.SC[6]; if (np > s) s = np; } }
     }
-    if (live) {
+    if (meter) {
         P.mst[mt][(size_t)c * 2 + pk] = s;
         P.mres[mt][(size_t)c * 3 + pk] = 10.0 * mlog10_dev(P.mtable, s + 1.0e-40);
         if (lane == 4) P.mres[2][(size_t)c * 3 + 2] = 20.0 * mlog10_dev(P.mtable, ast[10] + 1.0e-40);      // meter.c:99: *pgain = the AGC's gain
         else if (!pk) P.mres[mt][(size_t)c * 3 + 2] = 0.0;                                                  // the other two have no gain reading
+    } else if (back) {
+        ast[lane - 1] = s;
     }
 }
 
@@ -255,21 +287,32 @@ __device__ __forceinline__ void rf_block_max(double lm, double *scratch4, double
 // One fircore turn as a real call: its register allocation (the transform's sixteen points per thread, the four-bin MAC) is
 // then separate from the worker loop's, which carries two dozen pointers of its own.
 __device__ __noinline__ void rf_fircore(cd *S, const cd *twl, cd *pv, cd *fd, const cd *__restrict__ fmask, int nfor, int bi, int n, int tid,
-                                        const cd *__restrict__ x)
+                                        const cd *__restrict__ x, double *smag_x, long long *dbg)
 {
     const int n2 = 2 * n;
+    if (dbg && tid == 0) dbg[0] = clock64();
     if (x) {
-        for (int i = tid; i < n; i += RF_WORK) { const cd v = x[i]; S[fsw(i)] = pv[i]; S[fsw(n + i)] = v; pv[i] = v; }
-    } else {                                                // second fircore of the chain: its input is the first one's output
-        cd t0[8];                                           // n <= 1024: at most 8 samples per worker
+        // all of this thread's loads (the block and the previous block, both behind L2) are issued before anything waits on one
+        cd xv[8], pvv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const int i = tid + k * RF_WORK; if (i < n) t0[k] = S[fsw(i)]; }
+        for (int k = 0; k < 8; k++) { const int i = tid + k * RF_WORK; if (i < n) { xv[k] = x[i]; pvv[k] = pv[i]; } }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = tid + k * RF_WORK;
+            if (i < n) { S[fsw(i)] = pvv[k]; S[fsw(n + i)] = xv[k]; pv[i] = xv[k]; if (smag_x) smag_x[i] = rf_smag(xv[k]); }
+        }
+    } else {                                                // second fircore of the chain: its input is the first one's output
+        cd t0[8], pvv[8];                                   // n <= 1024: at most 8 samples per worker
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int i = tid + k * RF_WORK; if (i < n) { t0[k] = S[fsw(i)]; pvv[k] = pv[i]; } }
         rf_bar_work();
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const int i = tid + k * RF_WORK; if (i < n) { S[fsw(i)] = pv[i]; S[fsw(n + i)] = t0[k]; pv[i] = t0[k]; } }
+        for (int k = 0; k < 8; k++) { const int i = tid + k * RF_WORK; if (i < n) { S[fsw(i)] = pvv[k]; S[fsw(n + i)] = t0[k]; pv[i] = t0[k]; } }
     }
     rf_bar_work();
+    if (dbg && tid == 0) dbg[1] = clock64();
     fft_smem<1, RF_WORK>(S, n2, twl, -1, tid, RF_WORK);
+    if (dbg && tid == 0) dbg[2] = clock64();
     const int mask = nfor - 1;
     // partition MAC, four bins at a time with every load of the four issued before the arithmetic: the older spectra and the
     // masks come from L2, and one bin after another would pay that latency sixteen times over
@@ -285,25 +328,40 @@ __device__ __noinline__ void rf_fircore(cd *S, const cd *twl, cd *pv, cd *fd, co
             }
         }
         int k = bi;
-        for (int j = 1; j < nfor; j++) {
-            k = (k + mask) & mask;
-            const cd *fk = fd + (size_t)k * n2 + i0, *mk = fmask + (size_t)j * n2 + i0;
-            cd Y[4], mm[4];
+        for (int j = 1; j < nfor; j += 3) {
+            // up to three older spectra x four bins: 24 loads in flight per thread, then the arithmetic in the reference's order
+            cd Y[3][4], mm[3][4];
+            int kk = k;
 #pragma unroll
-            for (int u = 0; u < 4; u++) { if (i0 + u * RF_WORK < n2) { Y[u] = fk[u * RF_WORK]; mm[u] = mk[u * RF_WORK]; } }
+            for (int jj = 0; jj < 3; jj++) {
+                kk = (kk + mask) & mask;
+                if (j + jj < nfor) {
+                    const cd *fk = fd + (size_t)kk * n2 + i0, *mk = fmask + (size_t)(j + jj) * n2 + i0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (i0 + u * RF_WORK < n2) {
-                    acc[u].x += Y[u].x * mm[u].x - Y[u].y * mm[u].y;
-                    acc[u].y += Y[u].x * mm[u].y + Y[u].y * mm[u].x;
+                    for (int u = 0; u < 4; u++) { if (i0 + u * RF_WORK < n2) { Y[jj][u] = fk[u * RF_WORK]; mm[jj][u] = mk[u * RF_WORK]; } }
                 }
             }
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++) {
+                if (j + jj < nfor) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (i0 + u * RF_WORK < n2) {
+                            acc[u].x += Y[jj][u].x * mm[jj][u].x - Y[jj][u].y * mm[jj][u].y;
+                            acc[u].y += Y[jj][u].x * mm[jj][u].y + Y[jj][u].y * mm[jj][u].x;
+                        }
+                    }
+                }
+            }
+            k = kk;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) { const int i = i0 + u * RF_WORK; if (i < n2) { fd[(size_t)bi * n2 + i] = X[u]; S[fsw(i)] = acc[u]; } }
     }
     rf_bar_work();
+    if (dbg && tid == 0) dbg[3] = clock64();
     fft_smem<1, RF_WORK>(S, n2, twl, +1, tid, RF_WORK);
+    if (dbg && tid == 0) dbg[4] = clock64();
 }
 
 __device__ __forceinline__ void rf_worker_role(const RxaFusedParams &P, const RfSmem &m, int n, int c, int tid, bool agc_on, int ab, double *hs)
@@ -322,11 +380,16 @@ __device__ __forceinline__ void rf_worker_role(const RxaFusedParams &P, const Rf
         // overlaps the transforms instead of standing in front of that phase
         if (agc_on) for (int i = tid; i < ab; i += RF_WORK) A[i] = hs[i * 3 + 2];
         if (P.n_fir > 0) rf_fircore(S, m.twl, P.prev[0] + (size_t)c * n, P.fdl[0] + (size_t)c * P.nfor[0] * 2 * n, P.mask[0], P.nfor[0],
-                                    (P.buffidx[0] + b) & (P.nfor[0] - 1), n, tid, x);
+                                    (P.buffidx[0] + b) & (P.nfor[0] - 1), n, tid, x, RV, stamp ? P.dbg + 16 : nullptr);
         if (P.n_fir > 1) rf_fircore(S, m.twl, P.prev[1] + (size_t)c * n, P.fdl[1] + (size_t)c * P.nfor[1] * 2 * n, P.mask[1], P.nfor[1],
-                                    (P.buffidx[1] + b) & (P.nfor[1] - 1), n, tid, nullptr);
+                                    (P.buffidx[1] + b) & (P.nfor[1] - 1), n, tid, nullptr, nullptr, nullptr);
         if (P.n_fir == 0) {
-            for (int i = tid; i < n; i += RF_WORK) S[fsw(i)] = x[i];
+            const cd *xa = P.in_adc ? P.in_adc + (size_t)c * P.adc_stride + (size_t)b * n : x;
+            cd xv[8], av[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int i = tid + k * RF_WORK; if (i < n) { xv[k] = x[i]; av[k] = xa[i]; } }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int i = tid + k * RF_WORK; if (i < n) { S[fsw(i)] = xv[k]; RV[i] = rf_smag(av[k]); } }
             rf_bar_work();
         }
         if (stamp) P.dbg[1] = clock64();
@@ -334,7 +397,7 @@ __device__ __forceinline__ void rf_worker_role(const RxaFusedParams &P, const Rf
         double mx_adc = 0.0, mx_s = 0.0;
         for (int i = tid; i < n; i += RF_WORK) {
             const cd v = S[fsw(i)];
-            const double sm = rf_smag(v), sa = rf_smag(x[i]);
+            const double sm = rf_smag(v), sa = RV[i];         // |x|^2 was parked in RV when the block was loaded
             m.SMS[i] = sm; m.SMADC[i] = sa;
             mx_s = sm > mx_s ? sm : mx_s; mx_adc = sa > mx_adc ? sa : mx_adc;
             if (agc_on) {
@@ -395,18 +458,27 @@ __device__ __forceinline__ void rf_worker_role(const RxaFusedParams &P, const Rf
         if (stamp) P.dbg[6] = clock64();
         // ---- gain law, panel, output, siphon, AGC history
         double mx_agc = 0.0;
-        for (int i = tid; i < n; i += RF_WORK) {
+        cd dl[8];                                           // the delayed samples: history (behind L2) or this block, all asked for first
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = tid + k * RF_WORK;
+            if (i < n) {
+                if (agc_on && i < ab) dl[k] = make_double2(hs[i * 3], hs[i * 3 + 1]);
+                else dl[k] = S[fsw(agc_on ? i - ab : i)];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = tid + k * RF_WORK;
+            if (i >= n) continue;
             cd o;
+            const cd d = dl[k];
             if (agc_on) {
                 const double volts = RV[i];
                 const double lg = log10(__dmul_rn(P.a.inv_max_input, volts));
                 const double mult = __ddiv_rn(__dsub_rn(P.a.out_target, __dmul_rn(P.a.slope_constant, 0.0 < lg ? 0.0 : lg)), volts);
-                cd d;
-                if (i < ab) d = make_double2(hs[i * 3], hs[i * 3 + 1]);
-                else d = S[fsw(i - ab)];
                 o = make_double2(__dmul_rn(d.x, mult), __dmul_rn(d.y, mult));
             } else {
-                const cd d = S[fsw(i)];
                 o = P.agc_run ? make_double2(__dmul_rn(P.a.fixed_gain, d.x), __dmul_rn(P.a.fixed_gain, d.y)) : d;
             }
             const double sm = rf_smag(o);
@@ -443,7 +515,8 @@ __device__ __forceinline__ void rf_worker_role(const RxaFusedParams &P, const Rf
     }
 }
 
-__global__ void __launch_bounds__(RF_THREADS, 2) rxa_ssb_fused_kernel(RxaFusedParams P)
+template <int MINB>
+__global__ void __launch_bounds__(RF_THREADS, MINB) rxa_ssb_fused_kernel(RxaFusedParams P)
 {
     extern __shared__ double smem_raw[];
     const int n = P.n, c = blockIdx.x, tid = threadIdx.x;
@@ -455,13 +528,96 @@ __global__ void __launch_bounds__(RF_THREADS, 2) rxa_ssb_fused_kernel(RxaFusedPa
     double *ast = P.agc_state + (size_t)c * 16;
     if (tid < RF_WORK) rf_worker_role(P, m, n, c, tid, agc_on, ab, hs);
     else if (tid < RF_WORK + 32) rf_agc_role(P, m, n, agc_on, ast, tid == RF_WORK);
-    else rf_lin_role(P, m, n, c, tid - RF_WORK - 32, ast);
+    else rf_lin_role(P, m, n, c, tid - RF_WORK - 32, agc_on, ast);
+}
+
+
+// ---- the wide path: many DSP blocks per launch.  The overlap-save filter only carries state through its stored spectra,
+// so the transforms of ALL blocks of ALL channels are independent: a grid of (channel, block) CTAs does every forward
+// transform (fir_fwd_kernel), a second one every partition MAC + inverse transform (fir_mac_kernel: block b adds the spectra
+// of blocks b, b - 1, ... b - nfor + 1, reaching back into the frequency-domain delay line of the previous launch for the
+// first few), and only what is truly sequential along time -- the AGC's volts machine and the meters' averages -- runs one
+// CTA per channel over the blocks (the kernel above with n_fir = 0).  Same arithmetic per block as xfircore
+// (wdsp/firmin.c:409-430) in the same order.
+__global__ void __launch_bounds__(256) fir_fwd_kernel(const cd *in, long in_stride, int n, const cd *prev /*[C][n]*/, cd *spec /*[C][nblocks][2n]*/, int nblocks, const cd *tw)
+{
+    extern __shared__ double smem_raw[];
+    const int n2 = 2 * n, c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *S = twl + fft_tw_entries(n2);
+    fft_stage_twiddles(twl, tw, n2);
+    const cd *x = in + (size_t)c * in_stride + (size_t)b * n;
+    const cd *pv = b == 0 ? prev + (size_t)c * n : x - n;
+    for (int i = tid; i < n; i += nt) { S[fsw(i)] = pv[i]; S[fsw(n + i)] = x[i]; }
+    __syncthreads();
+    fft_smem<1>(S, n2, twl, -1, tid, nt);
+    cd *sp = spec + ((size_t)c * nblocks + b) * n2;
+    for (int i = tid; i < n2; i += nt) sp[i] = S[fsw(i)];
+}
+
+__global__ void __launch_bounds__(256) fir_mac_kernel(const cd *spec, int nblocks, int n, int nfor, int bi0, const cd *fdl /*[C][nfor][2n]*/,
+                                                       const cd *__restrict__ fmask, cd *out, long out_stride, const cd *tw)
+{
+    extern __shared__ double smem_raw[];
+    const int n2 = 2 * n, c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *S = twl + fft_tw_entries(n2);
+    fft_stage_twiddles(twl, tw, n2);
+    const int mask = nfor - 1;
+    const cd *sp = spec + (size_t)c * nblocks * n2;
+    const cd *fd = fdl + (size_t)c * nfor * n2;
+    for (int i = tid; i < n2; i += nt) {
+        const cd X = sp[(size_t)b * n2 + i];
+        const cd m0 = fmask[i];
+        cd acc = make_double2(X.x * m0.x - X.y * m0.y, X.x * m0.y + X.y * m0.x);
+        for (int j = 1; j < nfor; j++) {
+            // the spectrum of j blocks ago: this launch's if there is one, else the delay line's (ring index bi0 is block 0's slot)
+            const cd Y = b - j >= 0 ? sp[(size_t)(b - j) * n2 + i] : fd[(size_t)((bi0 + b - j) & mask) * n2 + i];
+            const cd m = fmask[(size_t)j * n2 + i];
+            acc.x += Y.x * m.x - Y.y * m.y;
+            acc.y += Y.x * m.y + Y.y * m.x;
+        }
+        S[fsw(i)] = acc;
+    }
+    __syncthreads();
+    fft_smem<1>(S, n2, twl, +1, tid, nt);
+    cd *y = out + (size_t)c * out_stride + (size_t)b * n;
+    for (int i = tid; i < n; i += nt) y[i] = S[fsw(i)];
+}
+
+// one fircore over nblocks blocks of every channel: transforms wide, then the delay line and `prev` brought up to date
+static int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_stride, int nblocks, cd *spec, cudaStream_t s)
+{
+    const int n = f->size, n2 = 2 * n, lanes = fft_threads(n2), C = f->C, nfor = f->nfor;
+    const size_t sh = ((size_t)n2 + fft_tw_entries(n2)) * sizeof(cd);
+    if (sh > 48 * 1024) {
+        QC_CUDA(cudaFuncSetAttribute(fir_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        QC_CUDA(cudaFuncSetAttribute(fir_mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    }
+    fir_fwd_kernel<<<dim3(C, nblocks), lanes, sh, s>>>(in, in_stride, n, f->d_prev, spec, nblocks, f->tw);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    // the last input block becomes `prev` now: the forward transforms have read the old one, and with in == out (second filter
+    // of a chain) the MAC kernel is about to overwrite the input
+    QC_CUDA(cudaMemcpy2DAsync(f->d_prev, (size_t)n * sizeof(cd), in + (size_t)(nblocks - 1) * n, (size_t)in_stride * sizeof(cd), (size_t)n * sizeof(cd), C,
+                              cudaMemcpyDeviceToDevice, s));
+    fir_mac_kernel<<<dim3(C, nblocks), lanes, sh, s>>>(spec, nblocks, n, nfor, f->buffidx, f->d_fdl, f->d_mask[f->cset], out, out_stride, f->tw);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    // state for the next call: the newest min(nblocks, nfor) spectra into their ring slots
+    for (int b = nblocks > nfor ? nblocks - nfor : 0; b < nblocks; b++) {
+        const int slot = (f->buffidx + b) & (nfor - 1);
+        QC_CUDA(cudaMemcpy2DAsync(f->d_fdl + (size_t)slot * n2, (size_t)nfor * n2 * sizeof(cd), spec + (size_t)b * n2, (size_t)nblocks * n2 * sizeof(cd),
+                                  (size_t)n2 * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
+    }
+    f->buffidx = (f->buffidx + nblocks) & (nfor - 1);
+    return QC_OK;
 }
 
 size_t rxa_fused_smem(int n, int ab)
 {
     const int n2 = 2 * n, tot = ab + n;
-    return ((size_t)fft_tw_entries(n2) + n2) * sizeof(cd) + ((size_t)tot + n + ((tot + 31) / 32 + 1) + n + 16) * sizeof(double);
+    return ((size_t)fft_tw_entries(n2) + n2) * sizeof(cd) + ((size_t)tot + n + ((tot + 31) / 32 + 1) + n + 48 + 2 * n + 2) * sizeof(double);
 }
 
 // The configurations this kernel covers: no shifter, no resamplers, side-band modes (neither demodulator running), dsp_size
@@ -482,8 +638,26 @@ int Rxa::xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, 
     P.in = (const cd *)din; P.in_stride = is; P.out = (cd *)dout; P.out_stride = os;
     P.n = dsp_size; P.nblocks = nblocks; P.C = C;
     FirCore *firs[2] = {nbp_run ? nbp0 : nullptr, bp1_run ? bp1 : nullptr};
+    const bool wide = nblocks >= 2 && (firs[0] || firs[1]) && !getenv("QUISK_RXA_NARROW");
+    if (wide) {
+        // filters first, all blocks at once, into the filtered-stream scratch; the sequential kernel then starts from there
+        const size_t need_spec = (size_t)C * nblocks * 2 * dsp_size, need_y = (size_t)C * nblocks * dsp_size;
+        if (need_spec > wide_spec_cap) { if (d_wide_spec) cudaFree(d_wide_spec); d_wide_spec = nullptr; wide_spec_cap = 0;
+                                         QC_CUDA(cudaMalloc((void **)&d_wide_spec, need_spec * sizeof(cd))); wide_spec_cap = need_spec; }
+        if (need_y > wide_y_cap) { if (d_wide_y) cudaFree(d_wide_y); d_wide_y = nullptr; wide_y_cap = 0;
+                                   QC_CUDA(cudaMalloc((void **)&d_wide_y, need_y * sizeof(cd))); wide_y_cap = need_y; }
+        const cd *cur = (const cd *)din; long cs = is;
+        const long ys = (long)nblocks * dsp_size;
+        for (FirCore *f : firs) {
+            if (!f) continue;
+            int rc = fircore_wide(f, cur, cs, d_wide_y, ys, nblocks, d_wide_spec, s); if (rc != QC_OK) return rc;
+            cur = d_wide_y; cs = ys;                       // a second filter runs in place on the scratch (each kernel pair reads before it writes per block: see below)
+        }
+        P.in_adc = (const cd *)din; P.adc_stride = is;
+        P.in = d_wide_y; P.in_stride = ys;
+    }
     for (FirCore *f : firs) {
-        if (!f) continue;
+        if (!f || wide) continue;
         const int k = P.n_fir++;
         P.prev[k] = f->d_prev; P.fdl[k] = f->d_fdl; P.mask[k] = f->d_mask[f->cset]; P.nfor[k] = f->nfor; P.buffidx[k] = f->buffidx;
         P.tw = f->tw;
@@ -499,9 +673,11 @@ int Rxa::xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, 
     P.sip = sip_run ? d_sip : nullptr; P.sipsize = sipsize; P.sip_idx = sip_idx;
     static long long *d_dbg = nullptr;
     if (getenv("QUISK_RXA_DEBUG")) {
-        if (!d_dbg) { cudaMalloc((void **)&d_dbg, 16 * sizeof(long long)); cudaMemset(d_dbg, 0, 16 * sizeof(long long)); }
+        if (!d_dbg) { cudaMalloc((void **)&d_dbg, 32 * sizeof(long long)); cudaMemset(d_dbg, 0, 32 * sizeof(long long)); }
         else {
-            long long h[16]; cudaDeviceSynchronize(); cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            long long h[32]; cudaDeviceSynchronize(); cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "rxa fused fircore: load %lld fft %lld mac %lld ifft %lld | agc block: full %lld failed %lld single %lld cycles %lld\n", h[17] - h[16], h[18] - h[17], h[19] - h[18], h[20] - h[19],
+                    h[24], h[25], h[26], h[27]);
             fprintf(stderr, "rxa fused stamps rel. to block start: fir_end %lld mags_end %lld w_afterA %lld agc_start %lld agc_end %lld lin_end %lld lin_afterB %lld w_afterB %lld w_end %lld\n",
                     h[1] - h[0], h[2] - h[0], h[12] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[13] - h[0], h[6] - h[0], h[7] - h[0]);
             fprintf(stderr, "rxa fused phases (cycles): fir %lld  mags/ring_max %lld  agc lane %lld  lin lane %lld  seq phase %lld  gain/out %lld\n",
@@ -511,11 +687,22 @@ int Rxa::xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, 
     }
     const int ab = agc_run && agc->agc.mode != 0 ? agc->agc.attack_buffsize : 0;
     const size_t sh = rxa_fused_smem(dsp_size, ab);
-    if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_ssb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    rxa_ssb_fused_kernel<<<C, RF_THREADS, sh, s>>>(P);
+    // few channels: one CTA per SM anyway, so the kernel may have every register (no spills in the transforms); many channels:
+    // two CTAs per SM matter more than the spills
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const char *force = getenv("QUISK_RXA_MINB");
+    const bool fat = force ? atoi(force) == 1 : C <= n_sm;
+    if (fat) {
+        if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_ssb_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        rxa_ssb_fused_kernel<1><<<C, RF_THREADS, sh, s>>>(P);
+    } else {
+        if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_ssb_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        rxa_ssb_fused_kernel<2><<<C, RF_THREADS, sh, s>>>(P);
+    }
     count_launch();
     QC_CUDA_LAUNCH();
-    for (FirCore *f : firs) if (f) f->buffidx = (f->buffidx + nblocks) & (f->nfor - 1);
+    if (!wide) for (FirCore *f : firs) if (f) f->buffidx = (f->buffidx + nblocks) & (f->nfor - 1);
     if (sip_run && dsp_size < sipsize) sip_idx = (int)(((long)sip_idx + (long)nblocks * dsp_size) & (sipsize - 1));
     return QC_OK;
 }

@@ -327,3 +327,39 @@ def test_rx_process_host_noise_blanker(packed, torch, tabs):
         assert n0 == n1 > 0
         assert np.array_equal(y0[:, :n0], y1[:, :n1])
     a_nb.close(); a_ref.close()
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_rx_process_host_pipelined_chunks(packed, torch, tabs):
+    """QC_RX_OPT_HOST_CHUNKS (15): the host entries split the channels into chunks whose H2D copy, kernels and D2H copy
+    overlap on streams of their own.  Each chunk is a chain over a channel subset, so the audio must be the same bits as
+    the single-sequence entry, call after call (state carries inside the chunks), for per-channel tuning and a channel
+    count the chunks do not divide."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    C, n, nblk, rate = 11, 15360, 3, 1536000
+    tune = [1000.0 * (c + 1) for c in range(C)]
+    if packed:
+        rng = np.random.default_rng(43)
+        xi = rng.integers(-20000, 20000, size=(C, n * nblk, 2)).astype(np.int16)
+    else:
+        x = np.stack([O.synth_iq(n * nblk, 30 + c, 1.0) for c in range(C)])
+    res = {}
+    for chunks in (1, 4):
+        rx = RxChain(C, rate, "USB", fi, fq, tabs, tune_hz=tune, fused=True)
+        rx.set_option(15, chunks)
+        outs = []
+        for b in range(nblk):
+            a = np.zeros((C, rx.max_out(n)))
+            if packed:
+                raw = np.ascontiguousarray(xi[:, b * n:(b + 1) * n].reshape(C, -1).view(np.uint8))
+                na = rx.process_host_packed(raw, n, 2, False, a)
+            else:
+                na = rx.process_host(np.ascontiguousarray(x[:, b * n:(b + 1) * n]), n, a)
+            outs.append(a[:, :na].copy())
+        res[chunks] = np.concatenate(outs, axis=1)
+        rx.close()
+    assert res[1].shape[1] == nblk * n // 32 and np.abs(res[1]).max() > 0
+    assert np.array_equal(res[1], res[4])
+    assert not np.array_equal(res[1][0], res[1][1])          # channels really differ (own tuning, own input)

@@ -46,7 +46,7 @@ __device__ __forceinline__ double agc_run(const double *A, double *RV, int n, do
             v = __dadd_rn(v, __dmul_rn(d, M));
             f = __dadd_rn(__dmul_rn(kf, ab[j]), __dmul_rn(kof, f));
             ok = ok && !p && !(v < minv);
-            if (store) RV[i + j] = v;
+            RV[i + j] = v; (void)store;
         }
         i += 8;
     }
