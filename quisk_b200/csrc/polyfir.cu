@@ -162,6 +162,100 @@ __global__ void __launch_bounds__(TM) polyfir_kernel(PolyFirParams p, int tiles,
         reinterpret_cast<T *>(p.out)[(long)c * p.out_stride + m] = scale(acc, p.gain);
 }
 
+
+// ---- register-blocked decimating FIR: complex samples, real taps, L = 1, M a power of two.
+// The generic kernel above pays one 16-byte shared-memory load per (output, tap) for four FP64 operations, which pins the
+// 1121-tap / 8 WDSP resampler (resample.c:121-157) to half of what the FP64 pipe could do.  Here a thread owns R consecutive
+// outputs and walks the SAMPLES it needs from the newest down: sample s meets output r at tap k_r = src_r - s, so one loaded
+// sample feeds R accumulators, each of which still receives its products in ascending-k order with separately rounded
+// multiply and add -- the same bits as the generic kernel and as the reference.  Taps sit in shared memory behind M (R - 1)
+// zeros at both ends, so every (sample, output) pair has a tap (a zero tap adds +0: exact); the R tap loads per step are
+// broadcasts.  Samples are staged with one pad element every R M so that the lane stride R M + 1 is odd.
+template <int R, int NT>
+__global__ void __launch_bounds__(NT) decim_rb_kernel(PolyFirParams p, int tiles, int pad_sh)
+{
+    extern __shared__ double smem[];
+    const int c = blockIdx.x / tiles, tile = blockIdx.x % tiles, tid = threadIdx.x;
+    const int M = p.M, K = p.K;
+    const int m0 = tile * NT * R;
+    if (tile == 0) write_hist<cd>(p, c);
+    if (m0 >= p.n_out) return;
+    const int zpad = M * (R - 1);
+    double *hp = smem;                                          // [K + 2 zpad] zero-padded taps
+    const int nh = K + 2 * zpad + 1;                            // + 1: the tap prefetch of the step behind the last one
+    cd *sX = reinterpret_cast<cd *>(smem + ((nh + 1) & ~1));
+    for (int i = tid; i < nh; i += NT) hp[i] = (i >= zpad && i < zpad + K) ? p.coef[i - zpad] : 0.0;
+    const long lo = p.u0 + (long)m0 * M - (K - 1);              // oldest sample the tile touches
+    const int nx = (NT * R - 1) * M + K;
+    // staging with eight loads in flight per thread (one after the other they would cost as much as the arithmetic)
+    if (lo >= 0 && lo + nx <= p.n_in) {
+        const cd *g = reinterpret_cast<const cd *>(p.in) + (long)c * p.in_stride + lo;
+        for (int i0 = tid; i0 < nx; i0 += 8 * NT) {
+            cd v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + u * NT; if (i < nx) v[u] = g[i]; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + u * NT; if (i < nx) sX[i + (i >> pad_sh)] = v[u]; }
+        }
+    } else {
+        for (int i = tid; i < nx; i += NT) sX[i + (i >> pad_sh)] = load_x<cd>(p, c, lo + i);
+    }
+    __syncthreads();
+    cd acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = make_double2(0.0, 0.0);
+    const int top = (tid * R + R - 1) * M + (K - 1);            // staged index of this thread's newest sample
+    const int J = K + zpad;
+    // the next step's sample and taps are fetched while the current step's products are formed
+    cd xn = sX[top + (top >> pad_sh)];
+    double hn[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) hn[r] = hp[M * r];
+#pragma unroll 2
+    for (int j = 0; j < J; j++) {
+        const cd x = xn;
+        double h[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) h[r] = hn[r];
+        const int nxt = max(top - j - 1, 0);                 // (the fetch behind the last step is never used)
+        xn = sX[nxt + (nxt >> pad_sh)];
+#pragma unroll
+        for (int r = 0; r < R; r++) hn[r] = hp[j + 1 + M * r];
+        // all products first, then all sums: a sum right behind its own product would wait out the multiply's latency
+        cd t[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) t[r] = make_double2(mul_rn(x.x, h[r]), mul_rn(x.y, h[r]));
+#pragma unroll
+        for (int r = 0; r < R; r++) { acc[r].x = add_rn(acc[r].x, t[r].x); acc[r].y = add_rn(acc[r].y, t[r].y); }
+    }
+    cd *o = reinterpret_cast<cd *>(p.out) + (long)c * p.out_stride + m0 + tid * R;
+#pragma unroll
+    for (int r = 0; r < R; r++) if (m0 + tid * R + r < p.n_out) o[r] = scale(acc[r], p.gain);
+}
+
+static int launch_decim_rb(const PolyFirParams &p, cudaStream_t stream)
+{
+    constexpr int R = 4, NT = 128;
+    const int tiles = (p.n_out + NT * R - 1) / (NT * R);
+    const long grid = (long)tiles * p.C;
+    if (grid <= 0 || grid > 0x7fffffffL) { set_error("polyfir: grid %ld out of range", grid); return QC_EINVAL; }
+    int pad_sh = 0;
+    while ((1 << pad_sh) < R * p.M) pad_sh++;
+    const int nh = p.K + 2 * p.M * (R - 1) + 1, nx = (NT * R - 1) * p.M + p.K;
+    const size_t sh = (size_t)((nh + 1) & ~1) * sizeof(double) + (size_t)(nx + (nx >> pad_sh) + 1) * sizeof(cd);
+    if (sh > 200 * 1024) return -100;                            // tile too large for shared memory: the generic kernel takes it
+    auto kern = decim_rb_kernel<R, NT>;
+    if (sh > 48 * 1024) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> g(mu);
+        QC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
+    kern<<<(unsigned)grid, NT, sh, stream>>>(p, tiles, pad_sh);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
 // Half-band forms with the reference's paired summation (filter.c:401-413, 444-451).
 template <typename T>
 __global__ void __launch_bounds__(TM) hb45_kernel(PolyFirParams p, int tiles)
@@ -270,6 +364,10 @@ int launch_polyfir(const PolyFirParams &p, cudaStream_t stream)
         return p.is_complex ? launch_hb<cd>(p, stream) : launch_hb<double>(p, stream);
     if (p.K < 1 || p.L < 1 || p.M < 1) { set_error("polyfir: bad K/L/M %d/%d/%d", p.K, p.L, p.M); return QC_EINVAL; }
     if (p.is_complex) {
+        if (p.tap_mode == TAP_REAL && p.L == 1 && p.order == 0 && p.K >= 64 && p.M <= 16 && (p.M & (p.M - 1)) == 0 && p.n_out >= 256) {
+            const int rc = launch_decim_rb(p, stream);
+            if (rc != -100) return rc;
+        }
         switch (p.tap_mode) {
         case TAP_REAL: return launch_t<cd, TAP_REAL>(p, stream);
         case TAP_COMPLEX: return launch_t<cd, TAP_COMPLEX>(p, stream);

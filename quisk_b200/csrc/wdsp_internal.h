@@ -53,6 +53,7 @@ struct SeqStage {
     double par[32] = {0};           // uniform parameters
     AgcParams agc;
     double *d_meter = nullptr;      // meter results [C][3]
+    int meter_sub = 1;              // meters: how many DSP blocks one run() call covers (peak hold is per block, meter.c:95)
     int init_common(int kind, int C, int state_doubles);
     void release();
     int flush();
@@ -143,7 +144,15 @@ struct Rxa {
     bool fusable() const;
     int xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s);
     int xrxa_multi(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s);
+    // every stage over a group of blocks per launch, for the configurations the single kernel does not cover (FM, AM, resamplers)
+    int xrxa_stages_wide(const void *din, long is, void *dout, long os, int g, cudaStream_t s);
+    cd *wmid = nullptr, *wmid2 = nullptr, *waudio = nullptr; long wstride = 0;
+    cudaStream_t side = nullptr; cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;     // meters next to the chain
 };
+
+// one fircore over nblocks consecutive blocks of every channel, transforms of all blocks in parallel (wdsp_rxa_fused.cu);
+// spec: scratch of C * nblocks * 2 * size complex; in may equal out
+int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_stride, int nblocks, cd *spec, cudaStream_t s);
 
 int launch_panel(const cd *in, long in_stride, cd *out, long out_stride, int n, int C, double gainI, double gainQ,
                  int inselect, int copy, cudaStream_t s, cd *sip = nullptr, int sipsize = 0, int sip_idx = 0);

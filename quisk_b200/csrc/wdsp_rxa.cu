@@ -188,6 +188,9 @@ void Rxa::release()
     if (hs) { cudaStreamSynchronize(hs); cudaStreamDestroy(hs); hs = nullptr; }
     if (d_uslew) cudaFree(d_uslew); if (d_cup) cudaFree(d_cup);
     d_uslew = nullptr; d_cup = nullptr;
+    if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); side = nullptr; for (cudaEvent_t *e : {&ev_a, &ev_b, &ev_c, &ev_d}) if (*e) { cudaEventDestroy(*e); *e = nullptr; } }
+    if (wmid) cudaFree(wmid); if (wmid2) cudaFree(wmid2); if (waudio) cudaFree(waudio);
+    wmid = wmid2 = waudio = nullptr; wstride = 0;
     if (d_wide_spec) cudaFree(d_wide_spec); if (d_wide_y) cudaFree(d_wide_y);
     d_wide_spec = d_wide_y = nullptr; wide_spec_cap = wide_y_cap = 0;
     if (d_sip) cudaFree(d_sip); if (d_sipout) cudaFree(d_sipout);
@@ -199,9 +202,100 @@ int Rxa::xrxa_multi(const void *din, long is, void *dout, long os, int nblocks, 
 {   // nblocks consecutive DSP blocks per channel: block b of a channel at in + b * dsp_insize, out + b * dsp_outsize
     if (nblocks <= 0) return QC_OK;
     if (fusable()) return xrxa_fused(din, is, dout, os, nblocks, s);
+    // the other configurations: every stage is a streaming operator with carried state, so it can take a GROUP of blocks per
+    // launch (the fircores as wide transform grids); the group is bounded by what the recurrent kernels stage in shared memory
+    int g = 8192 / dsp_size;
+    if (const char *e = getenv("QUISK_RXA_GROUP")) g = atoi(e);
+    if (fused_ok && g >= 2 && !(shift_run && shift_nonzero) && !(agc_run && agc->agc.mode == 5)) {
+        for (int b = 0; b < nblocks; b += g) {
+            const int gb = nblocks - b < g ? nblocks - b : g;
+            int rc = gb >= 2 ? xrxa_stages_wide((const cd *)din + (size_t)b * dsp_insize, is, (cd *)dout + (size_t)b * dsp_outsize, os, gb, s)
+                             : xrxa((const cd *)din + (size_t)b * dsp_insize, is, (cd *)dout + (size_t)b * dsp_outsize, os, s);
+            if (rc != QC_OK) return rc;
+        }
+        return QC_OK;
+    }
     for (int b = 0; b < nblocks; b++) {
         int rc = xrxa((const cd *)din + (size_t)b * dsp_insize, is, (cd *)dout + (size_t)b * dsp_outsize, os, s);
         if (rc != QC_OK) return rc;
+    }
+    return QC_OK;
+}
+
+int Rxa::xrxa_stages_wide(const void *din, long is, void *dout, long os, int g, cudaStream_t s)
+{   // xrxa's stage order (RXA.c:561-598) with g blocks per stage launch
+    int rc;
+    const int n = g * dsp_size, nin = g * dsp_insize;
+    const long need = (long)n + 64;                 // the group at the DSP rate: the input resampler reads the caller's buffer directly
+    if (need > wstride) {
+        for (cd **q : {&wmid, &wmid2, &waudio}) if (*q) { cudaFree(*q); *q = nullptr; }
+        wstride = 0;
+        QC_CUDA(cudaMalloc((void **)&wmid, (size_t)C * need * sizeof(cd)));
+        QC_CUDA(cudaMalloc((void **)&wmid2, (size_t)C * need * sizeof(cd)));
+        QC_CUDA(cudaMalloc((void **)&waudio, (size_t)C * need * sizeof(cd)));
+        wstride = need;
+    }
+    const size_t need_spec = (size_t)C * g * 2 * dsp_size;
+    if (need_spec > wide_spec_cap) { if (d_wide_spec) cudaFree(d_wide_spec); d_wide_spec = nullptr; wide_spec_cap = 0;
+                                     QC_CUDA(cudaMalloc((void **)&d_wide_spec, need_spec * sizeof(cd))); wide_spec_cap = need_spec; }
+    const long ws = wstride;
+    const cd *cur = (const cd *)din; long cs = is;
+    cd *m = wmid;
+    for (SeqStage *mt : {adcmeter, smeter, agcmeter}) mt->meter_sub = g;
+    if (rsmpin) {
+        int no = 0;
+        rc = rsmpin->f->run(cur, cs, nin, m, ws, &no, 0, s); if (rc) return rc;
+        if (no != n) { set_error("rxa: input resampler produced %d samples for %d blocks of %d", no, g, dsp_size); return QC_EINVAL; }
+        cur = m; cs = ws;
+    }
+    if (fmd_run && !amd_run && nbp_run) {
+        // FM: the two input-side meters only READ what the chain has produced, so they run on a side stream next to the stages
+        // that follow (the filter writes into the second scratch buffer instead of in place to make that safe)
+        if (!side) {
+            QC_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            for (cudaEvent_t *e : {&ev_a, &ev_b, &ev_c, &ev_d}) QC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+        QC_CUDA(cudaEventRecord(ev_a, s)); QC_CUDA(cudaStreamWaitEvent(side, ev_a, 0));
+        rc = adcmeter->run(cur, cs, nullptr, 0, n, side); if (rc) return rc;
+        QC_CUDA(cudaEventRecord(ev_b, side));
+        rc = fircore_wide(nbp0, cur, cs, wmid2, ws, g, d_wide_spec, s); if (rc) return rc;
+        QC_CUDA(cudaEventRecord(ev_c, s)); QC_CUDA(cudaStreamWaitEvent(side, ev_c, 0));
+        rc = smeter->run(wmid2, ws, nullptr, 0, n, side); if (rc) return rc;
+        QC_CUDA(cudaEventRecord(ev_d, side));
+        rc = fmpll->run(wmid2, ws, waudio, ws, n, s); if (rc) return rc;                // pll -> audio
+        QC_CUDA(cudaStreamWaitEvent(s, ev_b, 0));                                       // the ADC meter has read wmid: it may be overwritten
+        rc = fircore_wide(pde, waudio, ws, m, ws, g, d_wide_spec, s); if (rc) return rc;
+        rc = fircore_wide(paud, m, ws, m, ws, g, d_wide_spec, s); if (rc) return rc;
+        rc = sntch->run(m, ws, m, ws, n, s); if (rc) return rc;
+        QC_CUDA(cudaStreamWaitEvent(s, ev_d, 0));                                       // and the S meter wmid2, before the next group's filter writes it
+    } else {
+    rc = adcmeter->run(cur, cs, nullptr, 0, n, s);
+    if (rc == QC_OK && nbp_run) rc = fircore_wide(nbp0, cur, cs, m, ws, g, d_wide_spec, s);
+    else if (rc == QC_OK && cur != m) rc = cudaMemcpy2DAsync(m, (size_t)ws * sizeof(cd), cur, (size_t)cs * sizeof(cd), (size_t)n * sizeof(cd), C, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? QC_OK : QC_ECUDA;
+    if (rc == QC_OK) rc = smeter->run(m, ws, nullptr, 0, n, s);
+    if (rc == QC_OK && amd_run) rc = amd->run(m, ws, m, ws, n, s);
+    if (rc == QC_OK && fmd_run) {
+        rc = fmpll->run(m, ws, waudio, ws, n, s);                                       // pll -> audio
+        if (rc == QC_OK) rc = fircore_wide(pde, waudio, ws, m, ws, g, d_wide_spec, s);  // de-emphasis
+        if (rc == QC_OK) rc = fircore_wide(paud, m, ws, m, ws, g, d_wide_spec, s);      // audio filter, in place
+        if (rc == QC_OK) rc = sntch->run(m, ws, m, ws, n, s);                           // CTCSS notch (I rail)
+    }
+    }
+    if (rc == QC_OK && bp1_run) rc = fircore_wide(bp1, m, ws, m, ws, g, d_wide_spec, s);
+    if (rc == QC_OK && agc_run) { rc = agc->run(m, ws, wmid2, ws, n, s); m = wmid2; }
+    if (rc == QC_OK) rc = agcmeter->run(m, ws, agc->d_state, 0, n, s);
+    for (SeqStage *mt : {adcmeter, smeter, agcmeter}) mt->meter_sub = 1;
+    if (rc != QC_OK) return rc;
+    cd *sp = sip_run ? d_sip : nullptr;
+    const int sidx = sip_idx;
+    if (sip_run) sip_idx = n >= sipsize ? 0 : (sip_idx + n) & (sipsize - 1);           // siphon.c:110-124
+    if (rsmpout) {
+        rc = launch_panel(m, ws, m, ws, n, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s, sp, sipsize, sidx); if (rc) return rc;
+        int no = 0;
+        rc = rsmpout->f->run(m, ws, n, dout, os, &no, 0, s); if (rc) return rc;
+        if (no != g * dsp_outsize) { set_error("rxa: output resampler produced %d samples, expected %d", no, g * dsp_outsize); return QC_EINVAL; }
+    } else {
+        rc = launch_panel(m, ws, (cd *)dout, os, n, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s, sp, sipsize, sidx); if (rc) return rc;
     }
     return QC_OK;
 }

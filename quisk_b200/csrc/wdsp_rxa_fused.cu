@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(256) fir_mac_kernel(const cd *spec, int nblock
 }
 
 // one fircore over nblocks blocks of every channel: transforms wide, then the delay line and `prev` brought up to date
-static int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_stride, int nblocks, cd *spec, cudaStream_t s)
+int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_stride, int nblocks, cd *spec, cudaStream_t s)
 {
     const int n = f->size, n2 = 2 * n, lanes = fft_threads(n2), C = f->C, nfor = f->nfor;
     const size_t sh = ((size_t)n2 + fft_tw_entries(n2)) * sizeof(cd);

@@ -304,21 +304,60 @@ __global__ void amd_kernel(const cd *in, long is, cd *out, long os, int n, int C
 // the fixture of the reference's xfmd is matched to 1e-10.
 __global__ void fmpll_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
 {
-    SEQ_STAGE_IN();
-    double *ang = reinterpret_cast<double *>(sx + n);           // [n] arg(x[i]); 1e300 marks x == 0 (fmd.c:158: det = 0)
+    // shared memory: ang[n] only (the samples are not staged: every thread takes arg() of its share straight from global
+    // memory, lane 0's loop leaves the audio value in place of the angle, and all threads write the (a, a) pairs out)
+    extern __shared__ double seq_smem[];
+    double *ang = seq_smem;                                     // [n] arg(x[i]); 1e300 marks x == 0 (fmd.c:158: det = 0)
+    const int c = blockIdx.x;
+    const cd *gx = in + (size_t)c * is;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const cd v = sx[i];
+        const cd v = gx[i];
         ang[i] = (v.x == 0.0 && v.y == 0.0) ? 1.0e300 : atan2(v.y, v.x);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-    cd *y = sx;
     double *st = state + (size_t)c * 4;
     double phs = st[0], fil_out = st[1], omega = st[2], fmdc = st[3];
     const double omega_min = P.v[0], omega_max = P.v[1], g1 = P.v[2], g2 = P.v[3], mtau = P.v[4], onem_mtau = P.v[5], again = P.v[6];
-    for (int i = 0; i < n; i++) {
+    // The loop's only true cycle is phs -> det -> omega -> fil_out -> (two samples later) phs; everything is written so that
+    // nothing else sits on it: angles come in groups of eight through registers (32-bit shared-window addresses: no address
+    // re-derivation per group), the clamps are min / max, the two wrap-arounds are selects with the reference's while-loops
+    // as a never-taken fallback, the DC estimate and the output are side chains.  Same operations, same order, same
+    // roundings as fmd.c:153-168.
+    const unsigned ang_s = (unsigned)__cvta_generic_to_shared(ang);
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double a8[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a8[j]) : "r"(ang_s + 8u * (unsigned)(i + j)));
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double a_x = a8[j];
+            double det = a_x - phs;                             // in (-3 pi, pi]
+            const double detw = det + TWOPI_D;
+            det = det <= -kPI ? detw : det;
+            det = a_x > 1.0e299 ? 0.0 : det;
+            const double del_out = fil_out;
+            omega = fmin(fmax(omega + g2 * det, omega_min), omega_max);     // the two ifs of fmd.c:161-162 (no NaNs here)
+            fil_out = g1 * det + omega;
+            double p = phs + del_out;
+            const double pm = p - TWOPI_D;
+            p = p >= TWOPI_D ? pm : p;
+            const double pp = p + TWOPI_D;
+            p = p < 0.0 ? pp : p;
+            if (p >= TWOPI_D || p < 0.0) {                      // |del_out| > 2 pi: not with any loop bandwidth the stage is built with
+                while (p >= TWOPI_D) p -= TWOPI_D;
+                while (p < 0.0) p += TWOPI_D;
+            }
+            phs = p;
+            fmdc = mtau * fmdc + onem_mtau * fil_out;
+            const double a = again * (fil_out - fmdc);
+            asm volatile("st.shared.f64 [%0], %1;" :: "r"(ang_s + 8u * (unsigned)(i + j)), "d"(a) : "memory");
+        }
+    }
+    for (; i < n; i++) {
         const double a_x = ang[i];
-        double det = a_x - phs;                                 // in (-3 pi, pi]
+        double det = a_x - phs;
         if (det <= -kPI) det += TWOPI_D;
         if (a_x > 1.0e299) det = 0.0;
         const double del_out = fil_out;
@@ -330,34 +369,57 @@ __global__ void fmpll_kernel(const cd *in, long is, cd *out, long os, int n, int
         while (phs >= TWOPI_D) phs -= TWOPI_D;
         while (phs < 0.0) phs += TWOPI_D;
         fmdc = mtau * fmdc + onem_mtau * fil_out;
-        const double a = again * (fil_out - fmdc);
-        y[i] = make_double2(a, a);
+        ang[i] = again * (fil_out - fmdc);
     }
     st[0] = phs; st[1] = fil_out; st[2] = omega; st[3] = fmdc;
     }
-    SEQ_STAGE_OUT();
+    __syncthreads();
+    cd *gy = out + (size_t)c * os;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double a = ang[i]; gy[i] = make_double2(a, a); }
 }
 
 // ------------------------------------------------------------------------------------------ snotch
 // state: x1 x2 y1 y2 ; par: a0 a1 a2 b1 b2.  Only the I rail is filtered (iir.c:85-86).
 __global__ void snotch_kernel(const cd *in, long is, cd *out, long os, int n, int C, double *state, SeqPar P)
 {
-    SEQ_STAGE_IN();
+    // only the I rail is filtered (iir.c:85-86): its n doubles are what is staged; the Q rail passes from `in` to `out`
+    extern __shared__ double seq_smem[];
+    double *xr = seq_smem;
+    const int c = blockIdx.x;
+    const cd *gx = in + (size_t)c * is;
+    cd *gy = out + (size_t)c * os;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xr[i] = gx[i].x;
+    __syncthreads();
     if (threadIdx.x == 0) {
-    const cd *x = sx;
-    cd *y = sx;
-    double *st = state + (size_t)c * 4;
-    double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
-    const double a0 = P.v[0], a1 = P.v[1], a2 = P.v[2], b1 = P.v[3], b2 = P.v[4];
-    for (int i = 0; i < n; i++) {
-        const double x0 = x[i].x;
-        const double o = a0 * x0 + a1 * x1 + a2 * x2 + b1 * y1 + b2 * y2;
-        y[i] = make_double2(o, x[i].y);
-        y2 = y1; y1 = o; x2 = x1; x1 = x0;
+        double *st = state + (size_t)c * 4;
+        double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
+        const double a0 = P.v[0], a1 = P.v[1], a2 = P.v[2], b1 = P.v[3], b2 = P.v[4];
+        const unsigned x_s = (unsigned)__cvta_generic_to_shared(xr);
+        int i = 0;
+        for (; i + 8 <= n; i += 8) {
+            double x8[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x8[j]) : "r"(x_s + 8u * (unsigned)(i + j)));
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double x0 = x8[j];
+                // ((((a0 x0 + a1 x1) + a2 x2) + b1 y1) + b2 y2): the feed-forward part does not wait for y1
+                const double ff = a0 * x0 + a1 * x1 + a2 * x2;
+                const double o = ff + b1 * y1 + b2 * y2;
+                asm volatile("st.shared.f64 [%0], %1;" :: "r"(x_s + 8u * (unsigned)(i + j)), "d"(o) : "memory");
+                y2 = y1; y1 = o; x2 = x1; x1 = x0;
+            }
+        }
+        for (; i < n; i++) {
+            const double x0 = xr[i];
+            const double o = a0 * x0 + a1 * x1 + a2 * x2 + b1 * y1 + b2 * y2;
+            xr[i] = o;
+            y2 = y1; y1 = o; x2 = x1; x1 = x0;
+        }
+        st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
     }
-    st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
-    }
-    SEQ_STAGE_OUT();
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) gy[i] = make_double2(xr[i], gx[i].y);
 }
 
 // mlog10 (wdsp/meterlog10.c:547-554): WDSP's meters do not call log10 -- they take the exponent and an 11-bit table
@@ -386,32 +448,40 @@ const double *mlog10_table()
 // The averaging recurrence avg = avg * ma + (1 - ma) * |x|^2 is sequential in the reference's arithmetic, but its
 // inputs are not: every thread forms w[i] = (1 - ma) * |x[i]|^2 and the block maximum in parallel, lane 0 is left with
 // one multiply and one add per sample (the peak decay peak *= mp is a second, independent chain).
-__global__ void meter_kernel(const cd *in, long is, int n, int C, double *state, SeqPar P, double *result, const double *agc_state, const double *mtable)
+__global__ void meter_kernel(const cd *in, long is, int n, int C, double *state, SeqPar P, double *result, const double *agc_state, const double *mtable,
+                             int nsub)
 {
+    // nsub > 1: the call covers nsub consecutive blocks of n samples (the wide multi-block path); the peak is decayed per sample
+    // and raised to the block maximum at the END OF EACH BLOCK (meter.c:88-95), so the blocks are walked one after the other
     extern __shared__ double seq_smem[];
     double *w = seq_smem;                       // [n]
     __shared__ double s_max[2];
     const int c = blockIdx.x;
     const double ma = P.v[0], mp = P.v[1], oma = 1.0 - ma;
-    const cd *gx = in + (size_t)c * is;
-    double lm = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const cd v = gx[i];
-        const double smag = v.x * v.x + v.y * v.y;
-        w[i] = oma * smag;
-        lm = smag > lm ? smag : lm;
-    }
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, lm, o); lm = t > lm ? t : lm; }
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = lm;
-    __syncthreads();
-    if (threadIdx.x != 0) return;
     double avg = state[c * 2], peak = state[c * 2 + 1];
-    double np = s_max[0] > s_max[1] ? s_max[0] : s_max[1];
-    for (int i = 0; i < n; i++) {
-        avg = avg * ma + w[i];
-        peak *= mp;
+    for (int sb = 0; sb < nsub; sb++) {
+        const cd *gx = in + (size_t)c * is + (size_t)sb * n;
+        double lm = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const cd v = gx[i];
+            const double smag = v.x * v.x + v.y * v.y;
+            w[i] = oma * smag;
+            lm = smag > lm ? smag : lm;
+        }
+        for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, lm, o); lm = t > lm ? t : lm; }
+        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = lm;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double np = s_max[0] > s_max[1] ? s_max[0] : s_max[1];
+            for (int i = 0; i < n; i++) {
+                avg = avg * ma + w[i];
+                peak *= mp;
+            }
+            if (np > peak) peak = np;
+        }
+        __syncthreads();
     }
-    if (np > peak) peak = np;
+    if (threadIdx.x != 0) return;
     state[c * 2] = avg; state[c * 2 + 1] = peak;
     result[c * 3] = 10.0 * mlog10_dev(mtable, avg + 1.0e-40);
     result[c * 3 + 1] = 10.0 * mlog10_dev(mtable, peak + 1.0e-40);
@@ -547,7 +617,7 @@ int SeqStage::run(const void *d_in, long is, void *d_out, long os, int n, cudaSt
     memcpy(P.v, par, sizeof(P.v));
     const cd *in = (const cd *)d_in; cd *out = (cd *)d_out;
     const size_t sh = (size_t)n * sizeof(cd);           // the staged block
-    if (sh > 200 * 1024) { set_error("seq stage: block of %d samples does not fit in shared memory", n); return QC_EINVAL; }
+    if (kind != SEQ_METER && kind != SEQ_WCPAGC && sh > 200 * 1024) { set_error("seq stage: block of %d samples does not fit in shared memory", n); return QC_EINVAL; }
 #define QC_SEQ_OPTIN(k, bytes) do { if ((bytes) > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); } while (0)
     switch (kind) {
     case SEQ_SHIFT: QC_SEQ_OPTIN(shift_kernel, sh); shift_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, d_par); break;
@@ -559,10 +629,12 @@ int SeqStage::run(const void *d_in, long is, void *d_out, long os, int n, cudaSt
         wcpagc_kernel<<<C, 128, sa, s>>>(in, is, out, os, n, C, d_state, d_ring, agc);
         break; }
     case SEQ_AMD: QC_SEQ_OPTIN(amd_kernel, sh); amd_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
-    case SEQ_FMPLL: { const size_t sf = sh + (size_t)n * sizeof(double); QC_SEQ_OPTIN(fmpll_kernel, sf); fmpll_kernel<<<C, SEQ_T, sf, s>>>(in, is, out, os, n, C, d_state, P); break; }
-    case SEQ_SNOTCH: QC_SEQ_OPTIN(snotch_kernel, sh); snotch_kernel<<<C, SEQ_T, sh, s>>>(in, is, out, os, n, C, d_state, P); break;
+    case SEQ_FMPLL: { const size_t sf = (size_t)n * sizeof(double); QC_SEQ_OPTIN(fmpll_kernel, sf); fmpll_kernel<<<C, 128, sf, s>>>(in, is, out, os, n, C, d_state, P); break; }
+    case SEQ_SNOTCH: { const size_t sf = (size_t)n * sizeof(double); QC_SEQ_OPTIN(snotch_kernel, sf); snotch_kernel<<<C, SEQ_T, sf, s>>>(in, is, out, os, n, C, d_state, P); break; }
     case SEQ_METER: { const double *mt = mlog10_table(); if (!mt) { set_error("meter: table allocation failed"); return QC_ENOMEM; }
-        QC_SEQ_OPTIN(meter_kernel, sh); meter_kernel<<<C, SEQ_T, sh, s>>>(in, is, n, C, d_state, P, d_meter, (const double *)d_out, mt); break; }
+        const int ns = meter_sub > 1 ? meter_sub : 1, nb = n / ns;         // meter_sub blocks of nb samples in this call
+        const size_t shm = (size_t)nb * sizeof(double);
+        QC_SEQ_OPTIN(meter_kernel, shm); meter_kernel<<<C, SEQ_T, shm, s>>>(in, is, nb, C, d_state, P, d_meter, (const double *)d_out, mt, ns); break; }
     default: set_error("seq stage: unknown kind %d", kind); return QC_EINVAL;
     }
     count_launch();

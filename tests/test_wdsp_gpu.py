@@ -618,3 +618,46 @@ def test_rxa_fused_kernel_equals_per_stage_kernels(geom, agc_mode, torch, lib):
         assert np.max(np.abs(got[2] - ref[2])) <= 1e-6 * np.max(np.abs(ref[2])), kind
     # one launch for all blocks runs the transforms as their own wide kernels: again the same source compiled in another context
     assert max(O.rel_rms(res["multi"][0][c], res["fused"][0][c]) for c in range(NCH)) < 1e-13
+
+
+@pytest.mark.parametrize("cfg", ["fm_384k", "am", "sam_usb", "usb_out96k"])
+def test_rxa_multi_block_stage_groups_equal_per_block(cfg, torch, lib):
+    """quisk_cuda_rxa_xrxa_multi for the configurations outside the single-kernel chain (FM with the /8 input resampler, AM,
+    synchronous AM, an output resampler): every stage takes a group of blocks per launch -- the fircores as wide transform
+    grids, the recurrent stages and meters over the whole group (meters still peak-hold per block) -- and must give what
+    one xrxa call per block gives: same state machine trajectories, outputs to 1e-12, meters to 1e-9 dB."""
+    geo = {"fm_384k": (2048, 256, 384000, 48000, 48000, 5, 40), "am": (256, 256, 48000, 48000, 48000, 6, 20),
+           "sam_usb": (256, 256, 48000, 48000, 48000, 10, 20), "usb_out96k": (256, 256, 48000, 48000, 96000, 1, 20)}[cfg]
+    in_size, dsp_size, in_rate, dsp_rate, out_rate, mode, nblk = geo
+    x = (fm_sig if mode == 5 else am_sig if mode in (6, 10) else sig)(in_size * nblk, 780, float(in_rate))
+    d = _dev(torch, x)
+
+    def run(multi):
+        rxa = lib.quisk_cuda_rxa_create(NCH, in_size, dsp_size, in_rate, dsp_rate, out_rate)
+        assert rxa, lib.quisk_cuda_last_error()
+        assert lib.quisk_cuda_rxa_set_shift(rxa, 0, None) == 0
+        assert lib.quisk_cuda_rxa_set_mode(rxa, mode) == 0
+        assert lib.quisk_cuda_rxa_set_passband(rxa, *((-8000.0, 8000.0) if mode == 5 else (-4000.0, 4000.0) if mode in (6, 10) else (150.0, 2850.0))) == 0
+        osz = lib.quisk_cuda_rxa_out_size(rxa)
+        o = torch.zeros((NCH, osz * nblk), dtype=torch.complex128, device="cuda")
+        if multi:
+            assert lib.quisk_cuda_rxa_xrxa_multi(rxa, d.data_ptr(), d.stride(0), o.data_ptr(), o.stride(0), nblk, None) == 0, lib.quisk_cuda_last_error()
+        else:
+            for b in range(nblk):
+                blk = d[:, b * in_size:(b + 1) * in_size]; ob = o[:, b * osz:(b + 1) * osz]
+                assert lib.quisk_cuda_rxa_xrxa(rxa, blk.data_ptr(), d.stride(0), ob.data_ptr(), o.stride(0), None) == 0, lib.quisk_cuda_last_error()
+        torch.cuda.synchronize()
+        mt = np.zeros((3, 3, NCH))
+        for w in range(3):
+            assert lib.quisk_cuda_rxa_get_meter(rxa, w, mt[w, 0].ctypes.data, mt[w, 1].ctypes.data, mt[w, 2].ctypes.data) == 0
+        sip = np.zeros((NCH, 2 * 1024), dtype=np.float32)
+        assert lib.quisk_cuda_rxa_get_siphon(rxa, sip.ctypes.data, 1024, 1) == 0
+        lib.quisk_cuda_rxa_destroy(rxa)
+        return o.cpu().numpy(), mt, sip
+    ref, got = run(False), run(True)
+    assert np.abs(ref[0]).max() > 1e-3
+    errs = [O.rel_rms(got[0][c], ref[0][c]) for c in range(NCH)]
+    print(cfg, "multi vs per block", errs)
+    assert max(errs) < 1e-12
+    assert np.max(np.abs(got[1] - ref[1])) < 1e-9, got[1] - ref[1]
+    assert np.max(np.abs(got[2] - ref[2])) <= 1e-6 * max(np.max(np.abs(ref[2])), 1e-30)

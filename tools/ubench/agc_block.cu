@@ -61,7 +61,7 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
     const unsigned rv_s = (unsigned)__cvta_generic_to_shared(RV);
     constexpr int CH = 16;
     while (i < n) {
-        if (n - i >= CH && (state_ == 0 || state_ >= 3)) {
+        if (n - i >= CH && (state_ == 0 || state_ >= 3) && !(volts < k_minv)) {      // (a fresh channel starts with volts = 0: the general path clamps it first)
             // runs of sixteen samples on the assumption that the state does not change
             const double M = state_ == 0 ? k_attack : (state_ == 3 ? k_decay : k_hdecay);
             const bool want = state_ == 0;
