@@ -48,6 +48,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SAMPLE_RATE = 1536000
+RATE = [SAMPLE_RATE]                                     # the rx_chain / panadapter workloads' input rate (--rate; `pipeline` sets 192000)
 FFT_SIZE = 8192
 ALG_BYTES_RX = 16.0 + 8.0 * 48000 / SAMPLE_RATE          # 16 B in + 0.25 B out
 ALG_BYTES_PAN = 16.0                                     # C2: 16 B in (+ 8 B/bin per returned graph)
@@ -132,7 +133,7 @@ def load_peaks():
 def ref_worker_setup(fi, fq):
     from oracle import ref_ctypes as R
     lib = R.load(REF_RX_LIB if R.have_ref(REF_RX_LIB) else "libquisk_rx_ref.so", private_copy=True)
-    lib.ref_set_sample_rate(SAMPLE_RATE); lib.ref_init_chain()
+    lib.ref_set_sample_rate(RATE[0]); lib.ref_init_chain()
     lib.ref_set_filters(fi.ctypes.data_as(C.c_void_p), fq.ctypes.data_as(C.c_void_p), len(fi), 2800, 0)
     lib.ref_tune.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
     return lib
@@ -145,7 +146,7 @@ def ref_run_block(lib, x, scratch, dbuf, vec, tune_hz):
         m = min(61440, n - pos)
         scratch[:m] = x[pos:pos + m]
         if tune_hz:
-            lib.ref_tune(scratch.ctypes.data, m, tune_hz, SAMPLE_RATE, vec.ctypes.data)
+            lib.ref_tune(scratch.ctypes.data, m, tune_hz, RATE[0], vec.ctypes.data)
         nd = lib.ref_process_decimate(scratch.ctypes.data_as(C.c_void_p), m, 0, 3)
         total += lib.ref_process_demodulate(scratch.ctypes.data_as(C.c_void_p), dbuf.ctypes.data_as(C.c_void_p), nd, 0, 0, 3)
         pos += m
@@ -588,11 +589,11 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
     stream = ctx.stream
     tune = [args.tune + 3.0 * (c % 101) for c in range(C_)] if args.tune else None
     if "rx_chain" in workload:
-        rx = RxChain(C_, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=tune, fused=not args.unfused)
+        rx = RxChain(C_, RATE[0], "USB", fi, fq, tabs, tune_hz=tune, fused=not args.unfused)
         for opt, val in ((2, args.chunk), (3, args.threads), (4, args.min_r), (8, args.deepk)):
             if val:
                 rx.set_option(opt, val)
-        for opt, val in ((5, args.dense), (6, args.plans), (11, args.split), (12, args.tailwarp), (14, args.variant)):
+        for opt, val in ((5, args.dense), (6, args.plans), (11, args.split), (12, args.tailwarp)):
             if val >= 0:
                 rx.set_option(opt, val)
         if args.nco == "closed":
@@ -609,7 +610,7 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
     def step():
         if pan:
             L.check(lib, lib.quisk_cuda_pan_accumulate(pan, x.data_ptr(), block, frames, stream), "pan_accumulate")
-            L.check(lib, lib.quisk_cuda_pan_graph(pan, 1024, 1.0, 0.0, float(SAMPLE_RATE), graph.data_ptr(), stream), "pan_graph")
+            L.check(lib, lib.quisk_cuda_pan_graph(pan, 1024, 1.0, 0.0, float(RATE[0]), graph.data_ptr(), stream), "pan_graph")
         if rx:
             rx.process(x.data_ptr(), block, block, audio.data_ptr(), acap, stream=stream)
         if args.sync_steps:
@@ -620,6 +621,7 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
             rx.set_option(1, 1); rx.kernel_time()
     ms, ms_max, launches, clocks = timed_steps(ctx, step, steps, warmup, start_kernel_timing)
     kms, kn = (rx.kernel_time() if rx else (0.0, 0))
+    kname = rx.fused_kernel_name() if rx else ""
     if rx:
         rx.set_option(1, 0)
     if world > 1:       # per-rank diagnostics (stderr): a rank that is slower than the others shows up here
@@ -633,7 +635,7 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
         hx = torch.empty((C_, block), dtype=torch.complex128).pin_memory()
         hx.copy_(x.cpu())
         ha = torch.zeros((C_, acap), dtype=torch.float64).pin_memory()
-        rx_h = RxChain(C_, SAMPLE_RATE, "USB", fi, fq, tabs, tune_hz=tune, fused=not args.unfused)
+        rx_h = RxChain(C_, RATE[0], "USB", fi, fq, tabs, tune_hz=tune, fused=not args.unfused)
         if args.host_chunks >= 0:
             rx_h.set_option(15, args.host_chunks)
         hx_np = hx.numpy(); ha_np = ha.numpy()
@@ -694,11 +696,12 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
     roofline = None
     if rx and kn > 0:
         per_launch_ms = kms / kn
-        # fused kernel = tune + 4xHB45 + FIR/2 + HB45 + FIR/2: 16 B in per input sample, 16 B out per 128 inputs
-        alg = (16.0 + 16.0 / 128.0) * C_ * block
+        # fused kernel = tune + every half band / FIR down to the filter rate: 16 B in per input sample, 16 B out per Dtot inputs
+        # (Dtot = 128 at 1.536 MS/s: 4xHB45 + FIR98/2 + HB45 + FIR98/2; 16 at 192 kS/s)
+        dtot = RATE[0] // 12000
+        alg = (16.0 + 16.0 / dtot) * C_ * block
         ach = alg / (per_launch_ms / 1e3) / 1e9
-        kname = lib.quisk_cuda_rx_fused_kernel_name().decode() if hasattr(lib, "quisk_cuda_rx_fused_kernel_name") else "fused_decim_kernel"
-        roofline = {"bound": "hbm", "kernel": kname + " (tune + 4xHB45 + FIR98/2 + HB45 + FIR98/2, 1.536 MS/s -> 12 kS/s)", "achieved": ach, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": kname + " (tune + every half band / FIR of the cascade, %g kS/s -> 12 kS/s)" % (RATE[0] / 1e3), "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kms / ms,
                     "alg_bytes_per_launch": alg}
@@ -707,7 +710,7 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            if tj.get("kernel") == kname:
+            if kname and tj.get("kernel", "").replace(" ", "").find(kname.replace(" ", "")) >= 0:
                 roofline["traffic"] = tj["dram_bytes_per_input_sample"] * C_ * block
                 roofline["traffic_source"] = "profiles capture %s of %s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch" % (tj.get("capture", "?"), kname)
                 sb = tj.get("smem_bytes_per_input_sample"); clk = clocks.get("sm_mhz")
@@ -722,9 +725,11 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
         # FIRs at 1/32 and 1/128 (7.7), the tuning phasor (8): 59.5; the pipe's peak is measured on this device.
         pk = C.c_double(0.0)
         if lib.quisk_cuda_fp64_peak(C.byref(pk)) == 0 and pk.value > 0:
-            fma = 59.5 * C_ * block / (per_launch_ms / 1e3)
-            roofline["fp64"] = {"achieved": fma / 1e12, "peak": pk.value / 1e12, "unit": "TFMA/s", "frac": fma / pk.value,
-                                "fma_per_input_sample": 59.5, "peak_source": "measured (quisk_cuda_fp64_peak: 8 independent DFMA chains per thread)"}
+            fma_per = 59.5 if RATE[0] == SAMPLE_RATE else None
+            fma = (fma_per or 0.0) * C_ * block / (per_launch_ms / 1e3)
+            if fma_per:
+                roofline["fp64"] = {"achieved": fma / 1e12, "peak": pk.value / 1e12, "unit": "TFMA/s", "frac": fma / pk.value,
+                                    "fma_per_input_sample": 59.5, "peak_source": "measured (quisk_cuda_fp64_peak: 8 independent DFMA chains per thread)"}
     elif pan:
         alg = ALG_BYTES_PAN * C_ * block
         ach = alg * steps / (ms / 1e3) / 1e9
@@ -747,7 +752,7 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
     line = {"metric": "complex MS/s through RX chain", "value": value, "unit": "MS/s", "n_gpus": world, "steps": steps,
             "warmup": max(warmup, 3), "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "channels_per_gpu": C_, "block": block, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune, "tune_spread": "receiver c is tuned to tune_hz + 3 (c mod 101) Hz",
+            "config": {"workload": wl_name, "channels_per_gpu": C_, "block": block, "sample_rate": RATE[0], "tune_hz": args.tune, "tune_spread": "receiver c is tuned to tune_hz + 3 (c mod 101) Hz",
                        "fused": not args.unfused, "nco": args.nco if args.tune else "off", "l2": "input %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (C_ * block * 16 / 1e6)},
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
     if e2e_wire:
@@ -761,7 +766,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="", choices=["", "rx_chain", "panadapter", "rx_chain+panadapter", "rxa_usb", "rxa_fm", "channelizer"],
+    ap.add_argument("--rate", type=int, default=SAMPLE_RATE, help="rx_chain / panadapter input sample rate")
+    ap.add_argument("--workload", default="", choices=["", "rx_chain", "panadapter", "rx_chain+panadapter", "pipeline", "rxa_usb", "rxa_fm", "channelizer"],
                     help="default: rx_chain as the headline line plus short runs of the other workloads under `workloads`")
     ap.add_argument("--no-extra", action="store_true", help="default run: rx_chain only, no `workloads` key")
     ap.add_argument("--channels", type=int, default=0, help="channels per GPU (0 = the workload's own: 4096 / 16 / 64 / 256)")
@@ -775,7 +781,6 @@ def main():
     ap.add_argument("--plans", type=int, default=-1, help="fused decimator: 0 = generic kernel only")
     ap.add_argument("--split", type=int, default=-1, help="fused decimator: 1 = one lane per component in the half bands (default), 0 = complex lanes")
     ap.add_argument("--tailwarp", type=int, default=-1, help="fused decimator: 1 = low-rate stages on a fifth warp (default), 0 = all stages on the four main warps")
-    ap.add_argument("--variant", type=int, default=-1, help="fused decimator kernel generation: -1 = library default")
     ap.add_argument("--deepk", type=int, default=0, help="fused decimator: low-rate stages every k chunks (1 or 4)")
     ap.add_argument("--nco", default="exact", choices=["exact", "closed"], help="tuning phasor at block starts: the reference's recurrence (default) or closed form only")
     ap.add_argument("--host-chunks", type=int, default=-1, help="host entry points: channel chunks pipelined over copy / compute streams (-1 = library default)")
@@ -787,9 +792,20 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     workload = args.workload or "rx_chain"
+    if workload == "pipeline":
+        # the north star's target pipeline: >= 1024 concurrent 192 kS/s receivers through decimate -> band-pass (cRxFilterOut) ->
+        # SSB demodulation, with the panadapter on the same input; 1024 receivers per GPU here
+        workload = "rx_chain+panadapter"; args.rate = 192000
+        if args.channels <= 0:
+            args.channels = 1024
+    RATE[0] = args.rate
     wl_names = {"rx_chain": "rx_chain: C x 1.536 MS/s tune->4xHB45->FIR98/2->48k->HB45->FIR98/2->cRxFilterOut(164 I/Q, USB)->audio 48k (BASELINE configs[0], batched)",
                 "panadapter": "panadapter: C streams x 8192-pt Hann+FFT+|X| average+dB graph (BASELINE configs[1], batched)",
                 "rx_chain+panadapter": "rx_chain + panadapter on the same input (configs[0]+configs[1], batched)"}
+    if RATE[0] != SAMPLE_RATE:
+        wl_names = {k: v.replace("1.536 MS/s", "%g kS/s" % (RATE[0] / 1e3)).replace("tune->4xHB45->FIR98/2->48k", "tune->decimate->48k") for k, v in wl_names.items()}
+        if args.workload == "pipeline":
+            wl_names["rx_chain+panadapter"] = "pipeline (north-star target): C x 192 kS/s receivers, tune -> decimate to 48 k -> HB45 -> FIR98/2 -> cRxFilterOut band-pass (164 I/Q) -> USB demod -> audio 48 k, + 8192-pt panadapter on the same input"
 
     if args.impl == "reference":
         if rank != 0:
@@ -806,7 +822,7 @@ def main():
         line = {"impl": "reference", "metric": "complex MS/s through RX chain", "value": v, "unit": "MS/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl_names[workload], "channels": cores, "block": ref_block * blocks_per_step, "sample_rate": SAMPLE_RATE, "tune_hz": args.tune},
+                "config": {"workload": wl_names[workload], "channels": cores, "block": ref_block * blocks_per_step, "sample_rate": RATE[0], "tune_hz": args.tune},
                 "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference" if "rx_chain" in workload else "port",
                                  "sample": "%d channels (one per host core) x %d blocks of %d samples per step x %d steps; oracle/_ref = filter.c verbatim + quisk.c RX functions, " % (cores, blocks_per_step, ref_block, args.steps) + REF_FLAGS},
                 "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -835,6 +851,11 @@ def main():
             extra["rxa_usb"] = run_rxa(args, ctx, "rxa_usb", st, 3, 1, 3)
             extra["rxa_fm"] = run_rxa(args, ctx, "rxa_fm", st, 3, 1, 3)
             extra["channelizer"] = run_pfb(args, ctx, st, 3, 2, 8)
+            args.channels, args.block = 1024, 32768
+            RATE[0] = 192000
+            pname = "pipeline (north-star target): C x 192 kS/s receivers, tune -> decimate to 48 k -> HB45 -> FIR98/2 -> cRxFilterOut band-pass (164 I/Q) -> USB demod -> audio 48 k, + 8192-pt panadapter on the same input"
+            extra["pipeline"] = run_chain(args, ctx, "rx_chain+panadapter", st, 3, 2, 100, fi, fq, tabs, pname)
+            RATE[0] = args.rate
             args.channels, args.block = saved
             if line is not None:
                 line["workloads"] = extra

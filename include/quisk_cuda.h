@@ -273,6 +273,9 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value);
 /* Sum of the event-timed durations (ms) of the dominant kernel since the last call, and how
  * many launches that covers.  Synchronises on the recorded events. */
 int quisk_cuda_rx_kernel_time(qcRxChain *rx, double *ms_total, int *launches);
+/* Name (template instantiation) of the fused decimator kernel the last quisk_cuda_rx_process launched, "" before the
+ * first call or on the per-stage path.  bench.py quotes an ncu DRAM-traffic capture only when it names this kernel. */
+const char *quisk_cuda_rx_fused_kernel_name(qcRxChain *rx);
 /* Debug: copy the [n_channels][16 chunks][16 stamps] clock64() trace of the last fused launch to the host. */
 int quisk_cuda_rx_read_trace(qcRxChain *rx, long long *host_out, int n_channels);
 

@@ -58,6 +58,16 @@ int quisk_cuda_fircore_set_impulse(qcFircore *f, const double *impulse, int upda
 int quisk_cuda_fircore_update(qcFircore *f);
 int quisk_cuda_fircore_set_mp(qcFircore *f, int mp);                       /* setMp_fircore, firmin.c:469-473 */
 int quisk_cuda_fircore_flush(qcFircore *f);
+/* The three relatives of fircore that wdsp defines and no live chain instantiates:
+ *   firopt  (create_firopt / xfiropt, firmin.c:127-251): partitioned overlap-save, one mask set; taps = calc_firopt's
+ *           fir_bandpass(nc, f_low, f_high, rate, wintype, 1, gain).  Run / flush / destroy: the fircore calls.
+ *   bps     (create_bps / xbps, bandpass.c:35-105): one overlap-save block, size + 1 taps right-justified from index
+ *           size - 1 (fftcv_mults), gain on the spectrum.  Run / flush / destroy: the fircore calls.
+ *   firmin  (create_firmin / xfirmin, firmin.c:35-99): time-domain complex-tap ring FIR, bit-exact.  Run with
+ *           quisk_cuda_batch_run (n_out = count), flush_firmin = quisk_cuda_batch_reset, quisk_cuda_batch_destroy. */
+qcFircore *quisk_cuda_firopt_create(int n_channels, int size, int nc, double f_low, double f_high, int samplerate, int wintype, double gain);
+qcFircore *quisk_cuda_bps_create(int n_channels, int size, double f_low, double f_high, int samplerate, int wintype, double gain);
+qcBatchFilter *quisk_cuda_firmin_create(int n_channels, int nc, double f_low, double f_high, int samplerate, int wintype, double gain);
 
 /* ---- rational resampler (wdsp/resample.c:121-157) ---- */
 typedef struct qcResample qcResample;

@@ -659,6 +659,11 @@ int quisk_cuda_rx_read_trace(qcRxChain *rx, long long *host_out, int n_channels)
     return QC_OK;
 }
 
+const char *quisk_cuda_rx_fused_kernel_name(qcRxChain *rx)
+{
+    return rx ? rx->rx.fused_name : "";
+}
+
 int quisk_cuda_rx_kernel_time(qcRxChain *rx, double *ms_total, int *launches)
 {
     if (!rx) return QC_EINVAL;

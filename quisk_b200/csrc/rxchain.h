@@ -96,6 +96,7 @@ struct RxChain {
     int reset();
     // rxfused.cu
     size_t fusable_prefix(size_t limit);
+    const char *fused_name = "";        // the fused decimator instantiation the last process() launched (bench.py matches ncu captures by it)
     int run_fused_decimator(size_t n_stages, const cd *in, long in_stride, int count, cd *out, long out_stride, int *n_out, cudaStream_t s);
     int reset_fused();
     void release_fused();

@@ -967,12 +967,13 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     };
     int rcb;
     if (use_split) {
-        static const int plans[4][MAXST] = {{282, 242, 222, 222, 142}, {282, 242, 222, 222, 142, 222, 112},
-                                            {282, 242, 222, 222, 142, 222, 222, 112}, {282, 242, 222, 222, 142, 122}};
-        static const int lens[4] = {5, 7, 8, 6};
+        static const int plans[5][MAXST] = {{282, 242, 222, 222, 142}, {282, 242, 222, 222, 142, 222, 112},
+                                            {282, 242, 222, 222, 142, 222, 222, 112}, {282, 242, 222, 222, 142, 122},
+                                            {282, 142, 222, 142}};
+        static const int lens[5] = {5, 7, 8, 6, 4};
         rcb = build(ns, 1);
         bool found = false;
-        for (int p = 0; p < 4 && rcb == QC_OK; p++) {
+        for (int p = 0; p < 5 && rcb == QC_OK; p++) {
             if (lens[p] != ns) continue;
             bool ok = true;
             for (int i = 0; i < ns; i++) ok = ok && codes[i] == plans[p][i];
@@ -1032,11 +1033,13 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         static bool optin[64] = {}; \
         int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63; \
         if (!optin[dev_]) { QC_CUDA(cudaFuncSetAttribute(fused_decim_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin[dev_] = true; } \
+        fused_name = "fused_decim_kernel<" #__VA_ARGS__ ">"; \
         fused_decim_kernel<__VA_ARGS__><<<C, NT, sh, strm>>>(P); } while (0)
 #define QC_LAUNCH_TW(...) do { \
         static bool optin[64] = {}; \
         int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63; \
         if (!optin[dev_]) { QC_CUDA(cudaFuncSetAttribute(fused_decim_tw_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin[dev_] = true; } \
+        fused_name = "fused_decim_tw_kernel<" #__VA_ARGS__ ">"; \
         fused_decim_tw_kernel<__VA_ARGS__><<<C, 192, sh, strm>>>(P); } while (0)
     // tail-warp kernels (default): the stages behind the fourth half band run on a fifth warp, one chunk behind
     if (use_tw) {
@@ -1058,6 +1061,9 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     else if (is_plan(7, {282, 242, 222, 222, 142, 222, 112})) QC_LAUNCH(128, 8, 2, 7, 282, 242, 222, 222, 142, 222, 112);
     else if (is_plan(8, {282, 242, 222, 222, 142, 222, 222, 112})) QC_LAUNCH(128, 8, 2, 8, 282, 242, 222, 222, 142, 222, 222, 112);
     else if (is_plan(6, {282, 242, 222, 222, 142, 122})) QC_LAUNCH(128, 8, 2, 6, 282, 242, 222, 222, 142, 122);
+    // 192 kS/s -> 12 k (SSB at the north star's target rate): HB45 + FIR98/2 to 48 k, HB45 + FIR98/2 to 12 k
+    else if (is_plan(4, {282, 142, 222, 142})) QC_LAUNCH(128, 8, 2, 4, 282, 142, 222, 142);
+    else if (is_plan(4, {82, 142, 22, 142})) QC_LAUNCH(128, 8, 2, 4, 82, 142, 22, 142);
     // half-size chunks (1024 samples): 8 loads in flight per thread instead of 16, half the shared memory, three CTAs per SM
     else if (is_plan(7, {42, 22, 22, 22, 122, 22, 112}, 128)) QC_LAUNCH(128, 4, 3, 7, 42, 22, 22, 22, 122, 22, 112);
     else if (is_plan(5, {42, 22, 22, 22, 122}, 128)) QC_LAUNCH(128, 4, 3, 5, 42, 22, 22, 22, 122);

@@ -89,6 +89,7 @@ int FirCore::init(int C_, int size_, int nc_, int mp_, const double *impulse)
     QC_CUDA(cudaMalloc((void **)&d_gen, (size_t)nfor * n2 * sizeof(cd)));
     int rc = flush(); if (rc != QC_OK) return rc;
     cset = 0; masks_ready = 0;
+    if (!impulse) return QC_OK;             // the caller supplies the mask generator itself (set_gen: xbps)
     return set_impulse(impulse, 1);         // create_fircore: calc_fircore(a, 1)
 }
 
@@ -121,7 +122,12 @@ int FirCore::set_impulse(const double *impulse, int update)
     for (int j = 0; j < nfor; j++)
         for (int i = 0; i < size; i++)
             gen[(size_t)j * n2 + size + i] = make_double2(impulse[2 * ((size_t)size * j + i)], impulse[2 * ((size_t)size * j + i) + 1]);
-    QC_CUDA(cudaMemcpy(d_gen, gen.data(), gen.size() * sizeof(cd), cudaMemcpyHostToDevice));
+    return set_gen(gen.data(), update);
+}
+
+int FirCore::set_gen(const cd *gen, int update)
+{   // masks = forward transforms of nfor time-domain generator rows of 2*size samples
+    QC_CUDA(cudaMemcpy(d_gen, gen, (size_t)nfor * n2 * sizeof(cd), cudaMemcpyHostToDevice));
     int rc = quisk_cuda_fft_batch(d_gen, d_mask[1 - cset], n2, nfor, -1, nullptr);
     if (rc != QC_OK) return rc;
     QC_CUDA(cudaDeviceSynchronize());
@@ -203,6 +209,42 @@ int quisk_cuda_fircore_set_impulse(qcFircore *f, const double *impulse, int upda
 int quisk_cuda_fircore_set_mp(qcFircore *f, int mp) { return f ? f->f.set_mp(mp) : QC_EINVAL; }
 int quisk_cuda_fircore_update(qcFircore *f) { return f ? f->f.update() : QC_EINVAL; }
 int quisk_cuda_fircore_flush(qcFircore *f) { return f ? f->f.flush() : QC_EINVAL; }
+
+// ---- the three variants the reference defines next to fircore and never instantiates ----
+// firopt (firmin.c:127-251): partitioned overlap-save with ONE mask set = fircore's arithmetic with the taps of calc_firopt
+qcFircore *quisk_cuda_firopt_create(int n_channels, int size, int nc, double f_low, double f_high, int samplerate, int wintype, double gain)
+{
+    if (nc <= 0) { qc::set_error("firopt_create: nc"); return nullptr; }
+    std::vector<double> imp((size_t)2 * nc);
+    if (quisk_cuda_fir_bandpass(nc, f_low, f_high, (double)samplerate, wintype, 1, gain, imp.data()) != QC_OK) return nullptr;
+    return quisk_cuda_fircore_create(n_channels, size, nc, 0, imp.data());
+}
+
+// bps (bandpass.c:35-105): one overlap-save block; size + 1 taps stored right-justified from index size - 1 (fftcv_mults,
+// fir.c:29-42), `gain` applied to the spectrum at run time -- folded into the taps here
+qcFircore *quisk_cuda_bps_create(int n_channels, int size, double f_low, double f_high, int samplerate, int wintype, double gain)
+{
+    if (qc::ensure_device() != QC_OK) return nullptr;
+    if (size < 4) { qc::set_error("bps_create: size"); return nullptr; }
+    std::vector<double> imp((size_t)2 * (size + 1));
+    if (quisk_cuda_fir_bandpass(size + 1, f_low, f_high, (double)samplerate, wintype, 1, 1.0 / (double)(2 * size), imp.data()) != QC_OK) return nullptr;
+    qcFircore *f = new qcFircore();
+    if (f->f.init(n_channels, size, size, 0, nullptr) != QC_OK) { f->f.release(); delete f; return nullptr; }
+    std::vector<double2> gen((size_t)2 * size, make_double2(0.0, 0.0));
+    for (int i = 0; i <= size; i++) gen[size - 1 + i] = make_double2(gain * imp[2 * i], gain * imp[2 * i + 1]);
+    if (f->f.set_gen(gen.data(), 1) != QC_OK) { f->f.release(); delete f; return nullptr; }
+    return f;
+}
+
+// firmin (firmin.c:35-99): time-domain complex-tap FIR over a ring of nc samples, newest sample first = quisk_cCDecimate's
+// loop with decim 1; the taps are calc_firmin's.  Run it with quisk_cuda_batch_run, flush_firmin = quisk_cuda_batch_reset.
+qcBatchFilter *quisk_cuda_firmin_create(int n_channels, int nc, double f_low, double f_high, int samplerate, int wintype, double gain)
+{
+    if (nc <= 0 || (nc & (nc - 1))) { qc::set_error("firmin_create: nc must be a power of two (the reference masks its ring index with nc - 1)"); return nullptr; }
+    std::vector<double> imp((size_t)2 * nc);
+    if (quisk_cuda_fir_bandpass(nc, f_low, f_high, (double)samplerate, wintype, 1, gain, imp.data()) != QC_OK) return nullptr;
+    return quisk_cuda_batch_create(QC_C_CDECIMATE, n_channels, imp.data(), nc, 1, 1);
+}
 
 qcResample *quisk_cuda_resample_create(int n_channels, int in_rate, int out_rate, double fc, int ncoef, double gain)
 {

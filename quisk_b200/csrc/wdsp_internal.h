@@ -16,6 +16,7 @@ struct FirCore {
     void release();
     int flush();
     int set_impulse(const double *impulse, int update);
+    int set_gen(const cd *gen, int update);      // masks from nfor x 2*size time-domain generator rows
     int set_mp(int mp);                     // setMp_fircore, firmin.c:469-473
     std::vector<double> h_impulse;          // the impulse as handed in (a->impulse), for set_mp
     int update();

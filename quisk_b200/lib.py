@@ -75,6 +75,8 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rx_reset.argtypes = [vp]
     lib.quisk_cuda_rx_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.quisk_cuda_rx_kernel_time.argtypes = [vp, c_double_p, c_int_p]
+    lib.quisk_cuda_rx_fused_kernel_name.argtypes = [vp]
+    lib.quisk_cuda_rx_fused_kernel_name.restype = C.c_char_p
     lib.quisk_cuda_rx_read_trace.argtypes = [vp, vp, C.c_int]
     lib.quisk_cuda_pan_create.argtypes = [C.c_int, C.c_int]
     lib.quisk_cuda_fp64_peak.argtypes = [C.POINTER(C.c_double)]
@@ -130,6 +132,12 @@ def load() -> C.CDLL:
     lib.quisk_cuda_resample_design.argtypes = [C.c_int, C.c_int, D, C.c_int, D, c_int_p, c_int_p, c_int_p, vp, C.c_int]
     lib.quisk_cuda_fircore_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.quisk_cuda_fircore_create.restype = vp
+    lib.quisk_cuda_firopt_create.argtypes = [C.c_int, C.c_int, C.c_int, D, D, C.c_int, C.c_int, D]
+    lib.quisk_cuda_firopt_create.restype = vp
+    lib.quisk_cuda_bps_create.argtypes = [C.c_int, C.c_int, D, D, C.c_int, C.c_int, D]
+    lib.quisk_cuda_bps_create.restype = vp
+    lib.quisk_cuda_firmin_create.argtypes = [C.c_int, C.c_int, D, D, C.c_int, C.c_int, D]
+    lib.quisk_cuda_firmin_create.restype = vp
     lib.quisk_cuda_fircore_destroy.argtypes = [vp]; lib.quisk_cuda_fircore_destroy.restype = None
     lib.quisk_cuda_fircore_run.argtypes = [vp, vp, C.c_long, vp, C.c_long, vp]
     lib.quisk_cuda_fircore_set_impulse.argtypes = [vp, vp, C.c_int]

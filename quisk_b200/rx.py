@@ -120,6 +120,10 @@ class RxChain:
         L.check(self.lib, self.lib.quisk_cuda_rx_kernel_time(self.h, C.byref(ms), C.byref(n)), "rx_kernel_time")
         return ms.value, n.value
 
+    def fused_kernel_name(self):
+        """Template instantiation of the fused decimator the last process() launched ("" on the per-stage path)."""
+        return self.lib.quisk_cuda_rx_fused_kernel_name(self.h).decode()
+
     def close(self):
         if self.h:
             self.lib.quisk_cuda_rx_destroy(self.h); self.h = None
