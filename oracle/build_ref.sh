@@ -77,4 +77,26 @@ wait
 gcc -O3 -fPIC -w -c "$HERE/fftw_shim/fftw_shim.c" -o "$TMP/wobj/_fftw_shim.o"
 gcc -O3 -fPIC -w -c "$HERE/fft64.c" -o "$TMP/wobj/_fft64.o"
 gcc -shared -o "$OUT/libwdsp_ref.so" "$TMP"/wobj/*.o -lm -lpthread
+# 4. The reference's WHOLE _quisk extension (setup.py:17-20 source list; the five audio back ends replaced by
+#    ref_wrap/sound_stub.c, FFTW3 by the shim), twice: against its own filter.c, and against libquisk_cuda.so instead
+#    (the filter.h swap-in of INTEGRATION.md section 1 under the real quisk_process_samples / quisk_read_sound), plus
+#    the B4 sample-source plugin quisk_b200/plugin/quisk_block_source.c built like the reference's hardware plugins.
+QSRC="quisk.c sound.c is_key_down.c microphone.c utility.c extdemod.c freedv.c quisk_wdsp.c ac2yd/remote.c tci.c base64.c handshake.c sha1.c utf8.c ws.c"
+mkdir -p "$TMP/qobj" "$OUT/quisk_full/ref" "$OUT/quisk_full/cuda"
+for f in $QSRC; do
+    gcc -O2 -fPIC -w -I"$PYINC" -I"$REF" -I"$HERE/fftw_shim" -c "$REF/$f" -o "$TMP/qobj/$(basename "$f" .c).o" &
+done
+gcc -O2 -fPIC -w -I"$PYINC" -I"$REF" -c "$REF/filter.c" -o "$TMP/filter.o" &
+gcc -O2 -fPIC -w -I"$PYINC" -I"$REF" -c "$HERE/ref_wrap/sound_stub.c" -o "$TMP/qobj/_sound_stub.o" &
+gcc -O2 -fPIC -w -c "$HERE/fftw_shim/fftw_shim.c" -o "$TMP/qobj/_fftw_shim.o" &
+gcc -O2 -fPIC -w -c "$HERE/fft64.c" -o "$TMP/qobj/_fft64.o" &
+wait
+gcc -shared -o "$OUT/quisk_full/ref/_quisk.so" "$TMP"/qobj/*.o "$TMP/filter.o" -lm -lpthread
+if [ -f "$CUDALIB" ]; then
+    gcc -O2 -fPIC -w -I"$PYINC" -I"$REF" -c "$TMP/filters_data.c" -o "$TMP/filters_data.o"
+    gcc -shared -o "$OUT/quisk_full/cuda/_quisk.so" "$TMP"/qobj/*.o "$TMP/filters_data.o" \
+        -L"$HERE/../quisk_b200" -lquisk_cuda -Wl,-rpath,'$ORIGIN/../../../../quisk_b200' -lm -lpthread
+fi
+gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" "$HERE/../quisk_b200/plugin/quisk_block_source.c" "$REF/import_quisk_api.c" \
+    -o "$OUT/quisk_full/quisk_block_source.so"
 echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')"

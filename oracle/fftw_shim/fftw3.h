@@ -14,7 +14,12 @@
 extern "C" {
 #endif
 
+/* as FFTW itself does: the C99 type when <complex.h> came first (quisk.c:5-6), else double[2] (wdsp) -- same bytes */
+#if defined(_Complex_I) && defined(complex) && defined(I)
+typedef double _Complex fftw_complex;
+#else
 typedef double fftw_complex[2];
+#endif
 typedef struct fftw_shim_plan_s *fftw_plan;
 
 #define FFTW_FORWARD  (-1)
@@ -38,6 +43,7 @@ void *fftw_malloc(size_t n);
 void fftw_free(void *p);
 int fftw_import_wisdom_from_filename(const char *filename);
 int fftw_export_wisdom_to_filename(const char *filename);
+char *fftw_export_wisdom_to_string(void);
 
 #ifdef __cplusplus
 }
