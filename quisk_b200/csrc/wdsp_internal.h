@@ -141,6 +141,7 @@ struct Rxa {
     int xrxa(const void *din, long is, void *dout, long os, cudaStream_t s);
     // wdsp_rxa_fused.cu: the whole chain as one kernel for the configurations it covers, any number of DSP blocks per launch
     int fused_ok = 1;                       // QC_RXA_OPT_FUSED
+    double *d_wide_seq = nullptr; size_t wide_seq_cap = 0;                                           // pre-kernel outputs of the pipelined wide path
     cd *d_wide_spec = nullptr, *d_wide_y = nullptr; size_t wide_spec_cap = 0, wide_y_cap = 0;      // scratch of the many-blocks-per-launch path
     bool fusable() const;
     int xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s);

@@ -192,6 +192,7 @@ void Rxa::release()
     if (wmid) cudaFree(wmid); if (wmid2) cudaFree(wmid2); if (waudio) cudaFree(waudio);
     wmid = wmid2 = waudio = nullptr; wstride = 0;
     if (d_wide_spec) cudaFree(d_wide_spec); if (d_wide_y) cudaFree(d_wide_y);
+    if (d_wide_seq) cudaFree(d_wide_seq); d_wide_seq = nullptr; wide_seq_cap = 0;
     d_wide_spec = d_wide_y = nullptr; wide_spec_cap = wide_y_cap = 0;
     if (d_sip) cudaFree(d_sip); if (d_sipout) cudaFree(d_sipout);
     d_sip = nullptr; d_sipout = nullptr; sipout_cap = 0;

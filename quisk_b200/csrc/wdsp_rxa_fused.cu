@@ -126,18 +126,20 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
             // runs of sixteen samples on the assumption that the state does not change
             const double M = state_ == 0 ? k_attack : (state_ == 3 ? k_decay : k_hdecay);
             const bool want = state_ == 0;
-            double rm[CH], rn[CH];
+            double rm[CH], rn[CH], vp[CH];
             unsigned a0 = rv_s + 8u * (unsigned)i;
 #pragma unroll
             for (int j = 0; j < CH; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rm[j]) : "r"(a0 + 8u * j));
+            // The commit of a run that held is issued INSIDE the next run's chain (a single warp issues in order: sixteen stores and
+            // sixteen loads in front of the chain cost ~100 cycles per run, under it nothing).  Until the first run of this visit has
+            // held, the slot stores its own input back (vp = rm at the same addresses): a no-op.
+            unsigned ap = a0;
+#pragma unroll
+            for (int j = 0; j < CH; j++) vp[j] = rm[j];
             bool ok = true;
             while (ok && n - i >= CH) {
                 // the following run's ring_max is asked for now (RV beyond this run is still input): its latency hides under the chain
                 const bool more = n - i >= 2 * CH;
-                if (more) {
-#pragma unroll
-                    for (int j = 0; j < CH; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rn[j]) : "r"(a0 + 8u * (CH + j)));
-                }
                 double v = volts;
                 // The run holds if every d = ring_max - volts has the sign the state expects (d >= 0: attack, d < 0: decay; d is the
                 // chain's own first operation), read from the SIGN BITS with integer logic, off the chain.  The min_volts clamp needs
@@ -152,12 +154,15 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
                     const int hd = __double2hiint(d);
                     s_and &= hd; s_or |= hd;
                     vv[j] = v;
+                    asm volatile("st.shared.f64 [%0], %1;" :: "r"(ap + 8u * j), "d"(vp[j]) : "memory");
+                    if (more) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rn[j]) : "r"(a0 + 8u * (CH + j)));
                 }
                 ok = want ? s_or >= 0 : (s_and < 0 && !(v < k_minv));
                 if (ok) {
-                    // commit (all lanes store the same values)
+                    // held: its values wait in vp for the next pass through the loop (or the flush below)
+                    ap = a0;
 #pragma unroll
-                    for (int j = 0; j < CH; j++) asm volatile("st.shared.f64 [%0], %1;" :: "r"(a0 + 8u * j), "d"(vv[j]) : "memory");
+                    for (int j = 0; j < CH; j++) vp[j] = vv[j];
                     volts = v;
                     hang_counter = hang_counter > CH ? hang_counter - CH : 0;
                     i += CH;
@@ -166,6 +171,9 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
                     for (int j = 0; j < CH; j++) rm[j] = rn[j];
                 }
             }
+            // whatever held last is still in registers: commit it (after a failed run it has been stored already; storing twice is harmless)
+#pragma unroll
+            for (int j = 0; j < CH; j++) asm volatile("st.shared.f64 [%0], %1;" :: "r"(ap + 8u * j), "d"(vp[j]) : "memory");
             if (ok) continue;                               // fewer than a run's worth of samples left
             // the run did not hold (a handful of times per block): these samples go through the general machine one by one
             for (int g = 0; g < CH; g++) {
@@ -614,6 +622,307 @@ int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_str
     return QC_OK;
 }
 
+// ---- the wide path's sequential part, pipelined --------------------------------------------------------------------------
+// With the filters done for all blocks (fircore_wide), what is left per block is: (A) magnitudes, block maxima and the AGC's
+// sliding maximum -- parallel along time AND across blocks; (S) the volts machine and the meters' recurrences -- sequential;
+// (B) gain law, panel, output -- parallel, needs volts.  The one-kernel form above runs A, S, B one after the other for
+// every block (72 k cycles per 1024-sample block, 41 k of them S).  Here A is a grid of (channel, block) CTAs of its own
+// (rxa_wide_pre_kernel: ring_max, |y|^2, |x|^2, the delayed magnitudes and the block maxima go to global scratch), and the
+// per-channel kernel (rxa_wide_seq_kernel) is a two-stage pipeline over double-buffered shared memory: while the AGC / LIN
+// warps walk block t, the workers apply the gain law to block t - 1 and fetch block t + 1's inputs.  The sequential lanes
+// are then the only thing on the critical path.  Same arithmetic, same order, same state arrays as the kernel above.
+struct RxaWideParams {
+    const cd *y; long y_stride;             // the filtered stream [C][nblocks * n]
+    const cd *xadc; long adc_stride;        // the raw input (ADC meter)
+    cd *out; long out_stride;
+    int n, nblocks, C;
+    double *rm, *sms, *smadc, *absd;        // [C][nblocks * n]: ring_max, |y|^2, |x|^2, |sample leaving the AGC delay line|
+    double *np;                             // [C][nblocks][2]: block maxima of |x|^2, |y|^2
+    double *mst[3]; double *mres[3]; double m_ma, m_mp; const double *mtable;
+    int agc_run; double *agc_state; double *agc_hist; AgcParams a;
+    double gI, gQ; cd *sip; int sipsize, sip_idx;
+};
+
+__device__ __forceinline__ double rf_mag(cd v, int pmode)
+{
+    if (pmode == 0) { const double f0 = fabs(v.x), f1 = fabs(v.y); return f0 < f1 ? f1 : f0; }
+    return __dsqrt_rn(rf_smag(v));
+}
+
+__global__ void __launch_bounds__(RF_WORK) rxa_wide_pre_kernel(RxaWideParams P)
+{
+    extern __shared__ double smem_raw[];
+    const int n = P.n, c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const bool agc_on = P.agc_run && P.a.mode != 0;
+    const int ab = agc_on ? P.a.attack_buffsize : 0, tot = ab + n;
+    double *A = smem_raw, *BM = A + tot, *SC = BM + ((tot + 31) / 32 + 1);
+    const cd *ys = P.y + (size_t)c * P.y_stride, *x = ys + (size_t)b * n;
+    const cd *xa = P.xadc + (size_t)c * P.adc_stride + (size_t)b * n;
+    const double *hs = P.agc_hist + (size_t)c * (agc_on ? ab : 1) * 3;
+    const size_t off = ((size_t)c * P.nblocks + b) * n;
+    double *rm = P.rm + off, *sms = P.sms + off, *smadc = P.smadc + off, *absd = P.absd + off;
+    // [history | block] magnitudes: the history is the stream's own past, or the saved ring in front of the launch
+    for (int j = tid; j < ab; j += RF_WORK) {
+        const long idx = (long)b * n - ab + j;
+        A[j] = idx >= 0 ? rf_mag(ys[idx], P.a.pmode) : hs[(idx + ab) * 3 + 2];
+    }
+    double mx_adc = 0.0, mx_s = 0.0;
+    for (int i = tid; i < n; i += RF_WORK) {
+        const cd v = x[i], av = xa[i];
+        const double sm = rf_smag(v), sa = rf_smag(av);
+        sms[i] = sm; smadc[i] = sa;
+        mx_s = sm > mx_s ? sm : mx_s; mx_adc = sa > mx_adc ? sa : mx_adc;
+        if (agc_on) A[ab + i] = P.a.pmode == 0 ? rf_mag(v, 0) : __dsqrt_rn(sm);
+    }
+    rf_block_max(mx_adc, SC, SC + 4, tid);
+    rf_bar_work();
+    rf_block_max(mx_s, SC, SC + 5, tid);
+    rf_bar_work();
+    if (tid == 0) { P.np[((size_t)c * P.nblocks + b) * 2] = SC[4]; P.np[((size_t)c * P.nblocks + b) * 2 + 1] = SC[5]; }
+    if (!agc_on) return;
+    for (int i = tid; i < n; i += RF_WORK) absd[i] = A[i];
+    // ring_max[i] = max A[i + 1 .. i + ab], as in rf_worker_role
+    const int per = (n + RF_WORK - 1) / RF_WORK;
+    const int nblk = (tot + 31) >> 5;
+    for (int j = tid; j < nblk; j += RF_WORK) {
+        double mx = 0.0;
+        const int e = min(tot, (j + 1) << 5);
+        for (int k = j << 5; k < e; k++) mx = A[k] > mx ? A[k] : mx;
+        BM[j] = mx;
+    }
+    rf_bar_work();
+    const int i0 = tid * per;
+    if (i0 < n) {
+        const int cnt = min(per, n - i0);
+        if (ab >= per) {
+            const int lo = i0 + per, hi = i0 + ab;
+            double core = 0.0;
+            const int b0 = (lo + 31) >> 5, b1 = (hi + 1) >> 5;
+            if (b0 >= b1) {
+                for (int k = lo; k <= hi; k++) core = A[k] > core ? A[k] : core;
+            } else {
+                for (int k = lo; k < (b0 << 5); k++) core = A[k] > core ? A[k] : core;
+                for (int j = b0; j < b1; j++) core = BM[j] > core ? BM[j] : core;
+                for (int k = b1 << 5; k <= hi; k++) core = A[k] > core ? A[k] : core;
+            }
+            double hd[8], tl[8];
+            double run = 0.0;
+#pragma unroll
+            for (int k = 7; k >= 0; k--) { if (k < per) { hd[k] = run; const int q = i0 + k; if (k > 0 && q < tot) run = A[q] > run ? A[q] : run; } }
+            run = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { if (k < per) { if (k > 0) { const int q = i0 + ab + k; if (q < tot) run = A[q] > run ? A[q] : run; } tl[k] = run; } }
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < cnt) { double r = core > hd[k] ? core : hd[k]; r = tl[k] > r ? tl[k] : r; rm[i0 + k] = r; }
+        } else {
+            for (int k = 0; k < cnt; k++) { double r = 0.0; for (int q = i0 + k + 1; q <= i0 + k + ab; q++) r = A[q] > r ? A[q] : r; rm[i0 + k] = r; }
+        }
+    }
+}
+
+struct RwSmem {
+    double *RV[2], *SMS[2], *SMADC[2], *ABSD[2], *SMAGC[2], *FBA, *HBA, *SC;
+    volatile int *linpos;
+};
+__device__ __forceinline__ RwSmem rw_map(double *raw, int n)
+{
+    RwSmem m;
+    double *p = raw;
+    for (int k = 0; k < 2; k++) { m.RV[k] = p; p += n; m.SMS[k] = p; p += n; m.SMADC[k] = p; p += n; m.ABSD[k] = p; p += n; m.SMAGC[k] = p; p += n; }
+    m.FBA = p; p += n; m.HBA = p; p += n;
+    m.SC = p; p += 64;              // 0..3 warp maxima; 8 + 3 * parity + {0 adc, 1 s, 2 agc}: block maxima; 16..47 LIN lanes' dummy store targets
+    m.linpos = reinterpret_cast<volatile int *>(p);
+    return m;
+}
+static size_t rxa_wide_seq_smem(int n) { return ((size_t)12 * n + 64 + 2) * sizeof(double); }
+
+// block t's inputs from the pre kernel's scratch into the shared buffers of its parity
+__device__ __forceinline__ void rw_load_block(const RxaWideParams &P, const RwSmem &m, int n, int c, int t, int tid, bool agc_on)
+{
+    const size_t off = ((size_t)c * P.nblocks + t) * n;
+    const int par = t & 1;
+    double v[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = tid + k * RF_WORK;
+        if (i < n) {
+            v[0][k] = P.sms[off + i]; v[1][k] = P.smadc[off + i];
+            if (agc_on) { v[2][k] = P.rm[off + i]; v[3][k] = P.absd[off + i]; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = tid + k * RF_WORK;
+        if (i < n) {
+            m.SMS[par][i] = v[0][k]; m.SMADC[par][i] = v[1][k];
+            if (agc_on) { m.RV[par][i] = v[2][k]; m.ABSD[par][i] = v[3][k]; }
+        }
+    }
+    if (tid < 2) m.SC[8 + 3 * par + tid] = P.np[((size_t)c * P.nblocks + t) * 2 + tid];
+}
+
+// gain law, panel, output, siphon for block tb (its volts are in RV[tb & 1])
+__device__ __forceinline__ void rw_gain_block(const RxaWideParams &P, const RwSmem &m, int n, int c, int tb, int tid, bool agc_on, int ab, const double *hs)
+{
+    const int par = tb & 1;
+    const double *RV = m.RV[par];
+    double *SMAGC = m.SMAGC[par];
+    const cd *ys = P.y + (size_t)c * P.y_stride;
+    cd *y = P.out + (size_t)c * P.out_stride + (size_t)tb * n;
+    double mx_agc = 0.0;
+    cd dl[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = tid + k * RF_WORK;
+        if (i < n) {
+            const long idx = (long)tb * n + i - ab;         // the sample leaving the AGC's delay line
+            dl[k] = idx >= 0 ? ys[idx] : make_double2(hs[(idx + ab) * 3], hs[(idx + ab) * 3 + 1]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = tid + k * RF_WORK;
+        if (i >= n) continue;
+        cd o;
+        const cd d = dl[k];
+        if (agc_on) {
+            const double volts = RV[i];
+            const double lg = log10(__dmul_rn(P.a.inv_max_input, volts));
+            const double mult = __ddiv_rn(__dsub_rn(P.a.out_target, __dmul_rn(P.a.slope_constant, 0.0 < lg ? 0.0 : lg)), volts);
+            o = make_double2(__dmul_rn(d.x, mult), __dmul_rn(d.y, mult));
+        } else {
+            o = P.agc_run ? make_double2(__dmul_rn(P.a.fixed_gain, d.x), __dmul_rn(P.a.fixed_gain, d.y)) : d;
+        }
+        const double sm = rf_smag(o);
+        SMAGC[i] = sm;
+        mx_agc = sm > mx_agc ? sm : mx_agc;
+        if (P.sip) {
+            if (n >= P.sipsize) { if (i >= n - P.sipsize) P.sip[(size_t)c * P.sipsize + (i - (n - P.sipsize))] = o; }
+            else P.sip[(size_t)c * P.sipsize + ((P.sip_idx + tb * n + i) & (P.sipsize - 1))] = o;
+        }
+        y[i] = make_double2(__dmul_rn(P.gI, o.x), __dmul_rn(P.gQ, o.y));
+    }
+    rf_block_max(mx_agc, m.SC, m.SC + 8 + 3 * par + 2, tid);
+}
+
+__device__ __forceinline__ void rw_worker_role(const RxaWideParams &P, const RwSmem &m, int n, int c, int tid, bool agc_on, int ab, double *hs)
+{
+    const int nb = P.nblocks;
+    rw_load_block(P, m, n, c, 0, tid, agc_on);
+    rf_bar_all();                                           // set-up done
+    for (int t = 0; t < nb; t++) {
+        rf_bar_all();                                       // the sequential lanes start block t
+        if (t >= 1) rw_gain_block(P, m, n, c, t - 1, tid, agc_on, ab, hs);
+        rf_bar_work();                                      // RV[(t + 1) & 1] is free: every worker has read block t - 1's volts
+        if (t + 1 < nb) rw_load_block(P, m, n, c, t + 1, tid, agc_on);
+        rf_bar_all();                                       // block t's volts are final, block t + 1's inputs are in place
+    }
+    rf_bar_all();
+    rw_gain_block(P, m, n, c, nb - 1, tid, agc_on, ab, hs);
+    rf_bar_work();
+    if (agc_on) {
+        // the AGC ring for the next launch: the stream's last ab samples (older ones, when the launch was shorter than the ring, move down)
+        const long N = (long)nb * n;
+        const cd *ys = P.y + (size_t)c * P.y_stride;
+        if (N < ab) {
+            const int keep = ab - (int)N;
+            for (int j0 = 0; j0 < keep; j0 += RF_WORK) {
+                const int j = j0 + tid;
+                double r0 = 0, r1 = 0, r2 = 0;
+                if (j < keep) { r0 = hs[(N + j) * 3]; r1 = hs[(N + j) * 3 + 1]; r2 = hs[(N + j) * 3 + 2]; }
+                rf_bar_work();
+                if (j < keep) { hs[j * 3] = r0; hs[j * 3 + 1] = r1; hs[j * 3 + 2] = r2; }
+                rf_bar_work();
+            }
+        }
+        for (int k = tid + (N < ab ? ab - (int)N : 0); k < ab; k += RF_WORK) {
+            const cd v = ys[N - ab + k];
+            hs[k * 3] = v.x; hs[k * 3 + 1] = v.y; hs[k * 3 + 2] = rf_mag(v, P.a.pmode);
+        }
+    }
+    rf_bar_all();
+}
+
+__device__ __forceinline__ void rw_agc_role(const RxaWideParams &P, const RwSmem &m, int n, bool agc_on, double *ast, bool lane0)
+{
+    double volts = ast[3], save_volts = ast[4];
+    int hang_counter = (int)ast[7], decay_type = (int)ast[8], state_ = (int)ast[9];
+    rf_bar_all();
+    for (int t = 0; t < P.nblocks; t++) {
+        rf_bar_all();
+        if (agc_on) rf_agc_block(m.RV[t & 1], m.FBA, m.HBA, m.linpos, n, P.a, volts, save_volts, hang_counter, decay_type, state_, nullptr);
+        if (lane0 && agc_on && t == P.nblocks - 1) {
+            ast[3] = volts; ast[4] = save_volts;
+            ast[7] = hang_counter; ast[8] = decay_type; ast[9] = state_; ast[10] = __dmul_rn(volts, P.a.inv_out_target);
+        }
+        rf_bar_all();
+    }
+    rf_bar_all();
+    rf_bar_all();
+}
+
+__device__ __forceinline__ void rw_lin_role(const RxaWideParams &P, const RwSmem &m, int n, int c, int lane, bool agc_on, double *ast)
+{
+    // lanes as in rf_lin_role; the AGC meter's lanes run TWO blocks late here (block t - 1's gain law runs beside block t)
+    const int mt = lane < 6 ? lane >> 1 : 3, pk = lane & 1, nb = P.nblocks;
+    const bool meter = lane < 6, back = agc_on && (lane == 6 || lane == 7), live = meter || back;
+    double s = meter ? P.mst[mt][(size_t)c * 2 + pk] : (back ? ast[lane - 1] : 0.0);
+    double c1 = 0.0, c2 = 0.0;
+    if (meter) { c1 = pk ? 0.0 : 1.0 - P.m_ma; c2 = pk ? P.m_mp : P.m_ma; }
+    else if (lane == 6) { c1 = P.a.fast_backmult; c2 = P.a.onemfast_backmult; }
+    else if (lane == 7) { c1 = P.a.hang_backmult; c2 = P.a.onemhang_backmult; }
+    double *dst = lane == 6 ? m.FBA : (lane == 7 ? m.HBA : m.SC + 16 + lane);
+    const int dstep = lane == 6 || lane == 7 ? 1 : 0;
+    if (lane == 0) *m.linpos = 0;
+    rf_bar_all();
+    for (int t = 0; t < nb; t++) {
+        rf_bar_all();
+        const int par = t & 1;
+        const double *src = mt == 0 ? m.SMADC[par] : (mt == 1 ? m.SMS[par] : (mt == 2 ? m.SMAGC[par] : (back ? m.ABSD[par] : m.SMS[par])));
+        const bool run = mt != 2 || t >= 2;
+        const double r = rf_lin_block(run ? src : m.SMS[par], n, run ? c1 : 0.0, run ? c2 : 1.0, s, dst, dstep, m.linpos);
+        if (live) { s = r; if (meter && pk && run) { const double np = m.SC[8 + 3 * par + mt]; if (np > s) s = np; } }
+        rf_bar_all();
+        if (lane == 0) *m.linpos = 0;
+    }
+    // the AGC meter's last two blocks: nb - 2 beside the workers' last gain pass, nb - 1 after it
+    rf_bar_all();
+    if (nb >= 2) {
+        const int par = nb & 1;
+        const double r = rf_lin_block(m.SMAGC[par], n, mt == 2 ? c1 : 0.0, mt == 2 ? c2 : 1.0, s, m.SC + 16 + lane, 0, nullptr);
+        if (mt == 2) { s = r; if (pk) { const double np = m.SC[8 + 3 * par + 2]; if (np > s) s = np; } }
+    }
+    rf_bar_all();
+    {
+        const int par = (nb - 1) & 1;
+        const double r = rf_lin_block(m.SMAGC[par], n, mt == 2 ? c1 : 0.0, mt == 2 ? c2 : 1.0, s, m.SC + 16 + lane, 0, nullptr);
+        if (mt == 2) { s = r; if (pk) { const double np = m.SC[8 + 3 * par + 2]; if (np > s) s = np; } }
+    }
+    if (meter) {
+        P.mst[mt][(size_t)c * 2 + pk] = s;
+        P.mres[mt][(size_t)c * 3 + pk] = 10.0 * mlog10_dev(P.mtable, s + 1.0e-40);
+        if (lane == 4) P.mres[2][(size_t)c * 3 + 2] = 20.0 * mlog10_dev(P.mtable, ast[10] + 1.0e-40);
+        else if (!pk) P.mres[mt][(size_t)c * 3 + 2] = 0.0;
+    } else if (back) {
+        ast[lane - 1] = s;
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(RF_THREADS, MINB) rxa_wide_seq_kernel(RxaWideParams P)
+{
+    extern __shared__ double smem_raw[];
+    const int n = P.n, c = blockIdx.x, tid = threadIdx.x;
+    const bool agc_on = P.agc_run && P.a.mode != 0;
+    const int ab = agc_on ? P.a.attack_buffsize : 0;
+    const RwSmem m = rw_map(smem_raw, n);
+    double *hs = P.agc_hist + (size_t)c * (agc_on ? ab : 1) * 3;
+    double *ast = P.agc_state + (size_t)c * 16;
+    if (tid < RF_WORK) rw_worker_role(P, m, n, c, tid, agc_on, ab, hs);
+    else if (tid < RF_WORK + 32) rw_agc_role(P, m, n, agc_on, ast, tid == RF_WORK);
+    else rw_lin_role(P, m, n, c, tid - RF_WORK - 32, agc_on, ast);
+}
+
 size_t rxa_fused_smem(int n, int ab)
 {
     const int n2 = 2 * n, tot = ab + n;
@@ -655,6 +964,48 @@ int Rxa::xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, 
         }
         P.in_adc = (const cd *)din; P.adc_stride = is;
         P.in = d_wide_y; P.in_stride = ys;
+        if (!getenv("QUISK_RXA_WIDE_SERIAL")) {
+            // pipelined form: pre kernel over (channel, block), then the two-stage per-channel kernel
+            RxaWideParams W;
+            memset(&W, 0, sizeof(W));
+            W.y = d_wide_y; W.y_stride = ys; W.xadc = (const cd *)din; W.adc_stride = is; W.out = (cd *)dout; W.out_stride = os;
+            W.n = dsp_size; W.nblocks = nblocks; W.C = C;
+            const size_t per = (size_t)C * nblocks * dsp_size, need = 4 * per + (size_t)C * nblocks * 2;
+            if (need > wide_seq_cap) { if (d_wide_seq) cudaFree(d_wide_seq); d_wide_seq = nullptr; wide_seq_cap = 0;
+                                       QC_CUDA(cudaMalloc((void **)&d_wide_seq, need * sizeof(double))); wide_seq_cap = need; }
+            W.rm = d_wide_seq; W.sms = W.rm + per; W.smadc = W.sms + per; W.absd = W.smadc + per; W.np = W.absd + per;
+            SeqStage *mt[3] = {adcmeter, smeter, agcmeter};
+            for (int m = 0; m < 3; m++) { W.mst[m] = mt[m]->d_state; W.mres[m] = mt[m]->d_meter; }
+            W.m_ma = adcmeter->par[0]; W.m_mp = adcmeter->par[1];
+            W.mtable = mlog10_table();
+            if (!W.mtable) { set_error("rxa: table allocation failed"); return QC_ENOMEM; }
+            W.agc_run = agc_run; W.agc_state = agc->d_state; W.agc_hist = agc->d_ring; W.a = agc->agc;
+            W.gI = panel_gain1 * panel_gain2I; W.gQ = panel_gain1 * panel_gain2Q;
+            W.sip = sip_run ? d_sip : nullptr; W.sipsize = sipsize; W.sip_idx = sip_idx;
+            const int ab = agc_run && agc->agc.mode != 0 ? agc->agc.attack_buffsize : 0;
+            const int tot = ab + dsp_size;
+            const size_t sh_pre = ((size_t)tot + (tot + 31) / 32 + 1 + 16) * sizeof(double);
+            if (sh_pre > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_wide_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_pre));
+            rxa_wide_pre_kernel<<<dim3(C, nblocks), RF_WORK, sh_pre, s>>>(W);
+            count_launch();
+            QC_CUDA_LAUNCH();
+            const size_t sh = rxa_wide_seq_smem(dsp_size);
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            const char *force = getenv("QUISK_RXA_MINB");
+            const bool fat = force ? atoi(force) == 1 : C <= n_sm;
+            if (fat) {
+                if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_wide_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+                rxa_wide_seq_kernel<1><<<C, RF_THREADS, sh, s>>>(W);
+            } else {
+                if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_wide_seq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+                rxa_wide_seq_kernel<2><<<C, RF_THREADS, sh, s>>>(W);
+            }
+            count_launch();
+            QC_CUDA_LAUNCH();
+            if (sip_run && dsp_size < sipsize) sip_idx = (int)(((long)sip_idx + (long)nblocks * dsp_size) & (sipsize - 1));
+            return QC_OK;
+        }
     }
     for (FirCore *f : firs) {
         if (!f || wide) continue;
