@@ -284,7 +284,14 @@ int Rxa::xrxa_stages_wide(const void *din, long is, void *dout, long os, int g, 
     }
     if (rc == QC_OK && bp1_run) rc = fircore_wide(bp1, m, ws, m, ws, g, d_wide_spec, s);
     if (rc == QC_OK && agc_run) { rc = agc->run(m, ws, wmid2, ws, n, s); m = wmid2; }
-    if (rc == QC_OK) rc = agcmeter->run(m, ws, agc->d_state, 0, n, s);
+    bool agc_meter_aside = false;
+    if (rc == QC_OK && side && !rsmpout) {
+        // the AGC meter only reads the AGC's output and state: beside the panel on the side stream (the panel writes elsewhere)
+        QC_CUDA(cudaEventRecord(ev_a, s)); QC_CUDA(cudaStreamWaitEvent(side, ev_a, 0));
+        rc = agcmeter->run(m, ws, agc->d_state, 0, n, side);
+        QC_CUDA(cudaEventRecord(ev_b, side));
+        agc_meter_aside = true;
+    } else if (rc == QC_OK) rc = agcmeter->run(m, ws, agc->d_state, 0, n, s);
     for (SeqStage *mt : {adcmeter, smeter, agcmeter}) mt->meter_sub = 1;
     if (rc != QC_OK) return rc;
     cd *sp = sip_run ? d_sip : nullptr;
@@ -298,6 +305,7 @@ int Rxa::xrxa_stages_wide(const void *din, long is, void *dout, long os, int g, 
     } else {
         rc = launch_panel(m, ws, (cd *)dout, os, n, C, panel_gain1 * panel_gain2I, panel_gain1 * panel_gain2Q, 3, 0, s, sp, sipsize, sidx); if (rc) return rc;
     }
+    if (agc_meter_aside) QC_CUDA(cudaStreamWaitEvent(s, ev_b, 0));      // the meter has read the scratch (the next group's stages write it) and the AGC state
     return QC_OK;
 }
 

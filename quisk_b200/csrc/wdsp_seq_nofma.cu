@@ -327,33 +327,56 @@ __global__ void fmpll_kernel(const cd *in, long is, cd *out, long os, int n, int
     const unsigned ang_s = (unsigned)__cvta_generic_to_shared(ang);
     int i = 0;
     for (; i + 8 <= n; i += 8) {
-        double a8[8];
+        double a8[8], o8[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a8[j]) : "r"(ang_s + 8u * (unsigned)(i + j)));
+        // eight samples without a branch: a branch on the wrapped phase in every sample makes the (in-order) warp wait for the end
+        // of the phase chain before it may issue the next sample's det / omega / fil_out, which do not depend on it -- 155 cycles
+        // per sample instead of ~55.  Whether a single wrap was enough is collected off the chain and looked at once per group;
+        // if not (|del_out| > 2 pi: not with any loop bandwidth the stage is built with) the group is redone with the reference's loops.
+        const double phs0 = phs, fil0 = fil_out, om0 = omega, dc0 = fmdc;
+        bool bad = false;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const double a_x = a8[j];
             double det = a_x - phs;                             // in (-3 pi, pi]
             const double detw = det + TWOPI_D;
             det = det <= -kPI ? detw : det;
-            det = a_x > 1.0e299 ? 0.0 : det;
+            bad = bad || a_x > 1.0e299;                         // x == 0 (det = 0, fmd.c:158): the slow path handles it
             const double del_out = fil_out;
-            omega = fmin(fmax(omega + g2 * det, omega_min), omega_max);     // the two ifs of fmd.c:161-162 (no NaNs here)
+            omega = omega + g2 * det;                           // the two clamps of fmd.c:161-162 rarely act: tested off the chain
+            bad = bad || omega < omega_min || omega > omega_max;
             fil_out = g1 * det + omega;
-            double p = phs + del_out;
-            const double pm = p - TWOPI_D;
-            p = p >= TWOPI_D ? pm : p;
-            const double pp = p + TWOPI_D;
-            p = p < 0.0 ? pp : p;
-            if (p >= TWOPI_D || p < 0.0) {                      // |del_out| > 2 pi: not with any loop bandwidth the stage is built with
-                while (p >= TWOPI_D) p -= TWOPI_D;
-                while (p < 0.0) p += TWOPI_D;
-            }
-            phs = p;
+            const double p = phs + del_out;
+            const double pm = p - TWOPI_D, pp = p + TWOPI_D;    // both candidates and both tests hang off p side by side
+            const double pn = p >= TWOPI_D ? pm : (p < 0.0 ? pp : p);
+            bad = bad || pn >= TWOPI_D || pn < 0.0;
+            phs = pn;
             fmdc = mtau * fmdc + onem_mtau * fil_out;
-            const double a = again * (fil_out - fmdc);
-            asm volatile("st.shared.f64 [%0], %1;" :: "r"(ang_s + 8u * (unsigned)(i + j)), "d"(a) : "memory");
+            o8[j] = again * (fil_out - fmdc);
         }
+        if (bad) {
+            phs = phs0; fil_out = fil0; omega = om0; fmdc = dc0;
+            for (int j = 0; j < 8; j++) {
+                const double a_x = ang[i + j];
+                double det = a_x - phs;
+                if (det <= -kPI) det += TWOPI_D;
+                if (a_x > 1.0e299) det = 0.0;
+                const double del_out = fil_out;
+                omega += g2 * det;
+                if (omega < omega_min) omega = omega_min;
+                if (omega > omega_max) omega = omega_max;
+                fil_out = g1 * det + omega;
+                phs += del_out;
+                while (phs >= TWOPI_D) phs -= TWOPI_D;
+                while (phs < 0.0) phs += TWOPI_D;
+                fmdc = mtau * fmdc + onem_mtau * fil_out;
+                ang[i + j] = again * (fil_out - fmdc);
+            }
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) asm volatile("st.shared.f64 [%0], %1;" :: "r"(ang_s + 8u * (unsigned)(i + j)), "d"(o8[j]) : "memory");
     }
     for (; i < n; i++) {
         const double a_x = ang[i];
