@@ -285,7 +285,7 @@ int quisk_cuda_rx_read_trace(qcRxChain *rx, long long *host_out, int n_channels)
 
 typedef struct qcPanadapter qcPanadapter;
 
-/* fft_size: a power of two in [8, 32768] (pan_multirx: <= 8192), or ANY size in [8, 4096] (Quisk's own fft_size = data_width * fft_mult has
+/* fft_size: a power of two in [8, 32768] (pan_multirx: <= 8192), or ANY size in [8, 16384] (Quisk's own fft_size = data_width * fft_mult has
  * factors 3 ... 15, quisk.py:187-194, 4179): those run as a Bluestein convolution on the power-of-two transform, two
  * transforms per frame.  quisk_cuda_pan_multirx needs a power of two. */
 qcPanadapter *quisk_cuda_pan_create(int n_streams, int fft_size);

@@ -219,6 +219,81 @@ __global__ void __launch_bounds__(256) pan_accumulate_bluestein_kernel(const cd 
     for (int k = lane; k < n; k += lanes) dst[k] = sacc[k];
 }
 
+// Bluestein for frame sizes above 4096 that are not powers of two (data_width x fft_mult up to 16384): the convolution length
+// M = 16384 or 32768 no longer fits one CTA's shared memory, so the two M-point transforms run as SP = M / 4096 CTAs per
+// frame each -- a radix-SP decimation-in-frequency step on the way in, a 4096-point transform in shared memory -- with the
+// spectrum kept in its p-major order Z[p][k] = X[SP k + p] between them (the inverse consumes exactly that order):
+//   blue_big_fwd_kernel:  a = x window chirp (zero padded);  y_p[j] = (sum_q a[j + 4096 q] W_SP^{pq}) W_M^{pj};  Z[p] = FFT_4096(y_p) * B[SP k + p]
+//   blue_big_inv_kernel:  U[p][j] = conj(W_M^{pj}) * IFFT_4096(Z[p])[j]
+//   blue_big_acc_kernel:  c[j + 4096 q] = sum_p conj(W_SP^{pq}) U[p][j];  avg[k] += |c[b] chirp[b]| / M,  b = (k + n/2) mod n, frames in order
+// A correctness path like the small-size kernel above: three launches and a round trip through a scratch buffer per batch of frames.
+template <int SP>
+__global__ void __launch_bounds__(256) blue_big_fwd_kernel(const cd *frames, long stream_stride, int f0, int n, const cd *twM, const cd *tw4,
+                                                            const cd *chirpwin, const cd *B, cd *Z)
+{
+    extern __shared__ double smem_raw[];
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *s = twl + fft_tw_entries(4096);
+    fft_stage_twiddles(twl, tw4, 4096);
+    constexpr int M = SP * 4096;
+    const int p = blockIdx.x, f = blockIdx.y, stream = blockIdx.z, lane = threadIdx.x;
+    const cd *src = frames + (size_t)stream * stream_stride + (size_t)(f0 + f) * n;
+    for (int j = lane; j < 4096; j += 256) {
+        cd acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < SP; q++) {
+            const int idx = j + 4096 * q;
+            if (idx < n) {
+                const cd a = cmul(src[idx], chirpwin[idx]);
+                const cd w = twM[((p * q) & (SP - 1)) * 4096];              // W_SP^{pq}
+                acc = cadd(acc, cmul(a, w));
+            }
+        }
+        s[fsw(j)] = cmul(acc, twM[p * j]);
+    }
+    __syncthreads();
+    fft_smem<1>(s, 4096, twl, -1, lane, 256);
+    cd *z = Z + (((size_t)stream * gridDim.y + f) * SP + p) * 4096;
+    for (int k = lane; k < 4096; k += 256) z[k] = cmul(s[fsw(k)], B[SP * k + p]);
+    (void)M;
+}
+
+template <int SP>
+__global__ void __launch_bounds__(256) blue_big_inv_kernel(const cd *twM, const cd *tw4, cd *Z)
+{
+    extern __shared__ double smem_raw[];
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *s = twl + fft_tw_entries(4096);
+    fft_stage_twiddles(twl, tw4, 4096);
+    const int p = blockIdx.x, f = blockIdx.y, stream = blockIdx.z, lane = threadIdx.x;
+    cd *z = Z + (((size_t)stream * gridDim.y + f) * SP + p) * 4096;
+    for (int k = lane; k < 4096; k += 256) s[fsw(k)] = z[k];
+    __syncthreads();
+    fft_smem<1>(s, 4096, twl, +1, lane, 256);
+    for (int j = lane; j < 4096; j += 256) { cd w = twM[p * j]; w.y = -w.y; z[j] = cmul(s[fsw(j)], w); }
+}
+
+template <int SP>
+__global__ void __launch_bounds__(256) blue_big_acc_kernel(const cd *Z, int nfb, int n, const cd *twM, const cd *chirp, double *avg)
+{
+    const int stream = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int b = k + n / 2; if (b >= n) b -= n;
+    const int j = b & 4095, q = b >> 12;
+    const double inv_M = 1.0 / (double)(SP * 4096);
+    const cd ch = chirp[b];
+    double a = avg[(size_t)stream * n + k];
+    for (int f = 0; f < nfb; f++) {
+        const cd *u = Z + ((size_t)stream * nfb + f) * SP * 4096;
+        cd c = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int pp = 0; pp < SP; pp++) { cd w = twM[((pp * q) & (SP - 1)) * 4096]; w.y = -w.y; c = cadd(c, cmul(u[(size_t)pp * 4096 + j], w)); }
+        const cd X = cmul(c, ch);
+        a += sqrt(fma(X.x, X.x, X.y * X.y)) * inv_M;
+    }
+    avg[(size_t)stream * n + k] = a;
+}
+
 __global__ void pan_reduce_kernel(double *avg, const double *partial, int n, int groups)
 {
     const int stream = blockIdx.y;
@@ -318,13 +393,15 @@ struct Panadapter {
     int split8192 = 1;          // 8192-point frames: two 4096-point CTAs per frame (pan_accumulate_split_kernel)
     int M = 0;                  // > 0: Bluestein convolution length for a frame size that is not a power of two
     cd *d_chirpwin = nullptr, *d_chirp = nullptr, *d_B = nullptr;
+    const cd *tw4 = nullptr;    // M > 8192: the 4096-point table of the split transforms
+    cd *d_Z = nullptr; size_t z_cap = 0;
 
     int init(int streams, int fft_size)
     {
         S = streams; n = fft_size;
         const bool pow2 = fft_log2(n) >= 0 || n == 16384 || n == 32768;       // the two largest run split over 4 / 8 CTAs
-        if (S <= 0 || (!pow2 && (n < 8 || n > 4096))) {
-            set_error("pan_create: fft_size must be a power of two in [8, 32768] or any size in [8, 4096] (got %d)", fft_size); return QC_EINVAL;
+        if (S <= 0 || (!pow2 && (n < 8 || n > 16384))) {
+            set_error("pan_create: fft_size must be a power of two in [8, 32768] or any size in [8, 16384] (got %d)", fft_size); return QC_EINVAL;
         }
         if (!pow2) { M = 16; while (M < 2 * n - 1) M <<= 1; }
         tw = fft_twiddles(pow2 ? n : M);
@@ -352,16 +429,42 @@ struct Panadapter {
             QC_CUDA(cudaMemcpy(d_chirp, ch.data(), (size_t)n * sizeof(cd), cudaMemcpyHostToDevice));
             QC_CUDA(cudaMemcpy(d_chirpwin, cw.data(), (size_t)n * sizeof(cd), cudaMemcpyHostToDevice));
             QC_CUDA(cudaMemcpy(d_B, b.data(), (size_t)M * sizeof(cd), cudaMemcpyHostToDevice));
-            int rc = quisk_cuda_fft_batch(d_B, d_B, M, 1, -1, nullptr); if (rc != QC_OK) return rc;
-            QC_CUDA(cudaDeviceSynchronize());
+            if (M <= 8192) {
+                int rc = quisk_cuda_fft_batch(d_B, d_B, M, 1, -1, nullptr); if (rc != QC_OK) return rc;
+                QC_CUDA(cudaDeviceSynchronize());
+            } else {
+                // M = 16384 / 32768: the chirp's spectrum once, on the host (iterative radix 2 in long double)
+                std::vector<long double> re((size_t)M), im((size_t)M);
+                for (int i = 0, jr = 0; i < M; i++) {
+                    re[jr] = b[i].x; im[jr] = b[i].y;
+                    int bit = M >> 1;
+                    for (; jr & bit; bit >>= 1) jr ^= bit;
+                    jr ^= bit;
+                }
+                const long double PI_L = 3.141592653589793238462643383279502884L;
+                for (int len = 2; len <= M; len <<= 1) {
+                    for (int k = 0; k < len / 2; k++) {
+                        const long double a = -2.0L * PI_L * k / len, wr = cosl(a), wi = sinl(a);
+                        for (int i = k; i < M; i += len) {
+                            const int j2 = i + len / 2;
+                            const long double tr = re[j2] * wr - im[j2] * wi, ti = re[j2] * wi + im[j2] * wr;
+                            re[j2] = re[i] - tr; im[j2] = im[i] - ti; re[i] += tr; im[i] += ti;
+                        }
+                    }
+                }
+                for (int i = 0; i < M; i++) b[i] = make_double2((double)re[i], (double)im[i]);
+                QC_CUDA(cudaMemcpy(d_B, b.data(), (size_t)M * sizeof(cd), cudaMemcpyHostToDevice));
+                tw4 = fft_twiddles(4096);
+                if (!tw4) { set_error("pan_create: twiddle table allocation failed"); return QC_ENOMEM; }
+            }
         }
         return QC_OK;
     }
     void release()
     {
         if (d_window) cudaFree(d_window); if (d_avg) cudaFree(d_avg); if (d_partial) cudaFree(d_partial);
-        if (d_chirp) cudaFree(d_chirp); if (d_chirpwin) cudaFree(d_chirpwin); if (d_B) cudaFree(d_B);
-        d_window = d_avg = d_partial = nullptr; d_chirp = d_chirpwin = d_B = nullptr;
+        if (d_chirp) cudaFree(d_chirp); if (d_chirpwin) cudaFree(d_chirpwin); if (d_B) cudaFree(d_B); if (d_Z) cudaFree(d_Z);
+        d_window = d_avg = d_partial = nullptr; d_chirp = d_chirpwin = d_B = d_Z = nullptr; z_cap = 0;
     }
 };
 
@@ -421,6 +524,38 @@ int quisk_cuda_pan_accumulate(qcPanadapter *pp, const void *d_frames, long strea
     Panadapter &p = pp->p;
     if (n_frames <= 0) return QC_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (p.M > 8192) {
+        // Bluestein with a convolution length beyond one CTA: batches of frames through the three split kernels
+        const int SPm = p.M / 4096;
+        size_t per_frame = (size_t)p.S * p.M;
+        int nfb_cap = (int)(((size_t)256 << 20) / (per_frame * sizeof(cd)));
+        if (nfb_cap < 1) nfb_cap = 1;
+        if (nfb_cap > n_frames) nfb_cap = n_frames;
+        if (per_frame * nfb_cap > p.z_cap) {
+            if (p.d_Z) cudaFree(p.d_Z);
+            p.d_Z = nullptr; p.z_cap = 0;
+            QC_CUDA(cudaMalloc((void **)&p.d_Z, per_frame * nfb_cap * sizeof(cd)));
+            p.z_cap = per_frame * nfb_cap;
+        }
+        const size_t sh = ((size_t)4096 + fft_tw_entries(4096)) * sizeof(cd);
+        for (int f0 = 0; f0 < n_frames; f0 += nfb_cap) {
+            const int nfb = n_frames - f0 < nfb_cap ? n_frames - f0 : nfb_cap;
+            const dim3 grid(SPm, nfb, p.S);
+            int rc;
+#define BLUE_BIG(SP) do { \
+            rc = fft_smem_optin((const void *)blue_big_fwd_kernel<SP>, sh); if (rc != QC_OK) return rc; \
+            rc = fft_smem_optin((const void *)blue_big_inv_kernel<SP>, sh); if (rc != QC_OK) return rc; \
+            blue_big_fwd_kernel<SP><<<grid, 256, sh, s>>>((const cd *)d_frames, stream_stride, f0, p.n, p.tw, p.tw4, p.d_chirpwin, p.d_B, p.d_Z); \
+            blue_big_inv_kernel<SP><<<grid, 256, sh, s>>>(p.tw, p.tw4, p.d_Z); \
+            blue_big_acc_kernel<SP><<<dim3((p.n + 255) / 256, p.S), 256, 0, s>>>(p.d_Z, nfb, p.n, p.tw, p.d_chirp, p.d_avg); } while (0)
+            if (SPm == 4) BLUE_BIG(4); else BLUE_BIG(8);
+#undef BLUE_BIG
+            count_launch(); count_launch(); count_launch();
+            QC_CUDA_LAUNCH();
+        }
+        p.count += n_frames;
+        return QC_OK;
+    }
     // enough CTAs to fill the machine, but keep the reference's summation order when streams alone do
     // Frames of a stream are split over `groups` CTAs only when the streams alone cannot fill the machine, and then
     // so that ALL CTAs are resident at once (one wave): a grid a little larger than the number of slots costs a

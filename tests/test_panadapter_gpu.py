@@ -171,7 +171,37 @@ def test_panadapter_sizes_that_are_not_powers_of_two(n, torch, lib):
         ref_g = O.panadapter_pixels(ref_avg, count_fft, data_width, 1.0, 0.0, 48000.0)
         assert np.max(np.abs(g[s] - ref_g)) < 1e-8
     lib.quisk_cuda_pan_destroy(pan)
-    assert not lib.quisk_cuda_pan_create(2, 5000)            # beyond the Bluestein range and not a power of two
+    assert not lib.quisk_cuda_pan_create(2, 17000)           # beyond the Bluestein range and not a power of two
+
+
+@pytest.mark.parametrize("n,streams,count_fft", [(4800, 3, 3), (9600, 2, 5), (12000, 3, 2), (16384 - 2, 2, 2), (8193, 1, 3)])
+def test_panadapter_large_sizes_that_are_not_powers_of_two(n, streams, count_fft, torch, lib):
+    """Above 4096 points the Bluestein convolution (M = 16384 or 32768) runs as M / 4096 CTAs per frame and transform:
+    e.g. a 1200-pixel graph with fft_mult 8 (quisk.py:4179) is 9600 points."""
+    data_width = 1200 if n % 1200 == 0 else 1000
+    frames = np.stack([O.synth_iq(n * count_fft, 160 + s, 1.0).reshape(count_fft, n) for s in range(streams)])
+    d = torch.from_numpy(frames.reshape(streams, -1)).cuda()
+    pan = lib.quisk_cuda_pan_create(streams, n)
+    assert pan, lib.quisk_cuda_last_error()
+    # two calls: the running sum carries over
+    assert lib.quisk_cuda_pan_accumulate(pan, d.data_ptr(), n * count_fft, 1, None) == 0, lib.quisk_cuda_last_error()
+    assert lib.quisk_cuda_pan_accumulate(pan, d.data_ptr() + n * 16, n * count_fft, count_fft - 1, None) == 0, lib.quisk_cuda_last_error()
+    torch.cuda.synchronize()
+    assert lib.quisk_cuda_pan_count(pan) == count_fft
+    avg_ptr = lib.quisk_cuda_pan_average_ptr(pan)
+    avg = torch.empty((streams, n), dtype=torch.float64, device="cuda")
+    C.CDLL("libcudart.so.12").cudaMemcpy(C.c_void_p(avg.data_ptr()), C.c_void_p(avg_ptr), streams * n * 8, 3)
+    avg = avg.cpu().numpy()
+    g = torch.empty((streams, data_width), dtype=torch.float64, device="cuda")
+    assert lib.quisk_cuda_pan_graph(pan, data_width, 1.0, 0.0, 192000.0, g.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    g = g.cpu().numpy()
+    for s in range(streams):
+        ref_avg = O.panadapter_accumulate(frames[s])
+        assert O.rel_rms(avg[s], ref_avg) < 1e-12
+        ref_g = O.panadapter_pixels(ref_avg, count_fft, data_width, 1.0, 0.0, 192000.0)
+        assert np.max(np.abs(g[s] - ref_g)) < 1e-8
+    lib.quisk_cuda_pan_destroy(pan)
 
 
 @pytest.mark.parametrize("n,streams,count_fft", [(16384, 3, 3), (32768, 2, 2), (16384, 40, 1)])
