@@ -404,6 +404,9 @@ int quisk_cuda_pfb_prime(qcChannelizer *p, const void *d_in, int count, void *st
 #define QC_PFB_OPT_PIPELINE     3   /* 1: overlap the branch FIRs of slice i+1 with the transforms of slice i (two internal streams) */
 #define QC_PFB_OPT_FFT_PREFETCH 6   /* 1 (default): transform CTAs prefetch a later CTA's inputs into L2 */
 #define QC_PFB_OPT_RING         5   /* cp.async ring depth of the branch-FIR kernel in steps: 16 (default) or 32 */
+#define QC_PFB_OPT_FUSED        7   /* 1: 1024 channels, decim 512, 8 or 16 taps per branch run as ONE kernel (clusters of 8 CTAs, the branch-FIR
+                                       intermediate stays in distributed shared memory: 48 B of HBM traffic per sample instead of 112);
+                                       bit-identical, but measured slower (one CTA per SM, 15 clusters resident): default 0, the two-kernel path */
 #define QC_PFB_OPT_FFT_FRAMES   4   /* frames interleaved per transform CTA: 2 (default) or 4 */
 int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value);
 int quisk_cuda_pfb_process(qcChannelizer *p, const void *d_in, int count, void *d_out, long out_stride, int layout,

@@ -34,6 +34,8 @@
 // and the absolute sample index (frame phase and branch alignment both follow from it), so any block length works
 // and a time-block shard (shard.py) reproduces the sequential stream bit for bit after seek + prime.
 #include "fft_device.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace qc {
 
@@ -340,6 +342,203 @@ __global__ void __launch_bounds__(64 * PFI, 8 / PFI) pfb_fft_kernel(const cd *__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// (1b) D = K/2, K = 1024: branch FIRs and transforms in ONE kernel, u never leaves the chip.
+// A cluster of 8 CTAs x 128 branches covers the 1024 branches of a frame range; every CTA runs the register-resident branch
+// FIR of pfb_fir_kernel on its 128 branches and sends each finished value u_m[r] straight into the shared memory of the CTA
+// that will transform frame m (distributed shared memory): frames go in batches of 32, four consecutive frames per CTA, in the
+// interleaved layout pfb_fft_kernel's passes use.  One cluster barrier per batch says "all 1024 values of these 32 frames have
+// landed"; each CTA then runs its four 1024-point transforms (the 16 x 16 x 4 passes of pfb_fft_kernel, first pass in place)
+// and stores them.  Two receive buffers alternate; the one value per branch that a batch's closing step produces for the
+// batch after the next lands after the barrier (its buffer is only then known to be free).
+// HBM traffic per input sample: 16 B in + 32 B out (+ warm-up), against 112 B with u making its round trip.
+// MEASURED (B200, 16 Mi samples per call): 0.82 ms against 0.41 ms for the two-kernel path, so it is OFF by default
+// (QC_PFB_OPT_FUSED).  Where the time goes (QUISK_PFB_DBG switches parts off): branch FIRs alone 0.34 ms -- twice the
+// stand-alone FIR kernel, because 166 KB of shared memory leave one CTA = 8 warps per SM (the stand-alone kernel hides HBM
+// latency with 16) and only 15 clusters of 8 are resident (GPC boundaries): 120 of 148 SMs; the transforms add 0.30 ms
+// (same threads, nothing overlaps them), the remote stores 0.07 ms, the barriers 0.04 ms.  Beating two kernels that each
+// run at ~70 % of HBM bandwidth needs FIR and transform warps running side by side at full occupancy, not this form.
+// ------------------------------------------------------------------------------------------------------------
+struct PfbFusedParams {
+    const cd *in; int count;
+    const cd *hist; int H;
+    long long n0, f0; int nf, fs;
+    int D;
+    const double *taps; const cd *tw;
+    cd *out; long out_stride; int layout;
+    int dbg;                        // debug: 1 no sends, 2 no transforms, 4 no cluster barriers (results wrong; timing only)
+};
+static constexpr int PFU_BR = 128, PFU_CL = 8, PFU_K = 1024, PFU_PFI = 4;
+
+// four transforms of batch B, thread (b, f) = (tid / 4, tid % 4): pfb_fft_kernel<4, 4> with pass 1 reading the receive buffer
+__device__ __noinline__ void pfu_fft_batch(cd *sb, const cd *twl, const PfbFusedParams &p, int frame_first, int rb)
+{
+    constexpr int K = PFU_K, N1 = K / 16, PFI = PFU_PFI, R3 = 4;
+    const int tid = threadIdx.x, f = tid % PFI, b = tid / PFI;
+    const int fr = frame_first + f;
+    const bool live = fr < rb;
+    auto slot = [f](int i) { return PFI * (i ^ ((i >> 4) & (8 / PFI - 1))) + f; };
+    cd v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) v[j] = sb[slot(b + j * N1)];
+    dft16(v, -1.0);
+    __syncthreads();                                    // every thread holds its inputs: the buffer may be overwritten
+    if (b != 0) {
+        const cd w1 = fft_tw(twl, b, -1), w2 = fft_tw(twl, 2 * b, -1), w4 = fft_tw(twl, 4 * b, -1), w8 = fft_tw(twl, 8 * b, -1);
+        v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[4] = cmul(v[4], w4); v[8] = cmul(v[8], w8);
+        const cd w3 = cmul(w1, w2); v[3] = cmul(v[3], w3);
+        const cd w5 = cmul(w1, w4); v[5] = cmul(v[5], w5);
+        const cd w6 = cmul(w2, w4); v[6] = cmul(v[6], w6);
+        const cd w7 = cmul(w3, w4); v[7] = cmul(v[7], w7);
+        v[9] = cmul(v[9], cmul(w1, w8)); v[10] = cmul(v[10], cmul(w2, w8)); v[11] = cmul(v[11], cmul(w3, w8));
+        v[12] = cmul(v[12], cmul(w4, w8)); v[13] = cmul(v[13], cmul(w5, w8)); v[14] = cmul(v[14], cmul(w6, w8));
+        v[15] = cmul(v[15], cmul(w7, w8));
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) sb[slot(16 * b + k)] = v[k];
+    __syncthreads();
+    {
+        const int pp = b >> 4, q = b & 15;
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = sb[slot(q + 16 * (pp + R3 * j))];
+        dft16(v, -1.0);
+        if (pp != 0) {
+            const int pt = pp * 16;
+            const cd w1 = fft_tw(twl, pt, -1), w2 = fft_tw(twl, 2 * pt, -1), w4 = fft_tw(twl, 4 * pt, -1), w8 = fft_tw(twl, 8 * pt, -1);
+            v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[4] = cmul(v[4], w4); v[8] = cmul(v[8], w8);
+            const cd w3 = cmul(w1, w2); v[3] = cmul(v[3], w3);
+            const cd w5 = cmul(w1, w4); v[5] = cmul(v[5], w5);
+            const cd w6 = cmul(w2, w4); v[6] = cmul(v[6], w6);
+            const cd w7 = cmul(w3, w4); v[7] = cmul(v[7], w7);
+            v[9] = cmul(v[9], cmul(w1, w8)); v[10] = cmul(v[10], cmul(w2, w8)); v[11] = cmul(v[11], cmul(w3, w8));
+            v[12] = cmul(v[12], cmul(w4, w8)); v[13] = cmul(v[13], cmul(w5, w8)); v[14] = cmul(v[14], cmul(w6, w8));
+            v[15] = cmul(v[15], cmul(w7, w8));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; k++) sb[slot(q + 256 * pp + 16 * k)] = v[k];
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 16 / R3; t++) {
+            const int bb = b + N1 * t;
+#pragma unroll
+            for (int j = 0; j < R3; j++) v[t * R3 + j] = sb[slot(bb + 256 * j)];
+            bfly4(v[t * 4], v[t * 4 + 1], v[t * 4 + 2], v[t * 4 + 3], -1.0, v[t * 4], v[t * 4 + 1], v[t * 4 + 2], v[t * 4 + 3]);
+        }
+    }
+    __syncthreads();                                    // the buffer is free for the batch after the next
+    if (!live) return;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int ch = b + N1 * (e / R3) + 256 * (e % R3);
+        if (p.layout == 0) p.out[(size_t)ch * p.out_stride + fr] = v[e];
+        else p.out[(size_t)fr * p.out_stride + ch] = v[e];
+    }
+}
+
+template <int P, int RING>
+__global__ void __cluster_dims__(PFU_CL, 1, 1) __launch_bounds__(256, 1) pfb_fused_kernel(PfbFusedParams p)
+{
+    constexpr int K = PFU_K, PH = P / 2, PFI = PFU_PFI;
+    extern __shared__ double smem_raw[];
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *rbuf = twl + fft_tw_entries(K);                             // [2][K * PFI] receive buffers
+    cd (*ring)[PFU_BR] = reinterpret_cast<cd (*)[PFU_BR]>(rbuf + 2 * K * PFI);
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, half = lane >> 4;
+    const int rl = (tid >> 5) * 16 + (lane & 15);
+    const int r = rank * PFU_BR + rl;
+    const int D = p.D;
+    const int ra = (int)(blockIdx.x / PFU_CL) * p.fs;               // this cluster's frames [ra, rb) of the launch
+    const int rb = min(ra + p.fs, p.nf);
+    if (ra >= rb) return;                                           // the whole cluster
+    fft_stage_twiddles(twl, p.tw, K);
+    const int tau = (2 * D - 1 - r) % D;
+    double lo[PH], hi[PH];
+#pragma unroll
+    for (int a = 0; a < PH; a++) {
+        lo[a] = p.taps[tau + K * (half * PH + a)];
+        hi[a] = p.taps[tau + D + K * (half * PH + a)];
+    }
+    const long long fa = p.f0 + ra, fb = p.f0 + rb;
+    const long long a_lo = (fa >> 1) - 1, a_hi = (fb - 1) >> 1;
+    const int steps = (int)(a_hi - a_lo + 1);
+    const int mrel0 = (int)(2 * a_lo - p.f0) + (r >= D ? 1 : 0);
+    const int rel = (int)(a_lo * K + r - p.n0);
+    const cd *in = p.in, *he = p.hist + p.H;
+    cd w[PH];
+#pragma unroll
+    for (int q = 1; q < PH; q++) w[PH - q] = pfb_load(in, he, rel - (q + half * PH) * K, p.count, p.H);
+    w[0] = pfb_load(in, he, rel - (PH + half * PH) * K, p.count, p.H);
+    auto issue = [&](int step) {
+        if (!half) {
+            const int e = rel + step * K;
+            const cd *src = in; unsigned bytes = 0;
+            if (step < steps) {
+                if (e >= 0) { if (e < p.count) { src = in + e; bytes = 16; } }
+                else if (e >= -p.H) { src = he + e; bytes = 16; }
+            }
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&ring[step & (RING - 1)][rl]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll 1
+    for (int j = 0; j < RING - 2; j++) issue(j);
+    const int slot_r = PFI * (r ^ ((r >> 4) & (8 / PFI - 1)));
+    // value of launch-relative frame m (inside [ra, rb)) to the CTA that transforms it
+    auto send = [&](cd val, int mm) {
+        const int fbat = mm & 31;
+        cd *dst = cluster.map_shared_rank(rbuf, fbat >> 2) + (size_t)((mm >> 5) & 1) * K * PFI + slot_r + (fbat & 3);
+        *dst = val;
+    };
+    const int trig0 = 16 + (int)(fa & 1);                           // the step that completes batch 0; batch B: trig0 + 16 B
+    const int nbatch = (rb - ra + 31) >> 5;
+    int next_b = 0;
+    cluster.sync();                                                 // every CTA of the cluster is running: its shared memory may be written
+    for (int i = 0; i < steps; i += PH) {
+#pragma unroll
+        for (int j = 0; j < PH; j++) {
+            if (i + j < steps) {
+                const cd old = w[j];
+                const double ox = __shfl_sync(0xffffffffu, old.x, lane & 15), oy = __shfl_sync(0xffffffffu, old.y, lane & 15);
+                issue(i + j + RING - 2);
+                asm volatile("cp.async.wait_group %0;" ::"n"(RING - 2) : "memory");
+                w[j] = half ? make_double2(ox, oy) : ring[(i + j) & (RING - 1)][rl];
+                double xr = 0.0, xi = 0.0, yr = 0.0, yi = 0.0;
+#pragma unroll
+                for (int t = 0; t < PH; t++) {
+                    const cd x = w[(j - t + PH) % PH];
+                    xr = fma(x.x, lo[t], xr); xi = fma(x.y, lo[t], xi);
+                    yr = fma(x.x, hi[t], yr); yi = fma(x.y, hi[t], yi);
+                }
+                const double sr = half ? xr : yr, si = half ? xi : yi;
+                const double pr = __shfl_xor_sync(0xffffffffu, sr, 16), pi = __shfl_xor_sync(0xffffffffu, si, 16);
+                const int m = mrel0 + 2 * (i + j) + half;
+                const cd val = half ? make_double2(yr + pr, yi + pi) : make_double2(xr + pr, xi + pi);
+                const int mm = m - ra;
+                const bool inside = m >= ra && m < rb;
+                const bool trig = (i + j) == trig0 + 16 * next_b;           // uniform over the cluster
+                const bool later = inside && trig && (mm >> 5) > next_b;    // lands in the buffer of the batch transformed two rounds ago
+                if (inside && !later && !(p.dbg & 1)) send(val, mm);
+                if (trig) {
+                    if (!(p.dbg & 4)) cluster.sync();
+                    if (later && !(p.dbg & 1)) send(val, mm);
+                    if (!(p.dbg & 2)) pfu_fft_batch(rbuf + (size_t)(next_b & 1) * K * PFI, twl, p, ra + 32 * next_b + 4 * rank, rb);
+                    next_b++;
+                }
+            }
+        }
+    }
+    while (next_b < nbatch) {
+        cluster.sync();
+        pfu_fft_batch(rbuf + (size_t)(next_b & 1) * K * PFI, twl, p, ra + 32 * next_b + 4 * rank, rb);
+        next_b++;
+    }
+    cluster.sync();                                                 // nobody leaves while a neighbour may still write into it
+}
+
 struct Channelizer {
     int K = 0, D = 0, T = 0, P = 0, smax = 0;
     double *d_taps = nullptr;
@@ -355,6 +554,9 @@ struct Channelizer {
     int fft_frames = 2;             // frames interleaved per transform CTA (2: four CTAs per SM, measured 5 % faster; 4: 64-byte output runs)
     cd *d_u = nullptr; int u_frames = 0, u_bufs = 0;        // one slice of u (two back to back when pipelining)
     int pipeline = 0;               // 1: branch FIRs of slice i+1 overlap the transforms of slice i on two internal streams
+    int max_clusters = 0;           // resident clusters of the fused kernel (queried once)
+    int fused = 0;                  // 1: K = 1024, D = 512, 8 or 16 taps per branch run the one-kernel cluster path (pfb_fused_kernel);
+                                    // measured SLOWER than the two-kernel path (0.82 vs 0.41 ms per 16 Mi samples), see the kernel's header
     cudaStream_t sa = nullptr, sb = nullptr;
     cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_fft[2] = {nullptr, nullptr}, ev_edge = nullptr;
 
@@ -378,6 +580,7 @@ struct Channelizer {
         }
         int dev = 0; cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (const char *e = getenv("QUISK_PFB_FUSED")) fused = atoi(e) ? 1 : 0;     // debug override of QC_PFB_OPT_FUSED
         return QC_OK;
     }
     void release()
@@ -437,6 +640,49 @@ struct Channelizer {
     {
         if (ring == 32) pfb_fir_kernel<PP, OVS, 32><<<grid, 128, 0, s>>>(q);
         else pfb_fir_kernel<PP, OVS, 16><<<grid, 128, 0, s>>>(q);
+        return QC_OK;
+    }
+    // K = 1024, D = 512: one kernel, clusters of 8 CTAs per frame range
+    template <int PP> int launch_fused(const PfbFusedParams &q, int clusters, size_t sh, cudaStream_t s)
+    {
+        QC_CUDA(cudaFuncSetAttribute(pfb_fused_kernel<PP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        pfb_fused_kernel<PP, 16><<<clusters * PFU_CL, 256, sh, s>>>(q);
+        return QC_OK;
+    }
+    int process_fused(const cd *d_in, int count, cd *d_out, long out_stride, int layout, int nf, cudaStream_t s)
+    {
+        PfbFusedParams q;
+        q.in = d_in; q.count = count; q.hist = d_hist[cur]; q.H = T; q.n0 = n_abs; q.f0 = n_abs / D; q.nf = nf;
+        q.D = D; q.taps = d_taps; q.tw = tw; q.out = d_out; q.out_stride = out_stride; q.layout = layout;
+        q.dbg = getenv("QUISK_PFB_DBG") ? atoi(getenv("QUISK_PFB_DBG")) : 0;
+        const size_t sh0 = ((size_t)fft_tw_entries(K) + 2 * (size_t)K * PFU_PFI + (size_t)16 * PFU_BR) * sizeof(cd);
+        if (max_clusters == 0) {
+            // how many clusters the device holds at once (GPC boundaries decide, not the SM count)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(PFU_CL * 64); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = sh0;
+            cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = PFU_CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            int nc = 0;
+            if (P == 16) { cudaFuncSetAttribute(pfb_fused_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh0); cudaOccupancyMaxActiveClusters(&nc, pfb_fused_kernel<16, 16>, &cfg); }
+            else { cudaFuncSetAttribute(pfb_fused_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh0); cudaOccupancyMaxActiveClusters(&nc, pfb_fused_kernel<8, 16>, &cfg); }
+            cudaGetLastError();
+            max_clusters = nc > 0 ? nc : n_sm / PFU_CL;
+            if (getenv("QUISK_PFB_DBG")) fprintf(stderr, "pfb fused: %d clusters of %d CTAs resident\n", max_clusters, PFU_CL);
+        }
+        // frame ranges: a whole number of waves of resident clusters, at least 256 frames each
+        int waves = getenv("QUISK_PFB_WAVES") ? atoi(getenv("QUISK_PFB_WAVES")) : 2;
+        int S = waves * max_clusters;
+        if (S > (nf + 255) / 256) S = (nf + 255) / 256;
+        if (S < 1) S = 1;
+        int fs = (nf + S - 1) / S;
+        fs += fs & 1;
+        q.fs = fs;
+        S = (nf + fs - 1) / fs;
+        const size_t sh = ((size_t)fft_tw_entries(K) + 2 * (size_t)K * PFU_PFI + (size_t)16 * PFU_BR) * sizeof(cd);
+        int rc = P == 16 ? launch_fused<16>(q, S, sh, s) : launch_fused<8>(q, S, sh, s);
+        if (rc != QC_OK) return rc;
+        count_launch();
+        QC_CUDA_LAUNCH();
         return QC_OK;
     }
     // D = K or K/2: slices of (register FIR kernel, transform kernel)
@@ -524,7 +770,10 @@ struct Channelizer {
         if (n_frames) *n_frames = nf;
         if (count == 0) return QC_OK;
         if (nf > 0 && (layout == 0 ? out_stride < nf : out_stride < K)) { set_error("pfb_process: out_stride %ld too small", out_stride); return QC_EINVAL; }
-        if (nf > 0 && !force_generic && (D == K || 2 * D == K)) {
+        if (nf > 0 && !force_generic && fused && K == PFU_K && 2 * D == K && (P == 16 || P == 8)) {
+            int rc = process_fused(d_in, count, d_out, out_stride, layout, nf, s);
+            if (rc != QC_OK) return rc;
+        } else if (nf > 0 && !force_generic && (D == K || 2 * D == K)) {
             int rc = process_fast(d_in, count, d_out, out_stride, layout, nf, s);
             if (rc != QC_OK) return rc;
         } else if (nf > 0) {
@@ -581,6 +830,7 @@ int quisk_cuda_pfb_set_option(qcChannelizer *p, int option, int value)
     case QC_PFB_OPT_FFT_PREFETCH: p->c.fft_prefetch = value ? 1 : 0; return QC_OK;
     case QC_PFB_OPT_RING: if (value != 16 && value != 32) return QC_EINVAL; p->c.ring = value; return QC_OK;
     case QC_PFB_OPT_FFT_FRAMES: if (value != 2 && value != 4) return QC_EINVAL; p->c.fft_frames = value; return QC_OK;
+    case QC_PFB_OPT_FUSED: p->c.fused = value ? 1 : 0; return QC_OK;
     }
     qc::set_error("pfb_set_option: unknown option %d", option);
     return QC_EINVAL;

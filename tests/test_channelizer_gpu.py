@@ -85,6 +85,29 @@ def test_channelizer_block_split_invariance(layout, torch):
     ch.close()
 
 
+@pytest.mark.parametrize("P,start", [(16, 0), (16, 7 * 512), (8, 3 * 512 + 100)])
+def test_channelizer_one_kernel_cluster_path_equals_two_kernel_path(P, start, torch):
+    """QC_PFB_OPT_FUSED (option 7): branch FIRs and transforms in one kernel, clusters of 8 CTAs exchanging u through
+    distributed shared memory.  Same arithmetic as the two-kernel path: identical bits, from an even or an odd first
+    frame, over several frame ranges and ragged blocks."""
+    from quisk_b200.rx import Channelizer
+    K, D = 1024, 512
+    h = proto_taps(K, P)
+    n = 700 * D + 333
+    x = O.synth_iq(n, 35, 1.0)
+    splits = [300 * D + 5, 1, 0, 33 * D - 7]
+    splits.append(n - sum(splits))
+    ys = []
+    for fused in (0, 1):
+        ch = Channelizer(K, D, h)
+        ch.set_option(7, fused)
+        ch.seek(start)
+        ys.append(run(torch, ch, x, splits))
+        ch.close()
+    assert ys[0].shape[1] == (start + n) // D - start // D
+    assert np.array_equal(ys[0], ys[1])
+
+
 def test_channelizer_time_block_shard(torch):
     """A shard that starts mid-stream after seek(t - halo) + prime(halo) reproduces the sequential frames exactly
     (halo = n_taps rounded up to the decimation, block starts multiples of it)."""
