@@ -317,6 +317,21 @@ void quisk_cuda_bandscope_destroy(qcBandscope *b);
 int quisk_cuda_bandscope_accumulate(qcBandscope *b, const double *d_blocks, long stream_stride, int n_blocks, void *stream);
 int quisk_cuda_bandscope_graph(qcBandscope *b, int graph_width, int clock, double zoom, double deltaf, double *d_graph, void *stream);
 
+/* ---- 3b'. Waterfall pixel mapper behind the panadapter (quisk.c:5334-5480), batched over n_streams ----
+ * create          = watfall_RgbData (quisk.c:5334-5371): three 256-entry palettes, a ring of max_height zeroed rows of `width` pixels.
+ * on_graph_data   = watfall_OnGraphData (quisk.c:5373-5420): the ring steps back one row; d_db [n_streams][db_stride] holds n_db dB
+ *                   values per stream (quisk_cuda_pan_graph's output, on the device); colour index
+ *                   (int)((dB - gain + 40.0 + y_zero * 0.69) * (y_scale + 10) * 0.10 + 128) clamped to 0..255; zero fill past n_db.
+ * get_pixels      = watfall_GetPixels (quisk.c:5439-5480): `height` lines of width * 3 bytes per stream into
+ *                   d_pixels + stream * stream_stride_bytes, newest first, every row shifted by its own x_origin against the one asked
+ *                   for; scroll_mode (the reference's config value waterfall_scroll_mode, default 1) draws the newest seven rows
+ *                   8, 7, ... 2 times first (35 lines: height must be >= 35 then).  Byte-exact against the reference's methods. */
+typedef struct qcWaterfall qcWaterfall;
+qcWaterfall *quisk_cuda_waterfall_create(int n_streams, int width, int max_height, const unsigned char *red, const unsigned char *green, const unsigned char *blue);
+void quisk_cuda_waterfall_destroy(qcWaterfall *w);
+int quisk_cuda_waterfall_on_graph_data(qcWaterfall *w, const double *d_db, long db_stride, int n_db, int y_zero, int y_scale, double gain, int x_origin, void *stream);
+int quisk_cuda_waterfall_get_pixels(qcWaterfall *w, unsigned char *d_pixels, long stream_stride_bytes, int x_origin, int height, int scroll_mode, void *stream);
+
 /* ------------------------------------------------------------------------
  * 3c. process_agc (quisk.c:2162-2287) and cFracDecim (quisk.c:622-665), batched
  * --------------------------------------------------------------------- */

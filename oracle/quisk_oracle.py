@@ -860,3 +860,49 @@ def unpack_hermes(packet, n_rx: int) -> np.ndarray:
             n += 1
             index += 2
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Waterfall pixel mapper (quisk.c:5334-5480) -- TEST INFRASTRUCTURE like the rest of this file
+# ---------------------------------------------------------------------------------------------------------------
+class WaterfallOracle:
+    """watfall_RgbData / watfall_OnGraphData / watfall_GetPixels restated with an index ring instead of the linked list."""
+
+    def __init__(self, red, green, blue, width, max_height):            # quisk.c:5334-5371
+        self.pal = np.stack([np.asarray(red, np.uint8), np.asarray(green, np.uint8), np.asarray(blue, np.uint8)], axis=1)
+        self.width, self.H, self.cur = width, max_height, 0
+        self.rows = np.zeros((max_height, width, 3), dtype=np.uint8)
+        self.xo = np.zeros(max_height, dtype=np.int64)
+
+    def on_graph_data(self, db, y_zero, y_scale, gain, x_origin):        # quisk.c:5373-5420
+        self.cur = (self.cur - 1) % self.H                               # current_row = current_row->prior_row
+        self.xo[self.cur] = x_origin
+        db = np.asarray(db, dtype=np.float64)[:self.width]
+        yz = 40.0 + y_zero * 0.69
+        t = (db - gain + yz) * float(y_scale + 10) * 0.10 + 128          # numpy rounds every operation separately, like the C code
+        l = np.clip(np.trunc(t), 0, 255).astype(np.int64)                # (int) truncates toward zero
+        row = self.rows[self.cur]
+        row[:] = 0
+        row[:len(db)] = self.pal[l]
+
+    def get_pixels(self, x_origin, height, scroll_mode=1):               # quisk.c:5439-5480
+        order = []
+        k = 0
+        if scroll_mode:
+            for j in range(8, 1, -1):
+                order += [k] * j
+                k += 1
+                height -= j
+        order += list(range(k, k + max(height, 0)))
+        out = np.zeros((len(order), self.width, 3), dtype=np.uint8)
+        for ro, kk in enumerate(order):
+            r = (self.cur + kk) % self.H
+            dx = int(self.xo[r] - x_origin)                              # watfall_copy, quisk.c:5422-5437
+            if dx == 0:
+                out[ro] = self.rows[r]
+            elif abs(dx) < self.width:
+                if dx > 0:
+                    out[ro, dx:] = self.rows[r, :self.width - dx]
+                else:
+                    out[ro, :self.width + dx] = self.rows[r, -dx:]
+        return out.reshape(-1)

@@ -81,6 +81,11 @@ def load() -> C.CDLL:
     lib.quisk_cuda_pan_create.argtypes = [C.c_int, C.c_int]
     lib.quisk_cuda_fp64_peak.argtypes = [C.POINTER(C.c_double)]
     lib.quisk_cuda_pan_create.restype = vp
+    lib.quisk_cuda_waterfall_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.quisk_cuda_waterfall_create.restype = vp
+    lib.quisk_cuda_waterfall_destroy.argtypes = [vp]; lib.quisk_cuda_waterfall_destroy.restype = None
+    lib.quisk_cuda_waterfall_on_graph_data.argtypes = [vp, vp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp]
+    lib.quisk_cuda_waterfall_get_pixels.argtypes = [vp, vp, C.c_long, C.c_int, C.c_int, C.c_int, vp]
     lib.quisk_cuda_pan_destroy.argtypes = [vp]
     lib.quisk_cuda_pan_destroy.restype = None
     lib.quisk_cuda_pan_accumulate.argtypes = [vp, vp, C.c_long, C.c_int, vp]
