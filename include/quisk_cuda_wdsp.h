@@ -84,6 +84,7 @@ qcSeqStage *quisk_cuda_shift_create(int n_channels, int rate, const double *shif
 /* xwcpagc (wdsp/wcpAGC.c:161-348) with create_rxa's parameters (RXA.c:337-360) and the preset of
  * SetRXAAGCMode(mode) (wcpAGC.c:370-411); mode 0 = fixed gain. */
 qcSeqStage *quisk_cuda_wcpagc_create(int n_channels, int rate, int mode);
+qcSeqStage *quisk_cuda_wcpagc_create_fmlim(int n_channels, int rate, double lim_gain);   /* fmd's detector limiter: create_wcpagc as calc_fmd calls it (fmd.c:49-73) */
 int quisk_cuda_wcpagc_set_fixed_gain_db(qcSeqStage *s, double gain_db);     /* SetRXAAGCFixed */
 int quisk_cuda_wcpagc_set_top_db(qcSeqStage *s, double max_gain_db);        /* SetRXAAGCTop */
 /* xamd (wdsp/amd.c:115-239): mode 0 AM envelope, 1 synchronous AM; sbmode 0/1/2; create_rxa's constants. */
@@ -131,6 +132,8 @@ int quisk_cuda_rxa_nbp_delete_notch(qcRxa *rxa, int notch);
 int quisk_cuda_rxa_nbp_set_notches_run(qcRxa *rxa, int run);
 int quisk_cuda_rxa_nbp_set_tune_frequency(qcRxa *rxa, double tunefreq);
 int quisk_cuda_rxa_nbp_set_shift_frequency(qcRxa *rxa, double shift);
+int quisk_cuda_rxa_set_fm_lim_run(qcRxa *rxa, int run);                      /* SetRXAFMLimRun,  fmd.c:337-348: the FM detector limiter (a wcpAGC, fmd.c:49-73) */
+int quisk_cuda_rxa_set_fm_lim_gain(qcRxa *rxa, double gain_db);              /* SetRXAFMLimGain, fmd.c:350-363 */
 int quisk_cuda_rxa_set_mp(qcRxa *rxa, int mp);                               /* RXASetMP, RXA.c:949-958           */
 int quisk_cuda_rxa_set_panel_gain(qcRxa *r, double gain1);                  /* SetRXAPanelGain1                  */
 int quisk_cuda_rxa_in_size(const qcRxa *r);      /* dsp_insize: samples per channel consumed per xrxa  */
@@ -200,6 +203,8 @@ void SetRXAAMDFadeLevel(int channel, int levelfade);
 double GetRXAMeter(int channel, int mt);
 void RXAGetaSipF(int channel, float *out, int size);
 void RXAGetaSipF1(int channel, float *out, int size);
+void SetRXAFMLimRun(int channel, int run);
+void SetRXAFMLimGain(int channel, double gaindB);
 void SetRXAAMSQRun(int channel, int run);
 void SetRXAFMSQRun(int channel, int run);
 void SetRXAEMNRRun(int channel, int run);

@@ -150,6 +150,8 @@ void RXANBPSetTuneFrequency(int channel, double tunefreq) { CH("RXANBPSetTuneFre
 void RXANBPSetShiftFrequency(int channel, double shift) { CH("RXANBPSetShiftFrequency") return; quisk_cuda_rxa_nbp_set_shift_frequency(as_handle(r), shift); }
 void SetRXAAGCMode(int channel, int mode) { CH("SetRXAAGCMode") return; quisk_cuda_rxa_set_agc_mode(as_handle(r), mode); }
 void SetRXAAGCFixed(int channel, double fixed_agc) { CH("SetRXAAGCFixed") return; quisk_cuda_rxa_set_agc_fixed(as_handle(r), fixed_agc); }
+void SetRXAFMLimRun(int channel, int run) { CH("SetRXAFMLimRun") return; quisk_cuda_rxa_set_fm_lim_run(as_handle(r), run); }
+void SetRXAFMLimGain(int channel, double gaindB) { CH("SetRXAFMLimGain") return; quisk_cuda_rxa_set_fm_lim_gain(as_handle(r), gaindB); }
 void SetRXAAGCTop(int channel, double max_agc) { CH("SetRXAAGCTop") return; r->agc->agc.max_gain = pow(10.0, max_agc / 20.0); r->agc->load_agc(); }
 void SetRXAPanelRun(int channel, int run) { CH("SetRXAPanelRun") return; (void)run; }      // xpanel never looks at its run flag
 void SetRXAPanelGain1(int channel, double gain) { CH("SetRXAPanelGain1") return; r->panel_gain1 = gain; }

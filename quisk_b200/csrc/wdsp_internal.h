@@ -77,6 +77,7 @@ __device__ __forceinline__ double mlog10_dev(const double *__restrict__ mtable, 
 
 SeqStage *make_shift(int C, int rate, const double *shift_hz);
 SeqStage *make_wcpagc(int C, int rate, int mode);
+SeqStage *make_wcpagc_fmlim(int C, int rate, double lim_gain);      // fmd's detector limiter (fmd.c:49-73)
 SeqStage *make_amd(int C, int rate, int mode, int levelfade, int sbmode);
 SeqStage *make_fmpll(int C, int rate, double deviation, double fmin, double fmax, double zeta, double omegaN, double tau);
 SeqStage *make_snotch(int C, int rate, double f, double bw);
@@ -101,6 +102,8 @@ struct Rxa {
     // amd / fmd
     int amd_run = 0, amd_mode = 0; SeqStage *amd = nullptr;
     int fmd_run = 0, fm_nc_de = 0, fm_nc_aud = 0; SeqStage *fmpll = nullptr, *sntch = nullptr; FirCore *pde = nullptr, *paud = nullptr;
+    int lim_run = 0; double lim_pre_gain = 0.4, lim_gain = 2.5; SeqStage *plim = nullptr;     // fmd's detector limiter (fmd.c:106-108, 179-184)
+    int fm_limiter(cd *m, long ms, int n, cudaStream_t s);
     // bp1
     int bp1_run = 1, bp1_nc = 0; double bp1_flow = -4150.0, bp1_fhigh = -150.0, bp1_gain = 1.0; FirCore *bp1 = nullptr;
     // agc, panel

@@ -157,6 +157,8 @@ int Rxa::init(int C_, int in_size_, int dsp_size_, int in_rate_, int dsp_rate_, 
     amd = make_amd(C, dsp_rate, 0, 1, 0);
     fmpll = make_fmpll(C, dsp_rate, 5000.0, -8000.0, +8000.0, 1.0, 20000.0, 0.02);
     sntch = make_snotch(C, dsp_rate, 254.1, 0.0002);
+    plim = make_wcpagc_fmlim(C, dsp_rate, lim_gain);
+    if (!plim) return QC_EINVAL;
     if ((rc = make_fmd()) != QC_OK) return rc;
     agc = make_wcpagc(C, dsp_rate, 3);
     if (!shift || !adcmeter || !smeter || !agcmeter || !amd || !fmpll || !sntch || !agc) return QC_EINVAL;
@@ -178,7 +180,7 @@ static int raise_upflag(Rxa &r)
 
 void Rxa::release()
 {
-    for (SeqStage **p : {&shift, &adcmeter, &smeter, &agcmeter, &amd, &fmpll, &sntch, &agc}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
+    for (SeqStage **p : {&shift, &adcmeter, &smeter, &agcmeter, &amd, &fmpll, &sntch, &agc, &plim}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     for (FirCore **p : {&nbp0, &bp1, &pde, &paud}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     for (Resampler **p : {&rsmpin, &rsmpout}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     if (mid) cudaFree(mid); if (mid2) cudaFree(mid2); if (audio) cudaFree(audio);
@@ -197,6 +199,13 @@ void Rxa::release()
     if (d_sip) cudaFree(d_sip); if (d_sipout) cudaFree(d_sipout);
     d_sip = nullptr; d_sipout = nullptr; sipout_cap = 0;
     mid = mid2 = audio = nullptr;
+}
+
+int Rxa::fm_limiter(cd *m, long ms, int n, cudaStream_t s)
+{   // fmd.c:179-184: out *= lim_pre_gain, then the detector limiter (a wcpAGC with calc_fmd's constants) in place
+    if (!lim_run) return QC_OK;
+    int rc = launch_panel(m, ms, m, ms, n, C, lim_pre_gain, lim_pre_gain, 3, 0, s); if (rc) return rc;
+    return plim->run(m, ms, m, ms, n, s);
 }
 
 int Rxa::xrxa_multi(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s)
@@ -268,6 +277,7 @@ int Rxa::xrxa_stages_wide(const void *din, long is, void *dout, long os, int g, 
         rc = fircore_wide(pde, waudio, ws, m, ws, g, d_wide_spec, s); if (rc) return rc;
         rc = fircore_wide(paud, m, ws, m, ws, g, d_wide_spec, s); if (rc) return rc;
         rc = sntch->run(m, ws, m, ws, n, s); if (rc) return rc;
+        rc = fm_limiter(m, ws, n, s); if (rc) return rc;
         QC_CUDA(cudaStreamWaitEvent(s, ev_d, 0));                                       // and the S meter wmid2, before the next group's filter writes it
     } else {
     rc = adcmeter->run(cur, cs, nullptr, 0, n, s);
@@ -280,6 +290,7 @@ int Rxa::xrxa_stages_wide(const void *din, long is, void *dout, long os, int g, 
         if (rc == QC_OK) rc = fircore_wide(pde, waudio, ws, m, ws, g, d_wide_spec, s);  // de-emphasis
         if (rc == QC_OK) rc = fircore_wide(paud, m, ws, m, ws, g, d_wide_spec, s);      // audio filter, in place
         if (rc == QC_OK) rc = sntch->run(m, ws, m, ws, n, s);                           // CTCSS notch (I rail)
+        if (rc == QC_OK) rc = fm_limiter(m, ws, n, s);
     }
     }
     if (rc == QC_OK && bp1_run) rc = fircore_wide(bp1, m, ws, m, ws, g, d_wide_spec, s);
@@ -341,6 +352,7 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
         rc = pde->run(audio, dsp_size, m, ms, s); if (rc) return rc;                   // de-emphasis: audio -> out
         rc = paud->run(m, ms, m, ms, s); if (rc) return rc;                            // audio filter, in place
         rc = sntch->run(m, ms, m, ms, dsp_size, s); if (rc) return rc;                 // CTCSS notch (I rail)
+        rc = fm_limiter(m, ms, dsp_size, s); if (rc) return rc;
     }
     if (bp1_run) { rc = bp1->run(m, ms, m, ms, s); if (rc) return rc; }
     // out of place into the second scratch buffer (free by now): the AGC kernel then needs no sample staging
@@ -422,7 +434,7 @@ int Rxa::flush_main()
     QC_CUDA(cudaDeviceSynchronize());
     QC_CUDA(cudaMemset(d_outbuff, 0, (size_t)C * dsp_outsize * sizeof(cd)));
     int rc;
-    for (SeqStage *q : {shift, adcmeter, smeter, amd, fmpll, sntch, agc, agcmeter}) if (q) { rc = q->flush_ref(); if (rc) return rc; }
+    for (SeqStage *q : {shift, adcmeter, smeter, amd, fmpll, sntch, plim, agc, agcmeter}) if (q) { rc = q->flush_ref(); if (rc) return rc; }
     for (FirCore *f : {nbp0, pde, paud, bp1}) if (f) { rc = f->flush(); if (rc) return rc; }
     for (Resampler *q : {rsmpin, rsmpout}) if (q) { rc = q->f->reset(nullptr); if (rc) return rc; }
     QC_CUDA(cudaMemset(d_sip, 0, (size_t)C * sipsize * sizeof(cd)));
@@ -620,6 +632,21 @@ int quisk_cuda_rxa_set_nc(qcRxa *p, int nc)
     return QC_OK;
 }
 
+int quisk_cuda_rxa_set_fm_lim_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.lim_run = run ? 1 : 0; return QC_OK; }      /* SetRXAFMLimRun, fmd.c:337-348 */
+int quisk_cuda_rxa_set_fm_lim_gain(qcRxa *p, double gain_db)
+{   /* SetRXAFMLimGain, fmd.c:350-363: decalc_fmd / calc_fmd rebuild the limiter (and the notch) from scratch */
+    if (!p) return QC_EINVAL;
+    qc::Rxa &r = p->r;
+    const double g = pow(10.0, gain_db / 20.0);
+    if (g == r.lim_gain) return QC_OK;
+    if (cudaDeviceSynchronize() != cudaSuccess) return QC_ECUDA;
+    qc::SeqStage *nl = qc::make_wcpagc_fmlim(r.C, r.dsp_rate, g);
+    if (!nl) return QC_ENOMEM;
+    if (r.plim) { r.plim->release(); delete r.plim; }
+    r.plim = nl; r.lim_gain = g;
+    r.fmpll->flush(); r.sntch->flush();                 /* calc_fmd zeroes the PLL state and makes a new notch */
+    return QC_OK;
+}
 int quisk_cuda_rxa_set_agc_mode(qcRxa *p, int mode) { if (!p) return QC_EINVAL; agc_set_mode(p->r.agc, mode); return QC_OK; }
 int quisk_cuda_rxa_set_agc_fixed(qcRxa *p, double gain_db)
 { if (!p) return QC_EINVAL; p->r.agc->agc.fixed_gain = pow(10.0, gain_db / 20.0); p->r.agc->load_agc(); return QC_OK; }

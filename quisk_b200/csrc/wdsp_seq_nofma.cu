@@ -679,6 +679,24 @@ SeqStage *make_shift(int C, int rate, const double *shift_hz)
     return s;
 }
 
+SeqStage *make_wcpagc_fmlim(int C, int rate, double lim_gain)
+{   // the FM detector limiter: create_wcpagc's arguments in calc_fmd (wdsp/fmd.c:49-73)
+    SeqStage *s = new SeqStage();
+    AgcParams &a = s->agc;
+    memset(&a, 0, sizeof(a));
+    a.mode = 5; a.pmode = 1; a.sample_rate = (double)rate; a.tau_attack = 0.001; a.tau_decay = 0.008; a.n_tau = 4;
+    a.max_gain = lim_gain; a.var_gain = 1.0; a.fixed_gain = 1.0; a.max_input = 1.0; a.out_targ = 0.9;
+    a.tau_fast_backaverage = 0.250; a.tau_fast_decay = 0.004; a.pop_ratio = 4.0; a.hang_enable = 0;
+    a.tau_hang_backmult = 0.500; a.hangtime = 0.500; a.hang_thresh = 2.000; a.tau_hang_decay = 0.100;
+    s->load_agc();
+    s->kind = SEQ_WCPAGC;
+    s->ring_len = a.attack_buffsize;
+    a.ring_buffsize = s->ring_len;
+    if (cudaMalloc((void **)&s->d_ring, (size_t)C * s->ring_len * 3 * sizeof(double)) != cudaSuccess) { delete s; return nullptr; }
+    if (s->init_common(SEQ_WCPAGC, C, 16) != QC_OK) { s->release(); delete s; return nullptr; }
+    return s;
+}
+
 SeqStage *make_wcpagc(int C, int rate, int mode)
 {
     SeqStage *s = new SeqStage();
@@ -764,6 +782,8 @@ static qcSeqStage *wrap(qc::SeqStage *s) { if (!s) return nullptr; qcSeqStage *w
 
 qcSeqStage *quisk_cuda_shift_create(int n_channels, int rate, const double *shift_hz)
 { return qc::ensure_device() == QC_OK ? wrap(qc::make_shift(n_channels, rate, shift_hz)) : nullptr; }
+qcSeqStage *quisk_cuda_wcpagc_create_fmlim(int n_channels, int rate, double lim_gain)
+{ return qc::ensure_device() == QC_OK ? wrap(qc::make_wcpagc_fmlim(n_channels, rate, lim_gain)) : nullptr; }   // the FM detector limiter as a stage of its own (fmd.c:49-73)
 qcSeqStage *quisk_cuda_wcpagc_create(int n_channels, int rate, int mode)
 { return qc::ensure_device() == QC_OK ? wrap(qc::make_wcpagc(n_channels, rate, mode)) : nullptr; }
 int quisk_cuda_wcpagc_set_fixed_gain_db(qcSeqStage *s, double gain_db)

@@ -155,6 +155,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_resample_run.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p, vp]
     lib.quisk_cuda_shift_create.argtypes = [C.c_int, C.c_int, vp]; lib.quisk_cuda_shift_create.restype = vp
     lib.quisk_cuda_wcpagc_create.argtypes = [C.c_int, C.c_int, C.c_int]; lib.quisk_cuda_wcpagc_create.restype = vp
+    lib.quisk_cuda_wcpagc_create_fmlim.argtypes = [C.c_int, C.c_int, D]; lib.quisk_cuda_wcpagc_create_fmlim.restype = vp
     lib.quisk_cuda_wcpagc_set_fixed_gain_db.argtypes = [vp, D]
     lib.quisk_cuda_wcpagc_set_top_db.argtypes = [vp, D]
     lib.quisk_cuda_amd_create.argtypes = [C.c_int] * 5; lib.quisk_cuda_amd_create.restype = vp
@@ -181,6 +182,8 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_nbp_set_notches_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_nbp_set_tune_frequency.argtypes = [vp, D]
     lib.quisk_cuda_rxa_nbp_set_shift_frequency.argtypes = [vp, D]
+    lib.quisk_cuda_rxa_set_fm_lim_run.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_rxa_set_fm_lim_gain.argtypes = [vp, C.c_double]
     lib.quisk_cuda_rxa_set_mp.argtypes = [vp, C.c_int]
     lib.quisk_cuda_fircore_set_mp.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_set_panel_gain.argtypes = [vp, D]

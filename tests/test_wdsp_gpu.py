@@ -661,3 +661,56 @@ def test_rxa_multi_block_stage_groups_equal_per_block(cfg, torch, lib):
     assert max(errs) < 1e-12
     assert np.max(np.abs(got[1] - ref[1])) < 1e-9, got[1] - ref[1]
     assert np.max(np.abs(got[2] - ref[2])) <= 1e-6 * max(np.max(np.abs(ref[2])), 1e-30)
+
+
+def test_fm_limiter_stage_bit_exact(torch, lib):
+    """fmd's detector limiter (wdsp/fmd.c:49-73): a wcpAGC with calc_fmd's constants (mode 5, envelope detector, 1 ms
+    attack, 8 ms decay, no hang) run in place.  Same operations as xwcpagc in the same order: identical bits."""
+    kat = golden("wdsp_fmlim_kat.npz")
+    n = 256
+    st = lib.quisk_cuda_wcpagc_create_fmlim(NCH, 48000, 2.5)
+    assert st, lib.quisk_cuda_last_error()
+    d = _dev(torch, kat["lim_in"])
+    for b in range(40):
+        blk = d[:, b * n:(b + 1) * n]
+        assert lib.quisk_cuda_seq_run(st, blk.data_ptr(), d.stride(0), blk.data_ptr(), d.stride(0), n, None) == 0
+    torch.cuda.synchronize()
+    y = d.cpu().numpy()
+    ref = kat["lim_out"]
+    assert np.abs(ref).max() > 0.5 and np.abs(ref).max() < 1.0          # limited to out_target
+    for c in range(NCH):
+        assert np.array_equal(y[c], ref)
+    lib.quisk_cuda_seq_destroy(st)
+
+
+def test_rxa_fm_channel_with_detector_limiter(torch, lib):
+    """SetRXAFMLimRun(1) and SetRXAFMLimGain mid-stream (fmd.c:337-363: calc_fmd rebuilds the limiter and zeroes the PLL) on
+    an FM channel at 48 kS/s, against fexchange0 of the compiled reference.  The limiter's volts machine takes its decisions
+    on comparisons of the demodulated audio, so the reference itself moves by `cond` when its input moves by one ulp; the
+    stage alone is bit-exact (test above)."""
+    from tests.golden.make_golden_wdsp_fmlim import BLOCKS, GAIN_AT, N, TAIL
+    kat = golden("wdsp_fmlim_kat.npz")
+    x = _first_sample_swallowed(fm_sig(N * BLOCKS, 810, 48000.0))
+    rxa = lib.quisk_cuda_rxa_create(NCH, N, N, 48000, 48000, 48000)
+    assert rxa, lib.quisk_cuda_last_error()
+    lib.quisk_cuda_rxa_set_shift(rxa, 0, None)
+    assert lib.quisk_cuda_rxa_set_mode(rxa, 5) == 0
+    assert lib.quisk_cuda_rxa_set_passband(rxa, -8000.0, 8000.0) == 0
+    assert lib.quisk_cuda_rxa_set_fm_lim_run(rxa, 1) == 0
+    d = _dev(torch, x)
+    o = torch.zeros_like(d)
+    for b in range(BLOCKS):
+        if b == GAIN_AT:
+            assert lib.quisk_cuda_rxa_set_fm_lim_gain(rxa, -6.0) == 0
+        assert lib.quisk_cuda_rxa_xrxa(rxa, d[:, b * N:(b + 1) * N].data_ptr(), d.stride(0), o[:, b * N:(b + 1) * N].data_ptr(), o.stride(0), None) == 0
+    torch.cuda.synchronize()
+    y = o.cpu().numpy()
+    # fexchange0 hands out block b's result two calls later: the reference's segment [GAIN_AT - TAIL, GAIN_AT) + last TAIL blocks are our
+    # blocks shifted by two
+    seg = np.concatenate([y[:, (GAIN_AT - TAIL - 2) * N:(GAIN_AT - 2) * N], y[:, (BLOCKS - TAIL - 2) * N:(BLOCKS - 2) * N]], axis=1)
+    half = TAIL * N
+    for part, sl in enumerate((slice(0, half), slice(half, 2 * half))):
+        errs = [O.rel_rms(seg[c][sl], kat["y_seg"][sl]) for c in range(NCH)]
+        print("rxa fm + limiter, segment", part, errs, "reference's own one-ulp sensitivity", kat["conds"][part])
+        assert max(errs) < max(1e-12, 20.0 * float(kat["conds"][part]))
+    lib.quisk_cuda_rxa_destroy(rxa)
