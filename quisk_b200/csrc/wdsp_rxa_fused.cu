@@ -100,13 +100,18 @@ __device__ __forceinline__ RfSmem rf_map(double *raw, int n, int tot)
         }                                                                                                               \
     }                                                                                                                   \
     if (volts < k_minv) volts = k_minv;                                                                                 \
-    RV[i] = volts;                                                                                                      \
+    __syncwarp();                               /* every lane has read ring_max from RV[i] */                           \
+    if (l0) RV[i] = volts;                                                                                              \
+    __syncwarp();                                                                                                       \
     i++;
 
 // ---- role 1: the AGC warp.  All 32 lanes run the same instructions on the same data (no divergence inside the warp, so the
-// CTA-wide barriers are reached by whole warps) and store the same values to the same shared-memory words; lane 0 alone
-// writes the state back to global memory.  (A store predicated on the lane inside the dependent chain made the compiler
-// re-derive the chain from the chunk start for every store: 74 cycles per sample instead of 24.)
+// CTA-wide barriers are reached by whole warps); lane 0 alone stores -- to shared memory through inline PTX that carries its
+// own predicate, and the state back to global memory.  (A C++ store predicated on the lane inside the dependent chain made
+// the compiler re-derive the chain from the chunk start for every store: 74 cycles per sample instead of 24.)  What
+// compute-sanitizer's racecheck still reports in this kernel is the one lock-free hand-over it has: the LIN warp's lanes 6 / 7
+// write FBA / HBA and then publish their progress in `linpos` (fence, then a volatile store), the AGC warp's general path
+// spins on `linpos` before it reads them -- a flag protocol racecheck cannot see through.
 // One block of the volts machine: A[i] = |sample leaving the delay line|, RV[i] = ring_max on the way in, volts on the way out.
 __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, const double *HBA, volatile int *linpos, int n, const AgcParams &a,
                                              double &volts, double &save_volts, int &hang_counter, int &decay_type, int &state_, long long *dbg)
@@ -116,6 +121,10 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
     const double k_attack = a.attack_mult, k_decay = a.decay_mult, k_hdecay = a.hang_decay_mult, k_fdecay = a.fast_decay_mult,
                  k_pop = a.pop_ratio, k_hlevel = a.hang_level, k_minv = a.min_volts;
     int i = 0;
+    // Lane 0 alone stores (the predicate lives INSIDE the inline PTX, so the compiler still sees an unconditional statement and
+    // leaves the chain alone); every lane loads.  __syncwarp() at the run boundaries orders lane 0's stores against the other
+    // lanes' later loads of the same words, so the warp is race-free by construction and not only because it runs converged.
+    const int l0 = (threadIdx.x & 31) == 0 ? 1 : 0;
     // shared-memory accesses of the run loop go through 32-bit shared-window addresses kept in registers: left to itself the
     // compiler re-derives the window base (an S2R of the cluster CTA id) at the top of every chunk, ~100 cycles in front of
     // the chain each time
@@ -138,6 +147,7 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
             for (int j = 0; j < CH; j++) vp[j] = rm[j];
             bool ok = true;
             while (ok && n - i >= CH) {
+                __syncwarp();
                 // the following run's ring_max is asked for now (RV beyond this run is still input): its latency hides under the chain
                 const bool more = n - i >= 2 * CH;
                 double v = volts;
@@ -154,7 +164,7 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
                     const int hd = __double2hiint(d);
                     s_and &= hd; s_or |= hd;
                     vv[j] = v;
-                    asm volatile("st.shared.f64 [%0], %1;" :: "r"(ap + 8u * j), "d"(vp[j]) : "memory");
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" :: "r"(ap + 8u * j), "d"(vp[j]), "r"(l0) : "memory");
                     if (more) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(rn[j]) : "r"(a0 + 8u * (CH + j)));
                 }
                 ok = want ? s_or >= 0 : (s_and < 0 && !(v < k_minv));
@@ -172,8 +182,10 @@ __device__ __forceinline__ void rf_agc_block(double *RV, const double *FBA, cons
                 }
             }
             // whatever held last is still in registers: commit it (after a failed run it has been stored already; storing twice is harmless)
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < CH; j++) asm volatile("st.shared.f64 [%0], %1;" :: "r"(ap + 8u * j), "d"(vp[j]) : "memory");
+            for (int j = 0; j < CH; j++) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" :: "r"(ap + 8u * j), "d"(vp[j]), "r"(l0) : "memory");
+            __syncwarp();
             if (ok) continue;                               // fewer than a run's worth of samples left
             // the run did not hold (a handful of times per block): these samples go through the general machine one by one
             for (int g = 0; g < CH; g++) {
@@ -233,11 +245,11 @@ __device__ __forceinline__ double rf_lin_block(const double *x, int n, double c1
         s = __dadd_rn(__dmul_rn(c2, s), t1); dst[(i + 1) * dstep] = s;
         s = __dadd_rn(__dmul_rn(c2, s), t2); dst[(i + 2) * dstep] = s;
         s = __dadd_rn(__dmul_rn(c2, s), t3); dst[(i + 3) * dstep] = s;
-        if (pos && (i & 12) == 12) { __threadfence_block(); *pos = i + 4; }    // progress for the AGC lane's general path, every 16 samples
+        if (pos && (i & 12) == 12) { __threadfence_block(); __syncwarp(); if ((threadIdx.x & 31) == 0) *pos = i + 4; }    // progress for the AGC lane's general path, every 16 samples (lanes 6 and 7 have stored their averages)
 #pragma unroll
         for (int j = 0; j < 4; j++) xa[j] = xb[j];
     }
-    for (; i < n; i++) { s = __dadd_rn(__dmul_rn(c2, s), __dmul_rn(c1, x[i])); dst[i * dstep] = s; if (pos) { __threadfence_block(); *pos = i + 1; } }
+    for (; i < n; i++) { s = __dadd_rn(__dmul_rn(c2, s), __dmul_rn(c1, x[i])); dst[i * dstep] = s; if (pos) { __threadfence_block(); __syncwarp(); if ((threadIdx.x & 31) == 0) *pos = i + 1; } }
     return s;
 }
 
