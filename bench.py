@@ -388,7 +388,9 @@ def run_rxa(args, ctx, workload, steps, warmup, e2e_steps, cpu_steps):
     # H2D of the block, the DSP turn, D2H of the block that leaves the output ring
     e2e = None
     if e2e_steps > 0:
-        hx = np.ascontiguousarray(x[:, :m].cpu().numpy()); hy = np.zeros((C_, osz), dtype=np.complex128)
+        hxt = torch.empty((C_, m), dtype=torch.complex128).pin_memory(); hxt.copy_(x[:, :m].cpu())
+        hyt = torch.zeros((C_, osz), dtype=torch.complex128).pin_memory()
+        hx = hxt.numpy(); hy = hyt.numpy()
         err = C.c_int(0)
         lib.quisk_cuda_rxa_fexchange0(rxa, hx.ctypes.data, hy.ctypes.data, C.byref(err))
         ctx.barrier()
@@ -398,7 +400,7 @@ def run_rxa(args, ctx, workload, steps, warmup, e2e_steps, cpu_steps):
             lib.quisk_cuda_rxa_fexchange0(rxa, hx.ctypes.data, hy.ctypes.data, C.byref(err))
         dt = ctx.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": ctx.world * C_ * m * nb / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": C_ * m * 16 * blocks,
-               "d2h_bytes_per_step": C_ * osz * 16 * blocks, "channels": C_, "note": "quisk_cuda_rxa_fexchange0, pageable host buffers, one call per DSP block"}
+               "d2h_bytes_per_step": C_ * osz * 16 * blocks, "channels": C_, "note": "quisk_cuda_rxa_fexchange0 (the reference's exchange call for all channels at once), pinned host buffers, one call per DSP block: H2D, ring arithmetic, DSP turn, D2H, synchronous like the reference's blocking exchange"}
     lib.quisk_cuda_rxa_destroy(rxa)
     del x, y
     if ctx.rank != 0:
