@@ -309,11 +309,19 @@ def pin_to_gpu_numa_node(local_rank):
             elif part:
                 cpus.add(int(part))
         cpus &= os.sched_getaffinity(0)
+        node = None
+        try:
+            node = int(open(path.replace("local_cpulist", "numa_node")).read().strip())
+        except Exception:
+            pass
         if cpus:
             os.sched_setaffinity(0, cpus)
+            if os.environ.get("QUISK_BENCH_VERBOSE"):
+                print("[rank %d] GPU %s on NUMA node %s: host threads on %d CPUs (%d..%d)" % (local_rank, bus, node, len(cpus), min(cpus), max(cpus)), file=sys.stderr, flush=True)
             return sorted(cpus)
-    except Exception:
-        pass
+    except Exception as ex:
+        if os.environ.get("QUISK_BENCH_VERBOSE"):
+            print("[rank %d] NUMA pinning skipped: %s" % (local_rank, ex), file=sys.stderr, flush=True)
     return None
 
 
