@@ -49,3 +49,27 @@ def test_product_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=280)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+
+
+@pytest.mark.gpu
+def test_product_arm_contract_on_gpu():
+    """The line the driver records: one JSON line with the contract's keys, the roofline and cpu_baseline objects, an e2e
+    figure measured on the same channel count with host<->device copies, a launch count, and the other configurations
+    under `workloads` (each a complete sub-line).  Small sizes: this checks the shape of the line, not its numbers."""
+    d = run_bench("--steps", "2", "--warmup", "3", "--channels", "256", "--e2e-steps", "1")
+    for k in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline", "workloads"]:
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["e2e"]["channels"] == d["config"]["channels_per_gpu"]            # same channel count as `value`
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert "fused_decim" in r["kernel"] and 0.1 < r["kernel_share_of_step"] <= 1.0      # (small batches leave the step latency bound)
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] > 0
+    assert set(d["workloads"]) == {"panadapter", "rxa_usb", "rxa_fm", "channelizer", "pipeline"}
+    for name, w in d["workloads"].items():
+        assert w["value"] > 0 and w["gpu_launches"] > 0 and w["e2e"]["value"] > 0, name
+        assert w["roofline"]["frac"] > 0 and w["cpu_baseline"]["value"] > 0, name
