@@ -44,6 +44,24 @@ int quisk_cuda_nbp_impulse(int nc, double flow, double fhigh, double rate, int w
  * pfactor 16 and polarity 0 are what calc_fircore passes, firmin.c:328).  N * pfactor must be a power of two. */
 int quisk_cuda_mp_imp(int N, const double *fir, double *mpfir, int pfactor, int polarity);
 
+/* ---- emnr: spectral noise reduction "NR2" (wdsp/emnr.c): STFT overlap-add, per-bin gain from a running noise estimate ----
+ * create = create_emnr (emnr.c:561-581; fsize 4096 as create_rxa passes it, wintype 0); run = xemnr with run = 1 on bsize
+ * complex samples per channel (the real rail is processed, the imaginary rail comes back zero, emnr.c:1059-1064), in place
+ * or not; flush = flush_emnr.  gain_method 0 (Gaussian, linear amplitude), 1 (Gaussian, log amplitude), 2 (gamma prior:
+ * bilinear look-up in the two 241 x 241 tables GG / GGS of the WDSP distribution -- wdsp/calculus.c, or the `calculus`
+ * file calc_emnr prefers, emnr.c:313-323 -- which the HOST supplies once per process with quisk_cuda_emnr_set_tables;
+ * they are not part of this library); 3 is not built.  npe_method 0 (minimum statistics), 1, 2.  ae_run: the post-filter. */
+typedef struct qcEmnr qcEmnr;
+int quisk_cuda_emnr_set_tables(const double *GG, const double *GGS);     /* host pointers, 241 * 241 doubles each, copied */
+qcEmnr *quisk_cuda_emnr_create(int n_channels, int bsize, int fsize, int ovrlp, int rate, int wintype, double gain,
+                               int gain_method, int npe_method, int ae_run);
+void quisk_cuda_emnr_destroy(qcEmnr *e);
+int quisk_cuda_emnr_run(qcEmnr *e, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream);
+int quisk_cuda_emnr_flush(qcEmnr *e);
+int quisk_cuda_emnr_set_gain_method(qcEmnr *e, int method);             /* SetRXAEMNRgainMethod, emnr.c:1111-1117 */
+int quisk_cuda_emnr_set_npe_method(qcEmnr *e, int method);              /* SetRXAEMNRnpeMethod,  emnr.c:1119-1125 */
+int quisk_cuda_emnr_set_ae_run(qcEmnr *e, int run);                     /* SetRXAEMNRaeRun,      emnr.c:1127-1133 */
+
 /* ---- fircore: uniformly partitioned overlap-save complex FIR (wdsp/firmin.c:290-430) ---- */
 typedef struct qcFircore qcFircore;
 /* impulse: HOST, nc complex, the same for every channel (callers bake 1/(2*size) into it exactly as
@@ -132,6 +150,11 @@ int quisk_cuda_rxa_nbp_delete_notch(qcRxa *rxa, int notch);
 int quisk_cuda_rxa_nbp_set_notches_run(qcRxa *rxa, int run);
 int quisk_cuda_rxa_nbp_set_tune_frequency(qcRxa *rxa, double tunefreq);
 int quisk_cuda_rxa_nbp_set_shift_frequency(qcRxa *rxa, double shift);
+int quisk_cuda_rxa_set_emnr_run(qcRxa *rxa, int run);                        /* SetRXAEMNRRun, emnr.c:1096-1109 (bp1 follows: RXAbp1Check / RXAbp1Set) */
+int quisk_cuda_rxa_set_emnr_gain_method(qcRxa *rxa, int method);
+int quisk_cuda_rxa_set_emnr_npe_method(qcRxa *rxa, int method);
+int quisk_cuda_rxa_set_emnr_ae_run(qcRxa *rxa, int run);
+int quisk_cuda_rxa_set_emnr_position(qcRxa *rxa, int position);              /* SetRXAEMNRPosition, emnr.c:1135-1142: 0 in front of the AGC, 1 behind it */
 int quisk_cuda_rxa_set_fm_lim_run(qcRxa *rxa, int run);                      /* SetRXAFMLimRun,  fmd.c:337-348: the FM detector limiter (a wcpAGC, fmd.c:49-73) */
 int quisk_cuda_rxa_set_fm_lim_gain(qcRxa *rxa, double gain_db);              /* SetRXAFMLimGain, fmd.c:350-363 */
 int quisk_cuda_rxa_set_mp(qcRxa *rxa, int mp);                               /* RXASetMP, RXA.c:949-958           */
@@ -209,6 +232,9 @@ void SetRXAAMSQRun(int channel, int run);
 void SetRXAFMSQRun(int channel, int run);
 void SetRXAEMNRRun(int channel, int run);
 void SetRXAEMNRgainMethod(int channel, int method);
+void SetRXAEMNRnpeMethod(int channel, int method);
+void SetRXAEMNRaeRun(int channel, int run);
+void SetRXAEMNRPosition(int channel, int position);
 void SetRXASNBARun(int channel, int run);
 void SetRXAANFRun(int channel, int run);
 void SetRXAANRRun(int channel, int run);

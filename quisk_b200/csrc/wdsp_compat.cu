@@ -172,8 +172,15 @@ void RXAGetaSipF1(int channel, float *out, int size) { CH("RXAGetaSipF1") return
 // stages create_rxa builds switched off and this library does not have: fine while they stay off
 void SetRXAAMSQRun(int channel, int run) { CH("SetRXAAMSQRun") return; if (run) unsupported("SetRXAAMSQRun", channel); }
 void SetRXAFMSQRun(int channel, int run) { CH("SetRXAFMSQRun") return; if (run) unsupported("SetRXAFMSQRun", channel); }
-void SetRXAEMNRRun(int channel, int run) { CH("SetRXAEMNRRun") return; if (run) unsupported("SetRXAEMNRRun", channel); }
-void SetRXAEMNRgainMethod(int channel, int method) { CH("SetRXAEMNRgainMethod") return; (void)method; }
+void SetRXAEMNRRun(int channel, int run)
+{   // NR2.  Gain methods 0, 1 and 2 are built; 2 (create_rxa's and Quisk's choice) needs the distribution's tables first
+    CH("SetRXAEMNRRun") return;
+    if (quisk_cuda_rxa_set_emnr_run(as_handle(r), run) != QC_OK) fprintf(stderr, "libquisk_cuda: SetRXAEMNRRun(%d, %d): %s\n", channel, run, quisk_cuda_last_error());
+}
+void SetRXAEMNRgainMethod(int channel, int method) { CH("SetRXAEMNRgainMethod") return; quisk_cuda_rxa_set_emnr_gain_method(as_handle(r), method); }
+void SetRXAEMNRnpeMethod(int channel, int method) { CH("SetRXAEMNRnpeMethod") return; quisk_cuda_rxa_set_emnr_npe_method(as_handle(r), method); }
+void SetRXAEMNRaeRun(int channel, int run) { CH("SetRXAEMNRaeRun") return; quisk_cuda_rxa_set_emnr_ae_run(as_handle(r), run); }
+void SetRXAEMNRPosition(int channel, int position) { CH("SetRXAEMNRPosition") return; quisk_cuda_rxa_set_emnr_position(as_handle(r), position); }
 void SetRXASNBARun(int channel, int run) { CH("SetRXASNBARun") return; if (run) unsupported("SetRXASNBARun", channel); }
 void SetRXAANFRun(int channel, int run) { CH("SetRXAANFRun") return; if (run) unsupported("SetRXAANFRun", channel); }
 void SetRXAANRRun(int channel, int run) { CH("SetRXAANRRun") return; if (run) unsupported("SetRXAANRRun", channel); }

@@ -44,6 +44,15 @@ struct AgcParams {      // the fields of struct _wcpagc that xwcpagc reads (wdsp
     int n_tau;
 };
 
+// spectral noise reduction (wdsp_emnr_nofma.cu)
+struct Emnr;
+Emnr *make_emnr(int C, int bsize, int fsize, int ovrlp, int rate, int wintype, double gain, int gain_method, int npe_method, int ae_run);
+void emnr_destroy(Emnr *e);
+int emnr_run(Emnr *e, const cd *in, long is, cd *out, long os, cudaStream_t s);
+int emnr_flush(Emnr *e);
+int emnr_set(Emnr *e, int what /* 0 gain method, 1 npe method, 2 ae_run */, int value);
+bool emnr_tables_present();
+
 struct SeqStage {
     int kind = 0, C = 0;
     double *d_state = nullptr;      // [C][state_doubles]
@@ -102,6 +111,9 @@ struct Rxa {
     // amd / fmd
     int amd_run = 0, amd_mode = 0; SeqStage *amd = nullptr;
     int fmd_run = 0, fm_nc_de = 0, fm_nc_aud = 0; SeqStage *fmpll = nullptr, *sntch = nullptr; FirCore *pde = nullptr, *paud = nullptr;
+    int emnr_run = 0, emnr_position = 0, emnr_gain_method = 2; Emnr *emnr = nullptr;      // xemnr, RXA.c:319-332, 577-590
+    int emnr_run_stage(cd *m, long ms, cudaStream_t s);
+    int bp1_check_set();                                                                    // RXAbp1Check + RXAbp1Set, RXA.c:800-827
     int lim_run = 0; double lim_pre_gain = 0.4, lim_gain = 2.5; SeqStage *plim = nullptr;     // fmd's detector limiter (fmd.c:106-108, 179-184)
     int fm_limiter(cd *m, long ms, int n, cudaStream_t s);
     // bp1

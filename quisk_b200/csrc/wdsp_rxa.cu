@@ -159,6 +159,8 @@ int Rxa::init(int C_, int in_size_, int dsp_size_, int in_rate_, int dsp_rate_, 
     sntch = make_snotch(C, dsp_rate, 254.1, 0.0002);
     plim = make_wcpagc_fmlim(C, dsp_rate, lim_gain);
     if (!plim) return QC_EINVAL;
+    emnr = make_emnr(C, dsp_size, 4096, 4, dsp_rate, 0, 1.0, 2, 0, 1);        // create_rxa's arguments, RXA.c:319-332
+    if (!emnr) return QC_EINVAL;
     if ((rc = make_fmd()) != QC_OK) return rc;
     agc = make_wcpagc(C, dsp_rate, 3);
     if (!shift || !adcmeter || !smeter || !agcmeter || !amd || !fmpll || !sntch || !agc) return QC_EINVAL;
@@ -180,6 +182,7 @@ static int raise_upflag(Rxa &r)
 
 void Rxa::release()
 {
+    if (emnr) { emnr_destroy(emnr); emnr = nullptr; }
     for (SeqStage **p : {&shift, &adcmeter, &smeter, &agcmeter, &amd, &fmpll, &sntch, &agc, &plim}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     for (FirCore **p : {&nbp0, &bp1, &pde, &paud}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     for (Resampler **p : {&rsmpin, &rsmpout}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
@@ -201,6 +204,24 @@ void Rxa::release()
     mid = mid2 = audio = nullptr;
 }
 
+int Rxa::emnr_run_stage(cd *m, long ms, cudaStream_t s) { return qc::emnr_run(emnr, m, ms, m, ms, s); }
+
+int Rxa::bp1_check_set()
+{   // RXAbp1Check (gain 2 when the AM demodulator or a noise reducer feeds bp1; new masks wait for setUpdate) + RXAbp1Set
+    const int feeds = amd_run || emnr_run;
+    const double gain = feeds ? 2.0 : 1.0;
+    if (bp1_gain != gain) {
+        bp1_gain = gain;
+        std::vector<double> imp((size_t)2 * bp1_nc);
+        quisk_cuda_fir_bandpass(bp1_nc, bp1_flow, bp1_fhigh, (double)dsp_rate, 1, 1, bp1_gain / (double)(2 * dsp_size), imp.data());
+        int rc = bp1->set_impulse(imp.data(), 0); if (rc) return rc;
+    }
+    const int old = bp1_run;
+    bp1_run = feeds ? 1 : 0;
+    if (!old && bp1_run) { int rc = bp1->flush(); if (rc) return rc; }
+    return bp1->update();
+}
+
 int Rxa::fm_limiter(cd *m, long ms, int n, cudaStream_t s)
 {   // fmd.c:179-184: out *= lim_pre_gain, then the detector limiter (a wcpAGC with calc_fmd's constants) in place
     if (!lim_run) return QC_OK;
@@ -211,6 +232,13 @@ int Rxa::fm_limiter(cd *m, long ms, int n, cudaStream_t s)
 int Rxa::xrxa_multi(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s)
 {   // nblocks consecutive DSP blocks per channel: block b of a channel at in + b * dsp_insize, out + b * dsp_outsize
     if (nblocks <= 0) return QC_OK;
+    if (emnr_run) {         // the noise reducer frames its own stream: block by block through the per-stage chain
+        for (int b = 0; b < nblocks; b++) {
+            int rc = xrxa((const cd *)din + (size_t)b * dsp_insize, is, (cd *)dout + (size_t)b * dsp_outsize, os, s);
+            if (rc != QC_OK) return rc;
+        }
+        return QC_OK;
+    }
     if (fusable()) return xrxa_fused(din, is, dout, os, nblocks, s);
     // the other configurations: every stage is a streaming operator with carried state, so it can take a GROUP of blocks per
     // launch (the fircores as wide transform grids); the group is bounded by what the recurrent kernels stage in shared memory
@@ -354,9 +382,13 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
         rc = sntch->run(m, ms, m, ms, dsp_size, s); if (rc) return rc;                 // CTCSS notch (I rail)
         rc = fm_limiter(m, ms, dsp_size, s); if (rc) return rc;
     }
-    if (bp1_run) { rc = bp1->run(m, ms, m, ms, s); if (rc) return rc; }
+    // xemnr / xbandpass(bp1) at position 0 in front of the AGC, at position 1 behind it (RXA.c:577-590)
+    if (emnr_run && emnr_position == 0) { rc = emnr_run_stage(m, ms, s); if (rc) return rc; }
+    if (bp1_run && emnr_position == 0) { rc = bp1->run(m, ms, m, ms, s); if (rc) return rc; }
     // out of place into the second scratch buffer (free by now): the AGC kernel then needs no sample staging
     if (agc_run) { rc = agc->run(m, ms, mid2, ms, dsp_size, s); if (rc) return rc; m = mid2; }
+    if (emnr_run && emnr_position == 1) { rc = emnr_run_stage(m, ms, s); if (rc) return rc; }
+    if (bp1_run && emnr_position == 1) { rc = bp1->run(m, ms, m, ms, s); if (rc) return rc; }
     rc = agcmeter->run(m, ms, agc->d_state, 0, dsp_size, s); if (rc) return rc;
     // xpanel always applies gain1 * gain2 (F9), inselect 3, no copy
     cd *sp = sip_run ? d_sip : nullptr;
@@ -436,6 +468,7 @@ int Rxa::flush_main()
     int rc;
     for (SeqStage *q : {shift, adcmeter, smeter, amd, fmpll, sntch, plim, agc, agcmeter}) if (q) { rc = q->flush_ref(); if (rc) return rc; }
     for (FirCore *f : {nbp0, pde, paud, bp1}) if (f) { rc = f->flush(); if (rc) return rc; }
+    if (emnr) { rc = emnr_flush(emnr); if (rc) return rc; }
     for (Resampler *q : {rsmpin, rsmpout}) if (q) { rc = q->f->reset(nullptr); if (rc) return rc; }
     QC_CUDA(cudaMemset(d_sip, 0, (size_t)C * sipsize * sizeof(cd)));
     sip_idx = 0;
@@ -579,25 +612,12 @@ int quisk_cuda_rxa_set_mode(qcRxa *p, int mode)
     if (!p) return QC_EINVAL;
     Rxa &r = p->r;
     if (r.mode == mode) return QC_OK;
-    const int amd_run = (mode == QC_RXA_AM) || (mode == QC_RXA_SAM);
-    // RXAbp1Check: gain 2 when the AM demodulator (or a noise reducer) feeds bp1; new masks wait for setUpdate
-    const double gain = amd_run ? 2.0 : 1.0;
-    if (r.bp1_gain != gain) {
-        r.bp1_gain = gain;
-        std::vector<double> imp((size_t)2 * r.bp1_nc);
-        quisk_cuda_fir_bandpass(r.bp1_nc, r.bp1_flow, r.bp1_fhigh, (double)r.dsp_rate, 1, 1, r.bp1_gain / (double)(2 * r.dsp_size), imp.data());
-        int rc = r.bp1->set_impulse(imp.data(), 0); if (rc) return rc;
-    }
     r.mode = mode;
     r.amd_run = 0; r.fmd_run = 0; r.agc_run = 1;
     if (mode == QC_RXA_AM) { r.amd_run = 1; r.amd->par[0] = 0; }
     else if (mode == QC_RXA_SAM) { r.amd_run = 1; r.amd->par[0] = 1; }
     else if (mode == QC_RXA_FM) { r.fmd_run = 1; r.agc_run = 0; }
-    // RXAbp1Set, RXA.c:815-827
-    const int old = r.bp1_run;
-    r.bp1_run = r.amd_run ? 1 : 0;
-    if (!old && r.bp1_run) { int rc = r.bp1->flush(); if (rc) return rc; }
-    return r.bp1->update();
+    return r.bp1_check_set();       // RXAbp1Check + RXAbp1Set, RXA.c:800-827
 }
 
 int quisk_cuda_rxa_set_passband(qcRxa *p, double f_low, double f_high)
@@ -632,6 +652,24 @@ int quisk_cuda_rxa_set_nc(qcRxa *p, int nc)
     return QC_OK;
 }
 
+int quisk_cuda_rxa_set_emnr_run(qcRxa *p, int run)
+{   // SetRXAEMNRRun, emnr.c:1096-1109
+    if (!p) return QC_EINVAL;
+    qc::Rxa &r = p->r;
+    run = run ? 1 : 0;
+    if (r.emnr_run == run) return QC_OK;
+    if (run && r.emnr_gain_method == 2 && !qc::emnr_tables_present()) {
+        qc::set_error("SetRXAEMNRRun: gain method 2 needs the WDSP distribution's two gamma-prior tables: quisk_cuda_emnr_set_tables first (or choose gain method 0 or 1)");
+        return QC_EINVAL;
+    }
+    if (run && (r.emnr_gain_method < 0 || r.emnr_gain_method > 2)) { qc::set_error("SetRXAEMNRRun: gain method %d is not built", r.emnr_gain_method); return QC_EINVAL; }
+    r.emnr_run = run;
+    return r.bp1_check_set();
+}
+int quisk_cuda_rxa_set_emnr_gain_method(qcRxa *p, int method) { if (!p) return QC_EINVAL; p->r.emnr_gain_method = method; return qc::emnr_set(p->r.emnr, 0, method); }
+int quisk_cuda_rxa_set_emnr_npe_method(qcRxa *p, int method) { return p ? qc::emnr_set(p->r.emnr, 1, method) : QC_EINVAL; }
+int quisk_cuda_rxa_set_emnr_ae_run(qcRxa *p, int run) { return p ? qc::emnr_set(p->r.emnr, 2, run) : QC_EINVAL; }
+int quisk_cuda_rxa_set_emnr_position(qcRxa *p, int position) { if (!p) return QC_EINVAL; p->r.emnr_position = position ? 1 : 0; return QC_OK; }    /* SetRXAEMNRPosition moves bp1 with it */
 int quisk_cuda_rxa_set_fm_lim_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.lim_run = run ? 1 : 0; return QC_OK; }      /* SetRXAFMLimRun, fmd.c:337-348 */
 int quisk_cuda_rxa_set_fm_lim_gain(qcRxa *p, double gain_db)
 {   /* SetRXAFMLimGain, fmd.c:350-363: decalc_fmd / calc_fmd rebuild the limiter (and the notch) from scratch */

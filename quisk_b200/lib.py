@@ -182,6 +182,16 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_nbp_set_notches_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_nbp_set_tune_frequency.argtypes = [vp, D]
     lib.quisk_cuda_rxa_nbp_set_shift_frequency.argtypes = [vp, D]
+    lib.quisk_cuda_emnr_set_tables.argtypes = [vp, vp]
+    lib.quisk_cuda_emnr_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+    lib.quisk_cuda_emnr_create.restype = vp
+    lib.quisk_cuda_emnr_destroy.argtypes = [vp]; lib.quisk_cuda_emnr_destroy.restype = None
+    lib.quisk_cuda_emnr_run.argtypes = [vp, vp, C.c_long, vp, C.c_long, vp]
+    lib.quisk_cuda_emnr_flush.argtypes = [vp]
+    for _f in ("gain_method", "npe_method", "ae_run"):
+        getattr(lib, "quisk_cuda_emnr_set_" + _f).argtypes = [vp, C.c_int]
+    for _f in ("run", "gain_method", "npe_method", "ae_run", "position"):
+        getattr(lib, "quisk_cuda_rxa_set_emnr_" + _f).argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_set_fm_lim_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_set_fm_lim_gain.argtypes = [vp, C.c_double]
     lib.quisk_cuda_rxa_set_mp.argtypes = [vp, C.c_int]

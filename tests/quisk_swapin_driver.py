@@ -1,7 +1,7 @@
 """tests/quisk_swapin_driver.py -- run the reference's WHOLE _quisk extension on a synthetic block source.
 
 Subprocess helper of tests/test_quisk_swapin_gpu.py (TEST INFRASTRUCTURE).  argv: <build dir with _quisk.so>
-<out.npz> <rate> <mode> <tune_hz> <n_samples> <block> <wdsp: 0 | 1 | 2> <dc_remove_bw>.  It does what quisk.py does at start-up, in the
+<out.npz> <rate> <mode> <tune_hz> <n_samples> <block> <wdsp: 0 | 1 | 2 | 3> <dc_remove_bw>.  It does what quisk.py does at start-up, in the
 same order and through the same Python methods of _quisk (record_app, set_sound_name, open_sound, set_filters,
 set_rx_mode, set_tune, set_volume, start_sound), registers the B4 block source (quisk_block_source.open_samples ->
 quisk_sample_source4), then calls read_sound() until the source is dry: quisk_read_sound (sound.c:873) ->
@@ -69,6 +69,15 @@ def main():
             wl.SetRXAAGCMode(ch, 3)
             wl.SetRXAPanelRun(ch, 1)
             wl.SetRXAPanelGain1(ch, D(0.25))
+        if use_wdsp == 3:       # Quisk's NR2 button (quisk.py:6017-6027): gain method 2, run, in_use = 1
+            if hasattr(wl, "quisk_cuda_emnr_set_tables"):
+                # the GPU library takes the two gamma-prior tables of the WDSP distribution from the host: here from the compiled reference
+                ref = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libwdsp_ref.so"))
+                T = ctypes.c_double * (241 * 241)
+                gg, ggs = T.in_dll(ref, "GG"), T.in_dll(ref, "GGS")
+                assert wl.quisk_cuda_emnr_set_tables(ctypes.c_void_p(ctypes.addressof(gg)), ctypes.c_void_p(ctypes.addressof(ggs))) == 0
+            wl.SetRXAEMNRgainMethod(ch, 2)
+            wl.SetRXAEMNRRun(ch, 1)
         QS.wdsp_set_parameter(ch, in_use=1)
     x = O.synth_iq(n_samples, 77, 1.0)
     assert SRC.load(np.ascontiguousarray(x).tobytes(), block) == n_samples

@@ -71,10 +71,11 @@ def test_whole_quisk_on_gpu_filters_equals_reference(rate, mode, tune, n, block,
     assert int(ref["fft_error"][0]) == int(gpu["fft_error"][0])               # blocks above 3 x fft_size overrun get_graph's FIFO of four, in both
 
 
-@pytest.mark.parametrize("wdsp", [1, 2])
+@pytest.mark.parametrize("wdsp", [1, 2, 3])
 def test_whole_quisk_with_wdsp_channel_on_gpu(wdsp, tmp_path):
     """wdsp = 1: the channel as quisk_wdsp.py opens it (every RXA stage off: a delay line through the exchange rings, so
-    the two builds agree exactly); wdsp = 2: nbp0 band-pass, AGC (medium) and the panel switched on as well."""
+    the two builds agree exactly); wdsp = 2: nbp0 band-pass, AGC (medium) and the panel switched on as well; wdsp = 3: what
+    Quisk's NR2 button sends (SetRXAEMNRgainMethod(2), SetRXAEMNRRun(1), in_use = 1): the spectral noise reduction + bp1."""
     rate, mode, tune, n, block = 48000, 3, 2000, 100000, 1000
     ref = _run("ref", tmp_path, "wdsp", rate, mode, tune, n, block, wdsp=wdsp, wdsp_lib=os.path.join(R.REF_DIR, "libwdsp_ref.so"))
     gpu = _run("cuda", tmp_path, "wdsp", rate, mode, tune, n, block, wdsp=wdsp, wdsp_lib=os.path.join(ROOT, "quisk_b200", "libquisk_cuda.so"))
