@@ -16,7 +16,7 @@
 // plus wdspFexchange0, the re-blocker Quisk's own C side puts in front of fexchange0 (quisk_wdsp.c:24-73).
 // Each open channel number owns one single-channel chain; many receivers at once go through the batched
 // quisk_cuda_rxa_* handle API instead (same chain, same exchange code).  The stages this library does not build (AM /
-// FM squelch, EMNR, SNBA, ANF, ANR, EQ ...) are accepted when switched OFF and refused loudly when switched on.
+// FM squelch, SNBA, ANF, ANR, EQ ...; EMNR / NR2 IS built, wdsp_emnr_nofma.cu) are accepted when switched OFF and refused loudly when switched on.
 #include "wdsp_internal.h"
 #include <chrono>
 #include <cmath>
