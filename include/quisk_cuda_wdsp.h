@@ -31,6 +31,9 @@ int quisk_cuda_fc_impulse(int nc, double f0, double f1, double g0, double g1, in
 /* calc_resample, wdsp/resample.c:35-78: L, M, ncoef and (if h != NULL) the ncoef prototype taps. */
 int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_in, double gain,
                                int *L, int *M, int *ncoef, double *h, int h_cap);
+/* the same with calc_resample's fc_low member: < 0 low pass, >= 0 the band pass of setFCLow_resample (resample.c:185-193) */
+int quisk_cuda_resample_design_band(int in_rate, int out_rate, double fc_low, double fc, int ncoef_in, double gain,
+                                    int *L, int *M, int *ncoef, double *h, int h_cap);
 
 /* calc_nbp_impulse with the notches running (wdsp/nbp.c:64-179, 214-239): the pass band [flow, fhigh] minus the active
  * notches of the database (centres / widths in RF coordinates, offset = tunefreq + shift), designed piecewise with
@@ -61,6 +64,17 @@ int quisk_cuda_emnr_flush(qcEmnr *e);
 int quisk_cuda_emnr_set_gain_method(qcEmnr *e, int method);             /* SetRXAEMNRgainMethod, emnr.c:1111-1117 */
 int quisk_cuda_emnr_set_npe_method(qcEmnr *e, int method);              /* SetRXAEMNRnpeMethod,  emnr.c:1119-1125 */
 int quisk_cuda_emnr_set_ae_run(qcEmnr *e, int run);                     /* SetRXAEMNRaeRun,      emnr.c:1127-1133 */
+
+/* ---- snba: spectral noise blanker "SNB" (wdsp/snb.c): linear-prediction detection and least-squares interpolation of impulses ----
+ * create = create_snba (snb.c:68-119; xsize 256 and asize <= 64 as create_rxa passes them, RXA.c:237-255); run = xsnba with
+ * run = 1 on bsize complex samples per channel (real rail processed, imaginary rail back as zero), flush = flush_snba.
+ * Resamplers to the internal rate and back are part of the stage when inrate != internalrate. */
+typedef struct qcSnba qcSnba;
+qcSnba *quisk_cuda_snba_create(int n_channels, int inrate, int internalrate, int bsize, int ovrlp, int xsize, int asize, int npasses,
+                               double k1, double k2, int b, int pre, int post, double pmultmin, double out_low_cut, double out_high_cut);
+void quisk_cuda_snba_destroy(qcSnba *d);
+int quisk_cuda_snba_run(qcSnba *d, const void *d_in, long in_stride, void *d_out, long out_stride, void *stream);
+int quisk_cuda_snba_flush(qcSnba *d);
 
 /* ---- fircore: uniformly partitioned overlap-save complex FIR (wdsp/firmin.c:290-430) ---- */
 typedef struct qcFircore qcFircore;

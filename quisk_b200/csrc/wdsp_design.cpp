@@ -182,8 +182,10 @@ int quisk_cuda_fc_impulse(int nc, double f0, double f1, double g0, double g1, in
     return QC_OK;
 }
 
-int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_in, double gain,
-                               int *pL, int *pM, int *pncoef, double *h, int h_cap)
+/* calc_resample (resample.c:35-78) with its fc_low member: < 0 = low pass (what create_resample leaves, resample.c:92), >= 0 = the
+ * band pass setFCLow_resample / setBandwidth_resample make of it (resample.c:185-207; the noise blanker's two converters use it) */
+int quisk_cuda_resample_design_band(int in_rate, int out_rate, double fc_low, double fc, int ncoef_in, double gain,
+                                    int *pL, int *pM, int *pncoef, double *h, int h_cap)
 {
     if (in_rate <= 0 || out_rate <= 0) return QC_EINVAL;
     int x = in_rate, y = out_rate;
@@ -193,7 +195,7 @@ int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_i
     if (fc == 0.0) fc = 0.45 * (double)min_rate;
     const double full_rate = (double)(in_rate * L);
     const double fc_norm_high = fc / full_rate;
-    const double fc_norm_low = -fc_norm_high;                   // fc_low = -1 (resample.c:92)
+    const double fc_norm_low = fc_low < 0.0 ? -fc_norm_high : fc_low / full_rate;
     int ncoef = ncoef_in;
     if (ncoef == 0) ncoef = (int)(140.0 * full_rate / min_rate);
     ncoef = (ncoef / L + 1) * L;
@@ -207,6 +209,12 @@ int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_i
         return quisk_cuda_fir_bandpass(ncoef, fc_norm_low, fc_norm_high, 1.0, 1, 0, gain * (double)L, h);
     }
     return QC_OK;
+}
+
+int quisk_cuda_resample_design(int in_rate, int out_rate, double fc, int ncoef_in, double gain,
+                               int *pL, int *pM, int *pncoef, double *h, int h_cap)
+{
+    return quisk_cuda_resample_design_band(in_rate, out_rate, -1.0, fc, ncoef_in, gain, pL, pM, pncoef, h, h_cap);
 }
 
 

@@ -168,13 +168,15 @@ int FirCore::run(const void *d_in, long in_stride, void *d_out, long out_stride,
 }
 
 // ---- resampler: xresample is the streaming polyphase FIR with u = phnum + m*M (resample.c:134-150) ----
-int Resampler::init(int C_, int in_rate, int out_rate, double fc, int ncoef_in, double gain)
+int Resampler::init(int C_, int in_rate, int out_rate, double fc, int ncoef_in, double gain) { return init_band(C_, in_rate, out_rate, -1.0, fc, ncoef_in, gain); }
+
+int Resampler::init_band(int C_, int in_rate, int out_rate, double fc_low, double fc, int ncoef_in, double gain)
 {
     C = C_;
-    int rc = quisk_cuda_resample_design(in_rate, out_rate, fc, ncoef_in, gain, &L, &M, &ncoef, nullptr, 0);
+    int rc = quisk_cuda_resample_design_band(in_rate, out_rate, fc_low, fc, ncoef_in, gain, &L, &M, &ncoef, nullptr, 0);
     if (rc != QC_OK) { set_error("resample: bad rates %d -> %d", in_rate, out_rate); return rc; }
     std::vector<double> h((size_t)ncoef);
-    quisk_cuda_resample_design(in_rate, out_rate, fc, ncoef_in, gain, nullptr, nullptr, nullptr, h.data(), ncoef);
+    quisk_cuda_resample_design_band(in_rate, out_rate, fc_low, fc, ncoef_in, gain, nullptr, nullptr, nullptr, h.data(), ncoef);
     // QC_C_INTERPDECIM indexes coef[ph + k*L] with K = nTaps / L taps per phase and applies gain L;
     // the resampler's prototype already carries gain*L (resample.c:66), so divide it back out exactly
     // by running the filter object with its own gain switched off.

@@ -27,6 +27,7 @@ struct Resampler {
     int C = 0, L = 1, M = 1, ncoef = 0;
     BatchFilter *f = nullptr;
     int init(int C, int in_rate, int out_rate, double fc, int ncoef_in, double gain);
+    int init_band(int C, int in_rate, int out_rate, double fc_low, double fc, int ncoef_in, double gain);   // fc_low >= 0: setFCLow_resample's band pass
     void release();
 };
 
@@ -43,6 +44,14 @@ struct AgcParams {      // the fields of struct _wcpagc that xwcpagc reads (wdsp
            tau_hang_backmult, hang_thresh, tau_hang_decay;
     int n_tau;
 };
+
+// spectral noise blanker (wdsp_snba_nofma.cu)
+struct Snba;
+Snba *make_snba(int C, int inrate, int internalrate, int bsize, int ovrlp, int xsize, int asize, int npasses, double k1, double k2, int b,
+                int pre, int post, double pmultmin, double out_low, double out_high);
+void snba_destroy(Snba *d);
+int snba_run(Snba *d, const cd *in, long is, cd *out, long os, cudaStream_t s);
+int snba_flush(Snba *d);
 
 // spectral noise reduction (wdsp_emnr_nofma.cu)
 struct Emnr;
