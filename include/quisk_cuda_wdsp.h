@@ -164,6 +164,7 @@ int quisk_cuda_rxa_nbp_delete_notch(qcRxa *rxa, int notch);
 int quisk_cuda_rxa_nbp_set_notches_run(qcRxa *rxa, int run);
 int quisk_cuda_rxa_nbp_set_tune_frequency(qcRxa *rxa, double tunefreq);
 int quisk_cuda_rxa_nbp_set_shift_frequency(qcRxa *rxa, double shift);
+int quisk_cuda_rxa_set_snba_run(qcRxa *rxa, int run);                        /* SetRXASNBARun, snb.c:579-593 (bpsnba and bp1 follow: RXAbpsnbaCheck / Set, RXAbp1Check / Set) */
 int quisk_cuda_rxa_set_emnr_run(qcRxa *rxa, int run);                        /* SetRXAEMNRRun, emnr.c:1096-1109 (bp1 follows: RXAbp1Check / RXAbp1Set) */
 int quisk_cuda_rxa_set_emnr_gain_method(qcRxa *rxa, int method);
 int quisk_cuda_rxa_set_emnr_npe_method(qcRxa *rxa, int method);

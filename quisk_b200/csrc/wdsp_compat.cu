@@ -16,7 +16,7 @@
 // plus wdspFexchange0, the re-blocker Quisk's own C side puts in front of fexchange0 (quisk_wdsp.c:24-73).
 // Each open channel number owns one single-channel chain; many receivers at once go through the batched
 // quisk_cuda_rxa_* handle API instead (same chain, same exchange code).  The stages this library does not build (AM /
-// FM squelch, SNBA, ANF, ANR, EQ ...; EMNR / NR2 IS built, wdsp_emnr_nofma.cu) are accepted when switched OFF and refused loudly when switched on.
+// FM squelch, ANF, ANR, EQ ...; NR2 and SNB ARE built: wdsp_emnr_nofma.cu, wdsp_snba_nofma.cu) are accepted when switched OFF and refused loudly when switched on.
 #include "wdsp_internal.h"
 #include <chrono>
 #include <cmath>
@@ -181,7 +181,11 @@ void SetRXAEMNRgainMethod(int channel, int method) { CH("SetRXAEMNRgainMethod") 
 void SetRXAEMNRnpeMethod(int channel, int method) { CH("SetRXAEMNRnpeMethod") return; quisk_cuda_rxa_set_emnr_npe_method(as_handle(r), method); }
 void SetRXAEMNRaeRun(int channel, int run) { CH("SetRXAEMNRaeRun") return; quisk_cuda_rxa_set_emnr_ae_run(as_handle(r), run); }
 void SetRXAEMNRPosition(int channel, int position) { CH("SetRXAEMNRPosition") return; quisk_cuda_rxa_set_emnr_position(as_handle(r), position); }
-void SetRXASNBARun(int channel, int run) { CH("SetRXASNBARun") return; if (run) unsupported("SetRXASNBARun", channel); }
+void SetRXASNBARun(int channel, int run)
+{   // SNB
+    CH("SetRXASNBARun") return;
+    if (quisk_cuda_rxa_set_snba_run(as_handle(r), run) != QC_OK) fprintf(stderr, "libquisk_cuda: SetRXASNBARun(%d, %d): %s\n", channel, run, quisk_cuda_last_error());
+}
 void SetRXAANFRun(int channel, int run) { CH("SetRXAANFRun") return; if (run) unsupported("SetRXAANFRun", channel); }
 void SetRXAANRRun(int channel, int run) { CH("SetRXAANRRun") return; if (run) unsupported("SetRXAANRRun", channel); }
 #undef CH

@@ -52,6 +52,7 @@ Snba *make_snba(int C, int inrate, int internalrate, int bsize, int ovrlp, int x
 void snba_destroy(Snba *d);
 int snba_run(Snba *d, const cd *in, long is, cd *out, long os, cudaStream_t s);
 int snba_flush(Snba *d);
+int snba_set_output_bandwidth(Snba *d, double flow, double fhigh);
 
 // spectral noise reduction (wdsp_emnr_nofma.cu)
 struct Emnr;
@@ -120,8 +121,17 @@ struct Rxa {
     // amd / fmd
     int amd_run = 0, amd_mode = 0; SeqStage *amd = nullptr;
     int fmd_run = 0, fm_nc_de = 0, fm_nc_aud = 0; SeqStage *fmpll = nullptr, *sntch = nullptr; FirCore *pde = nullptr, *paud = nullptr;
+    // xsnba and the band pass that goes with it (xbpsnbain / xbpsnbaout, snb.c:700-827; RXAbpsnbaCheck / RXAbpsnbaSet, RXA.c:829-918)
+    int snba_run = 0; Snba *snba = nullptr;
+    FirCore *bpsnba = nullptr; int bps_nc = 0, bps_run = 0, bps_position = 0, bps_run_notches = 0, bps_hadnotch = 0;
+    double bps_flow = -5700.0, bps_fhigh = -250.0; cd *bps_buff = nullptr;
+    int bpsnba_impulse(std::vector<double> &imp, int *havnotch);
+    int make_bpsnba();
+    int bpsnba_check(int mode, int notch_run);
+    int bpsnba_set();
     int emnr_run = 0, emnr_position = 0, emnr_gain_method = 2; Emnr *emnr = nullptr;      // xemnr, RXA.c:319-332, 577-590
     int emnr_run_stage(cd *m, long ms, cudaStream_t s);
+    int snba_run_stage(cd *m, long ms, cudaStream_t s);
     int bp1_check_set();                                                                    // RXAbp1Check + RXAbp1Set, RXA.c:800-827
     int lim_run = 0; double lim_pre_gain = 0.4, lim_gain = 2.5; SeqStage *plim = nullptr;     // fmd's detector limiter (fmd.c:106-108, 179-184)
     int fm_limiter(cd *m, long ms, int n, cudaStream_t s);

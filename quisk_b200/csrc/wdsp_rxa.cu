@@ -103,6 +103,55 @@ int Rxa::make_nbp0()
     return nbp0 ? QC_OK : QC_EINVAL;
 }
 
+int Rxa::bpsnba_impulse(std::vector<double> &imp, int *havnotch)
+{   // calc_nbp_impulse of the nbp inside bpsnba (snb.c:706-727, 807-821): gain 1, wintype 0, the channel's notch database
+    imp.assign((size_t)2 * bps_nc, 0.0);
+    if (havnotch) *havnotch = 0;
+    const double scale = 1.0 / (double)(2 * dsp_size);
+    if (!bps_run_notches) return quisk_cuda_fir_bandpass(bps_nc, bps_flow, bps_fhigh, (double)dsp_rate, 0, 1, scale, imp.data());
+    return quisk_cuda_nbp_impulse(bps_nc, bps_flow, bps_fhigh, (double)dsp_rate, 0, scale, (int)ndb_fcenter.size(),
+                                  ndb_fcenter.data(), ndb_fwidth.data(), ndb_active.data(), ndb_tune, ndb_shift, 1, 1025, imp.data(), nullptr, havnotch);
+}
+
+int Rxa::make_bpsnba()
+{
+    std::vector<double> imp;
+    int rc = bpsnba_impulse(imp, &bps_hadnotch); if (rc != QC_OK) return rc;
+    if (bpsnba) { bpsnba->release(); delete bpsnba; }
+    bpsnba = new_fircore(C, dsp_size, bps_nc, imp);
+    return bpsnba ? QC_OK : QC_EINVAL;
+}
+
+int Rxa::bpsnba_check(int mode_, int notch_run)
+{   // RXAbpsnbaCheck, RXA.c:829-881: the band follows the mode's side band between 250 and 5700 Hz; new masks wait for the update
+    const double abs_low = 250.0, abs_high = 5700.0;
+    double f_low = 0.0, f_high = 0.0;
+    int run_notches = 0;
+    switch (mode_) {
+    case QC_RXA_LSB: case QC_RXA_CWL: case QC_RXA_DIGL: f_low = -abs_high; f_high = -abs_low; run_notches = notch_run; break;
+    case QC_RXA_USB: case QC_RXA_CWU: case QC_RXA_DIGU: f_low = +abs_low; f_high = +abs_high; run_notches = notch_run; break;
+    case QC_RXA_AM: case QC_RXA_SAM: case QC_RXA_DSB: case QC_RXA_FM: f_low = +abs_low; f_high = +abs_high; run_notches = 0; break;
+    default: break;
+    }
+    if (bps_flow != f_low || bps_fhigh != f_high || bps_run_notches != run_notches) {
+        bps_flow = f_low; bps_fhigh = f_high; bps_run_notches = run_notches;
+        std::vector<double> imp;
+        int rc = bpsnba_impulse(imp, &bps_hadnotch); if (rc != QC_OK) return rc;
+        return bpsnba->set_impulse(imp.data(), 0);
+    }
+    return QC_OK;
+}
+
+int Rxa::bpsnba_set()
+{   // RXAbpsnbaSet, RXA.c:883-918
+    switch (mode) {
+    case QC_RXA_LSB: case QC_RXA_CWL: case QC_RXA_DIGL: case QC_RXA_USB: case QC_RXA_CWU: case QC_RXA_DIGU: bps_run = snba_run; bps_position = 0; break;
+    case QC_RXA_AM: case QC_RXA_SAM: case QC_RXA_DSB: case QC_RXA_FM: bps_run = snba_run; bps_position = 1; break;
+    default: bps_run = 0; break;
+    }
+    return bpsnba->update();
+}
+
 int Rxa::make_bp1()
 {   // create_bandpass (bandpass.c:284-306), wintype 1
     std::vector<double> imp((size_t)2 * bp1_nc);
@@ -150,10 +199,14 @@ int Rxa::init(int C_, int in_size_, int dsp_size_, int in_rate_, int dsp_rate_, 
     adcmeter = make_meter(C, dsp_rate, 0.100, 0.100);
     smeter = make_meter(C, dsp_rate, 0.100, 0.100);
     agcmeter = make_meter(C, dsp_rate, 0.100, 0.100);
-    nbp_nc = bp1_nc = fm_nc_de = fm_nc_aud = dsp_size > 2048 ? dsp_size : 2048;       // max(2048, dsp_size)
+    nbp_nc = bp1_nc = bps_nc = fm_nc_de = fm_nc_aud = dsp_size > 2048 ? dsp_size : 2048;       // max(2048, dsp_size)
     int rc;
     if ((rc = make_nbp0()) != QC_OK) return rc;
     if ((rc = make_bp1()) != QC_OK) return rc;
+    if ((rc = make_bpsnba()) != QC_OK) return rc;
+    QC_CUDA(cudaMalloc((void **)&bps_buff, (size_t)C * dsp_size * sizeof(cd)));
+    QC_CUDA(cudaMemset(bps_buff, 0, (size_t)C * dsp_size * sizeof(cd)));
+    snba = make_snba(C, dsp_rate, 12000, dsp_size, 4, 256, 64, 2, 8.0, 20.0, 10, 2, 2, 0.5, 200.0, 5400.0);     // create_rxa's arguments, RXA.c:237-255
     amd = make_amd(C, dsp_rate, 0, 1, 0);
     fmpll = make_fmpll(C, dsp_rate, 5000.0, -8000.0, +8000.0, 1.0, 20000.0, 0.02);
     sntch = make_snotch(C, dsp_rate, 254.1, 0.0002);
@@ -183,6 +236,9 @@ static int raise_upflag(Rxa &r)
 void Rxa::release()
 {
     if (emnr) { emnr_destroy(emnr); emnr = nullptr; }
+    if (snba) { snba_destroy(snba); snba = nullptr; }
+    if (bpsnba) { bpsnba->release(); delete bpsnba; bpsnba = nullptr; }
+    if (bps_buff) { cudaFree(bps_buff); bps_buff = nullptr; }
     for (SeqStage **p : {&shift, &adcmeter, &smeter, &agcmeter, &amd, &fmpll, &sntch, &agc, &plim}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     for (FirCore **p : {&nbp0, &bp1, &pde, &paud}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
     for (Resampler **p : {&rsmpin, &rsmpout}) if (*p) { (*p)->release(); delete *p; *p = nullptr; }
@@ -205,10 +261,11 @@ void Rxa::release()
 }
 
 int Rxa::emnr_run_stage(cd *m, long ms, cudaStream_t s) { return qc::emnr_run(emnr, m, ms, m, ms, s); }
+int Rxa::snba_run_stage(cd *m, long ms, cudaStream_t s) { return qc::snba_run(snba, m, ms, m, ms, s); }
 
 int Rxa::bp1_check_set()
 {   // RXAbp1Check (gain 2 when the AM demodulator or a noise reducer feeds bp1; new masks wait for setUpdate) + RXAbp1Set
-    const int feeds = amd_run || emnr_run;
+    const int feeds = amd_run || snba_run || emnr_run;
     const double gain = feeds ? 2.0 : 1.0;
     if (bp1_gain != gain) {
         bp1_gain = gain;
@@ -232,7 +289,7 @@ int Rxa::fm_limiter(cd *m, long ms, int n, cudaStream_t s)
 int Rxa::xrxa_multi(const void *din, long is, void *dout, long os, int nblocks, cudaStream_t s)
 {   // nblocks consecutive DSP blocks per channel: block b of a channel at in + b * dsp_insize, out + b * dsp_outsize
     if (nblocks <= 0) return QC_OK;
-    if (emnr_run) {         // the noise reducer frames its own stream: block by block through the per-stage chain
+    if (emnr_run || snba_run) {         // the noise reducer / blanker frame their own streams: block by block through the per-stage chain
         for (int b = 0; b < nblocks; b++) {
             int rc = xrxa((const cd *)din + (size_t)b * dsp_insize, is, (cd *)dout + (size_t)b * dsp_outsize, os, s);
             if (rc != QC_OK) return rc;
@@ -366,14 +423,19 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
         rc = rsmpin->f->run(cur, cs, dsp_insize, m, ms, &no, 0, s); if (rc) return rc;
         if (no != dsp_size) { set_error("rxa: input resampler produced %d samples, dsp_size is %d", no, dsp_size); return QC_EINVAL; }
         rc = adcmeter->run(m, ms, nullptr, 0, dsp_size, s); if (rc) return rc;
+        // xbpsnbain(0): the block as it enters nbp0 (snb.c:795-799)
+        if (bps_run && bps_position == 0) QC_CUDA(cudaMemcpy2DAsync(bps_buff, (size_t)dsp_size * sizeof(cd), m, (size_t)ms * sizeof(cd), (size_t)dsp_size * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
         if (nbp_run) { rc = nbp0->run(m, ms, m, ms, s); if (rc) return rc; }
     } else {
         // no input resampler: the first stage that writes moves the block into midbuff, no separate copy
         rc = adcmeter->run(cur, cs, nullptr, 0, dsp_size, s); if (rc) return rc;
+        if (bps_run && bps_position == 0) QC_CUDA(cudaMemcpy2DAsync(bps_buff, (size_t)dsp_size * sizeof(cd), cur, (size_t)cs * sizeof(cd), (size_t)dsp_size * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
         if (nbp_run) { rc = nbp0->run(cur, cs, m, ms, s); if (rc) return rc; }
         else QC_CUDA(cudaMemcpy2DAsync(m, (size_t)ms * sizeof(cd), cur, (size_t)cs * sizeof(cd), (size_t)dsp_size * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
     }
     rc = smeter->run(m, ms, nullptr, 0, dsp_size, s); if (rc) return rc;
+    // xbpsnbaout(0): its own band pass of the saved block REPLACES nbp0's output (snb.c:801-805)
+    if (bps_run && bps_position == 0) { rc = bpsnba->run(bps_buff, dsp_size, m, ms, s); if (rc) return rc; }
     if (amd_run) { rc = amd->run(m, ms, m, ms, dsp_size, s); if (rc) return rc; }
     if (fmd_run) {
         rc = fmpll->run(m, ms, audio, dsp_size, dsp_size, s); if (rc) return rc;       // pll -> audio
@@ -382,6 +444,12 @@ int Rxa::xrxa(const void *din, long is, void *dout, long os, cudaStream_t s)
         rc = sntch->run(m, ms, m, ms, dsp_size, s); if (rc) return rc;                 // CTCSS notch (I rail)
         rc = fm_limiter(m, ms, dsp_size, s); if (rc) return rc;
     }
+    // xbpsnbain(1) + xbpsnbaout(1): behind the demodulators in the AM / FM modes (RXA.c:576-577)
+    if (bps_run && bps_position == 1) {
+        QC_CUDA(cudaMemcpy2DAsync(bps_buff, (size_t)dsp_size * sizeof(cd), m, (size_t)ms * sizeof(cd), (size_t)dsp_size * sizeof(cd), C, cudaMemcpyDeviceToDevice, s));
+        rc = bpsnba->run(bps_buff, dsp_size, m, ms, s); if (rc) return rc;
+    }
+    if (snba_run) { rc = snba_run_stage(m, ms, s); if (rc) return rc; }
     // xemnr / xbandpass(bp1) at position 0 in front of the AGC, at position 1 behind it (RXA.c:577-590)
     if (emnr_run && emnr_position == 0) { rc = emnr_run_stage(m, ms, s); if (rc) return rc; }
     if (bp1_run && emnr_position == 0) { rc = bp1->run(m, ms, m, ms, s); if (rc) return rc; }
@@ -469,6 +537,8 @@ int Rxa::flush_main()
     for (SeqStage *q : {shift, adcmeter, smeter, amd, fmpll, sntch, plim, agc, agcmeter}) if (q) { rc = q->flush_ref(); if (rc) return rc; }
     for (FirCore *f : {nbp0, pde, paud, bp1}) if (f) { rc = f->flush(); if (rc) return rc; }
     if (emnr) { rc = emnr_flush(emnr); if (rc) return rc; }
+    if (snba) { rc = snba_flush(snba); if (rc) return rc; }
+    if (bpsnba) { rc = bpsnba->flush(); if (rc) return rc; QC_CUDA(cudaMemset(bps_buff, 0, (size_t)C * dsp_size * sizeof(cd))); }
     for (Resampler *q : {rsmpin, rsmpout}) if (q) { rc = q->f->reset(nullptr); if (rc) return rc; }
     QC_CUDA(cudaMemset(d_sip, 0, (size_t)C * sipsize * sizeof(cd)));
     sip_idx = 0;
@@ -612,11 +682,13 @@ int quisk_cuda_rxa_set_mode(qcRxa *p, int mode)
     if (!p) return QC_EINVAL;
     Rxa &r = p->r;
     if (r.mode == mode) return QC_OK;
+    { int rcb = r.bpsnba_check(mode, r.ndb_run); if (rcb) return rcb; }        // RXA.c:754
     r.mode = mode;
     r.amd_run = 0; r.fmd_run = 0; r.agc_run = 1;
     if (mode == QC_RXA_AM) { r.amd_run = 1; r.amd->par[0] = 0; }
     else if (mode == QC_RXA_SAM) { r.amd_run = 1; r.amd->par[0] = 1; }
     else if (mode == QC_RXA_FM) { r.fmd_run = 1; r.agc_run = 0; }
+    { int rcb = r.bpsnba_set(); if (rcb) return rcb; }                          // RXA.c:784
     return r.bp1_check_set();       // RXAbp1Check + RXAbp1Set, RXA.c:800-827
 }
 
@@ -631,6 +703,7 @@ int quisk_cuda_rxa_set_passband(qcRxa *p, double f_low, double f_high)
         r.bp1_flow = f_low; r.bp1_fhigh = f_high;
         r.bp1->update();
     }
+    if (r.snba) { int rcs = qc::snba_set_output_bandwidth(r.snba, f_low, f_high); if (rcs) return rcs; }     // SetRXASNBAOutputBandwidth, RXA.c:930
     if (f_low != r.nbp_flow || f_high != r.nbp_fhigh) {
         r.nbp_flow = f_low; r.nbp_fhigh = f_high;
         std::vector<double> imp;
@@ -647,9 +720,24 @@ int quisk_cuda_rxa_set_nc(qcRxa *p, int nc)
     if (nc < r.dsp_size || nc % r.dsp_size) { set_error("rxa_set_nc: nc must be a multiple of dsp_size"); return QC_EINVAL; }
     int rc;
     if (r.nbp_nc != nc) { r.nbp_nc = nc; if ((rc = r.make_nbp0()) != QC_OK) return rc; }
+    if (r.bps_nc != nc) { r.bps_nc = nc; if ((rc = r.make_bpsnba()) != QC_OK) return rc; }      // RXABPSNBASetNC, snb.c:829-842
     if (r.bp1_nc != nc) { r.bp1_nc = nc; if ((rc = r.make_bp1()) != QC_OK) return rc; }
     if (r.fm_nc_de != nc || r.fm_nc_aud != nc) { r.fm_nc_de = r.fm_nc_aud = nc; if ((rc = r.make_fmd()) != QC_OK) return rc; }
     return QC_OK;
+}
+
+int quisk_cuda_rxa_set_snba_run(qcRxa *p, int run)
+{   // SetRXASNBARun, snb.c:579-593
+    if (!p) return QC_EINVAL;
+    qc::Rxa &r = p->r;
+    run = run ? 1 : 0;
+    if (r.snba_run == run) return QC_OK;
+    if (run && !r.snba) { qc::set_error("SetRXASNBARun: the noise blanker needs dsp_rate = 12000 x an integer and a dsp_size that divides accordingly"); return QC_EINVAL; }
+    int rc = r.bpsnba_check(r.mode, r.ndb_run); if (rc) return rc;
+    r.snba_run = run;
+    // RXAbp1Check before the flag flips in the reference, RXAbp1Set after: the helper does both from the new flags
+    rc = r.bp1_check_set(); if (rc) return rc;
+    return r.bpsnba_set();
 }
 
 int quisk_cuda_rxa_set_emnr_run(qcRxa *p, int run)
@@ -708,6 +796,13 @@ int quisk_cuda_rxa_set_shift(qcRxa *p, int run, const double *shift_hz)
 static int nbp_update(Rxa &r, bool lightweight)
 {   // UpdateNBPFilters (always recompute when the notches run) / UpdateNBPFiltersLightWeight (tune or shift moved:
     // recompute only if there were or are notches inside the pass band, nbp.c:181-212)
+    if (r.bps_run_notches) {        // the band pass of the noise blanker follows the same database (nbp.c:339, 345-355)
+        std::vector<double> bi;
+        int hb = 0;
+        int rcb = r.bpsnba_impulse(bi, &hb); if (rcb != QC_OK) return rcb;
+        if (!lightweight || r.bps_hadnotch || hb) { rcb = r.bpsnba->set_impulse(bi.data(), 1); if (rcb != QC_OK) return rcb; }
+        r.bps_hadnotch = hb;
+    } else if (lightweight) r.bps_hadnotch = 1;
     if (!r.ndb_run) { if (lightweight) r.nbp_hadnotch = 1; return QC_OK; }
     std::vector<double> imp;
     int hav = 0;
@@ -746,10 +841,12 @@ int quisk_cuda_rxa_nbp_set_notches_run(qcRxa *p, int run)
     Rxa &r = p->r;
     run = run ? 1 : 0;
     if (run == r.ndb_run) return QC_OK;
+    { int rcb = r.bpsnba_check(r.mode, run); if (rcb) return rcb; }            // nbp.c:504
     r.ndb_run = run;
     std::vector<double> imp;
     int rc = r.nbp0_impulse(imp, &r.nbp_hadnotch); if (rc != QC_OK) return rc;
-    return r.nbp0->set_impulse(imp.data(), 1);
+    rc = r.nbp0->set_impulse(imp.data(), 1); if (rc != QC_OK) return rc;
+    return r.bpsnba_set();                                                         // nbp.c:509
 }
 
 int quisk_cuda_rxa_nbp_set_tune_frequency(qcRxa *p, double tunefreq)

@@ -945,7 +945,7 @@ size_t rxa_fused_smem(int n, int ab)
 // a power of two <= 1024, nc / dsp_size partitions; anything else runs the per-stage kernels.
 bool Rxa::fusable() const
 {
-    if (!fused_ok || (shift_run && shift_nonzero) || rsmpin || rsmpout || amd_run || fmd_run || emnr_run) return false;
+    if (!fused_ok || (shift_run && shift_nonzero) || rsmpin || rsmpout || amd_run || fmd_run || emnr_run || snba_run) return false;
     if (dsp_size > 1024 || dsp_size < 8 || (dsp_size & (dsp_size - 1))) return false;
     const int ab = agc_run && agc->agc.mode != 0 ? agc->agc.attack_buffsize : 0;
     if (agc_run && agc->agc.mode == 5) return false;

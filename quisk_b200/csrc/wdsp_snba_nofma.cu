@@ -369,7 +369,7 @@ struct Snba {
     double *d_state = nullptr;
     cd *d_inbuff = nullptr, *d_outbuff = nullptr;
     Resampler *inres = nullptr, *outres = nullptr;
-    double out_low_cut = 0, out_high_cut = 0;
+    double out_low_cut = 0, out_high_cut = 0, out_fc_low = 200.0, out_fc = 0.0;        // the output resampler's current band (setFCLow 200, fc 0 = 0.45 min rate)
     int iainidx = 0, iaoutidx = 0, nsamps = 0, oainidx = 0, oaoutidx = 0, init_oaoutidx = 0;
 
     int init(int C_, int inrate_, int internalrate_, int bsize_, int ovrlp, int xsize, int asize, int npasses, double k1, double k2, int b,
@@ -462,6 +462,37 @@ struct Snba {
         return QC_OK;
     }
 };
+
+int snba_set_output_bandwidth(Snba *d, double flow, double fhigh)
+{   // SetRXASNBAOutputBandwidth, snb.c:660-696: the output resampler becomes a band pass inside [out_low_cut, out_high_cut]
+    double f_low = 0.0, f_high = 0.0;
+    bool set = false;
+    auto mx = [](double a, double b) { return a > b ? a : b; };
+    auto mn = [](double a, double b) { return a < b ? a : b; };
+    if (flow >= 0 && fhigh >= 0) {
+        if (fhigh < d->out_low_cut) fhigh = d->out_low_cut;
+        if (flow > d->out_high_cut) flow = d->out_high_cut;
+        f_low = mx(d->out_low_cut, flow); f_high = mn(d->out_high_cut, fhigh); set = true;
+    } else if (flow <= 0 && fhigh <= 0) {
+        if (flow > -d->out_low_cut) flow = -d->out_low_cut;
+        if (fhigh < -d->out_high_cut) fhigh = -d->out_high_cut;
+        f_low = mx(d->out_low_cut, -fhigh); f_high = mn(d->out_high_cut, -flow); set = true;
+    } else if (flow < 0 && fhigh > 0) {
+        double absmax = mx(-flow, fhigh);
+        if (absmax < d->out_low_cut) absmax = d->out_low_cut;
+        f_low = d->out_low_cut; f_high = mn(d->out_high_cut, absmax); set = true;
+    }
+    (void)set;      // (the reference passes whatever f_low / f_high hold: both zero when no branch applied)
+    if (!d->outres) return QC_OK;                           // no resamplers at the internal rate: setBandwidth_resample only touches the (unused) design
+    if (f_low == d->out_fc_low && f_high == d->out_fc) return QC_OK;
+    if (cudaDeviceSynchronize() != cudaSuccess) return QC_ECUDA;
+    Resampler *nr = new Resampler();
+    int rc = nr->init_band(d->C, d->internalrate, d->inrate, f_low, f_high, 0, 2.0);       // setBandwidth_resample: decalc + calc, state zeroed
+    if (rc != QC_OK) { nr->release(); delete nr; return rc; }
+    d->outres->release(); delete d->outres;
+    d->outres = nr; d->out_fc_low = f_low; d->out_fc = f_high;
+    return QC_OK;
+}
 
 Snba *make_snba(int C, int inrate, int internalrate, int bsize, int ovrlp, int xsize, int asize, int npasses, double k1, double k2, int b,
                 int pre, int post, double pmultmin, double out_low, double out_high)

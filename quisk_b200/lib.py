@@ -182,6 +182,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rxa_nbp_set_notches_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rxa_nbp_set_tune_frequency.argtypes = [vp, D]
     lib.quisk_cuda_rxa_nbp_set_shift_frequency.argtypes = [vp, D]
+    lib.quisk_cuda_rxa_set_snba_run.argtypes = [vp, C.c_int]
     lib.quisk_cuda_snba_create.argtypes = [C.c_int] * 8 + [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     lib.quisk_cuda_snba_create.restype = vp
     lib.quisk_cuda_snba_destroy.argtypes = [vp]; lib.quisk_cuda_snba_destroy.restype = None

@@ -1,7 +1,7 @@
 """tests/quisk_swapin_driver.py -- run the reference's WHOLE _quisk extension on a synthetic block source.
 
 Subprocess helper of tests/test_quisk_swapin_gpu.py (TEST INFRASTRUCTURE).  argv: <build dir with _quisk.so>
-<out.npz> <rate> <mode> <tune_hz> <n_samples> <block> <wdsp: 0 | 1 | 2 | 3> <dc_remove_bw>.  It does what quisk.py does at start-up, in the
+<out.npz> <rate> <mode> <tune_hz> <n_samples> <block> <wdsp: 0 | 1 | 2 | 3 | 4> <dc_remove_bw>.  It does what quisk.py does at start-up, in the
 same order and through the same Python methods of _quisk (record_app, set_sound_name, open_sound, set_filters,
 set_rx_mode, set_tune, set_volume, start_sound), registers the B4 block source (quisk_block_source.open_samples ->
 quisk_sample_source4), then calls read_sound() until the source is dry: quisk_read_sound (sound.c:873) ->
@@ -78,8 +78,14 @@ def main():
                 assert wl.quisk_cuda_emnr_set_tables(ctypes.c_void_p(ctypes.addressof(gg)), ctypes.c_void_p(ctypes.addressof(ggs))) == 0
             wl.SetRXAEMNRgainMethod(ch, 2)
             wl.SetRXAEMNRRun(ch, 1)
+        if use_wdsp == 4:       # Quisk's SNB menu item (quisk.py:6040-6043): SetRXASNBARun(1), in_use = 1
+            wl.SetRXASNBARun(ch, 1)
         QS.wdsp_set_parameter(ch, in_use=1)
     x = O.synth_iq(n_samples, 77, 1.0)
+    if os.environ.get("QUISK_SWAPIN_ULP"):      # the reference's own conditioning: the same stream with every sample moved by at most one ulp
+        v = np.ascontiguousarray(x).view(np.float64)
+        step = np.random.default_rng(int(os.environ["QUISK_SWAPIN_ULP"])).integers(-1, 2, v.shape)
+        x = (v + step * np.spacing(v)).view(np.complex128)
     assert SRC.load(np.ascontiguousarray(x).tobytes(), block) == n_samples
     QS.start_sound()
     graphs, reads = [], []
