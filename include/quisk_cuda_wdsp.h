@@ -208,7 +208,7 @@ int quisk_cuda_rxa_get_meter(qcRxa *r, int which, double *av, double *pk, double
  * version.c:4, RXA.c:749-958, shift.c:112-128, nbp.c:359-527, wcpAGC.c:370-548, patchpanel.c:125-156, amd.c:279-293,
  * meter.c:120, siphon.c:183-211 -- `ctypes.CDLL("libquisk_cuda.so")` in place of "./wdsp/libwdsp.so" (INTEGRATION.md
  * section 2).  One single-channel chain per open channel number, MAX_CHANNELS = 32.  The stages this library does not
- * build (squelches, EMNR, SNBA, ANF, ANR) are accepted switched off and refused with a message when switched on.
+ * build (squelches, ANF, ANR; EMNR and SNBA ARE built) are accepted switched off and refused with a message when switched on.
  * ------------------------------------------------------------------------------------------------------------------ */
 int GetWDSPVersion(void);
 void OpenChannel(int channel, int in_size, int dsp_size, int input_samplerate, int dsp_rate, int output_samplerate,

@@ -82,7 +82,16 @@ def test_whole_quisk_with_wdsp_channel_on_gpu(wdsp, tmp_path):
     on this noise-like stream the all-reference build itself moves by 2e-8 when every input sample moves by at most one ulp
     (measured here, third run), and the bound for that case is 20 x that."""
     rate, mode, tune, n, block = 48000, 3, 2000, 100000, 1000
-    ref = _run("ref", tmp_path, "wdsp", rate, mode, tune, n, block, wdsp=wdsp, wdsp_lib=os.path.join(R.REF_DIR, "libwdsp_ref.so"))
+    # The reference's exchange posts Sem_OutReady BEFORE it copies the next input block out of its two-block ring
+    # (iobuffs.c:595-602): when its DSP thread is descheduled right there (a loaded host), the caller overwrites that block
+    # and the reference's output is not a function of its input any more.  Two reference runs that agree rule that out.
+    for attempt in range(3):
+        ref = _run("ref", tmp_path, "wdsp", rate, mode, tune, n, block, wdsp=wdsp, wdsp_lib=os.path.join(R.REF_DIR, "libwdsp_ref.so"))
+        again = _run("ref", tmp_path, "wdsp_again", rate, mode, tune, n, block, wdsp=wdsp, wdsp_lib=os.path.join(R.REF_DIR, "libwdsp_ref.so"))
+        if np.array_equal(ref["audio"], again["audio"]):
+            break
+    else:
+        pytest.skip("the reference's WDSP exchange raced three times in a row on this host (iobuffs.c:595-602): no stable reference output")
     gpu = _run("cuda", tmp_path, "wdsp", rate, mode, tune, n, block, wdsp=wdsp, wdsp_lib=os.path.join(ROOT, "quisk_b200", "libquisk_cuda.so"))
     plain = _run("ref", tmp_path, "nowdsp", rate, mode, tune, n, block, wdsp=0)
     assert len(ref["audio"]) == len(gpu["audio"]) and len(ref["audio"]) > 0.9 * n
