@@ -16,6 +16,7 @@
 // taps it stages the needed slice of [history | block] and the chunk's taps in
 // shared memory (coalesced 16-byte loads), then every thread walks its own
 // output's taps out of shared memory.
+#include <cstdlib>
 #include "qc_common.cuh"
 
 namespace qc {
@@ -233,6 +234,74 @@ __global__ void __launch_bounds__(NT) decim_rb_kernel(PolyFirParams p, int tiles
     for (int r = 0; r < R; r++) if (m0 + tid * R + r < p.n_out) o[r] = scale(acc[r], p.gain);
 }
 
+// ---- the same for M = 8, R = 4 with the taps in registers.  Output r meets the sample of step j at tap hp[j + 8 r], so the
+// taps of step j + 8 are the taps of step j moved down by one output: for each of the 8 residues s = j mod 8 a window of
+// R = 4 taps slides by one per 8 steps.  With the 8 x 4 window in registers (the loop body is 32 steps, every index static)
+// a step costs ONE shared-memory tap load (broadcast) instead of four; with the sample load that is 5 wavefronts per warp
+// and step instead of 8 -- at R = 4 the generic form above asks shared memory for exactly its peak (32 wavefronts per 32
+// cycles and SM when the FP64 pipe runs flat out: 16 separately rounded instructions per step and lane).  Same products,
+// same sums, same order: bit-identical.  The step count is padded to a multiple of 32 with zero taps (they add +0).
+template <int NT>
+__global__ void __launch_bounds__(NT, 2) decim_rb8_kernel(PolyFirParams p, int tiles, int pad_sh, int Jpad)
+{
+    constexpr int R = 4, M = 8;
+    extern __shared__ double smem[];
+    const int c = blockIdx.x / tiles, tile = blockIdx.x % tiles, tid = threadIdx.x;
+    const int K = p.K;
+    const int m0 = tile * NT * R;
+    if (tile == 0) write_hist<cd>(p, c);
+    if (m0 >= p.n_out) return;
+    constexpr int zpad = M * (R - 1);
+    double *hp = smem;                                          // [Jpad + M R + 8] zero-padded taps
+    const int nh = Jpad + M * R + 8;
+    cd *sX = reinterpret_cast<cd *>(smem + ((nh + 1) & ~1));
+    for (int i = tid; i < nh; i += NT) hp[i] = (i >= zpad && i < zpad + K) ? p.coef[i - zpad] : 0.0;
+    const long lo = p.u0 + (long)m0 * M - (K - 1);
+    const int nx = (NT * R - 1) * M + K;
+    if (lo >= 0 && lo + nx <= p.n_in) {
+        const cd *g = reinterpret_cast<const cd *>(p.in) + (long)c * p.in_stride + lo;
+        for (int i0 = tid; i0 < nx; i0 += 8 * NT) {
+            cd v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + u * NT; if (i < nx) v[u] = g[i]; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + u * NT; if (i < nx) sX[i + (i >> pad_sh)] = v[u]; }
+        }
+    } else {
+        for (int i = tid; i < nx; i += NT) sX[i + (i >> pad_sh)] = load_x<cd>(p, c, lo + i);
+    }
+    __syncthreads();
+    cd acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = make_double2(0.0, 0.0);
+    const int top = (tid * R + R - 1) * M + (K - 1);
+    double W[M][R];                                             // W[s][(q + r) & 3] = hp[8 q + s + 8 r]
+#pragma unroll
+    for (int s_ = 0; s_ < M; s_++)
+#pragma unroll
+        for (int r = 0; r < R; r++) W[s_][r] = hp[s_ + M * r];
+    for (int j0 = 0; j0 < Jpad; j0 += M * R) {
+#pragma unroll
+        for (int qq = 0; qq < R; qq++) {
+#pragma unroll
+            for (int s_ = 0; s_ < M; s_++) {
+                const int j = j0 + qq * M + s_;
+                const int idx = max(top - j, 0);
+                const cd x = sX[idx + (idx >> pad_sh)];
+                cd t[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) { const double h = W[s_][(qq + r) & 3]; t[r] = make_double2(mul_rn(x.x, h), mul_rn(x.y, h)); }
+#pragma unroll
+                for (int r = 0; r < R; r++) { acc[r].x = add_rn(acc[r].x, t[r].x); acc[r].y = add_rn(acc[r].y, t[r].y); }
+                W[s_][qq & 3] = hp[j + M * R];                  // output R - 1's tap of step j + 8
+            }
+        }
+    }
+    cd *o = reinterpret_cast<cd *>(p.out) + (long)c * p.out_stride + m0 + tid * R;
+#pragma unroll
+    for (int r = 0; r < R; r++) if (m0 + tid * R + r < p.n_out) o[r] = scale(acc[r], p.gain);
+}
+
 static int launch_decim_rb(const PolyFirParams &p, cudaStream_t stream)
 {
     constexpr int R = 4, NT = 128;
@@ -241,7 +310,25 @@ static int launch_decim_rb(const PolyFirParams &p, cudaStream_t stream)
     if (grid <= 0 || grid > 0x7fffffffL) { set_error("polyfir: grid %ld out of range", grid); return QC_EINVAL; }
     int pad_sh = 0;
     while ((1 << pad_sh) < R * p.M) pad_sh++;
-    const int nh = p.K + 2 * p.M * (R - 1) + 1, nx = (NT * R - 1) * p.M + p.K;
+    const int nx = (NT * R - 1) * p.M + p.K;
+    if (p.M == 8 && !getenv("QUISK_DECIM_RB_GENERIC")) {
+        const int J = p.K + p.M * (R - 1), Jpad = (J + 31) & ~31;
+        const int nh8 = Jpad + 8 * R + 8;
+        const size_t sh8 = (size_t)((nh8 + 1) & ~1) * sizeof(double) + (size_t)(nx + (nx >> pad_sh) + 1) * sizeof(cd);
+        if (sh8 <= 113 * 1024) {
+            auto k8 = decim_rb8_kernel<NT>;
+            if (sh8 > 48 * 1024) {
+                static std::mutex mu8;
+                std::lock_guard<std::mutex> g(mu8);
+                QC_CUDA(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+            }
+            k8<<<(unsigned)grid, NT, sh8, stream>>>(p, tiles, pad_sh, Jpad);
+            count_launch();
+            QC_CUDA_LAUNCH();
+            return QC_OK;
+        }
+    }
+    const int nh = p.K + 2 * p.M * (R - 1) + 1;
     const size_t sh = (size_t)((nh + 1) & ~1) * sizeof(double) + (size_t)(nx + (nx >> pad_sh) + 1) * sizeof(cd);
     if (sh > 200 * 1024) return -100;                            // tile too large for shared memory: the generic kernel takes it
     auto kern = decim_rb_kernel<R, NT>;

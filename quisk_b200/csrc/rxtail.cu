@@ -9,7 +9,7 @@
 
 namespace qc {
 
-static constexpr int TT = 64;       // threads per CTA
+static constexpr int TT_MIN = 64;   // threads per CTA: 64 (blocks up to 256 samples), 128, 256 (long blocks)
 static constexpr int TR = 4;        // receive-filter outputs per thread
 // The filter phase reads X with a lane stride of TR = 4 samples (64 bytes): stored densely that is a 4-way bank
 // conflict on every load, so sample e lives at xp(e) = e + e/4, which sends eight consecutive lanes to eight
@@ -37,6 +37,7 @@ __constant__ double c_hbt[12] = {        // filter.c:381-384
     -0.096214669073304823, 0.314881034738348550, 0.500000000000000000 };
 
 // half-band x2 on a shared-memory line: in[H + i] (H = 22 history), i < cnt -> out[2i], out[2i+1]
+template <int TT>
 __device__ __forceinline__ void hb_interp_line(const double *in, int cnt, double *out, bool to_global)
 {
     for (int i = threadIdx.x; i < cnt; i += TT) {
@@ -50,6 +51,7 @@ __device__ __forceinline__ void hb_interp_line(const double *in, int cnt, double
     (void)to_global;
 }
 
+template <int TT>
 __global__ void __launch_bounds__(TT) rx_tail_kernel(TailParams P)
 {
     extern __shared__ double sm_raw[];
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(TT) rx_tail_kernel(TailParams P)
     double *D = reinterpret_cast<double *>(hc + N4);                // [i_H + n]
     double *ic = D + P.i_H + n;                                     // [ntap_i]
     double *E = ic + P.ntap_i;                                      // [22 + 2n]
-    double *F = E + 22 + 2 * n;                                     // [22 + 4n] (CW only)
+    double *F = E + 22 + 2 * n;                                     // [22 + 4n] (CW only: not allocated otherwise)
     // ---- stage
     const cd *gh = P.rx_hin + (size_t)c * Hx;
     for (int i = tid; i < XO; i += TT) X[xp(i)] = make_double2(0.0, 0.0);
@@ -122,11 +124,11 @@ __global__ void __launch_bounds__(TT) rx_tail_kernel(TailParams P)
     // ---- half band(s)
     double *go = P.out + (size_t)c * P.out_stride;
     if (P.n_hb == 1) {
-        hb_interp_line(E, 2 * n, go, true);
+        hb_interp_line<TT>(E, 2 * n, go, true);
     } else {
-        hb_interp_line(E, 2 * n, F + 22, false);
+        hb_interp_line<TT>(E, 2 * n, F + 22, false);
         __syncthreads();
-        hb_interp_line(F, 4 * n, go, true);
+        hb_interp_line<TT>(F, 4 * n, go, true);
     }
     // ---- histories: last N-1 filter inputs, last i_H interpolator inputs, last 22 half-band inputs
     cd *oh = P.rx_hout + (size_t)c * Hx;
@@ -169,10 +171,14 @@ int RxChain::run_tail(const cd *in, long in_stride, int n, double *out, long out
     const int nout = n * 2 * (P.n_hb == 2 ? 4 : 2);
     if (out_stride < nout) { set_error("rx_process: audio_stride %ld < %d", out_stride, nout); return QC_EINVAL; }
     const size_t sh = (size_t)(xp(8 + P.N - 1 + n + TR) + 1) * sizeof(cd) + (size_t)((P.N + 3) & ~3) * sizeof(double2) +
-                      (size_t)(P.i_H + n + P.ntap_i + 22 + 2 * n + 22 + 4 * n + 8) * sizeof(double);
+                      (size_t)(P.i_H + n + P.ntap_i + 22 + 2 * n + (P.n_hb == 2 ? 22 + 4 * n : 0) + 8) * sizeof(double);
     if (sh > 200 * 1024) return QC_ENOMEM;           // caller falls back to the per-stage kernels
-    if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rx_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    rx_tail_kernel<<<C, TT, sh, s>>>(P);
+    // one CTA per channel whatever the block length: long blocks (the 192 kS/s receivers hand over 2048 samples) get more threads
+#define QC_TAIL(TT_) do { \
+        if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rx_tail_kernel<TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); \
+        rx_tail_kernel<TT_><<<C, TT_, sh, s>>>(P); } while (0)
+    if (n <= TT_MIN * TR) QC_TAIL(64); else if (n <= 2 * TT_MIN * TR) QC_TAIL(128); else QC_TAIL(256);
+#undef QC_TAIL
     count_launch();
     QC_CUDA_LAUNCH();
     rxf->cur ^= 1;
