@@ -575,6 +575,13 @@ __global__ void __launch_bounds__(256) fir_fwd_kernel(const cd *in, long in_stri
     for (int i = tid; i < n2; i += nt) sp[i] = S[fsw(i)];
 }
 
+__device__ __forceinline__ cd fir_mac_first(cd X, cd m) { return make_double2(X.x * m.x - X.y * m.y, X.x * m.y + X.y * m.x); }
+__device__ __forceinline__ void fir_mac_add(cd &acc, cd Y, cd m)
+{
+    acc.x += Y.x * m.x - Y.y * m.y;
+    acc.y += Y.x * m.y + Y.y * m.x;
+}
+
 __global__ void __launch_bounds__(256) fir_mac_kernel(const cd *spec, int nblocks, int n, int nfor, int bi0, const cd *fdl /*[C][nfor][2n]*/,
                                                        const cd *__restrict__ fmask, cd *out, long out_stride, const cd *tw)
 {
@@ -589,13 +596,12 @@ __global__ void __launch_bounds__(256) fir_mac_kernel(const cd *spec, int nblock
     for (int i = tid; i < n2; i += nt) {
         const cd X = sp[(size_t)b * n2 + i];
         const cd m0 = fmask[i];
-        cd acc = make_double2(X.x * m0.x - X.y * m0.y, X.x * m0.y + X.y * m0.x);
+        cd acc = fir_mac_first(X, m0);
         for (int j = 1; j < nfor; j++) {
             // the spectrum of j blocks ago: this launch's if there is one, else the delay line's (ring index bi0 is block 0's slot)
             const cd Y = b - j >= 0 ? sp[(size_t)(b - j) * n2 + i] : fd[(size_t)((bi0 + b - j) & mask) * n2 + i];
             const cd m = fmask[(size_t)j * n2 + i];
-            acc.x += Y.x * m.x - Y.y * m.y;
-            acc.y += Y.x * m.y + Y.y * m.x;
+            fir_mac_add(acc, Y, m);
         }
         S[fsw(i)] = acc;
     }
@@ -603,6 +609,60 @@ __global__ void __launch_bounds__(256) fir_mac_kernel(const cd *spec, int nblock
     fft_smem<1>(S, n2, twl, +1, tid, nt);
     cd *y = out + (size_t)c * out_stride + (size_t)b * n;
     for (int i = tid; i < n; i += nt) y[i] = S[fsw(i)];
+}
+
+// The same for G consecutive blocks of a channel in one CTA.  fir_mac_kernel reads nfor spectra and nfor masks per block and
+// bin: with everything in L2 that IS its cost (C4: 8 partitions, 4 TB/s of L2 reads).  Here a thread walks the G + nfor - 1
+// spectra its bin needs ONCE, newest first, and keeps G accumulators: the spectrum of block bb meets block g0 + g at
+// partition p = g0 + g - bb, so every accumulator still receives its partitions in the order 0, 1, 2, ... (the order of
+// xfircore, firmin.c:417-427) -- bit-identical sums.  The masks slide through a G-long register window (one new mask value
+// per step).  Then G inverse transforms side by side.  Loads per bin: G + 2 nfor - 1 instead of 2 G nfor.
+template <int G>
+__global__ void __launch_bounds__(256) fir_mac_group_kernel(const cd *spec, int nblocks, int n, int nfor, int bi0, const cd *fdl, const cd *__restrict__ fmask,
+                                                             cd *out, long out_stride, const cd *tw, int lanes)
+{
+    extern __shared__ double smem_raw[];
+    const int n2 = 2 * n, c = blockIdx.y, g0 = blockIdx.x * G, tid = threadIdx.x, nt = blockDim.x;
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *S = twl + fft_tw_entries(n2);
+    fft_stage_twiddles(twl, tw, n2);
+    const int mask = nfor - 1;
+    const cd *sp = spec + (size_t)c * nblocks * n2;
+    const cd *fd = fdl + (size_t)c * nfor * n2;
+    const int steps = G + nfor - 1;
+    for (int i = tid; i < n2; i += nt) {
+        cd acc[G], mw[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) { acc[g] = make_double2(0.0, 0.0); mw[g] = make_double2(0.0, 0.0); }
+        mw[G - 1] = fmask[i];
+        for (int k = 0; k < steps; k++) {
+            const int bb = g0 + G - 1 - k;
+            const bool have = bb < nblocks;
+            cd Y = make_double2(0.0, 0.0);
+            if (have) Y = bb >= 0 ? sp[(size_t)bb * n2 + i] : fd[(size_t)((bi0 + bb) & mask) * n2 + i];
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int p = k + g - (G - 1);
+                if (have && p >= 0 && p < nfor) {
+                    if (p == 0) acc[g] = fir_mac_first(Y, mw[g]);
+                    else fir_mac_add(acc[g], Y, mw[g]);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g + 1 < G; g++) mw[g] = mw[g + 1];
+            mw[G - 1] = k + 1 < nfor ? fmask[(size_t)(k + 1) * n2 + i] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) if (g0 + g < nblocks) S[(size_t)g * n2 + fsw(i)] = acc[g];
+    }
+    __syncthreads();
+    const int sg = tid / lanes, ln = tid - sg * lanes;
+    fft_smem<1>(S + (size_t)sg * n2, n2, twl, +1, ln, lanes);
+    if (g0 + sg < nblocks) {
+        cd *y = out + (size_t)c * out_stride + (size_t)(g0 + sg) * n;
+        const cd *Sg = S + (size_t)sg * n2;
+        for (int i = ln; i < n; i += lanes) y[i] = Sg[fsw(i)];
+    }
 }
 
 // one fircore over nblocks blocks of every channel: transforms wide, then the delay line and `prev` brought up to date
@@ -621,7 +681,18 @@ int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_str
     // of a chain) the MAC kernel is about to overwrite the input
     QC_CUDA(cudaMemcpy2DAsync(f->d_prev, (size_t)n * sizeof(cd), in + (size_t)(nblocks - 1) * n, (size_t)in_stride * sizeof(cd), (size_t)n * sizeof(cd), C,
                               cudaMemcpyDeviceToDevice, s));
-    fir_mac_kernel<<<dim3(C, nblocks), lanes, sh, s>>>(spec, nblocks, n, nfor, f->buffidx, f->d_fdl, f->d_mask[f->cset], out, out_stride, f->tw);
+    const int G = n2 <= 512 ? 8 : (n2 <= 1024 ? 4 : (n2 <= 2048 ? 2 : 1));
+    if (G > 1 && nfor > 1 && C <= 65535 && G * lanes <= 256 && !getenv("QUISK_FIR_MAC_SINGLE")) {
+        const size_t shg = ((size_t)G * n2 + fft_tw_entries(n2)) * sizeof(cd);
+        const dim3 grid((nblocks + G - 1) / G, C);
+#define QC_MACG(G_) do { \
+            if (shg > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(fir_mac_group_kernel<G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shg)); \
+            fir_mac_group_kernel<G_><<<grid, G_ * lanes, shg, s>>>(spec, nblocks, n, nfor, f->buffidx, f->d_fdl, f->d_mask[f->cset], out, out_stride, f->tw, lanes); } while (0)
+        if (G == 8) QC_MACG(8); else if (G == 4) QC_MACG(4); else QC_MACG(2);
+#undef QC_MACG
+    } else {
+        fir_mac_kernel<<<dim3(C, nblocks), lanes, sh, s>>>(spec, nblocks, n, nfor, f->buffidx, f->d_fdl, f->d_mask[f->cset], out, out_stride, f->tw);
+    }
     count_launch();
     QC_CUDA_LAUNCH();
     // state for the next call: the newest min(nblocks, nfor) spectra into their ring slots
