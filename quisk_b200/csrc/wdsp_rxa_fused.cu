@@ -1006,6 +1006,212 @@ __global__ void __launch_bounds__(RF_THREADS, MINB) rxa_wide_seq_kernel(RxaWideP
     else rw_lin_role(P, m, n, c, tid - RF_WORK - 32, agc_on, ast);
 }
 
+// ---- the thin form of the per-channel kernel, for more channels than the GPU holds at two CTAs of 192 threads per SM.
+// The sequential lanes set the pace (66 cycles per sample); ONE worker warp applies the gain law 17 times faster than that,
+// so 128 workers only hold registers.  Here a CTA is three warps (worker, AGC, LIN) and walks the stream in sub-blocks of
+// `ns` <= 256 samples (an eighth of the shared memory), so four CTAs fit an SM where two did.  What belongs to the DSP block
+// rather than to the stream keeps its place: the peak meters are raised to the block maximum behind the LAST sub-block of
+// a block (meter.c:95), the AGC meter's block maximum is carried across the sub-blocks, the siphon takes the block's tail.
+// Same arithmetic per sample in the same order as rxa_wide_seq_kernel: identical outputs, states and meter readings.
+static constexpr int RT_W = 32, RT_THREADS = 96;
+__device__ __forceinline__ void rt_bar_all() { asm volatile("bar.sync 0, %0;" :: "r"(RT_THREADS) : "memory"); }
+
+__device__ __forceinline__ void rt_load_block(const RxaWideParams &P, const RwSmem &m, int ns, int sub, int c, int t, int lane, bool agc_on)
+{
+    const size_t off = (size_t)c * P.nblocks * P.n + (size_t)t * ns;
+    const int par = t & 1;
+    for (int i0 = 0; i0 < ns; i0 += 8 * RT_W) {
+        double v[4][8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + lane + k * RT_W;
+            if (i < ns) {
+                v[0][k] = P.sms[off + i]; v[1][k] = P.smadc[off + i];
+                if (agc_on) { v[2][k] = P.rm[off + i]; v[3][k] = P.absd[off + i]; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + lane + k * RT_W;
+            if (i < ns) {
+                m.SMS[par][i] = v[0][k]; m.SMADC[par][i] = v[1][k];
+                if (agc_on) { m.RV[par][i] = v[2][k]; m.ABSD[par][i] = v[3][k]; }
+            }
+        }
+    }
+    if (lane < 2) m.SC[8 + 3 * par + lane] = P.np[((size_t)c * P.nblocks + t / sub) * 2 + lane];
+}
+
+// gain law, panel, output, siphon for sub-block tb; run_max carries the block maximum of |out|^2 across a block's sub-blocks
+__device__ __forceinline__ void rt_gain_block(const RxaWideParams &P, const RwSmem &m, int ns, int sub, int c, int tb, int lane, bool agc_on, int ab,
+                                              const double *hs, double &run_max)
+{
+    const int par = tb & 1, n = P.n;
+    const double *RV = m.RV[par];
+    double *SMAGC = m.SMAGC[par];
+    const cd *ys = P.y + (size_t)c * P.y_stride;
+    cd *y = P.out + (size_t)c * P.out_stride + (size_t)tb * ns;
+    const int boff = (tb % sub) * ns;                           // the sub-block's place inside its DSP block
+    double mx_agc = 0.0;
+    for (int i0 = 0; i0 < ns; i0 += 8 * RT_W) {
+        cd dl[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + lane + k * RT_W;
+            if (i < ns) {
+                const long idx = (long)tb * ns + i - ab;         // the sample leaving the AGC's delay line
+                dl[k] = idx >= 0 ? ys[idx] : make_double2(hs[(idx + ab) * 3], hs[(idx + ab) * 3 + 1]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = i0 + lane + k * RT_W;
+            if (i >= ns) continue;
+            cd o;
+            const cd d = dl[k];
+            if (agc_on) {
+                const double volts = RV[i];
+                const double lg = log10(__dmul_rn(P.a.inv_max_input, volts));
+                const double mult = __ddiv_rn(__dsub_rn(P.a.out_target, __dmul_rn(P.a.slope_constant, 0.0 < lg ? 0.0 : lg)), volts);
+                o = make_double2(__dmul_rn(d.x, mult), __dmul_rn(d.y, mult));
+            } else {
+                o = P.agc_run ? make_double2(__dmul_rn(P.a.fixed_gain, d.x), __dmul_rn(P.a.fixed_gain, d.y)) : d;
+            }
+            const double sm = rf_smag(o);
+            SMAGC[i] = sm;
+            mx_agc = sm > mx_agc ? sm : mx_agc;
+            if (P.sip) {
+                const int a = boff + i;
+                if (n >= P.sipsize) { if (a >= n - P.sipsize) P.sip[(size_t)c * P.sipsize + (a - (n - P.sipsize))] = o; }
+                else P.sip[(size_t)c * P.sipsize + ((P.sip_idx + tb * ns + i) & (P.sipsize - 1))] = o;
+            }
+            y[i] = make_double2(__dmul_rn(P.gI, o.x), __dmul_rn(P.gQ, o.y));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx_agc, o); mx_agc = t > mx_agc ? t : mx_agc; }
+    if (boff == 0) run_max = 0.0;
+    run_max = mx_agc > run_max ? mx_agc : run_max;
+    if (lane == 0) m.SC[8 + 3 * par + 2] = run_max;
+}
+
+__device__ __forceinline__ void rt_worker_role(const RxaWideParams &P, const RwSmem &m, int ns, int sub, int c, int lane, bool agc_on, int ab, double *hs)
+{
+    const int nb = P.nblocks * sub;
+    double run_max = 0.0;
+    rt_load_block(P, m, ns, sub, c, 0, lane, agc_on);
+    rt_bar_all();
+    for (int t = 0; t < nb; t++) {
+        rt_bar_all();
+        if (t >= 1) rt_gain_block(P, m, ns, sub, c, t - 1, lane, agc_on, ab, hs, run_max);
+        __syncwarp();
+        if (t + 1 < nb) rt_load_block(P, m, ns, sub, c, t + 1, lane, agc_on);
+        rt_bar_all();
+    }
+    rt_bar_all();
+    rt_gain_block(P, m, ns, sub, c, nb - 1, lane, agc_on, ab, hs, run_max);
+    __syncwarp();
+    if (agc_on) {
+        const long N = (long)P.nblocks * P.n;
+        const cd *ys = P.y + (size_t)c * P.y_stride;
+        if (N < ab) {
+            const int keep = ab - (int)N;
+            for (int j0 = 0; j0 < keep; j0 += RT_W) {
+                const int j = j0 + lane;
+                double r0 = 0, r1 = 0, r2 = 0;
+                if (j < keep) { r0 = hs[(N + j) * 3]; r1 = hs[(N + j) * 3 + 1]; r2 = hs[(N + j) * 3 + 2]; }
+                __syncwarp();
+                if (j < keep) { hs[j * 3] = r0; hs[j * 3 + 1] = r1; hs[j * 3 + 2] = r2; }
+                __syncwarp();
+            }
+        }
+        for (int k = lane + (N < ab ? ab - (int)N : 0); k < ab; k += RT_W) {
+            const cd v = ys[N - ab + k];
+            hs[k * 3] = v.x; hs[k * 3 + 1] = v.y; hs[k * 3 + 2] = rf_mag(v, P.a.pmode);
+        }
+    }
+    rt_bar_all();
+}
+
+__device__ __forceinline__ void rt_agc_role(const RxaWideParams &P, const RwSmem &m, int ns, int sub, bool agc_on, double *ast, bool lane0)
+{
+    double volts = ast[3], save_volts = ast[4];
+    int hang_counter = (int)ast[7], decay_type = (int)ast[8], state_ = (int)ast[9];
+    const int nb = P.nblocks * sub;
+    rt_bar_all();
+    for (int t = 0; t < nb; t++) {
+        rt_bar_all();
+        if (agc_on) rf_agc_block(m.RV[t & 1], m.FBA, m.HBA, m.linpos, ns, P.a, volts, save_volts, hang_counter, decay_type, state_, nullptr);
+        if (lane0 && agc_on && t == nb - 1) {
+            ast[3] = volts; ast[4] = save_volts;
+            ast[7] = hang_counter; ast[8] = decay_type; ast[9] = state_; ast[10] = __dmul_rn(volts, P.a.inv_out_target);
+        }
+        rt_bar_all();
+    }
+    rt_bar_all();
+    rt_bar_all();
+}
+
+__device__ __forceinline__ void rt_lin_role(const RxaWideParams &P, const RwSmem &m, int ns, int sub, int c, int lane, bool agc_on, double *ast)
+{
+    const int mt = lane < 6 ? lane >> 1 : 3, pk = lane & 1, nb = P.nblocks * sub;
+    const bool meter = lane < 6, back = agc_on && (lane == 6 || lane == 7), live = meter || back;
+    double s = meter ? P.mst[mt][(size_t)c * 2 + pk] : (back ? ast[lane - 1] : 0.0);
+    double c1 = 0.0, c2 = 0.0;
+    if (meter) { c1 = pk ? 0.0 : 1.0 - P.m_ma; c2 = pk ? P.m_mp : P.m_ma; }
+    else if (lane == 6) { c1 = P.a.fast_backmult; c2 = P.a.onemfast_backmult; }
+    else if (lane == 7) { c1 = P.a.hang_backmult; c2 = P.a.onemhang_backmult; }
+    double *dst = lane == 6 ? m.FBA : (lane == 7 ? m.HBA : m.SC + 16 + lane);
+    const int dstep = lane == 6 || lane == 7 ? 1 : 0;
+    if (lane == 0) *m.linpos = 0;
+    rt_bar_all();
+    for (int t = 0; t < nb; t++) {
+        rt_bar_all();
+        const int par = t & 1;
+        const double *src = mt == 0 ? m.SMADC[par] : (mt == 1 ? m.SMS[par] : (mt == 2 ? m.SMAGC[par] : (back ? m.ABSD[par] : m.SMS[par])));
+        const bool run = mt != 2 || t >= 2;
+        const double r = rf_lin_block(run ? src : m.SMS[par], ns, run ? c1 : 0.0, run ? c2 : 1.0, s, dst, dstep, m.linpos);
+        const int u = mt == 2 ? t - 2 : t;                              // the sub-block this lane has just walked
+        if (live) { s = r; if (meter && pk && run && (u + 1) % sub == 0) { const double np = m.SC[8 + 3 * par + mt]; if (np > s) s = np; } }
+        rt_bar_all();
+        if (lane == 0) *m.linpos = 0;
+    }
+    rt_bar_all();
+    if (nb >= 2) {
+        const int par = nb & 1, u = nb - 2;
+        const double r = rf_lin_block(m.SMAGC[par], ns, mt == 2 ? c1 : 0.0, mt == 2 ? c2 : 1.0, s, m.SC + 16 + lane, 0, nullptr);
+        if (mt == 2) { s = r; if (pk && (u + 1) % sub == 0) { const double np = m.SC[8 + 3 * par + 2]; if (np > s) s = np; } }
+    }
+    rt_bar_all();
+    {
+        const int par = (nb - 1) & 1;
+        const double r = rf_lin_block(m.SMAGC[par], ns, mt == 2 ? c1 : 0.0, mt == 2 ? c2 : 1.0, s, m.SC + 16 + lane, 0, nullptr);
+        if (mt == 2) { s = r; if (pk) { const double np = m.SC[8 + 3 * par + 2]; if (np > s) s = np; } }
+    }
+    if (meter) {
+        P.mst[mt][(size_t)c * 2 + pk] = s;
+        P.mres[mt][(size_t)c * 3 + pk] = 10.0 * mlog10_dev(P.mtable, s + 1.0e-40);
+        if (lane == 4) P.mres[2][(size_t)c * 3 + 2] = 20.0 * mlog10_dev(P.mtable, ast[10] + 1.0e-40);
+        else if (!pk) P.mres[mt][(size_t)c * 3 + 2] = 0.0;
+    } else if (back) {
+        ast[lane - 1] = s;
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(RT_THREADS, MINB) rxa_thin_seq_kernel(RxaWideParams P, int ns, int sub)
+{
+    extern __shared__ double smem_raw[];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const bool agc_on = P.agc_run && P.a.mode != 0;
+    const int ab = agc_on ? P.a.attack_buffsize : 0;
+    const RwSmem m = rw_map(smem_raw, ns);
+    double *hs = P.agc_hist + (size_t)c * (agc_on ? ab : 1) * 3;
+    double *ast = P.agc_state + (size_t)c * 16;
+    if (tid < RT_W) rt_worker_role(P, m, ns, sub, c, tid, agc_on, ab, hs);
+    else if (tid < RT_W + 32) rt_agc_role(P, m, ns, sub, agc_on, ast, tid == RT_W);
+    else rt_lin_role(P, m, ns, sub, c, tid - RT_W - 32, agc_on, ast);
+}
+
 size_t rxa_fused_smem(int n, int ab)
 {
     const int n2 = 2 * n, tot = ab + n;
@@ -1075,11 +1281,22 @@ int Rxa::xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, 
             const size_t sh = rxa_wide_seq_smem(dsp_size);
             int dev = 0, n_sm = 148;
             cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            // one CTA per SM while the channels fit (174 registers, every worker warp busy), two while THAT fits in one wave, else the
+            // thin form at four per SM (QUISK_RXA_MINB = 1 / 2 / 4 forces one of them: tests, measurements)
             const char *force = getenv("QUISK_RXA_MINB");
-            const bool fat = force ? atoi(force) == 1 : C <= n_sm;
+            const int form = force ? atoi(force) : (C <= n_sm ? 1 : (C <= 2 * n_sm ? 2 : 4));
+            const bool fat = form == 1;
             if (fat) {
                 if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_wide_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
                 rxa_wide_seq_kernel<1><<<C, RF_THREADS, sh, s>>>(W);
+            } else if (form != 2) {
+                // more channels than two fat CTAs per SM hold: three-warp CTAs over sub-blocks, four per SM
+                const char *fs = getenv("QUISK_RXA_THIN_NS");
+                int ns = dsp_size > 256 ? 256 : dsp_size;
+                if (fs && atoi(fs) >= 8 && atoi(fs) <= dsp_size && dsp_size % atoi(fs) == 0) ns = atoi(fs);
+                const size_t sht = rxa_wide_seq_smem(ns);
+                if (sht > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_thin_seq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sht));
+                rxa_thin_seq_kernel<4><<<C, RT_THREADS, sht, s>>>(W, ns, dsp_size / ns);
             } else {
                 if (sh > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(rxa_wide_seq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
                 rxa_wide_seq_kernel<2><<<C, RF_THREADS, sh, s>>>(W);

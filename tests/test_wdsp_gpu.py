@@ -3,6 +3,7 @@ from the compiled reference (tests/golden/make_golden_wdsp.py -> wdsp_kat.npz). 
 identical channels through the batched kernels.  Tolerances: fircore-based stages 1e-12 relative RMS (the
 north star's FP64 bound; our FFT is not FFTW's), recurrent stages 1e-12 as well, resampler bit-exact."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -593,8 +594,16 @@ def test_rxa_fused_kernel_equals_per_stage_kernels(geom, agc_mode, torch, lib):
         assert lib.quisk_cuda_rxa_set_passband(rxa, 150.0, 2850.0) == 0
         assert lib.quisk_cuda_rxa_set_agc_mode(rxa, agc_mode) == 0
         o = torch.zeros_like(d)
-        if kind == "multi":
-            assert lib.quisk_cuda_rxa_xrxa_multi(rxa, d.data_ptr(), d.stride(0), o.data_ptr(), o.stride(0), nblk, None) == 0, lib.quisk_cuda_last_error()
+        if kind.startswith("multi"):
+            # the per-channel sequential kernel has three forms chosen by the channel count (one fat CTA per SM, two, or four
+            # three-warp CTAs over sub-blocks of the DSP block): force each of them on this small batch
+            env = {"multi": None, "multi_two": ("2", "0"), "multi_thin": ("4", "0"), "multi_thin64": ("4", "64")}[kind]
+            if env:
+                os.environ["QUISK_RXA_MINB"], os.environ["QUISK_RXA_THIN_NS"] = env
+            try:
+                assert lib.quisk_cuda_rxa_xrxa_multi(rxa, d.data_ptr(), d.stride(0), o.data_ptr(), o.stride(0), nblk, None) == 0, lib.quisk_cuda_last_error()
+            finally:
+                os.environ.pop("QUISK_RXA_MINB", None); os.environ.pop("QUISK_RXA_THIN_NS", None)
         else:
             for b in range(nblk):
                 fused = {"fused": 1, "stages": 0, "mixed": b % 3 != 1}[kind]
@@ -618,6 +627,11 @@ def test_rxa_fused_kernel_equals_per_stage_kernels(geom, agc_mode, torch, lib):
         assert np.max(np.abs(got[2] - ref[2])) <= 1e-6 * np.max(np.abs(ref[2])), kind
     # one launch for all blocks runs the transforms as their own wide kernels: again the same source compiled in another context
     assert max(O.rel_rms(res["multi"][0][c], res["fused"][0][c]) for c in range(NCH)) < 1e-13
+    # the three forms of the per-channel kernel: same arithmetic in the same order -- outputs, meters and siphon bit for bit
+    for kind in ("multi_two", "multi_thin", "multi_thin64"):
+        got = run(kind)
+        for a, b in zip(got, res["multi"]):
+            assert np.array_equal(a, b), kind
 
 
 @pytest.mark.parametrize("cfg", ["fm_384k", "am", "sam_usb", "usb_out96k"])
