@@ -330,7 +330,7 @@ int Rxa::xrxa_stages_wide(const void *din, long is, void *dout, long os, int g, 
         QC_CUDA(cudaMalloc((void **)&waudio, (size_t)C * need * sizeof(cd)));
         wstride = need;
     }
-    const size_t need_spec = (size_t)C * g * 2 * dsp_size;
+    const size_t need_spec = (size_t)C * g * 2 * dsp_size * 2;      // spectra + the partition MAC's products (fircore_wide)
     if (need_spec > wide_spec_cap) { if (d_wide_spec) cudaFree(d_wide_spec); d_wide_spec = nullptr; wide_spec_cap = 0;
                                      QC_CUDA(cudaMalloc((void **)&d_wide_spec, need_spec * sizeof(cd))); wide_spec_cap = need_spec; }
     const long ws = wstride;

@@ -18,6 +18,7 @@
 // Arithmetic in the recurrent parts is written with __dmul_rn / __dadd_rn: the reference is compiled for baseline x86-64,
 // where a * b + c rounds twice.  The transforms and MACs are the code of fircore_kernel (wdsp_fircore.cu), so the fused
 // kernel and the per-stage kernels produce the same bits and share their state arrays: a stream may switch between them.
+#include <cstring>
 #include "fft_device.cuh"
 #include "wdsp_internal.h"
 
@@ -665,6 +666,73 @@ __global__ void __launch_bounds__(256) fir_mac_group_kernel(const cd *spec, int 
     }
 }
 
+// The partition MAC on its own, streamed along time: one thread per (channel, bin) walks the spectra of its bin from the
+// NEWEST block of the launch down into the delay line of the previous one, each read exactly once, with NFOR accumulators
+// in flight: the spectrum of block t is partition p of block t + p, and walking backwards every block receives its
+// partitions in the order 0, 1, 2, ... of xfircore (firmin.c:417-427) -- bit-identical sums.  Block t + NFOR - 1 is complete
+// when spectrum t has been added and goes to `prod`.  The masks are NFOR register values per thread.  HBM / L2 traffic:
+// one read and one write per spectrum value, where a CTA per (channel, block) reads NFOR spectra and NFOR masks.
+template <int NFOR>
+__global__ void __launch_bounds__(256) fir_mac_stream_kernel(const cd *spec, int nblocks, int n2, int bi0, const cd *fdl, const cd *__restrict__ fmask, cd *prod)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+    if (i >= n2) return;
+    const cd *sp = spec + (size_t)c * nblocks * n2 + i;
+    const cd *fd = fdl + (size_t)c * NFOR * n2 + i;
+    cd *pr = prod + (size_t)c * nblocks * n2 + i;
+    cd m[NFOR], acc[NFOR];
+#pragma unroll
+    for (int p = 0; p < NFOR; p++) { m[p] = fmask[(size_t)p * n2 + i]; acc[p] = make_double2(0.0, 0.0); }
+    const int total = nblocks + NFOR - 1;                       // spectra walked: blocks nblocks - 1 .. -(NFOR - 1)
+    for (int u0 = 0; u0 < total; u0 += NFOR) {
+        cd Y[NFOR];
+#pragma unroll
+        for (int r = 0; r < NFOR; r++) {
+            const int t = nblocks - 1 - (u0 + r);
+            if (u0 + r < total) Y[r] = t >= 0 ? sp[(size_t)t * n2] : fd[(size_t)((bi0 + t) & (NFOR - 1)) * n2];
+        }
+#pragma unroll
+        for (int r = 0; r < NFOR; r++) {
+            const int u = u0 + r, t = nblocks - 1 - u;
+            if (u < total) {
+#pragma unroll
+                for (int p = 0; p < NFOR; p++) {
+                    // block t + p, accumulator (u - p) mod NFOR = (r - p) mod NFOR
+                    const int a = (r - p + NFOR) % NFOR;
+                    if (p <= u && t + p >= 0) {
+                        if (p == 0) acc[a] = fir_mac_first(Y[r], m[0]);
+                        else fir_mac_add(acc[a], Y[r], m[p]);
+                        if (p == NFOR - 1) pr[(size_t)(t + p) * n2] = acc[a];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// inverse transforms of the finished products, G blocks of a channel side by side in one CTA
+template <int G>
+__global__ void __launch_bounds__(256) fir_inv_group_kernel(const cd *prod, int nblocks, int n, cd *out, long out_stride, const cd *tw, int lanes)
+{
+    extern __shared__ double smem_raw[];
+    const int n2 = 2 * n, c = blockIdx.y, g0 = blockIdx.x * G, tid = threadIdx.x;
+    cd *twl = reinterpret_cast<cd *>(smem_raw);
+    cd *S = twl + fft_tw_entries(n2);
+    fft_stage_twiddles(twl, tw, n2);
+    const int sg = tid / lanes, ln = tid - sg * lanes;
+    cd *Sg = S + (size_t)sg * n2;
+    if (g0 + sg < nblocks) {
+        const cd *p = prod + ((size_t)c * nblocks + g0 + sg) * n2;
+        for (int i = ln; i < n2; i += lanes) Sg[fsw(i)] = p[i];
+    }
+    __syncthreads();
+    fft_smem<1>(Sg, n2, twl, +1, ln, lanes);
+    if (g0 + sg < nblocks) {
+        cd *y = out + (size_t)c * out_stride + (size_t)(g0 + sg) * n;
+        for (int i = ln; i < n; i += lanes) y[i] = Sg[fsw(i)];
+    }
+}
+
 // one fircore over nblocks blocks of every channel: transforms wide, then the delay line and `prev` brought up to date
 int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_stride, int nblocks, cd *spec, cudaStream_t s)
 {
@@ -682,7 +750,28 @@ int fircore_wide(FirCore *f, const cd *in, long in_stride, cd *out, long out_str
     QC_CUDA(cudaMemcpy2DAsync(f->d_prev, (size_t)n * sizeof(cd), in + (size_t)(nblocks - 1) * n, (size_t)in_stride * sizeof(cd), (size_t)n * sizeof(cd), C,
                               cudaMemcpyDeviceToDevice, s));
     const int G = n2 <= 512 ? 8 : (n2 <= 1024 ? 4 : (n2 <= 2048 ? 2 : 1));
-    if (G > 1 && nfor > 1 && C <= 65535 && G * lanes <= 256 && !getenv("QUISK_FIR_MAC_SINGLE")) {
+    const char *macform = getenv("QUISK_FIR_MAC");           // "single" / "group" / "stream" force one form (tests, measurements)
+    const bool can_stream = (nfor == 2 || nfor == 4 || nfor == 8 || nfor == 16) && C <= 65535 && G * lanes <= 256;
+    if (can_stream && !(macform && strcmp(macform, "stream"))) {
+        // `spec` is allocated twice as long as the spectra need: the second half takes the products
+        cd *prod = spec + (size_t)C * nblocks * n2;
+        const dim3 gm((n2 + 255) / 256, C);
+        switch (nfor) {
+        case 2: fir_mac_stream_kernel<2><<<gm, 256, 0, s>>>(spec, nblocks, n2, f->buffidx, f->d_fdl, f->d_mask[f->cset], prod); break;
+        case 4: fir_mac_stream_kernel<4><<<gm, 256, 0, s>>>(spec, nblocks, n2, f->buffidx, f->d_fdl, f->d_mask[f->cset], prod); break;
+        case 8: fir_mac_stream_kernel<8><<<gm, 256, 0, s>>>(spec, nblocks, n2, f->buffidx, f->d_fdl, f->d_mask[f->cset], prod); break;
+        default: fir_mac_stream_kernel<16><<<gm, 256, 0, s>>>(spec, nblocks, n2, f->buffidx, f->d_fdl, f->d_mask[f->cset], prod); break;
+        }
+        count_launch();
+        QC_CUDA_LAUNCH();
+        const size_t shg = ((size_t)G * n2 + fft_tw_entries(n2)) * sizeof(cd);
+        const dim3 grid((nblocks + G - 1) / G, C);
+#define QC_INVG(G_) do { \
+            if (shg > 48 * 1024) QC_CUDA(cudaFuncSetAttribute(fir_inv_group_kernel<G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shg)); \
+            fir_inv_group_kernel<G_><<<grid, G_ * lanes, shg, s>>>(prod, nblocks, n, out, out_stride, f->tw, lanes); } while (0)
+        if (G == 8) QC_INVG(8); else if (G == 4) QC_INVG(4); else if (G == 2) QC_INVG(2); else QC_INVG(1);
+#undef QC_INVG
+    } else if (G > 1 && nfor > 1 && C <= 65535 && G * lanes <= 256 && !(macform && !strcmp(macform, "single"))) {
         const size_t shg = ((size_t)G * n2 + fft_tw_entries(n2)) * sizeof(cd);
         const dim3 grid((nblocks + G - 1) / G, C);
 #define QC_MACG(G_) do { \
@@ -1239,7 +1328,7 @@ int Rxa::xrxa_fused(const void *din, long is, void *dout, long os, int nblocks, 
     const bool wide = nblocks >= 2 && (firs[0] || firs[1]) && !getenv("QUISK_RXA_NARROW");
     if (wide) {
         // filters first, all blocks at once, into the filtered-stream scratch; the sequential kernel then starts from there
-        const size_t need_spec = (size_t)C * nblocks * 2 * dsp_size, need_y = (size_t)C * nblocks * dsp_size;
+        const size_t need_spec = (size_t)C * nblocks * 2 * dsp_size * 2 /* spectra + products */, need_y = (size_t)C * nblocks * dsp_size;
         if (need_spec > wide_spec_cap) { if (d_wide_spec) cudaFree(d_wide_spec); d_wide_spec = nullptr; wide_spec_cap = 0;
                                          QC_CUDA(cudaMalloc((void **)&d_wide_spec, need_spec * sizeof(cd))); wide_spec_cap = need_spec; }
         if (need_y > wide_y_cap) { if (d_wide_y) cudaFree(d_wide_y); d_wide_y = nullptr; wide_y_cap = 0;
