@@ -230,6 +230,7 @@ void quisk_cuda_rx_destroy(qcRxChain *rx);
 int quisk_cuda_plan_decimation(int sample_rate, int *decim2, int *decim3, int *decim5);
 int quisk_cuda_rx_decim_srate(const qcRxChain *rx);     /* quisk_decim_srate  */
 int quisk_cuda_rx_filter_srate(const qcRxChain *rx);    /* quisk_filter_srate */
+int quisk_cuda_rx_squelch_active(qcRxChain *rx, int *h_active);            /* [n_channels] squelch_active after the last block (QC_RX_OPT_SSB_SQUELCH; quisk.c:1179) */
 /* Upper bound on audio samples per channel for `count` inputs (for sizing buffers). */
 int quisk_cuda_rx_max_out(const qcRxChain *rx, int count);
 /* d_iq: [n_channels][iq_stride] quisk_cd (device).  d_audio: [n_channels][audio_stride]
@@ -265,6 +266,12 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_NOISE_BLANKER 13  /* quisk_noise_blanker (0 = off, 1..3): quisk_cuda_rx_process_host / _host_packed run NoiseBlanker
                                       (quisk.c:679-784) on the staged block in front of the tuning stage, as quisk_process_samples
                                       does (quisk.c:2448-2449).  The device entry leaves the caller's buffer alone: run quisk_cuda_nb_run first */
+#define QC_RX_OPT_AUTO_NOTCH   16   /* quisk_auto_notch: dAutoNotch on the audio at the filter rate (CW / SSB / AM), between the detector and the
+                                      audio interpolators as in quisk_process_demodulate (quisk.c:1923-1924); the audio comes 1538 samples late */
+#define QC_RX_OPT_NOTCH_SIDETONE 17 /* rit_freq handed to dAutoNotch in the CW modes (a CW side tone is never notched) */
+#define QC_RX_OPT_SSB_SQUELCH  18   /* ssb_squelch_level (0 = off): ssb_squelch + d_delay behind the notch (quisk.c:1925-1928); the block of a
+                                      receiver whose squelch is closed comes back as zeros, as quisk_process_samples mutes it (quisk.c:2716-2719).
+                                      With either option the SSB / CW tail runs as per-stage kernels instead of the fused one. */
 #define QC_RX_OPT_HOST_CHUNKS  15   /* quisk_cuda_rx_process_host / _host_packed: channel chunks whose H2D copy, kernels and D2H copy are pipelined
                                       over streams of their own; 0 (default) = 8 from 1024 channels up, else 1; 1 = one copy-compute-copy sequence.
                                       With more than one chunk the host entries keep stage state of their own, separate from quisk_cuda_rx_process */

@@ -141,6 +141,15 @@ void ref_auto_notch(double *ds, int n, int sidetone, int rate, int reset)
     quisk_auto_notch = 0;
 }
 
+/* The optional stages inside quisk_process_demodulate itself: the reference's own switches (quisk_auto_notch,
+ * ssb_squelch_enabled / ssb_squelch_level, rit_freq for the CW side tone), and the flag quisk_process_samples mutes on. */
+void ref_set_chain_options(int auto_notch, int squelch_enabled, int squelch_level, int rit)
+{   /* set_auto_notch (quisk.c:6011-6019) re-initialises the notch when it is switched, set_ssb_squelch (quisk.c:6021-6029) only stores */
+    quisk_auto_notch = auto_notch; dAutoNotch(NULL, 0, 0, 0);
+    ssb_squelch_enabled = squelch_enabled; ssb_squelch_level = squelch_level; rit_freq = rit;
+}
+int ref_squelch_active(int bank) { return MeasureSquelch[bank].squelch_active; }
+
 /* NoiseBlanker (quisk.c:679-784): called on the raw samples in front of the tuning stage (quisk.c:2448-2449) when
  * quisk_noise_blanker > 0.  Its state is function-static: one private copy of this library per stream. */
 int quisk_noise_blanker;

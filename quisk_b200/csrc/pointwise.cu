@@ -132,6 +132,23 @@ __global__ void demod_ssb_kernel(const cd *in, long in_stride, double *out, long
     }
 }
 
+// rows (receivers) whose squelch flag state[c][1] is set come back as zeros (quisk_process_samples, quisk.c:2716-2719)
+__global__ void mute_rows_kernel(double *audio, long stride, int n, int C, const int *state)
+{
+    const int c = blockIdx.y;
+    if (!state[2 * c + 1]) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) audio[(long)c * stride + i] = 0.0;
+}
+
+int launch_mute_rows(double *audio, long stride, int n, int C, const int *d_state, cudaStream_t s)
+{
+    if (n <= 0 || C <= 0 || !d_state) return QC_OK;
+    mute_rows_kernel<<<dim3((n + 255) / 256 < 8 ? (n + 255) / 256 : 8, C), 256, 0, s>>>(audio, stride, n, C, d_state);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
 int launch_demod_ssb(const cd *in, long in_stride, double *out, long out_stride, int n, int C, int lower, cudaStream_t s)
 {
     if (n <= 0 || C <= 0) return QC_OK;

@@ -73,6 +73,7 @@ int launch_polyfir(const PolyFirParams &p, cudaStream_t stream);
 
 // Pointwise helpers (pointwise.cu)
 int launch_demod_ssb(const cd *in, long in_stride, double *out, long out_stride, int n, int C, int lower, cudaStream_t s);
+int launch_mute_rows(double *audio, long stride, int n, int C, const int *d_state, cudaStream_t s);
 int launch_tune(const cd *in, long in_stride, cd *out, long out_stride, int n, int C,
                 const double *d_nco /* [C][8] */, const cd *d_vstart /* [C] v at sample 0 of the block */, unsigned long long n0, cudaStream_t s);
 int launch_nco_advance(const cd *v_in, cd *v_out, const double *d_nco, int count, int C, unsigned *d_sched, unsigned epoch, cudaStream_t s);

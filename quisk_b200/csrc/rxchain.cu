@@ -47,6 +47,7 @@ static BatchFilter *mk(int kind, int C, const double *coefs, int n, int interp, 
 
 int RxChain::init(const qcRxConfig &cfg)
 {
+    filter_bandwidth = cfg.filter_bandwidth;
     C = cfg.n_channels; sample_rate = cfg.sample_rate; mode = cfg.mode; fused = cfg.fused;
     if (C <= 0 || sample_rate <= 0) { set_error("rx_create: bad channel count / sample rate"); return QC_EINVAL; }
     {   // keep what we were given: the pipelined host entries build channel-subset chains from it on first use
@@ -276,7 +277,7 @@ int RxChain::build_sub_chains(int k)
         RxChain *r = new RxChain();
         if (r->init(cfg) != QC_OK) { r->release(); delete r; release_sub_chains(); return QC_EINVAL; }
         r->host_chunks = 1;
-        r->exact_nco = exact_nco; r->fused_tail = fused_tail; r->nb_level = nb_level; r->fused_chunk = fused_chunk; r->fused_threads = fused_threads;
+        r->exact_nco = exact_nco; r->fused_tail = fused_tail; r->nb_level = nb_level; r->auto_notch = auto_notch; r->notch_sidetone = notch_sidetone; r->squelch_level = squelch_level; r->fused_chunk = fused_chunk; r->fused_threads = fused_threads;
         r->fused_plans = fused_plans; r->fused_tailwarp = fused_tailwarp; r->fused_dense = fused_dense; r->fused_split = fused_split;
         r->fused_min_r = fused_min_r; r->fused_deepk = fused_deepk;
         sub.push_back(r); sub_c0.push_back(c0);
@@ -295,6 +296,8 @@ void RxChain::release()
     if (s_nco) { cudaStreamSynchronize(s_nco); cudaStreamDestroy(s_nco); s_nco = nullptr; }
     if (d_sched) { cudaFree(d_sched); d_sched = nullptr; }
     if (nb) { quisk_cuda_nb_destroy(nb); nb = nullptr; }
+    if (anotch) { quisk_cuda_autonotch_destroy(anotch); anotch = nullptr; }
+    if (squelch) { quisk_cuda_ssb_squelch_destroy(squelch); squelch = nullptr; }
     for (int i = 0; i < NV; i++) {
         if (d_v[i]) cudaFree(d_v[i]); d_v[i] = nullptr;
         if (ev_r[i]) cudaEventDestroy(ev_r[i]); if (ev_f[i]) cudaEventDestroy(ev_f[i]);
@@ -424,7 +427,7 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
         latch.ok = true;
         return QC_OK;
     }
-    if (fused && fused_tail && tail_fusable()) {
+    if (fused && fused_tail && tail_fusable() && !audio_options()) {
         rc = run_tail(cur, stride, n, d_audio, audio_stride, &no, s);
         if (rc == QC_OK) { if (n_audio) *n_audio = no; latch.ok = true; return QC_OK; }
         if (rc != QC_ENOMEM) return rc;          // too long for shared memory: per-stage kernels below
@@ -445,6 +448,20 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
     case QC_MODE_FM: rc = launch_fm_detect(cur, cap, rcur, cap, n, C, d_fm, fm_a0, fm_a1, fm_b1, s); break;
     }
     if (rc != QC_OK) return rc;
+    if (audio_options()) {
+        // quisk.c:1923-1928 (and the same lines of the other side-band and AM branches): notch, then squelch + its delay line
+        if (auto_notch) {
+            if (!anotch) anotch = quisk_cuda_autonotch_create(C, filter_srate);
+            if (!anotch) return QC_EINVAL;
+            const bool cw = mode == QC_MODE_CWL || mode == QC_MODE_CWU;
+            rc = quisk_cuda_autonotch_run(anotch, rcur, rstride, n, cw ? notch_sidetone : 0, s); if (rc != QC_OK) return rc;
+        }
+        if (squelch_level > 0) {
+            if (!squelch) squelch = quisk_cuda_ssb_squelch_create(C, filter_srate, filter_bandwidth);
+            if (!squelch) return QC_EINVAL;
+            rc = quisk_cuda_ssb_squelch_run(squelch, rcur, rstride, n, squelch_level, s); if (rc != QC_OK) return rc;
+        }
+    }
     // audio stages; the last one writes straight into the caller's buffer
     for (size_t i = 0; i < rst.size(); i++) {
         const bool last = i + 1 == rst.size();
@@ -454,9 +471,19 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
         rc = rst[i]->run(rcur, (rcur == d_audio) ? audio_stride : cap, n, dst, dstride, &no, 0, s); if (rc != QC_OK) return rc;
         rcur = dst; rp ^= 1; n = no;
     }
+    if (squelch_level > 0 && squelch && audio_options() && n > 0) {
+        // quisk_process_samples mutes the block of a receiver whose squelch is closed (quisk.c:2552-2623, 2716-2719)
+        rc = launch_mute_rows(d_audio, audio_stride, n, C, quisk_cuda_ssb_squelch_state_ptr(squelch), s); if (rc != QC_OK) return rc;
+    }
     if (n_audio) *n_audio = n;
     latch.ok = true;
     return QC_OK;
+}
+
+bool RxChain::audio_options() const
+{   // the modes whose branch of quisk_process_demodulate has both stages at the filter rate: CW, SSB, AM
+    if (!auto_notch && squelch_level <= 0) return false;
+    return mode == QC_MODE_CWL || mode == QC_MODE_CWU || mode == QC_MODE_LSB || mode == QC_MODE_USB || mode == QC_MODE_AM;
 }
 
 // quisk_process_samples runs NoiseBlanker on the raw block in front of the tuning stage (quisk.c:2448-2449); the host
@@ -558,6 +585,8 @@ int RxChain::reset()
     if (d_fm) { rc = reset_fm(); if (rc != QC_OK) return rc; }
     if (tune) { rc = upload_nco(); if (rc != QC_OK) return rc; }
     rc = reset_fused(); if (rc != QC_OK) return rc;
+    if (anotch) { quisk_cuda_autonotch_destroy(anotch); anotch = nullptr; }          // created again, in its start state, by the next block
+    if (squelch) { quisk_cuda_ssb_squelch_destroy(squelch); squelch = nullptr; }
     for (RxChain *r : sub) { rc = r->reset(); if (rc != QC_OK) return rc; }
     QC_CUDA(cudaDeviceSynchronize());
     poisoned = false;
@@ -584,6 +613,15 @@ qcRxChain *quisk_cuda_rx_create(const struct qcRxConfig *cfg)
 void quisk_cuda_rx_destroy(qcRxChain *rx) { if (rx) { rx->rx.release(); delete rx; } }
 int quisk_cuda_rx_decim_srate(const qcRxChain *rx) { return rx ? rx->rx.decim_srate : QC_EINVAL; }
 int quisk_cuda_rx_filter_srate(const qcRxChain *rx) { return rx ? rx->rx.filter_srate : QC_EINVAL; }
+
+int quisk_cuda_rx_squelch_active(qcRxChain *rx, int *h_active)
+{   // MeasureSquelch[].squelch_active of every receiver after the last block (QC_RX_OPT_SSB_SQUELCH); all zero while the option is off
+    if (!rx || !h_active) return QC_EINVAL;
+    for (int c = 0; c < rx->rx.C; c++) h_active[c] = 0;
+    if (!rx->rx.squelch || rx->rx.squelch_level <= 0) return QC_OK;
+    QC_CUDA(cudaDeviceSynchronize());
+    return quisk_cuda_ssb_squelch_state(rx->rx.squelch, nullptr, h_active, nullptr);
+}
 int quisk_cuda_rx_max_out(const qcRxChain *rx, int count) { return rx ? rx->rx.max_out(count) : QC_EINVAL; }
 
 int quisk_cuda_rx_process(qcRxChain *rx, const void *d_iq, long iq_stride, int count, double *d_audio, long audio_stride,
@@ -619,6 +657,11 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
         rx->rx.nb_level = value;
         for (qc::RxChain *r : rx->rx.sub) r->nb_level = value;
         return QC_OK;
+    case QC_RX_OPT_AUTO_NOTCH: rx->rx.auto_notch = value ? 1 : 0; for (qc::RxChain *r : rx->rx.sub) r->auto_notch = rx->rx.auto_notch; return QC_OK;
+    case QC_RX_OPT_NOTCH_SIDETONE: rx->rx.notch_sidetone = value; for (qc::RxChain *r : rx->rx.sub) r->notch_sidetone = value; return QC_OK;
+    case QC_RX_OPT_SSB_SQUELCH:
+        if (value < 0) { qc::set_error("rx_set_option: squelch level must be 0 (off) or ssb_squelch_level > 0"); return QC_EINVAL; }
+        rx->rx.squelch_level = value; for (qc::RxChain *r : rx->rx.sub) r->squelch_level = value; return QC_OK;
     case QC_RX_OPT_HOST_CHUNKS:
         if (value < 0 || value > 64) { qc::set_error("rx_set_option: host chunks must be 0 (auto) .. 64"); return QC_EINVAL; }
         rx->rx.host_chunks = value; return QC_OK;

@@ -30,6 +30,11 @@ struct RxChain {
     int exact_nco = 1;                  // 1: block-start phasors from the reference's recurrence; 0: closed form only
     cudaStream_t s_nco = nullptr;
     qcNoiseBlanker *nb = nullptr; int nb_level = 0;     // QC_RX_OPT_NOISE_BLANKER: NoiseBlanker on the staged block of the host entries
+    // QC_RX_OPT_AUTO_NOTCH / _NOTCH_SIDETONE / _SSB_SQUELCH: dAutoNotch and ssb_squelch + d_delay on the audio at the filter rate,
+    // between the detector and the audio interpolators, where quisk_process_demodulate runs them (quisk.c:1923-1928); a squelched
+    // receiver's block comes back as zeros (quisk.c:2716-2719)
+    qcAutoNotch *anotch = nullptr; qcSsbSquelch *squelch = nullptr; int auto_notch = 0, notch_sidetone = 0, squelch_level = 0, filter_bandwidth = 0;
+    bool audio_options() const;
     int host_noise_blanker(cudaStream_t s, int count);
     unsigned *d_sched = nullptr;        // nco_advance_kernel's ticket counter + one worker slot per SM id
     unsigned nco_epoch = 0;

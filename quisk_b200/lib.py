@@ -69,6 +69,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_rx_destroy.restype = None
     lib.quisk_cuda_rx_decim_srate.argtypes = [vp]
     lib.quisk_cuda_rx_filter_srate.argtypes = [vp]
+    lib.quisk_cuda_rx_squelch_active.argtypes = [vp, vp]
     lib.quisk_cuda_rx_max_out.argtypes = [vp, C.c_int]
     lib.quisk_cuda_rx_process.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p, vp, C.c_long, c_int_p, vp]
     lib.quisk_cuda_rx_process_host.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p]
