@@ -66,26 +66,27 @@ int quisk_cuda_emnr_set_npe_method(qcEmnr *e, int method);              /* SetRX
 int quisk_cuda_emnr_set_ae_run(qcEmnr *e, int run);                     /* SetRXAEMNRaeRun,      emnr.c:1127-1133 */
 
 /* ---- analyzer: WDSP's spectrum engine (wdsp/analyzer.c) for a batch of displays that share one configuration: complex input,
- * one LO, one sub-span, no calibration table (SetAnalyzer with typ = 1, n_fft = 1, n_stch = 1, fmin = fmax = 0).
+ * one LO per sub-span, up to four stitched sub-spans, no calibration table (SetAnalyzer with typ = 1, n_fft = 1, fmin = fmax = 0).
  * create = XCreateAnalyzer (analyzer.c:1140); set = SetAnalyzer (:999-1137; size a power of two 64 .. 8192, overlap in samples,
  * clip / fsclip_low / fsclip_high in bins); set_detector_mode .. set_norm_onehz = SetDisplayDetectorMode (0 peak, 1 rosenfell,
  * 2 average, 3 sample, 4 rms), SetDisplayAverageMode (-1 peak hold, 0 none, 1 recursive, 2 window, 3 recursive on the log),
  * SetDisplayNumAverage, SetDisplayAvBackmult, SetDisplaySampleRate, SetDisplayNormOneHz (:1582-1675), all per pixel output
- * 0 .. 3; spectrum0 = Spectrum0 (:1536): d_samples [n_displays][buff_size] complex doubles on the device, stride in complex
- * samples, every frame the new samples complete is transformed, detected and averaged at once; get_pixels = GetPixels
+ * 0 .. 3; spectrum0 = Spectrum0 (:1536) for sub-span ss: d_samples [n_displays][buff_size] complex doubles on the device, stride
+ * in complex samples; a sub-span with `size` samples waiting sends one frame and waits for the stitch that uses it (:713-733),
+ * the line is detected and averaged as soon as every sub-span has reported; get_pixels = GetPixels
  * (:1315): h_pixels [n_displays][n_pixels] floats (dB), *flag = 1 if the line is new since the last call. */
 typedef struct qcAnalyzer qcAnalyzer;
 qcAnalyzer *quisk_cuda_analyzer_create(int n_displays, int max_size);
 void quisk_cuda_analyzer_destroy(qcAnalyzer *an);
 int quisk_cuda_analyzer_set(qcAnalyzer *an, int n_pixout, int flip, int size, int buff_size, int window_type, double pi_alpha, int overlap, int clip,
-                            double fsclip_low, double fsclip_high, int n_pixels, int max_writeahead);
+                            double fsclip_low, double fsclip_high, int n_pixels, int n_stitch, int max_writeahead);
 int quisk_cuda_analyzer_set_detector_mode(qcAnalyzer *an, int pixout, int mode);
 int quisk_cuda_analyzer_set_average_mode(qcAnalyzer *an, int pixout, int mode);
 int quisk_cuda_analyzer_set_num_average(qcAnalyzer *an, int pixout, int num);
 int quisk_cuda_analyzer_set_av_backmult(qcAnalyzer *an, int pixout, double mult);
 int quisk_cuda_analyzer_set_sample_rate(qcAnalyzer *an, int rate);
 int quisk_cuda_analyzer_set_norm_onehz(qcAnalyzer *an, int pixout, int norm);
-int quisk_cuda_analyzer_spectrum0(qcAnalyzer *an, const void *d_samples, long stride, void *stream);
+int quisk_cuda_analyzer_spectrum0(qcAnalyzer *an, int ss, const void *d_samples, long stride, void *stream);
 int quisk_cuda_analyzer_get_pixels(qcAnalyzer *an, int pixout, float *h_pixels, int *flag);
 double quisk_cuda_analyzer_get_enb(qcAnalyzer *an);                          /* GetDisplayENB, analyzer.c:1678 */
 

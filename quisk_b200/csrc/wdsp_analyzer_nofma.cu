@@ -6,8 +6,8 @@
 // ends of the span, stitch (:555-600) hands the bins to the detector (:282-461: bins -> pixels as peak / rosenfell /
 // average / sample / rms, or linear interpolation when there are more pixels than bins) and the averager (:463-553: peak
 // hold, none, recursive, window, recursive on the log; 10 mlog10 -> float), once per pixel output; GetPixels (:1315-1334)
-// copies the newest line.  One LO, one sub-span, no calibration table (SetAnalyzer with n_fft = 1, n_stch = 1, fmin = fmax
-// = 0) -- the configuration of a plain panadapter; spur elimination over several LOs and stitched spans are not built.
+// copies the newest line.  One LO per sub-span (this reference build has dMAX_NUM_FFT = 1, comm.h:125), up to four stitched sub-spans, no
+// calibration table (SetAnalyzer with typ = 1, n_fft = 1, fmin = fmax = 0); real input (typ = 0) is not built.
 //
 // Here: D displays share one configuration and run side by side.  Per frame three launches: (1) one CTA per display:
 // ring -> window -> shared-memory transform -> |X|^2 in Celiminate's order; (2) the detector, a thread per pixel.  Which
@@ -32,7 +32,7 @@ static constexpr int AN_MAX_PIXOUTS = 4, AN_MAX_AVERAGE = 60, AN_MAX_PIXELS = 16
 struct AnFrameParams {
     const cd *ring; int bsize, idx0, size;      // [D][bsize] samples as Spectrum0 stored them (x = I, y = Q)
     const double *window; const cd *tw;
-    double *bins; int m;                        // [D][m]
+    double *bins; int m, bin_off;               // [D][m]: this sub-span's bins start at bin_off
     int begin0, end0, begin1, end1, flip;       // Celiminate's two runs over the transform's output
 };
 
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) an_frame_kernel(AnFrameParams P)
     }
     __syncthreads();
     fft_smem<BPT>(s, n, twl, -1, lane, lanes);
-    double *bins = P.bins + (size_t)d * P.m;
+    double *bins = P.bins + (size_t)d * P.m + P.bin_off;
     const int n0 = P.end0 > P.begin0 ? P.end0 - P.begin0 : 0, n1 = P.end1 > P.begin1 ? P.end1 - P.begin1 : 0, ilim = n - 1;
     for (int k = lane; k < n0 + n1; k += lanes) {
         int i = k < n0 ? P.begin0 + k : P.begin1 + (k - n0);
@@ -184,7 +184,9 @@ struct Analyzer {
     double pi_alpha = 0.0, fsclipL = 0.0, fsclipH = 0.0, scale = 0.0, pix_per_bin = 0.0, bin_per_pix = 0.0, det_offset = 0.0;
     double inv_coherent_gain = 1.0, inherent_power_gain = 1.0, inv_enb = 1.0, norm_oneHz = 0.0;
     int fscL = 0, fscH = 0, sample_rate = 0, m = 0;
-    int begin0 = 0, end0 = 0, begin1 = 0, end1 = 0;
+    static constexpr int MAX_STITCH = 4;        // comm.h:124
+    int num_stitch = 1, begin_ss = 0, end_ss = 0, stitch_flag = 0;
+    int begin0[MAX_STITCH] = {0}, end0[MAX_STITCH] = {0}, begin1[MAX_STITCH] = {0}, end1[MAX_STITCH] = {0}, ss_bins[MAX_STITCH] = {0}, ss_off[MAX_STITCH] = {0};
     bool configured = false, span_empty = false;
     // per pixel output (SetDisplay*, analyzer.c:1582-1675)
     int det_type[AN_MAX_PIXOUTS] = {0}, av_mode[AN_MAX_PIXOUTS] = {0}, num_average[AN_MAX_PIXOUTS] = {0}, normalize[AN_MAX_PIXOUTS] = {0};
@@ -192,7 +194,7 @@ struct Analyzer {
     double av_backmult[AN_MAX_PIXOUTS] = {0};
     long frames_done = 0, frames_read[AN_MAX_PIXOUTS] = {0};
     // ring bookkeeping (the same for every display of the batch)
-    int bsize = 0, in_index = 0, out_index = 0, have = 0;
+    int bsize = 0, in_index[MAX_STITCH] = {0}, out_index[MAX_STITCH] = {0}, have[MAX_STITCH] = {0}, busy[MAX_STITCH] = {0};
     // device
     cd *d_ring = nullptr; double *d_window = nullptr, *d_bins = nullptr;
     double *d_t[AN_MAX_PIXOUTS] = {nullptr}, *d_sum[AN_MAX_PIXOUTS] = {nullptr}, *d_avbuf[AN_MAX_PIXOUTS] = {nullptr};
@@ -204,13 +206,15 @@ struct Analyzer {
 
     int init(int D_, int max_size_);
     void release();
-    int set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int max_w_);
+    int set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int n_stch, int max_w_);
     int new_window(int type, int sz, double PiAlpha);
     int build_plan(int det);
     int fill(double *p, double v);
     int set_average_mode(int po, int mode);
-    int frame(cudaStream_t s);
-    int spectrum0(const cd *d_in, long in_stride, cudaStream_t s);
+    int frame(int ss, cudaStream_t s);
+    int stitch(cudaStream_t s);
+    int dispatch(cudaStream_t s);
+    int spectrum0(int ss, const cd *d_in, long in_stride, cudaStream_t s);
 };
 
 int Analyzer::fill(double *p, double v)
@@ -226,10 +230,10 @@ int Analyzer::init(int D_, int max_size_)
 {   // XCreateAnalyzer, analyzer.c:1140-1236
     D = D_; max_size = max_size_;
     bsize = max_size * AN_BUFF_MULT;
-    QC_CUDA(cudaMalloc((void **)&d_ring, (size_t)D * bsize * sizeof(cd)));
-    QC_CUDA(cudaMemset(d_ring, 0, (size_t)D * bsize * sizeof(cd)));
+    QC_CUDA(cudaMalloc((void **)&d_ring, (size_t)MAX_STITCH * D * bsize * sizeof(cd)));
+    QC_CUDA(cudaMemset(d_ring, 0, (size_t)MAX_STITCH * D * bsize * sizeof(cd)));
     QC_CUDA(cudaMalloc((void **)&d_window, (size_t)max_size * sizeof(double)));
-    QC_CUDA(cudaMalloc((void **)&d_bins, (size_t)D * max_size * sizeof(double)));
+    QC_CUDA(cudaMalloc((void **)&d_bins, (size_t)MAX_STITCH * D * max_size * sizeof(double)));
     for (int i = 0; i < AN_MAX_PIXOUTS; i++) {
         QC_CUDA(cudaMalloc((void **)&d_t[i], (size_t)D * AN_MAX_PIXELS * sizeof(double)));
         QC_CUDA(cudaMalloc((void **)&d_sum[i], (size_t)D * AN_MAX_PIXELS * sizeof(double)));
@@ -321,8 +325,9 @@ static double an_host_mlog10(double val)
     return 0.301029995663981 * ((double)e + log10(1.0 + (double)mm / 2048.0) / log10(2.0));
 }
 
-int Analyzer::set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int max_w_)
+int Analyzer::set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int n_stch, int max_w_)
 {
+    if (n_stch < 1 || n_stch > MAX_STITCH) { set_error("analyzer: %d sub-spans (1 .. %d)", n_stch, MAX_STITCH); return QC_EINVAL; }
     if (n_pixout < 1 || n_pixout > AN_MAX_PIXOUTS) { set_error("analyzer: %d pixel outputs (1 .. %d)", n_pixout, AN_MAX_PIXOUTS); return QC_EINVAL; }
     if (sz < 64 || sz > 8192 || (sz & (sz - 1)) || sz > max_size) { set_error("analyzer: transform size %d (a power of two, 64 .. 8192, <= the %d given at creation)", sz, max_size); return QC_EINVAL; }
     if (bf_sz < 1 || bsize % bf_sz) { set_error("analyzer: buffer size %d must divide the ring of %d samples (analyzer.c:1569)", bf_sz, bsize); return QC_EINVAL; }
@@ -337,22 +342,34 @@ int Analyzer::set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double
     num_pixels = n_pix;
     out_size = size;
     scale = 1.0 / ((double)size * (double)size);
+    num_stitch = n_stch;
     fscL = (int)fsclipL; fscH = (int)fsclipH;
     const int usable = out_size - 1 - 2 * clip;
-    span_empty = usable <= 0 || fscL >= usable || fscH >= usable;       // the sub-span would be skipped altogether (analyzer.c:1093-1104)
-    if (span_empty) { set_error("analyzer: clip %d / span clips %g, %g leave no bins of a %d-point transform", clip, fsclipL, fsclipH, size); return QC_EINVAL; }
-    pix_per_bin = (double)num_pixels / ((double)(1 * (out_size - 1 - 2 * clip)) - fsclipL - fsclipH - 1.0);
+    if (usable <= 0) { set_error("analyzer: clip %d leaves no bins of a %d-point transform", clip, size); return QC_EINVAL; }
+    // sub-spans that the span clips remove altogether are skipped (analyzer.c:1093-1104)
+    begin_ss = 0; end_ss = num_stitch - 1;
+    for (int k = 0; k < MAX_STITCH; k++) ss_bins[k] = 0;
+    while (fscL >= usable && begin_ss < num_stitch) { fscL -= usable; begin_ss++; }
+    while (fscH >= usable && end_ss >= 0) { fscH -= usable; end_ss--; }
+    if (begin_ss > end_ss) { set_error("analyzer: span clips %g, %g leave nothing of %d sub-spans of %d bins", fsclipL, fsclipH, num_stitch, usable); return QC_EINVAL; }
+    pix_per_bin = (double)num_pixels / ((double)(num_stitch * (out_size - 1 - 2 * clip)) - fsclipL - fsclipH - 1.0);
     det_offset = -pix_per_bin * (fsclipL - floor(fsclipL));
-    bin_per_pix = ((double)(1 * (out_size - 1 - 2 * clip)) - 1.0 - fsclipL - fsclipH) / ((double)num_pixels - 1.0);
-    // Celiminate's two runs for the only sub-span, which is both the first and the last (analyzer.c:220-246)
-    begin0 = out_size / 2 + 1 + clip + fscL;
-    begin1 = begin0 > out_size ? begin0 - out_size : 0;
-    end1 = out_size / 2 - clip - fscH;
-    end0 = end1 < 0 ? out_size + end1 : out_size;
-    m = (end0 > begin0 ? end0 - begin0 : 0) + (end1 > begin1 ? end1 - begin1 : 0);
+    bin_per_pix = ((double)(num_stitch * (out_size - 1 - 2 * clip)) - 1.0 - fsclipL - fsclipH) / ((double)num_pixels - 1.0);
+    // Celiminate's two runs per sub-span (analyzer.c:220-246): the span clips act on the first and the last one
+    m = 0;
+    for (int ss = begin_ss; ss <= end_ss; ss++) {
+        if (ss == begin_ss) { begin0[ss] = out_size / 2 + 1 + clip + fscL; begin1[ss] = begin0[ss] > out_size ? begin0[ss] - out_size : 0; }
+        else { begin0[ss] = out_size / 2 + 1 + clip; begin1[ss] = 0; }
+        if (ss == end_ss) { end1[ss] = out_size / 2 - clip - fscH; end0[ss] = end1[ss] < 0 ? out_size + end1[ss] : out_size; }
+        else { end0[ss] = out_size; end1[ss] = out_size / 2 - clip; }
+        ss_bins[ss] = (end0[ss] > begin0[ss] ? end0[ss] - begin0[ss] : 0) + (end1[ss] > begin1[ss] ? end1[ss] - begin1[ss] : 0);
+        ss_off[ss] = m;
+        m += ss_bins[ss];
+    }
     if (m < 2) { set_error("analyzer: %d bins left", m); return QC_EINVAL; }
     for (int k = 0; k < 5; k++) plan_ok[k] = false;
-    in_index = out_index = have = 0;
+    for (int k = 0; k < MAX_STITCH; k++) in_index[k] = out_index[k] = have[k] = busy[k] = 0;
+    stitch_flag = 0;
     configured = true;
     return QC_OK;
 }
@@ -466,11 +483,13 @@ int Analyzer::set_average_mode(int po, int mode)
     }
 }
 
-int Analyzer::frame(cudaStream_t s)
-{   // Cspectra + Celiminate + stitch for the frame that starts at out_index
+int Analyzer::frame(int ss, cudaStream_t s)
+{   // Cspectra + Celiminate for sub-span ss, the frame that starts at out_index[ss] (a sub-span the clips removed only reports in)
+    if (ss < begin_ss || ss > end_ss) return QC_OK;
     AnFrameParams F;
-    F.ring = d_ring; F.bsize = bsize; F.idx0 = out_index; F.size = size; F.window = d_window; F.tw = tw; F.bins = d_bins; F.m = m;
-    F.begin0 = begin0; F.end0 = end0; F.begin1 = begin1; F.end1 = end1; F.flip = flip;
+    F.ring = d_ring + (size_t)ss * D * bsize; F.bsize = bsize; F.idx0 = out_index[ss]; F.size = size; F.window = d_window; F.tw = tw;
+    F.bins = d_bins; F.m = m; F.bin_off = ss_off[ss];
+    F.begin0 = begin0[ss]; F.end0 = end0[ss]; F.begin1 = begin1[ss]; F.end1 = end1[ss]; F.flip = flip;
     const int lanes = fft_threads(size);
     const size_t sh = ((size_t)size + fft_tw_entries(size)) * sizeof(cd);
     if (size > 4096) {
@@ -482,6 +501,11 @@ int Analyzer::frame(cudaStream_t s)
     }
     count_launch();
     QC_CUDA_LAUNCH();
+    return QC_OK;
+}
+
+int Analyzer::stitch(cudaStream_t s)
+{   // stitch (analyzer.c:555-600): the sub-spans' bins lie side by side in d_bins already; detector and averager per pixel output
     const double *mt = mlog10_table();
     if (!mt) { set_error("analyzer: table allocation failed"); return QC_ENOMEM; }
     const dim3 gp((num_pixels + 127) / 128, D);
@@ -533,20 +557,44 @@ int Analyzer::frame(cudaStream_t s)
     return QC_OK;
 }
 
-int Analyzer::spectrum0(const cd *d_in, long in_stride, cudaStream_t s)
-{   // Spectrum0 (analyzer.c:1536-1579) + the dispatcher's turn (sendbuf, :884-911) for every frame now complete
-    if (!configured) { set_error("analyzer: SetAnalyzer first"); return QC_EINVAL; }
-    an_store_kernel<<<dim3((buff_size + 127) / 128, D), 128, 0, s>>>(d_in, in_stride, d_ring, bsize, in_index, buff_size);
-    count_launch();
-    QC_CUDA_LAUNCH();
-    have += buff_size;
-    if ((in_index += buff_size) >= bsize) in_index = 0;
-    while (have >= size) {
-        int rc = frame(s); if (rc) return rc;
-        if ((out_index += incr) >= bsize) out_index -= bsize;
-        have -= incr;
+int Analyzer::dispatch(cudaStream_t s)
+{   // the dispatcher's turns (sendbuf, analyzer.c:884-911): a sub-span with `size` samples waiting sends one frame and is then
+    // busy until the stitch that uses it has been made (Cspectra, :713-733)
+    bool again = true;
+    while (again) {
+        again = false;
+        for (int ss = 0; ss < num_stitch; ss++) {
+            if (busy[ss] || have[ss] < size) continue;
+            busy[ss] = 1;
+            int rc = frame(ss, s); if (rc) return rc;
+            if ((out_index[ss] += incr) >= bsize) out_index[ss] -= bsize;
+            have[ss] -= incr;
+            stitch_flag |= 1 << ss;
+            if (stitch_flag == (1 << num_stitch) - 1) {
+                stitch_flag = 0;
+                for (int k = 0; k < MAX_STITCH; k++) busy[k] = 0;
+                rc = stitch(s); if (rc) return rc;
+                again = true;
+            }
+        }
     }
     return QC_OK;
+}
+
+int Analyzer::spectrum0(int ss, const cd *d_in, long in_stride, cudaStream_t s)
+{   // Spectrum0 (analyzer.c:1536-1579), then the dispatcher
+    if (!configured) { set_error("analyzer: SetAnalyzer first"); return QC_EINVAL; }
+    if (ss < 0 || ss >= num_stitch) { set_error("analyzer: sub-span %d of %d", ss, num_stitch); return QC_EINVAL; }
+    an_store_kernel<<<dim3((buff_size + 127) / 128, D), 128, 0, s>>>(d_in, in_stride, d_ring + (size_t)ss * D * bsize, bsize, in_index[ss], buff_size);
+    count_launch();
+    QC_CUDA_LAUNCH();
+    if (have[ss] > max_w) {         // samples arrive faster than frames leave (a sub-span waiting for its neighbours): skip some, analyzer.c:1559-1565
+        if ((out_index[ss] += have[ss] - max_w) >= bsize) out_index[ss] -= bsize;
+        have[ss] = max_w;
+    }
+    have[ss] += buff_size;
+    if ((in_index[ss] += buff_size) >= bsize) in_index[ss] = 0;
+    return dispatch(s);
 }
 
 }  // namespace qc
@@ -567,10 +615,10 @@ qcAnalyzer *quisk_cuda_analyzer_create(int n_displays, int max_size)
 void quisk_cuda_analyzer_destroy(qcAnalyzer *h) { if (h) { h->a.release(); delete h; } }
 
 int quisk_cuda_analyzer_set(qcAnalyzer *h, int n_pixout, int flip, int size, int buff_size, int window_type, double pi_alpha, int overlap, int clip,
-                            double fsclip_low, double fsclip_high, int n_pixels, int max_writeahead)
+                            double fsclip_low, double fsclip_high, int n_pixels, int n_stitch, int max_writeahead)
 {
     if (!h) return QC_EINVAL;
-    return h->a.set(n_pixout, flip, size, buff_size, window_type, pi_alpha, overlap, clip, fsclip_low, fsclip_high, n_pixels, max_writeahead);
+    return h->a.set(n_pixout, flip, size, buff_size, window_type, pi_alpha, overlap, clip, fsclip_low, fsclip_high, n_pixels, n_stitch, max_writeahead);
 }
 
 int quisk_cuda_analyzer_set_detector_mode(qcAnalyzer *h, int pixout, int mode)
@@ -622,10 +670,10 @@ int quisk_cuda_analyzer_set_norm_onehz(qcAnalyzer *h, int pixout, int norm)
     return QC_OK;
 }
 
-int quisk_cuda_analyzer_spectrum0(qcAnalyzer *h, const void *d_samples, long stride, void *stream)
+int quisk_cuda_analyzer_spectrum0(qcAnalyzer *h, int ss, const void *d_samples, long stride, void *stream)
 {
     if (!h || !d_samples) return QC_EINVAL;
-    return h->a.spectrum0((const double2 *)d_samples, stride, (cudaStream_t)stream);
+    return h->a.spectrum0(ss, (const double2 *)d_samples, stride, (cudaStream_t)stream);
 }
 
 int quisk_cuda_analyzer_get_pixels(qcAnalyzer *h, int pixout, float *h_pixels, int *flag)

@@ -33,17 +33,22 @@ CASES = {
                     outs=[(2, 0, 1, 0.0, 0), (0, 0, 1, 0.0, 0)]),
     "hamming_rect256": dict(sz=256, hop=256, win=4, pa=0.0, clip=0, fl=2.75, fh=0.0, npix=100, flip=1, rate=48000,
                             outs=[(3, 0, 1, 0.0, 0), (1, 3, 1, 0.3, 0)]),
+    # stitched spans: three sub-spans of which the low span clip removes the first one and a part of the second; two with overlap
+    "stitch3_skip": dict(sz=1024, hop=1024, win=2, pa=0.0, clip=20, fl=1100.5, fh=30.25, npix=900, flip=0, rate=192000, stitch=3,
+                         outs=[(0, 0, 1, 0.0, 0), (2, 1, 1, 0.7, 0)]),
+    "stitch2_overlap": dict(sz=512, hop=256, win=1, pa=0.0, clip=8, fl=0.0, fh=0.0, npix=1200, flip=0, rate=96000, stitch=2,
+                            outs=[(1, 0, 1, 0.0, 0), (4, 2, 3, 0.0, 0)]),
 }
 
 
-def analyzer_input(name, n):
-    """tones over noise with a level step, different per case"""
-    seed = sum(map(ord, name))
+def analyzer_input(name, n, ss=0):
+    """tones over noise with a level step, different per case and sub-span"""
+    seed = sum(map(ord, name)) + 1000 * ss
     rng = np.random.default_rng(seed)
     t = np.arange(n)
     x = 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
     for f, a in ((0.0131, 0.5), (-0.21, 0.2), (0.3777, 0.05), (-0.4402, 0.8)):
-        x += a * np.exp(2j * np.pi * f * t)
+        x += a * np.exp(2j * np.pi * (f + 0.017 * ss) * t)
     x[n // 2:] *= 0.3
     return x.astype(np.complex128)
 
@@ -77,7 +82,8 @@ def run_case(lib, disp, name, cfg):
     """one configuration through the reference's own entry points; returns {key: [FRAMES][pixels] float32} per pixel output"""
     I = C.c_int
     ok = I(1)
-    lib.XCreateAnalyzer(disp, C.byref(ok), 16384, 1, 1, b"")
+    nst = cfg.get("stitch", 1)
+    lib.XCreateAnalyzer(disp, C.byref(ok), 16384, 1, 4, b"")
     assert ok.value == 0
     lib.SetDisplaySampleRate(disp, cfg["rate"])
     for po, (det, av, num, back, norm) in enumerate(cfg["outs"]):
@@ -88,15 +94,18 @@ def run_case(lib, disp, name, cfg):
         lib.SetDisplayNormOneHz(disp, po, norm)
     flip = (I * 1)(cfg["flip"])
     lib.SetAnalyzer(disp, len(cfg["outs"]), 1, 1, flip, cfg["sz"], cfg["hop"], cfg["win"], D(cfg["pa"]), cfg["sz"] - cfg["hop"], cfg["clip"],
-                    D(cfg["fl"]), D(cfg["fh"]), cfg["npix"], 1, 0, D(0.0), D(0.0), 2 * cfg["sz"])
+                    D(cfg["fl"]), D(cfg["fh"]), cfg["npix"], nst, 0, D(0.0), D(0.0), 2 * cfg["sz"])
     calls = cfg["sz"] // cfg["hop"] - 1 + FRAMES
-    x = analyzer_input(name, calls * cfg["hop"])
+    xs = [analyzer_input(name, calls * cfg["hop"], ss) for ss in range(nst)]
     per_call = frames_expected(cfg, calls)
     pix = [[] for _ in cfg["outs"]]
     buf = np.zeros(cfg["hop"], dtype=np.complex128)
     for k in range(calls):
-        buf[:] = x[k * cfg["hop"]:(k + 1) * cfg["hop"]]
-        lib.Spectrum0(1, disp, 0, 0, buf.ctypes.data_as(C.c_void_p))
+        for ss in range(nst):       # one hop into every sub-span; the line is stitched when the last one has reported
+            buf[:] = xs[ss][k * cfg["hop"]:(k + 1) * cfg["hop"]]
+            lib.Spectrum0(1, disp, ss, 0, buf.ctypes.data_as(C.c_void_p))
+            if ss + 1 < nst and per_call[k]:
+                time.sleep(0.02)    # let the dispatcher send this sub-span's frame before the next one fills
         assert per_call[k] in (0, 1)
         if per_call[k]:
             for po in range(len(cfg["outs"])):

@@ -1,4 +1,4 @@
-"""The analyzer fixtures are what the COMPILED REFERENCE produces: two of the configurations are run again through
+"""The analyzer fixtures are what the COMPILED REFERENCE produces: three of the configurations (one of them a stitched span) are run again through
 oracle/_ref/libwdsp_ref.so (XCreateAnalyzer / SetAnalyzer / Spectrum0 / GetPixels on the reference's own worker threads)
 and must reproduce the committed lines bit for bit.  Skipped where oracle/_ref is not built."""
 import numpy as np
@@ -11,7 +11,7 @@ from tests.util import golden
 pytestmark = pytest.mark.skipif(not R.have_ref("libwdsp_ref.so"), reason="oracle/_ref not built")
 
 
-@pytest.mark.parametrize("disp,name", [(40, "hamming_rect256"), (41, "kaiser2048")])
+@pytest.mark.parametrize("disp,name", [(40, "hamming_rect256"), (41, "kaiser2048"), (42, "stitch3_skip")])
 def test_fixture_is_the_reference(disp, name):
     lib = bind(R.load("libwdsp_ref.so"))
     kat = golden("wdsp_analyzer_kat.npz")
