@@ -65,8 +65,8 @@ int quisk_cuda_emnr_set_gain_method(qcEmnr *e, int method);             /* SetRX
 int quisk_cuda_emnr_set_npe_method(qcEmnr *e, int method);              /* SetRXAEMNRnpeMethod,  emnr.c:1119-1125 */
 int quisk_cuda_emnr_set_ae_run(qcEmnr *e, int run);                     /* SetRXAEMNRaeRun,      emnr.c:1127-1133 */
 
-/* ---- analyzer: WDSP's spectrum engine (wdsp/analyzer.c) for a batch of displays that share one configuration: complex input,
- * one LO per sub-span, up to four stitched sub-spans, no calibration table (SetAnalyzer with typ = 1, n_fft = 1, fmin = fmax = 0).
+/* ---- analyzer: WDSP's spectrum engine (wdsp/analyzer.c) for a batch of displays that share one configuration: complex or real input,
+ * one LO per sub-span, up to four stitched sub-spans, no calibration table (SetAnalyzer with n_fft = 1, fmin = fmax = 0; input_type = typ: 0 real, the I rail alone, 1 complex).
  * create = XCreateAnalyzer (analyzer.c:1140); set = SetAnalyzer (:999-1137; size a power of two 64 .. 8192, overlap in samples,
  * clip / fsclip_low / fsclip_high in bins); set_detector_mode .. set_norm_onehz = SetDisplayDetectorMode (0 peak, 1 rosenfell,
  * 2 average, 3 sample, 4 rms), SetDisplayAverageMode (-1 peak hold, 0 none, 1 recursive, 2 window, 3 recursive on the log),
@@ -78,7 +78,7 @@ int quisk_cuda_emnr_set_ae_run(qcEmnr *e, int run);                     /* SetRX
 typedef struct qcAnalyzer qcAnalyzer;
 qcAnalyzer *quisk_cuda_analyzer_create(int n_displays, int max_size);
 void quisk_cuda_analyzer_destroy(qcAnalyzer *an);
-int quisk_cuda_analyzer_set(qcAnalyzer *an, int n_pixout, int flip, int size, int buff_size, int window_type, double pi_alpha, int overlap, int clip,
+int quisk_cuda_analyzer_set(qcAnalyzer *an, int n_pixout, int input_type, int flip, int size, int buff_size, int window_type, double pi_alpha, int overlap, int clip,
                             double fsclip_low, double fsclip_high, int n_pixels, int n_stitch, int max_writeahead);
 int quisk_cuda_analyzer_set_detector_mode(qcAnalyzer *an, int pixout, int mode);
 int quisk_cuda_analyzer_set_average_mode(qcAnalyzer *an, int pixout, int mode);

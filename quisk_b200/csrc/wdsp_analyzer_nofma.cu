@@ -7,7 +7,8 @@
 // average / sample / rms, or linear interpolation when there are more pixels than bins) and the averager (:463-553: peak
 // hold, none, recursive, window, recursive on the log; 10 mlog10 -> float), once per pixel output; GetPixels (:1315-1334)
 // copies the newest line.  One LO per sub-span (this reference build has dMAX_NUM_FFT = 1, comm.h:125), up to four stitched sub-spans, no
-// calibration table (SetAnalyzer with typ = 1, n_fft = 1, fmin = fmax = 0); real input (typ = 0) is not built.
+// calibration table (SetAnalyzer with n_fft = 1, fmin = fmax = 0); complex input (Cspectra / Celiminate) or real input
+// (spectra / eliminate, :179-212, 602-668: the I rail alone, bins 0 .. size / 2).
 //
 // Here: D displays share one configuration and run side by side.  Per frame three launches: (1) one CTA per display:
 // ring -> window -> shared-memory transform -> |X|^2 in Celiminate's order; (2) the detector, a thread per pixel.  Which
@@ -33,7 +34,8 @@ struct AnFrameParams {
     const cd *ring; int bsize, idx0, size;      // [D][bsize] samples as Spectrum0 stored them (x = I, y = Q)
     const double *window; const cd *tw;
     double *bins; int m, bin_off;               // [D][m]: this sub-span's bins start at bin_off
-    int begin0, end0, begin1, end1, flip;       // Celiminate's two runs over the transform's output
+    int begin0, end0, begin1, end1, flip;       // Celiminate's two runs over the transform's output (eliminate's one run for real input)
+    int real, out_size;                         // real input: only I enters the transform, bins 0 .. size / 2 come out
 };
 
 template <int BPT>
@@ -50,12 +52,12 @@ __global__ void __launch_bounds__(256) an_frame_kernel(AnFrameParams P)
         if (j >= P.bsize) j -= P.bsize;
         const cd v = ring[j];
         const double w = P.window[i];
-        s[fsw(i)] = make_double2(w * v.x, w * v.y);             // analyzer.c:688-689
+        s[fsw(i)] = make_double2(w * v.x, P.real ? 0.0 : w * v.y);   // analyzer.c:688-689 (complex), :620 (real: I only)
     }
     __syncthreads();
     fft_smem<BPT>(s, n, twl, -1, lane, lanes);
     double *bins = P.bins + (size_t)d * P.m + P.bin_off;
-    const int n0 = P.end0 > P.begin0 ? P.end0 - P.begin0 : 0, n1 = P.end1 > P.begin1 ? P.end1 - P.begin1 : 0, ilim = n - 1;
+    const int n0 = P.end0 > P.begin0 ? P.end0 - P.begin0 : 0, n1 = P.end1 > P.begin1 ? P.end1 - P.begin1 : 0, ilim = P.out_size - 1;
     for (int k = lane; k < n0 + n1; k += lanes) {
         int i = k < n0 ? P.begin0 + k : P.begin1 + (k - n0);
         if (P.flip) i = ilim - i;                               // analyzer.c:250-263: the same runs walked from the other end
@@ -180,7 +182,7 @@ static double an_bessi0(double x)
 struct Analyzer {
     int D = 0, max_size = 0;
     // SetAnalyzer's arguments and what it derives (analyzer.c:999-1137)
-    int num_pixout = 0, flip = 0, size = -1, buff_size = 0, window_type = -1, overlap = 0, clip = 0, num_pixels = -1, incr = 0, out_size = 0, max_w = 0;
+    int num_pixout = 0, type = 1, flip = 0, size = -1, buff_size = 0, window_type = -1, overlap = 0, clip = 0, num_pixels = -1, incr = 0, out_size = 0, max_w = 0;
     double pi_alpha = 0.0, fsclipL = 0.0, fsclipH = 0.0, scale = 0.0, pix_per_bin = 0.0, bin_per_pix = 0.0, det_offset = 0.0;
     double inv_coherent_gain = 1.0, inherent_power_gain = 1.0, inv_enb = 1.0, norm_oneHz = 0.0;
     int fscL = 0, fscH = 0, sample_rate = 0, m = 0;
@@ -206,7 +208,7 @@ struct Analyzer {
 
     int init(int D_, int max_size_);
     void release();
-    int set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int n_stch, int max_w_);
+    int set(int n_pixout, int typ, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int n_stch, int max_w_);
     int new_window(int type, int sz, double PiAlpha);
     int build_plan(int det);
     int fill(double *p, double v);
@@ -325,7 +327,7 @@ static double an_host_mlog10(double val)
     return 0.301029995663981 * ((double)e + log10(1.0 + (double)mm / 2048.0) / log10(2.0));
 }
 
-int Analyzer::set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int n_stch, int max_w_)
+int Analyzer::set(int n_pixout, int typ, int flp, int sz, int bf_sz, int win_type, double pi, int ovrlp, int clp, double fscLin, double fscHin, int n_pix, int n_stch, int max_w_)
 {
     if (n_stch < 1 || n_stch > MAX_STITCH) { set_error("analyzer: %d sub-spans (1 .. %d)", n_stch, MAX_STITCH); return QC_EINVAL; }
     if (n_pixout < 1 || n_pixout > AN_MAX_PIXOUTS) { set_error("analyzer: %d pixel outputs (1 .. %d)", n_pixout, AN_MAX_PIXOUTS); return QC_EINVAL; }
@@ -333,15 +335,16 @@ int Analyzer::set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double
     if (bf_sz < 1 || bsize % bf_sz) { set_error("analyzer: buffer size %d must divide the ring of %d samples (analyzer.c:1569)", bf_sz, bsize); return QC_EINVAL; }
     if (ovrlp < 0 || ovrlp >= sz || clp < 0 || fscLin < 0.0 || fscHin < 0.0 || n_pix < 2 || n_pix > AN_MAX_PIXELS) { set_error("analyzer: overlap / clip / pixel count out of range"); return QC_EINVAL; }
     QC_CUDA(cudaDeviceSynchronize());
-    num_pixout = n_pixout; flip = flp ? 1 : 0; buff_size = bf_sz; overlap = ovrlp; clip = clp; fsclipL = fscLin; fsclipH = fscHin;
+    if (typ != 0 && typ != 1) { set_error("analyzer: input type %d (0 real, 1 complex)", typ); return QC_EINVAL; }
+    num_pixout = n_pixout; type = typ; flip = flp ? 1 : 0; buff_size = bf_sz; overlap = ovrlp; clip = clp; fsclipL = fscLin; fsclipH = fscHin;
     if (sz != size || win_type != window_type || pi != pi_alpha) { int rc = new_window(win_type, sz, pi); if (rc) return rc; }
     if (sz != size) { tw = fft_twiddles(sz); if (!tw) { set_error("analyzer: twiddle table allocation failed"); return QC_ENOMEM; } }
     size = sz; window_type = win_type; pi_alpha = pi; max_w = max_w_;
     norm_oneHz = sample_rate > 0 ? 10.0 * an_host_mlog10(1.0 / ((double)sample_rate / (double)size)) : 0.0;
     incr = size - overlap;
     num_pixels = n_pix;
-    out_size = size;
-    scale = 1.0 / ((double)size * (double)size);
+    if (type == 0) { out_size = size / 2 + 1; scale = 4.0 / ((double)size * (double)size); }        // analyzer.c:1078-1087
+    else { out_size = size; scale = 1.0 / ((double)size * (double)size); }
     num_stitch = n_stch;
     fscL = (int)fsclipL; fscH = (int)fsclipH;
     const int usable = out_size - 1 - 2 * clip;
@@ -358,10 +361,16 @@ int Analyzer::set(int n_pixout, int flp, int sz, int bf_sz, int win_type, double
     // Celiminate's two runs per sub-span (analyzer.c:220-246): the span clips act on the first and the last one
     m = 0;
     for (int ss = begin_ss; ss <= end_ss; ss++) {
-        if (ss == begin_ss) { begin0[ss] = out_size / 2 + 1 + clip + fscL; begin1[ss] = begin0[ss] > out_size ? begin0[ss] - out_size : 0; }
-        else { begin0[ss] = out_size / 2 + 1 + clip; begin1[ss] = 0; }
-        if (ss == end_ss) { end1[ss] = out_size / 2 - clip - fscH; end0[ss] = end1[ss] < 0 ? out_size + end1[ss] : out_size; }
-        else { end0[ss] = out_size; end1[ss] = out_size / 2 - clip; }
+        if (type == 0) {            // eliminate, analyzer.c:179-212: one run
+            begin0[ss] = ss == begin_ss ? fscL + clip : clip;
+            end0[ss] = ss == end_ss ? out_size - 1 - clip - fscH : out_size - 1 - clip;
+            begin1[ss] = end1[ss] = 0;
+        } else {
+            if (ss == begin_ss) { begin0[ss] = out_size / 2 + 1 + clip + fscL; begin1[ss] = begin0[ss] > out_size ? begin0[ss] - out_size : 0; }
+            else { begin0[ss] = out_size / 2 + 1 + clip; begin1[ss] = 0; }
+            if (ss == end_ss) { end1[ss] = out_size / 2 - clip - fscH; end0[ss] = end1[ss] < 0 ? out_size + end1[ss] : out_size; }
+            else { end0[ss] = out_size; end1[ss] = out_size / 2 - clip; }
+        }
         ss_bins[ss] = (end0[ss] > begin0[ss] ? end0[ss] - begin0[ss] : 0) + (end1[ss] > begin1[ss] ? end1[ss] - begin1[ss] : 0);
         ss_off[ss] = m;
         m += ss_bins[ss];
@@ -489,7 +498,7 @@ int Analyzer::frame(int ss, cudaStream_t s)
     AnFrameParams F;
     F.ring = d_ring + (size_t)ss * D * bsize; F.bsize = bsize; F.idx0 = out_index[ss]; F.size = size; F.window = d_window; F.tw = tw;
     F.bins = d_bins; F.m = m; F.bin_off = ss_off[ss];
-    F.begin0 = begin0[ss]; F.end0 = end0[ss]; F.begin1 = begin1[ss]; F.end1 = end1[ss]; F.flip = flip;
+    F.begin0 = begin0[ss]; F.end0 = end0[ss]; F.begin1 = begin1[ss]; F.end1 = end1[ss]; F.flip = flip; F.real = type == 0; F.out_size = out_size;
     const int lanes = fft_threads(size);
     const size_t sh = ((size_t)size + fft_tw_entries(size)) * sizeof(cd);
     if (size > 4096) {
@@ -614,11 +623,11 @@ qcAnalyzer *quisk_cuda_analyzer_create(int n_displays, int max_size)
 
 void quisk_cuda_analyzer_destroy(qcAnalyzer *h) { if (h) { h->a.release(); delete h; } }
 
-int quisk_cuda_analyzer_set(qcAnalyzer *h, int n_pixout, int flip, int size, int buff_size, int window_type, double pi_alpha, int overlap, int clip,
+int quisk_cuda_analyzer_set(qcAnalyzer *h, int n_pixout, int input_type, int flip, int size, int buff_size, int window_type, double pi_alpha, int overlap, int clip,
                             double fsclip_low, double fsclip_high, int n_pixels, int n_stitch, int max_writeahead)
 {
     if (!h) return QC_EINVAL;
-    return h->a.set(n_pixout, flip, size, buff_size, window_type, pi_alpha, overlap, clip, fsclip_low, fsclip_high, n_pixels, n_stitch, max_writeahead);
+    return h->a.set(n_pixout, input_type, flip, size, buff_size, window_type, pi_alpha, overlap, clip, fsclip_low, fsclip_high, n_pixels, n_stitch, max_writeahead);
 }
 
 int quisk_cuda_analyzer_set_detector_mode(qcAnalyzer *h, int pixout, int mode)

@@ -188,7 +188,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_analyzer_create.argtypes = [C.c_int, C.c_int]
     lib.quisk_cuda_analyzer_destroy.restype = None
     lib.quisk_cuda_analyzer_destroy.argtypes = [vp]
-    lib.quisk_cuda_analyzer_set.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
+    lib.quisk_cuda_analyzer_set.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int]
     for fn in ("set_detector_mode", "set_average_mode", "set_num_average", "set_norm_onehz"):
         getattr(lib, "quisk_cuda_analyzer_" + fn).argtypes = [vp, C.c_int, C.c_int]
     lib.quisk_cuda_analyzer_set_av_backmult.argtypes = [vp, C.c_int, C.c_double]

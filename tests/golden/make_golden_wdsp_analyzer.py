@@ -36,6 +36,11 @@ CASES = {
     # stitched spans: three sub-spans of which the low span clip removes the first one and a part of the second; two with overlap
     "stitch3_skip": dict(sz=1024, hop=1024, win=2, pa=0.0, clip=20, fl=1100.5, fh=30.25, npix=900, flip=0, rate=192000, stitch=3,
                          outs=[(0, 0, 1, 0.0, 0), (2, 1, 1, 0.7, 0)]),
+    # real input (typ = 0): the I rail alone, bins 0 .. size / 2, eliminate instead of Celiminate
+    "real2048": dict(sz=2048, hop=1024, win=2, pa=0.0, clip=5, fl=3.5, fh=2.0, npix=600, flip=0, rate=48000, typ=0,
+                     outs=[(0, 0, 1, 0.0, 0), (2, 1, 1, 0.6, 0), (1, 0, 1, 0.0, 0)]),
+    "real512_flip_stitch2": dict(sz=512, hop=512, win=4, pa=0.0, clip=2, fl=0.0, fh=0.0, npix=1000, flip=1, rate=48000, typ=0, stitch=2,
+                                 outs=[(3, 0, 1, 0.0, 0), (0, 3, 1, 0.5, 0)]),
     "stitch2_overlap": dict(sz=512, hop=256, win=1, pa=0.0, clip=8, fl=0.0, fh=0.0, npix=1200, flip=0, rate=96000, stitch=2,
                             outs=[(1, 0, 1, 0.0, 0), (4, 2, 3, 0.0, 0)]),
 }
@@ -93,7 +98,7 @@ def run_case(lib, disp, name, cfg):
         lib.SetDisplayAvBackmult(disp, po, D(back))
         lib.SetDisplayNormOneHz(disp, po, norm)
     flip = (I * 1)(cfg["flip"])
-    lib.SetAnalyzer(disp, len(cfg["outs"]), 1, 1, flip, cfg["sz"], cfg["hop"], cfg["win"], D(cfg["pa"]), cfg["sz"] - cfg["hop"], cfg["clip"],
+    lib.SetAnalyzer(disp, len(cfg["outs"]), 1, cfg.get("typ", 1), flip, cfg["sz"], cfg["hop"], cfg["win"], D(cfg["pa"]), cfg["sz"] - cfg["hop"], cfg["clip"],
                     D(cfg["fl"]), D(cfg["fh"]), cfg["npix"], nst, 0, D(0.0), D(0.0), 2 * cfg["sz"])
     calls = cfg["sz"] // cfg["hop"] - 1 + FRAMES
     xs = [analyzer_input(name, calls * cfg["hop"], ss) for ss in range(nst)]

@@ -1,7 +1,7 @@
 """GPU parity of WDSP's spectrum engine (wdsp/analyzer.c) against fixtures from the compiled reference
 (tests/golden/make_golden_wdsp_analyzer.py): six configurations that between them use every window, every detector, every
 averaging mode, overlap, integer and fractional clipping of the span, a flipped LO, the interpolating branch (more pixels than
-bins), the 1 Hz normalisation, and two stitched spans (three sub-spans of which the span clip removes one and a half;
+bins), the 1 Hz normalisation, real input, and two stitched spans (three sub-spans of which the span clip removes one and a half;
 two with overlap); ten frames each, every pixel output of every frame.  Pixels are float32 dB.  The detector's
 index arithmetic, the averagers and mlog10 are the reference's expressions with separately rounded products and sums; what
 differs is the transform (ours against the reference's FFTW-API shim, 1e-15 relative per bin).  mlog10 is a table look-up on
@@ -50,7 +50,7 @@ def test_analyzer(name, torch, lib, kat):
         assert lib.quisk_cuda_analyzer_set_num_average(an, po, num) == 0
         assert lib.quisk_cuda_analyzer_set_av_backmult(an, po, back) == 0
         assert lib.quisk_cuda_analyzer_set_norm_onehz(an, po, norm) == 0
-    assert lib.quisk_cuda_analyzer_set(an, len(cfg["outs"]), cfg["flip"], cfg["sz"], cfg["hop"], cfg["win"], cfg["pa"], cfg["sz"] - cfg["hop"], cfg["clip"],
+    assert lib.quisk_cuda_analyzer_set(an, len(cfg["outs"]), cfg.get("typ", 1), cfg["flip"], cfg["sz"], cfg["hop"], cfg["win"], cfg["pa"], cfg["sz"] - cfg["hop"], cfg["clip"],
                                        cfg["fl"], cfg["fh"], cfg["npix"], cfg.get("stitch", 1), 2 * cfg["sz"]) == 0, lib.quisk_cuda_last_error()
     calls = cfg["sz"] // cfg["hop"] - 1 + FRAMES
     nst = cfg.get("stitch", 1)
@@ -84,13 +84,13 @@ def test_analyzer(name, torch, lib, kat):
 def test_analyzer_rejects_what_it_does_not_build(lib):
     an = lib.quisk_cuda_analyzer_create(1, 4096)
     assert an
-    assert lib.quisk_cuda_analyzer_set(an, 1, 0, 3000, 3000, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # not a power of two
-    assert lib.quisk_cuda_analyzer_set(an, 1, 0, 8192, 8192, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # larger than created
-    assert lib.quisk_cuda_analyzer_set(an, 5, 0, 1024, 1024, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # pixel outputs
-    assert lib.quisk_cuda_analyzer_set(an, 1, 0, 1024, 1024, 9, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # window type
-    assert lib.quisk_cuda_analyzer_set(an, 1, 0, 1024, 1024, 2, 0.0, 0, 600, 0.0, 0.0, 512, 1, 6000) != 0      # clip leaves nothing
-    assert lib.quisk_cuda_analyzer_set(an, 1, 0, 1024, 1024, 2, 0.0, 0, 0, 0.0, 0.0, 512, 5, 6000) != 0        # sub-spans
+    assert lib.quisk_cuda_analyzer_set(an, 1, 1, 0, 3000, 3000, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # not a power of two
+    assert lib.quisk_cuda_analyzer_set(an, 1, 1, 0, 8192, 8192, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # larger than created
+    assert lib.quisk_cuda_analyzer_set(an, 5, 1, 0, 1024, 1024, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # pixel outputs
+    assert lib.quisk_cuda_analyzer_set(an, 1, 1, 0, 1024, 1024, 9, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) != 0        # window type
+    assert lib.quisk_cuda_analyzer_set(an, 1, 1, 0, 1024, 1024, 2, 0.0, 0, 600, 0.0, 0.0, 512, 1, 6000) != 0      # clip leaves nothing
+    assert lib.quisk_cuda_analyzer_set(an, 1, 1, 0, 1024, 1024, 2, 0.0, 0, 0, 0.0, 0.0, 512, 5, 6000) != 0        # sub-spans
     assert lib.quisk_cuda_analyzer_set_detector_mode(an, 0, 7) != 0
-    assert lib.quisk_cuda_analyzer_set(an, 1, 0, 1024, 1024, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) == 0
+    assert lib.quisk_cuda_analyzer_set(an, 1, 1, 0, 1024, 1024, 2, 0.0, 0, 0, 0.0, 0.0, 512, 1, 6000) == 0
     assert abs(lib.quisk_cuda_analyzer_get_enb(an) - 1.5) < 0.01                                            # Hann: 1.5 bins
     lib.quisk_cuda_analyzer_destroy(an)
