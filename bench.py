@@ -603,7 +603,7 @@ def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq,
         for opt, val in ((2, args.chunk), (3, args.threads), (4, args.min_r), (8, args.deepk)):
             if val:
                 rx.set_option(opt, val)
-        for opt, val in ((5, args.dense), (6, args.plans), (11, args.split), (12, args.tailwarp)):
+        for opt, val in ((5, args.dense), (6, args.plans), (11, args.split), (12, args.tailwarp), (19, args.async_load), (20, args.p3)):
             if val >= 0:
                 rx.set_option(opt, val)
         if args.nco == "closed":
@@ -791,6 +791,8 @@ def main():
     ap.add_argument("--plans", type=int, default=-1, help="fused decimator: 0 = generic kernel only")
     ap.add_argument("--split", type=int, default=-1, help="fused decimator: 1 = one lane per component in the half bands (default), 0 = complex lanes")
     ap.add_argument("--tailwarp", type=int, default=-1, help="fused decimator: 1 = low-rate stages on a fifth warp (default), 0 = all stages on the four main warps")
+    ap.add_argument("--async-load", type=int, default=-1, help="fused decimator (tail-warp kernel): 1 = next chunk by cp.async into stage 0's buffer, 2 = same under a 128-register cap, 0 = register prefetch")
+    ap.add_argument("--p3", type=int, default=-1, help="fused decimator: 1 = three-group pipeline kernel, 0 = tail-warp kernel")
     ap.add_argument("--deepk", type=int, default=0, help="fused decimator: low-rate stages every k chunks (1 or 4)")
     ap.add_argument("--nco", default="exact", choices=["exact", "closed"], help="tuning phasor at block starts: the reference's recurrence (default) or closed form only")
     ap.add_argument("--host-chunks", type=int, default=-1, help="host entry points: channel chunks pipelined over copy / compute streams (-1 = library default)")

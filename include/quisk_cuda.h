@@ -262,7 +262,12 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_FUSED_PLANS  6   /* 1 (default): use plan-specialised kernels when the stage list matches one */
 #define QC_RX_OPT_FUSED_DENSE  5   /* 1: 128-register cap (more resident CTAs), 0: up to 255 registers */
 #define QC_RX_OPT_FUSED_TAILWARP 12 /* plan kernels run the low-rate stages on two tail warps, one chunk behind the four main warps: 1 (default: from stage 3), 2..4 = first tail stage, 0 = off */
-#define QC_RX_OPT_FUSED_SPLIT 11   /* 1: half-band stages of the plan kernels run one lane per component, twice the outputs per lane */
+#define QC_RX_OPT_FUSED_P3    20   /* 1: three-group pipeline kernel (commit + half band 0 | half bands 1-2 | the low-rate stages, each one chunk
+                                      behind the one in front), 0: tail-warp kernel */
+#define QC_RX_OPT_FUSED_ASYNC 19   /* tail-warp kernel: the next chunk travels by cp.async straight into stage 0's shared-memory buffer instead of
+                                      waiting in registers: 1 = on, 2 = on under a 128-register cap, 0 = register prefetch */
+#define QC_RX_OPT_FUSED_SPLIT 11   /* half-band stages of the plan kernels with one lane per component, twice the outputs per lane: 0 = off, 1 = on,
+                                      2 (default) = in the tail-warp kernel only, behind its first half band (measured +3 %, bit-identical) */
 #define QC_RX_OPT_NOISE_BLANKER 13  /* quisk_noise_blanker (0 = off, 1..3): quisk_cuda_rx_process_host / _host_packed run NoiseBlanker
                                       (quisk.c:679-784) on the staged block in front of the tuning stage, as quisk_process_samples
                                       does (quisk.c:2448-2449).  The device entry leaves the caller's buffer alone: run quisk_cuda_nb_run first */

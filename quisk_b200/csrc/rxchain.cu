@@ -278,7 +278,7 @@ int RxChain::build_sub_chains(int k)
         if (r->init(cfg) != QC_OK) { r->release(); delete r; release_sub_chains(); return QC_EINVAL; }
         r->host_chunks = 1;
         r->exact_nco = exact_nco; r->fused_tail = fused_tail; r->nb_level = nb_level; r->auto_notch = auto_notch; r->notch_sidetone = notch_sidetone; r->squelch_level = squelch_level; r->fused_chunk = fused_chunk; r->fused_threads = fused_threads;
-        r->fused_plans = fused_plans; r->fused_tailwarp = fused_tailwarp; r->fused_dense = fused_dense; r->fused_split = fused_split;
+        r->fused_plans = fused_plans; r->fused_tailwarp = fused_tailwarp; r->fused_dense = fused_dense; r->fused_split = fused_split; r->fused_async = fused_async; r->fused_p3 = fused_p3;
         r->fused_min_r = fused_min_r; r->fused_deepk = fused_deepk;
         sub.push_back(r); sub_c0.push_back(c0);
     }
@@ -684,7 +684,13 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
     case QC_RX_OPT_FUSED_DENSE: rx->rx.fused_dense = value; return QC_OK;
     case QC_RX_OPT_FUSED_TAILWARP: if (value < 0 || value > 4) { qc::set_error("rx_set_option: tail-warp split must be 0 (off), 1 (default) or the first tail stage 2..4"); return QC_EINVAL; }
         rx->rx.fused_tailwarp = value; return QC_OK;
-    case QC_RX_OPT_FUSED_SPLIT: rx->rx.fused_split = value != 0; return QC_OK;
+    case QC_RX_OPT_FUSED_SPLIT:
+        if (value < 0 || value > 2) { qc::set_error("rx_set_option: split must be 0, 1 or 2"); return QC_EINVAL; }
+        rx->rx.fused_split = value; return QC_OK;
+    case QC_RX_OPT_FUSED_P3: rx->rx.fused_p3 = value != 0; return QC_OK;
+    case QC_RX_OPT_FUSED_ASYNC:
+        if (value < 0 || value > 2) { qc::set_error("rx_set_option: async chunk loads must be 0, 1 or 2"); return QC_EINVAL; }
+        rx->rx.fused_async = value; return QC_OK;
     case QC_RX_OPT_FUSED_MIN_R:
         if (value != 0 && value != 2 && value != 4 && value != 8) { qc::set_error("rx_set_option: min R must be 0/2/4/8"); return QC_EINVAL; }
         rx->rx.fused_min_r = value; return QC_OK;

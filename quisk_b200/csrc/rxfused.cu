@@ -66,6 +66,7 @@ struct FusedParams {
     int scratch;        // offset of the history-slide scratch area (cd units)
     int coef_sm;        // offset of the tap copy in shared memory (cd units)
     int ncoef;
+    int ab_stride;      // three-group kernel: distance (cd units) between the two halves of stage 1's input buffer
     int tw_stride;      // tail-warp kernel: distance (cd units) between the two halves of the first tail stage's input buffer
     int deepk;          // multi-rate plans: the deep stages run once per this many chunks
     long long *trace;   // optional [C][16 chunks][16] clock64() stamps (debug)
@@ -328,6 +329,7 @@ template <int SYNC> __device__ __forceinline__ void group_sync()
 {
     if constexpr (SYNC == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
     else if constexpr (SYNC == 2) asm volatile("bar.sync 6, 64;" ::: "memory");
+    else if constexpr (SYNC == 3) asm volatile("bar.sync 7, 64;" ::: "memory");
     else __syncthreads();
 }
 
@@ -350,6 +352,7 @@ __device__ __forceinline__ int cascade_x(cd *sm, const FusedParams &P, int n_in,
         }
         const cd *sb = sm + S.buf + (IDX == START ? src_off : 0);
         if constexpr (TYPE == 0) hb_stage<R>(sb, S.p0, n_out, sink, t);
+        else if constexpr (TYPE == 2) hb_stage_split<2 * R, LAST>(sb, S.p0, n_out, sink, t);
         else fir_stage_c<D, NT, R, LAST>(sb, S, ft.cf[FIRIDX], n_out, sink, t);
         group_sync<SYNC>();
     }
@@ -638,8 +641,22 @@ __global__ void __launch_bounds__(NT, MINB) fused_decim_kernel(const __grid_cons
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int TS, int... PLAN>
-__global__ void __maxnreg__(TW_MAXREG) fused_decim_tw_kernel(const __grid_constant__ FusedParams P)
+// ASYNC (round 2, last third): the next chunk does not wait in 64 registers per main-warp thread while the cascade runs.
+// Each thread copies its sixteen samples straight from HBM into their (padded) places in stage 0's buffer with 16-byte
+// cp.async (LDGSTS: per-thread destinations, so the pad every 2 R0 elements costs nothing), issued as soon as the first
+// half band has consumed the buffer and its history has been slid; at the top of the next chunk the thread waits for
+// its own group and applies the tuning phasor in place (it reads back only what it copied itself, so no barrier in
+// between).  Costs one more 16-byte shared-memory read per sample; frees the registers for the half bands' own loads
+// in flight.  Same arithmetic: bit-identical.  ASYNC = 2 is the same under a 128-register cap.
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int ASYNC, int TS, int... PLAN>
+__global__ void __maxnreg__(ASYNC == 2 ? 128 : TW_MAXREG) fused_decim_tw_kernel(const __grid_constant__ FusedParams P)
 {
     constexpr int NT = 128, NTT = 64, NTA = NT + NTT, R0 = 8, NLD = 2 * R0, T0 = NLD * NT, NS = (int)sizeof...(PLAN);
     extern __shared__ double smem_raw[];
@@ -661,7 +678,7 @@ __global__ void __maxnreg__(TW_MAXREG) fused_decim_tw_kernel(const __grid_consta
     // 4 % of all shared-memory wavefronts of the kernel).
     const int js = (tid + ((8 - ((P.st[0].Ha + P.st[0].org) & 7)) & 7)) & (NT - 1);
     cd nx[NLD];
-    if (tid < NT && n_full > 0) {
+    if (!ASYNC && tid < NT && n_full > 0) {
 #pragma unroll
         for (int k = 0; k < NLD; k++) nx[k] = gin[k * NT + js];
     }
@@ -679,6 +696,17 @@ __global__ void __maxnreg__(TW_MAXREG) fused_decim_tw_kernel(const __grid_consta
     }
     for (int i = tid; i < P.smem_cd; i += NTA) sm[i] = make_double2(0.0, 0.0);
     __syncthreads();
+    constexpr int STEP_PAD0 = NT + NT / (2 * R0);
+    unsigned pb0s = 0;
+    if constexpr (ASYNC != 0) {
+        const FStage &S0 = P.st[0];
+        pb0s = (unsigned)__cvta_generic_to_shared(sm + S0.buf + phys(S0, S0.Ha + js));
+        if (tid < NT && n_full > 0) {
+#pragma unroll
+            for (int k = 0; k < NLD; k++) cp_async16(pb0s + k * STEP_PAD0 * (int)sizeof(cd), gin + k * NT + js);
+            cp_async_commit();
+        }
+    }
 #pragma unroll
     for (int e = 0; e < NHL; e++) if (hdst[e] >= 0) sm[hdst[e]] = hv[e];
     {
@@ -742,32 +770,67 @@ __global__ void __maxnreg__(TW_MAXREG) fused_decim_tw_kernel(const __grid_consta
         constexpr int NSL = 2;                  // four half bands: 4 x 48 history elements
         int sl_src[NSL], sl_dst[NSL];
 #pragma unroll
-        for (int e = 0; e < NSL; e++) slide_entry(P, 0, TS, tid + e * NT, sl_src[e], sl_dst[e]);
+        for (int e = 0; e < NSL; e++) slide_entry(P, ASYNC ? 1 : 0, TS, tid + e * NT, sl_src[e], sl_dst[e]);
         if (P.tune) pstep = s_pstep;
         const FStage &S0 = P.st[0];
         cd *pb0 = sm + S0.buf + phys(S0, S0.Ha + js);
         constexpr int STEP_PAD = NT + NT / (2 * R0);
         const bool tune = P.tune != 0;
+        // ASYNC: element i of stage 0's history is slid by the thread whose last cp.async of the next chunk lands on its
+        // old place (logical Ha + T0 - Ha + i = row NLD-1, column NT - Ha + i), so the read precedes the overwrite in
+        // program order (the store of the value read has issued before the copy does)
+        int s0_src = -1, s0_dst = -1;
+        if constexpr (ASYNC != 0) {
+            const int i = js - (NT - S0.Ha);
+            if (i >= 0 && i < S0.Ha) { s0_src = S0.buf + phys(S0, S0.n_full + i); s0_dst = S0.buf + phys(S0, i); }
+        }
         for (int ch = 0; ch < n_full; ch++) {
             const int p = ch & 1;
-            if (tune) {
+            if constexpr (ASYNC != 0) {
+                cp_async_wait_all();
+                if (tune) {
 #pragma unroll
-                for (int k = 0; k < NLD; k++) {
-                    const cd q = s_q[k];
-                    const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
-                    nx[k] = make_double2(fma(nx[k].x, v.x, -nx[k].y * v.y), fma(nx[k].x, v.y, nx[k].y * v.x));
+                    for (int k = 0; k < NLD; k++) nx[k] = pb0[k * STEP_PAD];       // all loads first: the stores below must not fence them
+#pragma unroll
+                    for (int k = 0; k < NLD; k++) {
+                        const cd q = s_q[k];
+                        const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                        nx[k] = make_double2(fma(nx[k].x, v.x, -nx[k].y * v.y), fma(nx[k].x, v.y, nx[k].y * v.x));
+                    }
+#pragma unroll
+                    for (int k = 0; k < NLD; k++) pb0[k * STEP_PAD] = nx[k];
+                    u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
                 }
-                u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
-            }
+                group_sync<1>();
+                cascade_x<NT, 1, true, 0, 1, 0, 0, PLAN...>(sm, P, T0, nullptr, ft, tid, 0, 0);
+                if (s0_src >= 0) sm[s0_dst] = sm[s0_src];
+                if (ch + 1 < n_full) {
+                    const cd *g1 = gin + (size_t)(ch + 1) * T0 + js;
 #pragma unroll
-            for (int k = 0; k < NLD; k++) pb0[k * STEP_PAD] = nx[k];
-            group_sync<1>();
-            if (ch + 1 < n_full) {
-                const cd *g1 = gin + (size_t)(ch + 1) * T0 + js;
+                    for (int k = 0; k < NLD; k++) cp_async16(pb0s + k * STEP_PAD * (int)sizeof(cd), g1 + k * NT);
+                    cp_async_commit();
+                }
+                cascade_x<NT, 1, true, 1, TS - 1, 0, 0, PLAN...>(sm, P, T0, nullptr, ft, tid, 0, 0);
+            } else {
+                if (tune) {
 #pragma unroll
-                for (int k = 0; k < NLD; k++) nx[k] = g1[k * NT];
+                    for (int k = 0; k < NLD; k++) {
+                        const cd q = s_q[k];
+                        const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                        nx[k] = make_double2(fma(nx[k].x, v.x, -nx[k].y * v.y), fma(nx[k].x, v.y, nx[k].y * v.x));
+                    }
+                    u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
+                }
+#pragma unroll
+                for (int k = 0; k < NLD; k++) pb0[k * STEP_PAD] = nx[k];
+                group_sync<1>();
+                if (ch + 1 < n_full) {
+                    const cd *g1 = gin + (size_t)(ch + 1) * T0 + js;
+#pragma unroll
+                    for (int k = 0; k < NLD; k++) nx[k] = g1[k * NT];
+                }
+                cascade_x<NT, 1, true, 0, TS - 1, 0, 0, PLAN...>(sm, P, T0, nullptr, ft, tid, 0, 0);
             }
-            cascade_x<NT, 1, true, 0, TS - 1, 0, 0, PLAN...>(sm, P, T0, nullptr, ft, tid, 0, 0);
             if (ch >= 2) bar_sync(4 + p, NTA);                  // the tail warp has finished with half p (chunk ch - 2)
             cascade_x<NT, 1, true, TS - 1, TS, 0, 0, PLAN...>(sm, P, 0, nullptr, ft, tid, 0, p * tws);
             bar_arrive(2 + p, NTA);
@@ -787,6 +850,222 @@ __global__ void __maxnreg__(TW_MAXREG) fused_decim_tw_kernel(const __grid_consta
     }
     group_sync<1>();
     // ---- ragged tail (at most one partial chunk): every stage on the main warps, generic indexing
+    int n_s = 0;
+    if (rem > 0) {
+        load_taps(tid);
+        const cd *g1 = P.in + (size_t)c * P.in_stride + (size_t)n_full * T0;
+        const FStage &S0 = P.st[0];
+        for (int i = js, k = 0; i < rem; i += NT, k++) {
+            cd x = g1[i];
+            if (P.tune) {
+                const cd q = s_q[k];
+                const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                x = make_double2(fma(x.x, v.x, -x.y * v.y), fma(x.x, v.y, x.y * v.x));
+            }
+            sm[S0.buf + phys(S0, S0.Ha + i)] = x;
+        }
+        group_sync<1>();
+        cascade_x<NT, 1, false, 0, NS, 0, 0, PLAN...>(sm, P, rem, gout + n_full * P.st[NS - 1].n_out_full, ft, tid, 0, 0);
+        n_s = rem;
+    }
+    for (int s = 0; s < P.ns; s++) {
+        const FStage &S = P.st[s];
+        cd *h = S.hout + (size_t)c * S.Hs;
+        for (int i = tid; i < S.Hs; i += NT) h[i] = sm[S.buf + phys(S, n_s + (S.Ha - S.Hs) + i)];
+        n_s = stage_out_count(S, n_s);
+    }
+}
+
+
+// ---- Three-group pipeline (round 2, last third).  The tail-warp kernel's four main warps still walk through commit ->
+// half band 0 -> half band 1 -> half band 2 as barrier-separated phases, the last two at R = 4 / R = 2 outputs per thread
+// (7.25 / 12.5 shared-memory loads per output).  Here the chunk pipeline has three stations, each one chunk behind the
+// one in front, all busy at the same time:
+//   group A, 4 warps: tuning phasor + commit + half band 0 (R = 8)            of chunk n      -> half n & 1 of stage 1's input
+//   group B, 2 warps: half band 1 (R = 8) and half band 2 (R = 4)             of chunk n - 1  -> half of stage 3's input
+//   group C, 2 warps: half band 3, FIR, half band, FIR (the former tail warps) of chunk n - 2  -> HBM
+// so every half band in front of the tail streams at 4.6 - 7.25 loads per output and the FP64 work per warp is even
+// (12.6 / 14 / 10.5 % of a chunk).  Hand-over by named barriers: READY / FREE per half and per pair of groups
+// (A-B: 8+p / 10+p, 192 threads; B-C: 2+p / 4+p, 128 threads), each group keeps a barrier of its own (1, 7, 6).
+// Eight warps per CTA, two CTAs per SM under a 128-register cap.  Same arithmetic in the same order: bit-identical.
+template <int... PLAN>
+__global__ void __launch_bounds__(256, 2) fused_decim_p3_kernel(const __grid_constant__ FusedParams P)
+{
+    constexpr int NT = 128, NTB = 64, NTT = 64, NTA = NT + NTB + NTT, R0 = 8, NLD = 2 * R0, T0 = NLD * NT, NS = (int)sizeof...(PLAN), TS = 3;
+    extern __shared__ double smem_raw[];
+    cd *sm = reinterpret_cast<cd *>(smem_raw);
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ cd s_pstep;
+    __shared__ cd s_q[NLD];
+
+    const int n_full = P.n_in / T0;
+    const int rem = P.n_in - n_full * T0;
+    const cd *gin = P.in + (size_t)c * P.in_stride;
+    const int js = (tid + ((8 - ((P.st[0].Ha + P.st[0].org) & 7)) & 7)) & (NT - 1);      // see fused_decim_tw_kernel
+    cd nx[NLD];
+    if (tid < NT && n_full > 0) {
+#pragma unroll
+        for (int k = 0; k < NLD; k++) nx[k] = gin[k * NT + js];
+    }
+    constexpr int NHL = 2;                      // history elements per thread (2 x 256 = the 512 the planner admits)
+    cd hv[NHL]; int hdst[NHL];
+#pragma unroll
+    for (int e = 0; e < NHL; e++) {
+        int idx = tid + e * NTA;
+        hdst[e] = -1;
+        for (int s = 0; s < P.ns; s++) {
+            const FStage &S = P.st[s];
+            if (idx >= 0 && idx < S.Hs) { hdst[e] = S.buf + phys(S, (S.Ha - S.Hs) + idx); hv[e] = S.hin[(size_t)c * S.Hs + idx]; }
+            idx -= S.Hs;
+        }
+    }
+    for (int i = tid; i < P.smem_cd; i += NTA) sm[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < NHL; e++) if (hdst[e] >= 0) sm[hdst[e]] = hv[e];
+    {
+        double *cs = reinterpret_cast<double *>(sm + P.coef_sm);
+        for (int i = tid; i < P.ncoef; i += NTA) cs[i] = P.coef[i];
+    }
+    cd u = make_double2(1.0, 0.0), pstep = make_double2(1.0, 0.0);
+    if (P.tune) {
+        const double *nc = P.nco + (size_t)c * 8;
+        if (tid == NT) s_pstep = nco_pow(nc, (unsigned long long)T0);
+        if (tid >= NT + NTB && tid < NT + NTB + NLD) s_q[tid - NT - NTB] = nco_pow(nc, (unsigned long long)(tid - NT - NTB) * NT);
+        if (tid < NT) u = cmul_rn(P.vstart[c], nco_pow(nc, P.n_base + (unsigned long long)js));
+    }
+    __syncthreads();
+    const FStage &S1 = P.st[1];
+    const FStage &ST = P.st[TS];
+    const int abs_ = P.ab_stride, tws = P.tw_stride;
+    cd *gout = P.out + (size_t)c * P.out_stride;
+    FirTaps ft;
+    auto load_taps = [&](int lane) {
+        const double *cs = reinterpret_cast<const double *>(sm + P.coef_sm);
+        int fi = 0;
+        for (int s = 0; s < P.ns && fi < MAXFIR; s++) {
+            if (P.st[s].type == 1) {
+#pragma unroll
+                for (int kk = 0; kk < FIR_KB; kk++) {
+                    const double v = cs[P.st[s].coef + (lane & 7) * FIR_KB + kk];
+                    if (fi == 0) ft.cf[0][kk] = v; else ft.cf[1][kk] = v;
+                }
+                fi++;
+            }
+        }
+    };
+
+    if (tid >= NT + NTB) {
+        // ================= group C: stages TS .. NS-1, two chunks behind group A
+        const int t = tid - NT - NTB;
+        load_taps(t);
+        constexpr int NSLT = 384 / NTT;
+        int ts_src[NSLT], ts_dst[NSLT];
+#pragma unroll
+        for (int e = 0; e < NSLT; e++) slide_entry(P, TS + 1, P.ns, t + e * NTT, ts_src[e], ts_dst[e]);
+        int out_pos = 0;
+        for (int ch = 0; ch < n_full; ch++) {
+            const int p = ch & 1;
+            long long *tr = (P.trace && t == 0 && ch < 16) ? P.trace + ((size_t)c * 16 + ch) * 16 : nullptr;
+            if (tr) tr[8] = clock64();
+            bar_sync(2 + p, NTB + NTT);
+            if (tr) tr[9] = clock64();
+            out_pos += cascade_x<NTT, 2, true, TS, NS, 0, 0, PLAN...>(sm, P, 0, gout + out_pos, ft, t, p * tws, 0);
+            if (tr) tr[10] = clock64();
+            const cd *hs = sm + ST.buf + p * tws;
+            cd *hd = sm + ST.buf + (p ^ 1) * tws;
+            for (int i = t; i < ST.Ha; i += NTT) hd[phys(ST, i)] = hs[phys(ST, ST.n_full + i)];
+            cd kd[NSLT];
+#pragma unroll
+            for (int e = 0; e < NSLT; e++) if (ts_src[e] >= 0) kd[e] = sm[ts_src[e]];
+            group_sync<2>();
+#pragma unroll
+            for (int e = 0; e < NSLT; e++) if (ts_src[e] >= 0) sm[ts_dst[e]] = kd[e];
+            group_sync<2>();
+            if (ch + 2 < n_full) bar_arrive(4 + p, NTB + NTT);
+            if (tr) tr[11] = clock64();
+        }
+    } else if (tid >= NT) {
+        // ================= group B: half bands 1 and 2, one chunk behind group A
+        const int t = tid - NT;
+        int b_src, b_dst;
+        slide_entry(P, 2, 3, t, b_src, b_dst);               // stage 2's history (48 elements) slides in place
+        for (int ch = 0; ch < n_full; ch++) {
+            const int p = ch & 1;
+            long long *tr = (P.trace && t == 0 && ch < 16) ? P.trace + ((size_t)c * 16 + ch) * 16 : nullptr;
+            if (tr) tr[4] = clock64();
+            bar_sync(8 + p, NT + NTB);
+            if (tr) tr[5] = clock64();
+            cascade_x<NTB, 3, true, 1, 2, 0, 0, PLAN...>(sm, P, 0, nullptr, ft, t, p * abs_, 0);
+            {   // stage 1's history: from the end of this half to the front of the other
+                const cd *hs = sm + S1.buf + p * abs_;
+                cd *hd = sm + S1.buf + (p ^ 1) * abs_;
+                for (int i = t; i < S1.Ha; i += NTB) hd[phys(S1, i)] = hs[phys(S1, S1.n_full + i)];
+            }
+            if (ch + 2 < n_full) bar_arrive(10 + p, NT + NTB);
+            if (tr) tr[6] = clock64();
+            if (ch >= 2) bar_sync(4 + p, NTB + NTT);           // group C has finished with half p of stage 3's input
+            if (tr) tr[7] = clock64();
+            cascade_x<NTB, 3, true, 2, 3, 0, 0, PLAN...>(sm, P, 0, nullptr, ft, t, 0, p * tws);
+            bar_arrive(2 + p, NTB + NTT);
+            cd keep = make_double2(0.0, 0.0);
+            if (b_src >= 0) keep = sm[b_src];
+            group_sync<3>();
+            if (b_src >= 0) sm[b_dst] = keep;
+            if (tr) tr[12] = clock64();
+        }
+    } else {
+        // ================= group A: NCO + commit + half band 0
+        int a_src, a_dst;
+        slide_entry(P, 0, 1, tid, a_src, a_dst);
+        if (P.tune) pstep = s_pstep;
+        const FStage &S0 = P.st[0];
+        cd *pb0 = sm + S0.buf + phys(S0, S0.Ha + js);
+        constexpr int STEP_PAD = NT + NT / (2 * R0);
+        const bool tune = P.tune != 0;
+        for (int ch = 0; ch < n_full; ch++) {
+            const int p = ch & 1;
+            long long *tr = (P.trace && tid == 0 && ch < 16) ? P.trace + ((size_t)c * 16 + ch) * 16 : nullptr;
+            if (tr) tr[0] = clock64();
+            if (tune) {
+#pragma unroll
+                for (int k = 0; k < NLD; k++) {
+                    const cd q = s_q[k];
+                    const cd v = make_double2(fma(u.x, q.x, -u.y * q.y), fma(u.x, q.y, u.y * q.x));
+                    nx[k] = make_double2(fma(nx[k].x, v.x, -nx[k].y * v.y), fma(nx[k].x, v.y, nx[k].y * v.x));
+                }
+                u = make_double2(fma(u.x, pstep.x, -u.y * pstep.y), fma(u.x, pstep.y, u.y * pstep.x));
+            }
+#pragma unroll
+            for (int k = 0; k < NLD; k++) pb0[k * STEP_PAD] = nx[k];
+            group_sync<1>();
+            if (ch + 1 < n_full) {
+                const cd *g1 = gin + (size_t)(ch + 1) * T0 + js;
+#pragma unroll
+                for (int k = 0; k < NLD; k++) nx[k] = g1[k * NT];
+            }
+            if (tr) tr[1] = clock64();
+            if (ch >= 2) bar_sync(10 + p, NT + NTB);            // group B has finished with half p of stage 1's input
+            if (tr) tr[2] = clock64();
+            cascade_x<NT, 1, true, 0, 1, 0, 0, PLAN...>(sm, P, T0, nullptr, ft, tid, 0, p * abs_);
+            bar_arrive(8 + p, NT + NTB);
+            if (tr) tr[3] = clock64();
+            cd keep = make_double2(0.0, 0.0);
+            if (a_src >= 0) keep = sm[a_src];
+            group_sync<1>();
+            if (a_src >= 0) sm[a_dst] = keep;
+        }
+    }
+    __syncthreads();
+    if (tid >= NT) return;
+    // the histories of the double-buffered stages sit at the front of half (n_full & 1): bring them to half 0
+    if (n_full & 1) {
+        for (int i = tid; i < S1.Ha; i += NT) sm[S1.buf + phys(S1, i)] = sm[S1.buf + abs_ + phys(S1, i)];
+        for (int i = tid; i < ST.Ha; i += NT) sm[ST.buf + phys(ST, i)] = sm[ST.buf + tws + phys(ST, i)];
+    }
+    group_sync<1>();
+    // ---- ragged tail (at most one partial chunk): every stage on group A, generic indexing
     int n_s = 0;
     if (rem > 0) {
         load_taps(tid);
@@ -882,8 +1161,14 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     // component-split half bands (hb_stage_split): plan kernels at the full chunk only
     // tail-warp kernel: stages from index tw_ts on belong to the two tail warps (option value 2, 3 or 4; 1 = default)
     const int tw_ts = fused_tailwarp >= 2 && fused_tailwarp <= 4 ? fused_tailwarp : 3;
-    bool use_tw = fused_tailwarp && fused_plans && NT == 128 && T0 == 2048 && split == ns && ns > 4 && !d_trace;
-    bool use_split = !use_tw && fused_split && fused_plans && NT == 128 && T0 == 2048 && split == ns;
+    bool use_tw = fused_tailwarp && fused_plans && NT == 128 && T0 == 2048 && split == ns && ns > 4 && (!d_trace || fused_p3);
+    bool use_split = !use_tw && fused_split == 1 && fused_plans && NT == 128 && T0 == 2048 && split == ns;
+    // tail-warp kernel with component-split half bands behind the first one (stage 0 keeps complex lanes: its commit
+    // layout is built around the pad every 16 elements)
+    bool tw_split = use_tw && fused_split && tw_ts == 3;
+    // three-group pipeline (fused_decim_p3_kernel): half bands 1 and 2 on a group of their own
+    bool use_p3 = use_tw && fused_p3 && tw_ts == 3;
+    if (use_p3) tw_split = false;
     // stage descriptors for a given multi-rate split (no filter state is touched here)
     auto build = [&](int split, int deepk) -> int {
     P.deepk = deepk;
@@ -900,16 +1185,16 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
             S.type = 0; S.D = 2; S.nTaps = 43; S.Ha = 48;
             S.u0 = 1 - f->phase;
             const int nout = chunk_in / 2;
-            const int nts = (use_tw && s >= tw_ts) ? 64 : NT;          // the tail warps are 64 threads
+            const int nts = ((use_tw && s >= tw_ts) || (use_p3 && s >= 1)) ? 64 : NT;          // the tail warps (and group B) are 64 threads
             S.R = nout > 4 * nts ? 8 : (nout > 2 * nts ? 4 : 2);
             if (fused_min_r > S.R) S.R = fused_min_r;
-            if (use_split) { S.split = 1; S.R *= 2; }
+            if (use_split || (tw_split && s > 0)) { S.split = 1; S.R *= 2; }
             S.pu = 2 * S.R;
             S.magic = (unsigned)((0x100000000ULL + S.pu - 1) / S.pu);
             // window start of thread 0 (logical Ha + u0 - 42) must land on a pad boundary
             const int ws = S.Ha + S.u0 - 42;
             S.org = (S.pu - (ws % S.pu)) % S.pu;
-            const int qmax = S.Ha + chunk_in + S.org + 2 * S.R + 64;
+            const int qmax = S.Ha + chunk_in + S.org + 2 * S.R + (use_p3 ? 16 : 64);      // p3: two more buffer halves have to fit
             S.buf_len = qmax + qmax / S.pu + 8;
             const int q0 = ws + S.org;
             S.p0 = q0 + q0 / S.pu;
@@ -934,6 +1219,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         S.buf = off;
         off += S.buf_len;
         if (use_tw && s == tw_ts) { P.tw_stride = S.buf_len; off += S.buf_len; }
+        if (use_p3 && s == 1) { P.ab_stride = S.buf_len; off += S.buf_len; }
         S.n_full = chunk_in;
         S.n_out_full = chunk_in / S.D;
         chunk_in = chunk_in / S.D;
@@ -991,11 +1277,16 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         for (int p = 0; p < 4 && rcb == QC_OK; p++) {
             if (lens[p] != ns) continue;
             bool ok = true;
-            for (int i = 0; i < ns; i++) ok = ok && codes[i] == (i < 4 ? head[tw_ts - 2][i] : tails[p][i - 4]);
+            for (int i = 0; i < ns; i++) {
+                int want = i < 4 ? head[tw_ts - 2][i] : tails[p][i - 4];
+                if (tw_split && i > 0 && want < 100) want += 200;
+                if (use_p3 && i < 4) want = i < 2 ? 82 : (i == 2 ? 42 : 22);
+                ok = ok && codes[i] == want;
+            }
             found = found || ok;
         }
         for (int s = 0; s < ns; s++) if (P.st[s].type == 1 && P.st[s].Kpad != 8 * FIR_KB) found = false;
-        if (!found) { use_tw = false; P.tw_stride = 0; }
+        if (!found) { use_tw = false; tw_split = false; use_p3 = false; P.tw_stride = 0; P.ab_stride = 0; }
     }
     if (use_tw || use_split) {
     } else if (split != ns) {
@@ -1043,12 +1334,28 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         fused_decim_tw_kernel<__VA_ARGS__><<<C, 192, sh, strm>>>(P); } while (0)
     // tail-warp kernels (default): the stages behind the fourth half band run on a fifth warp, one chunk behind
     if (use_tw) {
-#define QC_TW_PLANS(TS, H2) \
-        if (ns == 5) QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142); \
-        else if (ns == 7) QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142, 22, 122); \
-        else if (ns == 8) QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142, 22, 22, 112); \
-        else QC_LAUNCH_TW(TS, 82, 42, H2, 22, 142, 142)
-        if (tw_ts == 2) { QC_TW_PLANS(2, 42); } else if (tw_ts == 3) { QC_TW_PLANS(3, 22); } else { QC_TW_PLANS(4, 22); }
+#define QC_TW_PLANS(AS, TS, H1, H2, H3) \
+        if (ns == 5) QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142); \
+        else if (ns == 7) QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142, H3, 122); \
+        else if (ns == 8) QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142, H3, H3, 112); \
+        else QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142, 142)
+        if (use_p3) {
+#define QC_LAUNCH_P3(...) do { \
+        static bool optin[64] = {}; \
+        int dev_ = 0; cudaGetDevice(&dev_); dev_ &= 63; \
+        if (!optin[dev_]) { QC_CUDA(cudaFuncSetAttribute(fused_decim_p3_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); optin[dev_] = true; } \
+        fused_name = "fused_decim_p3_kernel<" #__VA_ARGS__ ">"; \
+        fused_decim_p3_kernel<__VA_ARGS__><<<C, 256, sh, strm>>>(P); } while (0)
+            if (ns == 5) QC_LAUNCH_P3(82, 82, 42, 22, 142);
+            else if (ns == 7) QC_LAUNCH_P3(82, 82, 42, 22, 142, 22, 122);
+            else if (ns == 8) QC_LAUNCH_P3(82, 82, 42, 22, 142, 22, 22, 112);
+            else QC_LAUNCH_P3(82, 82, 42, 22, 142, 142);
+#undef QC_LAUNCH_P3
+        }
+        else if (tw_ts == 2) { QC_TW_PLANS(0, 2, 42, 42, 22); } else if (tw_ts == 4) { QC_TW_PLANS(0, 4, 42, 22, 22); }
+        else if (tw_split) { QC_TW_PLANS(0, 3, 242, 222, 222); }
+        else if (fused_async == 1) { QC_TW_PLANS(1, 3, 42, 22, 22); } else if (fused_async == 2) { QC_TW_PLANS(2, 3, 42, 22, 22); }
+        else { QC_TW_PLANS(0, 3, 42, 22, 22); }
 #undef QC_TW_PLANS
     }
     // single-rate plans (every stage every chunk)

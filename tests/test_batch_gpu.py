@@ -218,14 +218,15 @@ def test_c1_chain_ragged_blocks_tuned(fused, torch, tabs):
     rx.close()
 
 
-FUSED_VARIANTS = [("tailwarp", 12, 0), ("tailwarp", 12, 2), ("tailwarp", 12, 3), ("tailwarp", 12, 4), ("split", 11, 1)]
+FUSED_VARIANTS = [("tailwarp", 12, 0), ("tailwarp", 12, 2), ("tailwarp", 12, 3), ("tailwarp", 12, 4), ("split", 11, 1),
+                  ("async", 19, 0), ("async", 19, 1), ("async", 19, 2), ("async_twsplit", 11, 1), ("async_p3", 20, 1)]     # async: on the default tail-warp kernel
 
 
 @pytest.mark.parametrize("variant", FUSED_VARIANTS, ids=["%s%d" % (v[0], v[2]) for v in FUSED_VARIANTS])
 @pytest.mark.parametrize("mode", ["USB", "CWU", "AM"])
 def test_fused_kernel_variants(mode, variant, torch, tabs):
     """Every variant of the fused decimator (all stages on the main warps; the stages from index 2, 3 or 4 on the two
-    tail warps; component-split half bands) against the reference fixture, over full chunks, blocks that end inside a
+    tail warps; component-split half bands; the next chunk by cp.async instead of a register prefetch) against the reference fixture, over full chunks, blocks that end inside a
     chunk, blocks shorter than a chunk and odd / even numbers of full chunks (the tail warps' double buffer ends on
     either half) -- histories, phases and the tuning phasor carry over between all of them."""
     from quisk_b200.rx import RxChain
@@ -246,6 +247,8 @@ def test_fused_kernel_variants(mode, variant, torch, tabs):
     splits.append(153600 - sum(splits))
     base, cb, _, _ = _run_chain(torch, rx, x, splits)
     rx.reset()
+    if variant[0].startswith("async"):
+        rx.set_option(12, 1)
     rx.set_option(variant[1], variant[2])
     aud, ca, _, _ = _run_chain(torch, rx, x, splits)
     rx.close()
