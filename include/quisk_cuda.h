@@ -176,7 +176,8 @@ typedef struct qcRxChain qcRxChain;
 
 enum qcRxMode {     /* values of rx_mode_type, quisk.h:56-70 */
     QC_MODE_CWL = 0, QC_MODE_CWU = 1, QC_MODE_LSB = 2, QC_MODE_USB = 3, QC_MODE_AM = 4, QC_MODE_FM = 5,
-    QC_MODE_DGT_U = 7, QC_MODE_DGT_L = 8, QC_MODE_DGT_IQ = 9, QC_MODE_FDV_U = 11, QC_MODE_FDV_L = 12
+    QC_MODE_DGT_U = 7, QC_MODE_DGT_L = 8, QC_MODE_DGT_IQ = 9, QC_MODE_FDV_U = 11, QC_MODE_FDV_L = 12,
+    QC_MODE_DGT_FM = 13     /* the FM branch (quisk.c:2026-2027 is one case for FM and DGT_FM) */
 };
 
 /* The reference keeps its decimation / audio coefficient tables in filters.h;

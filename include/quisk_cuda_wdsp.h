@@ -56,6 +56,13 @@ int quisk_cuda_mp_imp(int N, const double *fir, double *mpfir, int pfactor, int 
  * they are not part of this library); 3 is not built.  npe_method 0 (minimum statistics), 1, 2.  ae_run: the post-filter. */
 typedef struct qcEmnr qcEmnr;
 int quisk_cuda_emnr_set_tables(const double *GG, const double *GGS);     /* host pointers, 241 * 241 doubles each, copied */
+/* gain method 3 ("trained", the second state of Quisk's NR2 button, quisk.py:6020-6023; emnr.c:965-1010): method 0's gain,
+ * applied twice, then a 60 x 60 table of the distribution (wdsp/zetahat.c, or the `zetaHat` file readZetaHat prefers,
+ * emnr.c:206-238) says per (gamma, xi) cell whether the bin is speech (gain 1) or not (gain 0); the host hands over the
+ * table, its validity map and the four range limits once per process, as readZetaHat returns them */
+int quisk_cuda_emnr_set_zeta(const double *zeta_hat, const int *zeta_valid, int rows, int cols,
+                             double gamma_min, double gamma_max, double xihat_min, double xihat_max);
+int quisk_cuda_emnr_set_train(qcEmnr *e, double zeta_thresh, double t2);  /* SetRXAEMNRtrainZetaThresh / SetRXAEMNRtrainT2, emnr.c:1160-1174 */
 qcEmnr *quisk_cuda_emnr_create(int n_channels, int bsize, int fsize, int ovrlp, int rate, int wintype, double gain,
                                int gain_method, int npe_method, int ae_run);
 void quisk_cuda_emnr_destroy(qcEmnr *e);
@@ -194,6 +201,7 @@ int quisk_cuda_rxa_set_emnr_run(qcRxa *rxa, int run);                        /* 
 int quisk_cuda_rxa_set_emnr_gain_method(qcRxa *rxa, int method);
 int quisk_cuda_rxa_set_emnr_npe_method(qcRxa *rxa, int method);
 int quisk_cuda_rxa_set_emnr_ae_run(qcRxa *rxa, int run);
+int quisk_cuda_rxa_set_emnr_train(qcRxa *rxa, int what, double value);        /* 0: SetRXAEMNRtrainZetaThresh, 1: SetRXAEMNRtrainT2 (emnr.c:1160-1174) */
 int quisk_cuda_rxa_set_emnr_position(qcRxa *rxa, int position);              /* SetRXAEMNRPosition, emnr.c:1135-1142: 0 in front of the AGC, 1 behind it */
 int quisk_cuda_rxa_set_fm_lim_run(qcRxa *rxa, int run);                      /* SetRXAFMLimRun,  fmd.c:337-348: the FM detector limiter (a wcpAGC, fmd.c:49-73) */
 int quisk_cuda_rxa_set_fm_lim_gain(qcRxa *rxa, double gain_db);              /* SetRXAFMLimGain, fmd.c:350-363 */
@@ -275,6 +283,8 @@ void SetRXAEMNRgainMethod(int channel, int method);
 void SetRXAEMNRnpeMethod(int channel, int method);
 void SetRXAEMNRaeRun(int channel, int run);
 void SetRXAEMNRPosition(int channel, int position);
+void SetRXAEMNRtrainZetaThresh(int channel, double thresh);    /* emnr.c:1160-1166 */
+void SetRXAEMNRtrainT2(int channel, double t2);                 /* emnr.c:1168-1174 */
 void SetRXASNBARun(int channel, int run);
 void SetRXAANFRun(int channel, int run);
 void SetRXAANRRun(int channel, int run);

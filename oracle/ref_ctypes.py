@@ -58,7 +58,7 @@ TABLES = {   # filter.h:57-86
 }
 
 MODES = {"CWL": 0, "CWU": 1, "LSB": 2, "USB": 3, "AM": 4, "FM": 5,
-         "DGT-U": 7, "DGT-L": 8, "DGT-IQ": 9, "FDV-U": 11, "FDV-L": 12}   # quisk.h:56-70
+         "DGT-U": 7, "DGT-L": 8, "DGT-IQ": 9, "FDV-U": 11, "FDV-L": 12, "DGT-FM": 13}   # quisk.h:56-70
 
 
 def have_ref(name: str = "libquisk_filter_ref.so") -> bool:

@@ -131,7 +131,7 @@ int RxChain::init(const qcRxConfig &cfg)
         QC_CUDA(cudaMalloc((void **)&d_dc, (size_t)C * sizeof(double)));
         QC_CUDA(cudaMemset(d_dc, 0, (size_t)C * sizeof(double)));
         break;
-    case QC_MODE_FM: {                          // quisk.c:2027-2090
+    case QC_MODE_FM: case QC_MODE_DGT_FM: {     // quisk.c:2026-2075 (one case label for both: DGT-FM differs only in where quisk_process_samples sends the audio, quisk.c:2633)
         filter_srate = decim_srate;
         rxf = mk(QC_D_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
         ADD(rst, mk(QC_D_DECIMATE, C, T.lpFilt48, T.n_lpFilt48, 1, 4));
@@ -165,6 +165,8 @@ int RxChain::init(const qcRxConfig &cfg)
         if (cfg.filter_bandwidth < 19000) rxf = mk(QC_D_RXFILTER, C, iq.data(), cfg.n_filt, 1, 1);
         break;
     default:
+        // EXT (6) leaves quisk_process_samples for quisk_extern_demod before the demodulator (quisk.c:2490-2494); IMD (10) has no
+        // case in quisk_process_demodulate's switch at all (the reference returns the buffer untouched)
         set_error("rx_create: mode %d is not on the accelerated path", mode); return QC_EINVAL;
     }
     if (!rxf && !iq_out) return QC_EINVAL;
@@ -445,7 +447,7 @@ int RxChain::process(const void *d_iq, long iq_stride, int count, double *d_audi
     case QC_MODE_CWL: case QC_MODE_LSB: case QC_MODE_DGT_L: case QC_MODE_FDV_L: rc = launch_demod_ssb(cur, cap, rcur, rstride, n, C, 1, s); break;
     case QC_MODE_CWU: case QC_MODE_USB: case QC_MODE_DGT_U: case QC_MODE_FDV_U: rc = launch_demod_ssb(cur, cap, rcur, rstride, n, C, 0, s); break;
     case QC_MODE_AM: rc = launch_am_detect(cur, cap, rcur, cap, n, C, d_dc, s); break;
-    case QC_MODE_FM: rc = launch_fm_detect(cur, cap, rcur, cap, n, C, d_fm, fm_a0, fm_a1, fm_b1, s); break;
+    case QC_MODE_FM: case QC_MODE_DGT_FM: rc = launch_fm_detect(cur, cap, rcur, cap, n, C, d_fm, fm_a0, fm_a1, fm_b1, s); break;
     }
     if (rc != QC_OK) return rc;
     if (audio_options()) {

@@ -180,6 +180,8 @@ void SetRXAEMNRRun(int channel, int run)
 void SetRXAEMNRgainMethod(int channel, int method) { CH("SetRXAEMNRgainMethod") return; quisk_cuda_rxa_set_emnr_gain_method(as_handle(r), method); }
 void SetRXAEMNRnpeMethod(int channel, int method) { CH("SetRXAEMNRnpeMethod") return; quisk_cuda_rxa_set_emnr_npe_method(as_handle(r), method); }
 void SetRXAEMNRaeRun(int channel, int run) { CH("SetRXAEMNRaeRun") return; quisk_cuda_rxa_set_emnr_ae_run(as_handle(r), run); }
+void SetRXAEMNRtrainZetaThresh(int channel, double thresh) { CH("SetRXAEMNRtrainZetaThresh") return; quisk_cuda_rxa_set_emnr_train(as_handle(r), 0, thresh); }    /* emnr.c:1160-1166 */
+void SetRXAEMNRtrainT2(int channel, double t2) { CH("SetRXAEMNRtrainT2") return; quisk_cuda_rxa_set_emnr_train(as_handle(r), 1, t2); }                          /* emnr.c:1168-1174 */
 void SetRXAEMNRPosition(int channel, int position) { CH("SetRXAEMNRPosition") return; quisk_cuda_rxa_set_emnr_position(as_handle(r), position); }
 void SetRXASNBARun(int channel, int run)
 {   // SNB

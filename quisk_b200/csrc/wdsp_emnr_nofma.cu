@@ -36,6 +36,9 @@ struct EmnrPar {
     // g
     double gf1p5, alpha, eps_floor, gamma_max, xi_min, q, gmax;
     const double *GG, *GGS;
+    // gain method 3 (emnr.c:329-334, 866-884): the trained zeta table, its validity map and mlog10's table
+    const double *zeta_hat; const int *zeta_true; const double *mtable;
+    int dim_zeta; double z_gamma_min, z_gamma_max, z_xihat_min, z_xihat_max, zeta_thresh;
     // np (LambdaD)
     double alphaCsmooth, alphaMax, alphaCmin, alphaMin_max_value, snrq, betamax, invQeqMax, av, MofD, MofV;
     int U, V, D;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(EM_T) emnr_frame_kernel(EmnrPar P, EmnrLayout 
             const double ly = LY[k], ld = lambda_d[k], pm = prev_mask[k];
             const double gamma = e_min(ly / ld, P.gamma_max);
             double eps_hat = P.alpha * pm * pm * prev_gamma[k] + (1.0 - P.alpha) * e_max(gamma - 1.0, P.eps_floor);
-            double mask;
+            double mask, pmask_out = 0.0;
             if (P.gain_method == 0) {
                 eps_hat = e_max(eps_hat, P.xi_min);
                 const double v = (eps_hat / (1.0 + eps_hat)) * gamma;
@@ -291,12 +294,51 @@ __global__ void __launch_bounds__(EM_T) emnr_frame_kernel(EmnrPar P, EmnrLayout 
                 mask = ehr * exp(e_min(700.0, 0.5 * e_e1xb(v)));
                 if (mask > P.gmax) mask = P.gmax;
                 if (mask != mask) mask = 0.01;
-            } else {
+            } else if (P.gain_method == 2) {
                 const double eps_p = eps_hat / (1.0 - P.q);
                 mask = e_getKey(P.GG, gamma, eps_hat) * e_getKey(P.GGS, gamma, eps_p);
+            } else {
+                // method 3 (emnr.c:965-1010): method 0's gain, kept as prev_mask; the same law once more from the a-priori SNR
+                // that gain implies (with the FIRST pass's v in the speech-presence factor, as the reference has it); then
+                // the trained table decides 1 or 0 where it holds a value for this (gamma, xi) cell
+                double xi_hat = e_max(eps_hat, P.xi_min);
+                const double v = (xi_hat / (1.0 + xi_hat)) * gamma;
+                mask = P.gf1p5 * sqrt(v) / gamma * exp(-0.5 * v) * ((1.0 + v) * e_bessI0(0.5 * v) + v * e_bessI1(0.5 * v));
+                const double v2 = e_min(v, 700.0);
+                {
+                    const double eta = mask * mask * ly / ld;
+                    const double eps = eta / (1.0 - P.q);
+                    const double witchHat = (1.0 - P.q) / P.q * exp(v2) / (1.0 + eps);
+                    mask *= witchHat / (1.0 + witchHat);
+                }
+                if (mask > P.gmax) mask = P.gmax;
+                if (mask != mask) mask = 0.01;
+                pmask_out = mask;
+                {
+                    double xi_ts = mask * mask * gamma;
+                    xi_ts = e_max(xi_ts, P.xi_min);
+                    const double v_ts = (xi_ts / (1.0 + xi_ts)) * gamma;
+                    mask = P.gf1p5 * sqrt(v_ts) / gamma * exp(-0.5 * v_ts) * ((1.0 + v_ts) * e_bessI0(0.5 * v_ts) + v_ts * e_bessI1(0.5 * v_ts));
+                    const double eta = mask * mask * ly / ld;
+                    const double eps = eta / (1.0 - P.q);
+                    const double witchHat = (1.0 - P.q) / P.q * exp(v2) / (1.0 + eps);
+                    mask *= witchHat / (1.0 + witchHat);
+                    xi_hat = xi_ts;
+                }
+                {   // getZeta, emnr.c:866-884 (its second range test compares xi in dB, not its cell index, with dim_zeta: kept)
+                    const double gamma_dB = 10.0 * mlog10_dev(P.mtable, gamma), xi_dB = 10.0 * mlog10_dev(P.mtable, xi_hat);
+                    const double gamma_per_cell = (P.z_gamma_max - P.z_gamma_min) / P.dim_zeta;
+                    const double xi_per_cell = (P.z_xihat_max - P.z_xihat_min) / P.dim_zeta;
+                    const int i_gamma = (int)floor((gamma_dB - P.z_gamma_min) / gamma_per_cell);
+                    const int i_xi = (int)floor((xi_dB - P.z_xihat_min) / xi_per_cell);
+                    if (!(i_gamma < 0 || i_gamma >= P.dim_zeta || i_xi < 0 || xi_dB >= P.dim_zeta)) {
+                        const int index = i_gamma * P.dim_zeta + i_xi;
+                        if (P.zeta_true[index] > 0) mask = P.zeta_hat[index] > P.zeta_thresh ? 1.0 : 0.0;
+                    }
+                }
             }
             MK[k] = mask;
-            prev_gamma[k] = gamma; prev_mask[k] = mask;
+            prev_gamma[k] = gamma; prev_mask[k] = P.gain_method == 3 ? pmask_out : mask;
         }
     }
     __syncthreads();
@@ -327,7 +369,8 @@ __global__ void __launch_bounds__(EM_T) emnr_frame_kernel(EmnrPar P, EmnrLayout 
             SCR[k] = a;
         }
         __syncthreads();
-        for (int k = tid; k < ms; k += EM_T) MK[k] = SCR[k];
+        const double damp = (P.gain_method == 3 && zetaT < P.t2) ? 0.05 : 1.0;         // emnr.c:813-815
+        for (int k = tid; k < ms; k += EM_T) MK[k] = damp == 1.0 ? SCR[k] : SCR[k] * damp;
         __syncthreads();
     }
     // ---- back: g1 * Y on bins 0 .. fs/2, the Hermitian extension above, inverse transform (emnr.c:1038-1044)
@@ -375,6 +418,8 @@ __global__ void emnr_out_kernel(cd *out, long os, int n, const double *state, Em
 
 // the two gamma-prior tables, handed over once per process (host copies), uploaded per device on first use
 static std::mutex g_tab_mu;
+static std::vector<double> g_zeta; static std::vector<int> g_zvalid; static double g_zpar[4];
+static double *g_dzeta[64] = {nullptr}; static int *g_dzvalid[64] = {nullptr};
 static std::vector<double> g_GG, g_GGS;
 static double *g_dGG[64] = {nullptr}, *g_dGGS[64] = {nullptr};
 
@@ -449,6 +494,7 @@ struct Emnr {
         P.delta_LF = 1000.0 / (rt / 2) * P.ms; P.delta_MF = 3000.0 / (rt / 2) * P.ms;
         P.delta_0 = 2.0; P.delta_1 = 2.0; P.delta_2 = 5.0;
         P.zetaThresh = 0.75; P.psi = 20.0; P.t2 = 0.20;
+        P.zeta_thresh = -2.0;           // g.zeta_thresh, emnr.c:332
         // state row
         size_t o = 0;
         const size_t ms = (size_t)P.ms;
@@ -506,6 +552,22 @@ struct Emnr {
 
     int tables()
     {
+        if (P.gain_method == 3) {
+            std::lock_guard<std::mutex> g(g_tab_mu);
+            if (g_zeta.empty()) { set_error("emnr: gain method 3 needs the trained zeta table of the WDSP distribution (wdsp/zetahat.c or its `zetaHat` file, emnr.c:206-238): hand it over with quisk_cuda_emnr_set_zeta first"); return QC_EINVAL; }
+            int dev = 0; cudaGetDevice(&dev); dev &= 63;
+            if (!g_dzeta[dev]) {
+                QC_CUDA(cudaMalloc((void **)&g_dzeta[dev], g_zeta.size() * sizeof(double)));
+                QC_CUDA(cudaMalloc((void **)&g_dzvalid[dev], g_zvalid.size() * sizeof(int)));
+                QC_CUDA(cudaMemcpy(g_dzeta[dev], g_zeta.data(), g_zeta.size() * sizeof(double), cudaMemcpyHostToDevice));
+                QC_CUDA(cudaMemcpy(g_dzvalid[dev], g_zvalid.data(), g_zvalid.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+            P.zeta_hat = g_dzeta[dev]; P.zeta_true = g_dzvalid[dev]; P.dim_zeta = 60;
+            P.z_gamma_min = g_zpar[0]; P.z_gamma_max = g_zpar[1]; P.z_xihat_min = g_zpar[2]; P.z_xihat_max = g_zpar[3];
+            P.mtable = mlog10_table();
+            if (!P.mtable) return QC_ECUDA;
+            return QC_OK;
+        }
         if (P.gain_method != 2) return QC_OK;
         std::lock_guard<std::mutex> g(g_tab_mu);
         if (g_GG.empty()) { set_error("emnr: gain method 2 needs the two 241 x 241 tables of the WDSP distribution (wdsp/calculus.c or its `calculus` file): hand them over with quisk_cuda_emnr_set_tables first"); return QC_EINVAL; }
@@ -522,7 +584,7 @@ struct Emnr {
 
     int run(const cd *d_in, long is, cd *d_out, long os, cudaStream_t s)
     {   // xemnr with run = 1, emnr.c:1015-1064
-        if (P.gain_method < 0 || P.gain_method > 2) { set_error("emnr: gain method %d is not built (0, 1, 2 are)", P.gain_method); return QC_EINVAL; }
+        if (P.gain_method < 0 || P.gain_method > 3) { set_error("emnr: there is no gain method %d (0 .. 3)", P.gain_method); return QC_EINVAL; }
         int rc = tables(); if (rc != QC_OK) return rc;
         emnr_in_kernel<<<C, 256, 0, s>>>(d_in, is, P.bsize, d_state, L, iainidx, P.iasize);
         count_launch();
@@ -569,6 +631,12 @@ int emnr_set(Emnr *e, int what, int value)
     return QC_EINVAL;
 }
 bool emnr_tables_present() { std::lock_guard<std::mutex> g(g_tab_mu); return !g_GG.empty(); }
+bool emnr_zeta_present() { std::lock_guard<std::mutex> g(g_tab_mu); return !g_zeta.empty(); }
+int emnr_set_train(Emnr *e, int what, double value)
+{   // SetRXAEMNRtrainZetaThresh (emnr.c:1160-1166), SetRXAEMNRtrainT2 (emnr.c:1168-1174)
+    if (what == 0) e->P.zeta_thresh = value; else e->P.t2 = value;
+    return QC_OK;
+}
 
 }  // namespace qc
 
@@ -589,6 +657,21 @@ int quisk_cuda_emnr_set_tables(const double *GG, const double *GGS)
     return QC_OK;
 }
 
+int quisk_cuda_emnr_set_zeta(const double *zeta_hat, const int *zeta_valid, int rows, int cols, double gamma_min, double gamma_max, double xihat_min, double xihat_max)
+{
+    if (!zeta_hat || !zeta_valid || rows != 60 || cols != 60) { qc::set_error("emnr_set_zeta: a 60 x 60 table (dim_zeta, emnr.c:329) and its validity map"); return QC_EINVAL; }
+    std::lock_guard<std::mutex> g(qc::g_tab_mu);
+    qc::g_zeta.assign(zeta_hat, zeta_hat + 3600);
+    qc::g_zvalid.assign(zeta_valid, zeta_valid + 3600);
+    qc::g_zpar[0] = gamma_min; qc::g_zpar[1] = gamma_max; qc::g_zpar[2] = xihat_min; qc::g_zpar[3] = xihat_max;
+    for (int d = 0; d < 64; d++) {
+        if (qc::g_dzeta[d]) { cudaFree(qc::g_dzeta[d]); qc::g_dzeta[d] = nullptr; }
+        if (qc::g_dzvalid[d]) { cudaFree(qc::g_dzvalid[d]); qc::g_dzvalid[d] = nullptr; }
+    }
+    return QC_OK;
+}
+int quisk_cuda_emnr_set_train(qcEmnr *h, double zeta_thresh, double t2);
+
 qcEmnr *quisk_cuda_emnr_create(int n_channels, int bsize, int fsize, int ovrlp, int rate, int wintype, double gain, int gain_method, int npe_method, int ae_run)
 {
     if (qc::ensure_device() != QC_OK) return nullptr;
@@ -608,5 +691,11 @@ int quisk_cuda_emnr_flush(qcEmnr *h) { return h ? h->e->flush() : QC_EINVAL; }
 int quisk_cuda_emnr_set_gain_method(qcEmnr *h, int method) { return h ? qc::emnr_set(h->e, 0, method) : QC_EINVAL; }
 int quisk_cuda_emnr_set_npe_method(qcEmnr *h, int method) { return h ? qc::emnr_set(h->e, 1, method) : QC_EINVAL; }
 int quisk_cuda_emnr_set_ae_run(qcEmnr *h, int run) { return h ? qc::emnr_set(h->e, 2, run) : QC_EINVAL; }
+int quisk_cuda_emnr_set_train(qcEmnr *h, double zeta_thresh, double t2)
+{
+    if (!h) return QC_EINVAL;
+    qc::emnr_set_train(h->e, 0, zeta_thresh); qc::emnr_set_train(h->e, 1, t2);
+    return QC_OK;
+}
 
 }  // extern "C"

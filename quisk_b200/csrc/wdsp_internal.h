@@ -62,6 +62,8 @@ int emnr_run(Emnr *e, const cd *in, long is, cd *out, long os, cudaStream_t s);
 int emnr_flush(Emnr *e);
 int emnr_set(Emnr *e, int what /* 0 gain method, 1 npe method, 2 ae_run */, int value);
 bool emnr_tables_present();
+bool emnr_zeta_present();
+int emnr_set_train(Emnr *e, int what /* 0 zeta threshold, 1 t2 */, double value);
 
 struct SeqStage {
     int kind = 0, C = 0;

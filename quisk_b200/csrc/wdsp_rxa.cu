@@ -750,13 +750,18 @@ int quisk_cuda_rxa_set_emnr_run(qcRxa *p, int run)
         qc::set_error("SetRXAEMNRRun: gain method 2 needs the WDSP distribution's two gamma-prior tables: quisk_cuda_emnr_set_tables first (or choose gain method 0 or 1)");
         return QC_EINVAL;
     }
-    if (run && (r.emnr_gain_method < 0 || r.emnr_gain_method > 2)) { qc::set_error("SetRXAEMNRRun: gain method %d is not built", r.emnr_gain_method); return QC_EINVAL; }
+    if (run && r.emnr_gain_method == 3 && !qc::emnr_zeta_present()) {
+        qc::set_error("SetRXAEMNRRun: gain method 3 needs the WDSP distribution's trained zeta table: quisk_cuda_emnr_set_zeta first (or choose gain method 0 or 1)");
+        return QC_EINVAL;
+    }
+    if (run && (r.emnr_gain_method < 0 || r.emnr_gain_method > 3)) { qc::set_error("SetRXAEMNRRun: there is no gain method %d", r.emnr_gain_method); return QC_EINVAL; }
     r.emnr_run = run;
     return r.bp1_check_set();
 }
 int quisk_cuda_rxa_set_emnr_gain_method(qcRxa *p, int method) { if (!p) return QC_EINVAL; p->r.emnr_gain_method = method; return qc::emnr_set(p->r.emnr, 0, method); }
 int quisk_cuda_rxa_set_emnr_npe_method(qcRxa *p, int method) { return p ? qc::emnr_set(p->r.emnr, 1, method) : QC_EINVAL; }
 int quisk_cuda_rxa_set_emnr_ae_run(qcRxa *p, int run) { return p ? qc::emnr_set(p->r.emnr, 2, run) : QC_EINVAL; }
+int quisk_cuda_rxa_set_emnr_train(qcRxa *p, int what, double value) { return p ? qc::emnr_set_train(p->r.emnr, what, value) : QC_EINVAL; }   /* SetRXAEMNRtrainZetaThresh (0), SetRXAEMNRtrainT2 (1) */
 int quisk_cuda_rxa_set_emnr_position(qcRxa *p, int position) { if (!p) return QC_EINVAL; p->r.emnr_position = position ? 1 : 0; return QC_OK; }    /* SetRXAEMNRPosition moves bp1 with it */
 int quisk_cuda_rxa_set_fm_lim_run(qcRxa *p, int run) { if (!p) return QC_EINVAL; p->r.lim_run = run ? 1 : 0; return QC_OK; }      /* SetRXAFMLimRun, fmd.c:337-348 */
 int quisk_cuda_rxa_set_fm_lim_gain(qcRxa *p, double gain_db)

@@ -10,7 +10,7 @@ import numpy as np
 from . import lib as L
 
 MODES = {"CWL": 0, "CWU": 1, "LSB": 2, "USB": 3, "AM": 4, "FM": 5,
-         "DGT-U": 7, "DGT-L": 8, "DGT-IQ": 9, "FDV-U": 11, "FDV-L": 12}     # quisk.h:56-70
+         "DGT-U": 7, "DGT-L": 8, "DGT-IQ": 9, "FDV-U": 11, "FDV-L": 12, "DGT-FM": 13}     # quisk.h:56-70
 KINDS = {"cDecim2HB45": 1, "cDecimate": 2, "cCDecimate": 3, "dDecimate": 4, "cInterpolate": 5,
          "dInterpolate": 6, "cInterpDecim": 7, "cInterp2HB45": 8, "dInterp2HB45": 9,
          "cRxFilter": 10, "dRxFilter": 11}
