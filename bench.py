@@ -587,6 +587,102 @@ def run_pfb(args, ctx, steps, warmup, e2e_steps, cpu_steps):
             "cpu_baseline": cpu}
 
 
+def tx_reference_rate(block, steps, warmup, mode=3, preemph=0.6, clip=2.5):
+    """Microphone samples per second of the reference's own tx_filter (oracle/_ref/libquisk_tx_ref.so: microphone.c's
+    tx_filter + CcmPeak extracted at build time + filter.c verbatim) on all host cores, one private copy per core."""
+    import ctypes as C
+    from oracle import ref_ctypes as R
+    from tests.golden.make_golden_tx import mic_audio
+    cores = os.cpu_count() or 1
+    libs = []
+    for _ in range(cores):
+        lib = R.load("libquisk_tx_ref.so", private_copy=True)
+        lib.ref_tx_init.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+        lib.ref_tx_filter.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_tx_init(mode, 48000, preemph, clip)
+        libs.append(lib)
+    x = np.resize(mic_audio(), block).astype(np.complex128)
+    bufs = [np.zeros(2 * block, dtype=np.complex128) for _ in range(cores)]
+
+    def work(i, nsteps):
+        for _ in range(nsteps):
+            bufs[i][:block] = x
+            libs[i].ref_tx_filter(bufs[i].ctypes.data_as(C.c_void_p), block)
+
+    def run(nsteps):
+        th = [threading.Thread(target=work, args=(i, nsteps)) for i in range(cores)]
+        t0 = time.perf_counter()
+        for t in th: t.start()
+        for t in th: t.join()
+        return time.perf_counter() - t0
+
+    run(warmup)
+    dt = run(steps)
+    return cores * block * steps / dt / 1e6, cores, dt
+
+
+def run_tx(args, ctx, steps, warmup, e2e_steps, cpu_steps):
+    """The TX mirror: C transmitters x 48 kS/s microphone audio through tx_filter (USB), 0.25 s blocks."""
+    torch, lib = ctx.torch, ctx.lib
+    from quisk_b200.rx import TxFilter, load_tables
+    from tests.golden.make_golden_tx import mic_audio
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    C_ = args.channels if args.channels > 0 else 4096
+    n = 12000
+    tx = TxFilter(C_, "USB", load_tables(), mic_sample_rate=48000, preemphasis=0.6, clip=2.5)
+    base = torch.from_numpy(np.resize(mic_audio(), n + 101)).to(dev)
+    x = torch.stack([base[(c % 101):(c % 101) + n] for c in range(C_)]).to(torch.complex128).contiguous()
+    y = torch.zeros((C_, tx.max_out(n) + 8), dtype=torch.complex128, device=dev)
+    stream = ctx.stream             # torch's current stream: the copies of the e2e leg and the kernels share it
+
+    def step():
+        tx.process(x.data_ptr(), x.stride(0), n, y.data_ptr(), y.stride(0), stream)
+
+    ms, ms_max, launches, clocks = timed_steps(ctx, step, steps, warmup)
+    value = world * C_ * n * steps / (ms_max / 1e3) / 1e6
+    e2e = None
+    if e2e_steps > 0:
+        hx = torch.empty((C_, n, 2), dtype=torch.float64).pin_memory(); hx.copy_(torch.view_as_real(x).cpu())
+        hy = torch.empty((C_, n, 2), dtype=torch.float64).pin_memory()
+        xr = torch.view_as_real(x); yr = torch.view_as_real(y)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            xr.copy_(hx, non_blocking=True)
+            step()
+            hy.copy_(yr[:, :n], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * C_ * n * e2e_steps / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": int(hx.numel() * 8), "d2h_bytes_per_step": int(hy.numel() * 8),
+               "channels": C_, "note": "pinned host microphone blocks (complex double, as tx_filter takes them) -> H2D -> quisk_cuda_tx_filter_process -> D2H of the 48 kS/s I/Q"}
+        del hx, hy
+    tx.close()
+    del x, y
+    if rank != 0:
+        return None
+    peak, peak_src = load_peaks()
+    alg = 32.0 * C_ * n
+    ach = alg * steps / (ms / 1e3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, cores, dt = tx_reference_rate(48000, cpu_steps, 1)
+            cpu = {"value": v, "unit": "MS/s", "cores": cores, "kind": "reference",
+                   "sample": "%d transmitters (one per host core) x 48000 samples x %d steps, %.1f s wall; oracle/_ref/libquisk_tx_ref.so = microphone.c tx_filter + CcmPeak + filter.c verbatim, gcc -O2" % (cores, cpu_steps, dt)}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "MS/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
+    return {"metric": "complex MS/s through RX chain", "value": value, "unit": "MS/s", "n_gpus": world, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "tx_filter: C transmitters x 48 kS/s microphone audio -> microphone.c tx_filter (USB: decimate, band-limit, pre-emphasis, compressor, limiter, peak rounder, x6 interpolation) -> 48 kS/s I/Q (the TX mirror, SURVEY 8(f)4); value counts microphone samples",
+                       "channels_per_gpu": C_, "block": n, "mic_rate": 48000,
+                       "l2": "input %.0f MB + output %.0f MB per step per GPU >> 126 MB L2, no flush needed" % (C_ * n * 16 / 1e6, C_ * n * 16 / 1e6)},
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e,
+            "roofline": {"bound": "hbm", "kernel": "whole step (exact FIR kernels + two per-transmitter gain recurrences at 8 kS/s)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_sample": 32.0},
+            "cpu_baseline": cpu}
+
+
 def run_chain(args, ctx, workload, steps, warmup, e2e_steps, cpu_blocks, fi, fq, tabs, wl_name):
     """rx_chain (BASELINE configs[0] batched), panadapter (configs[1] batched) or both on the same input."""
     torch, lib, L = ctx.torch, ctx.lib, ctx.L
@@ -777,7 +873,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rate", type=int, default=SAMPLE_RATE, help="rx_chain / panadapter input sample rate")
-    ap.add_argument("--workload", default="", choices=["", "rx_chain", "panadapter", "rx_chain+panadapter", "pipeline", "rxa_usb", "rxa_fm", "channelizer"],
+    ap.add_argument("--workload", default="", choices=["", "rx_chain", "panadapter", "rx_chain+panadapter", "pipeline", "rxa_usb", "rxa_fm", "channelizer", "tx_filter"],
                     help="default: rx_chain as the headline line plus short runs of the other workloads under `workloads`")
     ap.add_argument("--no-extra", action="store_true", help="default run: rx_chain only, no `workloads` key")
     ap.add_argument("--channels", type=int, default=0, help="channels per GPU (0 = the workload's own: 4096 / 16 / 64 / 256)")
@@ -849,6 +945,8 @@ def main():
         line = run_rxa(args, ctx, workload, args.steps, args.warmup, args.e2e_steps, 8)
     elif workload == "channelizer":
         line = run_pfb(args, ctx, args.steps, args.warmup, args.e2e_steps, 30)
+    elif workload == "tx_filter":
+        line = run_tx(args, ctx, args.steps, args.warmup, args.e2e_steps, 40)
     else:
         line = run_chain(args, ctx, workload, args.steps, args.warmup, args.e2e_steps, 600, fi, fq, tabs, wl_names[workload])
         if not args.workload and not args.no_extra:
@@ -863,6 +961,7 @@ def main():
             extra["rxa_usb"] = run_rxa(args, ctx, "rxa_usb", st, 3, 1, 3)
             extra["rxa_fm"] = run_rxa(args, ctx, "rxa_fm", st, 3, 1, 3)
             extra["channelizer"] = run_pfb(args, ctx, st, 3, 2, 8)
+            extra["tx_filter"] = run_tx(args, ctx, st, 3, 2, 10)
             args.channels, args.block = 1024, 32768
             RATE[0] = 192000
             pname = "pipeline (north-star target): C x 192 kS/s receivers, tune -> decimate to 48 k -> HB45 -> FIR98/2 -> cRxFilterOut band-pass (164 I/Q) -> USB demod -> audio 48 k, + 8192-pt panadapter on the same input"

@@ -361,6 +361,27 @@ void quisk_cuda_fracdecim_destroy(qcFracDecim *f);
 int quisk_cuda_fracdecim_run(qcFracDecim *f, const void *d_in, long in_stride, int count, double fdecim,
                              void *d_out, long out_stride, int *n_out, void *stream);
 
+/* ---- 3c'. The transmit-audio chain of microphone.c, batched over n_channels independent transmitters (SURVEY.md 8(f) row 4,
+ * "the TX mirror"): tx_filter (microphone.c:372-604) with its peak rounder CcmPeak (:161-233).  Input: microphone audio
+ * on the real rail of complex double samples, +-CLIP16, at 48000 or 8000 samples per second (`count` per transmitter, any
+ * block size); output: the filtered, compressed, peak-limited modulation at 48 kS/s -- complex (I/Q) for LSB / USB, on the
+ * real rail for AM / FM -- exactly what tx_filter leaves in its `filtered` buffer for transmit_mic_carrier / the SSB
+ * up-converter to take.  mic_preemphasis = quisk_mic_preemphasis, mic_clip = quisk_mic_clip (microphone.c:35-37).  The
+ * three coefficient tables are the reference's filters.h tables of the same names.  CcmPeak's first call only
+ * initialises (microphone.c:174-191): the first block of a stream passes the peak rounder untouched, as there. */
+typedef struct qcTxFilter qcTxFilter;
+typedef struct {
+    const double *mic_filt8;  int n_mic_filt8;      /* quiskMicFilt8Coefs  (93)  */
+    const double *lp_filt48;  int n_lp_filt48;      /* quiskLpFilt48Coefs  (186) */
+    const double *tx8k_audio; int n_tx8k_audio;     /* quiskFiltTx8kAudioB (168) */
+} qcTxTables;
+qcTxFilter *quisk_cuda_tx_filter_create(int n_channels, int mode /* QC_MODE_LSB, _USB, _AM, _FM */, int mic_sample_rate,
+                                        double mic_preemphasis, double mic_clip, const qcTxTables *tables);
+void quisk_cuda_tx_filter_destroy(qcTxFilter *t);
+int quisk_cuda_tx_filter_max_out(const qcTxFilter *t, int count);        /* upper bound of the samples one call returns */
+int quisk_cuda_tx_filter_process(qcTxFilter *t, const void *d_in, long in_stride, int count,
+                                 void *d_out, long out_stride, int *n_out, void *stream);   /* device pointers, strides in complex samples */
+
 /* ---- 3d. NoiseBlanker (quisk.c:679-784), batched: the optional impulse blanker Quisk runs on the raw samples in front
  * of the tuning stage (quisk.c:2448-2449).  In place on d_samples [n_channels][stride] quisk_cd;
  * `level` = quisk_noise_blanker (1, 2, 3 -> threshold 6, 4, 2.5 times the mean magnitude of the last 1.5 ms; <= 0: off,

@@ -11,6 +11,7 @@
 #   _ref/libquisk_rx_ref.so      filter.c + the static RX functions of quisk.c (see ref_wrap/quisk_rx_wrap.c)
 #   _ref/libquisk_rx_ref_O3.so   the same at -O3: what bench.py times as the CPU reference
 #   _ref/libquisk_rx_dropin.so   the same RX functions of quisk.c linked against quisk_b200/libquisk_cuda.so instead of filter.c
+#   _ref/libquisk_tx_ref.so      filter.c + tx_filter / CcmPeak of microphone.c (see ref_wrap/quisk_tx_wrap.c)
 #   _ref/libquisk_wdspglue_ref.so  wdspFexchange0 of quisk_wdsp.c (the re-blocker in front of fexchange0)
 #   _ref/libwdsp_ref.so          wdsp/*.c (minus the make_*.c table generators) + our FFTW-API shim
 #
@@ -64,6 +65,11 @@ fi
 # 2c. Quisk's side of the WDSP boundary: wdspFexchange0 (quisk_wdsp.c:7-69) through its own wrapper TU
 sed -n '7,69p' "$REF/quisk_wdsp.c" > "$TMP/quisk_wdsp_glue.inc"
 gcc -O2 -fPIC -shared -w -I"$TMP" "$HERE/ref_wrap/quisk_wdsp_wrap.c" -o "$OUT/libquisk_wdspglue_ref.so" -lm
+
+# 2d. The transmit-audio chain of microphone.c (tx_filter + CcmPeak) through its own wrapper TU: the TX mirror of the
+#     receive path, same filter.c underneath
+{ sed -n '161,233p' "$REF/microphone.c"; sed -n '372,604p' "$REF/microphone.c"; } > "$TMP/quisk_tx_funcs.inc"
+gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_tx_wrap.c" "$REF/filter.c" -o "$OUT/libquisk_tx_ref.so" -lm
 
 # 3. WDSP against the FFTW shim
 WSRC=$(ls "$REF"/wdsp/*.c | grep -v '/make_')

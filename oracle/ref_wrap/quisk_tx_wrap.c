@@ -1,0 +1,39 @@
+/* oracle/ref_wrap/quisk_tx_wrap.c -- TEST INFRASTRUCTURE, not product code.
+ *
+ * Turns the `static` transmit-audio functions of the reference's microphone.c into a loadable library WITHOUT copying
+ * them into this repository: oracle/build_ref.sh extracts the line ranges below from /root/reference/microphone.c into a
+ * scratch file at build time and this wrapper `#include`s it.  Everything in THIS file is our own glue: the file-scope
+ * variables those functions read (microphone.c:29-37, 65; quisk.c:111) and `ref_tx_*` accessors for ctypes.
+ *
+ * Extracted ranges (microphone.c): 161-233 CcmPeak, 372-604 tx_filter.
+ */
+#include <Python.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <complex.h>
+#include "quisk.h"
+#include "filter.h"
+
+#define DEBUG 0
+#define DEBUG_IO 0
+#define MIC_OUT_RATE 48000              /* microphone.c:29-31 */
+
+struct sound_conf quisk_sound_state;
+rx_mode_type rxMode;
+double quisk_mic_preemphasis;
+double quisk_mic_clip;
+static double mic_agc_level = 0.10;     /* microphone.c:65 */
+
+#include "quisk_tx_funcs.inc"           /* microphone.c:161-233, 372-604 */
+
+void ref_tx_init(int mode, int mic_sample_rate, double preemphasis, double clip)
+{
+    rxMode = (rx_mode_type)mode;
+    quisk_sound_state.mic_sample_rate = mic_sample_rate;
+    quisk_mic_preemphasis = preemphasis;
+    quisk_mic_clip = clip;
+    tx_filter(NULL, 0);
+}
+
+int ref_tx_filter(complex double *samples, int count) { return tx_filter(samples, count); }

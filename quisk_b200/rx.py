@@ -250,6 +250,44 @@ class Panadapter:
     __del__ = close
 
 
+class TxTables(C.Structure):
+    _fields_ = [("mic_filt8", C.POINTER(C.c_double)), ("n_mic_filt8", C.c_int),
+                ("lp_filt48", C.POINTER(C.c_double)), ("n_lp_filt48", C.c_int),
+                ("tx8k_audio", C.POINTER(C.c_double)), ("n_tx8k_audio", C.c_int)]
+
+
+class TxFilter:
+    """The transmit-audio chain of the reference's microphone.c for a batch of transmitters: `tx_filter`
+    (microphone.c:372-604; what `quisk_process_microphone` runs on the microphone block at :1232) with its peak rounder
+    `CcmPeak` (:161-233).  mode: "LSB", "USB" (complex I/Q out), "AM", "FM" (real rail out).  `preemphasis` and `clip` are
+    the reference's `quisk_mic_preemphasis` and `quisk_mic_clip`.  process(): device pointers, [n_channels][stride]
+    complex128 in (microphone audio on the real rail, +-CLIP16) and out (48 kS/s); returns the samples per channel."""
+
+    def __init__(self, n_channels: int, mode: str, tables: dict, mic_sample_rate: int = 48000, preemphasis: float = 0.6, clip: float = 1.0):
+        self.lib = L.require_device()
+        self.n_channels = n_channels
+        self._keep = [np.ascontiguousarray(tables[k], dtype=np.float64) for k in ("quiskMicFilt8Coefs", "quiskLpFilt48Coefs", "quiskFiltTx8kAudioB")]
+        t = TxTables()
+        for (name, cnt), a in zip((("mic_filt8", "n_mic_filt8"), ("lp_filt48", "n_lp_filt48"), ("tx8k_audio", "n_tx8k_audio")), self._keep):
+            setattr(t, name, a.ctypes.data_as(C.POINTER(C.c_double))); setattr(t, cnt, len(a))
+        self.h = self.lib.quisk_cuda_tx_filter_create(n_channels, MODES[mode], mic_sample_rate, preemphasis, clip, C.byref(t))
+        if not self.h:
+            raise L.QuiskCudaError("tx_filter_create: " + self.lib.quisk_cuda_last_error().decode())
+
+    def max_out(self, count: int) -> int:
+        return self.lib.quisk_cuda_tx_filter_max_out(self.h, count)
+
+    def process(self, d_in: int, in_stride: int, count: int, d_out: int, out_stride: int, stream: int = 0) -> int:
+        n = C.c_int(0)
+        L.check(self.lib, self.lib.quisk_cuda_tx_filter_process(self.h, d_in, in_stride, count, d_out, out_stride, C.byref(n), stream or None), "tx_filter_process")
+        return n.value
+
+    def close(self):
+        if self.h:
+            self.lib.quisk_cuda_tx_filter_destroy(self.h)
+            self.h = None
+
+
 class RxOptions:
     """Host-side mirror of the three optional receive stages Quisk switches from Python -- `set_noise_blanker(level)`
     (quisk.c:4605-4611), `set_auto_notch(on)` (quisk.c:4596-4603) and `set_ssb_squelch(enabled, level)`
