@@ -374,8 +374,10 @@ typedef struct {
     const double *mic_filt8;  int n_mic_filt8;      /* quiskMicFilt8Coefs  (93)  */
     const double *lp_filt48;  int n_lp_filt48;      /* quiskLpFilt48Coefs  (186) */
     const double *tx8k_audio; int n_tx8k_audio;     /* quiskFiltTx8kAudioB (168) */
+    const double *dgt_filt48; int n_dgt_filt48;     /* quiskDgtFilt48Coefs (520): the digital modes only, may be NULL otherwise */
 } qcTxTables;
-qcTxFilter *quisk_cuda_tx_filter_create(int n_channels, int mode /* QC_MODE_LSB, _USB, _AM, _FM */, int mic_sample_rate,
+qcTxFilter *quisk_cuda_tx_filter_create(int n_channels, int mode /* QC_MODE_LSB, _USB, _AM, _FM: tx_filter; _DGT_U/L, _FDV_U/L: tx_filter_digital
+                                           (microphone.c:605-624: one tuned filter at 48 kS/s, no speech processing) */, int mic_sample_rate,
                                         double mic_preemphasis, double mic_clip, const qcTxTables *tables);
 void quisk_cuda_tx_filter_destroy(qcTxFilter *t);
 int quisk_cuda_tx_filter_max_out(const qcTxFilter *t, int count);        /* upper bound of the samples one call returns */

@@ -5,7 +5,7 @@
  * scratch file at build time and this wrapper `#include`s it.  Everything in THIS file is our own glue: the file-scope
  * variables those functions read (microphone.c:29-37, 65; quisk.c:111) and `ref_tx_*` accessors for ctypes.
  *
- * Extracted ranges (microphone.c): 161-233 CcmPeak, 372-604 tx_filter.
+ * Extracted ranges (microphone.c): 161-233 CcmPeak, 372-604 tx_filter, 605-624 tx_filter_digital.
  */
 #include <Python.h>
 #include <stdlib.h>
@@ -25,7 +25,7 @@ double quisk_mic_preemphasis;
 double quisk_mic_clip;
 static double mic_agc_level = 0.10;     /* microphone.c:65 */
 
-#include "quisk_tx_funcs.inc"           /* microphone.c:161-233, 372-604 */
+#include "quisk_tx_funcs.inc"           /* microphone.c:161-233, 372-624 */
 
 void ref_tx_init(int mode, int mic_sample_rate, double preemphasis, double clip)
 {
@@ -37,3 +37,6 @@ void ref_tx_init(int mode, int mic_sample_rate, double preemphasis, double clip)
 }
 
 int ref_tx_filter(complex double *samples, int count) { return tx_filter(samples, count); }
+
+void ref_tx_digital_init(int mode) { rxMode = (rx_mode_type)mode; tx_filter_digital(NULL, 0); }
+int ref_tx_filter_digital(complex double *samples, int count) { return tx_filter_digital(samples, count); }

@@ -58,6 +58,13 @@ __global__ void tx_carry_kernel(const double *__restrict__ in, long st, int n, d
     if (c < C && n > 0) x1[c] = in[(size_t)c * st + n - 1];
 }
 
+__global__ void tx_real_rail_kernel(const cd *__restrict__ in, long is, cd *__restrict__ out, long os, int n)
+{
+    const int c = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[(size_t)c * os + i] = make_double2(in[(size_t)c * is + i].x, 0.0);          // creal(filtered[i]), microphone.c:620
+}
+
 __global__ void tx_promote_kernel(const double *__restrict__ in, long is, cd *__restrict__ out, long os, int n)
 {
     const int c = blockIdx.y;
@@ -208,7 +215,7 @@ __global__ void tx_out_real_kernel(const double *__restrict__ in, long is, cd *_
 
 struct TxFilter {
     int C = 0, mode = 0, mic_rate = 48000, decim = 6;
-    bool ssb = false, ccm_started = false;
+    bool ssb = false, ccm_started = false, digital = false;
     double preemph = 0.0;
     TxLevelPar P;
     BatchFilter *fDecim = nullptr, *fAudio1 = nullptr, *fAudio2 = nullptr, *fAudio3 = nullptr, *fInterp = nullptr, *fTune1 = nullptr, *fTune2 = nullptr;
@@ -244,7 +251,22 @@ struct TxFilter {
     {
         C = C_; mode = mode_; mic_rate = mic_rate_; preemph = preemph_;
         if (C <= 0 || (mic_rate != 8000 && mic_rate != 48000)) { set_error("tx_filter_create: the microphone rate must be 8000 or 48000 (microphone.c:373)"); return QC_EINVAL; }
-        if (mode != QC_MODE_LSB && mode != QC_MODE_USB && mode != QC_MODE_AM && mode != QC_MODE_FM) { set_error("tx_filter_create: tx_filter serves LSB, USB, AM and FM"); return QC_EINVAL; }
+        digital = mode == QC_MODE_DGT_U || mode == QC_MODE_DGT_L || mode == QC_MODE_FDV_U || mode == QC_MODE_FDV_L;
+        if (digital) {
+            // tx_filter_digital (microphone.c:605-624): ONE filter, quiskDgtFilt48Coefs tuned to +-1650 Hz at 48 kS/s, times two
+            if (mic_rate != 48000) { set_error("tx_filter_create: the digital modes run at 48000 samples per second (microphone.c:617)"); return QC_EINVAL; }
+            if (!T.dgt_filt48 || T.n_dgt_filt48 <= 0) { set_error("tx_filter_create: quiskDgtFilt48Coefs is needed for the digital modes"); return QC_EINVAL; }
+            decim = 1;
+            struct quisk_dFilter tf;
+            memset(&tf, 0, sizeof(tf));
+            std::vector<double> taps(T.dgt_filt48, T.dgt_filt48 + T.n_dgt_filt48);
+            quisk_filt_dInit(&tf, taps.data(), T.n_dgt_filt48);
+            quisk_filt_tune(&tf, 1650.0 / 48000, mode != QC_MODE_DGT_L && mode != QC_MODE_FDV_L);
+            fTune1 = mk(QC_C_CDECIMATE, C, (const double *)tf.cpxCoefs, T.n_dgt_filt48, 1, 1);
+            free(tf.cpxCoefs); free(tf.dSamples);
+            return fTune1 ? QC_OK : QC_EINVAL;
+        }
+        if (mode != QC_MODE_LSB && mode != QC_MODE_USB && mode != QC_MODE_AM && mode != QC_MODE_FM) { set_error("tx_filter_create: tx_filter serves LSB, USB, AM and FM, tx_filter_digital DGT-U/L and FDV-U/L"); return QC_EINVAL; }
         if (!T.mic_filt8 || !T.lp_filt48 || !T.tx8k_audio) { set_error("tx_filter_create: quiskMicFilt8Coefs, quiskLpFilt48Coefs and quiskFiltTx8kAudioB are needed"); return QC_EINVAL; }
         ssb = mode == QC_MODE_LSB || mode == QC_MODE_USB;
         decim = mic_rate / 8000;
@@ -302,7 +324,7 @@ struct TxFilter {
         return QC_OK;
     }
 
-    int max_out(int count) const { return (count / decim + 1) * decim; }
+    int max_out(int count) const { return digital ? count : (count / decim + 1) * decim; }
 
     int process(const cd *d_in, long is, int count, cd *d_out, long os, int *n_out, cudaStream_t s)
     {
@@ -313,6 +335,14 @@ struct TxFilter {
         const dim3 g((unsigned)((count + 255) / 256 < 64 ? (count + 255) / 256 : 64), (unsigned)C);
         const int gc = (C + 63) / 64;
         int n = count, no = 0;
+        if (digital) {
+            // filtered[i] = quisk_dC_out(creal(filtered[i]), &filter1) * 2.00: the real rail promoted, the tuned taps, times two
+            tx_real_rail_kernel<<<g, 256, 0, s>>>(d_in, is, d_c[0], cap, n); count_launch(); QC_CUDA_LAUNCH();
+            rc = fTune1->run(d_c[0], cap, n, d_out, os, &no, 0, s); if (rc != QC_OK) return rc;
+            tx_scale_c_kernel<<<g, 256, 0, s>>>(d_out, os, n, 2.0); count_launch(); QC_CUDA_LAUNCH();
+            if (n_out) *n_out = n;
+            return QC_OK;
+        }
         tx_in_kernel<<<g, 256, 0, s>>>(d_in, is, d_r[0], cap, n); count_launch(); QC_CUDA_LAUNCH();
         int cur = 0;
         if (fDecim) { rc = fDecim->run(d_r[0], cap, n, d_r[1], cap, &no, 0, s); if (rc != QC_OK) return rc; n = no; cur = 1; }

@@ -253,22 +253,24 @@ class Panadapter:
 class TxTables(C.Structure):
     _fields_ = [("mic_filt8", C.POINTER(C.c_double)), ("n_mic_filt8", C.c_int),
                 ("lp_filt48", C.POINTER(C.c_double)), ("n_lp_filt48", C.c_int),
-                ("tx8k_audio", C.POINTER(C.c_double)), ("n_tx8k_audio", C.c_int)]
+                ("tx8k_audio", C.POINTER(C.c_double)), ("n_tx8k_audio", C.c_int),
+                ("dgt_filt48", C.POINTER(C.c_double)), ("n_dgt_filt48", C.c_int)]
 
 
 class TxFilter:
     """The transmit-audio chain of the reference's microphone.c for a batch of transmitters: `tx_filter`
     (microphone.c:372-604; what `quisk_process_microphone` runs on the microphone block at :1232) with its peak rounder
-    `CcmPeak` (:161-233).  mode: "LSB", "USB" (complex I/Q out), "AM", "FM" (real rail out).  `preemphasis` and `clip` are
+    `CcmPeak` (:161-233); in the digital modes "DGT-U", "DGT-L", "FDV-U", "FDV-L" it is `tx_filter_digital` (:605-624: one tuned
+    filter at 48 kS/s).  mode: "LSB", "USB" (complex I/Q out), "AM", "FM" (real rail out).  `preemphasis` and `clip` are
     the reference's `quisk_mic_preemphasis` and `quisk_mic_clip`.  process(): device pointers, [n_channels][stride]
     complex128 in (microphone audio on the real rail, +-CLIP16) and out (48 kS/s); returns the samples per channel."""
 
     def __init__(self, n_channels: int, mode: str, tables: dict, mic_sample_rate: int = 48000, preemphasis: float = 0.6, clip: float = 1.0):
         self.lib = L.require_device()
         self.n_channels = n_channels
-        self._keep = [np.ascontiguousarray(tables[k], dtype=np.float64) for k in ("quiskMicFilt8Coefs", "quiskLpFilt48Coefs", "quiskFiltTx8kAudioB")]
+        self._keep = [np.ascontiguousarray(tables[k], dtype=np.float64) for k in ("quiskMicFilt8Coefs", "quiskLpFilt48Coefs", "quiskFiltTx8kAudioB", "quiskDgtFilt48Coefs")]
         t = TxTables()
-        for (name, cnt), a in zip((("mic_filt8", "n_mic_filt8"), ("lp_filt48", "n_lp_filt48"), ("tx8k_audio", "n_tx8k_audio")), self._keep):
+        for (name, cnt), a in zip((("mic_filt8", "n_mic_filt8"), ("lp_filt48", "n_lp_filt48"), ("tx8k_audio", "n_tx8k_audio"), ("dgt_filt48", "n_dgt_filt48")), self._keep):
             setattr(t, name, a.ctypes.data_as(C.POINTER(C.c_double))); setattr(t, cnt, len(a))
         self.h = self.lib.quisk_cuda_tx_filter_create(n_channels, MODES[mode], mic_sample_rate, preemphasis, clip, C.byref(t))
         if not self.h:

@@ -3,6 +3,7 @@ microphone.c:372-604, with CcmPeak :161-233) from the COMPILED REFERENCE (oracle
 functions extracted at build time + filter.c verbatim, oracle/ref_wrap/quisk_tx_wrap.c).  Microphone audio at 48 kS/s in
 the +-CLIP16 range, ragged blocks, the four modes tx_filter distinguishes (LSB / USB: the SSB branch; AM / FM: the real
 branch), with pre-emphasis and enough clip gain that the compressor, the clipper and the peak rounder all engage.
+Also tx_filter_digital (microphone.c:605-624), the digital modes' one-filter chain, both side bands.
 Writes tests/golden/tx_kat.npz.   Run:  python tests/golden/make_golden_tx.py"""
 import ctypes as C
 import os
@@ -17,6 +18,7 @@ from oracle import ref_ctypes as R            # noqa: E402
 
 MIC_RATE = 48000
 TX_MODES = {"LSB": 2, "USB": 3, "AM": 4, "FM": 5}
+DGT_TX_MODES = {"DGT-U": 7, "DGT-L": 8}       # FDV-U / FDV-L tune like DGT-U / DGT-L (microphone.c:617)
 PREEMPH, CLIP = 0.6, 2.5
 TX_SPLITS = [4800, 4806, 1, 5, 9600, 1023, 12000, 600, 6, 7, 48000 - 4800 - 4806 - 1 - 5 - 9600 - 1023 - 12000 - 600 - 6 - 7, 24000]
 
@@ -56,6 +58,19 @@ def main():
         out["tx_%s/y" % name] = y
         out["tx_%s/counts" % name] = np.array(counts)
         print(name, "out", len(y), "peak", np.abs(y).max(), "rms", np.sqrt(np.mean(np.abs(y) ** 2)))
+    # tx_filter_digital (microphone.c:605-624): one tuned 520-tap filter at 48 kS/s, upper and lower side band
+    for name, mode in DGT_TX_MODES.items():
+        lib = R.load("libquisk_tx_ref.so", private_copy=True)
+        lib.ref_tx_filter_digital.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_tx_digital_init(mode)
+        outs, pos = [], 0
+        for n in TX_SPLITS[:6]:
+            buf = np.zeros(max(n, 16), dtype=np.complex128); buf[:n] = x[pos:pos + n]; pos += n
+            nr = lib.ref_tx_filter_digital(buf.ctypes.data_as(C.c_void_p), n)
+            assert nr == n
+            outs.append(buf[:nr].copy())
+        out["txd_%s/y" % name] = np.concatenate(outs)
+        print(name, "digital out", len(out["txd_%s/y" % name]), "peak", np.abs(out["txd_%s/y" % name]).max())
     np.savez_compressed(os.path.join(HERE, "tx_kat.npz"), **out)
     print("wrote tx_kat.npz")
 

@@ -33,3 +33,19 @@ def test_tx_fixture_is_the_compiled_reference(mode):
         assert not y.imag.any()
         y = y.real
     assert np.array_equal(y, ref)
+
+
+@pytest.mark.skipif(not R.have_ref("libquisk_tx_ref.so"), reason="compiled reference not built (oracle/build_ref.sh)")
+@pytest.mark.parametrize("mode,key", [("DGT-U", "DGT-U"), ("DGT-L", "DGT-L"), ("FDV-U", "DGT-U"), ("FDV-L", "DGT-L")])
+def test_tx_digital_fixture_is_the_compiled_reference(mode, key):
+    kat = golden("tx_kat.npz")
+    x = mic_audio()
+    lib = R.load("libquisk_tx_ref.so", private_copy=True)
+    lib.ref_tx_filter_digital.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_tx_digital_init(R.MODES[mode])
+    outs, pos = [], 0
+    for n in TX_SPLITS[:6]:
+        buf = np.zeros(max(n, 16), dtype=np.complex128); buf[:n] = x[pos:pos + n]; pos += n
+        assert lib.ref_tx_filter_digital(buf.ctypes.data_as(C.c_void_p), n) == n
+        outs.append(buf[:n].copy())
+    assert np.array_equal(np.concatenate(outs), kat["txd_%s/y" % key])

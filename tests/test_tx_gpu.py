@@ -59,6 +59,26 @@ def test_tx_filter_parity(mode, torch, tabs):
     assert np.isfinite(y[2]).all() and np.abs(y[2]).max() > 1000.0 and O.rel_rms(y[2], ref) > 1e-3
 
 
+@pytest.mark.parametrize("mode", ["DGT-U", "DGT-L", "FDV-U", "FDV-L"])
+def test_tx_filter_digital_parity(mode, torch, tabs):
+    """tx_filter_digital (microphone.c:605-624): quisk_dC_out on the 520 tuned taps, times two -- exact kernels: bit for bit."""
+    from quisk_b200.rx import TxFilter
+    kat = golden("tx_kat.npz")
+    ref = kat["txd_%s/y" % {"FDV-U": "DGT-U", "FDV-L": "DGT-L"}.get(mode, mode)]        # FDV tunes like DGT (microphone.c:617)
+    x = mic_audio()
+    tx = TxFilter(2, mode, tabs, mic_sample_rate=48000)
+    d = torch.from_numpy(np.ascontiguousarray(np.stack([x + 0.25j * x, x]).astype(np.complex128))).cuda()      # the imaginary rail is ignored
+    outs, pos = [], 0
+    for n in TX_SPLITS[:6]:
+        blk = d[:, pos:pos + n].contiguous(); pos += n
+        out = torch.zeros((2, tx.max_out(n) + 8), dtype=torch.complex128, device="cuda")
+        assert tx.process(blk.data_ptr(), blk.stride(0), n, out.data_ptr(), out.stride(0)) == n
+        outs.append(out[:, :n].cpu().numpy())
+    tx.close()
+    y = np.concatenate(outs, axis=1)
+    assert np.array_equal(y[0], ref) and np.array_equal(y[1], ref)
+
+
 def test_tx_filter_rejects_what_tx_filter_does_not_serve(torch, tabs):
     from quisk_b200 import lib as L
     from quisk_b200.rx import TxFilter
