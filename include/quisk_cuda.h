@@ -380,6 +380,10 @@ qcTxFilter *quisk_cuda_tx_filter_create(int n_channels, int mode /* QC_MODE_LSB,
                                            (microphone.c:605-624: one tuned filter at 48 kS/s, no speech processing) */, int mic_sample_rate,
                                         double mic_preemphasis, double mic_clip, const qcTxTables *tables);
 void quisk_cuda_tx_filter_destroy(qcTxFilter *t);
+/* process_alc (microphone.c:270-370) behind the filter, as quisk_process_microphone chains them (:1232-1233).  enable = 1:
+ * init_alc(&tx_alc, 960) the first time and init_alc(&tx_alc, 0) every time (key down, :1207: the 20 ms delay line and the
+ * gain ramp cleared, the gain itself kept); enable = 0: off */
+int quisk_cuda_tx_filter_set_alc(qcTxFilter *t, int enable);
 int quisk_cuda_tx_filter_max_out(const qcTxFilter *t, int count);        /* upper bound of the samples one call returns */
 int quisk_cuda_tx_filter_process(qcTxFilter *t, const void *d_in, long in_stride, int count,
                                  void *d_out, long out_stride, int *n_out, void *stream);   /* device pointers, strides in complex samples */

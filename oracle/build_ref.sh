@@ -66,9 +66,9 @@ fi
 sed -n '7,69p' "$REF/quisk_wdsp.c" > "$TMP/quisk_wdsp_glue.inc"
 gcc -O2 -fPIC -shared -w -I"$TMP" "$HERE/ref_wrap/quisk_wdsp_wrap.c" -o "$OUT/libquisk_wdspglue_ref.so" -lm
 
-# 2d. The transmit-audio chain of microphone.c (tx_filter + CcmPeak + tx_filter_digital) through its own wrapper TU: the TX mirror of the
+# 2d. The transmit-audio chain of microphone.c (tx_filter + CcmPeak + tx_filter_digital + process_alc) through its own wrapper TU: the TX mirror of the
 #     receive path, same filter.c underneath
-{ sed -n '161,233p' "$REF/microphone.c"; sed -n '372,624p' "$REF/microphone.c"; } > "$TMP/quisk_tx_funcs.inc"
+{ sed -n '42,56p' "$REF/microphone.c"; sed -n '161,233p' "$REF/microphone.c"; sed -n '235,370p' "$REF/microphone.c"; sed -n '372,624p' "$REF/microphone.c"; } > "$TMP/quisk_tx_funcs.inc"
 gcc -O2 -fPIC -shared -w -I"$PYINC" -I"$REF" -I"$TMP" "$HERE/ref_wrap/quisk_tx_wrap.c" "$REF/filter.c" -o "$OUT/libquisk_tx_ref.so" -lm
 
 # 3. WDSP against the FFTW shim

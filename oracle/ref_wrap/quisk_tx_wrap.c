@@ -5,7 +5,8 @@
  * scratch file at build time and this wrapper `#include`s it.  Everything in THIS file is our own glue: the file-scope
  * variables those functions read (microphone.c:29-37, 65; quisk.c:111) and `ref_tx_*` accessors for ctypes.
  *
- * Extracted ranges (microphone.c): 161-233 CcmPeak, 372-604 tx_filter, 605-624 tx_filter_digital.
+ * Extracted ranges (microphone.c): 42-56 struct alc, 161-233 CcmPeak, 235-370 init_alc / process_alc, 372-604 tx_filter,
+ * 605-624 tx_filter_digital.
  */
 #include <Python.h>
 #include <stdlib.h>
@@ -25,7 +26,8 @@ double quisk_mic_preemphasis;
 double quisk_mic_clip;
 static double mic_agc_level = 0.10;     /* microphone.c:65 */
 
-#include "quisk_tx_funcs.inc"           /* microphone.c:161-233, 372-624 */
+#define DEBUG_LEVEL 0
+#include "quisk_tx_funcs.inc"           /* microphone.c:42-56, 161-233, 235-370, 372-624 */
 
 void ref_tx_init(int mode, int mic_sample_rate, double preemphasis, double clip)
 {
@@ -40,3 +42,8 @@ int ref_tx_filter(complex double *samples, int count) { return tx_filter(samples
 
 void ref_tx_digital_init(int mode) { rxMode = (rx_mode_type)mode; tx_filter_digital(NULL, 0); }
 int ref_tx_filter_digital(complex double *samples, int count) { return tx_filter_digital(samples, count); }
+
+static struct alc tx_alc;
+void ref_alc_init(void) { init_alc(&tx_alc, 960); init_alc(&tx_alc, 0); }      /* microphone.c:1178, 1207 */
+void ref_alc_key_down(void) { init_alc(&tx_alc, 0); }
+void ref_process_alc(complex double *samples, int count, int mode) { process_alc(samples, count, &tx_alc, (rx_mode_type)mode); }

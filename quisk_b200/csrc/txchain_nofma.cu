@@ -197,6 +197,70 @@ __global__ void __launch_bounds__(32 * CCM_WPB) tx_ccm_kernel(void *__restrict__
     if (lane == 0) { s[0] = themax; s[1] = level; s[2] = (double)idx; }
 }
 
+// process_alc (microphone.c:270-370): the transmit level control behind tx_filter (quisk_process_microphone, :1232-1233).  A
+// 960-sample (20 ms) delay line; every new sample that would clip at the gain the ramp is heading for re-aims the ramp so
+// that the gain is right when that sample leaves the line; once per trip round the line the ramp is re-aimed upward (at most
+// a doubling in five seconds) from the loudest sample seen.  A scalar state machine: one warp per transmitter keeps the
+// delay line in shared memory and stages the block 32 samples at a time, lane 0 walks it.
+// state per transmitter: gain_now, gain_change, next_change, final_gain, index, block_index, counter, fault, then 960 complex.
+static constexpr int ALC_N = 960, ALC_WPB = 2, ALC_SW = 8 + 2 * ALC_N;
+__global__ void __launch_bounds__(32 * ALC_WPB) tx_alc_kernel(cd *__restrict__ data, long st, int n, double *__restrict__ state, int C)
+{
+    __shared__ __align__(16) double sm[ALC_WPB * (2 * ALC_N + 128)];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * ALC_WPB + w;
+    if (c >= C) return;
+    double *s = state + (size_t)c * ALC_SW;
+    cd *buf = reinterpret_cast<cd *>(sm + w * (2 * ALC_N + 128));
+    cd *sin = buf + ALC_N, *sout = sin + 32;
+    for (int j = lane; j < ALC_N; j += 32) buf[j] = reinterpret_cast<const cd *>(s + 8)[j];
+    double gain_now = s[0], gain_change = s[1], next_change = s[2], final_gain = s[3];
+    int index = (int)s[4], block_index = (int)s[5], counter = (int)s[6], fault = (int)s[7];
+    const double gain_max = 3.0, gain_min = 0.1, top = (double)(32767 - 10);
+    cd *x = data + (size_t)c * st;
+    __syncwarp();
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int m = n - i0 < 32 ? n - i0 : 32;
+        if (lane < m) sin[lane] = x[i0 + lane];
+        __syncwarp();
+        if (lane == 0) {
+            for (int k = 0; k < m; k++) {
+                const cd csamp = sin[k];
+                const cd b = buf[index];
+                sout[k] = make_double2(b.x * gain_now, b.y * gain_now);
+                buf[index] = csamp;
+                const double magn = hypot(csamp.x, csamp.y);
+                if (magn * (gain_now + gain_change * ALC_N) > top) {
+                    gain_change = (top / magn - gain_now) / ALC_N;
+                    final_gain = gain_now + gain_change * ALC_N;
+                    if (final_gain > gain_max) { final_gain = gain_max; gain_change = (final_gain - gain_now) / ALC_N; }
+                    else if (final_gain < gain_min) { final_gain = gain_min; gain_change = (final_gain - gain_now) / ALC_N; }
+                    block_index = index; counter = 0; fault = 0; next_change = 1E10;
+                } else if (index == block_index) {
+                    double d = 5.0;
+                    d = 1.0 / (48000.0 * d);
+                    if (next_change > d) next_change = d;
+                    if (next_change != 1E10 && fault < ALC_N - 10) gain_change = next_change;
+                    final_gain = gain_now + gain_change * ALC_N;
+                    if (final_gain > gain_max) { final_gain = gain_max; gain_change = (final_gain - gain_now) / ALC_N; }
+                    else if (final_gain < gain_min) { final_gain = gain_min; gain_change = (final_gain - gain_now) / ALC_N; }
+                    fault = 0; counter = 0; next_change = 1E10;
+                } else {
+                    if (magn < 100) fault++;
+                    else { const double d = (top / magn - final_gain) / ++counter; if (next_change > d) next_change = d; }
+                }
+                gain_now += gain_change;
+                if (++index >= ALC_N) index = 0;
+            }
+        }
+        __syncwarp();
+        if (lane < m) x[i0 + lane] = sout[lane];
+        __syncwarp();
+    }
+    for (int j = lane; j < ALC_N; j += 32) reinterpret_cast<cd *>(s + 8)[j] = buf[j];
+    if (lane == 0) { s[0] = gain_now; s[1] = gain_change; s[2] = next_change; s[3] = final_gain; s[4] = index; s[5] = block_index; s[6] = counter; s[7] = fault; }
+}
+
 __global__ void tx_scale_c_kernel(cd *__restrict__ x, long st, int n, double g)
 {
     const int c = blockIdx.y;
@@ -219,7 +283,8 @@ struct TxFilter {
     double preemph = 0.0;
     TxLevelPar P;
     BatchFilter *fDecim = nullptr, *fAudio1 = nullptr, *fAudio2 = nullptr, *fAudio3 = nullptr, *fInterp = nullptr, *fTune1 = nullptr, *fTune2 = nullptr;
-    double *d_x1 = nullptr, *d_inmax = nullptr, *d_ccm = nullptr, *d_r[2] = {nullptr, nullptr};
+    double *d_x1 = nullptr, *d_inmax = nullptr, *d_ccm = nullptr, *d_alc = nullptr, *d_r[2] = {nullptr, nullptr};
+    bool alc_on = false;
     cd *d_c[2] = {nullptr, nullptr};
     long cap = 0;
 
@@ -307,8 +372,33 @@ struct TxFilter {
     {
         for (BatchFilter *f : {fDecim, fAudio1, fAudio2, fAudio3, fInterp, fTune1, fTune2}) if (f) { f->release(); delete f; }
         fDecim = fAudio1 = fAudio2 = fAudio3 = fInterp = fTune1 = fTune2 = nullptr;
-        for (void *p : {(void *)d_x1, (void *)d_inmax, (void *)d_ccm, (void *)d_r[0], (void *)d_r[1], (void *)d_c[0], (void *)d_c[1]}) if (p) cudaFree(p);
-        d_x1 = d_inmax = d_ccm = d_r[0] = d_r[1] = nullptr; d_c[0] = d_c[1] = nullptr;
+        for (void *p : {(void *)d_x1, (void *)d_inmax, (void *)d_ccm, (void *)d_alc, (void *)d_r[0], (void *)d_r[1], (void *)d_c[0], (void *)d_c[1]}) if (p) cudaFree(p);
+        d_x1 = d_inmax = d_ccm = d_alc = d_r[0] = d_r[1] = nullptr; d_c[0] = d_c[1] = nullptr;
+    }
+
+    int set_alc(int enable)
+    {   // enable: init_alc(&tx_alc, 960) the first time (gain 1.4 in the digital modes, 1.0 otherwise, microphone.c:242-254), and
+        // init_alc(&tx_alc, 0) every time (what quisk_process_microphone does on key down, :1207): line and ramp cleared, gain kept
+        alc_on = enable != 0;
+        if (!alc_on) return QC_OK;
+        std::vector<double> st((size_t)C * ALC_SW, 0.0);
+        if (d_alc) {
+            std::vector<double> old((size_t)C * ALC_SW);
+            QC_CUDA(cudaMemcpy(old.data(), d_alc, old.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int c = 0; c < C; c++) st[(size_t)c * ALC_SW] = old[(size_t)c * ALC_SW];
+        } else {
+            QC_CUDA(cudaMalloc((void **)&d_alc, st.size() * sizeof(double)));
+            for (int c = 0; c < C; c++) st[(size_t)c * ALC_SW] = digital ? 1.4 : 1.0;
+        }
+        QC_CUDA(cudaMemcpy(d_alc, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+        return QC_OK;
+    }
+
+    int run_alc(cd *d_out, long os, int n, cudaStream_t s)
+    {
+        if (!alc_on || n <= 0) return QC_OK;
+        tx_alc_kernel<<<(C + ALC_WPB - 1) / ALC_WPB, 32 * ALC_WPB, 0, s>>>(d_out, os, n, d_alc, C); count_launch(); QC_CUDA_LAUNCH();
+        return QC_OK;
     }
 
     int reserve(int count)
@@ -340,6 +430,7 @@ struct TxFilter {
             tx_real_rail_kernel<<<g, 256, 0, s>>>(d_in, is, d_c[0], cap, n); count_launch(); QC_CUDA_LAUNCH();
             rc = fTune1->run(d_c[0], cap, n, d_out, os, &no, 0, s); if (rc != QC_OK) return rc;
             tx_scale_c_kernel<<<g, 256, 0, s>>>(d_out, os, n, 2.0); count_launch(); QC_CUDA_LAUNCH();
+            rc = run_alc(d_out, os, n, s); if (rc != QC_OK) return rc;
             if (n_out) *n_out = n;
             return QC_OK;
         }
@@ -381,6 +472,7 @@ struct TxFilter {
             const dim3 g2((unsigned)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64), (unsigned)C);
             tx_out_real_kernel<<<g2, 256, 0, s>>>(d_r[cur], cap, d_out, os, n); count_launch(); QC_CUDA_LAUNCH();
         }
+        rc = run_alc(d_out, os, n, s); if (rc != QC_OK) return rc;
         if (n_out) *n_out = n;
         return QC_OK;
     }
@@ -401,6 +493,7 @@ qcTxFilter *quisk_cuda_tx_filter_create(int n_channels, int mode, int mic_sample
     return h;
 }
 void quisk_cuda_tx_filter_destroy(qcTxFilter *h) { if (h) { h->t.release(); delete h; } }
+int quisk_cuda_tx_filter_set_alc(qcTxFilter *h, int enable) { return h ? h->t.set_alc(enable) : QC_EINVAL; }
 int quisk_cuda_tx_filter_max_out(const qcTxFilter *h, int count) { return h ? h->t.max_out(count) : 0; }
 int quisk_cuda_tx_filter_process(qcTxFilter *h, const void *d_in, long in_stride, int count, void *d_out, long out_stride, int *n_out, void *stream)
 {

@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     lib.quisk_cuda_tx_filter_destroy.argtypes = [vp]
     lib.quisk_cuda_tx_filter_destroy.restype = None
     lib.quisk_cuda_tx_filter_max_out.argtypes = [vp, C.c_int]
+    lib.quisk_cuda_tx_filter_set_alc.argtypes = [vp, C.c_int]
     lib.quisk_cuda_tx_filter_process.argtypes = [vp, vp, C.c_long, C.c_int, vp, C.c_long, c_int_p, vp]
     lib.quisk_cuda_pan_create.argtypes = [C.c_int, C.c_int]
     lib.quisk_cuda_fp64_peak.argtypes = [C.POINTER(C.c_double)]

@@ -276,6 +276,10 @@ class TxFilter:
         if not self.h:
             raise L.QuiskCudaError("tx_filter_create: " + self.lib.quisk_cuda_last_error().decode())
 
+    def set_alc(self, enable: int = 1):
+        """process_alc behind the filter (microphone.c:1232-1233); every call with 1 is a key down (init_alc(&tx_alc, 0), :1207)."""
+        L.check(self.lib, self.lib.quisk_cuda_tx_filter_set_alc(self.h, int(enable)), "tx_filter_set_alc")
+
     def max_out(self, count: int) -> int:
         return self.lib.quisk_cuda_tx_filter_max_out(self.h, count)
 

@@ -20,6 +20,10 @@ MIC_RATE = 48000
 TX_MODES = {"LSB": 2, "USB": 3, "AM": 4, "FM": 5}
 DGT_TX_MODES = {"DGT-U": 7, "DGT-L": 8}       # FDV-U / FDV-L tune like DGT-U / DGT-L (microphone.c:617)
 PREEMPH, CLIP = 0.6, 2.5
+ALC_SPLITS = [4800, 4806, 6, 12, 960, 954, 2004, 6000]     # blocks of the ALC fixtures
+ALC_CASES = ["USB", "DGT-U"]
+ALC_IN_SCALE = {"USB": 1.0, "DGT-U": 2.5}
+ALC_KEY_DOWN_AT = 6                                         # init_alc(&tx_alc, 0) in front of this block
 TX_SPLITS = [4800, 4806, 1, 5, 9600, 1023, 12000, 600, 6, 7, 48000 - 4800 - 4806 - 1 - 5 - 9600 - 1023 - 12000 - 600 - 6 - 7, 24000]
 
 
@@ -33,6 +37,31 @@ def mic_audio(n=72000, seed=5):
     x += 0.003 * rng.standard_normal(n)
     x[30000:30040] += 1.5                      # a thump
     return np.round(x * 12000.0)
+
+
+def alc_chain(name, x):
+    """tx_filter (USB) or tx_filter_digital (DGT-U, microphone audio x 2.5 so that the control has to pull the gain down from
+    its initial 1.4) followed by process_alc, block by block, on a fresh copy of the compiled reference"""
+    lib = R.load("libquisk_tx_ref.so", private_copy=True)
+    lib.ref_tx_init.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
+    lib.ref_tx_filter.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_tx_filter_digital.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_process_alc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    mode = R.MODES[name]
+    if name == "USB":
+        lib.ref_tx_init(mode, MIC_RATE, PREEMPH, CLIP)
+    else:
+        lib.ref_tx_digital_init(mode)
+    lib.ref_alc_init()
+    outs, pos = [], 0
+    for k, n in enumerate(ALC_SPLITS):
+        if k == ALC_KEY_DOWN_AT:
+            lib.ref_alc_key_down()
+        buf = np.zeros(max(2 * n, 16), dtype=np.complex128); buf[:n] = x[pos:pos + n] * ALC_IN_SCALE[name]; pos += n
+        nr = lib.ref_tx_filter(buf.ctypes.data_as(C.c_void_p), n) if name == "USB" else lib.ref_tx_filter_digital(buf.ctypes.data_as(C.c_void_p), n)
+        lib.ref_process_alc(buf.ctypes.data_as(C.c_void_p), nr, mode)
+        outs.append(buf[:nr].copy())
+    return np.concatenate(outs)
 
 
 def main():
@@ -71,6 +100,11 @@ def main():
             outs.append(buf[:nr].copy())
         out["txd_%s/y" % name] = np.concatenate(outs)
         print(name, "digital out", len(out["txd_%s/y" % name]), "peak", np.abs(out["txd_%s/y" % name]).max())
+    # process_alc (microphone.c:270-370) behind tx_filter / tx_filter_digital, as quisk_process_microphone chains them
+    # (:1232-1233): the look-ahead level control with its 960-sample delay line, a key down in the middle (init_alc(.., 0), :1207)
+    for name in ALC_CASES:
+        out["alc_%s/y" % name] = alc_chain(name, x)
+        print(name, "alc out", len(out["alc_%s/y" % name]), "peak", np.abs(out["alc_%s/y" % name]).max())
     np.savez_compressed(os.path.join(HERE, "tx_kat.npz"), **out)
     print("wrote tx_kat.npz")
 

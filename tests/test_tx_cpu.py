@@ -49,3 +49,10 @@ def test_tx_digital_fixture_is_the_compiled_reference(mode, key):
         assert lib.ref_tx_filter_digital(buf.ctypes.data_as(C.c_void_p), n) == n
         outs.append(buf[:n].copy())
     assert np.array_equal(np.concatenate(outs), kat["txd_%s/y" % key])
+
+
+@pytest.mark.skipif(not R.have_ref("libquisk_tx_ref.so"), reason="compiled reference not built (oracle/build_ref.sh)")
+@pytest.mark.parametrize("name", ["USB", "DGT-U"])
+def test_alc_fixture_is_the_compiled_reference(name):
+    from tests.golden.make_golden_tx import alc_chain
+    assert np.array_equal(alc_chain(name, mic_audio()), golden("tx_kat.npz")["alc_%s/y" % name])

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import quisk_oracle as O
-from tests.golden.make_golden_tx import CLIP, MIC_RATE, PREEMPH, TX_SPLITS, mic_audio
+from tests.golden.make_golden_tx import ALC_IN_SCALE, ALC_KEY_DOWN_AT, ALC_SPLITS, CLIP, MIC_RATE, PREEMPH, TX_SPLITS, mic_audio
 from tests.util import golden
 
 pytestmark = pytest.mark.gpu
@@ -77,6 +77,34 @@ def test_tx_filter_digital_parity(mode, torch, tabs):
     tx.close()
     y = np.concatenate(outs, axis=1)
     assert np.array_equal(y[0], ref) and np.array_equal(y[1], ref)
+
+
+@pytest.mark.parametrize("mode", ["USB", "DGT-U"])
+def test_tx_filter_with_alc(mode, torch, tabs):
+    """tx_filter / tx_filter_digital followed by process_alc (microphone.c:1232-1233, 270-370), with a key down in the middle
+    (init_alc(&tx_alc, 0): delay line and ramp cleared, gain kept), against the same chain of the compiled reference."""
+    from quisk_b200.rx import TxFilter
+    kat = golden("tx_kat.npz")
+    ref = kat["alc_%s/y" % mode]
+    x = mic_audio() * ALC_IN_SCALE[mode]
+    tx = TxFilter(2, mode, tabs, mic_sample_rate=MIC_RATE, preemphasis=PREEMPH, clip=CLIP)
+    tx.set_alc(1)
+    d = torch.from_numpy(np.ascontiguousarray(np.stack([x, x]).astype(np.complex128))).cuda()
+    outs, pos = [], 0
+    for k, n in enumerate(ALC_SPLITS):
+        if k == ALC_KEY_DOWN_AT:
+            tx.set_alc(1)
+        blk = d[:, pos:pos + n].contiguous(); pos += n
+        out = torch.zeros((2, tx.max_out(n) + 8), dtype=torch.complex128, device="cuda")
+        no = tx.process(blk.data_ptr(), blk.stride(0), n, out.data_ptr(), out.stride(0))
+        outs.append(out[:, :no].cpu().numpy())
+    tx.close()
+    y = np.concatenate(outs, axis=1)
+    assert y.shape[1] == len(ref)
+    errs = [O.rel_rms(y[c], ref) for c in range(2)]
+    print("tx + alc", mode, errs, "peak", np.abs(ref).max(), "(CLIP16 - 10 = 32757)")
+    assert np.abs(ref).max() > 32756.0           # the control is working against the limit
+    assert max(errs) < 1e-12
 
 
 def test_tx_filter_rejects_what_tx_filter_does_not_serve(torch, tabs):
