@@ -69,7 +69,7 @@ def test_product_arm_contract_on_gpu():
     assert "fused_decim" in r["kernel"] and 0.1 < r["kernel_share_of_step"] <= 1.0      # (small batches leave the step latency bound)
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] > 0
-    assert set(d["workloads"]) == {"panadapter", "rxa_usb", "rxa_fm", "channelizer", "pipeline"}
+    assert set(d["workloads"]) == {"panadapter", "rxa_usb", "rxa_fm", "channelizer", "pipeline", "tx_filter"}
     for name, w in d["workloads"].items():
         assert w["value"] > 0 and w["gpu_launches"] > 0 and w["e2e"]["value"] > 0, name
         assert w["roofline"]["frac"] > 0 and w["cpu_baseline"]["value"] > 0, name
