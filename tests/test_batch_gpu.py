@@ -260,6 +260,28 @@ def test_fused_kernel_variants(mode, variant, torch, tabs):
             assert O.rel_rms(aud[c], ref) < 1e-12
 
 
+def test_fused_192k_plan_split_equals_complex_lanes(torch, tabs):
+    """The four-stage plan of the 192 kS/s chain (HB45, FIR 98/2, HB45, FIR 98/2: the north star's target rate) runs with
+    component-split half bands by default; the complex-lane form of the same plan must agree bit for bit."""
+    from quisk_b200.rx import RxChain
+    kat = golden("chain_kat.npz")
+    fi, fq = kat["c1/filt_i"], kat["c1/filt_q"]
+    C = 3
+    x = np.stack([O.synth_iq(40960, 30 + c, 1.0) for c in range(C)])
+    splits = [2048, 4096, 2047, 2049, 8192 + 5, 100, 1, 10240]
+    splits.append(40960 - sum(splits))
+    res = []
+    for split in (0, 2):
+        rx = RxChain(C, 192000, "USB", fi, fq, tabs, tune_hz=[4321.0] * C, fused=True)
+        rx.set_option(11, split)
+        res.append(_run_chain(torch, rx, x, splits)[:2])
+        name = rx.lib.quisk_cuda_rx_fused_kernel_name(rx.h).decode()
+        assert ("282" in name) == (split == 2), name
+        rx.close()
+    assert res[0][1] == res[1][1]
+    assert np.array_equal(res[0][0], res[1][0])
+
+
 def test_c1_chain_closed_form_nco(torch, tabs):
     """QC_RX_OPT_EXACT_NCO = 0: block-start phasors from the closed form instead of the reference's recurrence;
     over the 0.1 s fixture both are far inside the tolerance (tests/test_c1_fullsize_gpu.py shows where they part)."""
