@@ -268,8 +268,9 @@ int quisk_cuda_rx_reset(qcRxChain *rx);
 #define QC_RX_OPT_FUSED_ASYNC 19   /* tail-warp kernel: the next chunk travels by cp.async straight into stage 0's shared-memory buffer instead of
                                       waiting in registers: 1 = on, 2 = on under a 128-register cap, 0 = register prefetch */
 #define QC_RX_OPT_FUSED_SPLIT 11   /* half-band stages of the plan kernels with one lane per component, twice the outputs per lane: 0 = off, 1 = on,
-                                      2 (default) = in the tail-warp kernel behind its first half band (measured +3 %) and in the four-stage
-                                      192 kS/s plan kernel (measured +4 %); bit-identical either way */
+                                      2 = in the tail-warp kernel behind its first half band (measured +3 %) and in the four-stage 192 kS/s plan
+                                      kernel (measured +4 %), 3 (default) = the first half band of the tail-warp kernel too (+1 %);
+                                      bit-identical in every form */
 #define QC_RX_OPT_NOISE_BLANKER 13  /* quisk_noise_blanker (0 = off, 1..3): quisk_cuda_rx_process_host / _host_packed run NoiseBlanker
                                       (quisk.c:679-784) on the staged block in front of the tuning stage, as quisk_process_samples
                                       does (quisk.c:2448-2449).  The device entry leaves the caller's buffer alone: run quisk_cuda_nb_run first */

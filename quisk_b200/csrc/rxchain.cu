@@ -687,7 +687,7 @@ int quisk_cuda_rx_set_option(qcRxChain *rx, int option, int value)
     case QC_RX_OPT_FUSED_TAILWARP: if (value < 0 || value > 4) { qc::set_error("rx_set_option: tail-warp split must be 0 (off), 1 (default) or the first tail stage 2..4"); return QC_EINVAL; }
         rx->rx.fused_tailwarp = value; return QC_OK;
     case QC_RX_OPT_FUSED_SPLIT:
-        if (value < 0 || value > 2) { qc::set_error("rx_set_option: split must be 0, 1 or 2"); return QC_EINVAL; }
+        if (value < 0 || value > 3) { qc::set_error("rx_set_option: split must be 0 .. 3"); return QC_EINVAL; }
         rx->rx.fused_split = value; return QC_OK;
     case QC_RX_OPT_FUSED_P3: rx->rx.fused_p3 = value != 0; return QC_OK;
     case QC_RX_OPT_FUSED_ASYNC:

@@ -81,7 +81,7 @@ struct RxChain {
     int fused_tailwarp = 1;             // plan kernels: the low-rate stages run on a fifth warp, one chunk behind (fused_decim_tw_kernel)
     int fused_p3 = 0;                   // three-group pipeline kernel (fused_decim_p3_kernel): half bands 1-2 on two warps of their own
     int fused_async = 0;                // tail-warp kernel: next chunk by cp.async into stage 0's buffer (1; 2 = under a 128-register cap) instead of a register prefetch
-    int fused_split = 2;                // plan kernels: half bands with one lane per component (hb_stage_split): 0 off, 1 on, 2 (default) only behind half band 0 of the tail-warp kernel
+    int fused_split = 3;                // plan kernels: half bands with one lane per component (hb_stage_split): 0 off, 1 on, 2 behind half band 0 of the tail-warp kernel (+ the 192 kS/s plan), 3 (default) every half band of it
     int fused_min_r = 0;                // force at least this many outputs per thread in half-band stages
     int fused_tail = 1;                 // SSB / CW: run filter + demod + audio interpolators as one kernel (rxtail.cu)
     // optional device timing of the dominant (fused) kernel

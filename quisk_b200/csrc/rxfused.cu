@@ -696,7 +696,8 @@ __global__ void __maxnreg__(ASYNC == 2 ? 128 : TW_MAXREG) fused_decim_tw_kernel(
     }
     for (int i = tid; i < P.smem_cd; i += NTA) sm[i] = make_double2(0.0, 0.0);
     __syncthreads();
-    constexpr int STEP_PAD0 = NT + NT / (2 * R0);
+    constexpr int PU0 = PlanFirst<PLAN...>::code / 100 == 2 ? 4 * R0 : 2 * R0;      // stage 0's pad unit (component split: twice as wide)
+    constexpr int STEP_PAD0 = NT + NT / PU0;
     unsigned pb0s = 0;
     if constexpr (ASYNC != 0) {
         const FStage &S0 = P.st[0];
@@ -774,7 +775,7 @@ __global__ void __maxnreg__(ASYNC == 2 ? 128 : TW_MAXREG) fused_decim_tw_kernel(
         if (P.tune) pstep = s_pstep;
         const FStage &S0 = P.st[0];
         cd *pb0 = sm + S0.buf + phys(S0, S0.Ha + js);
-        constexpr int STEP_PAD = NT + NT / (2 * R0);
+        constexpr int STEP_PAD = NT + NT / PU0;
         const bool tune = P.tune != 0;
         // ASYNC: element i of stage 0's history is slid by the thread whose last cp.async of the next chunk lands on its
         // old place (logical Ha + T0 - Ha + i = row NLD-1, column NT - Ha + i), so the read precedes the overwrite in
@@ -1163,7 +1164,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     const int tw_ts = fused_tailwarp >= 2 && fused_tailwarp <= 4 ? fused_tailwarp : 3;
     bool use_tw = fused_tailwarp && fused_plans && NT == 128 && T0 == 2048 && split == ns && ns > 4 && (!d_trace || fused_p3);
     // (split = 2, the default, also takes the four-stage 192 kS/s plan: measured 0.530 -> 0.509 ms per launch at 1024 receivers)
-    bool use_split = !use_tw && (fused_split == 1 || (fused_split == 2 && ns == 4)) && fused_plans && NT == 128 && T0 == 2048 && split == ns;
+    bool use_split = !use_tw && (fused_split == 1 || (fused_split >= 2 && ns == 4)) && fused_plans && NT == 128 && T0 == 2048 && split == ns;
     // tail-warp kernel with component-split half bands behind the first one (stage 0 keeps complex lanes: its commit
     // layout is built around the pad every 16 elements)
     bool tw_split = use_tw && fused_split && tw_ts == 3;
@@ -1189,7 +1190,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
             const int nts = ((use_tw && s >= tw_ts) || (use_p3 && s >= 1)) ? 64 : NT;          // the tail warps (and group B) are 64 threads
             S.R = nout > 4 * nts ? 8 : (nout > 2 * nts ? 4 : 2);
             if (fused_min_r > S.R) S.R = fused_min_r;
-            if (use_split || (tw_split && s > 0)) { S.split = 1; S.R *= 2; }
+            if (use_split || (tw_split && (s > 0 || fused_split == 3))) { S.split = 1; S.R *= 2; }
             S.pu = 2 * S.R;
             S.magic = (unsigned)((0x100000000ULL + S.pu - 1) / S.pu);
             // window start of thread 0 (logical Ha + u0 - 42) must land on a pad boundary
@@ -1280,7 +1281,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
             bool ok = true;
             for (int i = 0; i < ns; i++) {
                 int want = i < 4 ? head[tw_ts - 2][i] : tails[p][i - 4];
-                if (tw_split && i > 0 && want < 100) want += 200;
+                if (tw_split && (i > 0 || fused_split == 3) && want < 100) want += 200;
                 if (use_p3 && i < 4) want = i < 2 ? 82 : (i == 2 ? 42 : 22);
                 ok = ok && codes[i] == want;
             }
@@ -1335,11 +1336,12 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
         fused_decim_tw_kernel<__VA_ARGS__><<<C, 192, sh, strm>>>(P); } while (0)
     // tail-warp kernels (default): the stages behind the fourth half band run on a fifth warp, one chunk behind
     if (use_tw) {
-#define QC_TW_PLANS(AS, TS, H1, H2, H3) \
-        if (ns == 5) QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142); \
-        else if (ns == 7) QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142, H3, 122); \
-        else if (ns == 8) QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142, H3, H3, 112); \
-        else QC_LAUNCH_TW(AS, TS, 82, H1, H2, H3, 142, 142)
+#define QC_TW_PLANS0(AS, TS, H0, H1, H2, H3) \
+        if (ns == 5) QC_LAUNCH_TW(AS, TS, H0, H1, H2, H3, 142); \
+        else if (ns == 7) QC_LAUNCH_TW(AS, TS, H0, H1, H2, H3, 142, H3, 122); \
+        else if (ns == 8) QC_LAUNCH_TW(AS, TS, H0, H1, H2, H3, 142, H3, H3, 112); \
+        else QC_LAUNCH_TW(AS, TS, H0, H1, H2, H3, 142, 142)
+#define QC_TW_PLANS(AS, TS, H1, H2, H3) QC_TW_PLANS0(AS, TS, 82, H1, H2, H3)
         if (use_p3) {
 #define QC_LAUNCH_P3(...) do { \
         static bool optin[64] = {}; \
@@ -1354,10 +1356,12 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
 #undef QC_LAUNCH_P3
         }
         else if (tw_ts == 2) { QC_TW_PLANS(0, 2, 42, 42, 22); } else if (tw_ts == 4) { QC_TW_PLANS(0, 4, 42, 22, 22); }
+        else if (tw_split && fused_split == 3) { QC_TW_PLANS0(0, 3, 282, 242, 222, 222); }
         else if (tw_split) { QC_TW_PLANS(0, 3, 242, 222, 222); }
         else if (fused_async == 1) { QC_TW_PLANS(1, 3, 42, 22, 22); } else if (fused_async == 2) { QC_TW_PLANS(2, 3, 42, 22, 22); }
         else { QC_TW_PLANS(0, 3, 42, 22, 22); }
 #undef QC_TW_PLANS
+#undef QC_TW_PLANS0
     }
     // single-rate plans (every stage every chunk)
     else if (is_plan(5, {82, 42, 22, 22, 142})) QC_LAUNCH(128, 8, 2, 5, 82, 42, 22, 22, 142);                        // 1.536 MS/s -> 48 k

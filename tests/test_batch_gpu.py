@@ -219,7 +219,7 @@ def test_c1_chain_ragged_blocks_tuned(fused, torch, tabs):
 
 
 FUSED_VARIANTS = [("tailwarp", 12, 0), ("tailwarp", 12, 2), ("tailwarp", 12, 3), ("tailwarp", 12, 4), ("split", 11, 1),
-                  ("async", 19, 0), ("async", 19, 1), ("async", 19, 2), ("async_twsplit", 11, 1), ("async_p3", 20, 1)]     # async: on the default tail-warp kernel
+                  ("async", 19, 0), ("async", 19, 1), ("async", 19, 2), ("async_twsplit", 11, 1), ("async_twsplit0", 11, 3), ("async_p3", 20, 1)]     # async: on the default tail-warp kernel
 
 
 @pytest.mark.parametrize("variant", FUSED_VARIANTS, ids=["%s%d" % (v[0], v[2]) for v in FUSED_VARIANTS])
@@ -271,12 +271,12 @@ def test_fused_192k_plan_split_equals_complex_lanes(torch, tabs):
     splits = [2048, 4096, 2047, 2049, 8192 + 5, 100, 1, 10240]
     splits.append(40960 - sum(splits))
     res = []
-    for split in (0, 2):
+    for split in (0, 3):
         rx = RxChain(C, 192000, "USB", fi, fq, tabs, tune_hz=[4321.0] * C, fused=True)
         rx.set_option(11, split)
         res.append(_run_chain(torch, rx, x, splits)[:2])
         name = rx.lib.quisk_cuda_rx_fused_kernel_name(rx.h).decode()
-        assert ("282" in name) == (split == 2), name
+        assert ("282" in name) == (split == 3), name
         rx.close()
     assert res[0][1] == res[1][1]
     assert np.array_equal(res[0][0], res[1][0])
