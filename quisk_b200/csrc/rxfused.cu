@@ -1167,7 +1167,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
     bool use_split = !use_tw && (fused_split == 1 || (fused_split >= 2 && ns == 4)) && fused_plans && NT == 128 && T0 == 2048 && split == ns;
     // tail-warp kernel with component-split half bands behind the first one (stage 0 keeps complex lanes: its commit
     // layout is built around the pad every 16 elements)
-    bool tw_split = use_tw && fused_split && tw_ts == 3;
+    bool tw_split = use_tw && fused_split && (tw_ts == 3 || (tw_ts == 4 && fused_split == 3));
     // three-group pipeline (fused_decim_p3_kernel): half bands 1 and 2 on a group of their own
     bool use_p3 = use_tw && fused_p3 && tw_ts == 3;
     if (use_p3) tw_split = false;
@@ -1355,6 +1355,7 @@ int RxChain::run_fused_decimator(size_t n_stages, const cd *in, long in_stride, 
             else QC_LAUNCH_P3(82, 82, 42, 22, 142, 142);
 #undef QC_LAUNCH_P3
         }
+        else if (tw_split && fused_split == 3 && tw_ts == 4) { QC_TW_PLANS0(0, 4, 282, 242, 222, 222); }
         else if (tw_ts == 2) { QC_TW_PLANS(0, 2, 42, 42, 22); } else if (tw_ts == 4) { QC_TW_PLANS(0, 4, 42, 22, 22); }
         else if (tw_split && fused_split == 3) { QC_TW_PLANS0(0, 3, 282, 242, 222, 222); }
         else if (tw_split) { QC_TW_PLANS(0, 3, 242, 222, 222); }

@@ -219,7 +219,7 @@ def test_c1_chain_ragged_blocks_tuned(fused, torch, tabs):
 
 
 FUSED_VARIANTS = [("tailwarp", 12, 0), ("tailwarp", 12, 2), ("tailwarp", 12, 3), ("tailwarp", 12, 4), ("split", 11, 1),
-                  ("async", 19, 0), ("async", 19, 1), ("async", 19, 2), ("async_twsplit", 11, 1), ("async_twsplit0", 11, 3), ("async_p3", 20, 1)]     # async: on the default tail-warp kernel
+                  ("async", 19, 0), ("async", 19, 1), ("async", 19, 2), ("async_twsplit", 11, 1), ("async_twsplit0", 11, 3), ("async_p3", 20, 1), ("tw4split", 12, 4)]     # async: on the default tail-warp kernel
 
 
 @pytest.mark.parametrize("variant", FUSED_VARIANTS, ids=["%s%d" % (v[0], v[2]) for v in FUSED_VARIANTS])
@@ -249,6 +249,8 @@ def test_fused_kernel_variants(mode, variant, torch, tabs):
     rx.reset()
     if variant[0].startswith("async"):
         rx.set_option(12, 1)
+    if variant[0] == "tw4split":
+        rx.set_option(11, 3)
     rx.set_option(variant[1], variant[2])
     aud, ca, _, _ = _run_chain(torch, rx, x, splits)
     rx.close()
