@@ -79,24 +79,39 @@ __device__ __forceinline__ double tx_inmax(double inMax, double magn, const TxLe
     return inMax * (1 - P.time_long) + P.time_long * P.agc_level;
 }
 
-// SSB: csample = 2 z; normalise by the running peak, clip gain, limit to the unit circle, keep the real part (microphone.c:470-496)
-__global__ void tx_level_ssb_kernel(const cd *__restrict__ in, long is, double *__restrict__ out, long os, int n, double *__restrict__ inmax, int C, TxLevelPar P)
+// SSB: csample = 2 z; normalise by the running peak, clip gain, limit to the unit circle, keep the real part (microphone.c:470-496).
+// A lane per transmitter, 32 transmitters per warp: the recurrence is scalar per transmitter, so the lanes are the batch.  The
+// block travels through a [32 transmitters][32 samples] shared-memory tile (rows padded by one element), loaded and stored
+// row by row so that HBM sees 512-byte / 256-byte runs instead of 32 strided words per instruction.
+__global__ void __launch_bounds__(32) tx_level_ssb_kernel(const cd *__restrict__ in, long is, double *__restrict__ out, long os, int n, double *__restrict__ inmax, int C, TxLevelPar P)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double im = inmax[c];
-    const cd *x = in + (size_t)c * is;
-    double *y = out + (size_t)c * os;
-    for (int i = 0; i < n; i++) {
-        cd z = make_double2(x[i].x * 2.0, x[i].y * 2.0);
-        double magn = hypot(z.x, z.y);
-        im = tx_inmax(im, magn, P);
-        z.x /= im; z.y /= im; magn /= im;
-        z.x *= P.clip; z.y *= P.clip; magn *= P.clip;
-        if (magn > 1.0) { z.x /= magn; z.y /= magn; }
-        y[i] = z.x;
+    __shared__ cd tin[32][33];
+    __shared__ double tout[32][33];
+    const int lane = threadIdx.x;
+    const int c0 = blockIdx.x * 32, c = c0 + lane;
+    const int rows = C - c0 < 32 ? C - c0 : 32;
+    double im = c < C ? inmax[c] : 1.0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int m = n - i0 < 32 ? n - i0 : 32;
+        for (int r = 0; r < rows; r++) if (lane < m) tin[r][lane] = in[(size_t)(c0 + r) * is + i0 + lane];
+        __syncwarp();
+        if (c < C) {
+            for (int k = 0; k < m; k++) {
+                const cd x = tin[lane][k];
+                cd z = make_double2(x.x * 2.0, x.y * 2.0);
+                double magn = hypot(z.x, z.y);
+                im = tx_inmax(im, magn, P);
+                z.x /= im; z.y /= im; magn /= im;
+                z.x *= P.clip; z.y *= P.clip; magn *= P.clip;
+                if (magn > 1.0) { z.x /= magn; z.y /= magn; }
+                tout[lane][k] = z.x;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; r++) if (lane < m) out[(size_t)(c0 + r) * os + i0 + lane] = tout[r][lane];
+        __syncwarp();
     }
-    inmax[c] = im;
+    if (c < C) inmax[c] = im;
 }
 
 // AM / FM: the same normaliser on the real rail, then the quadratic soft knee (microphone.c:499-527)
@@ -446,7 +461,7 @@ struct TxFilter {
         if (ssb) {
             tx_promote_kernel<<<g, 256, 0, s>>>(d_r[cur], cap, d_c[0], cap, n); count_launch(); QC_CUDA_LAUNCH();
             rc = fTune1->run(d_c[0], cap, n, d_c[1], cap, &no, 0, s); if (rc != QC_OK) return rc;
-            tx_level_ssb_kernel<<<gc, 64, 0, s>>>(d_c[1], cap, d_r[cur], cap, n, d_inmax, C, P); count_launch(); QC_CUDA_LAUNCH();
+            tx_level_ssb_kernel<<<(C + 31) / 32, 32, 0, s>>>(d_c[1], cap, d_r[cur], cap, n, d_inmax, C, P); count_launch(); QC_CUDA_LAUNCH();
         } else {
             tx_level_real_kernel<<<gc, 64, 0, s>>>(d_r[cur], cap, n, d_inmax, C, P); count_launch(); QC_CUDA_LAUNCH();
         }
